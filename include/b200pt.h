@@ -1,0 +1,347 @@
+/*
+ * b200pt.h — C-ABI of the B200-native wavefront path tracer (libb200pt.so).
+ *
+ * This is the drop-in boundary for ONE path of nvpro-samples/vk_gltf_renderer: the path tracer
+ * backend (reference: src/renderer_pathtracer.{cpp,hpp} + shaders/gltf_pathtrace.slang).  The
+ * reference has no FFI: the path sits behind the C++ virtual class `BaseRenderer`
+ * (reference src/renderer_base.hpp:33-55).  Every entry point below states which reference
+ * interface it stands in for; INTEGRATION.md shows the `B200PathTracer : BaseRenderer` shim a
+ * maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - plain C, plain pointers + sizes, no C++/torch types; all structs are POD with the byte
+ *     layouts of the reference's host<->device structs (shaders/shaderio.h, gltf_scene_io.h.slang).
+ *   - return 0 on success, negative B200PT_E_* on failure (the reference aborts through
+ *     NVVK_CHECK; a C ABI cannot, so the code + b200pt_last_error() carry the same information).
+ *   - one handle per GPU / per rank; a handle is single-threaded (reference: all BaseRenderer
+ *     virtuals run on the render thread, renderer_base.hpp:39-51).
+ *   - matrices are glm column-major float[16], exactly as the reference uploads them.
+ *   - host pointers are only read during the call (data is copied to HBM); caller keeps ownership.
+ */
+#ifndef B200PT_H
+#define B200PT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200PT_ABI_VERSION 1
+
+/* error codes */
+#define B200PT_OK 0
+#define B200PT_E_INVALID -1     /* bad argument / call order                         */
+#define B200PT_E_CUDA -2        /* CUDA runtime error (see b200pt_last_error)        */
+#define B200PT_E_NOMEM -3       /* host or device allocation failed                  */
+#define B200PT_E_UNSUPPORTED -4 /* feature outside the built path (e.g. physical sky) */
+
+typedef struct b200pt b200pt_t; /* opaque renderer handle */
+
+/* ---- scene data contract ---------------------------------------------------------------- */
+
+/* reference: shaders/gltf_scene_io.h.slang:41-47 (GltfRenderNode, 136 B) */
+typedef struct b200pt_render_node
+{
+  float   objectToWorld[16];
+  float   worldToObject[16];
+  int32_t materialID;
+  int32_t renderPrimID;
+} b200pt_render_node;
+
+/* reference: shaders/gltf_scene_io.h.slang:50-64 (GltfRenderPrimitive + VertexBuffers: the
+ * reference stores 7 device addresses; here they are host pointers + the two counts the host
+ * side knows from RenderPrimitive::indexCount/vertexCount, src/gltf_scene.cpp:2153-2154).
+ * Optional attribute arrays are NULL when the glTF primitive lacks them
+ * (src/gltf_scene_vk.cpp:760-851). */
+typedef struct b200pt_render_primitive
+{
+  const uint32_t* indices;      /* 3 per triangle, always widened to u32 */
+  const float*    positions;    /* float3 per vertex                     */
+  const float*    normals;      /* float3 or NULL                        */
+  const uint32_t* colors;       /* packed unorm4x8 or NULL               */
+  const float*    tangents;     /* float4 or NULL                        */
+  const float*    texCoords[2]; /* float2 or NULL                        */
+  uint32_t        triangleCount;
+  uint32_t        vertexCount;
+} b200pt_render_primitive;
+
+/* reference: shaders/gltf_scene_io.h.slang:121-128 (GltfTextureInfo, 32 B) */
+typedef struct b200pt_texture_info
+{
+  float   uvTransform[6]; /* glm::mat3x2 column-major: c0.xy c1.xy c2.xy */
+  int32_t index;          /* glTF texture index, -1 = none               */
+  int32_t texCoord;       /* 0 or 1                                      */
+} b200pt_texture_info;
+
+/* reference: shaders/gltf_scene_io.h.slang:147-310 (GltfShadeMaterial with every MAT_EXT_*=1,
+ * 288 B; anchors 0/32/40/48/52 are static_asserted in src/gltf_material_cache.cpp:46-56). */
+typedef struct b200pt_shade_material
+{
+  float    pbrBaseColorFactor[4];
+  float    emissiveFactor[3];
+  float    normalTextureScale;
+  float    pbrRoughnessFactor;
+  float    pbrMetallicFactor;
+  int32_t  alphaMode; /* 0 opaque, 1 mask, 2 blend */
+  float    alphaCutoff;
+  float    occlusionStrength;
+  int32_t  doubleSided;
+  float    attenuationColor[3];
+  float    ior;
+  float    transmissionFactor;
+  float    thicknessFactor;
+  float    attenuationDistance;
+  float    clearcoatFactor;
+  float    specularColorFactor[3];
+  float    clearcoatRoughness;
+  float    specularFactor;
+  int32_t  unlit;
+  float    iridescenceFactor;
+  float    iridescenceThicknessMinimum;
+  float    iridescenceThicknessMaximum;
+  float    iridescenceIor;
+  float    anisotropyRotation[2]; /* (sin, cos) */
+  float    sheenColorFactor[3];
+  float    anisotropyStrength;
+  float    sheenRoughnessFactor;
+  float    dispersion;
+  int32_t  pbrModel; /* 0 metallic-roughness, 1 specular-glossiness */
+  float    pbrDiffuseFactor[4];
+  float    pbrSpecularFactor[3];
+  float    pbrGlossinessFactor;
+  float    diffuseTransmissionColor[3];
+  float    diffuseTransmissionFactor;
+  float    retroreflectionFactor;
+  float    multiscatterColorFactor[3];
+  float    scatterAnisotropy;
+  /* uint16 indices into the texture-info array, 0 = "no texture" */
+  uint16_t pbrBaseColorTexture;
+  uint16_t normalTexture;
+  uint16_t pbrMetallicRoughnessTexture;
+  uint16_t emissiveTexture;
+  uint16_t occlusionTexture;
+  uint16_t transmissionTexture;
+  uint16_t thicknessTexture;
+  uint16_t clearcoatTexture;
+  uint16_t clearcoatRoughnessTexture;
+  uint16_t clearcoatNormalTexture;
+  uint16_t specularTexture;
+  uint16_t specularColorTexture;
+  uint16_t iridescenceTexture;
+  uint16_t iridescenceThicknessTexture;
+  uint16_t anisotropyTexture;
+  uint16_t sheenColorTexture;
+  uint16_t sheenRoughnessTexture;
+  uint16_t pbrDiffuseTexture;
+  uint16_t pbrSpecularGlossinessTexture;
+  uint16_t diffuseTransmissionTexture;
+  uint16_t diffuseTransmissionColorTexture;
+  uint16_t retroreflectionTexture;
+  uint16_t _pad16[2];
+  uint64_t _pad;
+} b200pt_shade_material;
+
+/* reference: shaders/gltf_scene_io.h.slang:85-100 (GltfLight, 64 B) */
+typedef struct b200pt_light
+{
+  float   direction[3];
+  int32_t type; /* 0 none, 1 directional, 2 spot, 3 point */
+  float   position[3];
+  float   radius;
+  float   color[3];
+  float   intensity;
+  float   angularSizeOrInvRange;
+  float   innerAngle;
+  float   outerAngle;
+  int32_t _pad;
+} b200pt_light;
+
+/* One decoded glTF texture (image + sampler), reference: SceneVk::createTextureImages /
+ * getSampler, src/gltf_scene_vk.cpp:909-1098.  Pixels are RGBA8 (4 B/texel), row 0 first.
+ * Mip chain is generated on load (reference: GPU blit chain, gltf_scene_vk.cpp:1254-1332). */
+typedef struct b200pt_texture
+{
+  const uint8_t* rgba8;
+  int32_t        width;
+  int32_t        height;
+  int32_t        srgb;      /* 1: decode sRGB->linear on fetch (findSrgbImages, :1102-1154) */
+  int32_t        wrapS;     /* glTF enum: 10497 repeat, 33071 clamp, 33648 mirrored         */
+  int32_t        wrapT;
+  int32_t        magFilter; /* glTF enum 9728 nearest / 9729 linear, -1 default(linear)     */
+  int32_t        minFilter; /* glTF enum 9728..9987, -1 default(linear-mip-linear)          */
+} b200pt_texture;
+
+/* Everything SceneVk + SceneRtx hand the reference path tracer (Resources::sceneVk.sceneDesc(),
+ * sceneRtx.topLevelAS(); reference src/renderer_pathtracer.cpp:667-712,1559). */
+typedef struct b200pt_scene_desc
+{
+  const b200pt_render_node*      renderNodes;
+  uint32_t                       numRenderNodes;
+  const uint8_t*                 renderNodeVisible; /* NULL = all visible (SceneRtx skips invisible, gltf_scene_rtx.cpp:317-334) */
+  const b200pt_render_primitive* renderPrimitives;
+  uint32_t                       numRenderPrimitives;
+  const b200pt_shade_material*   materials;
+  uint32_t                       numMaterials;
+  const b200pt_texture_info*     textureInfos; /* element 0 is the reserved "none" slot */
+  uint32_t                       numTextureInfos;
+  const b200pt_texture*          textures;
+  uint32_t                       numTextures;
+  const b200pt_light*            lights;
+  uint32_t                       numLights;
+} b200pt_scene_desc;
+
+/* reference: shaders/shaderio.h:148-168 (SceneFrameInfo, 396 B) */
+typedef struct b200pt_frame_info
+{
+  float   viewMatrix[16];
+  float   projInv[16];
+  float   viewInv[16];
+  float   viewProjMatrix[16];
+  float   prevMVP[16];
+  float   jitter[2];
+  float   imageSize[2];
+  int32_t flags; /* B200PT_SCENE_* */
+  float   envRotation;
+  float   envBlur;
+  float   envIntensity;
+  float   backgroundColor[3];
+  int32_t visualization;
+  float   infinitePlaneDistance;
+  float   infinitePlaneBaseColor[3];
+  float   infinitePlaneMetallic;
+  float   infinitePlaneRoughness;
+  float   shadowCatcherDarkenAmount;
+} b200pt_frame_info;
+
+/* SceneFrameInfoFlags, reference shaders/shaderio.h:138-145 */
+#define B200PT_SCENE_IS_ORTHOGRAPHIC (1 << 0)
+#define B200PT_SCENE_USE_SOLID_BACKGROUND (1 << 1)
+#define B200PT_SCENE_USE_HDR_ENVIRONMENT (1 << 2)
+#define B200PT_SCENE_USE_INFINITE_PLANE (1 << 3)
+#define B200PT_SCENE_INFINITE_PLANE_SHADOW_CATCHER (1 << 4)
+
+/* PathtracerFlags, reference shaders/shaderio.h:170-175 */
+#define B200PT_PT_USE_DLSS (1 << 0)
+#define B200PT_PT_USE_OPTIX_DENOISER (1 << 1)
+#define B200PT_PT_FIRST_FRAME (1 << 2)
+
+/* reference: shaders/shaderio.h:179-196 (PathtracePushConstant) minus its four device
+ * pointers, which the handle owns. 48 B. */
+typedef struct b200pt_push_constant
+{
+  int32_t maxDepth;
+  int32_t frameCount;
+  float   fireflyClampThreshold;
+  float   texGradScale;
+  int32_t numSamples;
+  int32_t totalSamples;
+  float   focalDistance;
+  float   aperture;
+  int32_t flags;
+  float   pixelAngle;
+  float   mouseCoord[2];
+} b200pt_push_constant;
+
+/* Counters the reference lacks (it reports MSps only, src/benchmarking.cpp:269-279); needed for
+ * Mray/s and for the algorithmic-bytes roofline. All are totals since the last
+ * b200pt_reset_stats(). */
+typedef struct b200pt_stats
+{
+  uint64_t closestRays;   /* Trace() calls (primary + bounce + volume continues)  */
+  uint64_t shadowRays;    /* TraceShadow() calls                                   */
+  uint64_t shadedHits;    /* surface interactions shaded                           */
+  uint64_t pathsStarted;  /* samplePixel() calls                                   */
+  uint64_t nodesVisited;  /* BVH nodes fetched (only when built with B200PT_COUNT_TRAVERSAL) */
+  uint64_t trisTested;    /* triangles tested  (same)                              */
+  double   msTraceClosest; /* CUDA-event time inside closest-hit traversal kernels */
+  double   msTraceShadow;
+  double   msShade;
+  double   msOther;       /* raygen + accumulate + queue housekeeping              */
+  double   msTotal;
+  uint64_t kernelLaunches;
+} b200pt_stats;
+
+/* ---- lifecycle --------------------------------------------------------------------------- */
+
+/* PathTracer::onAttach (reference src/renderer_pathtracer.cpp:80-112): create the device
+ * context on `cuda_device`, streams, counters.  No shader compile step exists here: the
+ * kernels are AOT-compiled for sm_100a. */
+int b200pt_create(b200pt_t** out, int cuda_device);
+
+/* PathTracer::onDetach (reference :163-184). */
+void b200pt_destroy(b200pt_t* h);
+
+int         b200pt_abi_version(void);
+const char* b200pt_last_error(const b200pt_t* h);
+
+/* Resources::sceneVk / sceneRtx hand-off; stands in for SceneVk::create (gltf_scene_vk.cpp:218-252)
+ * + SceneRtx BLAS/TLAS build (gltf_scene_rtx.cpp:140-388) + PathTracer::onSceneInvalidated
+ * (renderer_pathtracer.hpp:72).  Copies all arrays to HBM, builds the software wide BVH over the
+ * world-space triangles of every visible render node, creates bindless texture objects. */
+int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* scene);
+
+/* nvvk::HdrIbl::loadEnvironment (external; reference call site src/renderer.cpp:1994-1996):
+ * takes the decoded lat-long image (RGB float, row 0 = +Y pole), builds the alias table
+ * (EnvAccel) and stores the per-texel pdf in alpha.  Returns the integral the reference exposes
+ * as HdrIbl::getIntegral() through *integral_out (may be NULL). */
+int b200pt_set_environment(b200pt_t* h, const float* rgb, int width, int height, float* integral_out);
+
+/* BaseRenderer::onResize (reference src/renderer_base.hpp:43): (re)allocates the RGBA32F
+ * accumulation image (Resources::eImgRendered) and the path-state pool.
+ * tile_y0/tile_rows select the rows this handle renders (multi-GPU framebuffer tiling; the
+ * reference is single-GPU: pass 0,height).  Seeds always use global pixel coordinates. */
+int b200pt_resize(b200pt_t* h, int width, int height, int tile_y0, int tile_rows);
+
+/* BaseRenderer::onRender (reference src/renderer_pathtracer.cpp:500-614): one frame =
+ * pc->numSamples paths per pixel accumulated into the RGBA32F image exactly like
+ * processPixel (shaders/gltf_pathtrace.slang:546-630).  Asynchronous on the handle's stream. */
+int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_push_constant* pc);
+
+/* Blocks until all submitted frames are done (vkQueueWaitIdle analogue). */
+int b200pt_synchronize(b200pt_t* h);
+
+/* gBuffers[eImgRendered] access: device pointer to the tile's RGBA32F rows (tile_rows x width),
+ * or a copy of it into host memory. */
+int b200pt_get_accum_device(b200pt_t* h, float** dev_rgba32f, size_t* num_floats);
+int b200pt_read_accum(b200pt_t* h, float* host_rgba32f, size_t num_floats);
+
+/* Let the caller own the accumulation storage (e.g. a torch tensor that NCCL all-gathers):
+ * dev_rgba32f must hold tile_rows*width*4 floats on the handle's device. NULL restores the
+ * internal buffer. */
+int b200pt_set_accum_device(b200pt_t* h, float* dev_rgba32f, size_t num_floats);
+
+/* The CUDA stream the handle launches on (cudaStream_t as void*), for event timing by callers. */
+void* b200pt_stream(b200pt_t* h);
+
+int b200pt_get_stats(b200pt_t* h, b200pt_stats* out);
+int b200pt_reset_stats(b200pt_t* h);
+/* enable per-stage CUDA-event timing (adds a sync per frame when on) */
+int b200pt_set_profiling(b200pt_t* h, int enabled);
+
+/* ---- ray-level entry points (parity tests + traversal micro-benchmarks) ------------------- */
+
+/* Closest-hit traversal of n rays given as 8 floats each (ox,oy,oz,tmin,dx,dy,dz,tmax), all in
+ * device memory; writes 6 x 32-bit per ray: t(float), rnodeID, rprimID, primitiveID (int32,
+ * -1 on miss), u, v (float) — the reference HitPayload minus the seed
+ * (shaders/raytracer_interface.h.slang:36-47).  Semantics of RayQueryRaytracer::Trace
+ * (:69-122) incl. back-face culling flags; `seeds` (u32 per ray, device, may be NULL) feeds the
+ * stochastic alpha test and is advanced in place. */
+int b200pt_trace_closest(b200pt_t* h, const float* dev_rays, uint32_t n, float* dev_hits, uint32_t* dev_seeds);
+
+/* TraceShadow semantics (:139-187): writes rgb transmission (3 floats per ray). */
+int b200pt_trace_shadow(b200pt_t* h, const float* dev_rays, uint32_t n, float* dev_transmission, uint32_t* dev_seeds);
+
+/* Size in bytes of the traversal structure (nodes, triangles) for the roofline model. */
+int b200pt_bvh_info(b200pt_t* h, uint64_t* node_bytes, uint64_t* tri_bytes, uint32_t* num_nodes, uint32_t* num_tris);
+
+/* BSDF unit-test hooks: evaluate/sample n materials on the device.
+ * in: per item 48 floats (see vk_gltf_renderer_b200/bsdf_io.py for the packing); device ptrs. */
+int b200pt_bsdf_eval(b200pt_t* h, const float* dev_in, uint32_t n, float* dev_out);
+int b200pt_bsdf_sample(b200pt_t* h, const float* dev_in, uint32_t n, float* dev_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PT_H */

@@ -1,0 +1,149 @@
+"""ctypes mirror of include/b200pt.h (the C-ABI structs).
+
+The same POD structs are consumed by the CUDA library (libb200pt.so) and — in tests only — by the
+CPU oracle (oracle/liboracle_pt.so), so both sides see byte-identical inputs.
+
+Layouts follow the reference's host<->device structs:
+  GltfRenderNode / GltfTextureInfo / GltfShadeMaterial / GltfLight  shaders/gltf_scene_io.h.slang:41-310
+  SceneFrameInfo / PathtracePushConstant                           shaders/shaderio.h:148-196
+"""
+import ctypes as C
+
+import numpy as np
+
+c_float_p = C.POINTER(C.c_float)
+c_u32_p = C.POINTER(C.c_uint32)
+c_u8_p = C.POINTER(C.c_uint8)
+
+
+class RenderNode(C.Structure):
+    _fields_ = [("objectToWorld", C.c_float * 16), ("worldToObject", C.c_float * 16),
+                ("materialID", C.c_int32), ("renderPrimID", C.c_int32)]
+
+
+class RenderPrimitive(C.Structure):
+    _fields_ = [("indices", c_u32_p), ("positions", c_float_p), ("normals", c_float_p),
+                ("colors", c_u32_p), ("tangents", c_float_p), ("texCoords", c_float_p * 2),
+                ("triangleCount", C.c_uint32), ("vertexCount", C.c_uint32)]
+
+
+class TextureInfo(C.Structure):
+    _fields_ = [("uvTransform", C.c_float * 6), ("index", C.c_int32), ("texCoord", C.c_int32)]
+
+
+_MAT_FLOAT_FIELDS = [
+    ("pbrBaseColorFactor", C.c_float * 4), ("emissiveFactor", C.c_float * 3), ("normalTextureScale", C.c_float),
+    ("pbrRoughnessFactor", C.c_float), ("pbrMetallicFactor", C.c_float), ("alphaMode", C.c_int32),
+    ("alphaCutoff", C.c_float), ("occlusionStrength", C.c_float), ("doubleSided", C.c_int32),
+    ("attenuationColor", C.c_float * 3), ("ior", C.c_float), ("transmissionFactor", C.c_float),
+    ("thicknessFactor", C.c_float), ("attenuationDistance", C.c_float), ("clearcoatFactor", C.c_float),
+    ("specularColorFactor", C.c_float * 3), ("clearcoatRoughness", C.c_float), ("specularFactor", C.c_float),
+    ("unlit", C.c_int32), ("iridescenceFactor", C.c_float), ("iridescenceThicknessMinimum", C.c_float),
+    ("iridescenceThicknessMaximum", C.c_float), ("iridescenceIor", C.c_float),
+    ("anisotropyRotation", C.c_float * 2), ("sheenColorFactor", C.c_float * 3), ("anisotropyStrength", C.c_float),
+    ("sheenRoughnessFactor", C.c_float), ("dispersion", C.c_float), ("pbrModel", C.c_int32),
+    ("pbrDiffuseFactor", C.c_float * 4), ("pbrSpecularFactor", C.c_float * 3), ("pbrGlossinessFactor", C.c_float),
+    ("diffuseTransmissionColor", C.c_float * 3), ("diffuseTransmissionFactor", C.c_float),
+    ("retroreflectionFactor", C.c_float), ("multiscatterColorFactor", C.c_float * 3), ("scatterAnisotropy", C.c_float),
+]
+MATERIAL_TEXTURE_SLOTS = [
+    "pbrBaseColorTexture", "normalTexture", "pbrMetallicRoughnessTexture", "emissiveTexture", "occlusionTexture",
+    "transmissionTexture", "thicknessTexture", "clearcoatTexture", "clearcoatRoughnessTexture",
+    "clearcoatNormalTexture", "specularTexture", "specularColorTexture", "iridescenceTexture",
+    "iridescenceThicknessTexture", "anisotropyTexture", "sheenColorTexture", "sheenRoughnessTexture",
+    "pbrDiffuseTexture", "pbrSpecularGlossinessTexture", "diffuseTransmissionTexture",
+    "diffuseTransmissionColorTexture", "retroreflectionTexture",
+]
+
+
+class ShadeMaterial(C.Structure):
+    _fields_ = (_MAT_FLOAT_FIELDS + [(n, C.c_uint16) for n in MATERIAL_TEXTURE_SLOTS]
+                + [("_pad16", C.c_uint16 * 2), ("_pad", C.c_uint64)])
+
+
+class Light(C.Structure):
+    _fields_ = [("direction", C.c_float * 3), ("type", C.c_int32), ("position", C.c_float * 3),
+                ("radius", C.c_float), ("color", C.c_float * 3), ("intensity", C.c_float),
+                ("angularSizeOrInvRange", C.c_float), ("innerAngle", C.c_float), ("outerAngle", C.c_float),
+                ("_pad", C.c_int32)]
+
+
+class Texture(C.Structure):
+    _fields_ = [("rgba8", c_u8_p), ("width", C.c_int32), ("height", C.c_int32), ("srgb", C.c_int32),
+                ("wrapS", C.c_int32), ("wrapT", C.c_int32), ("magFilter", C.c_int32), ("minFilter", C.c_int32)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("renderNodes", C.POINTER(RenderNode)), ("numRenderNodes", C.c_uint32),
+                ("renderNodeVisible", c_u8_p),
+                ("renderPrimitives", C.POINTER(RenderPrimitive)), ("numRenderPrimitives", C.c_uint32),
+                ("materials", C.POINTER(ShadeMaterial)), ("numMaterials", C.c_uint32),
+                ("textureInfos", C.POINTER(TextureInfo)), ("numTextureInfos", C.c_uint32),
+                ("textures", C.POINTER(Texture)), ("numTextures", C.c_uint32),
+                ("lights", C.POINTER(Light)), ("numLights", C.c_uint32)]
+
+
+class FrameInfo(C.Structure):
+    _fields_ = [("viewMatrix", C.c_float * 16), ("projInv", C.c_float * 16), ("viewInv", C.c_float * 16),
+                ("viewProjMatrix", C.c_float * 16), ("prevMVP", C.c_float * 16), ("jitter", C.c_float * 2),
+                ("imageSize", C.c_float * 2), ("flags", C.c_int32), ("envRotation", C.c_float),
+                ("envBlur", C.c_float), ("envIntensity", C.c_float), ("backgroundColor", C.c_float * 3),
+                ("visualization", C.c_int32), ("infinitePlaneDistance", C.c_float),
+                ("infinitePlaneBaseColor", C.c_float * 3), ("infinitePlaneMetallic", C.c_float),
+                ("infinitePlaneRoughness", C.c_float), ("shadowCatcherDarkenAmount", C.c_float)]
+
+
+class PushConstant(C.Structure):
+    _fields_ = [("maxDepth", C.c_int32), ("frameCount", C.c_int32), ("fireflyClampThreshold", C.c_float),
+                ("texGradScale", C.c_float), ("numSamples", C.c_int32), ("totalSamples", C.c_int32),
+                ("focalDistance", C.c_float), ("aperture", C.c_float), ("flags", C.c_int32),
+                ("pixelAngle", C.c_float), ("mouseCoord", C.c_float * 2)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("closestRays", C.c_uint64), ("shadowRays", C.c_uint64), ("shadedHits", C.c_uint64),
+                ("pathsStarted", C.c_uint64), ("nodesVisited", C.c_uint64), ("trisTested", C.c_uint64),
+                ("msTraceClosest", C.c_double), ("msTraceShadow", C.c_double), ("msShade", C.c_double),
+                ("msOther", C.c_double), ("msTotal", C.c_double), ("kernelLaunches", C.c_uint64)]
+
+
+# sizes fixed by the reference's layouts
+assert C.sizeof(RenderNode) == 136
+assert C.sizeof(TextureInfo) == 32
+assert C.sizeof(ShadeMaterial) == 288, C.sizeof(ShadeMaterial)
+assert C.sizeof(Light) == 64
+assert C.sizeof(FrameInfo) == 396
+assert C.sizeof(PushConstant) == 48
+assert ShadeMaterial.pbrRoughnessFactor.offset == 32 and ShadeMaterial.alphaMode.offset == 40
+assert ShadeMaterial.occlusionStrength.offset == 48 and ShadeMaterial.doubleSided.offset == 52
+
+SCENE_IS_ORTHOGRAPHIC = 1 << 0
+SCENE_USE_SOLID_BACKGROUND = 1 << 1
+SCENE_USE_HDR_ENVIRONMENT = 1 << 2
+SCENE_USE_INFINITE_PLANE = 1 << 3
+SCENE_INFINITE_PLANE_SHADOW_CATCHER = 1 << 4
+PT_USE_DLSS = 1 << 0
+PT_USE_OPTIX_DENOISER = 1 << 1
+PT_FIRST_FRAME = 1 << 2
+
+
+def fptr(a):
+    """numpy float32 array -> float* (None -> NULL)."""
+    if a is None:
+        return c_float_p()
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(c_float_p)
+
+
+def u32ptr(a):
+    if a is None:
+        return c_u32_p()
+    assert a.dtype == np.uint32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(c_u32_p)
+
+
+def u8ptr(a):
+    if a is None:
+        return c_u8_p()
+    assert a.dtype == np.uint8 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(c_u8_p)

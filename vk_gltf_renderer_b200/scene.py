@@ -1,0 +1,590 @@
+"""Minimal glTF 2.0 -> path-tracer scene arrays.
+
+The reference's CPU scene model (src/gltf_scene.cpp, tinygltf) is *consumed*, not rebuilt, by
+the hot path.  tinygltf/glm are not in this image, so this module produces
+the same *outputs* that SceneVk/MaterialCache/SceneRtx hand the path tracer:
+
+  RenderPrimitive[]   unique (attributes, indices) in mesh/primitive order   gltf_scene.cpp:2139-2163
+  RenderNode[]        one per (node, primitive), DFS order, + GPU instancing  gltf_scene.cpp:2338-2429
+  GltfShadeMaterial[] + GltfTextureInfo[] (slot 0 reserved)                  gltf_material_cache.cpp:63-251
+  vertex arrays       float3 pos/nrm, float2 uv0/uv1, float4 tan, unorm4x8   gltf_scene_vk.cpp:741-869
+  GltfLight[]                                                                 gltf_scene_vk.cpp:1354-1394
+  textures + samplers + sRGB set                                              gltf_scene_vk.cpp:909-947,1102-1154
+  first camera (eye/center/up from node extras or node matrix)               gltf_scene.cpp:2215-2267
+"""
+import base64
+import ctypes as C
+import io
+import json
+import math
+import os
+import struct
+
+import numpy as np
+
+from . import abi
+
+_COMP = {5120: np.int8, 5121: np.uint8, 5122: np.int16, 5123: np.uint16, 5125: np.uint32, 5126: np.float32}
+_NCOMP = {"SCALAR": 1, "VEC2": 2, "VEC3": 3, "VEC4": 4, "MAT2": 4, "MAT3": 9, "MAT4": 16}
+
+
+class Camera:
+    def __init__(self):
+        self.type = "perspective"
+        self.eye = np.array([0, 0, 1], np.float32)
+        self.center = np.zeros(3, np.float32)
+        self.up = np.array([0, 1, 0], np.float32)
+        self.yfov = math.radians(45.0)
+        self.znear = 0.1
+        self.zfar = 1000.0
+        self.xmag = 1.0
+        self.ymag = 1.0
+
+
+class Scene:
+    """Flat scene arrays + the ctypes SceneDesc that points at them."""
+
+    def __init__(self):
+        self.render_nodes = []        # list of dict(objectToWorld f32[16] (glm column-major), materialID, renderPrimID, visible)
+        self.render_prims = []        # list of dict(indices u32[T,3], positions f32[V,3], normals?, colors?, tangents?, uv0?, uv1?)
+        self.materials = []           # list of abi.ShadeMaterial
+        self.texture_infos = [abi.TextureInfo()]
+        self.texture_infos[0].index = -1
+        self.texture_infos[0].uvTransform[:] = [1, 0, 0, 1, 0, 0]
+        self.textures = []            # list of dict(rgba8 u8[H,W,4], srgb, wrapS, wrapT, magFilter, minFilter)
+        self.lights = []              # list of abi.Light
+        self.camera = None
+        self._keep = []
+
+    # -- bounds (reference: Scene::getSceneBounds, gltf_scene.cpp:2303-2336, from transformed vertices)
+    def bounds(self):
+        lo = np.full(3, np.inf)
+        hi = np.full(3, -np.inf)
+        for rn in self.render_nodes:
+            m = np.asarray(rn["objectToWorld"], np.float64).reshape(4, 4).T
+            p = self.render_prims[rn["renderPrimID"]]["positions"].astype(np.float64)
+            w = p @ m[:3, :3].T + m[:3, 3]
+            lo = np.minimum(lo, w.min(0))
+            hi = np.maximum(hi, w.max(0))
+        return lo, hi
+
+    def num_triangles(self):
+        return sum(len(self.render_prims[rn["renderPrimID"]]["indices"]) for rn in self.render_nodes
+                   if rn.get("visible", True))
+
+    def add_material(self, **kw):
+        m = default_material()
+        for k, v in kw.items():
+            cur = getattr(m, k)
+            if hasattr(cur, "__len__"):
+                for i, x in enumerate(v):
+                    cur[i] = x
+            else:
+                setattr(m, k, v)
+        self.materials.append(m)
+        return len(self.materials) - 1
+
+    def add_texture_info(self, tex_index, texcoord=0, uv_transform=(1, 0, 0, 1, 0, 0)):
+        ti = abi.TextureInfo()
+        ti.index = tex_index
+        ti.texCoord = min(texcoord, 1)
+        ti.uvTransform[:] = list(uv_transform)
+        self.texture_infos.append(ti)
+        return len(self.texture_infos) - 1
+
+    def add_texture(self, rgba8, srgb=False, wrapS=10497, wrapT=10497, magFilter=-1, minFilter=-1):
+        rgba8 = np.ascontiguousarray(rgba8, np.uint8)
+        assert rgba8.ndim == 3 and rgba8.shape[2] == 4
+        self.textures.append(dict(rgba8=rgba8, srgb=int(srgb), wrapS=wrapS, wrapT=wrapT,
+                                  magFilter=magFilter, minFilter=minFilter))
+        return len(self.textures) - 1
+
+    def add_primitive(self, positions, indices, normals=None, uv0=None, uv1=None, tangents=None, colors=None):
+        prim = dict(
+            positions=np.ascontiguousarray(positions, np.float32).reshape(-1, 3),
+            indices=np.ascontiguousarray(indices, np.uint32).reshape(-1, 3),
+            normals=None if normals is None else np.ascontiguousarray(normals, np.float32).reshape(-1, 3),
+            uv0=None if uv0 is None else np.ascontiguousarray(uv0, np.float32).reshape(-1, 2),
+            uv1=None if uv1 is None else np.ascontiguousarray(uv1, np.float32).reshape(-1, 2),
+            tangents=None if tangents is None else np.ascontiguousarray(tangents, np.float32).reshape(-1, 4),
+            colors=None if colors is None else np.ascontiguousarray(colors, np.uint32).reshape(-1),
+        )
+        self.render_prims.append(prim)
+        return len(self.render_prims) - 1
+
+    def add_node(self, prim_id, material_id, matrix=None, visible=True):
+        m = np.eye(4, dtype=np.float64) if matrix is None else np.asarray(matrix, np.float64).reshape(4, 4)
+        self.render_nodes.append(dict(objectToWorld=_glm(m), worldToObject=_glm(np.linalg.inv(m)),
+                                      materialID=material_id, renderPrimID=prim_id, visible=visible))
+        return len(self.render_nodes) - 1
+
+    # -- ctypes view ---------------------------------------------------------------------------
+    def desc(self):
+        """Build (and cache) the abi.SceneDesc; arrays stay alive as long as `self` does."""
+        keep = []
+        n = len(self.render_nodes)
+        nodes = (abi.RenderNode * max(n, 1))()
+        vis = np.ones(max(n, 1), np.uint8)
+        for i, rn in enumerate(self.render_nodes):
+            nodes[i].objectToWorld[:] = rn["objectToWorld"].tolist()
+            nodes[i].worldToObject[:] = rn["worldToObject"].tolist()
+            nodes[i].materialID = rn["materialID"]
+            nodes[i].renderPrimID = rn["renderPrimID"]
+            vis[i] = 1 if rn.get("visible", True) else 0
+        prims = (abi.RenderPrimitive * max(len(self.render_prims), 1))()
+        for i, p in enumerate(self.render_prims):
+            prims[i].indices = abi.u32ptr(p["indices"])
+            prims[i].positions = abi.fptr(p["positions"])
+            prims[i].normals = abi.fptr(p["normals"])
+            prims[i].colors = abi.u32ptr(p["colors"])
+            prims[i].tangents = abi.fptr(p["tangents"])
+            prims[i].texCoords[0] = abi.fptr(p["uv0"])
+            prims[i].texCoords[1] = abi.fptr(p["uv1"])
+            prims[i].triangleCount = len(p["indices"])
+            prims[i].vertexCount = len(p["positions"])
+        mats = (abi.ShadeMaterial * max(len(self.materials), 1))(*self.materials)
+        tis = (abi.TextureInfo * len(self.texture_infos))(*self.texture_infos)
+        texs = (abi.Texture * max(len(self.textures), 1))()
+        for i, t in enumerate(self.textures):
+            texs[i].rgba8 = abi.u8ptr(t["rgba8"])
+            texs[i].height, texs[i].width = t["rgba8"].shape[:2]
+            for k in ("srgb", "wrapS", "wrapT", "magFilter", "minFilter"):
+                setattr(texs[i], k, t[k])
+        lights = (abi.Light * max(len(self.lights), 1))(*self.lights)
+        d = abi.SceneDesc()
+        d.renderNodes, d.numRenderNodes = nodes, n
+        d.renderNodeVisible = abi.u8ptr(vis)
+        d.renderPrimitives, d.numRenderPrimitives = prims, len(self.render_prims)
+        d.materials, d.numMaterials = mats, len(self.materials)
+        d.textureInfos, d.numTextureInfos = tis, len(self.texture_infos)
+        d.textures, d.numTextures = texs, len(self.textures)
+        d.lights, d.numLights = lights, len(self.lights)
+        keep += [nodes, vis, prims, mats, tis, texs, lights]
+        self._keep = keep
+        return d
+
+
+def _glm(m):
+    """4x4 (row, col) math matrix -> glm column-major float32[16]."""
+    return np.ascontiguousarray(np.asarray(m, np.float64).T.reshape(16), np.float32)
+
+
+def default_material():
+    """GltfShadeMaterial member defaults (gltf_scene_io.h.slang:147-310) overlaid with the glTF /
+    KHR extension defaults populateShaderMaterial writes (gltf_material_cache.cpp:103-233;
+    tinygltf_utils.hpp:50-248)."""
+    m = abi.ShadeMaterial()
+    m.pbrBaseColorFactor[:] = [1, 1, 1, 1]
+    m.normalTextureScale = 1.0
+    m.pbrRoughnessFactor = 1.0
+    m.pbrMetallicFactor = 1.0
+    m.alphaCutoff = 0.5
+    m.occlusionStrength = 1.0
+    m.attenuationColor[:] = [1, 1, 1]
+    m.ior = 1.5
+    m.attenuationDistance = float(np.finfo(np.float32).max)
+    m.specularColorFactor[:] = [1, 1, 1]
+    m.specularFactor = 1.0
+    m.iridescenceThicknessMinimum = 100.0
+    m.iridescenceThicknessMaximum = 400.0
+    m.iridescenceIor = 1.3
+    m.pbrDiffuseFactor[:] = [1, 1, 1, 1]
+    m.pbrSpecularFactor[:] = [1, 1, 1]
+    m.pbrGlossinessFactor = 1.0
+    m.diffuseTransmissionColor[:] = [1, 1, 1]
+    return m
+
+
+# ------------------------------------------------------------------------------------------------
+# glTF parsing
+# ------------------------------------------------------------------------------------------------
+class _Gltf:
+    def __init__(self, path):
+        self.dir = os.path.dirname(os.path.abspath(path))
+        raw = open(path, "rb").read()
+        self.bin_chunk = None
+        if raw[:4] == b"glTF":
+            _, _, total = struct.unpack("<4sII", raw[:12])
+            off = 12
+            self.json = None
+            while off < total:
+                clen, ctype = struct.unpack("<II", raw[off:off + 8])
+                data = raw[off + 8: off + 8 + clen]
+                if ctype == 0x4E4F534A:
+                    self.json = json.loads(data.decode("utf-8"))
+                elif ctype == 0x004E4942:
+                    self.bin_chunk = data
+                off += 8 + clen
+        else:
+            self.json = json.loads(raw.decode("utf-8"))
+        self._buffers = {}
+
+    def buffer(self, i):
+        if i not in self._buffers:
+            b = self.json["buffers"][i]
+            uri = b.get("uri")
+            if uri is None:
+                data = self.bin_chunk
+            elif uri.startswith("data:"):
+                data = base64.b64decode(uri.split(",", 1)[1])
+            else:
+                data = open(os.path.join(self.dir, uri), "rb").read()
+            self._buffers[i] = data
+        return self._buffers[i]
+
+    def accessor(self, idx, normalize=True):
+        """Decode an accessor to float32 (normalized ints -> [0,1]/[-1,1]) or its integer type.
+        reference: tinygltf::utils::getAccessorData / copyAccessorData (tinygltf_utils.hpp:756-)."""
+        a = self.json["accessors"][idx]
+        dt = np.dtype(_COMP[a["componentType"]])
+        nc = _NCOMP[a["type"]]
+        count = a["count"]
+        if "bufferView" in a:
+            bv = self.json["bufferViews"][a["bufferView"]]
+            buf = self.buffer(bv["buffer"])
+            start = bv.get("byteOffset", 0) + a.get("byteOffset", 0)
+            stride = bv.get("byteStride", 0) or dt.itemsize * nc
+            if stride == dt.itemsize * nc:
+                arr = np.frombuffer(buf, dt, count * nc, start).reshape(count, nc)
+            else:
+                arr = np.ndarray((count, nc), dt, buf, start, (stride, dt.itemsize))
+            arr = np.array(arr)
+        else:
+            arr = np.zeros((count, nc), dt)
+        if "sparse" in a:
+            sp = a["sparse"]
+            ibv = self.json["bufferViews"][sp["indices"]["bufferView"]]
+            idt = np.dtype(_COMP[sp["indices"]["componentType"]])
+            ii = np.frombuffer(self.buffer(ibv["buffer"]), idt, sp["count"],
+                               ibv.get("byteOffset", 0) + sp["indices"].get("byteOffset", 0))
+            vbv = self.json["bufferViews"][sp["values"]["bufferView"]]
+            vv = np.frombuffer(self.buffer(vbv["buffer"]), dt, sp["count"] * nc,
+                               vbv.get("byteOffset", 0) + sp["values"].get("byteOffset", 0)).reshape(-1, nc)
+            arr[ii] = vv
+        if dt == np.float32 or not normalize:
+            return arr
+        if a.get("normalized", False):
+            if dt == np.uint8:
+                return (arr / 255.0).astype(np.float32)
+            if dt == np.uint16:
+                return (arr / 65535.0).astype(np.float32)
+            if dt == np.int8:
+                return np.maximum(arr / 127.0, -1.0).astype(np.float32)
+            if dt == np.int16:
+                return np.maximum(arr / 32767.0, -1.0).astype(np.float32)
+        return arr.astype(np.float32)
+
+
+def _node_matrix(node):
+    """tinygltf::utils::getNodeMatrix (tinygltf_utils.cpp:641-654): matrix, else T*R*S."""
+    if "matrix" in node:
+        return np.asarray(node["matrix"], np.float64).reshape(4, 4).T
+    t = np.asarray(node.get("translation", [0, 0, 0]), np.float64)
+    q = np.asarray(node.get("rotation", [0, 0, 0, 1]), np.float64)
+    s = np.asarray(node.get("scale", [1, 1, 1]), np.float64)
+    return _trs(t, q, s)
+
+
+def _trs(t, q, s):
+    x, y, z, w = q
+    r = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    m = np.eye(4)
+    m[:3, :3] = r * s[None, :]
+    m[:3, 3] = t
+    return m
+
+
+def _pack_unorm4x8(c):
+    """glm::packUnorm4x8: round(clamp(c,0,1)*255), x in the low byte."""
+    q = np.round(np.clip(c, 0.0, 1.0) * 255.0).astype(np.uint32)
+    return (q[:, 0] | (q[:, 1] << 8) | (q[:, 2] << 16) | (q[:, 3] << 24)).astype(np.uint32)
+
+
+def _tex_transform(tinfo):
+    """KHR_texture_transform -> float3x2 exactly as getTextureInfoImpl builds it
+    (gltf_material_cache.cpp:84-88 from tinygltf_utils.hpp:66-85)."""
+    ext = tinfo.get("extensions", {}).get("KHR_texture_transform")
+    if not ext:
+        return (1, 0, 0, 1, 0, 0)
+    ox, oy = ext.get("offset", [0, 0])
+    rot = ext.get("rotation", 0.0)
+    sx, sy = ext.get("scale", [1, 1])
+    c, s = math.cos(rot), math.sin(rot)
+    return (sx * c, -sy * s, sx * s, sy * c, ox, oy)
+
+
+def load_gltf(path):
+    g = _Gltf(path)
+    j = g.json
+    scn = Scene()
+
+    # ---- textures / images (SceneVk::createTextureImages) ----
+    images = j.get("images", [])
+    srgb_images = set()
+
+    def tex_image(tex_id):
+        t = j["textures"][tex_id]
+        for e in ("KHR_texture_basisu", "EXT_texture_webp", "MSFT_texture_dds", "EXT_texture_avif"):
+            if e in t.get("extensions", {}):
+                return t["extensions"][e]["source"]
+        return t.get("source", -1)
+
+    def mark_srgb(tinfo):
+        if tinfo and tinfo.get("index", -1) > -1:
+            srgb_images.add(tex_image(tinfo["index"]))
+
+    for m in j.get("materials", []):
+        mark_srgb(m.get("pbrMetallicRoughness", {}).get("baseColorTexture"))
+        mark_srgb(m.get("emissiveTexture"))
+        ex = m.get("extensions", {})
+        mark_srgb(ex.get("KHR_materials_specular", {}).get("specularColorTexture"))
+        mark_srgb(ex.get("KHR_materials_sheen", {}).get("sheenColorTexture"))
+        mark_srgb(ex.get("KHR_materials_pbrSpecularGlossiness", {}).get("diffuseTexture"))
+        mark_srgb(ex.get("KHR_materials_pbrSpecularGlossiness", {}).get("specularGlossinessTexture"))
+    for t in j.get("textures", []):
+        ex = t.get("extras")
+        if isinstance(ex, dict) and float(ex.get("gamma", 0)) > 1.0:
+            srgb_images.add(tex_image(j["textures"].index(t)))
+
+    decoded = {}
+
+    def decode_image(i):
+        if i in decoded:
+            return decoded[i]
+        from PIL import Image
+        try:
+            im = images[i]
+            if "uri" in im:
+                if im["uri"].startswith("data:"):
+                    data = base64.b64decode(im["uri"].split(",", 1)[1])
+                else:
+                    data = open(os.path.join(g.dir, im["uri"]), "rb").read()
+            else:
+                bv = j["bufferViews"][im["bufferView"]]
+                data = g.buffer(bv["buffer"])[bv.get("byteOffset", 0): bv.get("byteOffset", 0) + bv["byteLength"]]
+            arr = np.asarray(Image.open(io.BytesIO(data)).convert("RGBA"), np.uint8)
+        except Exception:
+            arr = np.array([[[255, 0, 255, 255]]], np.uint8)  # magenta default (gltf_scene_vk.cpp:1054-1060)
+        decoded[i] = np.ascontiguousarray(arr)
+        return decoded[i]
+
+    for ti, t in enumerate(j.get("textures", [])):
+        src = tex_image(ti)
+        smp = j["samplers"][t["sampler"]] if t.get("sampler", -1) > -1 else {}
+        rgba = decode_image(src) if src > -1 else np.array([[[255, 255, 255, 255]]], np.uint8)
+        scn.add_texture(rgba, srgb=(src in srgb_images), wrapS=smp.get("wrapS", 10497), wrapT=smp.get("wrapT", 10497),
+                        magFilter=smp.get("magFilter", -1), minFilter=smp.get("minFilter", -1))
+
+    # ---- materials (MaterialCache::buildFromMaterials) ----
+    def handle(mat, slot, tinfo):
+        if tinfo is not None and tinfo.get("index", -1) != -1:
+            setattr(mat, slot, scn.add_texture_info(tinfo["index"], tinfo.get("texCoord", 0), _tex_transform(tinfo)))
+
+    src_mats = j.get("materials", []) or [{}]
+    for sm in src_mats:
+        m = default_material()
+        am = sm.get("alphaMode", "OPAQUE")
+        m.alphaMode = 0 if am == "OPAQUE" else (1 if am == "MASK" else 2)
+        m.alphaCutoff = sm.get("alphaCutoff", 0.5)
+        m.doubleSided = 1 if sm.get("doubleSided", False) else 0
+        pbr = sm.get("pbrMetallicRoughness", {})
+        m.pbrBaseColorFactor[:] = pbr.get("baseColorFactor", [1, 1, 1, 1])
+        m.pbrMetallicFactor = pbr.get("metallicFactor", 1.0)
+        m.pbrRoughnessFactor = pbr.get("roughnessFactor", 1.0)
+        m.normalTextureScale = (sm.get("normalTexture") or {}).get("scale", 1.0)
+        m.occlusionStrength = (sm.get("occlusionTexture") or {}).get("strength", 1.0)
+        m.emissiveFactor[:] = sm.get("emissiveFactor", [0, 0, 0])
+        handle(m, "emissiveTexture", sm.get("emissiveTexture"))
+        handle(m, "normalTexture", sm.get("normalTexture"))
+        handle(m, "pbrBaseColorTexture", pbr.get("baseColorTexture"))
+        handle(m, "pbrMetallicRoughnessTexture", pbr.get("metallicRoughnessTexture"))
+        handle(m, "occlusionTexture", sm.get("occlusionTexture"))
+        ex = sm.get("extensions", {})
+        e = ex.get("KHR_materials_transmission", {})
+        m.transmissionFactor = e.get("transmissionFactor", 0.0)
+        handle(m, "transmissionTexture", e.get("transmissionTexture"))
+        m.ior = ex.get("KHR_materials_ior", {}).get("ior", 1.5)
+        e = ex.get("KHR_materials_volume", {})
+        m.attenuationColor[:] = e.get("attenuationColor", [1, 1, 1])
+        m.thicknessFactor = e.get("thicknessFactor", 0.0)
+        m.attenuationDistance = min(e.get("attenuationDistance", float(np.finfo(np.float32).max)),
+                                    float(np.finfo(np.float32).max))
+        handle(m, "thicknessTexture", e.get("thicknessTexture"))
+        e = ex.get("KHR_materials_clearcoat", {})
+        m.clearcoatFactor = e.get("clearcoatFactor", 0.0)
+        m.clearcoatRoughness = e.get("clearcoatRoughnessFactor", 0.0)
+        handle(m, "clearcoatRoughnessTexture", e.get("clearcoatRoughnessTexture"))
+        handle(m, "clearcoatTexture", e.get("clearcoatTexture"))
+        handle(m, "clearcoatNormalTexture", e.get("clearcoatNormalTexture"))
+        e = ex.get("KHR_materials_specular", {})
+        m.specularFactor = e.get("specularFactor", 1.0)
+        m.specularColorFactor[:] = e.get("specularColorFactor", [1, 1, 1])
+        handle(m, "specularTexture", e.get("specularTexture"))
+        handle(m, "specularColorTexture", e.get("specularColorTexture"))
+        strength = ex.get("KHR_materials_emissive_strength", {}).get("emissiveStrength", 1.0)
+        for k in range(3):
+            m.emissiveFactor[k] = m.emissiveFactor[k] * strength
+        m.unlit = 1 if "KHR_materials_unlit" in ex else 0
+        e = ex.get("KHR_materials_iridescence", {})
+        m.iridescenceFactor = e.get("iridescenceFactor", 0.0)
+        m.iridescenceIor = e.get("iridescenceIor", 1.3)
+        m.iridescenceThicknessMinimum = e.get("iridescenceThicknessMinimum", 100.0)
+        m.iridescenceThicknessMaximum = e.get("iridescenceThicknessMaximum", 400.0)
+        handle(m, "iridescenceTexture", e.get("iridescenceTexture"))
+        handle(m, "iridescenceThicknessTexture", e.get("iridescenceThicknessTexture"))
+        e = ex.get("KHR_materials_anisotropy", {})
+        rot = e.get("anisotropyRotation", 0.0)
+        m.anisotropyRotation[:] = [math.sin(rot), math.cos(rot)]
+        m.anisotropyStrength = e.get("anisotropyStrength", 0.0)
+        handle(m, "anisotropyTexture", e.get("anisotropyTexture"))
+        e = ex.get("KHR_materials_sheen", {})
+        m.sheenColorFactor[:] = e.get("sheenColorFactor", [0, 0, 0])
+        m.sheenRoughnessFactor = e.get("sheenRoughnessFactor", 0.0)
+        handle(m, "sheenColorTexture", e.get("sheenColorTexture"))
+        handle(m, "sheenRoughnessTexture", e.get("sheenRoughnessTexture"))
+        m.dispersion = ex.get("KHR_materials_dispersion", {}).get("dispersion", 0.0)
+        if "KHR_materials_pbrSpecularGlossiness" in ex:
+            e = ex["KHR_materials_pbrSpecularGlossiness"]
+            m.pbrModel = 1
+            m.pbrDiffuseFactor[:] = e.get("diffuseFactor", [1, 1, 1, 1])
+            m.pbrSpecularFactor[:] = e.get("specularFactor", [1, 1, 1])
+            m.pbrGlossinessFactor = e.get("glossinessFactor", 1.0)
+            handle(m, "pbrDiffuseTexture", e.get("diffuseTexture"))
+            handle(m, "pbrSpecularGlossinessTexture", e.get("specularGlossinessTexture"))
+        e = ex.get("KHR_materials_diffuse_transmission", {})
+        m.diffuseTransmissionFactor = e.get("diffuseTransmissionFactor", 0.0)
+        m.diffuseTransmissionColor[:] = e.get("diffuseTransmissionColorFactor", [1, 1, 1])
+        handle(m, "diffuseTransmissionTexture", e.get("diffuseTransmissionTexture"))
+        handle(m, "diffuseTransmissionColorTexture", e.get("diffuseTransmissionColorTexture"))
+        e = ex.get("KHR_materials_retroreflection", {})
+        m.retroreflectionFactor = e.get("retroreflectionFactor", 0.0)
+        handle(m, "retroreflectionTexture", e.get("retroreflectionTexture"))
+        e = ex.get("KHR_materials_volume_scatter", {})
+        m.multiscatterColorFactor[:] = e.get("multiscatterColorFactor", e.get("multiscatterColor", [0, 0, 0]))
+        m.scatterAnisotropy = e.get("scatterAnisotropy", 0.0)
+        scn.materials.append(m)
+
+    # ---- unique primitives (Scene::buildPrimitiveKeyMap) ----
+    prim_map = {}
+
+    def prim_key(p):
+        return " ".join(f"{k}:{v}" for k, v in sorted(p["attributes"].items())) + f" indices:{p.get('indices', -1)}"
+
+    for mesh in j.get("meshes", []):
+        for p in mesh["primitives"]:
+            if p.get("mode", 4) != 4:
+                continue
+            key = prim_key(p)
+            if key in prim_map:
+                continue
+            at = p["attributes"]
+            pos = g.accessor(at["POSITION"])
+            if "indices" in p:
+                idx = g.accessor(p["indices"], normalize=False).astype(np.uint32).reshape(-1)
+            else:
+                idx = np.arange(len(pos), dtype=np.uint32)
+            idx = idx[: (len(idx) // 3) * 3].reshape(-1, 3)
+            colors = None
+            if "COLOR_0" in at:
+                c = g.accessor(at["COLOR_0"])
+                if c.shape[1] == 3:
+                    c = np.concatenate([c, np.ones((len(c), 1), np.float32)], 1)
+                colors = _pack_unorm4x8(c)
+            prim_map[key] = scn.add_primitive(
+                pos, idx,
+                normals=g.accessor(at["NORMAL"]) if "NORMAL" in at else None,
+                uv0=g.accessor(at["TEXCOORD_0"]) if "TEXCOORD_0" in at else None,
+                uv1=g.accessor(at["TEXCOORD_1"]) if "TEXCOORD_1" in at else None,
+                tangents=g.accessor(at["TANGENT"]) if "TANGENT" in at else None,
+                colors=colors)
+
+    # ---- scene graph (Scene::parseScene) ----
+    nodes = j.get("nodes", [])
+    gl_lights = j.get("extensions", {}).get("KHR_lights_punctual", {}).get("lights", [])
+    scene_id = j.get("scene", 0)
+    cam_found = []
+
+    def visit(nid, parent):
+        node = nodes[nid]
+        world = parent @ _node_matrix(node)
+        if "camera" in node and not cam_found:
+            cam_found.append((nid, world))
+        li = node.get("extensions", {}).get("KHR_lights_punctual", {}).get("light", -1)
+        if 0 <= li < len(gl_lights):
+            gll = gl_lights[li]
+            L = abi.Light()
+            L.position[:] = world[:3, 3].tolist()
+            L.direction[:] = (-world[:3, 2]).tolist()
+            spot = gll.get("spot", {})
+            L.innerAngle = spot.get("innerConeAngle", 0.0)
+            L.outerAngle = spot.get("outerConeAngle", math.pi / 4)
+            L.color[:] = gll.get("color", [1, 1, 1])
+            L.intensity = gll.get("intensity", 1.0)
+            L.type = {"point": 3, "spot": 2}.get(gll.get("type"), 1)
+            ex = gll.get("extras")
+            L.radius = float(ex.get("radius", 0.0)) if isinstance(ex, dict) else 0.0
+            if L.type == 1:
+                L.angularSizeOrInvRange = 2.0 * math.atan(L.radius / 149597870.0)
+            else:
+                rng = gll.get("range", 0.0)
+                L.angularSizeOrInvRange = 1.0 / rng if rng > 0 else 0.0
+            scn.lights.append(L)
+        if node.get("mesh", -1) > -1:
+            visible = node.get("extensions", {}).get("KHR_node_visibility", {}).get("visible", True)
+            inst = node.get("extensions", {}).get("EXT_mesh_gpu_instancing")
+            locals_ = [np.eye(4)]
+            if inst:
+                at = inst["attributes"]
+                T = g.accessor(at["TRANSLATION"]) if "TRANSLATION" in at else None
+                R = g.accessor(at["ROTATION"]) if "ROTATION" in at else None
+                S = g.accessor(at["SCALE"]) if "SCALE" in at else None
+                n = max(len(x) for x in (T, R, S) if x is not None)
+                locals_ = [_trs(T[i] if T is not None and i < len(T) else np.zeros(3),
+                                R[i] if R is not None and i < len(R) else np.array([0, 0, 0, 1.0]),
+                                S[i] if S is not None and i < len(S) else np.ones(3)) for i in range(n)]
+            for p in j["meshes"][node["mesh"]]["primitives"]:
+                if p.get("mode", 4) != 4:
+                    continue
+                for lm in locals_:
+                    scn.add_node(prim_map[prim_key(p)], p.get("material", -1), world @ lm, visible)
+        for c in node.get("children", []):
+            visit(c, world)
+
+    for root in j.get("scenes", [{"nodes": list(range(len(nodes)))}])[scene_id]["nodes"]:
+        visit(root, np.eye(4))
+
+    # ---- camera (Scene::handleCameraTraversal) ----
+    if cam_found:
+        nid, world = cam_found[0]
+        gc = j["cameras"][nodes[nid]["camera"]]
+        cam = Camera()
+        lo, hi = scn.bounds() if scn.render_nodes else (np.full(3, -1.0), np.full(3, 1.0))
+        center = (lo + hi) * 0.5
+        radius = float(np.linalg.norm(hi - lo) * 0.5)
+        if gc["type"] == "perspective":
+            pp = gc["perspective"]
+            cam.yfov, cam.znear, cam.zfar = pp["yfov"], pp["znear"], pp.get("zfar", 0.0)
+        else:
+            cam.type = "orthographic"
+            oo = gc["orthographic"]
+            cam.xmag, cam.ymag, cam.znear, cam.zfar = oo["xmag"], oo["ymag"], oo["znear"], oo["zfar"]
+        if cam.zfar <= cam.znear:
+            cam.zfar = max(cam.znear * 2.0, 4.0 * radius)
+        # extractCameraVectors: eye = translation, forward = -Z, center at the scene-centre distance
+        eye = world[:3, 3]
+        fwd = -world[:3, 2] / max(np.linalg.norm(world[:3, 2]), 1e-20)
+        dist = float(np.linalg.norm(center - eye))
+        cam.eye, cam.center, cam.up = eye.astype(np.float32), (eye + fwd * dist).astype(np.float32), \
+            (world[:3, 1] / max(np.linalg.norm(world[:3, 1]), 1e-20)).astype(np.float32)
+        ex = nodes[nid].get("extras")
+        if isinstance(ex, dict):
+            if "camera::eye" in ex:
+                cam.eye = np.asarray(ex["camera::eye"], np.float32)
+            if "camera::center" in ex:
+                cam.center = np.asarray(ex["camera::center"], np.float32)
+            if "camera::up" in ex:
+                cam.up = np.asarray(ex["camera::up"], np.float32)
+        scn.camera = cam
+    return scn
