@@ -1,0 +1,70 @@
+"""Loader for the CUDA library (libb200pt.so) behind include/b200pt.h.
+
+There is NO CPU fallback: if the library is missing or fails to load this raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200pt.so")
+
+# every symbol include/b200pt.h declares
+EXPORTS = [
+    "b200pt_create", "b200pt_destroy", "b200pt_abi_version", "b200pt_last_error", "b200pt_set_scene",
+    "b200pt_set_environment", "b200pt_resize", "b200pt_render_frame", "b200pt_synchronize",
+    "b200pt_get_accum_device", "b200pt_read_accum", "b200pt_set_accum_device", "b200pt_stream",
+    "b200pt_get_stats", "b200pt_reset_stats", "b200pt_set_profiling", "b200pt_trace_closest",
+    "b200pt_trace_shadow", "b200pt_bvh_info", "b200pt_bsdf_eval", "b200pt_bsdf_sample",
+]
+
+
+def build(verbose=False):
+    """Compile libb200pt.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc"), "-s"],
+                          stdout=None if verbose else subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the CUDA path is the product; there is no fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u32, f32p = C.c_void_p, C.c_int, C.c_uint32, C.c_void_p
+    L.b200pt_create.argtypes = [C.POINTER(vp), i32]
+    L.b200pt_destroy.argtypes = [vp]
+    L.b200pt_destroy.restype = None
+    L.b200pt_abi_version.restype = i32
+    L.b200pt_last_error.argtypes = [vp]
+    L.b200pt_last_error.restype = C.c_char_p
+    L.b200pt_set_scene.argtypes = [vp, C.POINTER(abi.SceneDesc)]
+    L.b200pt_set_environment.argtypes = [vp, f32p, i32, i32, C.POINTER(C.c_float)]
+    L.b200pt_resize.argtypes = [vp, i32, i32, i32, i32]
+    L.b200pt_render_frame.argtypes = [vp, C.POINTER(abi.FrameInfo), C.POINTER(abi.PushConstant)]
+    L.b200pt_synchronize.argtypes = [vp]
+    L.b200pt_get_accum_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.b200pt_read_accum.argtypes = [vp, f32p, C.c_size_t]
+    L.b200pt_set_accum_device.argtypes = [vp, vp, C.c_size_t]
+    L.b200pt_stream.argtypes = [vp]
+    L.b200pt_stream.restype = vp
+    L.b200pt_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
+    L.b200pt_reset_stats.argtypes = [vp]
+    L.b200pt_set_profiling.argtypes = [vp, i32]
+    L.b200pt_trace_closest.argtypes = [vp, vp, u32, vp, vp]
+    L.b200pt_trace_shadow.argtypes = [vp, vp, u32, vp, vp]
+    L.b200pt_bvh_info.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(u32), C.POINTER(u32)]
+    L.b200pt_bsdf_eval.argtypes = [vp, vp, u32, vp]
+    L.b200pt_bsdf_sample.argtypes = [vp, vp, u32, vp]
+    for name in EXPORTS:
+        getattr(L, name)  # raises AttributeError if a declared symbol is not exported
+    _lib = L
+    return L

@@ -1,0 +1,1432 @@
+// b200pt.cu — wavefront path-tracer kernels for sm_100a + the C-ABI of include/b200pt.h.
+//
+// Stage map (reference function -> kernel), SURVEY.md Appendix C:
+//   processPixel head / samplePixel / getRay      gltf_pathtrace.slang:546-581,502-530  -> k_raygen (+ regen in finalizeSample)
+//   IRaytracer::Trace                              raytracer_interface.h.slang:69-122    -> k_trace
+//   pathTraceOneBounce                             gltf_pathtrace.slang:87-430           -> k_shade
+//   TraceShadow + RR + depth++ (pathTrace tail)    gltf_pathtrace.slang:462-485          -> k_post
+//   accumulation                                   gltf_pathtrace.slang:582-630          -> k_accumulate
+// One path slot per pixel; samples of a pixel within a frame run back to back in the same slot
+// (path regeneration) because the reference continues ONE rng stream across a pixel's samples.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bvh.h"
+#include "shade.cuh"
+
+using namespace pt;
+
+static_assert(sizeof(b200pt_render_node) == 136, "GltfRenderNode layout");
+static_assert(sizeof(b200pt_texture_info) == 32, "GltfTextureInfo layout");
+static_assert(sizeof(b200pt_shade_material) == 288, "GltfShadeMaterial layout");
+static_assert(sizeof(b200pt_light) == 64, "GltfLight layout");
+static_assert(sizeof(b200pt_frame_info) == 396, "SceneFrameInfo layout");
+static_assert(sizeof(b200pt_push_constant) == 48, "PathtracePushConstant layout");
+
+namespace {
+
+constexpr int kMaxIters = 4096;  // per-frame iteration counter slots
+
+// -------------------------------------------------------------------------------------------------
+// queue helper: warp-aggregated append
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void queuePush(uint32_t* q, uint32_t* cnt, uint32_t value)
+{
+  const unsigned mask = __activemask();
+  const int      lane = threadIdx.x & 31;
+  const int      leader = __ffs(mask) - 1;
+  uint32_t       base = 0;
+  if(lane == leader)
+    base = atomicAdd(cnt, (uint32_t)__popc(mask));
+  base = __shfl_sync(mask, base, leader);
+  q[base + __popc(mask & ((1u << lane) - 1u))] = value;
+}
+
+__device__ __forceinline__ void statAdd(unsigned long long* p, unsigned long long v)
+{
+  // per-warp aggregation of a uniform +v
+  const unsigned mask = __activemask();
+  const int      lane = threadIdx.x & 31;
+  if(lane == __ffs(mask) - 1)
+    atomicAdd(p, v * (unsigned long long)__popc(mask));
+}
+
+// -------------------------------------------------------------------------------------------------
+// camera ray + sample start (samplePixel head: gltf_pathtrace.slang:502-530; getRay: pathtrace_functions.h.slang:791-811)
+// -------------------------------------------------------------------------------------------------
+__device__ void startSample(const PathState& P, const FrameParams& F, uint32_t i, uint32_t seed, float2 jitter, uint32_t sampleIdx)
+{
+  const uint32_t x = i % (uint32_t)F.width;
+  const uint32_t y = (uint32_t)F.tileY0 + i / (uint32_t)F.width;
+  const Mat4&    projI = *reinterpret_cast<const Mat4*>(F.fi.projInv);
+  const Mat4&    viewI = *reinterpret_cast<const Mat4*>(F.fi.viewInv);
+  const bool     ortho = (F.fi.flags & B200PT_SCENE_IS_ORTHOGRAPHIC) != 0;
+  const float2   clip = f2(((float)x + jitter.x) / F.fi.imageSize[0] * 2.0f - 1.0f, ((float)y + jitter.y) / F.fi.imageSize[1] * 2.0f - 1.0f);
+  float4         vc = mul_vM(f4(clip.x, clip.y, -1.0f, 1.0f), projI);
+  vc = vc / vc.w;
+  float3 org, dir;
+  if(ortho)
+  {
+    org = xyz(mul_vM(vc, viewI));
+    dir = normalize(xyz(mul_vM(f4(0, 0, -1, 0), viewI)));
+  }
+  else
+  {
+    org = f3(viewI.m[12], viewI.m[13], viewI.m[14]);
+    dir = normalize(xyz(mul_vM(vc, viewI)) - org);
+    // thin-lens DOF: the two rand() are consumed even when aperture == 0 (:519-520)
+    const float3 focalPoint = dir * F.pc.focalDistance;
+    const float  cam_r1 = rnd(seed) * kTwoPi;
+    const float  cam_r2 = rnd(seed) * F.pc.aperture;
+    const float4 camRight = mul_Mv(viewI, f4(1, 0, 0, 0));
+    const float4 camUp = mul_Mv(viewI, f4(0, 1, 0, 0));
+    const float3 rap = (xyz(camRight) * cosf(cam_r1) + xyz(camUp) * sinf(cam_r1)) * sqrtf(cam_r2);
+    dir = normalize(focalPoint - rap);
+    org += rap;
+  }
+  dir = normalize(dir);  // pathTrace() re-normalises at the top of every loop iteration (:447)
+  P.rayO[i] = f4(org, 0.0f);
+  P.rayD[i] = f4(dir, kInfinite);
+  P.thr[i] = f4(1.0f, 1.0f, 1.0f, kDirac);
+  P.rad[i] = f4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
+  P.misc[i] = f4(0.0f, 0.0f, __uint_as_float(PF_SOLID), __uint_as_float(seed));
+  P.medium[i] = make_uint4(0u, 0u, 0u, sampleIdx << 16);
+}
+
+// end of one samplePixel(): firefly clamp, add to the pixel sum, start the pixel's next sample if any
+__device__ void finalizeSample(const PathState& P, const FrameParams& F, uint32_t i, float3 radiance, bool solid, uint32_t seed, uint32_t sampleIdx,
+                               uint32_t* qNext, uint32_t* cntNext, DevStats* stats)
+{
+  float4      r = f4(radiance, solid ? 1.0f : 0.0f);
+  const float lum = (r.x + r.y + r.z) * (1.0f / 3.0f);
+  if(lum > F.pc.fireflyClampThreshold)
+    r = r * (F.pc.fireflyClampThreshold / lum);
+  P.pixSum[i] = P.pixSum[i] + r;
+  const uint32_t s = sampleIdx + 1;
+  if((int)s < F.pc.numSamples)
+  {
+    const float a = rnd(seed), b = rnd(seed);
+    startSample(P, F, i, seed, f2(a, b), s);
+    statAdd(&stats->pathsStarted, 1ull);
+    queuePush(qNext, cntNext, i);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// kernels
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_raygen(PathState P, const __grid_constant__ FrameParams F, uint32_t* qTrace, uint32_t* cnt0, DevStats* stats)
+{
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < F.numPaths; i += stride)
+  {
+    const uint32_t x = i % (uint32_t)F.width;
+    const uint32_t y = (uint32_t)F.tileY0 + i / (uint32_t)F.width;
+    uint32_t       seed = xxhash32(x, y, (uint32_t)F.pc.frameCount);
+    const float    u1 = rnd(seed), u2 = rnd(seed);
+    // sampleGaussian (pathtrace_functions.h.slang:784-789), sigma = 0.4246609 px
+    const float  rr = sqrtf(-2.0f * logf(fmaxf(1e-38f, u1)));
+    const float  theta = 2.0f * kPi * u2;
+    const float2 jitter = f2(0.5f + (rr * cosf(theta)) * 0.4246609f, 0.5f + (rr * sinf(theta)) * 0.4246609f);
+    P.pixSum[i] = f4(0.f, 0.f, 0.f, 0.f);
+    startSample(P, F, i, seed, jitter, 0u);
+    qTrace[i] = i;
+  }
+  if(blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    *cnt0 = F.numPaths;
+    atomicAdd(&stats->pathsStarted, (unsigned long long)F.numPaths);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_trace(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn, DevStats* stats)
+{
+  const uint32_t count = *cntIn;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for(uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
+  {
+    const uint32_t i = q[k];
+    const float4   o = P.rayO[i];
+    const float4   d = P.rayD[i];
+    uint32_t       seed = 0;
+    if(!S.allOpaque)
+      seed = __float_as_uint(P.misc[i].w);
+    const uint32_t seedIn = seed;
+    const TraceHit h = traceClosest(S, xyz(o), xyz(d), 0.0f, d.w, seed, stats);
+    P.hit[i] = f4(h.t, h.u, h.v, __uint_as_float(h.slot));
+    if(seed != seedIn)
+      reinterpret_cast<uint32_t*>(&P.misc[i])[3] = seed;
+  }
+  if(blockIdx.x == 0 && threadIdx.x == 0)
+    atomicAdd(&stats->closestRays, (unsigned long long)count);
+}
+
+__global__ void __launch_bounds__(128) k_shade(PathState P, DevScene S, const __grid_constant__ FrameParams F, const uint32_t* __restrict__ q,
+                                               const uint32_t* __restrict__ cntIn, uint32_t* qPost, uint32_t* cntPost, uint32_t* qNext, uint32_t* cntNext, DevStats* stats)
+{
+  const uint32_t count = *cntIn;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for(uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
+  {
+    const uint32_t i = q[k];
+    const float4   ro = P.rayO[i];
+    const float4   rd = P.rayD[i];
+    const float4   hr = P.hit[i];
+    float4         thr4 = P.thr[i];
+    float4         rad4 = P.rad[i];
+    float4         misc = P.misc[i];
+    uint4          med = P.medium[i];
+    float3         org = xyz(ro), dir = xyz(rd);
+    float          coneWidth = ro.w;
+    float3         throughput = xyz(thr4), radiance = xyz(rad4);
+    float          lastSamplePdf = thr4.w;
+    uint32_t       flags = __float_as_uint(misc.z);
+    uint32_t       seed = __float_as_uint(misc.w);
+    uint32_t       scatterBounces = __float_as_uint(rad4.w);
+    const uint32_t sampleIdx = med.w >> 16;
+    uint32_t       depth = flags & PF_DEPTH_MASK;
+    const uint32_t slot = __float_as_uint(hr.w);
+    const float    hitT = hr.x;
+
+    if(slot == 0xFFFFFFFFu)
+    {
+      // ---- environment (gltf_pathtrace.slang:129-156) ----
+      if(depth == 0)
+      {
+        flags &= ~PF_SOLID;  // tryPrimaryMissBackplate: pt.solid = false
+        if(F.fi.flags & B200PT_SCENE_USE_SOLID_BACKGROUND)
+        {
+          finalizeSample(P, F, i, f3(F.fi.backgroundColor[0], F.fi.backgroundColor[1], F.fi.backgroundColor[2]), false, seed, sampleIdx, qNext, cntNext, stats);
+          continue;
+        }
+      }
+      const float3 edir = rotateAxis(dir, f3(0, 1, 0), -F.fi.envRotation);
+      const float4 env = sampleEnvTex(S, getSphericalUv(edir));
+      float        misWeight = 1.0f;
+      if(lastSamplePdf != kDirac)
+      {
+        float lw, ew;
+        techniqueProbabilities(S, F, lw, ew);
+        misWeight = lastSamplePdf / (lastSamplePdf + ew * env.w);
+      }
+      radiance += throughput * misWeight * (xyz(env) * F.fi.envIntensity);
+      finalizeSample(P, F, i, radiance, (flags & PF_SOLID) != 0, seed, sampleIdx, qNext, cntNext, stats);
+      continue;
+    }
+
+    // ---- hit-attribute fetch ----
+    const uint2               meta = S.triMeta[slot];
+    const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
+    const DevPrim             prim = S.prims[node.renderPrimID];
+    const float3              bary = f3(1.0f - hr.y - hr.z, hr.y, hr.z);
+    const HitState            hit = getHitState(prim, bary, node.worldToObject, node.objectToWorld, meta.y, dir);
+    statAdd(&stats->shadedHits, 1ull);
+
+    const float worldFoot = (coneWidth + F.pc.pixelAngle * hitT) / fmaxf(fabsf(dot(hit.geonrm, -dir)), 1e-3f);
+    const int   materialIndex = max(0, node.materialID);
+    const float texGrad = worldFoot * hit.texelDensity * F.pc.texGradScale;
+    const b200pt_shade_material& gmat = S.mats[materialIndex];
+    PbrMaterial                  pbrMat = evaluateMaterial(S, gmat, hit, (flags & PF_INSIDE) != 0, texGrad);
+
+    // firefly control: never get sharper than the roughest bounce so far (:267-268)
+    misc.x = fmaxf(pbrMat.roughness.x, misc.x);
+    misc.y = fmaxf(pbrMat.roughness.y, misc.y);
+    pbrMat.roughness = f2(misc.x, misc.y);
+
+    radiance += pbrMat.emissive * throughput;
+
+    if(gmat.unlit > 0)
+    {
+      radiance += pbrMat.baseColor;
+      finalizeSample(P, F, i, radiance, (flags & PF_SOLID) != 0, seed, sampleIdx, qNext, cntNext, stats);
+      continue;
+    }
+
+    flags &= ~(PF_POST_VOLUME | PF_SHADOW_VALID | PF_SHADOW_INSIDE);
+
+    // ---- in-volume segment (pathtrace_functions.h.slang:904-939, 605-672) ----
+    if(flags & PF_INSIDE)
+    {
+      const VolumeMedium vm = unpackMedium(med);
+      if(hasVolumeMedium(vm))
+      {
+        const float3 ext = vm.extinction, sc = vm.scatterCoefficient;
+        bool         scattered = false;
+        if(maxc(sc) > 0.001f)
+        {
+          const float maxExt = maxc(ext);
+          const float scatterDist = -logf(fmaxf(rnd(seed), 1.0e-10f)) / maxExt;
+          if(scatterDist < hitT)
+          {
+            throughput *= f3(1.0f) - (ext - sc) / maxExt;
+            const float3 wi = dir;
+            const float3 originBefore = org;
+            org = org + dir * scatterDist;
+            const float a = rnd(seed), b = rnd(seed);
+            dir = sampleHenyeyGreenstein(f2(a, b), vm.scatterAnisotropy, wi);
+            lastSamplePdf = henyeyGreensteinPdf(dot(wi, dir), vm.scatterAnisotropy);
+            scattered = true;
+            scatterBounces++;
+            coneWidth += F.pc.pixelAngle * length(org - originBefore);
+            // NEE at the scatter point (volumeScatterNEE)
+            const DirectLight dl = sampleLights(S, F, org, seed);
+            if(dl.pdf > 0.0f)
+            {
+              const float phasePdf = henyeyGreensteinPdf(dot(wi, dl.direction), vm.scatterAnisotropy);
+              const float misWeight = dl.pdf / (dl.pdf + phasePdf);
+              // reference: throughput * radianceOverPdf * misWeight * phasePdf * shadowFactor
+              P.shC[i] = f4(throughput * dl.radianceOverPdf * misWeight * phasePdf, 0.0f);
+              P.shO[i] = f4(org, dl.distance);
+              P.shD[i] = f4(dl.direction, 0.0f);
+              flags |= PF_SHADOW_VALID | PF_SHADOW_INSIDE;
+            }
+            flags |= PF_POST_VOLUME;
+          }
+          else
+            throughput *= expv((f3(maxExt) - ext) * hitT);
+        }
+        else
+          throughput *= expv(ext * -hitT);
+        if(scattered)
+        {
+          P.rayO[i] = f4(org, coneWidth);
+          P.rayD[i] = f4(normalize(dir), kInfinite);
+          P.thr[i] = f4(throughput, lastSamplePdf);
+          P.rad[i] = f4(radiance, __uint_as_float(scatterBounces));
+          P.misc[i] = f4(misc.x, misc.y, __uint_as_float(flags), __uint_as_float(seed));
+          queuePush(qPost, cntPost, i);
+          continue;
+        }
+      }
+    }
+
+    coneWidth = worldFoot;
+
+    // ---- next-event estimation: one light-or-environment sample, MIS (:316-351) ----
+    const DirectLight directLight = sampleLights(S, F, hit.pos, seed);
+    const bool nextEventValid = (dot(directLight.direction, hit.nrm) > 0.0f || pbrMat.diffuseTransmissionFactor > 0.0f) && directLight.pdf != 0.0f;
+    float3     contribution = f3(0.0f);
+    if(nextEventValid)
+    {
+      const float    a = rnd(seed), b = rnd(seed), c = rnd(seed);
+      const BsdfEval ev = bsdfEvaluate(pbrMat, -dir, directLight.direction, f3(a, b, c));
+      if(ev.pdf > 0.0f)
+      {
+        const float  misWeight = (directLight.pdf == kDirac) ? 1.0f : directLight.pdf / (directLight.pdf + ev.pdf);
+        const float3 w = throughput * directLight.radianceOverPdf * misWeight;
+        contribution += w * ev.bsdf_diffuse;
+        contribution += w * ev.bsdf_glossy;
+      }
+    }
+
+    // ---- BSDF sampling: next direction + throughput (:357-416) ----
+    {
+      const float      a = rnd(seed), b = rnd(seed), c = rnd(seed);
+      const BsdfSample sd = bsdfSample(pbrMat, -dir, f3(a, b, c));
+      throughput *= sd.bsdf_over_pdf;
+      dir = sd.k2;
+      lastSamplePdf = sd.pdf;
+      if(sd.event_type != BSDF_EVENT_ABSORB)
+      {
+        const float3 offsetDir = dot(dir, hit.geonrm) > 0 ? hit.geonrm : -hit.geonrm;
+        org = safeOffsetRay(hit.pos, offsetDir);
+        if(sd.event_type & BSDF_EVENT_TRANSMISSION)
+        {
+          flags ^= PF_INSIDE;
+          if(flags & PF_INSIDE)
+            med = packMedium(makeVolumeMedium(pbrMat), med.w >> 16);
+        }
+      }
+      else
+        depth = (uint32_t)F.pc.maxDepth;
+    }
+
+    // ---- shadow ray for the delayed NEE visibility test (:418-426) ----
+    if(nextEventValid)
+    {
+      const bool   forward = dot(directLight.direction, hit.nrm) > 0.0f;
+      const float3 sDir = forward ? hit.geonrm : -hit.geonrm;
+      const float3 sBase = forward ? hit.shadowPos : hit.pos;
+      P.shO[i] = f4(safeOffsetRay(sBase, sDir), directLight.distance);
+      P.shD[i] = f4(directLight.direction, 0.0f);
+      P.shC[i] = f4(contribution, 0.0f);
+      flags |= PF_SHADOW_VALID;
+    }
+
+    flags = (flags & ~PF_DEPTH_MASK) | (depth & PF_DEPTH_MASK);
+    P.rayO[i] = f4(org, coneWidth);
+    P.rayD[i] = f4(normalize(dir), kInfinite);
+    P.thr[i] = f4(throughput, lastSamplePdf);
+    P.rad[i] = f4(radiance, __uint_as_float(scatterBounces));
+    P.misc[i] = f4(misc.x, misc.y, __uint_as_float(flags), __uint_as_float(seed));
+    P.medium[i] = med;
+    queuePush(qPost, cntPost, i);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_post(PathState P, DevScene S, const __grid_constant__ FrameParams F, const uint32_t* __restrict__ q,
+                                              const uint32_t* __restrict__ cntIn, uint32_t* qNext, uint32_t* cntNext, DevStats* stats)
+{
+  const uint32_t count = *cntIn;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for(uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
+  {
+    const uint32_t i = q[k];
+    float4         misc = P.misc[i];
+    uint32_t       flags = __float_as_uint(misc.z);
+    uint32_t       seed = __float_as_uint(misc.w);
+    float4         rad4 = P.rad[i];
+    float3         radiance = xyz(rad4);
+    bool           radDirty = false;
+    if(flags & PF_SHADOW_VALID)
+    {
+      const float4 so = P.shO[i];
+      const float4 sdv = P.shD[i];
+      const float3 T = traceShadow(S, xyz(so), xyz(sdv), so.w, seed, (flags & PF_SHADOW_INSIDE) != 0, stats);
+      radiance += xyz(P.shC[i]) * T;
+      radDirty = true;
+      statAdd(&stats->shadowRays, 1ull);
+    }
+    float4   thr4 = P.thr[i];
+    float3   throughput = xyz(thr4);
+    uint32_t depth = flags & PF_DEPTH_MASK;
+    bool     alive = true;
+    bool     thrDirty = false;
+    if(flags & PF_POST_VOLUME)
+    {
+      // in-volume Russian roulette only after VOLUME_FREE_BUDGET scatters (pathtrace_functions.h.slang:925-931)
+      if(__float_as_uint(rad4.w) >= 64u)
+      {
+        const float rrPcont = fminf(maxc(throughput) + 0.001f, 0.95f);
+        if(rnd(seed) >= rrPcont)
+          alive = false;
+        else
+        {
+          throughput /= rrPcont;
+          thrDirty = true;
+        }
+      }
+    }
+    else
+    {
+      // surface Russian roulette from depth 3 (gltf_pathtrace.slang:476-485)
+      if(depth >= 3u)
+      {
+        const float rrPcont = fminf(maxc(throughput) + 0.001f, 0.95f);
+        if(rnd(seed) >= rrPcont)
+          alive = false;
+        else
+        {
+          throughput /= rrPcont;
+          thrDirty = true;
+        }
+      }
+      if(alive)
+      {
+        depth++;
+        if((int)depth >= F.pc.maxDepth)
+          alive = false;
+      }
+    }
+    if(!alive)
+    {
+      finalizeSample(P, F, i, radiance, (flags & PF_SOLID) != 0, seed, P.medium[i].w >> 16, qNext, cntNext, stats);
+      continue;
+    }
+    flags = (flags & ~(PF_DEPTH_MASK | PF_POST_VOLUME | PF_SHADOW_VALID | PF_SHADOW_INSIDE)) | (depth & PF_DEPTH_MASK);
+    if(radDirty)
+      P.rad[i] = f4(radiance, rad4.w);
+    if(thrDirty)
+      P.thr[i] = f4(throughput, thr4.w);
+    P.misc[i] = f4(misc.x, misc.y, __uint_as_float(flags), __uint_as_float(seed));
+    queuePush(qNext, cntNext, i);
+  }
+}
+
+// processPixel tail: mean over the frame's samples + running mean over frames (gltf_pathtrace.slang:596,619-630)
+__global__ void __launch_bounds__(256) k_accumulate(PathState P, const __grid_constant__ FrameParams F, float4* __restrict__ accum)
+{
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < F.numPaths; i += stride)
+  {
+    const float4 c = P.pixSum[i] / (float)F.pc.numSamples;
+    if(F.pc.flags & B200PT_PT_FIRST_FRAME)
+      accum[i] = c;
+    else
+    {
+      const float  total = (float)F.pc.totalSamples, n = (float)F.pc.numSamples;
+      const float  after = (float)(F.pc.totalSamples + F.pc.numSamples);
+      const float4 old = accum[i];
+      accum[i] = f4((old.x * total + c.x * n) / after, (old.y * total + c.y * n) / after, (old.z * total + c.z * n) / after, (old.w * total + c.w * n) / after);
+    }
+  }
+}
+
+// ---- ray-level kernels (parity tests / traversal micro-benchmark) ---------------------------------
+__global__ void __launch_bounds__(128) k_trace_rays(DevScene S, const float4* __restrict__ rays, uint32_t n, float* __restrict__ hits, uint32_t* seeds, DevStats* stats)
+{
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    const float4   o = rays[i * 2], d = rays[i * 2 + 1];
+    uint32_t       seed = seeds ? seeds[i] : 0u;
+    const TraceHit h = traceClosest(S, xyz(o), xyz(d), o.w, d.w, seed, stats);
+    if(seeds)
+      seeds[i] = seed;
+    float* out = hits + (size_t)i * 6;
+    int    rnode = -1, rprim = -1, primId = -1;
+    float  t = kInfinite, u = 0.f, v = 0.f;
+    if(h.slot != 0xFFFFFFFFu)
+    {
+      const uint2 meta = S.triMeta[h.slot];
+      rnode = (int)(meta.x & 0x0fffffffu);
+      rprim = S.nodes[rnode].renderPrimID;
+      primId = (int)meta.y;
+      t = h.t;
+      u = h.u;
+      v = h.v;
+    }
+    out[0] = t;
+    out[1] = __int_as_float(rnode);
+    out[2] = __int_as_float(rprim);
+    out[3] = __int_as_float(primId);
+    out[4] = u;
+    out[5] = v;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_shadow_rays(DevScene S, const float4* __restrict__ rays, uint32_t n, float* __restrict__ out, uint32_t* seeds, DevStats* stats)
+{
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    const float4 o = rays[i * 2], d = rays[i * 2 + 1];
+    uint32_t     seed = seeds ? seeds[i] : 0u;
+    const float3 T = traceShadow(S, xyz(o), xyz(d), d.w, seed, false, stats);
+    if(seeds)
+      seeds[i] = seed;
+    out[i * 3] = T.x;
+    out[i * 3 + 1] = T.y;
+    out[i * 3 + 2] = T.z;
+  }
+}
+
+// packing of the BSDF test records: vk_gltf_renderer_b200/bsdf_io.py
+__device__ PbrMaterial unpackTestMaterial(const float* p)
+{
+  PbrMaterial m;
+  m.baseColor = f3(p[0], p[1], p[2]);
+  m.opacity = 1.0f;
+  m.roughness = f2(p[3], p[4]);
+  m.metallic = p[5];
+  m.emissive = f3(0.0f);
+  m.N = f3(p[6], p[7], p[8]);
+  m.T = f3(p[9], p[10], p[11]);
+  m.B = f3(p[12], p[13], p[14]);
+  m.Ng = f3(p[15], p[16], p[17]);
+  m.ior1 = p[18];
+  m.ior2 = p[19];
+  m.specular = p[20];
+  m.specularColor = f3(p[21], p[22], p[23]);
+  m.transmission = p[24];
+  m.attenuationColor = f3(1.0f);
+  m.attenuationDistance = 1.0f;
+  m.thickness = p[25];
+  m.clearcoat = p[26];
+  m.clearcoatRoughness = p[27];
+  m.Nc = m.N;
+  m.iridescence = p[28];
+  m.iridescenceIor = p[29];
+  m.iridescenceThickness = p[30];
+  m.sheenColor = f3(p[31], p[32], p[33]);
+  m.sheenRoughness = p[34];
+  m.diffuseTransmissionFactor = p[35];
+  m.diffuseTransmissionColor = f3(p[36], p[37], p[38]);
+  m.scatterCoefficient = f3(0.0f);
+  m.scatterAnisotropy = 0.0f;
+  return m;
+}
+
+__global__ void k_bsdf_eval(const float* __restrict__ in, uint32_t n, float* __restrict__ out)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n)
+    return;
+  const float*      p = in + (size_t)i * 48;
+  const PbrMaterial m = unpackTestMaterial(p);
+  const BsdfEval    d = bsdfEvaluate(m, f3(p[39], p[40], p[41]), f3(p[42], p[43], p[44]), f3(p[45], p[46], p[47]));
+  float*            q = out + (size_t)i * 8;
+  q[0] = d.bsdf_diffuse.x;
+  q[1] = d.bsdf_diffuse.y;
+  q[2] = d.bsdf_diffuse.z;
+  q[3] = d.bsdf_glossy.x;
+  q[4] = d.bsdf_glossy.y;
+  q[5] = d.bsdf_glossy.z;
+  q[6] = d.pdf;
+  q[7] = 0.f;
+}
+
+__global__ void k_bsdf_sample(const float* __restrict__ in, uint32_t n, float* __restrict__ out)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n)
+    return;
+  const float*      p = in + (size_t)i * 48;
+  const PbrMaterial m = unpackTestMaterial(p);
+  const BsdfSample  d = bsdfSample(m, f3(p[39], p[40], p[41]), f3(p[45], p[46], p[47]));
+  float*            q = out + (size_t)i * 8;
+  q[0] = d.k2.x;
+  q[1] = d.k2.y;
+  q[2] = d.k2.z;
+  q[3] = d.bsdf_over_pdf.x;
+  q[4] = d.bsdf_over_pdf.y;
+  q[5] = d.bsdf_over_pdf.z;
+  q[6] = d.pdf;
+  q[7] = (float)d.event_type;
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+struct TexRes
+{
+  cudaMipmappedArray_t arr = nullptr;
+  cudaTextureObject_t  obj = 0;
+};
+
+}  // namespace
+
+struct b200pt
+{
+  int          device = 0;
+  cudaStream_t stream = nullptr;
+  std::string  err;
+  int          numSMs = 148;
+
+  // scene
+  std::vector<void*>  sceneAllocs;
+  std::vector<TexRes> texRes;
+  DevScene            S{};
+  bool                haveScene = false;
+  bool                hasVolume = false;
+  uint64_t            nodeBytes = 0, triBytes = 0;
+  uint32_t            numNodes = 0, numTris = 0;
+
+  // env
+  float4* dEnv = nullptr;
+  uint2*  dEnvAccel = nullptr;
+  bool    haveEnv = false;
+
+  // framebuffer + path pool
+  int                width = 0, height = 0, tileY0 = 0, tileRows = 0;
+  uint32_t           numPaths = 0;
+  float4*            dAccumOwned = nullptr;
+  float4*            dAccum = nullptr;
+  PathState          P{};
+  std::vector<void*> poolAllocs;
+  uint32_t *         dQ[3] = {nullptr, nullptr, nullptr}, *dCounters = nullptr;
+  uint32_t*          hCount = nullptr;  // pinned
+  DevStats*          dStats = nullptr;
+
+  // stats / profiling
+  bool         profiling = false;
+  double       msTrace = 0, msShadow = 0, msShade = 0, msOther = 0, msTotal = 0;
+  uint64_t     kernelLaunches = 0;
+  cudaEvent_t  ev[2] = {nullptr, nullptr};
+};
+
+namespace {
+
+#define CK(call)                                                                                                                            \
+  do                                                                                                                                        \
+  {                                                                                                                                         \
+    cudaError_t e__ = (call);                                                                                                               \
+    if(e__ != cudaSuccess)                                                                                                                  \
+    {                                                                                                                                       \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e__);                                                                         \
+      return B200PT_E_CUDA;                                                                                                                 \
+    }                                                                                                                                       \
+  } while(0)
+
+template <typename T>
+int upload(b200pt* h, std::vector<void*>& owner, const T* src, size_t count, T** out)
+{
+  *out = nullptr;
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  void*        d = nullptr;
+  CK(cudaMalloc(&d, bytes));
+  owner.push_back(d);
+  if(count)
+    CK(cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  else
+    CK(cudaMemsetAsync(d, 0, bytes, h->stream));
+  *out = (T*)d;
+  return 0;
+}
+
+void freeScene(b200pt* h)
+{
+  for(auto& t : h->texRes)
+  {
+    if(t.obj)
+      cudaDestroyTextureObject(t.obj);
+    if(t.arr)
+      cudaFreeMipmappedArray(t.arr);
+  }
+  h->texRes.clear();
+  for(void* p : h->sceneAllocs)
+    cudaFree(p);
+  h->sceneAllocs.clear();
+  h->haveScene = false;
+}
+
+void freePool(b200pt* h)
+{
+  for(void* p : h->poolAllocs)
+    cudaFree(p);
+  h->poolAllocs.clear();
+  h->dAccumOwned = nullptr;
+}
+
+float srgbToLinear(float c) { return (c <= 0.04045f) ? c / 12.92f : powf((c + 0.055f) / 1.055f, 2.4f); }
+float linearToSrgb(float c) { return (c <= 0.0031308f) ? c * 12.92f : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f; }
+
+// mip chain like the reference's vkCmdBlitImage(VK_FILTER_LINEAR) loop (src/gltf_scene_vk.cpp:1254-1332):
+// every level is the linear-filtered half-size copy of the previous 8-bit level (sRGB images are
+// filtered in linear light and re-encoded).
+void downsample(const std::vector<uint8_t>& src, int w, int h, bool srgb, std::vector<uint8_t>& dst, int nw, int nh)
+{
+  dst.resize((size_t)nw * nh * 4);
+  std::vector<float> lin((size_t)w * h * 4);
+  for(size_t i = 0; i < (size_t)w * h; i++)
+    for(int c = 0; c < 4; c++)
+    {
+      float v = src[i * 4 + c] / 255.0f;
+      lin[i * 4 + c] = (srgb && c < 3) ? srgbToLinear(v) : v;
+    }
+  for(int y = 0; y < nh; y++)
+    for(int x = 0; x < nw; x++)
+    {
+      const float sx = (x + 0.5f) * (float)w / (float)nw - 0.5f;
+      const float sy = (y + 0.5f) * (float)h / (float)nh - 0.5f;
+      int         x0 = (int)floorf(sx), y0 = (int)floorf(sy);
+      const float fx = sx - x0, fy = sy - y0;
+      const int   x1 = std::min(x0 + 1, w - 1), y1 = std::min(y0 + 1, h - 1);
+      x0 = std::max(x0, 0);
+      y0 = std::max(y0, 0);
+      for(int c = 0; c < 4; c++)
+      {
+        const float a = lin[((size_t)y0 * w + x0) * 4 + c], b = lin[((size_t)y0 * w + x1) * 4 + c];
+        const float cc = lin[((size_t)y1 * w + x0) * 4 + c], d = lin[((size_t)y1 * w + x1) * 4 + c];
+        float       v = (a * (1 - fx) + b * fx) * (1 - fy) + (cc * (1 - fx) + d * fx) * fy;
+        if(srgb && c < 3)
+          v = linearToSrgb(v);
+        dst[((size_t)y * nw + x) * 4 + c] = (uint8_t)std::min(255.0f, std::max(0.0f, floorf(v * 255.0f + 0.5f)));
+      }
+    }
+}
+
+cudaTextureAddressMode addressMode(int gl)
+{
+  if(gl == 33071)
+    return cudaAddressModeClamp;
+  if(gl == 33648)
+    return cudaAddressModeMirror;
+  return cudaAddressModeWrap;
+}
+
+int createTexture(b200pt* h, const b200pt_texture& src, TexRes& out, DevTex& dev)
+{
+  int w = src.width, hh = src.height;
+  if(w <= 0 || hh <= 0 || !src.rgba8)
+  {
+    h->err = "texture without pixels";
+    return B200PT_E_INVALID;
+  }
+  int levels = 1;
+  for(int m = std::max(w, hh); m > 1; m >>= 1)
+    levels++;
+  cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+  CK(cudaMallocMipmappedArray(&out.arr, &fmt, make_cudaExtent((size_t)w, (size_t)hh, 0), (unsigned)levels));
+  std::vector<uint8_t> cur(src.rgba8, src.rgba8 + (size_t)w * hh * 4), nxt;
+  for(int l = 0; l < levels; l++)
+  {
+    cudaArray_t la;
+    CK(cudaGetMipmappedArrayLevel(&la, out.arr, (unsigned)l));
+    CK(cudaMemcpy2DToArray(la, 0, 0, cur.data(), (size_t)w * 4, (size_t)w * 4, (size_t)hh, cudaMemcpyHostToDevice));
+    if(l + 1 < levels)
+    {
+      const int nw = std::max(1, w / 2), nh = std::max(1, hh / 2);
+      downsample(cur, w, hh, src.srgb != 0, nxt, nw, nh);
+      cur.swap(nxt);
+      w = nw;
+      hh = nh;
+    }
+  }
+  cudaResourceDesc rd{};
+  rd.resType = cudaResourceTypeMipmappedArray;
+  rd.res.mipmap.mipmap = out.arr;
+  cudaTextureDesc td{};
+  td.addressMode[0] = addressMode(src.wrapS);
+  td.addressMode[1] = addressMode(src.wrapT);
+  // sampler quirks kept from getSampler (src/gltf_scene_vk.cpp:909-947): one filter object; mip mode follows magFilter
+  const bool magLinear = (src.magFilter != 9728);
+  td.filterMode = magLinear ? cudaFilterModeLinear : cudaFilterModePoint;
+  td.mipmapFilterMode = magLinear ? cudaFilterModeLinear : cudaFilterModePoint;
+  td.readMode = cudaReadModeNormalizedFloat;
+  td.sRGB = src.srgb ? 1 : 0;
+  td.normalizedCoords = 1;
+  td.maxAnisotropy = 1;
+  td.minMipmapLevelClamp = 0.f;
+  td.maxMipmapLevelClamp = (float)(levels - 1);
+  CK(cudaCreateTextureObject(&out.obj, &rd, &td, nullptr));
+  dev.obj = out.obj;
+  dev.w = (float)src.width;
+  dev.h = (float)src.height;
+  dev.maxLevel = (float)(levels - 1);
+  dev.mipLinear = magLinear ? 1 : 0;
+  return 0;
+}
+
+int gridFor(const b200pt* h, int perSM) { return h->numSMs * perSM; }
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int b200pt_abi_version(void) { return B200PT_ABI_VERSION; }
+
+int b200pt_create(b200pt_t** out, int cuda_device)
+{
+  if(!out)
+    return B200PT_E_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if(cudaGetDeviceCount(&n) != cudaSuccess || cuda_device < 0 || cuda_device >= n)
+    return B200PT_E_CUDA;
+  b200pt* h = new b200pt();
+  h->device = cuda_device;
+  if(cudaSetDevice(cuda_device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+  {
+    delete h;
+    return B200PT_E_CUDA;
+  }
+  cudaDeviceProp prop{};
+  cudaGetDeviceProperties(&prop, cuda_device);
+  h->numSMs = prop.multiProcessorCount;
+  cudaMalloc((void**)&h->dStats, sizeof(DevStats));
+  cudaMemset(h->dStats, 0, sizeof(DevStats));
+  cudaMalloc((void**)&h->dCounters, sizeof(uint32_t) * 2 * kMaxIters);
+  cudaMallocHost((void**)&h->hCount, sizeof(uint32_t) * 4);
+  cudaEventCreate(&h->ev[0]);
+  cudaEventCreate(&h->ev[1]);
+  *out = h;
+  return B200PT_OK;
+}
+
+void b200pt_destroy(b200pt_t* h)
+{
+  if(!h)
+    return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  freeScene(h);
+  freePool(h);
+  if(h->dEnv)
+    cudaFree(h->dEnv);
+  if(h->dEnvAccel)
+    cudaFree(h->dEnvAccel);
+  cudaFree(h->dStats);
+  cudaFree(h->dCounters);
+  cudaFreeHost(h->hCount);
+  cudaEventDestroy(h->ev[0]);
+  cudaEventDestroy(h->ev[1]);
+  cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* b200pt_last_error(const b200pt_t* h) { return h ? h->err.c_str() : "null handle"; }
+
+void* b200pt_stream(b200pt_t* h) { return h ? (void*)h->stream : nullptr; }
+
+int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
+{
+  if(!h || !s || s->numMaterials == 0 || (s->numRenderNodes && (!s->renderNodes || !s->renderPrimitives)))
+  {
+    if(h)
+      h->err = "b200pt_set_scene: invalid scene description";
+    return B200PT_E_INVALID;
+  }
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  freeScene(h);
+  DevScene& S = h->S;
+  S = DevScene{};
+  S.envRgba = h->dEnv;
+  S.envAccel = h->dEnvAccel;
+
+  // --- AoS tables: same bytes as the reference SSBOs ---
+  b200pt_render_node*    dNodes;
+  b200pt_shade_material* dMats;
+  b200pt_texture_info*   dTi;
+  b200pt_light*          dLights;
+  int                    rc;
+  if((rc = upload(h, h->sceneAllocs, s->renderNodes, s->numRenderNodes, &dNodes)))
+    return rc;
+  if((rc = upload(h, h->sceneAllocs, s->materials, s->numMaterials, &dMats)))
+    return rc;
+  if((rc = upload(h, h->sceneAllocs, s->textureInfos, s->numTextureInfos, &dTi)))
+    return rc;
+  if((rc = upload(h, h->sceneAllocs, s->lights, s->numLights, &dLights)))
+    return rc;
+  S.nodes = dNodes;
+  S.mats = dMats;
+  S.texInfos = dTi;
+  S.lights = dLights;
+  S.numLights = (int)s->numLights;
+
+  // --- vertex data: separate attribute arrays per primitive, as SceneVk::createVertexBuffers ---
+  std::vector<DevPrim> prims(s->numRenderPrimitives);
+  for(uint32_t i = 0; i < s->numRenderPrimitives; i++)
+  {
+    const b200pt_render_primitive& p = s->renderPrimitives[i];
+    DevPrim&                       d = prims[i];
+    uint32_t*                      di;
+    float*                         df;
+    if((rc = upload(h, h->sceneAllocs, p.indices, (size_t)p.triangleCount * 3, &di)))
+      return rc;
+    d.idx = di;
+    if((rc = upload(h, h->sceneAllocs, p.positions, (size_t)p.vertexCount * 3, &df)))
+      return rc;
+    d.pos = df;
+    d.nrm = d.tan = d.uv0 = d.uv1 = nullptr;
+    d.col = nullptr;
+    if(p.normals)
+    {
+      if((rc = upload(h, h->sceneAllocs, p.normals, (size_t)p.vertexCount * 3, &df)))
+        return rc;
+      d.nrm = df;
+    }
+    if(p.tangents)
+    {
+      if((rc = upload(h, h->sceneAllocs, p.tangents, (size_t)p.vertexCount * 4, &df)))
+        return rc;
+      d.tan = df;
+    }
+    if(p.texCoords[0])
+    {
+      if((rc = upload(h, h->sceneAllocs, p.texCoords[0], (size_t)p.vertexCount * 2, &df)))
+        return rc;
+      d.uv0 = df;
+    }
+    if(p.texCoords[1])
+    {
+      if((rc = upload(h, h->sceneAllocs, p.texCoords[1], (size_t)p.vertexCount * 2, &df)))
+        return rc;
+      d.uv1 = df;
+    }
+    if(p.colors)
+    {
+      if((rc = upload(h, h->sceneAllocs, p.colors, (size_t)p.vertexCount, &di)))
+        return rc;
+      d.col = di;
+    }
+  }
+  DevPrim* dPrims;
+  if((rc = upload(h, h->sceneAllocs, prims.data(), prims.size(), &dPrims)))
+    return rc;
+  S.prims = dPrims;
+
+  // --- textures ---
+  std::vector<DevTex> devTex(s->numTextures);
+  h->texRes.resize(s->numTextures);
+  for(uint32_t i = 0; i < s->numTextures; i++)
+    if((rc = createTexture(h, s->textures[i], h->texRes[i], devTex[i])))
+      return rc;
+  DevTex* dTex;
+  if((rc = upload(h, h->sceneAllocs, devTex.data(), devTex.size(), &dTex)))
+    return rc;
+  S.textures = dTex;
+  S.numTextures = (int)s->numTextures;
+
+  // --- flatten instances to world space + build the wide BVH (TLAS/BLAS replacement) ---
+  std::vector<FlatTri> flat;
+  bool                 allOpaque = true;
+  h->hasVolume = false;
+  for(uint32_t n = 0; n < s->numRenderNodes; n++)
+  {
+    if(s->renderNodeVisible && !s->renderNodeVisible[n])
+      continue;
+    const b200pt_render_node& node = s->renderNodes[n];
+    if(node.renderPrimID < 0 || (uint32_t)node.renderPrimID >= s->numRenderPrimitives)
+    {
+      h->err = "render node references a missing primitive";
+      return B200PT_E_INVALID;
+    }
+    const b200pt_render_primitive& p = s->renderPrimitives[node.renderPrimID];
+    const b200pt_shade_material&   m = s->materials[std::min<uint32_t>((uint32_t)std::max(0, node.materialID), s->numMaterials - 1)];
+    uint32_t                       flags = 0;
+    if(m.transmissionFactor == 0.0f && m.alphaMode == 0 && m.diffuseTransmissionFactor == 0.0f)
+      flags |= TRI_OPAQUE;
+    else
+      allOpaque = false;
+    if(m.doubleSided == 1 || m.thicknessFactor > 0.0f || m.transmissionFactor > 0.0f)
+      flags |= TRI_NOCULL;
+    if(m.thicknessFactor > 0.0f)
+      h->hasVolume = true;
+    const float* a = node.objectToWorld;
+    const float  det = a[0] * (a[5] * a[10] - a[9] * a[6]) - a[4] * (a[1] * a[10] - a[9] * a[2]) + a[8] * (a[1] * a[6] - a[5] * a[2]);
+    const bool   mirrored = det < 0.0f;
+    for(uint32_t t = 0; t < p.triangleCount; t++)
+    {
+      float3 v[3];
+      for(int k = 0; k < 3; k++)
+      {
+        const uint32_t vi = p.indices[t * 3 + k];
+        v[k] = xfPoint(a, f3(p.positions[vi * 3], p.positions[vi * 3 + 1], p.positions[vi * 3 + 2]));
+      }
+      FlatTri T;
+      T.rnode = n;
+      T.prim = t;
+      T.flags = flags;
+      if(mirrored)
+      {
+        std::swap(v[1], v[2]);
+        T.flags |= TRI_FLIPPED;
+      }
+      const float3 e1 = v[1] - v[0], e2 = v[2] - v[0];
+      T.v0[0] = v[0].x, T.v0[1] = v[0].y, T.v0[2] = v[0].z;
+      T.e1[0] = e1.x, T.e1[1] = e1.y, T.e1[2] = e1.z;
+      T.e2[0] = e2.x, T.e2[1] = e2.y, T.e2[2] = e2.z;
+      flat.push_back(T);
+    }
+  }
+  WideBvh bvh;
+  buildWideBvh(flat, bvh);
+  float *   dNodesBvh, *dTris;
+  uint32_t* dMeta;
+  if((rc = upload(h, h->sceneAllocs, bvh.nodes.data(), bvh.nodes.size(), &dNodesBvh)))
+    return rc;
+  if((rc = upload(h, h->sceneAllocs, bvh.tris.data(), bvh.tris.size(), &dTris)))
+    return rc;
+  if((rc = upload(h, h->sceneAllocs, bvh.triMeta.data(), bvh.triMeta.size(), &dMeta)))
+    return rc;
+  S.bvh.nodes = reinterpret_cast<const float4*>(dNodesBvh);
+  S.bvh.tris = reinterpret_cast<const float4*>(dTris);
+  S.triMeta = reinterpret_cast<const uint2*>(dMeta);
+  S.allOpaque = allOpaque ? 1 : 0;
+  h->nodeBytes = bvh.nodes.size() * sizeof(float);
+  h->triBytes = bvh.tris.size() * sizeof(float);
+  h->numNodes = bvh.numNodes;
+  h->numTris = bvh.numTris;
+  CK(cudaStreamSynchronize(h->stream));
+  h->haveScene = true;
+  return B200PT_OK;
+}
+
+int b200pt_bvh_info(b200pt_t* h, uint64_t* node_bytes, uint64_t* tri_bytes, uint32_t* num_nodes, uint32_t* num_tris)
+{
+  if(!h || !h->haveScene)
+    return B200PT_E_INVALID;
+  if(node_bytes)
+    *node_bytes = h->nodeBytes;
+  if(tri_bytes)
+    *tri_bytes = h->triBytes;
+  if(num_nodes)
+    *num_nodes = h->numNodes;
+  if(num_tris)
+    *num_tris = h->numTris;
+  return B200PT_OK;
+}
+
+int b200pt_set_environment(b200pt_t* h, const float* rgb, int w, int hh, float* integral_out)
+{
+  if(!h || !rgb || w <= 0 || hh <= 0)
+    return B200PT_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  const size_t n = (size_t)w * hh;
+  // importance = texel solid angle * max(r,g,b); Vose alias table; pdf stored in alpha
+  // (nvvk::HdrIbl, external to the reference tree; call site src/renderer.cpp:1994-1996)
+  std::vector<float>  rgba(n * 4), importance(n), q(n);
+  std::vector<uint32_t> alias(n);
+  const float         stepPhi = kTwoPi / (float)w, stepTheta = kPi / (float)hh;
+  for(int y = 0; y < hh; y++)
+  {
+    const float theta0 = (float)y * stepTheta, theta1 = (float)(y + 1) * stepTheta;
+    const float area = (cosf(theta0) - cosf(theta1)) * stepPhi;
+    for(int x = 0; x < w; x++)
+    {
+      const size_t i = (size_t)y * w + x;
+      const float  r = rgb[i * 3], g = rgb[i * 3 + 1], b = rgb[i * 3 + 2];
+      rgba[i * 4] = r;
+      rgba[i * 4 + 1] = g;
+      rgba[i * 4 + 2] = b;
+      importance[i] = area * std::max(r, std::max(g, b));
+    }
+  }
+  float sum = 0.f;
+  for(float d : importance)
+    sum += d;
+  const float average = sum / (float)n;
+  for(size_t i = 0; i < n; i++)
+  {
+    q[i] = importance[i] / average;
+    alias[i] = (uint32_t)i;
+  }
+  {
+    std::vector<uint32_t> part(n);
+    uint32_t              s = 0u, large = (uint32_t)n;
+    for(uint32_t i = 0; i < (uint32_t)n; ++i)
+    {
+      if(q[i] < 1.f)
+        part[s++] = i;
+      else
+        part[--large] = i;
+    }
+    for(s = 0; s < large && large < (uint32_t)n; ++s)
+    {
+      const uint32_t j = part[s], k = part[large];
+      alias[j] = k;
+      const float diff = 1.f - q[j];
+      q[k] -= diff;
+      if(q[k] < 1.0f)
+        large++;
+    }
+  }
+  const float inv = 1.0f / sum;
+  for(size_t i = 0; i < n; i++)
+    rgba[i * 4 + 3] = std::max(rgba[i * 4], std::max(rgba[i * 4 + 1], rgba[i * 4 + 2])) * inv;
+  std::vector<uint32_t> accel(n * 2);
+  for(size_t i = 0; i < n; i++)
+  {
+    accel[i * 2] = alias[i];
+    memcpy(&accel[i * 2 + 1], &q[i], 4);
+  }
+  if(h->dEnv)
+    cudaFree(h->dEnv);
+  if(h->dEnvAccel)
+    cudaFree(h->dEnvAccel);
+  h->dEnv = nullptr;
+  h->dEnvAccel = nullptr;
+  CK(cudaMalloc((void**)&h->dEnv, n * sizeof(float4)));
+  CK(cudaMalloc((void**)&h->dEnvAccel, n * sizeof(uint2)));
+  CK(cudaMemcpy(h->dEnv, rgba.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->dEnvAccel, accel.data(), n * sizeof(uint2), cudaMemcpyHostToDevice));
+  h->S.envRgba = h->dEnv;
+  h->S.envAccel = h->dEnvAccel;
+  h->S.envW = w;
+  h->S.envH = hh;
+  h->haveEnv = true;
+  if(integral_out)
+    *integral_out = sum;
+  return B200PT_OK;
+}
+
+int b200pt_resize(b200pt_t* h, int width, int height, int tile_y0, int tile_rows)
+{
+  if(!h || width <= 0 || height <= 0 || tile_y0 < 0 || tile_rows <= 0 || tile_y0 + tile_rows > height)
+  {
+    if(h)
+      h->err = "b200pt_resize: invalid extent / tile";
+    return B200PT_E_INVALID;
+  }
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  freePool(h);
+  h->width = width;
+  h->height = height;
+  h->tileY0 = tile_y0;
+  h->tileRows = tile_rows;
+  h->numPaths = (uint32_t)((size_t)width * tile_rows);
+  const size_t n = h->numPaths;
+  auto         alloc16 = [&](void** p) -> int {
+    CK(cudaMalloc(p, n * 16));
+    h->poolAllocs.push_back(*p);
+    return 0;
+  };
+  int rc = 0;
+  rc |= alloc16((void**)&h->P.rayO);
+  rc |= alloc16((void**)&h->P.rayD);
+  rc |= alloc16((void**)&h->P.hit);
+  rc |= alloc16((void**)&h->P.thr);
+  rc |= alloc16((void**)&h->P.rad);
+  rc |= alloc16((void**)&h->P.misc);
+  rc |= alloc16((void**)&h->P.medium);
+  rc |= alloc16((void**)&h->P.pixSum);
+  rc |= alloc16((void**)&h->P.shO);
+  rc |= alloc16((void**)&h->P.shD);
+  rc |= alloc16((void**)&h->P.shC);
+  rc |= alloc16((void**)&h->dAccumOwned);
+  if(rc)
+    return B200PT_E_NOMEM;
+  for(int k = 0; k < 3; k++)
+  {
+    CK(cudaMalloc((void**)&h->dQ[k], n * sizeof(uint32_t)));
+    h->poolAllocs.push_back(h->dQ[k]);
+  }
+  CK(cudaMemsetAsync(h->dAccumOwned, 0, n * 16, h->stream));
+  h->dAccum = h->dAccumOwned;
+  return B200PT_OK;
+}
+
+int b200pt_set_accum_device(b200pt_t* h, float* dev, size_t num_floats)
+{
+  if(!h || h->numPaths == 0)
+    return B200PT_E_INVALID;
+  if(dev == nullptr)
+  {
+    h->dAccum = h->dAccumOwned;
+    return B200PT_OK;
+  }
+  if(num_floats < (size_t)h->numPaths * 4)
+  {
+    h->err = "b200pt_set_accum_device: buffer too small";
+    return B200PT_E_INVALID;
+  }
+  h->dAccum = reinterpret_cast<float4*>(dev);
+  return B200PT_OK;
+}
+
+int b200pt_get_accum_device(b200pt_t* h, float** dev, size_t* num_floats)
+{
+  if(!h || h->numPaths == 0)
+    return B200PT_E_INVALID;
+  if(dev)
+    *dev = reinterpret_cast<float*>(h->dAccum);
+  if(num_floats)
+    *num_floats = (size_t)h->numPaths * 4;
+  return B200PT_OK;
+}
+
+int b200pt_read_accum(b200pt_t* h, float* host, size_t num_floats)
+{
+  if(!h || h->numPaths == 0 || !host || num_floats < (size_t)h->numPaths * 4)
+    return B200PT_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(host, h->dAccum, (size_t)h->numPaths * 16, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return B200PT_OK;
+}
+
+int b200pt_synchronize(b200pt_t* h)
+{
+  if(!h)
+    return B200PT_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  return B200PT_OK;
+}
+
+int b200pt_set_profiling(b200pt_t* h, int enabled)
+{
+  if(!h)
+    return B200PT_E_INVALID;
+  h->profiling = enabled != 0;
+  return B200PT_OK;
+}
+
+int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_push_constant* pc)
+{
+  if(!h || !fi || !pc)
+    return B200PT_E_INVALID;
+  if(!h->haveScene || h->numPaths == 0)
+  {
+    h->err = "b200pt_render_frame: set_scene and resize must come first";
+    return B200PT_E_INVALID;
+  }
+  if(!(fi->flags & B200PT_SCENE_USE_HDR_ENVIRONMENT) || !h->haveEnv)
+  {
+    h->err = "b200pt_render_frame: only the HDR environment (--envSystem 1) is built; physical sky is out of scope";
+    return B200PT_E_UNSUPPORTED;
+  }
+  if(fi->flags & B200PT_SCENE_USE_INFINITE_PLANE)
+  {
+    h->err = "b200pt_render_frame: infinite plane / shadow catcher is not built";
+    return B200PT_E_UNSUPPORTED;
+  }
+  if(pc->flags & (B200PT_PT_USE_DLSS | B200PT_PT_USE_OPTIX_DENOISER))
+  {
+    h->err = "b200pt_render_frame: denoiser guide variants are out of scope";
+    return B200PT_E_UNSUPPORTED;
+  }
+  if(pc->numSamples < 1 || pc->maxDepth < 0 || (int)fi->imageSize[0] != h->width || (int)fi->imageSize[1] != h->height)
+  {
+    h->err = "b200pt_render_frame: bad numSamples / maxDepth / imageSize";
+    return B200PT_E_INVALID;
+  }
+  CK(cudaSetDevice(h->device));
+  FrameParams F;
+  F.fi = *fi;
+  F.pc = *pc;
+  F.width = h->width;
+  F.height = h->height;
+  F.tileY0 = h->tileY0;
+  F.tileRows = h->tileRows;
+  F.numPaths = h->numPaths;
+
+  cudaStream_t st = h->stream;
+  uint32_t*    cntTrace = h->dCounters;             // [kMaxIters]
+  uint32_t*    cntPost = h->dCounters + kMaxIters;  // [kMaxIters]
+  CK(cudaMemsetAsync(h->dCounters, 0, sizeof(uint32_t) * 2 * kMaxIters, st));
+
+  float tTrace = 0, tShade = 0, tPost = 0, tOther = 0;
+  auto  timed = [&](float& acc, auto&& launch) {
+    if(h->profiling)
+    {
+      cudaEventRecord(h->ev[0], st);
+      launch();
+      cudaEventRecord(h->ev[1], st);
+      cudaEventSynchronize(h->ev[1]);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+      acc += ms;
+    }
+    else
+      launch();
+    h->kernelLaunches++;
+  };
+
+  const int gridWide = gridFor(h, 8);
+  timed(tOther, [&] { k_raygen<<<gridWide, 256, 0, st>>>(h->P, F, h->dQ[0], &cntTrace[0], h->dStats); });
+
+  if(pc->maxDepth > 0)
+  {
+    int       it = 0;
+    int       cur = 0;  // dQ[cur] = trace queue, dQ[2] = post queue, dQ[1-cur] = next queue
+    const int firstBatch = pc->maxDepth;
+    const bool mayOverrun = h->hasVolume || pc->numSamples > 1;
+    int        remaining = firstBatch;
+    for(;;)
+    {
+      for(int k = 0; k < remaining && it < kMaxIters - 1; k++, it++)
+      {
+        uint32_t* qT = h->dQ[cur];
+        uint32_t* qN = h->dQ[1 - cur];
+        timed(tTrace, [&] { k_trace<<<gridFor(h, 8), 128, 0, st>>>(h->P, h->S, qT, &cntTrace[it], h->dStats); });
+        timed(tShade, [&] { k_shade<<<gridFor(h, 8), 128, 0, st>>>(h->P, h->S, F, qT, &cntTrace[it], h->dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats); });
+        timed(tPost, [&] { k_post<<<gridFor(h, 8), 128, 0, st>>>(h->P, h->S, F, h->dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats); });
+        cur = 1 - cur;
+      }
+      if(!mayOverrun)
+        break;
+      CK(cudaMemcpyAsync(h->hCount, &cntTrace[it], sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if(h->hCount[0] == 0)
+        break;
+      if(it >= kMaxIters - 1)
+      {
+        h->err = "b200pt_render_frame: iteration budget exhausted (runaway volume walk?)";
+        return B200PT_E_INVALID;
+      }
+      remaining = 4;
+    }
+  }
+  else
+  {
+    // maxDepth == 0: every sample is black (the while loop never runs)
+  }
+  timed(tOther, [&] { k_accumulate<<<gridWide, 256, 0, st>>>(h->P, F, h->dAccum); });
+  CK(cudaGetLastError());
+  if(h->profiling)
+  {
+    h->msTrace += tTrace;
+    h->msShade += tShade;
+    h->msShadow += tPost;
+    h->msOther += tOther;
+    h->msTotal += tTrace + tShade + tPost + tOther;
+  }
+  return B200PT_OK;
+}
+
+int b200pt_get_stats(b200pt_t* h, b200pt_stats* out)
+{
+  if(!h || !out)
+    return B200PT_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  DevStats d{};
+  CK(cudaMemcpy(&d, h->dStats, sizeof(d), cudaMemcpyDeviceToHost));
+  out->closestRays = d.closestRays;
+  out->shadowRays = d.shadowRays;
+  out->shadedHits = d.shadedHits;
+  out->pathsStarted = d.pathsStarted;
+  out->nodesVisited = d.nodesVisited;
+  out->trisTested = d.trisTested;
+  out->msTraceClosest = h->msTrace;
+  out->msTraceShadow = h->msShadow;
+  out->msShade = h->msShade;
+  out->msOther = h->msOther;
+  out->msTotal = h->msTotal;
+  out->kernelLaunches = h->kernelLaunches;
+  return B200PT_OK;
+}
+
+int b200pt_reset_stats(b200pt_t* h)
+{
+  if(!h)
+    return B200PT_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemset(h->dStats, 0, sizeof(DevStats)));
+  h->msTrace = h->msShadow = h->msShade = h->msOther = h->msTotal = 0;
+  h->kernelLaunches = 0;
+  return B200PT_OK;
+}
+
+int b200pt_trace_closest(b200pt_t* h, const float* dev_rays, uint32_t n, float* dev_hits, uint32_t* dev_seeds)
+{
+  if(!h || !h->haveScene || !dev_rays || !dev_hits)
+    return B200PT_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  if(n)
+    k_trace_rays<<<gridFor(h, 8), 128, 0, h->stream>>>(h->S, reinterpret_cast<const float4*>(dev_rays), n, dev_hits, dev_seeds, h->dStats);
+  CK(cudaGetLastError());
+  h->kernelLaunches++;
+  return B200PT_OK;
+}
+
+int b200pt_trace_shadow(b200pt_t* h, const float* dev_rays, uint32_t n, float* dev_transmission, uint32_t* dev_seeds)
+{
+  if(!h || !h->haveScene || !dev_rays || !dev_transmission)
+    return B200PT_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  if(n)
+    k_shadow_rays<<<gridFor(h, 8), 128, 0, h->stream>>>(h->S, reinterpret_cast<const float4*>(dev_rays), n, dev_transmission, dev_seeds, h->dStats);
+  CK(cudaGetLastError());
+  h->kernelLaunches++;
+  return B200PT_OK;
+}
+
+int b200pt_bsdf_eval(b200pt_t* h, const float* dev_in, uint32_t n, float* dev_out)
+{
+  if(!h || !dev_in || !dev_out)
+    return B200PT_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  if(n)
+    k_bsdf_eval<<<(n + 127) / 128, 128, 0, h->stream>>>(dev_in, n, dev_out);
+  CK(cudaGetLastError());
+  return B200PT_OK;
+}
+
+int b200pt_bsdf_sample(b200pt_t* h, const float* dev_in, uint32_t n, float* dev_out)
+{
+  if(!h || !dev_in || !dev_out)
+    return B200PT_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  if(n)
+    k_bsdf_sample<<<(n + 127) / 128, 128, 0, h->stream>>>(dev_in, n, dev_out);
+  CK(cudaGetLastError());
+  return B200PT_OK;
+}
+
+}  // extern "C"

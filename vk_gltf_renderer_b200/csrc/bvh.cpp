@@ -1,0 +1,429 @@
+// bvh.cpp — SAH BVH2 (binned) -> 8-wide collapse -> compressed wide nodes.  See bvh.h.
+#include "bvh.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+namespace pt {
+namespace {
+
+struct Box
+{
+  float lo[3], hi[3];
+  void  reset()
+  {
+    for(int a = 0; a < 3; a++)
+    {
+      lo[a] = FLT_MAX;
+      hi[a] = -FLT_MAX;
+    }
+  }
+  void grow(const Box& b)
+  {
+    for(int a = 0; a < 3; a++)
+    {
+      lo[a] = std::min(lo[a], b.lo[a]);
+      hi[a] = std::max(hi[a], b.hi[a]);
+    }
+  }
+  float halfArea() const
+  {
+    float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    return dx * dy + dy * dz + dz * dx;
+  }
+};
+
+struct Node2
+{
+  Box      box;
+  uint32_t left = 0, right = 0;   // inner
+  uint32_t first = 0, count = 0;  // leaf when count > 0
+};
+
+struct Builder
+{
+  const std::vector<FlatTri>& tris;
+  std::vector<Box>            tbox;
+  std::vector<float>          cen;  // 3 per tri
+  std::vector<uint32_t>       order;
+  std::vector<Node2>          n2;
+
+  explicit Builder(const std::vector<FlatTri>& t)
+      : tris(t)
+  {
+  }
+
+  void prepare()
+  {
+    const size_t n = tris.size();
+    tbox.resize(n);
+    cen.resize(n * 3);
+    order.resize(n);
+    for(size_t i = 0; i < n; i++)
+    {
+      const FlatTri& T = tris[i];
+      Box&           b = tbox[i];
+      for(int a = 0; a < 3; a++)
+      {
+        // the kernel intersects (v0, v0+e1, v0+e2): bound exactly that, padded a few ulp
+        float v1 = T.v0[a] + T.e1[a], v2 = T.v0[a] + T.e2[a];
+        float lo = std::min(T.v0[a], std::min(v1, v2)), hi = std::max(T.v0[a], std::max(v1, v2));
+        float pad = std::max(std::fabs(lo), std::fabs(hi)) * 4e-7f + 1e-30f;
+        b.lo[a] = lo - pad;
+        b.hi[a] = hi + pad;
+        cen[i * 3 + a] = 0.5f * (b.lo[a] + b.hi[a]);
+      }
+      order[i] = (uint32_t)i;
+    }
+  }
+
+  // binned SAH, leaves of <= 3 triangles (a CWBVH child slot addresses at most 3)
+  void build2()
+  {
+    struct Job
+    {
+      uint32_t node, first, count;
+    };
+    n2.clear();
+    n2.reserve(tris.size() * 2);
+    n2.push_back(Node2());
+    std::vector<Job> stack;
+    stack.push_back({0, 0, (uint32_t)tris.size()});
+    const int NB = 16;
+    while(!stack.empty())
+    {
+      Job j = stack.back();
+      stack.pop_back();
+      Box bb, cb;
+      bb.reset();
+      cb.reset();
+      for(uint32_t i = j.first; i < j.first + j.count; i++)
+      {
+        uint32_t t = order[i];
+        bb.grow(tbox[t]);
+        for(int a = 0; a < 3; a++)
+        {
+          cb.lo[a] = std::min(cb.lo[a], cen[t * 3 + a]);
+          cb.hi[a] = std::max(cb.hi[a], cen[t * 3 + a]);
+        }
+      }
+      n2[j.node].box = bb;
+      n2[j.node].first = j.first;
+      n2[j.node].count = j.count;
+      if(j.count <= 3)
+      {
+        bool split = false;
+        if(j.count > 1)
+        {
+          // split tiny leaves only when it clearly pays (long thin triangles side by side)
+          split = false;
+        }
+        if(!split)
+          continue;
+      }
+      float bestCost = FLT_MAX;
+      int   bestAxis = -1, bestBin = -1;
+      for(int ax = 0; ax < 3; ax++)
+      {
+        float e = cb.hi[ax] - cb.lo[ax];
+        if(!(e > 0.f))
+          continue;
+        Box      bins[NB];
+        uint32_t cnt[NB];
+        for(int b = 0; b < NB; b++)
+        {
+          bins[b].reset();
+          cnt[b] = 0;
+        }
+        const float scale = (float)NB / e, c0 = cb.lo[ax];
+        for(uint32_t i = j.first; i < j.first + j.count; i++)
+        {
+          uint32_t t = order[i];
+          int      b = std::min(NB - 1, (int)((cen[t * 3 + ax] - c0) * scale));
+          cnt[b]++;
+          bins[b].grow(tbox[t]);
+        }
+        float    rArea[NB];
+        uint32_t rCnt[NB];
+        Box      acc;
+        acc.reset();
+        uint32_t c = 0;
+        for(int b = NB - 1; b > 0; b--)
+        {
+          acc.grow(bins[b]);
+          c += cnt[b];
+          rArea[b] = c ? acc.halfArea() : 0.f;
+          rCnt[b] = c;
+        }
+        acc.reset();
+        c = 0;
+        for(int b = 0; b < NB - 1; b++)
+        {
+          acc.grow(bins[b]);
+          c += cnt[b];
+          if(c == 0 || rCnt[b + 1] == 0)
+            continue;
+          // cost in units of "triangle slots": leaves hold up to 3 triangles per slot
+          float cost = acc.halfArea() * (float)c + rArea[b + 1] * (float)rCnt[b + 1];
+          if(cost < bestCost)
+          {
+            bestCost = cost;
+            bestAxis = ax;
+            bestBin = b;
+          }
+        }
+      }
+      uint32_t mid;
+      if(bestAxis < 0)
+        mid = j.first + j.count / 2;
+      else
+      {
+        const float e = cb.hi[bestAxis] - cb.lo[bestAxis], scale = (float)NB / e, c0 = cb.lo[bestAxis];
+        auto        it = std::partition(order.begin() + j.first, order.begin() + j.first + j.count, [&](uint32_t t) {
+          int b = std::min(NB - 1, (int)((cen[t * 3 + bestAxis] - c0) * scale));
+          return b <= bestBin;
+        });
+        mid = (uint32_t)(it - order.begin());
+        if(mid == j.first || mid == j.first + j.count)
+          mid = j.first + j.count / 2;
+      }
+      uint32_t l = (uint32_t)n2.size();
+      n2.push_back(Node2());
+      n2.push_back(Node2());
+      n2[j.node].left = l;
+      n2[j.node].right = l + 1;
+      n2[j.node].count = 0;
+      stack.push_back({l, j.first, mid - j.first});
+      stack.push_back({l + 1, mid, j.first + j.count - mid});
+    }
+  }
+};
+
+static inline uint32_t f2u(float f)
+{
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+static inline float u2f(uint32_t u)
+{
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+}  // namespace
+
+void buildWideBvh(const std::vector<FlatTri>& tris, WideBvh& out)
+{
+  out = WideBvh();
+  out.numTris = (uint32_t)tris.size();
+  for(int a = 0; a < 3; a++)
+  {
+    out.boundsLo[a] = 0.f;
+    out.boundsHi[a] = 0.f;
+  }
+  if(tris.empty())
+  {
+    // a single empty node keeps the traversal kernels branch-free about "no scene"
+    out.nodes.assign(20, 0.f);
+    out.numNodes = 1;
+    return;
+  }
+  Builder B(tris);
+  B.prepare();
+  B.build2();
+  for(int a = 0; a < 3; a++)
+  {
+    out.boundsLo[a] = B.n2[0].box.lo[a];
+    out.boundsHi[a] = B.n2[0].box.hi[a];
+  }
+
+  // ---- collapse to 8-wide + emit ---------------------------------------------------------------
+  struct Pending
+  {
+    uint32_t n2;     // BVH2 node this wide node covers
+    uint32_t index;  // index of the wide node in out.nodes
+    uint32_t depth;
+  };
+  std::vector<Pending> queue;
+  out.nodes.assign(20, 0.f);
+  queue.push_back({0, 0, 1});
+  out.tris.reserve(tris.size() * 12);
+  out.triMeta.reserve(tris.size() * 2);
+  size_t qi = 0;
+  // a root that is itself a leaf: wrap it in a wide node with one leaf child (handled by the generic path
+  // because a leaf BVH2 node is simply a child that cannot be opened)
+  while(qi < queue.size())
+  {
+    Pending pn = queue[qi++];
+    out.maxDepth = std::max(out.maxDepth, pn.depth);
+    const Node2& root = B.n2[pn.n2];
+    // gather up to 8 children: repeatedly open the inner child with the largest surface area
+    uint32_t ch[8];
+    int      nch = 0;
+    if(root.count > 0)
+      ch[nch++] = pn.n2;
+    else
+    {
+      ch[nch++] = root.left;
+      ch[nch++] = root.right;
+      while(nch < 8)
+      {
+        int   best = -1;
+        float bestA = -1.f;
+        for(int i = 0; i < nch; i++)
+        {
+          const Node2& c = B.n2[ch[i]];
+          if(c.count == 0 && c.box.halfArea() > bestA)
+          {
+            bestA = c.box.halfArea();
+            best = i;
+          }
+        }
+        if(best < 0)
+          break;
+        const Node2& c = B.n2[ch[best]];
+        ch[best] = c.left;
+        ch[nch++] = c.right;
+      }
+    }
+    // slot assignment: slot s is visited first by rays whose negative-direction bits equal s, so a
+    // child far along +x wants bit 4 set, +y bit 2, +z bit 1 (greedy maximum of centroid . diagonal)
+    const Box& nb = root.box;
+    float      cx = 0.5f * (nb.lo[0] + nb.hi[0]), cy = 0.5f * (nb.lo[1] + nb.hi[1]), cz = 0.5f * (nb.lo[2] + nb.hi[2]);
+    float      cost[8][8];
+    for(int i = 0; i < nch; i++)
+    {
+      const Box& b = B.n2[ch[i]].box;
+      float      dx = 0.5f * (b.lo[0] + b.hi[0]) - cx, dy = 0.5f * (b.lo[1] + b.hi[1]) - cy, dz = 0.5f * (b.lo[2] + b.hi[2]) - cz;
+      for(int s = 0; s < 8; s++)
+        cost[i][s] = dx * ((s & 4) ? 1.f : -1.f) + dy * ((s & 2) ? 1.f : -1.f) + dz * ((s & 1) ? 1.f : -1.f);
+    }
+    int  slotOf[8];
+    int  childAt[8];
+    bool cu[8] = {false, false, false, false, false, false, false, false};
+    for(int s = 0; s < 8; s++)
+      childAt[s] = -1;
+    for(int k = 0; k < nch; k++)
+    {
+      float best = -FLT_MAX;
+      int   bi = -1, bs = -1;
+      for(int i = 0; i < nch; i++)
+      {
+        if(cu[i])
+          continue;
+        for(int s = 0; s < 8; s++)
+        {
+          if(childAt[s] >= 0)
+            continue;
+          if(cost[i][s] > best)
+          {
+            best = cost[i][s];
+            bi = i;
+            bs = s;
+          }
+        }
+      }
+      cu[bi] = true;
+      slotOf[bi] = bs;
+      childAt[bs] = bi;
+    }
+    (void)slotOf;
+
+    // quantisation frame
+    float    p[3] = {nb.lo[0], nb.lo[1], nb.lo[2]};
+    uint32_t eb[3];
+    double   scale[3];
+    for(int a = 0; a < 3; a++)
+    {
+      double ext = (double)nb.hi[a] - (double)nb.lo[a];
+      int    e = (ext > 0.0) ? (int)std::ceil(std::log2(ext / 255.0)) : -126;
+      // make sure 255 * 2^e really covers the extent after float rounding
+      while(std::ldexp(255.0, e) < ext)
+        e++;
+      e = std::max(-126, std::min(127, e));
+      eb[a] = (uint32_t)(e + 127);
+      scale[a] = std::ldexp(1.0, e);
+    }
+    uint8_t  imask = 0, meta[8], qlo[3][8], qhi[3][8];
+    uint32_t childBase = (uint32_t)(out.nodes.size() / 20);  // internal children appended below
+    uint32_t triBase = (uint32_t)(out.tris.size() / 12);
+    uint32_t triCount = 0, innerCount = 0;
+    for(int s = 0; s < 8; s++)
+    {
+      meta[s] = 0;
+      for(int a = 0; a < 3; a++)
+      {
+        qlo[a][s] = 255;  // empty slot: inverted box never hits
+        qhi[a][s] = 0;
+      }
+      if(childAt[s] < 0)
+        continue;
+      const Node2& c = B.n2[ch[childAt[s]]];
+      for(int a = 0; a < 3; a++)
+      {
+        double lo = ((double)c.box.lo[a] - (double)p[a]) / scale[a];
+        double hi = ((double)c.box.hi[a] - (double)p[a]) / scale[a];
+        int    ql = (int)std::floor(lo - 1e-3), qh = (int)std::ceil(hi + 1e-3);
+        qlo[a][s] = (uint8_t)std::max(0, std::min(255, ql));
+        qhi[a][s] = (uint8_t)std::max(0, std::min(255, qh));
+      }
+      if(c.count == 0)
+      {
+        imask |= (uint8_t)(1u << s);
+        meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
+        innerCount++;
+      }
+      else
+      {
+        // unary count in the high 3 bits, triangle offset in the low 5
+        uint32_t bits = (c.count == 1) ? 1u : (c.count == 2 ? 3u : 7u);
+        meta[s] = (uint8_t)((bits << 5) | triCount);
+        for(uint32_t k = 0; k < c.count; k++)
+        {
+          uint32_t       gid = B.order[c.first + k];
+          const FlatTri& T = tris[gid];
+          float          rec[12] = {T.v0[0], T.v0[1], T.v0[2], u2f(T.rnode | (T.flags << 28)), T.e1[0], T.e1[1], T.e1[2], u2f(T.prim), T.e2[0], T.e2[1], T.e2[2], u2f(gid)};
+          out.tris.insert(out.tris.end(), rec, rec + 12);
+          out.triMeta.push_back(T.rnode | (T.flags << 28));
+          out.triMeta.push_back(T.prim);
+        }
+        triCount += c.count;
+      }
+    }
+    // reserve the internal children (ascending slot order) and queue them
+    out.nodes.resize(out.nodes.size() + (size_t)innerCount * 20, 0.f);
+    uint32_t k = 0;
+    for(int s = 0; s < 8; s++)
+    {
+      if(childAt[s] < 0)
+        continue;
+      const uint32_t cn = ch[childAt[s]];
+      if(B.n2[cn].count == 0)
+        queue.push_back({cn, childBase + k++, pn.depth + 1});
+    }
+    float* N = &out.nodes[(size_t)pn.index * 20];
+    N[0] = p[0];
+    N[1] = p[1];
+    N[2] = p[2];
+    N[3] = u2f(eb[0] | (eb[1] << 8) | (eb[2] << 16) | ((uint32_t)imask << 24));
+    N[4] = u2f(childBase);
+    N[5] = u2f(triBase);
+    N[6] = u2f((uint32_t)meta[0] | ((uint32_t)meta[1] << 8) | ((uint32_t)meta[2] << 16) | ((uint32_t)meta[3] << 24));
+    N[7] = u2f((uint32_t)meta[4] | ((uint32_t)meta[5] << 8) | ((uint32_t)meta[6] << 16) | ((uint32_t)meta[7] << 24));
+    auto pack4 = [](const uint8_t* q) { return (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24); };
+    for(int a = 0; a < 3; a++)
+    {
+      N[8 + a * 4 + 0] = u2f(pack4(&qlo[a][0]));
+      N[8 + a * 4 + 1] = u2f(pack4(&qlo[a][4]));
+      N[8 + a * 4 + 2] = u2f(pack4(&qhi[a][0]));
+      N[8 + a * 4 + 3] = u2f(pack4(&qhi[a][4]));
+    }
+  }
+  out.numNodes = (uint32_t)(out.nodes.size() / 20);
+}
+
+}  // namespace pt

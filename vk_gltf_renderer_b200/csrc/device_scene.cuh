@@ -1,0 +1,105 @@
+// device_scene.cuh — HBM-resident scene + per-frame parameter blocks shared by all kernels.
+//
+// Data contract = what SceneVk / MaterialCache / HdrIbl give the reference shaders
+// (shaders/gltf_scene_io.h.slang:41-322; shaders/shaderio.h:148-196), re-laid for CUDA:
+//   GltfRenderNode[] / GltfShadeMaterial[] / GltfTextureInfo[] / GltfLight[]  : same bytes, AoS
+//   GltfRenderPrimitive (7 device addresses)                                  : DevPrim
+//   bindless Sampler2D allTextures[]                                          : cudaTextureObject_t[]
+//   HDR env Sampler2D + StructuredBuffer<EnvAccel>                            : float4[] + uint2[]
+//   TLAS/BLAS                                                                 : BvhView (+ triMeta)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/b200pt.h"
+#include "traverse.cuh"
+
+namespace pt {
+
+struct DevPrim
+{
+  const uint32_t* idx;
+  const float*    pos;
+  const float*    nrm;
+  const uint32_t* col;
+  const float*    tan;
+  const float*    uv0;
+  const float*    uv1;
+};
+
+struct DevTex
+{
+  cudaTextureObject_t obj;
+  float               w, h;
+  float               maxLevel;
+  int                 mipLinear;
+};
+
+struct DevScene
+{
+  const b200pt_render_node*    nodes;
+  const DevPrim*               prims;
+  const b200pt_shade_material* mats;
+  const b200pt_texture_info*   texInfos;
+  const DevTex*                textures;
+  const b200pt_light*          lights;
+  int                          numLights;
+  int                          numTextures;
+  BvhView                      bvh;
+  const uint2*                 triMeta;  // per triangle slot: (rnode | flags<<28, primitiveID)
+  const float4*                envRgba;  // lat-long radiance, pdf in .w
+  const uint2*                 envAccel; // (alias, q bits)
+  int                          envW, envH;
+  int                          allOpaque;  // every triangle FORCE_OPAQUE: shadow rays may stop at the first hit
+};
+
+struct FrameParams
+{
+  b200pt_frame_info    fi;
+  b200pt_push_constant pc;
+  int                  width, height;
+  int                  tileY0, tileRows;
+  uint32_t             numPaths;  // tileRows * width
+};
+
+// ---- wavefront path state (SoA, one slot per pixel of the tile) --------------------------------
+// 16-byte records so every access is one 128-bit load/store.
+struct PathState
+{
+  float4*   rayO;    // origin.xyz | cone width
+  float4*   rayD;    // direction.xyz | tmax
+  float4*   hit;     // t | u | v | triangle slot (bits; 0xFFFFFFFF = miss)
+  float4*   thr;     // throughput.xyz | lastSamplePdf
+  float4*   rad;     // radiance.xyz | scatterBounces (bits)
+  float4*   misc;    // maxRoughness.xy | flags (bits) | seed (bits)
+  uint4*    medium;  // fp16x3 extinction | fp16x3 scatter | fp16 anisotropy (packed) | sample index
+  float4*   pixSum;  // per-pixel sum of the frame's samples (rgb + solid flag)
+  float4*   shO;     // shadow ray origin.xyz | tmax
+  float4*   shD;     // shadow ray direction.xyz | unused
+  float4*   shC;     // NEE contribution.xyz | unused
+};
+
+// flags word in misc.z
+enum : uint32_t
+{
+  PF_DEPTH_MASK = 0xffffu,
+  PF_INSIDE = 1u << 16,
+  PF_SOLID = 1u << 17,
+  PF_POST_VOLUME = 1u << 18,   // post stage runs the in-volume RR rule instead of the surface one
+  PF_SHADOW_VALID = 1u << 19,
+  PF_SHADOW_INSIDE = 1u << 20, // TraceShadow(initialInside = true)
+};
+
+struct Queues
+{
+  uint32_t* qTrace;   // paths to trace + shade this iteration
+  uint32_t* qPost;    // paths entering the shadow / RR stage
+  uint32_t* qNext;    // paths for the next iteration
+  uint32_t* counters; // [0] = count(qTrace) [1] = count(qPost) [2] = count(qNext)
+};
+
+struct DevStats
+{
+  unsigned long long closestRays, shadowRays, shadedHits, pathsStarted, nodesVisited, trisTested;
+};
+
+}  // namespace pt

@@ -1,0 +1,213 @@
+"""Host-side mirror of the reference's path-tracer backend interface.
+
+`PathTracer` mirrors `class PathTracer : public BaseRenderer` (reference src/renderer_base.hpp:33-55,
+src/renderer_pathtracer.hpp:61-88): onAttach / onDetach / onResize / onRender / onSceneInvalidated,
+the `--pt*` parameters (src/renderer_pathtracer.cpp:119-132) and the public push-constant block.
+`Resources` carries what the reference's `Resources` bag hands the renderer (src/resources.hpp:167-276):
+scene, HDR environment, camera, settings, frame counter and the RGBA32F accumulation image.
+
+Everything below the virtuals is one call into libb200pt.so (include/b200pt.h); there is no
+CPU path here.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib, abi, camera as cam_mod
+
+
+class B200PTError(RuntimeError):
+    pass
+
+
+@dataclass
+class Settings:
+    """Resources::settings (reference src/resources.hpp:82-133) — fields the path tracer reads."""
+    envSystem: int = 1            # 0 sky (not built), 1 HDR
+    hdrEnvIntensity: float = 1.0
+    hdrEnvRotation: float = 0.0
+    hdrBlur: float = 0.0
+    useSolidBackground: bool = False
+    solidBackgroundColor: tuple = (0.0, 0.0, 0.0)
+    maxFrames: int = 500
+
+
+@dataclass
+class Resources:
+    scene: object = None          # vk_gltf_renderer_b200.scene.Scene
+    hdr_rgb: np.ndarray = None    # float32 [H, W, 3]
+    camera: object = None
+    settings: Settings = field(default_factory=Settings)
+    size: tuple = (1920, 1080)    # (width, height)
+    frameCount: int = -1          # reset to -1, pre-incremented (src/renderer.cpp:1939-1977)
+    tile: tuple = None            # (y0, rows) for framebuffer tiling; None = full image
+
+
+class PathTracer:
+    """Drop-in for the reference's PathTracer renderer, backed by the CUDA library."""
+
+    def __init__(self, device=0):
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        self._device = device
+        # PathtracePushConstant defaults (shaders/shaderio.h:181-190) + registerParameters names
+        self.ptMaxDepth = 5
+        self.ptSamples = 1
+        self.ptFireflyClamp = 10.0
+        self.ptTexGradScale = 1.0
+        self.ptAperture = 0.0
+        self.ptFocalDistance = 0.0
+        self.ptAutoFocus = True
+        self.m_totalSamplesAccumulated = 0
+        self.m_pushConst = abi.PushConstant()
+        self.hdr_integral = None
+        self._attached = False
+
+    # -- error plumbing (reference: NVVK_CHECK aborts; here: exceptions carrying b200pt_last_error) --
+    def _ck(self, rc, what):
+        if rc != 0:
+            msg = self._L.b200pt_last_error(self._h)
+            raise B200PTError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def registerParameters(self, registry):
+        """nvutils::ParameterRegistry analogue: registry is any dict-like; names as the reference CLI."""
+        for name in ("ptMaxDepth", "ptSamples", "ptFireflyClamp", "ptTexGradScale", "ptAperture",
+                     "ptFocalDistance", "ptAutoFocus"):
+            registry[name] = (self, name)
+
+    # -- BaseRenderer virtuals --------------------------------------------------------------------
+    def onAttach(self, resources, profiler=None):
+        rc = self._L.b200pt_create(C.byref(self._h), self._device)
+        if rc != 0:
+            raise B200PTError(f"b200pt_create failed ({rc}): no usable CUDA device {self._device}")
+        self._attached = True
+        if profiler:
+            self._ck(self._L.b200pt_set_profiling(self._h, 1), "b200pt_set_profiling")
+        if resources.scene is not None:
+            self.onSceneInvalidated(resources)
+        if resources.hdr_rgb is not None:
+            self.setEnvironment(resources.hdr_rgb)
+        self.onResize(None, resources.size, resources)
+
+    def onDetach(self, resources=None):
+        if self._attached:
+            self._L.b200pt_destroy(self._h)
+            self._h = C.c_void_p()
+            self._attached = False
+
+    def __del__(self):
+        try:
+            self.onDetach()
+        except Exception:
+            pass
+
+    def onSceneInvalidated(self, resources):
+        d = resources.scene.desc()
+        self._ck(self._L.b200pt_set_scene(self._h, C.byref(d)), "b200pt_set_scene")
+
+    def setEnvironment(self, rgb):
+        rgb = np.ascontiguousarray(rgb, np.float32)
+        integral = C.c_float()
+        self._ck(self._L.b200pt_set_environment(self._h, rgb.ctypes.data_as(C.c_void_p), rgb.shape[1], rgb.shape[0],
+                                                C.byref(integral)), "b200pt_set_environment")
+        self.hdr_integral = integral.value
+
+    def onResize(self, cmd, size, resources):
+        w, h = size
+        y0, rows = resources.tile if resources.tile else (0, h)
+        self._ck(self._L.b200pt_resize(self._h, w, h, y0, rows), "b200pt_resize")
+        self._size = (w, h)
+        self._tile = (y0, rows)
+        resources.size = (w, h)
+
+    def onRender(self, cmd, resources):
+        """One frame: setupPushConstant (renderer_pathtracer.cpp:1496-1574) + dispatch + updateStatistics."""
+        w, h = self._size
+        s = resources.settings
+        if resources.frameCount == 0:
+            self.m_totalSamplesAccumulated = 0
+        fi = cam_mod.make_frame_info(resources.camera, w, h, use_hdr=(s.envSystem == 1), env_rotation=s.hdrEnvRotation,
+                                     env_intensity=s.hdrEnvIntensity, env_blur=s.hdrBlur,
+                                     solid_background=s.useSolidBackground, background=s.solidBackgroundColor)
+        pc = cam_mod.make_push_constant(resources.camera, h, frame_count=resources.frameCount,
+                                        total_samples=self.m_totalSamplesAccumulated, num_samples=self.ptSamples,
+                                        max_depth=self.ptMaxDepth, firefly_clamp=self.ptFireflyClamp,
+                                        tex_grad_scale=self.ptTexGradScale, aperture=self.ptAperture,
+                                        focal_distance=None if self.ptAutoFocus else self.ptFocalDistance)
+        self.m_pushConst = pc
+        self._ck(self._L.b200pt_render_frame(self._h, C.byref(fi), C.byref(pc)), "b200pt_render_frame")
+        self.m_totalSamplesAccumulated += self.ptSamples
+
+    # -- C-ABI passthroughs -------------------------------------------------------------------------
+    def render_frame_raw(self, fi, pc):
+        self._ck(self._L.b200pt_render_frame(self._h, C.byref(fi), C.byref(pc)), "b200pt_render_frame")
+
+    def synchronize(self):
+        self._ck(self._L.b200pt_synchronize(self._h), "b200pt_synchronize")
+
+    def read_accum(self):
+        w, _ = self._size
+        rows = self._tile[1]
+        out = np.empty((rows, w, 4), np.float32)
+        self._ck(self._L.b200pt_read_accum(self._h, out.ctypes.data_as(C.c_void_p), out.size), "b200pt_read_accum")
+        return out
+
+    def accum_device_ptr(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self._L.b200pt_get_accum_device(self._h, C.byref(p), C.byref(n)), "b200pt_get_accum_device")
+        return p.value, n.value
+
+    def set_accum_device(self, ptr, num_floats):
+        self._ck(self._L.b200pt_set_accum_device(self._h, C.c_void_p(ptr), num_floats), "b200pt_set_accum_device")
+
+    def stream(self):
+        return self._L.b200pt_stream(self._h)
+
+    def stats(self):
+        st = abi.Stats()
+        self._ck(self._L.b200pt_get_stats(self._h, C.byref(st)), "b200pt_get_stats")
+        return {n: getattr(st, n) for n, _ in abi.Stats._fields_}
+
+    def reset_stats(self):
+        self._ck(self._L.b200pt_reset_stats(self._h), "b200pt_reset_stats")
+
+    def set_profiling(self, on):
+        self._ck(self._L.b200pt_set_profiling(self._h, 1 if on else 0), "b200pt_set_profiling")
+
+    def bvh_info(self):
+        nb, tb, nn, nt = C.c_uint64(), C.c_uint64(), C.c_uint32(), C.c_uint32()
+        self._ck(self._L.b200pt_bvh_info(self._h, C.byref(nb), C.byref(tb), C.byref(nn), C.byref(nt)), "b200pt_bvh_info")
+        return dict(node_bytes=nb.value, tri_bytes=tb.value, num_nodes=nn.value, num_tris=nt.value)
+
+    # ray-level entry points take device pointers (ints), e.g. torch tensors' data_ptr()
+    def trace_closest(self, rays_ptr, n, hits_ptr, seeds_ptr=None):
+        self._ck(self._L.b200pt_trace_closest(self._h, C.c_void_p(rays_ptr), n, C.c_void_p(hits_ptr),
+                                              C.c_void_p(seeds_ptr) if seeds_ptr else None), "b200pt_trace_closest")
+
+    def trace_shadow(self, rays_ptr, n, out_ptr, seeds_ptr=None):
+        self._ck(self._L.b200pt_trace_shadow(self._h, C.c_void_p(rays_ptr), n, C.c_void_p(out_ptr),
+                                             C.c_void_p(seeds_ptr) if seeds_ptr else None), "b200pt_trace_shadow")
+
+    def bsdf_eval(self, in_ptr, n, out_ptr):
+        self._ck(self._L.b200pt_bsdf_eval(self._h, C.c_void_p(in_ptr), n, C.c_void_p(out_ptr)), "b200pt_bsdf_eval")
+
+    def bsdf_sample(self, in_ptr, n, out_ptr):
+        self._ck(self._L.b200pt_bsdf_sample(self._h, C.c_void_p(in_ptr), n, C.c_void_p(out_ptr)), "b200pt_bsdf_sample")
+
+
+def render_headless(resources, frames, *, pt=None, device=0, **pt_params):
+    """The reference's headless loop (src/main.cpp:133-136 + nvapp frame loop):
+    frameCount runs 0..frames-1, each frame adds ptSamples spp.  Returns (PathTracer, accum RGBA32F)."""
+    own = pt is None
+    if own:
+        pt = PathTracer(device)
+        for k, v in pt_params.items():
+            setattr(pt, k, v)
+        pt.onAttach(resources)
+    resources.frameCount = -1
+    for _ in range(min(frames, max(resources.settings.maxFrames, frames))):
+        resources.frameCount += 1
+        pt.onRender(None, resources)
+    img = pt.read_accum()
+    return pt, img
