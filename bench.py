@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 wavefront path tracer.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2], the one `metric` is quoted on): Sponza 1920x1080, depth 12, NEE+MIS,
+HDR environment, frames x 1 spp.  The Khronos Sponza asset is not available offline, so the seeded
+stand-in SURVEY.md §8d specifies is used: SynthSponza (seed 1234, 262 144 instanced triangles,
+25 materials, 2048^2 sRGB/MR/normal value-noise textures, 10 % alpha-MASK foliage) + std_env.hdr.
+One step = one frame = one pass of the hot path (ray-gen -> [traverse -> shade -> shadow/RR] x depth
+-> accumulate) over every pixel of the framebuffer.
+
+Numbers on the JSON line
+  value          Mray/s, whole job, device-timed (CUDA events on the renderer's stream, max over ranks),
+                 scene/BVH/textures/environment already resident in HBM.
+  e2e            same metric through the public API with host buffers: every step passes the frame's
+                 SceneFrameInfo + push constants from host memory and reads the RGBA32F accumulation
+                 image back into pinned host memory.
+  roofline       dominant kernel: algorithmic bytes (SURVEY.md §8d / DESIGN.md) / measured kernel time
+                 vs the measured HBM peak in MEASURED_PEAKS.json.
+  cpu_baseline   the CPU oracle (scalar port of the reference algorithm) on a bounded row band of the
+                 same frame, all host threads.
+N > 1: the framebuffer is tiled by rows (one strip per rank, scene replicated), one NCCL all-gather of
+the strips per frame; total work is fixed, so scaling is "strong".
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Mray/s @1080p SynthSponza (Sponza stand-in), depth 12, NEE+MIS, HDR env"
+NODE_BYTES, TRI_BYTES = 80, 48
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--depth", type=int, default=12)
+    ap.add_argument("--tex", type=int, default=2048)
+    ap.add_argument("--detail", type=float, default=1.0)
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the frame the CPU baseline renders (0 = sized for ~12 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def build_workload(args):
+    """SynthSponza is deterministic in (seed, tex, detail); the generated arrays are cached as a pickle under
+    the system temp dir so the N=1,2,4,8 and reference-arm invocations on one box generate it once."""
+    import pickle
+    from vk_gltf_renderer_b200 import hdr, synth
+    env = hdr.load_hdr(os.path.join(ROOT, "tests", "assets", "std_env.hdr"))
+    cache = os.path.join(tempfile.gettempdir(), "b200pt_synthsponza_s1234_t%d_d%g.pkl" % (args.tex, args.detail))
+    rank = int(os.environ.get("RANK", "0"))
+    scn = None
+    if os.path.exists(cache):
+        try:
+            with open(cache, "rb") as f:
+                scn = synth.scene_from_state(pickle.load(f))
+        except Exception:
+            scn = None
+    if scn is None:
+        scn = synth.synth_sponza(seed=1234, tex_size=args.tex, detail=args.detail)
+        if rank == 0:
+            try:
+                tmp = cache + ".%d.tmp" % os.getpid()
+                with open(tmp, "wb") as f:
+                    pickle.dump(synth.scene_state(scn), f, protocol=4)
+                os.replace(tmp, cache)
+            except Exception:
+                pass
+    return scn, env
+
+
+def workload_config(args, scn, n_gpus):
+    return {"workload": "SynthSponza(seed=1234) stand-in for Sponza, %dx%d, depth %d, 1 spp/frame, std_env.hdr, NEE+MIS"
+                        % (args.width, args.height, args.depth),
+            "triangles": scn.num_triangles(), "materials": len(scn.materials), "textures": len(scn.textures),
+            "texture_size": args.tex, "partition": "1 GPU" if n_gpus == 1 else "row strips x%d + NCCL all-gather/frame" % n_gpus,
+            "l2_policy": "working set (path state 11x16 B x 2.07M paths = 365 MB + 33 MB image) exceeds the 126 MB L2 every frame"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            self.path = tempfile.mktemp(suffix=".csv")
+            q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def cpu_baseline(args, scn, env, oracle=None, frame=0):
+    """Oracle (port of the reference algorithm) on a row band in the middle of the frame, all host threads."""
+    from oracle import oracle as O
+    from vk_gltf_renderer_b200 import camera as cm
+    if oracle is None:
+        oracle = O.Oracle()
+        oracle.set_scene(scn)
+        oracle.set_environment(env)
+    threads = os.cpu_count() or 1
+    fi = cm.make_frame_info(scn.camera, args.width, args.height)
+    pc = cm.make_push_constant(scn.camera, args.height, frame_count=frame, total_samples=0, max_depth=args.depth)
+    rows = args.cpu_rows
+    if rows <= 0:
+        # size the band for ~12 s of CPU work from a 8-row probe
+        probe = np.zeros((8, args.width, 4), np.float32)
+        t0 = time.perf_counter()
+        oracle.render_frame(fi, pc, probe, y0=args.height // 2, rows=8, threads=threads)
+        per_row = (time.perf_counter() - t0) / 8
+        rows = int(max(8, min(args.height, 12.0 / max(per_row, 1e-6))))
+        args.cpu_rows = rows
+    rows = min(rows, args.height)
+    y0 = (args.height - rows) // 2
+    accum = np.zeros((rows, args.width, 4), np.float32)
+    oracle.reset_stats()
+    t0 = time.perf_counter()
+    oracle.render_frame(fi, pc, accum, y0=y0, rows=rows, threads=threads)
+    dt = time.perf_counter() - t0
+    st = oracle.stats()
+    rays = st["closestRays"] + st["shadowRays"]
+    return oracle, {"value": rays / dt / 1e6, "unit": "Mray/s", "cores": threads, "kind": "port",
+                    "sample": "rows %d..%d of frame %d (%d paths, %d rays, %.1f s)" % (y0, y0 + rows - 1, frame, rows * args.width, rays, dt),
+                    "spp_per_s_full_frame": (rows / args.height) / dt}, dt, rays
+
+
+def run_reference(args):
+    """--impl reference: the reference's own algorithm on the host cores (oracle port: the Vulkan-RT
+    reference cannot be built or run here — DESIGN.md §Oracle)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scn, env = build_workload(args)
+    oracle = None
+    for w in range(args.warmup):
+        oracle, _, _, _ = cpu_baseline(args, scn, env, oracle, frame=w)
+    tot_t = tot_r = 0.0
+    cb = None
+    for k in range(args.steps):
+        oracle, cb, dt, rays = cpu_baseline(args, scn, env, oracle, frame=args.warmup + k)
+        tot_t += dt
+        tot_r += rays
+    val = tot_r / tot_t / 1e6
+    cb["value"] = val
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mray/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, scn, 1),
+            "cpu_baseline": cb, "e2e": {"value": val, "unit": "Mray/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "note": "each step = the sample band of one 1080p frame on the host cores; Mray/s is size-independent"}
+    print(json.dumps(line))
+
+
+def traversal_counts(args, scn, env, device):
+    """Per-ray node / triangle averages on the SAME BVH and the same frame, from the counter build of the library."""
+    from vk_gltf_renderer_b200.renderer import PathTracer, Resources
+    res = Resources(scene=scn, hdr_rgb=env, camera=scn.camera, size=(args.width, args.height))
+    pt = PathTracer(device, count_traversal=True)
+    pt.ptMaxDepth = args.depth
+    pt.onAttach(res)
+    res.frameCount = 0
+    pt.onRender(None, res)
+    st = pt.stats()
+    pt.onDetach()
+    rays = st["closestRays"] + st["shadowRays"]
+    return st["nodesVisited"] / max(rays, 1), st["trisTested"] / max(rays, 1), st
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from vk_gltf_renderer_b200.renderer import PathTracer, Resources
+    scn, env = build_workload(args)
+    W, H = args.width, args.height
+    rows_per = (H + world - 1) // world
+    y0 = rank * rows_per
+    rows = max(0, min(rows_per, H - y0))
+    res = Resources(scene=scn, hdr_rgb=env, camera=scn.camera, size=(W, H), tile=(y0, rows))
+    pt = PathTracer(local)
+    pt.ptMaxDepth = args.depth
+    pt.onAttach(res)
+    stream = torch.cuda.ExternalStream(pt.stream(), device=local)
+    tile = torch.zeros((rows_per, W, 4), dtype=torch.float32, device="cuda")
+    pt.set_accum_device(tile.data_ptr(), rows * W * 4)
+    full = torch.empty((world * rows_per, W, 4), dtype=torch.float32, device="cuda") if world > 1 else None
+    pinned = torch.empty((rows, W, 4), dtype=torch.float32).pin_memory()
+
+    frame = [-1]
+
+    def step(gather=True):
+        frame[0] += 1
+        res.frameCount = frame[0]
+        pt.onRender(None, res)
+        if world > 1 and gather:
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(full, tile)
+
+    def barrier():
+        torch.cuda.synchronize()
+        pt.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(n):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def rays_now():
+        st = pt.stats()
+        r = torch.tensor([st["closestRays"] + st["shadowRays"], st["closestRays"], st["shadowRays"], st["shadedHits"], st["kernelLaunches"]],
+                         dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(r)
+        return r.cpu().numpy()
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        step()
+    # ---- pass A: device-timed throughput (headline `value`) ----
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    pt.reset_stats()
+    ms = timed(args.steps, step)
+    cl = clocks.stop() if rank == 0 else None
+    r = rays_now()
+    rays_total, launches = r[0], int(r[4])
+    value = rays_total / (ms * 1e-3) / 1e6
+    spp_per_s = args.steps / (ms * 1e-3)
+
+    # ---- pass B: same steps with per-launch CUDA events -> stage shares + roofline ----
+    pt.set_profiling(True)
+    pt.reset_stats()
+    timed(args.steps, step)
+    stB = pt.stats()
+    pt.set_profiling(False)
+
+    # ---- pass C: end to end through the public API with host buffers ----
+    def step_e2e():
+        step()
+        pt._ck(pt._L.b200pt_read_accum(pt._h, pinned.data_ptr(), pinned.numel()), "b200pt_read_accum")
+    pt.reset_stats()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    re = rays_now()
+    e2e_val = re[0] / float(dt.item()) / 1e6
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline model (rank 0) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    nn = nt = None
+    counts_note = "skipped"
+    if world == 1:
+        nn, nt, stc = traversal_counts(args, scn, env, local)
+        counts_note = "frame 0, counter build of the same library: %.2f nodes/ray, %.2f tris/ray" % (nn, nt)
+    stages = {}
+    tot_ms = max(stB["msTotal"], 1e-9)
+    closest_b = shadow_b = None
+    if nn is not None:
+        closest_b = 32 + 24 + nn * NODE_BYTES + nt * TRI_BYTES
+        shadow_b = 32 + 16 + nn * NODE_BYTES + nt * TRI_BYTES
+    shade_b = 1100.0  # ~1.0-1.2 KB per shaded hit
+    for name, ms_k, n_l, units, per in (("k_trace", stB["msTraceClosest"], stB["launchesTraceClosest"], stB["closestRays"], closest_b),
+                                        ("k_shade", stB["msShade"], stB["launchesShade"], stB["shadedHits"], shade_b),
+                                        ("k_post", stB["msTraceShadow"], stB["launchesTraceShadow"], stB["shadowRays"], shadow_b)):
+        ach = (units * per / (ms_k * 1e-3) / 1e9) if (per and ms_k > 0) else None
+        stages[name] = {"share": ms_k / tot_ms, "ms_per_launch": ms_k / max(n_l, 1), "launches": int(n_l), "units": int(units),
+                        "bytes_per_unit": per, "achieved_GBps": ach}
+    dom = max(stages, key=lambda k: stages[k]["share"])
+    roof = {"kernel": dom, "bound": "hbm", "achieved": stages[dom]["achieved_GBps"], "peak": peak_gbs, "unit": "GB/s",
+            "frac": (stages[dom]["achieved_GBps"] / peak_gbs) if stages[dom]["achieved_GBps"] else None, "traffic": None,
+            "peak_source": peak_src, "model": "algorithmic bytes/unit x units / CUDA-event kernel time (pass B); " + counts_note,
+            "stages": stages}
+
+    cb = None
+    if not args.no_cpu_baseline and world == 1:
+        _, cb, _, _ = cpu_baseline(args, scn, env)
+
+    line = {"metric": METRIC, "value": value, "unit": "Mray/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, scn, world), "spp_per_s": spp_per_s,
+            "throughput_MSps": W * H * spp_per_s / 1e6, "rays_per_sample": rays_total / (args.steps * W * H),
+            "clocks": cl, "e2e": {"value": e2e_val, "unit": "Mray/s", "h2d_bytes_per_step": 396 + 48, "d2h_bytes_per_step": rows * W * 16 * world,
+                                  "ms_per_step": 1e3 * float(dt.item()) / args.steps},
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -261,6 +261,9 @@ typedef struct b200pt_stats
   double   msOther;       /* raygen + accumulate + queue housekeeping              */
   double   msTotal;
   uint64_t kernelLaunches;
+  uint64_t launchesTraceClosest; /* launches measured into msTraceClosest (profiling on) */
+  uint64_t launchesShade;
+  uint64_t launchesTraceShadow;
 } b200pt_stats;
 
 /* ---- lifecycle --------------------------------------------------------------------------- */
@@ -317,7 +320,8 @@ void* b200pt_stream(b200pt_t* h);
 
 int b200pt_get_stats(b200pt_t* h, b200pt_stats* out);
 int b200pt_reset_stats(b200pt_t* h);
-/* enable per-stage CUDA-event timing (adds a sync per frame when on) */
+/* enable per-stage CUDA-event timing: event pairs around every launch on the handle's stream,
+ * resolved lazily in b200pt_get_stats (no host sync inside a frame) */
 int b200pt_set_profiling(b200pt_t* h, int enabled);
 
 /* ---- ray-level entry points (parity tests + traversal micro-benchmarks) ------------------- */

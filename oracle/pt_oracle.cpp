@@ -82,9 +82,25 @@ struct BvhNode
   uint32_t first, count; // leaf range into triOrder (count > 0 => leaf)
 };
 
+// per-thread counters, merged into the shared totals when a worker finishes (no atomics per ray)
+struct LocalStats
+{
+  uint64_t closestRays = 0, shadowRays = 0, shadedHits = 0, paths = 0, nodes = 0, tris = 0;
+};
+static thread_local LocalStats tls;
 struct Stats
 {
   std::atomic<uint64_t> closestRays{0}, shadowRays{0}, shadedHits{0}, paths{0}, nodes{0}, tris{0};
+  void                  merge()
+  {
+    closestRays += tls.closestRays;
+    shadowRays += tls.shadowRays;
+    shadedHits += tls.shadedHits;
+    paths += tls.paths;
+    nodes += tls.nodes;
+    tris += tls.tris;
+    tls = LocalStats();
+  }
 };
 
 struct Oracle
@@ -132,6 +148,12 @@ static void buildTexture(Texture& T, const b200pt_texture& src)
   //  src/gltf_scene_vk.cpp:1254-1332: each level is an 8-bit image again)
   int                  w = src.width, h = src.height;
   std::vector<uint8_t> cur(src.rgba8, src.rgba8 + (size_t)w * h * 4);
+  float                lutL[256], lutS[256];  // 8-bit decode tables (same values as the per-texel formulas)
+  for(int i = 0; i < 256; i++)
+  {
+    lutL[i] = (float)i / 255.0f;
+    lutS[i] = srgbToLinear((float)i / 255.0f);
+  }
   for(;;)
   {
     MipLevel L;
@@ -141,12 +163,7 @@ static void buildTexture(Texture& T, const b200pt_texture& src)
     for(size_t i = 0; i < (size_t)w * h; i++)
     {
       for(int c = 0; c < 4; c++)
-      {
-        float v = cur[i * 4 + c] / 255.0f;
-        if(T.srgb && c < 3)
-          v = srgbToLinear(v);
-        L.rgba[i * 4 + c] = v;
-      }
+        L.rgba[i * 4 + c] = (T.srgb && c < 3) ? lutS[cur[i * 4 + c]] : lutL[cur[i * 4 + c]];
     }
     T.mips.push_back(std::move(L));
     if(w == 1 && h == 1)
@@ -658,8 +675,8 @@ static bool nextHit(Oracle& o, const Ray& r, bool cull, float loT, uint32_t loId
         stack[sp++] = N.right;
     }
   }
-  o.stats.nodes += nodes;
-  o.stats.tris += tris;
+  tls.nodes += nodes;
+  tls.tris += tris;
   if(best.tri == 0xFFFFFFFFu)
     return false;
   if(o.tris[best.tri].flags & TRI_FLIPPED)
@@ -1127,7 +1144,7 @@ struct HitPayload
 
 static void Trace(Oracle& o, const Ray& ray, HitPayload& p, uint32_t& seed)
 {
-  o.stats.closestRays++;
+  tls.closestRays++;
   p.hitT = INFINITE_F;
   p.rnodeID = p.rprimID = p.primitiveID = -1;
   p.bx = p.by = 0.f;
@@ -1166,7 +1183,7 @@ static void Trace(Oracle& o, const Ray& ray, HitPayload& p, uint32_t& seed)
 
 static float3 TraceShadow(Oracle& o, const Ray& ray, uint32_t& seed, bool initialInside)
 {
-  o.stats.shadowRays++;
+  tls.shadowRays++;
   float3   total = f3(1.0f);
   bool     isInside = initialInside;
   float    prevHitT = 0.f;
@@ -1552,7 +1569,7 @@ static PathStepResult pathTraceOneBounce(const Ctx& c, Ray& ray, uint32_t& seed,
   const Prim&               P = o.prims[payload.rprimID];
   const float3              barys = f3(1.0f - payload.bx - payload.by, payload.bx, payload.by);
   HitState hit = getHitState(P, barys, *(const mat4*)renderNode.worldToObject, *(const mat4*)renderNode.objectToWorld, (uint32_t)payload.primitiveID, ray.d);
-  o.stats.shadedHits++;
+  tls.shadedHits++;
 
   // rayConeWorldFootprint
   float worldFoot;
@@ -1761,14 +1778,14 @@ static void processPixel(const Ctx& c, int x, int y, float* px)
     float2 g = sampleGaussian(f2(a, b));
     jitter = jitter + g * 0.4246609f;
   }
-  c.o->stats.paths++;
+  tls.paths++;
   SampleResult sr = samplePixel(c, seed, samplePos, jitter, imageSize);
   float4       pixelColor = sr.radiance;
   for(int s = 1; s < c.pc->numSamples; s++)
   {
     float a = rnd(seed), b = rnd(seed);
     jitter = f2(a, b);
-    c.o->stats.paths++;
+    tls.paths++;
     sr = samplePixel(c, seed, samplePos, jitter, imageSize);
     pixelColor += sr.radiance;
   }
@@ -1835,8 +1852,20 @@ int oracle_set_scene(void* h, const b200pt_scene_desc* s)
   o.texInfos.assign(s->textureInfos, s->textureInfos + s->numTextureInfos);
   o.textures.clear();
   o.textures.resize(s->numTextures);
-  for(uint32_t i = 0; i < s->numTextures; i++)
-    buildTexture(o.textures[i], s->textures[i]);
+  {
+    std::atomic<uint32_t>    nextTex{0};
+    std::vector<std::thread> workers;
+    auto                     job = [&]() {
+      for(uint32_t i = nextTex.fetch_add(1); i < s->numTextures; i = nextTex.fetch_add(1))
+        buildTexture(o.textures[i], s->textures[i]);
+    };
+    const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), s->numTextures));
+    for(unsigned t = 1; t < nt; t++)
+      workers.emplace_back(job);
+    job();
+    for(auto& t : workers)
+      t.join();
+  }
   o.lights.assign(s->lights, s->lights + s->numLights);
 
   // flatten: one world-space triangle per (visible render node, triangle), node order then triangle
@@ -1926,6 +1955,7 @@ int oracle_render_frame(void* h, const b200pt_frame_info* fi, const b200pt_push_
       for(int x = 0; x < W; x++)
         processPixel(c, x, y0 + r, accum + ((size_t)r * W + x) * 4);
     }
+    o.stats.merge();
   };
   for(int t = 1; t < nthreads; t++)
     th.emplace_back(work);
@@ -1958,6 +1988,7 @@ int oracle_trace_closest(void* h, const float* rays, uint32_t n, float* hits, ui
     out[4] = p.bx;
     out[5] = p.by;
   }
+  o.stats.merge();
   return 0;
 }
 
@@ -1979,6 +2010,7 @@ int oracle_trace_shadow(void* h, const float* rays, uint32_t n, float* transmiss
     transmission[i * 3 + 1] = t.y;
     transmission[i * 3 + 2] = t.z;
   }
+  o.stats.merge();
   return 0;
 }
 

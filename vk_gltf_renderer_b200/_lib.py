@@ -28,17 +28,20 @@ def build(verbose=False):
     return LIB_PATH
 
 
-_lib = None
+COUNT_LIB_PATH = os.path.join(_HERE, "libb200pt_count.so")
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+def lib(count_traversal=False):
+    """count_traversal=True loads the variant compiled with -DB200PT_COUNT_TRAVERSAL (per-ray node /
+    triangle counters for the roofline model; never used for timing)."""
+    path = COUNT_LIB_PATH if count_traversal else LIB_PATH
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(the CUDA path is the product; there is no fallback)")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     vp, i32, u32, f32p = C.c_void_p, C.c_int, C.c_uint32, C.c_void_p
     L.b200pt_create.argtypes = [C.POINTER(vp), i32]
     L.b200pt_destroy.argtypes = [vp]
@@ -66,5 +69,5 @@ def lib():
     L.b200pt_bsdf_sample.argtypes = [vp, vp, u32, vp]
     for name in EXPORTS:
         getattr(L, name)  # raises AttributeError if a declared symbol is not exported
-    _lib = L
+    _libs[path] = L
     return L

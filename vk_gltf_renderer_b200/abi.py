@@ -104,7 +104,8 @@ class Stats(C.Structure):
     _fields_ = [("closestRays", C.c_uint64), ("shadowRays", C.c_uint64), ("shadedHits", C.c_uint64),
                 ("pathsStarted", C.c_uint64), ("nodesVisited", C.c_uint64), ("trisTested", C.c_uint64),
                 ("msTraceClosest", C.c_double), ("msTraceShadow", C.c_double), ("msShade", C.c_double),
-                ("msOther", C.c_double), ("msTotal", C.c_double), ("kernelLaunches", C.c_uint64)]
+                ("msOther", C.c_double), ("msTotal", C.c_double), ("kernelLaunches", C.c_uint64),
+                ("launchesTraceClosest", C.c_uint64), ("launchesShade", C.c_uint64), ("launchesTraceShadow", C.c_uint64)]
 
 
 # sizes fixed by the reference's layouts

@@ -11,10 +11,12 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "bvh.h"
@@ -634,11 +636,19 @@ struct b200pt
   uint32_t*          hCount = nullptr;  // pinned
   DevStats*          dStats = nullptr;
 
-  // stats / profiling
-  bool         profiling = false;
-  double       msTrace = 0, msShadow = 0, msShade = 0, msOther = 0, msTotal = 0;
-  uint64_t     kernelLaunches = 0;
-  cudaEvent_t  ev[2] = {nullptr, nullptr};
+  // stats / profiling: CUDA-event pairs recorded around every launch on the handle's stream and
+  // resolved lazily (no host sync inside a frame)
+  struct EvRec
+  {
+    cudaEvent_t a, b;
+    int         cat;
+  };
+  bool               profiling = false;
+  std::vector<EvRec> evPool;
+  size_t             evUsed = 0;
+  double             msCat[4] = {0, 0, 0, 0};  // 0 trace-closest, 1 shade, 2 shadow+RR, 3 other
+  uint64_t           launchesCat[4] = {0, 0, 0, 0};
+  uint64_t           kernelLaunches = 0;
 };
 
 namespace {
@@ -694,6 +704,23 @@ void freePool(b200pt* h)
   h->dAccumOwned = nullptr;
 }
 
+void flushEvents(b200pt* h)
+{
+  if(h->evUsed == 0)
+    return;
+  cudaStreamSynchronize(h->stream);
+  for(size_t i = 0; i < h->evUsed; i++)
+  {
+    float ms = 0.f;
+    if(cudaEventElapsedTime(&ms, h->evPool[i].a, h->evPool[i].b) == cudaSuccess)
+    {
+      h->msCat[h->evPool[i].cat] += ms;
+      h->launchesCat[h->evPool[i].cat]++;
+    }
+  }
+  h->evUsed = 0;
+}
+
 float srgbToLinear(float c) { return (c <= 0.04045f) ? c / 12.92f : powf((c + 0.055f) / 1.055f, 2.4f); }
 float linearToSrgb(float c) { return (c <= 0.0031308f) ? c * 12.92f : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f; }
 
@@ -704,12 +731,15 @@ void downsample(const std::vector<uint8_t>& src, int w, int h, bool srgb, std::v
 {
   dst.resize((size_t)nw * nh * 4);
   std::vector<float> lin((size_t)w * h * 4);
+  float              lutL[256], lutS[256];
+  for(int i = 0; i < 256; i++)
+  {
+    lutL[i] = (float)i / 255.0f;
+    lutS[i] = srgbToLinear((float)i / 255.0f);
+  }
   for(size_t i = 0; i < (size_t)w * h; i++)
     for(int c = 0; c < 4; c++)
-    {
-      float v = src[i * 4 + c] / 255.0f;
-      lin[i * 4 + c] = (srgb && c < 3) ? srgbToLinear(v) : v;
-    }
+      lin[i * 4 + c] = (srgb && c < 3) ? lutS[src[i * 4 + c]] : lutL[src[i * 4 + c]];
   for(int y = 0; y < nh; y++)
     for(int x = 0; x < nw; x++)
     {
@@ -741,33 +771,41 @@ cudaTextureAddressMode addressMode(int gl)
   return cudaAddressModeWrap;
 }
 
-int createTexture(b200pt* h, const b200pt_texture& src, TexRes& out, DevTex& dev)
+struct MipChain
+{
+  std::vector<std::vector<uint8_t>> level;
+  std::vector<int>                  w, h;
+};
+
+void buildMipChain(const b200pt_texture& src, MipChain& mc)
 {
   int w = src.width, hh = src.height;
-  if(w <= 0 || hh <= 0 || !src.rgba8)
+  mc.level.emplace_back(src.rgba8, src.rgba8 + (size_t)w * hh * 4);
+  mc.w.push_back(w);
+  mc.h.push_back(hh);
+  while(w > 1 || hh > 1)
   {
-    h->err = "texture without pixels";
-    return B200PT_E_INVALID;
+    const int            nw = std::max(1, w / 2), nh = std::max(1, hh / 2);
+    std::vector<uint8_t> nxt;
+    downsample(mc.level.back(), w, hh, src.srgb != 0, nxt, nw, nh);
+    mc.level.push_back(std::move(nxt));
+    mc.w.push_back(nw);
+    mc.h.push_back(nh);
+    w = nw;
+    hh = nh;
   }
-  int levels = 1;
-  for(int m = std::max(w, hh); m > 1; m >>= 1)
-    levels++;
+}
+
+int createTexture(b200pt* h, const b200pt_texture& src, const MipChain& mc, TexRes& out, DevTex& dev)
+{
+  const int levels = (int)mc.level.size();
   cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
-  CK(cudaMallocMipmappedArray(&out.arr, &fmt, make_cudaExtent((size_t)w, (size_t)hh, 0), (unsigned)levels));
-  std::vector<uint8_t> cur(src.rgba8, src.rgba8 + (size_t)w * hh * 4), nxt;
+  CK(cudaMallocMipmappedArray(&out.arr, &fmt, make_cudaExtent((size_t)src.width, (size_t)src.height, 0), (unsigned)levels));
   for(int l = 0; l < levels; l++)
   {
     cudaArray_t la;
     CK(cudaGetMipmappedArrayLevel(&la, out.arr, (unsigned)l));
-    CK(cudaMemcpy2DToArray(la, 0, 0, cur.data(), (size_t)w * 4, (size_t)w * 4, (size_t)hh, cudaMemcpyHostToDevice));
-    if(l + 1 < levels)
-    {
-      const int nw = std::max(1, w / 2), nh = std::max(1, hh / 2);
-      downsample(cur, w, hh, src.srgb != 0, nxt, nw, nh);
-      cur.swap(nxt);
-      w = nw;
-      hh = nh;
-    }
+    CK(cudaMemcpy2DToArray(la, 0, 0, mc.level[l].data(), (size_t)mc.w[l] * 4, (size_t)mc.w[l] * 4, (size_t)mc.h[l], cudaMemcpyHostToDevice));
   }
   cudaResourceDesc rd{};
   rd.resType = cudaResourceTypeMipmappedArray;
@@ -827,8 +865,6 @@ int b200pt_create(b200pt_t** out, int cuda_device)
   cudaMemset(h->dStats, 0, sizeof(DevStats));
   cudaMalloc((void**)&h->dCounters, sizeof(uint32_t) * 2 * kMaxIters);
   cudaMallocHost((void**)&h->hCount, sizeof(uint32_t) * 4);
-  cudaEventCreate(&h->ev[0]);
-  cudaEventCreate(&h->ev[1]);
   *out = h;
   return B200PT_OK;
 }
@@ -848,8 +884,11 @@ void b200pt_destroy(b200pt_t* h)
   cudaFree(h->dStats);
   cudaFree(h->dCounters);
   cudaFreeHost(h->hCount);
-  cudaEventDestroy(h->ev[0]);
-  cudaEventDestroy(h->ev[1]);
+  for(auto& e : h->evPool)
+  {
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
   cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -949,9 +988,30 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
   // --- textures ---
   std::vector<DevTex> devTex(s->numTextures);
   h->texRes.resize(s->numTextures);
-  for(uint32_t i = 0; i < s->numTextures; i++)
-    if((rc = createTexture(h, s->textures[i], h->texRes[i], devTex[i])))
-      return rc;
+  {
+    for(uint32_t i = 0; i < s->numTextures; i++)
+      if(s->textures[i].width <= 0 || s->textures[i].height <= 0 || !s->textures[i].rgba8)
+      {
+        h->err = "texture without pixels";
+        return B200PT_E_INVALID;
+      }
+    std::vector<MipChain>    chains(s->numTextures);
+    std::atomic<uint32_t>    nextTex{0};
+    std::vector<std::thread> workers;
+    auto                     job = [&]() {
+      for(uint32_t i = nextTex.fetch_add(1); i < s->numTextures; i = nextTex.fetch_add(1))
+        buildMipChain(s->textures[i], chains[i]);
+    };
+    const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), s->numTextures));
+    for(unsigned t = 1; t < nt; t++)
+      workers.emplace_back(job);
+    job();
+    for(auto& t : workers)
+      t.join();
+    for(uint32_t i = 0; i < s->numTextures; i++)
+      if((rc = createTexture(h, s->textures[i], chains[i], h->texRes[i], devTex[i])))
+        return rc;
+  }
   DevTex* dTex;
   if((rc = upload(h, h->sceneAllocs, devTex.data(), devTex.size(), &dTex)))
     return rc;
@@ -1231,7 +1291,19 @@ int b200pt_set_profiling(b200pt_t* h, int enabled)
 {
   if(!h)
     return B200PT_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  flushEvents(h);
   h->profiling = enabled != 0;
+  if(h->profiling && h->evPool.empty())
+  {
+    h->evPool.resize(2048);
+    for(auto& e : h->evPool)
+    {
+      CK(cudaEventCreate(&e.a));
+      CK(cudaEventCreate(&e.b));
+      e.cat = 3;
+    }
+  }
   return B200PT_OK;
 }
 
@@ -1279,17 +1351,23 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
   uint32_t*    cntPost = h->dCounters + kMaxIters;  // [kMaxIters]
   CK(cudaMemsetAsync(h->dCounters, 0, sizeof(uint32_t) * 2 * kMaxIters, st));
 
-  float tTrace = 0, tShade = 0, tPost = 0, tOther = 0;
-  auto  timed = [&](float& acc, auto&& launch) {
+  enum
+  {
+    tTrace = 0,
+    tShade = 1,
+    tPost = 2,
+    tOther = 3
+  };
+  auto timed = [&](int cat, auto&& launch) {
     if(h->profiling)
     {
-      cudaEventRecord(h->ev[0], st);
+      if(h->evUsed == h->evPool.size())
+        flushEvents(h);
+      b200pt::EvRec& r = h->evPool[h->evUsed++];
+      r.cat = cat;
+      cudaEventRecord(r.a, st);
       launch();
-      cudaEventRecord(h->ev[1], st);
-      cudaEventSynchronize(h->ev[1]);
-      float ms = 0;
-      cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
-      acc += ms;
+      cudaEventRecord(r.b, st);
     }
     else
       launch();
@@ -1337,14 +1415,6 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
   }
   timed(tOther, [&] { k_accumulate<<<gridWide, 256, 0, st>>>(h->P, F, h->dAccum); });
   CK(cudaGetLastError());
-  if(h->profiling)
-  {
-    h->msTrace += tTrace;
-    h->msShade += tShade;
-    h->msShadow += tPost;
-    h->msOther += tOther;
-    h->msTotal += tTrace + tShade + tPost + tOther;
-  }
   return B200PT_OK;
 }
 
@@ -1362,12 +1432,16 @@ int b200pt_get_stats(b200pt_t* h, b200pt_stats* out)
   out->pathsStarted = d.pathsStarted;
   out->nodesVisited = d.nodesVisited;
   out->trisTested = d.trisTested;
-  out->msTraceClosest = h->msTrace;
-  out->msTraceShadow = h->msShadow;
-  out->msShade = h->msShade;
-  out->msOther = h->msOther;
-  out->msTotal = h->msTotal;
+  flushEvents(h);
+  out->msTraceClosest = h->msCat[0];
+  out->msShade = h->msCat[1];
+  out->msTraceShadow = h->msCat[2];
+  out->msOther = h->msCat[3];
+  out->msTotal = h->msCat[0] + h->msCat[1] + h->msCat[2] + h->msCat[3];
   out->kernelLaunches = h->kernelLaunches;
+  out->launchesTraceClosest = h->launchesCat[0];
+  out->launchesShade = h->launchesCat[1];
+  out->launchesTraceShadow = h->launchesCat[2];
   return B200PT_OK;
 }
 
@@ -1378,7 +1452,12 @@ int b200pt_reset_stats(b200pt_t* h)
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaMemset(h->dStats, 0, sizeof(DevStats)));
-  h->msTrace = h->msShadow = h->msShade = h->msOther = h->msTotal = 0;
+  flushEvents(h);
+  for(int k = 0; k < 4; k++)
+  {
+    h->msCat[k] = 0;
+    h->launchesCat[k] = 0;
+  }
   h->kernelLaunches = 0;
   return B200PT_OK;
 }

@@ -47,8 +47,8 @@ class Resources:
 class PathTracer:
     """Drop-in for the reference's PathTracer renderer, backed by the CUDA library."""
 
-    def __init__(self, device=0):
-        self._L = _lib.lib()
+    def __init__(self, device=0, count_traversal=False):
+        self._L = _lib.lib(count_traversal)
         self._h = C.c_void_p()
         self._device = device
         # PathtracePushConstant defaults (shaders/shaderio.h:181-190) + registerParameters names

@@ -1,0 +1,352 @@
+"""Seeded procedural stand-ins for the BASELINE scenes that are not in the container.
+
+The Khronos sample assets BASELINE.json names (Sponza, DamagedHelmet, DragonDispersion) are not
+available offline.  `synth_sponza` is the stand-in the survey specifies: a seeded
+atrium of 262 144 instanced triangles, 25 materials, value-noise baseColor(sRGB) / metallic-roughness /
+normal textures and ~10 % alpha-MASK foliage quads.  `synth_glass` is the transmission/volume case.
+Everything is deterministic in `seed` so the oracle, the CUDA path and the bench see identical bytes.
+"""
+import math
+
+import numpy as np
+
+from .scene import Camera, Scene
+
+
+# ------------------------------------------------------------------------------------------------
+# mesh helpers
+# ------------------------------------------------------------------------------------------------
+def param_surface(f, nu, nv, uv_scale=(1.0, 1.0)):
+    """Tessellate p = f(u, v), u,v in [0,1], into nu x nv quads (2 triangles each, CCW seen from +normal =
+    dP/du x dP/dv).  Returns positions, normals, uv, tangents(w=+1), indices."""
+    u = np.linspace(0.0, 1.0, nu + 1)
+    v = np.linspace(0.0, 1.0, nv + 1)
+    U, V = np.meshgrid(u, v, indexing="xy")  # [nv+1, nu+1]
+    P = f(U, V)
+    e = 1e-4
+    du = (f(np.clip(U + e, 0, 1), V) - f(np.clip(U - e, 0, 1), V))
+    dv = (f(U, np.clip(V + e, 0, 1)) - f(U, np.clip(V - e, 0, 1)))
+    n = np.cross(du, dv)
+    n /= np.maximum(np.linalg.norm(n, axis=-1, keepdims=True), 1e-20)
+    t = du / np.maximum(np.linalg.norm(du, axis=-1, keepdims=True), 1e-20)
+    t = t - n * np.sum(n * t, -1, keepdims=True)
+    t /= np.maximum(np.linalg.norm(t, axis=-1, keepdims=True), 1e-20)
+    pos = P.reshape(-1, 3).astype(np.float32)
+    nrm = n.reshape(-1, 3).astype(np.float32)
+    uv = np.stack([U * uv_scale[0], V * uv_scale[1]], -1).reshape(-1, 2).astype(np.float32)
+    tan = np.concatenate([t.reshape(-1, 3), np.ones((pos.shape[0], 1))], 1).astype(np.float32)
+    i0 = (np.arange(nv)[:, None] * (nu + 1) + np.arange(nu)[None, :]).reshape(-1)
+    i1, i2, i3 = i0 + 1, i0 + (nu + 1), i0 + (nu + 2)
+    idx = np.stack([np.stack([i0, i1, i3], 1), np.stack([i0, i3, i2], 1)], 1).reshape(-1, 3).astype(np.uint32)
+    return pos, nrm, uv, tan, idx
+
+
+def _xyz(x, y, z):
+    return np.stack([x, y, z], -1)
+
+
+def value_noise(size, octaves, rng, channels=1):
+    """Tileable multi-octave value noise in [0,1], shape [size,size,channels]
+    (smoothstep-interpolated random lattices, evaluated as two small matmuls per octave)."""
+    out = np.zeros((channels, size, size), np.float32)
+    amp, tot = 1.0, 0.0
+    for o in range(octaves):
+        n = 4 << o
+        if n > size:
+            break
+        g = rng.random((channels, n, n)).astype(np.float32)
+        x = np.arange(size, dtype=np.float32) * (n / size)
+        x0 = np.floor(x).astype(np.int64)
+        fx = x - x0
+        fx = fx * fx * (3 - 2 * fx)
+        W = np.zeros((size, n), np.float32)
+        W[np.arange(size), x0 % n] += 1 - fx
+        W[np.arange(size), (x0 + 1) % n] += fx
+        out += amp * np.matmul(np.matmul(W, g), W.T)
+        tot += amp
+        amp *= 0.5
+    return np.ascontiguousarray(np.moveaxis(out / tot, 0, -1))
+
+
+def _u8(a):
+    return np.clip(np.round(a * 255.0), 0, 255).astype(np.uint8)
+
+
+def make_texture_set(size, rng, tint):
+    """(baseColor sRGB RGBA8, metallicRoughness RGBA8 [G=rough,B=metal], normal RGBA8)."""
+    h = value_noise(size, 7, rng, 1)[..., 0]
+    detail = value_noise(size, 7, rng, 3)
+    base = np.clip(np.asarray(tint, np.float32)[None, None, :] * (0.55 + 0.6 * h[..., None]) * (0.8 + 0.4 * detail), 0, 1)
+    base_rgba = np.concatenate([_u8(base), np.full((size, size, 1), 255, np.uint8)], -1)
+    rough = np.clip(0.35 + 0.6 * value_noise(size, 6, rng, 1)[..., 0], 0, 1)
+    metal = (value_noise(size, 4, rng, 1)[..., 0] > 0.62).astype(np.float32) * 0.9
+    mr = np.stack([np.ones_like(rough), rough, metal, np.ones_like(rough)], -1)
+    # normal map from the height field (central differences, tileable)
+    s = 6.0
+    dx = (np.roll(h, -1, 1) - np.roll(h, 1, 1)) * s
+    dy = (np.roll(h, -1, 0) - np.roll(h, 1, 0)) * s
+    n = np.stack([-dx, -dy, np.ones_like(h)], -1)
+    n /= np.linalg.norm(n, axis=-1, keepdims=True)
+    nm = np.concatenate([_u8(n * 0.5 + 0.5), np.full((size, size, 1), 255, np.uint8)], -1)
+    return base_rgba, _u8(mr), nm
+
+
+def make_leaf_texture(size, rng):
+    """Foliage atlas: green sRGB colour, alpha = leaf-shaped mask (MASK mode, cutoff 0.5)."""
+    y, x = np.mgrid[0:size, 0:size].astype(np.float32) / size
+    cells = 4
+    cx, cy = (x * cells) % 1.0 - 0.5, (y * cells) % 1.0 - 0.5
+    leaf = ((cx / 0.28) ** 2 + (cy / 0.45) ** 2) < 1.0
+    vein = np.abs(cx) < 0.015
+    n = value_noise(size, 6, rng, 3)
+    col = np.clip(np.array([0.10, 0.42, 0.08], np.float32) * (0.6 + 0.9 * n), 0, 1)
+    col[vein & leaf] *= 0.6
+    alpha = leaf.astype(np.float32)
+    return np.concatenate([_u8(col), _u8(alpha)[..., None]], -1)
+
+
+# ------------------------------------------------------------------------------------------------
+# SynthSponza
+# ------------------------------------------------------------------------------------------------
+def synth_sponza(seed=1234, tex_size=2048, tri_budget=262144, detail=1.0):
+    """Procedural atrium stand-in for Sponza. `detail` scales tessellation (tests use < 1);
+    with detail=1 the instanced triangle count is exactly `tri_budget`."""
+    rng = np.random.default_rng(seed)
+    scn = Scene()
+
+    def q(n):  # tessellation scaled by detail, at least 2
+        return max(2, int(round(n * math.sqrt(detail))))
+
+    # ---- textures + 25 materials ----
+    tints = [(0.75, 0.70, 0.62), (0.62, 0.55, 0.48), (0.55, 0.30, 0.22), (0.30, 0.38, 0.55), (0.78, 0.74, 0.70), (0.45, 0.45, 0.47)]
+    tex_sets = []
+    for t in tints:
+        b, mr, nm = make_texture_set(tex_size, rng, t)
+        tex_sets.append((scn.add_texture(b, srgb=True), scn.add_texture(mr), scn.add_texture(nm)))
+    leaf_tex = scn.add_texture(make_leaf_texture(tex_size, rng), srgb=True)
+
+    mats = []
+    for m in range(24):
+        ts = tex_sets[m % len(tex_sets)]
+        uvs = 1.0 + (m % 3)
+        xf = (uvs, 0, 0, uvs, 0.13 * m, 0.07 * m)
+        kw = dict(
+            pbrBaseColorFactor=[0.7 + 0.3 * rng.random(), 0.7 + 0.3 * rng.random(), 0.7 + 0.3 * rng.random(), 1.0],
+            pbrRoughnessFactor=0.5 + 0.5 * rng.random(), pbrMetallicFactor=1.0 if m % 5 == 0 else 0.3 * rng.random(),
+            pbrBaseColorTexture=scn.add_texture_info(ts[0], 0, xf),
+            pbrMetallicRoughnessTexture=scn.add_texture_info(ts[1], 0, xf),
+            normalTexture=scn.add_texture_info(ts[2], 0, xf), normalTextureScale=0.6 + 0.4 * rng.random(),
+            doubleSided=1 if m % 4 == 1 else 0)
+        if m == 7:
+            kw.update(clearcoatFactor=1.0, clearcoatRoughness=0.05)
+        if m == 11:
+            kw.update(emissiveFactor=[1.5, 1.2, 0.8])
+        mats.append(scn.add_material(**kw))
+    leaf_mat = scn.add_material(pbrBaseColorFactor=[1, 1, 1, 1], pbrRoughnessFactor=0.6, pbrMetallicFactor=0.0,
+                                alphaMode=1, alphaCutoff=0.5, doubleSided=1,
+                                pbrBaseColorTexture=scn.add_texture_info(leaf_tex, 0))
+
+    LX, LZ, H = 15.0, 6.0, 12.0
+
+    def add(pos, nrm, uv, tan, idx, mat, matrix=None):
+        p = scn.add_primitive(pos, idx, normals=nrm, uv0=uv, tangents=tan)
+        scn.add_node(p, mat, matrix)
+        return p
+
+    def T(x, y, z, s=1.0, ry=0.0):
+        c, sn = math.cos(ry), math.sin(ry)
+        return np.array([[c * s, 0, sn * s, x], [0, s, 0, y], [-sn * s, 0, c * s, z], [0, 0, 0, 1]], np.float64)
+
+    # floor (slightly bumpy), normal up
+    def floor_f(u, v):
+        x, z = (u * 2 - 1) * LX, (1 - v * 2) * LZ
+        return _xyz(x, 0.03 * np.sin(x * 3.0) * np.sin(z * 2.5), z)
+    add(*param_surface(floor_f, q(128), q(64), (10, 4)), mats[0])
+
+    # long walls (z = -LZ facing +z, z = +LZ facing -z), short walls
+    def wall_zm(u, v):
+        return _xyz((u * 2 - 1) * LX, v * H, np.full_like(u, -LZ) + 0.05 * np.sin(u * 40) * np.sin(v * 25))
+    def wall_zp(u, v):
+        return _xyz((1 - u * 2) * LX, v * H, np.full_like(u, LZ) - 0.05 * np.sin(u * 40) * np.sin(v * 25))
+    def wall_xm(u, v):
+        return _xyz(np.full_like(u, -LX), v * H, (1 - u * 2) * LZ)
+    def wall_xp(u, v):
+        return _xyz(np.full_like(u, LX), v * H, (u * 2 - 1) * LZ)
+    add(*param_surface(wall_zm, q(64), q(32), (8, 3)), mats[1])
+    add(*param_surface(wall_zp, q(64), q(32), (8, 3)), mats[2])
+    add(*param_surface(wall_xm, q(32), q(32), (3, 3)), mats[3])
+    add(*param_surface(wall_xp, q(32), q(32), (3, 3)), mats[4])
+
+    # ceiling ring with an open slot (so the environment lights the atrium), normal down
+    def ceil_a(u, v):
+        return _xyz((u * 2 - 1) * LX, np.full_like(u, H), -LZ + v * (LZ * 0.55))
+    def ceil_b(u, v):
+        return _xyz((1 - u * 2) * LX, np.full_like(u, H), LZ - v * (LZ * 0.55))
+    add(*param_surface(ceil_a, q(64), q(16), (8, 1)), mats[5])
+    add(*param_surface(ceil_b, q(64), q(16), (8, 1)), mats[6])
+
+    # columns: one primitive, 48 instances (two rows, two storeys)
+    def column_f(u, v):
+        r = 0.35 * (1.0 + 0.12 * np.cos(u * 2 * math.pi * 12) * (v > 0.08) * (v < 0.92)) * (1.0 + 0.5 * (np.abs(v - 0.5) > 0.46))
+        a = u * 2 * math.pi
+        return _xyz(r * np.cos(a), v * 4.5, -r * np.sin(a))
+    cp = scn.add_primitive(*[x for x in _split(param_surface(column_f, q(32), q(16), (2, 4)))])
+    k = 0
+    for storey in range(2):
+        for row in (-1, 1):
+            for c in range(12):
+                x = -LX + 1.8 + c * (2 * LX - 3.6) / 11
+                scn.add_node(cp, mats[8 + (k % 4)], T(x, storey * 5.2, row * (LZ - 1.6), 1.0, 0.37 * k))
+                k += 1
+
+    # gallery slabs (upper floor) along both long sides
+    def slab(zc):
+        def f(u, v):
+            return _xyz((u * 2 - 1) * LX, np.full_like(u, 4.9) + 0.02 * np.sin(u * 60), zc + (0.5 - v) * 2.6)
+        return f
+    add(*param_surface(slab(-(LZ - 1.3)), q(64), q(8), (8, 1)), mats[12])
+    add(*param_surface(slab(LZ - 1.3), q(64), q(8), (8, 1)), mats[13])
+
+    # curtains: displaced cloth panels hanging in the arcades
+    def curtain(phase):
+        def f(u, v):
+            return _xyz((u - 0.5) * 2.2, 4.6 - v * 3.6, 0.18 * np.sin(u * 2 * math.pi * 3 + phase) * (0.3 + v))
+        return f
+    for c in range(8):
+        pos, nrm, uv, tan, idx = param_surface(curtain(1.7 * c), q(64), q(64), (2, 3))
+        p = scn.add_primitive(pos, idx, normals=nrm, uv0=uv, tangents=tan)
+        side = -1 if c % 2 == 0 else 1
+        scn.add_node(p, mats[14 + (c % 4)], T(-LX + 4.0 + (c // 2) * 7.3, 0.0, side * (LZ - 1.65), 1.0, 0.0 if side > 0 else math.pi))
+
+    # vases / spheres: one primitive, 16 instances
+    def vase_f(u, v):
+        th = v * math.pi
+        r = 0.55 * np.sin(th) * (1.0 + 0.25 * np.sin(v * 9.0)) + 0.02
+        a = u * 2 * math.pi
+        return _xyz(r * np.cos(a), 0.9 - 0.9 * np.cos(th), -r * np.sin(a))
+    vp = scn.add_primitive(*[x for x in _split(param_surface(vase_f, q(64), q(32), (3, 2)))])
+    for c in range(16):
+        x = -LX + 2.5 + (c % 8) * (2 * LX - 5.0) / 7
+        z = -1.8 if c < 8 else 1.8
+        scn.add_node(vp, mats[18 + (c % 6)], T(x, 0.0, z, 0.8 + 0.4 * rng.random(), rng.random() * 6.28))
+
+    # filler rubble strip down the middle: sized so the total hits the budget exactly (detail == 1)
+    def tri_total():
+        return scn.num_triangles()
+    foliage_quads = int(round(tri_budget * 0.10 / 2 * detail))
+    remaining = int(tri_budget * detail) - tri_total() - foliage_quads * 2
+    if remaining >= 8:
+        nv_ = 8
+        nu_ = max(1, remaining // (2 * nv_))
+        def rubble(u, v):
+            x, z = (u * 2 - 1) * (LX - 2), (v - 0.5) * 1.6
+            return _xyz(x, 0.05 + 0.12 * np.abs(np.sin(x * 5.0) * np.cos(z * 7.0)), -z)
+        add(*param_surface(rubble, nu_, nv_, (12, 1)), mats[7])
+        left = int(tri_budget * detail) - tri_total() - foliage_quads * 2
+        foliage_quads += max(0, left) // 2
+
+    # foliage: alpha-masked double-sided quads in clumps around the vases (MASK, ~10 % of triangles)
+    per_prim = 1024
+    done = 0
+    while done < foliage_quads:
+        nq = min(per_prim, foliage_quads - done)
+        vi = rng.integers(0, 16, nq)
+        vx = -LX + 2.5 + (vi % 8) * (2 * LX - 5.0) / 7
+        vz = np.where(vi < 8, -1.8, 1.8)
+        c = np.stack([vx, np.full(nq, 2.1), vz], 1) + rng.normal(size=(nq, 3)) * np.array([0.55, 0.45, 0.55])
+        ax = rng.normal(size=(nq, 3))
+        ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+        bx = np.cross(ax, rng.normal(size=(nq, 3)))
+        bx /= np.linalg.norm(bx, axis=1, keepdims=True)
+        sz = 0.10 + 0.12 * rng.random((nq, 1))
+        corners = np.stack([c - ax * sz - bx * sz, c + ax * sz - bx * sz, c + ax * sz + bx * sz, c - ax * sz + bx * sz], 1)
+        nrm = np.repeat(np.cross(ax, bx)[:, None, :], 4, 1)
+        cell = rng.integers(0, 4, (nq, 2)).astype(np.float32) * 0.25
+        uv = np.stack([cell, cell + [0.25, 0], cell + [0.25, 0.25], cell + [0, 0.25]], 1)
+        base = (np.arange(nq) * 4)[:, None]
+        idx = np.concatenate([base + [0, 1, 2], base + [0, 2, 3]], 1).reshape(-1, 3)
+        p = scn.add_primitive(corners.reshape(-1, 3), idx, normals=nrm.reshape(-1, 3), uv0=uv.reshape(-1, 2))
+        scn.add_node(p, leaf_mat)
+        done += nq
+
+    cam = Camera()
+    cam.eye = np.array([-LX + 1.5, 2.2, 0.4], np.float32)
+    cam.center = np.array([LX - 2.0, 4.0, -0.3], np.float32)
+    cam.up = np.array([0, 1, 0], np.float32)
+    cam.yfov = math.radians(60.0)
+    cam.znear, cam.zfar = 0.05, 200.0
+    scn.camera = cam
+    return scn
+
+
+def _split(t):
+    pos, nrm, uv, tan, idx = t
+    return [pos, idx, nrm, uv, None, tan, None]
+
+
+# ------------------------------------------------------------------------------------------------
+# SynthGlass: transmission + volume stand-in for DragonDispersion
+# ------------------------------------------------------------------------------------------------
+def synth_glass(seed=1234, n=96, scatter=False):
+    rng = np.random.default_rng(seed)
+    scn = Scene()
+    k = rng.random(6) * 6.28
+
+    def blob(u, v):
+        th, a = v * math.pi, u * 2 * math.pi
+        r = 1.0 + 0.12 * np.sin(3 * a + k[0]) * np.sin(4 * th + k[1]) + 0.06 * np.sin(7 * a + k[2]) * np.sin(5 * th + k[3])
+        return _xyz(r * np.sin(th) * np.cos(a), 1.15 - r * np.cos(th), -r * np.sin(th) * np.sin(a))
+    pos, nrm, uv, tan, idx = param_surface(blob, n, n // 2, (1, 1))
+    glass = scn.add_material(pbrBaseColorFactor=[1, 1, 1, 1], pbrRoughnessFactor=0.05, pbrMetallicFactor=0.0,
+                             transmissionFactor=1.0, thicknessFactor=1.0, attenuationDistance=0.5,
+                             attenuationColor=[0.85, 0.35, 0.25], ior=1.5,
+                             multiscatterColorFactor=[0.6, 0.6, 0.6] if scatter else [0, 0, 0], scatterAnisotropy=0.3)
+    scn.add_node(scn.add_primitive(pos, idx, normals=nrm, uv0=uv, tangents=tan), glass)
+
+    def ground(u, v):
+        return _xyz((u * 2 - 1) * 6, np.zeros_like(u), (1 - v * 2) * 6)
+    gp, gn, guv, gt, gi = param_surface(ground, 8, 8, (4, 4))
+    gm = scn.add_material(pbrBaseColorFactor=[0.6, 0.6, 0.6, 1], pbrRoughnessFactor=0.7, pbrMetallicFactor=0.0)
+    scn.add_node(scn.add_primitive(gp, gi, normals=gn, uv0=guv, tangents=gt), gm)
+    cam = Camera()
+    cam.eye = np.array([0.0, 1.8, 4.2], np.float32)
+    cam.center = np.array([0.0, 1.0, 0.0], np.float32)
+    cam.yfov = math.radians(45.0)
+    cam.znear, cam.zfar = 0.05, 100.0
+    scn.camera = cam
+    return scn
+
+
+def triangle_soup(n, seed=1234, extent=1.0, size=0.15):
+    """n random triangles in a cube: stress input for traversal parity tests."""
+    rng = np.random.default_rng(seed)
+    c = (rng.random((n, 1, 3)) - 0.5) * 2 * extent
+    v = c + (rng.random((n, 3, 3)) - 0.5) * 2 * size
+    scn = Scene()
+    m = scn.add_material(pbrBaseColorFactor=[0.8, 0.8, 0.8, 1], pbrMetallicFactor=0.0, doubleSided=0)
+    p = scn.add_primitive(v.reshape(-1, 3), np.arange(n * 3).reshape(-1, 3))
+    scn.add_node(p, m)
+    return scn
+
+
+def scene_state(scn):
+    """Plain-python snapshot of a Scene (for caching generated workloads)."""
+    import ctypes as C
+    cam = scn.camera
+    return dict(render_nodes=scn.render_nodes, render_prims=scn.render_prims,
+                materials=[bytes(m) for m in scn.materials], texture_infos=[bytes(t) for t in scn.texture_infos],
+                textures=scn.textures, lights=[bytes(l) for l in scn.lights],
+                camera=None if cam is None else dict(cam.__dict__))
+
+
+def scene_from_state(st):
+    from . import abi
+    scn = Scene()
+    scn.render_nodes, scn.render_prims, scn.textures = st["render_nodes"], st["render_prims"], st["textures"]
+    scn.materials = [abi.ShadeMaterial.from_buffer_copy(b) for b in st["materials"]]
+    scn.texture_infos = [abi.TextureInfo.from_buffer_copy(b) for b in st["texture_infos"]]
+    scn.lights = [abi.Light.from_buffer_copy(b) for b in st["lights"]]
+    if st["camera"] is not None:
+        scn.camera = Camera()
+        scn.camera.__dict__.update(st["camera"])
+    return scn
