@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--detail", type=float, default=1.0)
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the frame the CPU baseline renders (0 = sized for ~12 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-only", action="store_true", help="warm-up + K steps only (for runs under ncu); prints no bench line")
     return ap.parse_args()
 
 
@@ -291,6 +292,11 @@ def main():
         return r.cpu().numpy()
 
     # ---- warm-up ----
+    if args.profile_only:
+        for _ in range(args.warmup + args.steps):
+            step()
+        barrier()
+        return
     for _ in range(max(args.warmup, 3)):
         step()
     # ---- pass A: device-timed throughput (headline `value`) ----

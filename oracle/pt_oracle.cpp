@@ -21,8 +21,14 @@
 // single-triangle hits, alias-table normalisation, MIS weights, BSDF energy/reciprocity ...).
 //
 // Hardware any-hit order is unspecified in the reference (raytracer_interface.h.slang:53;
-// gltf_pathtrace.slang:798-801).  This oracle — and the CUDA path — pin it to strict
-// front-to-back order of (t, global triangle id), which is one of the orders the reference allows.
+// gltf_pathtrace.slang:798-801).  This oracle — and the CUDA path — pin it as follows:
+//   Trace:       closest FORCE_OPAQUE hit first; then the non-opaque candidates nearer than it, strictly
+//                front-to-back in (t, global triangle id) order, each consuming one rand(); the first
+//                accepted candidate commits, otherwise the opaque hit does.
+//   TraceShadow: any FORCE_OPAQUE occluder => 0 without consuming rand(); otherwise all non-opaque
+//                candidates front-to-back as in the RayQuery loop (:149-179).
+// Both are orders the reference's RayQuery/any-hit semantics allow; they make the result (and the
+// RNG stream) independent of the acceleration-structure layout.
 // =================================================================================================
 #include <algorithm>
 #include <atomic>
@@ -88,6 +94,7 @@ struct LocalStats
   uint64_t closestRays = 0, shadowRays = 0, shadedHits = 0, paths = 0, nodes = 0, tris = 0;
 };
 static thread_local LocalStats tls;
+static thread_local bool        dbgPixel = false;  // reference analogue: doDebug at pushConst.mouseCoord (gltf_pathtrace.slang:553-557)
 struct Stats
 {
   std::atomic<uint64_t> closestRays{0}, shadowRays{0}, shadedHits{0}, paths{0}, nodes{0}, tris{0};
@@ -113,8 +120,12 @@ struct Oracle
   std::vector<Texture>               textures;
   std::vector<b200pt_light>          lights;
   std::vector<FlatTri>               tris;
-  std::vector<uint32_t>              triOrder;
-  std::vector<BvhNode>               bvh;
+  struct Tree
+  {
+    std::vector<uint32_t> triOrder;
+    std::vector<BvhNode>  bvh;
+  };
+  Tree treeOpaque, treeAlpha;  // FORCE_OPAQUE triangles / any-hit (non-opaque) triangles
   // environment
   int                   envW = 0, envH = 0;
   std::vector<float>    envRgba;
@@ -410,18 +421,19 @@ static float halfArea(float3 lo, float3 hi)
   return d.x * d.y + d.y * d.z + d.z * d.x;
 }
 
-static void buildBvh(Oracle& o)
+static void buildBvh(const Oracle& scene, Oracle::Tree& o, const std::vector<uint32_t>& ids)
 {
-  const uint32_t n = (uint32_t)o.tris.size();
-  o.triOrder.resize(n);
+  const uint32_t n = (uint32_t)ids.size();
+  o.triOrder = ids;
   o.bvh.clear();
   if(n == 0)
     return;
-  std::vector<float3> lo(n), hi(n), ce(n);
-  for(uint32_t i = 0; i < n; i++)
+  const uint32_t      nAll = (uint32_t)scene.tris.size();
+  std::vector<float3> lo(nAll), hi(nAll), ce(nAll);
+  for(uint32_t k = 0; k < n; k++)
   {
-    o.triOrder[i] = i;
-    triBounds(o.tris[i], lo[i], hi[i]);
+    const uint32_t i = ids[k];
+    triBounds(scene.tris[i], lo[i], hi[i]);
     ce[i] = (lo[i] + hi[i]) * 0.5f;
   }
   o.bvh.reserve(2 * n);
@@ -601,7 +613,7 @@ static inline bool slab(const BvhNode& N, const Ray& r, float3 invD, float tmax,
 
 // closest hit with (t,id) strictly greater than (loT, loId) in lexicographic order, t in (tmin,tmax).
 // cull: apply back-face culling (closest-hit rays) honouring TRI_NOCULL.
-static bool nextHit(Oracle& o, const Ray& r, bool cull, float loT, uint32_t loId, bool haveLo, Hit& best)
+static bool nextHit(const Oracle& scene, const Oracle::Tree& o, const Ray& r, bool cull, float loT, uint32_t loId, bool haveLo, Hit& best, bool anyExit = false)
 {
   if(o.bvh.empty())
     return false;
@@ -624,7 +636,7 @@ static bool nextHit(Oracle& o, const Ray& r, bool cull, float loT, uint32_t loId
       for(uint32_t i = N.first; i < N.first + N.count; i++)
       {
         const uint32_t id = o.triOrder[i];
-        const FlatTri& T = o.tris[id];
+        const FlatTri& T = scene.tris[id];
         float          t, u, v, det;
         tris++;
         if(!intersectTri(T, r, t, u, v, det))
@@ -646,6 +658,11 @@ static bool nextHit(Oracle& o, const Ray& r, bool cull, float loT, uint32_t loId
           best.tri = id;
           best.u = u;
           best.v = v;
+          if(anyExit)
+          {
+            sp = 0;
+            break;
+          }
         }
       }
     }
@@ -679,7 +696,7 @@ static bool nextHit(Oracle& o, const Ray& r, bool cull, float loT, uint32_t loId
   tls.tris += tris;
   if(best.tri == 0xFFFFFFFFu)
     return false;
-  if(o.tris[best.tri].flags & TRI_FLIPPED)
+  if(scene.tris[best.tri].flags & TRI_FLIPPED)
     std::swap(best.u, best.v);
   return true;
 }
@@ -1148,43 +1165,63 @@ static void Trace(Oracle& o, const Ray& ray, HitPayload& p, uint32_t& seed)
   p.hitT = INFINITE_F;
   p.rnodeID = p.rprimID = p.primitiveID = -1;
   p.bx = p.by = 0.f;
-  float    loT = 0.f;
-  uint32_t loId = 0;
-  bool     haveLo = false;
-  for(;;)
+  auto commit = [&](const Hit& h) {
+    const FlatTri& T = o.tris[h.tri];
+    p.hitT = h.t;
+    p.rnodeID = (int)T.rnode;
+    p.rprimID = o.nodes[T.rnode].renderPrimID;
+    p.primitiveID = (int)T.prim;
+    p.bx = h.u;
+    p.by = h.v;
+  };
+  // 1. closest FORCE_OPAQUE hit
+  Hit  ho;
+  bool haveOpaque = nextHit(o, o.treeOpaque, ray, true, 0.f, 0u, false, ho);
+  // 2. non-opaque candidates nearer than it, front to back (stochastic alpha, :104-111)
+  if(!o.treeAlpha.bvh.empty())
   {
-    Hit h;
-    if(!nextHit(o, ray, true, loT, loId, haveLo, h))
-      return;
-    const FlatTri&            T = o.tris[h.tri];
-    const b200pt_render_node& node = o.nodes[T.rnode];
-    bool                      commit = (T.flags & TRI_OPAQUE) != 0;
-    if(!commit)
+    Ray r2 = ray;
+    if(haveOpaque)
+      r2.tmax = ho.t;
+    float    loT = 0.f;
+    uint32_t loId = 0;
+    bool     haveLo = false;
+    for(;;)
     {
-      float3 bary = f3(1.0f - h.u - h.v, h.u, h.v);
-      float  opacity = getOpacity(o, node, o.prims[node.renderPrimID], T.prim, bary);
-      commit = rnd(seed) <= opacity;
+      Hit h;
+      if(!nextHit(o, o.treeAlpha, r2, true, loT, loId, haveLo, h))
+        break;
+      const FlatTri&            T = o.tris[h.tri];
+      const b200pt_render_node& node = o.nodes[T.rnode];
+      const float3              bary = f3(1.0f - h.u - h.v, h.u, h.v);
+      const float               opacity = getOpacity(o, node, o.prims[node.renderPrimID], T.prim, bary);
+      if(rnd(seed) <= opacity)
+      {
+        commit(h);
+        return;
+      }
+      loT = h.t;
+      loId = h.tri;
+      haveLo = true;
     }
-    if(commit)
-    {
-      p.hitT = h.t;
-      p.rnodeID = (int)T.rnode;
-      p.rprimID = node.renderPrimID;
-      p.primitiveID = (int)T.prim;
-      p.bx = h.u;
-      p.by = h.v;
-      return;
-    }
-    loT = h.t;
-    loId = h.tri;
-    haveLo = true;
   }
+  if(haveOpaque)
+    commit(ho);
 }
 
 static float3 TraceShadow(Oracle& o, const Ray& ray, uint32_t& seed, bool initialInside)
 {
   tls.shadowRays++;
-  float3   total = f3(1.0f);
+  // 1. any opaque occluder
+  {
+    Hit h;
+    if(nextHit(o, o.treeOpaque, ray, false, 0.f, 0u, false, h, true))
+      return f3(0.0f);
+  }
+  float3 total = f3(1.0f);
+  if(o.treeAlpha.bvh.empty())
+    return total;
+  // 2. every non-opaque candidate, front to back (:149-179)
   bool     isInside = initialInside;
   float    prevHitT = 0.f;
   float    loT = 0.f;
@@ -1193,11 +1230,9 @@ static float3 TraceShadow(Oracle& o, const Ray& ray, uint32_t& seed, bool initia
   for(;;)
   {
     Hit h;
-    if(!nextHit(o, ray, false, loT, loId, haveLo, h))
+    if(!nextHit(o, o.treeAlpha, ray, false, loT, loId, haveLo, h))
       return total;
-    const FlatTri& T = o.tris[h.tri];
-    if(T.flags & TRI_OPAQUE)
-      return f3(0.0f);
+    const FlatTri&            T = o.tris[h.tri];
     const b200pt_render_node& node = o.nodes[T.rnode];
     const Prim&               P = o.prims[node.renderPrimID];
     float3                    bary = f3(1.0f - h.u - h.v, h.u, h.v);
@@ -1515,7 +1550,11 @@ static PathStepResult processVolumeSegment(const Ctx& c, float hitDistance, Ray&
     {
       pt.scatterBounces++;
       pt.coneWidth += pt.coneSpread * length(ray.o - originBefore);
-      pt.radiance += volumeScatterNEE(c, pt.medium, ray.o, wiBefore, pt.throughput, seed);
+      const float3 nee = volumeScatterNEE(c, pt.medium, ray.o, wiBefore, pt.throughput, seed);
+      pt.radiance += nee;
+      if(dbgPixel)
+        fprintf(stderr, "DBG scatter n=%d o=%.9g %.9g %.9g d=%.9g %.9g %.9g thr=%.9g %.9g %.9g pdf=%.9g nee=%.9g %.9g %.9g seed=%u\n", pt.scatterBounces, ray.o.x, ray.o.y, ray.o.z, ray.d.x,
+                ray.d.y, ray.d.z, pt.throughput.x, pt.throughput.y, pt.throughput.z, pt.lastSamplePdf, nee.x, nee.y, nee.z, seed);
       if(pt.scatterBounces >= 64)
       {
         float rrPcont = fminf(maxc(pt.throughput) + 0.001f, 0.95f);
@@ -1565,6 +1604,9 @@ static PathStepResult pathTraceOneBounce(const Ctx& c, Ray& ray, uint32_t& seed,
     return eBreak;
   }
 
+  if(dbgPixel)
+    fprintf(stderr, "DBG hit t=%.9g rnode=%d prim=%d bary=%.9g %.9g org=%.9g %.9g %.9g dir=%.9g %.9g %.9g seed=%u depth=%d\n", payload.hitT, payload.rnodeID,
+            payload.primitiveID, payload.bx, payload.by, ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, seed, pt.surfaceDepth);
   const b200pt_render_node& renderNode = o.nodes[payload.rnodeID];
   const Prim&               P = o.prims[payload.rprimID];
   const float3              barys = f3(1.0f - payload.bx - payload.by, payload.bx, payload.by);
@@ -1616,6 +1658,11 @@ static PathStepResult pathTraceOneBounce(const Ctx& c, Ray& ray, uint32_t& seed,
   sampleLights(c, hit.pos, pbrMat.N, seed, directLight, false);
 
   bounce.nextEventValid = (dot(directLight.direction, hit.nrm) > 0.0f || pbrMat.diffuseTransmissionFactor > 0.0f) && directLight.pdf != 0.0f;
+  if(dbgPixel)
+    fprintf(stderr, "DBG shade pos=%.9g %.9g %.9g nrm=%.9g %.9g %.9g gn=%.9g %.9g %.9g N=%.9g %.9g %.9g rough=%.9g %.9g metal=%.9g base=%.9g %.9g %.9g L=%.9g %.9g %.9g lpdf=%.9g valid=%d seed=%u\n",
+            hit.pos.x, hit.pos.y, hit.pos.z, hit.nrm.x, hit.nrm.y, hit.nrm.z, hit.geonrm.x, hit.geonrm.y, hit.geonrm.z, pbrMat.N.x, pbrMat.N.y, pbrMat.N.z, pbrMat.roughness.x,
+            pbrMat.roughness.y, pbrMat.metallic, pbrMat.baseColor.x, pbrMat.baseColor.y, pbrMat.baseColor.z, directLight.direction.x, directLight.direction.y,
+            directLight.direction.z, directLight.pdf, (int)bounce.nextEventValid, seed);
 
   if(bounce.nextEventValid)
   {
@@ -1640,6 +1687,9 @@ static PathStepResult pathTraceOneBounce(const Ctx& c, Ray& ray, uint32_t& seed,
     float a = rnd(seed), b = rnd(seed), cc = rnd(seed);
     sd.xi = f3(a, b, cc);
     bsdfSample(sd, pbrMat);
+    if(dbgPixel)
+      fprintf(stderr, "DBG sample xi=%.9g %.9g %.9g k2=%.9g %.9g %.9g bop=%.9g %.9g %.9g pdf=%.9g ev=%d contrib=%.9g %.9g %.9g\n", sd.xi.x, sd.xi.y, sd.xi.z, sd.k2.x, sd.k2.y,
+              sd.k2.z, sd.bsdf_over_pdf.x, sd.bsdf_over_pdf.y, sd.bsdf_over_pdf.z, sd.pdf, sd.event_type, bounce.contribution.x, bounce.contribution.y, bounce.contribution.z);
     pt.throughput *= sd.bsdf_over_pdf;
     ray.d = sd.k2;
     pt.lastSamplePdf = sd.pdf;
@@ -1695,6 +1745,9 @@ static SampleResult pathTrace(const Ctx& c, Ray ray, uint32_t& seed)
       sr.tmin = 0.0f;
       sr.tmax = bounce.shadowRayDist;
       float3 shadowFactor = TraceShadow(*c.o, sr, seed, false);
+      if(dbgPixel)
+        fprintf(stderr, "DBG shadow o=%.9g %.9g %.9g d=%.9g %.9g %.9g tmax=%.9g T=%.9g %.9g %.9g\n", sr.o.x, sr.o.y, sr.o.z, sr.d.x, sr.d.y, sr.d.z, sr.tmax, shadowFactor.x,
+                shadowFactor.y, shadowFactor.z);
       pt.radiance += bounce.contribution * shadowFactor;
     }
     if(pt.surfaceDepth >= 3)
@@ -1771,6 +1824,7 @@ static void processPixel(const Ctx& c, int x, int y, float* px)
   const float2 imageSize = f2(c.fi->imageSize[0], c.fi->imageSize[1]);
   const float2 samplePos = f2((float)x, (float)y);
   uint32_t     seed = xxhash32((uint32_t)x, (uint32_t)y, (uint32_t)c.pc->frameCount);
+  dbgPixel = ((float)x == c.pc->mouseCoord[0] && (float)y == c.pc->mouseCoord[1]);
   const bool   firstFrame = (c.pc->flags & B200PT_PT_FIRST_FRAME) != 0;
   float2       jitter = f2(0.5f, 0.5f);
   {
@@ -1906,7 +1960,11 @@ int oracle_set_scene(void* h, const b200pt_scene_desc* s)
       o.tris.push_back(T);
     }
   }
-  buildBvh(o);
+  std::vector<uint32_t> idsO, idsA;
+  for(uint32_t i = 0; i < (uint32_t)o.tris.size(); i++)
+    ((o.tris[i].flags & TRI_OPAQUE) ? idsO : idsA).push_back(i);
+  buildBvh(o, o.treeOpaque, idsO);
+  buildBvh(o, o.treeAlpha, idsA);
   return 0;
 }
 

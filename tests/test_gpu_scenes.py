@@ -120,18 +120,45 @@ def test_render_parity_shader_ball(shader_ball_scene, std_env, oracle_mod):
     assert e <= 1e-3
 
 
-@pytest.mark.parametrize("scatter", [False, True])
-def test_render_parity_glass_volume(std_env, oracle_mod, scatter):
-    """Transmission + volume (+ scatter random walk, NEE inside the medium, coloured shadow transmission)."""
+def test_render_parity_glass_volume(std_env, oracle_mod):
+    """Transmission + volume absorption (Beer), IOR swap inside, coloured shadow transmission through the
+    any-hit tree: stream-replicated parity, rel RMSE <= 1e-3."""
     from vk_gltf_renderer_b200 import synth
-    scn = synth.synth_glass(n=48, scatter=scatter)
+    scn = synth.synth_glass(n=48, scatter=False)
     o = _oracle(oracle_mod, scn, std_env)
     ref = oracle_mod.render(o, scn.camera, 128, 128, 8, max_depth=12)
     pt, img = _gpu_render(scn, std_env, 128, 128, 8, ptMaxDepth=12)
     assert np.isfinite(img).all()
     e = rel_rmse(img, ref)
-    print("glass scatter=%s rel RMSE" % scatter, e)
+    print("glass rel RMSE", e)
     assert e <= 1e-3
+
+
+def test_render_parity_glass_volume_scatter_statistical(std_env, oracle_mod):
+    """KHR_materials_volume_scatter: in-volume random walks (up to 64+ scatters, NEE inside the medium).
+    Paths with ~100 chaotic events amplify 1e-7 libm differences to O(1), so per-pixel stream parity is
+    not attainable by ANY two fp32 implementations; SURVEY.md section 8d's fallback protocol applies:
+    (1) the two estimators must agree exactly on the early part of every path => the median per-pixel
+    relative difference stays tiny, (2) no bias: image-mean radiance within 1 %, 16x16-tile means within
+    5 sigma of the sampling error, (3) identical ray budgets within 0.5 %."""
+    from vk_gltf_renderer_b200 import synth
+    scn = synth.synth_glass(n=48, scatter=True)
+    o = _oracle(oracle_mod, scn, std_env)
+    frames = 16
+    ref = oracle_mod.render(o, scn.camera, 128, 128, frames, max_depth=12)
+    pt, img = _gpu_render(scn, std_env, 128, 128, frames, ptMaxDepth=12)
+    assert np.isfinite(img).all()
+    rel = np.abs(img[..., :3] - ref[..., :3]).sum(-1) / np.maximum(ref[..., :3].sum(-1), 1e-3)
+    print("glass scatter: median rel diff", np.median(rel), "mean ratio", img[..., :3].mean() / ref[..., :3].mean())
+    assert np.median(rel) <= 1e-4
+    assert abs(img[..., :3].mean() / ref[..., :3].mean() - 1.0) <= 1e-2
+    lum_g = img[..., :3].mean(-1).reshape(8, 16, 8, 16).mean((1, 3))
+    lum_r = ref[..., :3].mean(-1).reshape(8, 16, 8, 16).mean((1, 3))
+    sig = ref[..., :3].mean(-1).reshape(8, 16, 8, 16).std((1, 3)) / 16.0 + 1e-4
+    assert (np.abs(lum_g - lum_r) <= 5.0 * sig + 1e-2 * lum_r).all()
+    st, so = pt.stats(), o.stats()
+    assert abs(st["closestRays"] / so["closestRays"] - 1.0) <= 5e-3
+    assert abs(st["shadowRays"] / so["shadowRays"] - 1.0) <= 5e-3
 
 
 def test_multisample_frames_and_tiling(box_scene, std_env, oracle_mod):

@@ -147,23 +147,121 @@ __global__ void __launch_bounds__(256) k_raygen(PathState P, const __grid_consta
   }
 }
 
-__global__ void __launch_bounds__(128) k_trace(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn, DevStats* stats)
+// Persistent-warp scheme (Aila & Laine 2009 style): all 32 lanes of a warp reconverge at the fetch point
+// (__syncwarp), lanes that finished their ray take the next queue entries from a global cursor, then the
+// warp walks the tree until fewer than kRefillThreshold lanes are still busy and goes back to refill.
+constexpr int kRefillThreshold = 22;
+
+// full-warp fetch: every lane calls it; lanes with need==true receive the next queue slot or 0xFFFFFFFF
+__device__ __forceinline__ uint32_t fetchWork(bool need, uint32_t* workCounter, uint32_t count)
 {
+  const unsigned want = __ballot_sync(0xffffffffu, need);
+  if(want == 0)
+    return 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(want) - 1;
+  uint32_t  base = 0;
+  if(lane == leader)
+    base = atomicAdd(workCounter, (uint32_t)__popc(want));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if(!need)
+    return 0xFFFFFFFFu;
+  const uint32_t k = base + (uint32_t)__popc(want & ((1u << lane) - 1u));
+  return k < count ? k : 0xFFFFFFFFu;
+}
+
+// IRaytracer::Trace for every path in the queue.
+__global__ void __launch_bounds__(128) k_trace(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn,
+                                               uint32_t* workCounter, DevStats* stats)
+{
+  stageSrgbLut(S.lutSrgb);
   const uint32_t count = *cntIn;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for(uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
+  TravState      T;
+  int            path = -1;  // -1: lane needs a ray, -2: queue exhausted
+  int            phase = 0;  // 0: opaque tree, 1: alpha (any-hit) tree
+  TraceHit       ho;
+  uint32_t       seed = 0, seedIn = 0;
+  float          tmaxRay = 0.f;
+  ho.slot = 0xFFFFFFFFu;
+  for(;;)
   {
-    const uint32_t i = q[k];
-    const float4   o = P.rayO[i];
-    const float4   d = P.rayD[i];
-    uint32_t       seed = 0;
-    if(!S.allOpaque)
-      seed = __float_as_uint(P.misc[i].w);
-    const uint32_t seedIn = seed;
-    const TraceHit h = traceClosest(S, xyz(o), xyz(d), 0.0f, d.w, seed, stats);
-    P.hit[i] = f4(h.t, h.u, h.v, __uint_as_float(h.slot));
-    if(seed != seedIn)
-      reinterpret_cast<uint32_t*>(&P.misc[i])[3] = seed;
+    __syncwarp();
+    const bool     need = (path == -1);
+    const uint32_t k = fetchWork(need, workCounter, count);
+    if(need)
+    {
+      if(k == 0xFFFFFFFFu)
+        path = -2;
+      else
+      {
+        path = (int)q[k];
+        const float4 o = P.rayO[path];
+        const float4 d = P.rayD[path];
+        tmaxRay = d.w;
+        if(S.hasAlpha)
+          seed = seedIn = __float_as_uint(P.misc[path].w);
+        phase = 0;
+        T.init(S.bvh, xyz(o), xyz(d), 0.0f, tmaxRay, true, false, false, 0.f, 0u);
+      }
+    }
+    if(__all_sync(0xffffffffu, path == -2))
+      break;
+    while(path >= 0)
+    {
+      if(T.step())
+      {
+        T.flushCounters(&stats->nodesVisited, &stats->trisTested);
+        TraceHit res;
+        bool     done = false;
+        if(phase == 0)
+        {
+          ho = T.result();
+          if(S.hasAlpha)
+          {
+            // non-opaque candidates nearer than the opaque hit, front to back (raytracer_interface.h.slang:82-112)
+            phase = 1;
+            T.init(S.bvhAlpha, T.org, T.dir, 0.0f, (ho.slot != 0xFFFFFFFFu) ? ho.t : tmaxRay, true, false, false, 0.f, 0u);
+          }
+          else
+          {
+            res = ho;
+            done = true;
+          }
+        }
+        else
+        {
+          const TraceHit h = T.result();
+          if(h.slot == 0xFFFFFFFFu)
+          {
+            res = ho;
+            done = true;
+          }
+          else
+          {
+            const uint2               meta = S.triMeta[h.slot];
+            const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
+            const float               opacity = getOpacity(S, node, S.prims[node.renderPrimID], meta.y, f3(1.0f - h.u - h.v, h.u, h.v));
+            if(rnd(seed) <= opacity)
+            {
+              res = h;
+              done = true;
+            }
+            else
+              T.init(S.bvhAlpha, T.org, T.dir, 0.0f, T.tmax, true, false, true, h.t, h.gid);
+          }
+        }
+        if(done)
+        {
+          P.hit[path] = f4(res.t, res.u, res.v, __uint_as_float(res.slot));
+          if(seed != seedIn)
+            reinterpret_cast<uint32_t*>(&P.misc[path])[3] = seed;
+          path = -1;
+          break;
+        }
+      }
+      if(__popc(__activemask()) < kRefillThreshold)
+        break;
+    }
   }
   if(blockIdx.x == 0 && threadIdx.x == 0)
     atomicAdd(&stats->closestRays, (unsigned long long)count);
@@ -172,6 +270,7 @@ __global__ void __launch_bounds__(128) k_trace(PathState P, DevScene S, const ui
 __global__ void __launch_bounds__(128) k_shade(PathState P, DevScene S, const __grid_constant__ FrameParams F, const uint32_t* __restrict__ q,
                                                const uint32_t* __restrict__ cntIn, uint32_t* qPost, uint32_t* cntPost, uint32_t* qNext, uint32_t* cntNext, DevStats* stats)
 {
+  stageSrgbLut(S.lutSrgb);
   const uint32_t count = *cntIn;
   const uint32_t stride = gridDim.x * blockDim.x;
   for(uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
@@ -226,6 +325,13 @@ __global__ void __launch_bounds__(128) k_shade(PathState P, DevScene S, const __
     const uint2               meta = S.triMeta[slot];
     const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
     const DevPrim             prim = S.prims[node.renderPrimID];
+#ifdef B200PT_DEBUG
+    // reference analogue: doDebug at pushConst.mouseCoord (gltf_pathtrace.slang:553-557)
+    const bool dbgPixel = ((float)(i % (uint32_t)F.width) == F.pc.mouseCoord[0] && (float)(F.tileY0 + i / (uint32_t)F.width) == F.pc.mouseCoord[1]);
+    if(dbgPixel)
+      printf("DBG hit t=%.9g rnode=%d prim=%d bary=%.9g %.9g org=%.9g %.9g %.9g dir=%.9g %.9g %.9g seed=%u depth=%d\n", hitT, (int)(meta.x & 0x0fffffffu), (int)meta.y, hr.y, hr.z,
+             org.x, org.y, org.z, dir.x, dir.y, dir.z, seed, (int)depth);
+#endif
     const float3              bary = f3(1.0f - hr.y - hr.z, hr.y, hr.z);
     const HitState            hit = getHitState(prim, bary, node.worldToObject, node.objectToWorld, meta.y, dir);
     statAdd(&stats->shadedHits, 1ull);
@@ -289,6 +395,12 @@ __global__ void __launch_bounds__(128) k_shade(PathState P, DevScene S, const __
               flags |= PF_SHADOW_VALID | PF_SHADOW_INSIDE;
             }
             flags |= PF_POST_VOLUME;
+#ifdef B200PT_DEBUG
+            if(dbgPixel)
+              printf("DBG scatter n=%d o=%.9g %.9g %.9g d=%.9g %.9g %.9g thr=%.9g %.9g %.9g pdf=%.9g neeC=%.9g %.9g %.9g valid=%d seed=%u\n", (int)scatterBounces, org.x, org.y, org.z, dir.x, dir.y,
+                     dir.z, throughput.x, throughput.y, throughput.z, lastSamplePdf, (flags & PF_SHADOW_VALID) ? P.shC[i].x : 0.f, (flags & PF_SHADOW_VALID) ? P.shC[i].y : 0.f,
+                     (flags & PF_SHADOW_VALID) ? P.shC[i].z : 0.f, (int)((flags & PF_SHADOW_VALID) != 0), seed);
+#endif
           }
           else
             throughput *= expv((f3(maxExt) - ext) * hitT);
@@ -314,6 +426,13 @@ __global__ void __launch_bounds__(128) k_shade(PathState P, DevScene S, const __
     const DirectLight directLight = sampleLights(S, F, hit.pos, seed);
     const bool nextEventValid = (dot(directLight.direction, hit.nrm) > 0.0f || pbrMat.diffuseTransmissionFactor > 0.0f) && directLight.pdf != 0.0f;
     float3     contribution = f3(0.0f);
+#ifdef B200PT_DEBUG
+    if(dbgPixel)
+      printf("DBG shade pos=%.9g %.9g %.9g nrm=%.9g %.9g %.9g gn=%.9g %.9g %.9g N=%.9g %.9g %.9g rough=%.9g %.9g metal=%.9g base=%.9g %.9g %.9g L=%.9g %.9g %.9g lpdf=%.9g valid=%d seed=%u\n",
+             hit.pos.x, hit.pos.y, hit.pos.z, hit.nrm.x, hit.nrm.y, hit.nrm.z, hit.geonrm.x, hit.geonrm.y, hit.geonrm.z, pbrMat.N.x, pbrMat.N.y, pbrMat.N.z, pbrMat.roughness.x,
+             pbrMat.roughness.y, pbrMat.metallic, pbrMat.baseColor.x, pbrMat.baseColor.y, pbrMat.baseColor.z, directLight.direction.x, directLight.direction.y,
+             directLight.direction.z, directLight.pdf, (int)nextEventValid, seed);
+#endif
     if(nextEventValid)
     {
       const float    a = rnd(seed), b = rnd(seed), c = rnd(seed);
@@ -331,6 +450,11 @@ __global__ void __launch_bounds__(128) k_shade(PathState P, DevScene S, const __
     {
       const float      a = rnd(seed), b = rnd(seed), c = rnd(seed);
       const BsdfSample sd = bsdfSample(pbrMat, -dir, f3(a, b, c));
+#ifdef B200PT_DEBUG
+      if(dbgPixel)
+        printf("DBG sample xi=%.9g %.9g %.9g k2=%.9g %.9g %.9g bop=%.9g %.9g %.9g pdf=%.9g ev=%d contrib=%.9g %.9g %.9g\n", a, b, c, sd.k2.x, sd.k2.y, sd.k2.z, sd.bsdf_over_pdf.x,
+               sd.bsdf_over_pdf.y, sd.bsdf_over_pdf.z, sd.pdf, sd.event_type, contribution.x, contribution.y, contribution.z);
+#endif
       throughput *= sd.bsdf_over_pdf;
       dir = sd.k2;
       lastSamplePdf = sd.pdf;
@@ -372,82 +496,191 @@ __global__ void __launch_bounds__(128) k_shade(PathState P, DevScene S, const __
   }
 }
 
-__global__ void __launch_bounds__(128) k_post(PathState P, DevScene S, const __grid_constant__ FrameParams F, const uint32_t* __restrict__ q,
-                                              const uint32_t* __restrict__ cntIn, uint32_t* qNext, uint32_t* cntNext, DevStats* stats)
+// pathTrace() tail for every path that survived shading: delayed NEE visibility (TraceShadow), Russian
+// roulette, depth++ (gltf_pathtrace.slang:462-485).  Same persistent-warp scheme as k_trace; paths without a
+// shadow ray finish immediately and their lanes are refilled.
+__device__ void finishPost(const PathState& P, const FrameParams& F, uint32_t i, uint32_t flags, uint32_t seed, bool haveShadow, float3 Tfac,
+                           uint32_t* qNext, uint32_t* cntNext, DevStats* stats)
 {
-  const uint32_t count = *cntIn;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for(uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
+  const float4 misc = P.misc[i];
+  const float4 rad4 = P.rad[i];
+  float3       radiance = xyz(rad4);
+  if(haveShadow)
+    radiance += xyz(P.shC[i]) * Tfac;
+  const float4 thr4 = P.thr[i];
+  float3       throughput = xyz(thr4);
+  uint32_t     depth = flags & PF_DEPTH_MASK;
+  bool         alive = true, thrDirty = false;
+  if(flags & PF_POST_VOLUME)
   {
-    const uint32_t i = q[k];
-    float4         misc = P.misc[i];
-    uint32_t       flags = __float_as_uint(misc.z);
-    uint32_t       seed = __float_as_uint(misc.w);
-    float4         rad4 = P.rad[i];
-    float3         radiance = xyz(rad4);
-    bool           radDirty = false;
-    if(flags & PF_SHADOW_VALID)
+    // in-volume Russian roulette only after VOLUME_FREE_BUDGET scatters (pathtrace_functions.h.slang:925-931)
+    if(__float_as_uint(rad4.w) >= 64u)
     {
-      const float4 so = P.shO[i];
-      const float4 sdv = P.shD[i];
-      const float3 T = traceShadow(S, xyz(so), xyz(sdv), so.w, seed, (flags & PF_SHADOW_INSIDE) != 0, stats);
-      radiance += xyz(P.shC[i]) * T;
-      radDirty = true;
-      statAdd(&stats->shadowRays, 1ull);
-    }
-    float4   thr4 = P.thr[i];
-    float3   throughput = xyz(thr4);
-    uint32_t depth = flags & PF_DEPTH_MASK;
-    bool     alive = true;
-    bool     thrDirty = false;
-    if(flags & PF_POST_VOLUME)
-    {
-      // in-volume Russian roulette only after VOLUME_FREE_BUDGET scatters (pathtrace_functions.h.slang:925-931)
-      if(__float_as_uint(rad4.w) >= 64u)
+      const float rrPcont = fminf(maxc(throughput) + 0.001f, 0.95f);
+      if(rnd(seed) >= rrPcont)
+        alive = false;
+      else
       {
-        const float rrPcont = fminf(maxc(throughput) + 0.001f, 0.95f);
-        if(rnd(seed) >= rrPcont)
-          alive = false;
+        throughput /= rrPcont;
+        thrDirty = true;
+      }
+    }
+  }
+  else
+  {
+    // surface Russian roulette from depth 3 (gltf_pathtrace.slang:476-485)
+    if(depth >= 3u)
+    {
+      const float rrPcont = fminf(maxc(throughput) + 0.001f, 0.95f);
+      if(rnd(seed) >= rrPcont)
+        alive = false;
+      else
+      {
+        throughput /= rrPcont;
+        thrDirty = true;
+      }
+    }
+    if(alive)
+    {
+      depth++;
+      if((int)depth >= F.pc.maxDepth)
+        alive = false;
+    }
+  }
+  if(!alive)
+  {
+    finalizeSample(P, F, i, radiance, (flags & PF_SOLID) != 0, seed, P.medium[i].w >> 16, qNext, cntNext, stats);
+    return;
+  }
+  flags = (flags & ~(PF_DEPTH_MASK | PF_POST_VOLUME | PF_SHADOW_VALID | PF_SHADOW_INSIDE)) | (depth & PF_DEPTH_MASK);
+  if(haveShadow)
+    P.rad[i] = f4(radiance, rad4.w);
+  if(thrDirty)
+    P.thr[i] = f4(throughput, thr4.w);
+  P.misc[i] = f4(misc.x, misc.y, __uint_as_float(flags), __uint_as_float(seed));
+  queuePush(qNext, cntNext, i);
+}
+
+__global__ void __launch_bounds__(128) k_post(PathState P, DevScene S, const __grid_constant__ FrameParams F, const uint32_t* __restrict__ q,
+                                              const uint32_t* __restrict__ cntIn, uint32_t* workCounter, uint32_t* qNext, uint32_t* cntNext, DevStats* stats)
+{
+  stageSrgbLut(S.lutSrgb);
+  const uint32_t count = *cntIn;
+  TravState      T;
+  int            path = -1;  // -1: lane needs work, -2: queue exhausted
+  int            phase = 0;  // 0: opaque occlusion query, 1: any-hit candidates front to back
+  uint32_t       flags = 0, seed = 0;
+  float3         total = f3(1.0f);
+  bool           isInside = false;
+  float          prevHitT = 0.f;
+  for(;;)
+  {
+    __syncwarp();
+    // refill: paths without a shadow ray are finished on the spot and the lane fetches again
+    for(;;)
+    {
+      const bool     need = (path == -1);
+      const uint32_t k = fetchWork(need, workCounter, count);
+      if(need)
+      {
+        if(k == 0xFFFFFFFFu)
+          path = -2;
         else
         {
-          throughput /= rrPcont;
-          thrDirty = true;
+          path = (int)q[k];
+          const float4 misc = P.misc[path];
+          flags = __float_as_uint(misc.z);
+          seed = __float_as_uint(misc.w);
+          if(!(flags & PF_SHADOW_VALID))
+          {
+            finishPost(P, F, (uint32_t)path, flags, seed, false, f3(1.0f), qNext, cntNext, stats);
+            path = -1;
+          }
+          else
+          {
+            const float4 so = P.shO[path];
+            const float4 sd = P.shD[path];
+            statAdd(&stats->shadowRays, 1ull);
+            phase = 0;
+            total = f3(1.0f);
+            isInside = (flags & PF_SHADOW_INSIDE) != 0;
+            prevHitT = 0.f;
+            // 1. any FORCE_OPAQUE occluder ends the query (raytracer_interface.h.slang:181-184)
+            T.init(S.bvh, xyz(so), xyz(sd), 0.0f, so.w, false, true, false, 0.f, 0u);
+          }
         }
       }
+      __syncwarp();
+      if(!__any_sync(0xffffffffu, path == -1))
+        break;
     }
-    else
+    if(__all_sync(0xffffffffu, path == -2))
+      break;
+    while(path >= 0)
     {
-      // surface Russian roulette from depth 3 (gltf_pathtrace.slang:476-485)
-      if(depth >= 3u)
+      if(T.step())
       {
-        const float rrPcont = fminf(maxc(throughput) + 0.001f, 0.95f);
-        if(rnd(seed) >= rrPcont)
-          alive = false;
+        T.flushCounters(&stats->nodesVisited, &stats->trisTested);
+        bool done = false;
+        if(phase == 0)
+        {
+          if(T.best.slot != 0xFFFFFFFFu)
+          {
+            total = f3(0.0f);
+            done = true;
+          }
+          else if(S.hasAlpha)
+          {
+            phase = 1;
+            T.init(S.bvhAlpha, T.org, T.dir, 0.0f, T.tmax, false, false, false, 0.f, 0u);
+          }
+          else
+            done = true;
+        }
         else
         {
-          throughput /= rrPcont;
-          thrDirty = true;
+          // 2. every non-opaque candidate, front to back (:149-179)
+          const TraceHit h = T.result();
+          if(h.slot == 0xFFFFFFFFu)
+            done = true;
+          else
+          {
+            const uint2               meta = S.triMeta[h.slot];
+            const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
+            const DevPrim&            prim = S.prims[node.renderPrimID];
+            const float3              bary = f3(1.0f - h.u - h.v, h.u, h.v);
+            const float               opacity = getOpacity(S, node, prim, meta.y, bary);
+            const float               r = rnd(seed);
+            if(r < opacity)
+            {
+              const float  seg = fmaxf(0.0f, h.t - prevHitT);
+              const float3 cur = getShadowTransmission(S, node, prim, meta.y, bary, seg, T.dir, isInside);
+              prevHitT = h.t;
+              total *= cur;
+              if(maxc(total) <= 0.01f)
+              {
+                total = f3(0.0f);
+                done = true;
+              }
+            }
+            if(!done)
+              T.init(S.bvhAlpha, T.org, T.dir, 0.0f, T.tmax, false, false, true, h.t, h.gid);
+          }
+        }
+        if(done)
+        {
+#ifdef B200PT_DEBUG
+          if((float)((uint32_t)path % (uint32_t)F.width) == F.pc.mouseCoord[0] && (float)(F.tileY0 + (uint32_t)path / (uint32_t)F.width) == F.pc.mouseCoord[1])
+            printf("DBG shadow o=%.9g %.9g %.9g d=%.9g %.9g %.9g tmax=%.9g T=%.9g %.9g %.9g\n", T.org.x, T.org.y, T.org.z, T.dir.x, T.dir.y, T.dir.z, T.tmax, total.x, total.y, total.z);
+#endif
+          finishPost(P, F, (uint32_t)path, flags, seed, true, total, qNext, cntNext, stats);
+          path = -1;
+          break;
         }
       }
-      if(alive)
-      {
-        depth++;
-        if((int)depth >= F.pc.maxDepth)
-          alive = false;
-      }
+      if(__popc(__activemask()) < kRefillThreshold)
+        break;
     }
-    if(!alive)
-    {
-      finalizeSample(P, F, i, radiance, (flags & PF_SOLID) != 0, seed, P.medium[i].w >> 16, qNext, cntNext, stats);
-      continue;
-    }
-    flags = (flags & ~(PF_DEPTH_MASK | PF_POST_VOLUME | PF_SHADOW_VALID | PF_SHADOW_INSIDE)) | (depth & PF_DEPTH_MASK);
-    if(radDirty)
-      P.rad[i] = f4(radiance, rad4.w);
-    if(thrDirty)
-      P.thr[i] = f4(throughput, thr4.w);
-    P.misc[i] = f4(misc.x, misc.y, __uint_as_float(flags), __uint_as_float(seed));
-    queuePush(qNext, cntNext, i);
   }
 }
 
@@ -473,6 +706,7 @@ __global__ void __launch_bounds__(256) k_accumulate(PathState P, const __grid_co
 // ---- ray-level kernels (parity tests / traversal micro-benchmark) ---------------------------------
 __global__ void __launch_bounds__(128) k_trace_rays(DevScene S, const float4* __restrict__ rays, uint32_t n, float* __restrict__ hits, uint32_t* seeds, DevStats* stats)
 {
+  stageSrgbLut(S.lutSrgb);
   const uint32_t stride = gridDim.x * blockDim.x;
   for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
   {
@@ -505,6 +739,7 @@ __global__ void __launch_bounds__(128) k_trace_rays(DevScene S, const float4* __
 
 __global__ void __launch_bounds__(128) k_shadow_rays(DevScene S, const float4* __restrict__ rays, uint32_t n, float* __restrict__ out, uint32_t* seeds, DevStats* stats)
 {
+  stageSrgbLut(S.lutSrgb);
   const uint32_t stride = gridDim.x * blockDim.x;
   for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
   {
@@ -635,6 +870,7 @@ struct b200pt
   uint32_t *         dQ[3] = {nullptr, nullptr, nullptr}, *dCounters = nullptr;
   uint32_t*          hCount = nullptr;  // pinned
   DevStats*          dStats = nullptr;
+  float*             dLutSrgb = nullptr;
 
   // stats / profiling: CUDA-event pairs recorded around every launch on the handle's stream and
   // resolved lazily (no host sync inside a frame)
@@ -762,15 +998,6 @@ void downsample(const std::vector<uint8_t>& src, int w, int h, bool srgb, std::v
     }
 }
 
-cudaTextureAddressMode addressMode(int gl)
-{
-  if(gl == 33071)
-    return cudaAddressModeClamp;
-  if(gl == 33648)
-    return cudaAddressModeMirror;
-  return cudaAddressModeWrap;
-}
-
 struct MipChain
 {
   std::vector<std::vector<uint8_t>> level;
@@ -811,24 +1038,28 @@ int createTexture(b200pt* h, const b200pt_texture& src, const MipChain& mc, TexR
   rd.resType = cudaResourceTypeMipmappedArray;
   rd.res.mipmap.mipmap = out.arr;
   cudaTextureDesc td{};
-  td.addressMode[0] = addressMode(src.wrapS);
-  td.addressMode[1] = addressMode(src.wrapT);
-  // sampler quirks kept from getSampler (src/gltf_scene_vk.cpp:909-947): one filter object; mip mode follows magFilter
-  const bool magLinear = (src.magFilter != 9728);
-  td.filterMode = magLinear ? cudaFilterModeLinear : cudaFilterModePoint;
-  td.mipmapFilterMode = magLinear ? cudaFilterModeLinear : cudaFilterModePoint;
-  td.readMode = cudaReadModeNormalizedFloat;
-  td.sRGB = src.srgb ? 1 : 0;
+  td.addressMode[0] = cudaAddressModeClamp;  // wrap / mirror are applied in software on integer texel coordinates
+  td.addressMode[1] = cudaAddressModeClamp;
+  td.filterMode = cudaFilterModePoint;
+  td.mipmapFilterMode = cudaFilterModePoint;
+  td.readMode = cudaReadModeElementType;
+  td.sRGB = 0;
   td.normalizedCoords = 1;
   td.maxAnisotropy = 1;
   td.minMipmapLevelClamp = 0.f;
   td.maxMipmapLevelClamp = (float)(levels - 1);
   CK(cudaCreateTextureObject(&out.obj, &rd, &td, nullptr));
+  // sampler quirks kept from getSampler (src/gltf_scene_vk.cpp:909-947): the mip mode follows magFilter
   dev.obj = out.obj;
-  dev.w = (float)src.width;
-  dev.h = (float)src.height;
+  dev.w0 = src.width;
+  dev.h0 = src.height;
   dev.maxLevel = (float)(levels - 1);
-  dev.mipLinear = magLinear ? 1 : 0;
+  dev.wrapS = src.wrapS;
+  dev.wrapT = src.wrapT;
+  dev.srgb = src.srgb ? 1 : 0;
+  dev.magLinear = (src.magFilter != 9728) ? 1 : 0;
+  dev.minLinear = (src.minFilter == 9728 || src.minFilter == 9984 || src.minFilter == 9986) ? 0 : 1;
+  dev.mipLinear = (src.magFilter != 9728) ? 1 : 0;
   return 0;
 }
 
@@ -863,8 +1094,15 @@ int b200pt_create(b200pt_t** out, int cuda_device)
   h->numSMs = prop.multiProcessorCount;
   cudaMalloc((void**)&h->dStats, sizeof(DevStats));
   cudaMemset(h->dStats, 0, sizeof(DevStats));
-  cudaMalloc((void**)&h->dCounters, sizeof(uint32_t) * 2 * kMaxIters);
+  cudaMalloc((void**)&h->dCounters, sizeof(uint32_t) * 4 * kMaxIters);
   cudaMallocHost((void**)&h->hCount, sizeof(uint32_t) * 4);
+  {
+    float lutS[256];
+    for(int i = 0; i < 256; i++)
+      lutS[i] = srgbToLinear((float)i / 255.0f);
+    cudaMalloc((void**)&h->dLutSrgb, sizeof(lutS));
+    cudaMemcpy(h->dLutSrgb, lutS, sizeof(lutS), cudaMemcpyHostToDevice);
+  }
   *out = h;
   return B200PT_OK;
 }
@@ -882,6 +1120,7 @@ void b200pt_destroy(b200pt_t* h)
   if(h->dEnvAccel)
     cudaFree(h->dEnvAccel);
   cudaFree(h->dStats);
+  cudaFree(h->dLutSrgb);
   cudaFree(h->dCounters);
   cudaFreeHost(h->hCount);
   for(auto& e : h->evPool)
@@ -909,9 +1148,13 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
   CK(cudaStreamSynchronize(h->stream));
   freeScene(h);
   DevScene& S = h->S;
+  const int envW0 = S.envW, envH0 = S.envH;
   S = DevScene{};
   S.envRgba = h->dEnv;
   S.envAccel = h->dEnvAccel;
+  S.envW = envW0;
+  S.envH = envH0;
+  S.lutSrgb = h->dLutSrgb;
 
   // --- AoS tables: same bytes as the reference SSBOs ---
   b200pt_render_node*    dNodes;
@@ -1020,7 +1263,6 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
 
   // --- flatten instances to world space + build the wide BVH (TLAS/BLAS replacement) ---
   std::vector<FlatTri> flat;
-  bool                 allOpaque = true;
   h->hasVolume = false;
   for(uint32_t n = 0; n < s->numRenderNodes; n++)
   {
@@ -1037,8 +1279,6 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
     uint32_t                       flags = 0;
     if(m.transmissionFactor == 0.0f && m.alphaMode == 0 && m.diffuseTransmissionFactor == 0.0f)
       flags |= TRI_OPAQUE;
-    else
-      allOpaque = false;
     if(m.doubleSided == 1 || m.thicknessFactor > 0.0f || m.transmissionFactor > 0.0f)
       flags |= TRI_NOCULL;
     if(m.thicknessFactor > 0.0f)
@@ -1070,24 +1310,50 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
       flat.push_back(T);
     }
   }
-  WideBvh bvh;
-  buildWideBvh(flat, bvh);
-  float *   dNodesBvh, *dTris;
+  // opaque and any-hit (non-opaque) geometry go into separate trees over ONE shared triangle array;
+  // the global triangle id (flatten order) stays the tie-break key in both
+  std::vector<FlatTri>  flatO, flatA;
+  std::vector<uint32_t> gidO, gidA;
+  for(uint32_t i = 0; i < (uint32_t)flat.size(); i++)
+  {
+    if(flat[i].flags & TRI_OPAQUE)
+    {
+      flatO.push_back(flat[i]);
+      gidO.push_back(i);
+    }
+    else
+    {
+      flatA.push_back(flat[i]);
+      gidA.push_back(i);
+    }
+  }
+  WideBvh bvhO, bvhA;
+  buildWideBvh(flatO, gidO, 0u, bvhO);
+  buildWideBvh(flatA, gidA, bvhO.numTris, bvhA);
+  std::vector<float>    allTris(bvhO.tris);
+  std::vector<uint32_t> allMeta(bvhO.triMeta);
+  allTris.insert(allTris.end(), bvhA.tris.begin(), bvhA.tris.end());
+  allMeta.insert(allMeta.end(), bvhA.triMeta.begin(), bvhA.triMeta.end());
+  float *   dNodesO, *dNodesA, *dTris;
   uint32_t* dMeta;
-  if((rc = upload(h, h->sceneAllocs, bvh.nodes.data(), bvh.nodes.size(), &dNodesBvh)))
+  if((rc = upload(h, h->sceneAllocs, bvhO.nodes.data(), bvhO.nodes.size(), &dNodesO)))
     return rc;
-  if((rc = upload(h, h->sceneAllocs, bvh.tris.data(), bvh.tris.size(), &dTris)))
+  if((rc = upload(h, h->sceneAllocs, bvhA.nodes.data(), bvhA.nodes.size(), &dNodesA)))
     return rc;
-  if((rc = upload(h, h->sceneAllocs, bvh.triMeta.data(), bvh.triMeta.size(), &dMeta)))
+  if((rc = upload(h, h->sceneAllocs, allTris.data(), allTris.size(), &dTris)))
     return rc;
-  S.bvh.nodes = reinterpret_cast<const float4*>(dNodesBvh);
+  if((rc = upload(h, h->sceneAllocs, allMeta.data(), allMeta.size(), &dMeta)))
+    return rc;
+  S.bvh.nodes = reinterpret_cast<const float4*>(dNodesO);
   S.bvh.tris = reinterpret_cast<const float4*>(dTris);
+  S.bvhAlpha.nodes = reinterpret_cast<const float4*>(dNodesA);
+  S.bvhAlpha.tris = reinterpret_cast<const float4*>(dTris);
+  S.hasAlpha = flatA.empty() ? 0 : 1;
   S.triMeta = reinterpret_cast<const uint2*>(dMeta);
-  S.allOpaque = allOpaque ? 1 : 0;
-  h->nodeBytes = bvh.nodes.size() * sizeof(float);
-  h->triBytes = bvh.tris.size() * sizeof(float);
-  h->numNodes = bvh.numNodes;
-  h->numTris = bvh.numTris;
+  h->nodeBytes = (bvhO.nodes.size() + bvhA.nodes.size()) * sizeof(float);
+  h->triBytes = allTris.size() * sizeof(float);
+  h->numNodes = bvhO.numNodes + bvhA.numNodes;
+  h->numTris = bvhO.numTris + bvhA.numTris;
   CK(cudaStreamSynchronize(h->stream));
   h->haveScene = true;
   return B200PT_OK;
@@ -1349,7 +1615,9 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
   cudaStream_t st = h->stream;
   uint32_t*    cntTrace = h->dCounters;             // [kMaxIters]
   uint32_t*    cntPost = h->dCounters + kMaxIters;  // [kMaxIters]
-  CK(cudaMemsetAsync(h->dCounters, 0, sizeof(uint32_t) * 2 * kMaxIters, st));
+  uint32_t*    workTrace = h->dCounters + 2 * kMaxIters;  // dynamic-fetch cursors of the persistent kernels
+  uint32_t*    workPost = h->dCounters + 3 * kMaxIters;
+  CK(cudaMemsetAsync(h->dCounters, 0, sizeof(uint32_t) * 4 * kMaxIters, st));
 
   enum
   {
@@ -1390,9 +1658,9 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
       {
         uint32_t* qT = h->dQ[cur];
         uint32_t* qN = h->dQ[1 - cur];
-        timed(tTrace, [&] { k_trace<<<gridFor(h, 8), 128, 0, st>>>(h->P, h->S, qT, &cntTrace[it], h->dStats); });
-        timed(tShade, [&] { k_shade<<<gridFor(h, 8), 128, 0, st>>>(h->P, h->S, F, qT, &cntTrace[it], h->dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats); });
-        timed(tPost, [&] { k_post<<<gridFor(h, 8), 128, 0, st>>>(h->P, h->S, F, h->dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats); });
+        timed(tTrace, [&] { k_trace<<<gridFor(h, 8), 128, 1024, st>>>(h->P, h->S, qT, &cntTrace[it], &workTrace[it], h->dStats); });
+        timed(tShade, [&] { k_shade<<<gridFor(h, 8), 128, 1024, st>>>(h->P, h->S, F, qT, &cntTrace[it], h->dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats); });
+        timed(tPost, [&] { k_post<<<gridFor(h, 8), 128, 1024, st>>>(h->P, h->S, F, h->dQ[2], &cntPost[it], &workPost[it], qN, &cntTrace[it + 1], h->dStats); });
         cur = 1 - cur;
       }
       if(!mayOverrun)
@@ -1468,7 +1736,7 @@ int b200pt_trace_closest(b200pt_t* h, const float* dev_rays, uint32_t n, float* 
     return B200PT_E_INVALID;
   CK(cudaSetDevice(h->device));
   if(n)
-    k_trace_rays<<<gridFor(h, 8), 128, 0, h->stream>>>(h->S, reinterpret_cast<const float4*>(dev_rays), n, dev_hits, dev_seeds, h->dStats);
+    k_trace_rays<<<gridFor(h, 8), 128, 1024, h->stream>>>(h->S, reinterpret_cast<const float4*>(dev_rays), n, dev_hits, dev_seeds, h->dStats);
   CK(cudaGetLastError());
   h->kernelLaunches++;
   return B200PT_OK;
@@ -1480,7 +1748,7 @@ int b200pt_trace_shadow(b200pt_t* h, const float* dev_rays, uint32_t n, float* d
     return B200PT_E_INVALID;
   CK(cudaSetDevice(h->device));
   if(n)
-    k_shadow_rays<<<gridFor(h, 8), 128, 0, h->stream>>>(h->S, reinterpret_cast<const float4*>(dev_rays), n, dev_transmission, dev_seeds, h->dStats);
+    k_shadow_rays<<<gridFor(h, 8), 128, 1024, h->stream>>>(h->S, reinterpret_cast<const float4*>(dev_rays), n, dev_transmission, dev_seeds, h->dStats);
   CK(cudaGetLastError());
   h->kernelLaunches++;
   return B200PT_OK;

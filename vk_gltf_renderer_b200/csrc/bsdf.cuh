@@ -124,7 +124,7 @@ PT_D float smithG1(float3 k, float2 roughness)
   return 2.0f / (1.0f + sqrtf(1.0f + inv_a_2));
 }
 
-PT_D float3 thinFilmFactor(float thickness, float coatIor, float baseIor, float inIor, float kh)
+__device__ __noinline__ float3 thinFilmFactor(float thickness, float coatIor, float baseIor, float inIor, float kh)
 {
   const float cie[16][3] = {
       {0.02986f, 0.00310f, 0.13609f}, {0.20715f, 0.02304f, 0.99584f}, {0.36717f, 0.06469f, 1.89550f}, {0.28549f, 0.13661f, 1.67236f},
@@ -512,7 +512,7 @@ PT_D void sheenSample(BsdfSample& d, const PbrMaterial& mat, float3 k1, float3 x
   d.event_type = BSDF_EVENT_GLOSSY_REFLECTION;
 }
 
-PT_D BsdfEval bsdfEvaluate(const PbrMaterial& mat, float3 k1, float3 k2, float3 xi)
+__device__ __noinline__ BsdfEval bsdfEvaluate(const PbrMaterial& mat, float3 k1, float3 k2, float3 xi)
 {
   BsdfEval d;
   d.bsdf_diffuse = f3(0.0f);
@@ -548,7 +548,7 @@ PT_D BsdfEval bsdfEvaluate(const PbrMaterial& mat, float3 k1, float3 k2, float3 
   return d;
 }
 
-PT_D BsdfSample bsdfSample(const PbrMaterial& mat, float3 k1, float3 xi)
+__device__ __noinline__ BsdfSample bsdfSample(const PbrMaterial& mat, float3 k1, float3 xi)
 {
   BsdfSample d;
   d.k2 = f3(0.0f);

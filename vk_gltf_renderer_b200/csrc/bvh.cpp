@@ -216,7 +216,7 @@ static inline float u2f(uint32_t u)
 
 }  // namespace
 
-void buildWideBvh(const std::vector<FlatTri>& tris, WideBvh& out)
+void buildWideBvh(const std::vector<FlatTri>& tris, const std::vector<uint32_t>& gids, uint32_t triBaseOffset, WideBvh& out)
 {
   out = WideBvh();
   out.numTris = (uint32_t)tris.size();
@@ -350,7 +350,7 @@ void buildWideBvh(const std::vector<FlatTri>& tris, WideBvh& out)
     }
     uint8_t  imask = 0, meta[8], qlo[3][8], qhi[3][8];
     uint32_t childBase = (uint32_t)(out.nodes.size() / 20);  // internal children appended below
-    uint32_t triBase = (uint32_t)(out.tris.size() / 12);
+    uint32_t triBase = triBaseOffset + (uint32_t)(out.tris.size() / 12);
     uint32_t triCount = 0, innerCount = 0;
     for(int s = 0; s < 8; s++)
     {
@@ -384,8 +384,9 @@ void buildWideBvh(const std::vector<FlatTri>& tris, WideBvh& out)
         meta[s] = (uint8_t)((bits << 5) | triCount);
         for(uint32_t k = 0; k < c.count; k++)
         {
-          uint32_t       gid = B.order[c.first + k];
-          const FlatTri& T = tris[gid];
+          const uint32_t local = B.order[c.first + k];
+          const uint32_t gid = gids[local];
+          const FlatTri& T = tris[local];
           float          rec[12] = {T.v0[0], T.v0[1], T.v0[2], u2f(T.rnode | (T.flags << 28)), T.e1[0], T.e1[1], T.e1[2], u2f(T.prim), T.e2[0], T.e2[1], T.e2[2], u2f(gid)};
           out.tris.insert(out.tris.end(), rec, rec + 12);
           out.triMeta.push_back(T.rnode | (T.flags << 28));

@@ -45,6 +45,8 @@ struct WideBvh
   uint32_t              maxDepth = 0;
 };
 
-void buildWideBvh(const std::vector<FlatTri>& tris, WideBvh& out);
+// gids[i] = global (flatten-order) id of tris[i], the tie-break key stored in the triangle record;
+// triBaseOffset is added to every node's triangle base (several trees may share one triangle array).
+void buildWideBvh(const std::vector<FlatTri>& tris, const std::vector<uint32_t>& gids, uint32_t triBaseOffset, WideBvh& out);
 
 }  // namespace pt

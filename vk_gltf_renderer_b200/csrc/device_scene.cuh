@@ -28,10 +28,12 @@ struct DevPrim
 
 struct DevTex
 {
-  cudaTextureObject_t obj;
-  float               w, h;
+  cudaTextureObject_t obj;  // RGBA8 mip pyramid, point-sampled (filtering happens in fp32 in the kernel)
+  int                 w0, h0;
   float               maxLevel;
-  int                 mipLinear;
+  int                 wrapS, wrapT;  // glTF enums
+  int                 srgb;
+  int                 magLinear, minLinear, mipLinear;
 };
 
 struct DevScene
@@ -44,12 +46,14 @@ struct DevScene
   const b200pt_light*          lights;
   int                          numLights;
   int                          numTextures;
-  BvhView                      bvh;
-  const uint2*                 triMeta;  // per triangle slot: (rnode | flags<<28, primitiveID)
+  BvhView                      bvh;       // FORCE_OPAQUE triangles (no any-hit work)
+  BvhView                      bvhAlpha;  // non-opaque triangles (alpha / transmission candidates); shares the triangle array
+  int                          hasAlpha;  // bvhAlpha is non-empty
+  const uint2*                 triMeta;   // per triangle slot: (rnode | flags<<28, primitiveID)
   const float4*                envRgba;  // lat-long radiance, pdf in .w
   const uint2*                 envAccel; // (alias, q bits)
+  const float*                 lutSrgb;  // 256-entry sRGB decode table (staged into shared memory per block)
   int                          envW, envH;
-  int                          allOpaque;  // every triangle FORCE_OPAQUE: shadow rays may stop at the first hit
 };
 
 struct FrameParams

@@ -128,21 +128,97 @@ PT_D HitState getHitState(const DevPrim& P, float3 bary, const float* W2O, const
 }
 
 // ---- textures -----------------------------------------------------------------------------------
-// Explicit-LOD fetch from a bindless texture object.  lambda is computed in fp32 exactly like the
-// Vulkan SampleGrad definition the reference relies on: log2(max(|ddx*size|, |ddy*size|)).
-PT_D float4 sampleTexture(const DevTex& T, float2 uv, float2 ddx, float2 ddy, bool useGrad)
+// 8-bit sRGB EOTF decode table (same fp32 values as the oracle's), staged in shared memory by every kernel
+// that can touch a texture (divergent indices: constant memory would serialise them)
+extern __shared__ float s_lutSrgb[];
+PT_D void stageSrgbLut(const float* __restrict__ lutGlobal)
+{
+  for(int i = threadIdx.x; i < 256; i += blockDim.x)
+    s_lutSrgb[i] = __ldg(lutGlobal + i);
+  __syncthreads();
+}
+
+// Explicit-LOD fetch.  lambda is computed in fp32 exactly like the Vulkan SampleGrad definition the
+// reference relies on: log2(max(|ddx*size|, |ddy*size|)); lambda <= 0 is magnification (level 0).
+//
+// Filtering is done in fp32 in the kernel from point-sampled texels (bindless texture objects are
+// used for the 2D-local fetch path only).  Hardware bilinear/trilinear blends use 8-bit fixed-point
+// weights; an alpha-MASK cutoff evaluated on such a blend flips at leaf silhouettes relative to the
+// fp32 definition and the paths diverge, so the exact definition is kept (measured: 1e-5 of rays).
+PT_D int wrapCoord(int i, int n, int mode)
+{
+  if(mode == 33071)  // CLAMP_TO_EDGE
+    return min(max(i, 0), n - 1);
+  if(mode == 33648)  // MIRRORED_REPEAT
+  {
+    const int p = 2 * n;
+    const int m = ((i % p) + p) % p;
+    return m < n ? m : p - 1 - m;
+  }
+  return ((i % n) + n) % n;  // REPEAT
+}
+
+// texel (x, y) of `level`, coordinates already wrapped; point fetch at the texel centre
+PT_D float4 fetchTexel(const DevTex& T, float level, float invW, float invH, int x, int y)
+{
+  const uchar4 p = tex2DLod<uchar4>(T.obj, ((float)x + 0.5f) * invW, ((float)y + 0.5f) * invH, level);
+  const float  a = (float)p.w / 255.0f;
+  if(T.srgb)
+    return f4(s_lutSrgb[p.x], s_lutSrgb[p.y], s_lutSrgb[p.z], a);
+  return f4((float)p.x / 255.0f, (float)p.y / 255.0f, (float)p.z / 255.0f, a);
+}
+
+PT_D int wrapFast(int i, int n, int mode)
+{
+  if(mode == 10497 && (n & (n - 1)) == 0)
+    return i & (n - 1);  // REPEAT on a power-of-two level: no integer division
+  return wrapCoord(i, n, mode);
+}
+
+PT_D float4 sampleLevel(const DevTex& T, int level, float2 uv, bool linear)
+{
+  const int   w = max(1, T.w0 >> level), h = max(1, T.h0 >> level);
+  const float invW = 1.0f / (float)w, invH = 1.0f / (float)h, lv = (float)level;
+  float       x = uv.x * (float)w, y = uv.y * (float)h;
+  if(!linear)
+    return fetchTexel(T, lv, invW, invH, wrapFast((int)floorf(x), w, T.wrapS), wrapFast((int)floorf(y), h, T.wrapT));
+  x -= 0.5f;
+  y -= 0.5f;
+  const float  fx0 = floorf(x), fy0 = floorf(y);
+  const float  fx = x - fx0, fy = y - fy0;
+  const int    x0 = wrapFast((int)fx0, w, T.wrapS), x1 = wrapFast((int)fx0 + 1, w, T.wrapS);
+  const int    y0 = wrapFast((int)fy0, h, T.wrapT), y1 = wrapFast((int)fy0 + 1, h, T.wrapT);
+  const float4 a = fetchTexel(T, lv, invW, invH, x0, y0), b = fetchTexel(T, lv, invW, invH, x1, y0);
+  const float4 c = fetchTexel(T, lv, invW, invH, x0, y1), d = fetchTexel(T, lv, invW, invH, x1, y1);
+  const float4 top = a * (1.0f - fx) + b * fx;
+  const float4 bot = c * (1.0f - fx) + d * fx;
+  return top * (1.0f - fy) + bot * fy;
+}
+
+__device__ __noinline__ float4 sampleTexture(const DevTex& T, float2 uv, float2 ddx, float2 ddy, bool useGrad)
 {
   if(!useGrad)
-    return tex2DLod<float4>(T.obj, uv.x, uv.y, 0.0f);
-  const float lx = sqrtf(ddx.x * T.w * ddx.x * T.w + ddx.y * T.h * ddx.y * T.h);
-  const float ly = sqrtf(ddy.x * T.w * ddy.x * T.w + ddy.y * T.h * ddy.y * T.h);
+    return sampleLevel(T, 0, uv, T.magLinear != 0);
+  const float w = (float)T.w0, h = (float)T.h0;
+  const float lx = sqrtf(ddx.x * w * ddx.x * w + ddx.y * h * ddx.y * h);
+  const float ly = sqrtf(ddy.x * w * ddy.x * w + ddy.y * h * ddy.y * h);
   float       lambda = log2f(fmaxf(lx, ly));
   if(!(lambda > 0.0f))
-    return tex2DLod<float4>(T.obj, uv.x, uv.y, 0.0f);
+    return sampleLevel(T, 0, uv, T.magLinear != 0);
   lambda = fminf(lambda, T.maxLevel);
   if(!T.mipLinear)
-    lambda = fminf(T.maxLevel, fmaxf(0.0f, ceilf(lambda + 0.5f) - 1.0f));
-  return tex2DLod<float4>(T.obj, uv.x, uv.y, lambda);
+  {
+    const int lv = (int)fminf(T.maxLevel, fmaxf(0.0f, ceilf(lambda + 0.5f) - 1.0f));
+    return sampleLevel(T, lv, uv, T.minLinear != 0);
+  }
+  const int    l0 = (int)floorf(lambda);
+  const int    l1 = min(l0 + 1, (int)T.maxLevel);
+  const float  f = lambda - (float)l0;
+  const float4 a = sampleLevel(T, l0, uv, T.minLinear != 0);
+  if(f == 0.0f || l1 == l0)
+    return a;
+  const float4 b = sampleLevel(T, l1, uv, T.minLinear != 0);
+  return a * (1.0f - f) + b * f;
 }
 
 PT_D float4 getTexture(const DevScene& S, uint16_t slot, float2 tc0, float2 tc1, float texGrad)
@@ -162,7 +238,8 @@ PT_D float4 sampleLevel0(const DevScene& S, const b200pt_texture_info& ti, float
 {
   if(ti.index < 0 || ti.index >= S.numTextures)
     return f4(1, 1, 1, 1);
-  return tex2DLod<float4>(S.textures[ti.index].obj, uv.x, uv.y, 0.0f);
+  const DevTex T = S.textures[ti.index];
+  return sampleLevel(T, 0, uv, T.magLinear != 0);
 }
 
 // ---- material evaluation ------------------------------------------------------------------------
@@ -431,19 +508,28 @@ PT_D float3 getShadowTransmission(const DevScene& S, const b200pt_render_node& n
   return cur * att;
 }
 
-// ---- Trace / TraceShadow: front-to-back candidate loops over traverseNext -------------------------
+// ---- Trace / TraceShadow -------------------------------------------------------------------------
+// The reference leaves any-hit order to the hardware (raytracer_interface.h.slang:53).  Pinned here:
+//   Trace:       closest FORCE_OPAQUE hit (opaque tree) first, then the non-opaque candidates nearer
+//                than it front-to-back in (t, triangle id) order from the alpha tree, one rand() each.
+//   TraceShadow: any opaque occluder => 0 with no rand(); else every non-opaque candidate front-to-back.
+// Opaque and any-hit geometry live in separate trees, so the common (opaque) case is ONE traversal.
 PT_D TraceHit traceClosest(const DevScene& S, float3 org, float3 dir, float tmin, float tmax, uint32_t& seed, DevStats* stats)
 {
-  bool     haveLo = false;
-  float    loT = 0.f;
-  uint32_t loId = 0;
+  unsigned long long* nc = stats ? &stats->nodesVisited : nullptr;
+  unsigned long long* tc = stats ? &stats->trisTested : nullptr;
+  const TraceHit      ho = traverseNext<true, false>(S.bvh, org, dir, tmin, tmax, false, 0.f, 0u, nc, tc);
+  if(!S.hasAlpha)
+    return ho;
+  const float tlimit = (ho.slot != 0xFFFFFFFFu) ? ho.t : tmax;
+  bool        haveLo = false;
+  float       loT = 0.f;
+  uint32_t    loId = 0;
   for(;;)
   {
-    TraceHit h = traverseNext<true, false>(S.bvh, org, dir, tmin, tmax, haveLo, loT, loId, stats ? &stats->nodesVisited : nullptr, stats ? &stats->trisTested : nullptr);
+    const TraceHit h = traverseNext<true, false>(S.bvhAlpha, org, dir, tmin, tlimit, haveLo, loT, loId, nc, tc);
     if(h.slot == 0xFFFFFFFFu)
-      return h;
-    if((h.w0 >> 28) & TRI_OPAQUE)
-      return h;
+      return ho;
     const uint2               meta = S.triMeta[h.slot];
     const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
     const float               opacity = getOpacity(S, node, S.prims[node.renderPrimID], meta.y, f3(1.0f - h.u - h.v, h.u, h.v));
@@ -457,12 +543,16 @@ PT_D TraceHit traceClosest(const DevScene& S, float3 org, float3 dir, float tmin
 
 PT_D float3 traceShadow(const DevScene& S, float3 org, float3 dir, float tmax, uint32_t& seed, bool initialInside, DevStats* stats)
 {
-  if(S.allOpaque)
+  unsigned long long* nc = stats ? &stats->nodesVisited : nullptr;
+  unsigned long long* tc = stats ? &stats->trisTested : nullptr;
   {
-    TraceHit h = traverseNext<false, true>(S.bvh, org, dir, 0.0f, tmax, false, 0.f, 0u, stats ? &stats->nodesVisited : nullptr, stats ? &stats->trisTested : nullptr);
-    return (h.slot == 0xFFFFFFFFu) ? f3(1.0f) : f3(0.0f);
+    const TraceHit h = traverseNext<false, true>(S.bvh, org, dir, 0.0f, tmax, false, 0.f, 0u, nc, tc);
+    if(h.slot != 0xFFFFFFFFu)
+      return f3(0.0f);
   }
-  float3   total = f3(1.0f);
+  float3 total = f3(1.0f);
+  if(!S.hasAlpha)
+    return total;
   bool     isInside = initialInside;
   float    prevHitT = 0.f;
   bool     haveLo = false;
@@ -470,11 +560,9 @@ PT_D float3 traceShadow(const DevScene& S, float3 org, float3 dir, float tmax, u
   uint32_t loId = 0;
   for(;;)
   {
-    TraceHit h = traverseNext<false, false>(S.bvh, org, dir, 0.0f, tmax, haveLo, loT, loId, stats ? &stats->nodesVisited : nullptr, stats ? &stats->trisTested : nullptr);
+    const TraceHit h = traverseNext<false, false>(S.bvhAlpha, org, dir, 0.0f, tmax, haveLo, loT, loId, nc, tc);
     if(h.slot == 0xFFFFFFFFu)
       return total;
-    if((h.w0 >> 28) & TRI_OPAQUE)
-      return f3(0.0f);
     const uint2               meta = S.triMeta[h.slot];
     const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
     const DevPrim&            P = S.prims[node.renderPrimID];

@@ -33,45 +33,64 @@ PT_D uint32_t signExtendS8x4(uint32_t x)
   return ((x >> 7) & 0x01010101u) * 0xffu;
 }
 
-#ifdef B200PT_COUNT_TRAVERSAL
-#define PT_COUNT_NODE() (nodeCount++)
-#define PT_COUNT_TRI() (triCount++)
-#else
-#define PT_COUNT_NODE()
-#define PT_COUNT_TRI()
-#endif
-
-// MODE_CLOSEST: back-face culling per triangle flags (RAY_FLAG_CULL_BACK_FACING_TRIANGLES + instance
-//               cull-disable);  MODE_SHADOW: no culling (RAY_FLAG_NONE).
-// anyHitExit: stop at the first accepted triangle (valid only when every triangle is opaque).
-template <bool CULL, bool ANY_EXIT>
-PT_D TraceHit traverseNext(const BvhView bvh, float3 org, float3 dir, float tmin, float tmax, bool haveLo, float loT, uint32_t loId,
-                           unsigned long long* nodeCounter = nullptr, unsigned long long* triCounter = nullptr)
+// One traversal in flight, resumable one node-step at a time (the persistent kernels interleave the
+// steps of 32 independent rays per warp and re-fill finished lanes from a global work counter).
+//   cull    : back-face culling per triangle flags (RAY_FLAG_CULL_BACK_FACING_TRIANGLES + instance cull-disable)
+//   anyExit : stop at the first accepted triangle (occlusion query against the opaque tree)
+//   lo      : only hits lexicographically after (loT, loId) in (t, global id) order count
+struct TravState
 {
+  const float4* nodes;
+  const float4* tris;
+  float3        org, dir;
+  float         idx, idy, idz;
+  float         tmin, tmax, tLow, loT;
+  uint32_t      loId, octInv4;
+  bool          haveLo, cull, anyExit;
+  TraceHit      best;
+  uint2         cur;
+  int           sp;
+  uint2         stack[24];
 #ifdef B200PT_COUNT_TRAVERSAL
-  unsigned int nodeCount = 0, triCount = 0;
+  unsigned int nodeCount, triCount;
 #endif
-  TraceHit best;
-  best.t = tmax;
-  best.slot = 0xFFFFFFFFu;
-  best.gid = 0xFFFFFFFFu;
-  best.u = best.v = 0.f;
-  best.w0 = 0;
 
-  const float ooeps = 1e-20f;
-  const float dx = fabsf(dir.x) > ooeps ? dir.x : copysignf(ooeps, dir.x);
-  const float dy = fabsf(dir.y) > ooeps ? dir.y : copysignf(ooeps, dir.y);
-  const float dz = fabsf(dir.z) > ooeps ? dir.z : copysignf(ooeps, dir.z);
-  const float idx = 1.0f / dx, idy = 1.0f / dy, idz = 1.0f / dz;
-  const uint32_t octInv = ((dir.x < 0.f ? 0u : 4u) | (dir.y < 0.f ? 0u : 2u) | (dir.z < 0.f ? 0u : 1u));
-  const uint32_t octInv4 = octInv * 0x01010101u;
-  const float    tLow = haveLo ? fmaxf(tmin, loT) : tmin;
+  PT_D void init(const BvhView bvh, float3 o, float3 d, float tmin_, float tmax_, bool cull_, bool anyExit_, bool haveLo_, float loT_, uint32_t loId_)
+  {
+    nodes = bvh.nodes;
+    tris = bvh.tris;
+    org = o;
+    dir = d;
+    const float ooeps = 1e-20f;
+    const float dx = fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x);
+    const float dy = fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y);
+    const float dz = fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z);
+    idx = 1.0f / dx;
+    idy = 1.0f / dy;
+    idz = 1.0f / dz;
+    octInv4 = ((d.x < 0.f ? 0u : 4u) | (d.y < 0.f ? 0u : 2u) | (d.z < 0.f ? 0u : 1u)) * 0x01010101u;
+    tmin = tmin_;
+    tmax = tmax_;
+    haveLo = haveLo_;
+    loT = loT_;
+    loId = loId_;
+    tLow = haveLo_ ? fmaxf(tmin_, loT_) : tmin_;
+    cull = cull_;
+    anyExit = anyExit_;
+    best.t = tmax_;
+    best.slot = 0xFFFFFFFFu;
+    best.gid = 0xFFFFFFFFu;
+    best.u = best.v = 0.f;
+    best.w0 = 0;
+    cur = make_uint2(0u, 0x80000000u);
+    sp = 0;
+#ifdef B200PT_COUNT_TRAVERSAL
+    nodeCount = triCount = 0;
+#endif
+  }
 
-  uint2 stack[32];
-  int   sp = 0;
-  uint2 cur = make_uint2(0u, 0x80000000u);
-
-  while(true)
+  // one node (or one postponed triangle group); returns true when the traversal is complete
+  PT_D bool step()
   {
     uint2 triGroup;
     if(cur.y & 0xff000000u)
@@ -81,19 +100,20 @@ PT_D TraceHit traverseNext(const BvhView bvh, float3 org, float3 dir, float tmin
       cur.y &= ~(1u << childBit);
       if(cur.y & 0xff000000u)
       {
-        if(sp < 32)
+        if(sp < 24)
           stack[sp++] = cur;
       }
       const uint32_t slotIndex = (uint32_t)(childBit - 24) ^ (octInv4 & 0xffu);
       const uint32_t relative = __popc(hitsImask & ~(0xffffffffu << slotIndex));
       const uint32_t nodeIndex = cur.x + relative;
-      PT_COUNT_NODE();
-
-      const float4 n0 = __ldg(&bvh.nodes[nodeIndex * 5 + 0]);
-      const float4 n1 = __ldg(&bvh.nodes[nodeIndex * 5 + 1]);
-      const float4 n2 = __ldg(&bvh.nodes[nodeIndex * 5 + 2]);
-      const float4 n3 = __ldg(&bvh.nodes[nodeIndex * 5 + 3]);
-      const float4 n4 = __ldg(&bvh.nodes[nodeIndex * 5 + 4]);
+#ifdef B200PT_COUNT_TRAVERSAL
+      nodeCount++;
+#endif
+      const float4 n0 = __ldg(&nodes[nodeIndex * 5 + 0]);
+      const float4 n1 = __ldg(&nodes[nodeIndex * 5 + 1]);
+      const float4 n2 = __ldg(&nodes[nodeIndex * 5 + 2]);
+      const float4 n3 = __ldg(&nodes[nodeIndex * 5 + 3]);
+      const float4 n4 = __ldg(&nodes[nodeIndex * 5 + 4]);
 
       const uint32_t eImask = __float_as_uint(n0.w);
       const float    adx = __uint_as_float(extractByte(eImask, 0) << 23) * idx;
@@ -151,45 +171,40 @@ PT_D TraceHit traverseNext(const BvhView bvh, float3 org, float3 dir, float tmin
       cur = make_uint2(0u, 0u);
     }
 
+    // Triangle group.  The body is branch-free up to the final "closer hit" update: an early `continue`
+    // per rejection test lets lanes drift apart inside the loop (measured: 1 active lane per warp
+    // instruction), so every test is folded into one predicate and the lanes stay converged.
     while(triGroup.y != 0)
     {
       const int triBit = 31 - __clz(triGroup.y);
       triGroup.y &= ~(1u << triBit);
       const uint32_t slot = triGroup.x + (uint32_t)triBit;
-      PT_COUNT_TRI();
-      const float4 a = __ldg(&bvh.tris[slot * 3 + 0]);
-      const float4 b = __ldg(&bvh.tris[slot * 3 + 1]);
-      const float4 c = __ldg(&bvh.tris[slot * 3 + 2]);
+#ifdef B200PT_COUNT_TRAVERSAL
+      triCount++;
+#endif
+      const float4 a = __ldg(&tris[slot * 3 + 0]);
+      const float4 b = __ldg(&tris[slot * 3 + 1]);
+      const float4 c = __ldg(&tris[slot * 3 + 2]);
       const float3 v0 = f3(a.x, a.y, a.z), e1 = f3(b.x, b.y, b.z), e2 = f3(c.x, c.y, c.z);
       // Moeller-Trumbore, explicit fma chain (bit-identical to oracle/pt_oracle.cpp intersectTri)
-      const float3 pvec = crossFma(dir, e2);
-      const float  det = dotFma(e1, pvec);
-      if(det == 0.0f)
-        continue;
-      const float  inv = 1.0f / det;
-      const float3 tvec = org - v0;
-      const float  u = dotFma(tvec, pvec) * inv;
-      if(u < 0.0f || u > 1.0f)
-        continue;
-      const float3 qvec = crossFma(tvec, e1);
-      const float  v = dotFma(dir, qvec) * inv;
-      if(v < 0.0f || u + v > 1.0f)
-        continue;
+      const float3   pvec = crossFma(dir, e2);
+      const float    det = dotFma(e1, pvec);
+      const float    inv = 1.0f / det;
+      const float3   tvec = org - v0;
+      const float    u = dotFma(tvec, pvec) * inv;
+      const float3   qvec = crossFma(tvec, e1);
+      const float    v = dotFma(dir, qvec) * inv;
       const float    t = dotFma(e2, qvec) * inv;
       const uint32_t w0 = __float_as_uint(a.w);
       const uint32_t flags = w0 >> 28;
-      if(CULL && !(flags & TRI_NOCULL))
-      {
-        const bool front = (flags & TRI_FLIPPED) ? (det < 0.0f) : (det > 0.0f);
-        if(!front)
-          continue;
-      }
-      if(!(t > tmin && t < tmax))
-        continue;
       const uint32_t gid = __float_as_uint(c.w);
-      if(haveLo && !(t > loT || (t == loT && gid > loId)))
-        continue;
-      if(t < best.t || (t == best.t && gid < best.gid))
+      // det == 0 gives inf/NaN in u,v,t: every comparison below is then false except the ones guarded by `det != 0`
+      bool hit = (det != 0.0f) & (u >= 0.0f) & (u <= 1.0f) & (v >= 0.0f) & (u + v <= 1.0f) & (t > tmin) & (t < tmax);
+      const bool front = (flags & TRI_FLIPPED) ? (det < 0.0f) : (det > 0.0f);
+      hit &= !cull | ((flags & TRI_NOCULL) != 0) | front;
+      hit &= !haveLo | (t > loT) | ((t == loT) & (gid > loId));
+      hit &= (t < best.t) | ((t == best.t) & (gid < best.gid));
+      if(hit)
       {
         best.t = t;
         best.u = u;
@@ -197,11 +212,12 @@ PT_D TraceHit traverseNext(const BvhView bvh, float3 org, float3 dir, float tmin
         best.slot = slot;
         best.gid = gid;
         best.w0 = w0;
-        if(ANY_EXIT)
+        if(anyExit)
         {
-          sp = 0;
+          // occlusion query satisfied: drop all pending work, the pop below reports completion
+          triGroup.y = 0;
           cur.y = 0;
-          break;
+          sp = 0;
         }
       }
     }
@@ -209,23 +225,51 @@ PT_D TraceHit traverseNext(const BvhView bvh, float3 org, float3 dir, float tmin
     if((cur.y & 0xff000000u) == 0)
     {
       if(sp == 0)
-        break;
+        return true;
       cur = stack[--sp];
     }
+    return false;
   }
-  if(best.slot != 0xFFFFFFFFu && ((best.w0 >> 28) & TRI_FLIPPED))
+
+  // the hit with (u,v) restored for mirrored instances
+  PT_D TraceHit result() const
   {
-    const float tmp = best.u;
-    best.u = best.v;
-    best.v = tmp;
+    TraceHit h = best;
+    if(h.slot != 0xFFFFFFFFu && ((h.w0 >> 28) & TRI_FLIPPED))
+    {
+      h.u = best.v;
+      h.v = best.u;
+    }
+    return h;
   }
+
+  PT_D void flushCounters(unsigned long long* nodeCounter, unsigned long long* triCounter)
+  {
 #ifdef B200PT_COUNT_TRAVERSAL
-  if(nodeCounter)
-    atomicAdd(nodeCounter, (unsigned long long)nodeCount);
-  if(triCounter)
-    atomicAdd(triCounter, (unsigned long long)triCount);
+    if(nodeCounter)
+      atomicAdd(nodeCounter, (unsigned long long)nodeCount);
+    if(triCounter)
+      atomicAdd(triCounter, (unsigned long long)triCount);
+    nodeCount = triCount = 0;
+#else
+    (void)nodeCounter;
+    (void)triCounter;
 #endif
-  return best;
+  }
+};
+
+// run one traversal to completion (ray-level API kernels and the any-hit restart loops)
+template <bool CULL, bool ANY_EXIT>
+PT_D TraceHit traverseNext(const BvhView bvh, float3 org, float3 dir, float tmin, float tmax, bool haveLo, float loT, uint32_t loId,
+                           unsigned long long* nodeCounter = nullptr, unsigned long long* triCounter = nullptr)
+{
+  TravState T;
+  T.init(bvh, org, dir, tmin, tmax, CULL, ANY_EXIT, haveLo, loT, loId);
+  while(!T.step())
+  {
+  }
+  T.flushCounters(nodeCounter, triCounter);
+  return T.result();
 }
 
 }  // namespace pt
