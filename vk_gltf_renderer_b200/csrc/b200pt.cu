@@ -171,14 +171,19 @@ __device__ __forceinline__ uint32_t fetchWork(bool need, uint32_t* workCounter, 
 }
 
 // IRaytracer::Trace for every path in the queue.
+// Per lane: path (-1 needs work, -2 exhausted), a resumable traversal, and a small state machine that runs in
+// the CONVERGED part of the loop (phase changes, stochastic alpha test, result write), never inside the
+// traversal loop, so the hot loop contains nothing but node / triangle steps.
 __global__ void __launch_bounds__(128) k_trace(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn,
                                                uint32_t* workCounter, DevStats* stats)
 {
   stageSrgbLut(S.lutSrgb);
   const uint32_t count = *cntIn;
   TravState      T;
-  int            path = -1;  // -1: lane needs a ray, -2: queue exhausted
-  int            phase = 0;  // 0: opaque tree, 1: alpha (any-hit) tree
+  uint2          stack[TravState::kStackSize];
+  int            path = -1;
+  int            phase = 0;        // 0: opaque tree, 1: alpha (any-hit) tree
+  bool           travDone = false;  // traversal finished, state machine pending
   TraceHit       ho;
   uint32_t       seed = 0, seedIn = 0;
   float          tmaxRay = 0.f;
@@ -186,80 +191,89 @@ __global__ void __launch_bounds__(128) k_trace(PathState P, DevScene S, const ui
   for(;;)
   {
     __syncwarp();
-    const bool     need = (path == -1);
-    const uint32_t k = fetchWork(need, workCounter, count);
-    if(need)
+    // ---- state machine for lanes whose traversal completed ----
+    if(path >= 0 && travDone)
     {
-      if(k == 0xFFFFFFFFu)
-        path = -2;
+      travDone = false;
+      T.flushCounters(&stats->nodesVisited, &stats->trisTested);
+      TraceHit res;
+      bool     done = false;
+      if(phase == 0)
+      {
+        ho = T.result();
+        if(S.hasAlpha)
+        {
+          // non-opaque candidates nearer than the opaque hit, front to back (raytracer_interface.h.slang:82-112)
+          phase = 1;
+          T.init(S.bvhAlpha, T.org, T.dir, 0.0f, (ho.slot != 0xFFFFFFFFu) ? ho.t : tmaxRay, true, false, false, 0.f, 0u);
+        }
+        else
+        {
+          res = ho;
+          done = true;
+        }
+      }
       else
       {
-        path = (int)q[k];
-        const float4 o = P.rayO[path];
-        const float4 d = P.rayD[path];
-        tmaxRay = d.w;
-        if(S.hasAlpha)
-          seed = seedIn = __float_as_uint(P.misc[path].w);
-        phase = 0;
-        T.init(S.bvh, xyz(o), xyz(d), 0.0f, tmaxRay, true, false, false, 0.f, 0u);
+        const TraceHit h = T.result();
+        if(h.slot == 0xFFFFFFFFu)
+        {
+          res = ho;
+          done = true;
+        }
+        else
+        {
+          const uint2               meta = S.triMeta[h.slot];
+          const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
+          const float               opacity = getOpacity(S, node, S.prims[node.renderPrimID], meta.y, f3(1.0f - h.u - h.v, h.u, h.v));
+          if(rnd(seed) <= opacity)
+          {
+            res = h;
+            done = true;
+          }
+          else
+            T.init(S.bvhAlpha, T.org, T.dir, 0.0f, T.tmax, true, false, true, h.t, h.gid);
+        }
+      }
+      if(done)
+      {
+        P.hit[path] = f4(res.t, res.u, res.v, __uint_as_float(res.slot));
+        if(seed != seedIn)
+          reinterpret_cast<uint32_t*>(&P.misc[path])[3] = seed;
+        path = -1;
+      }
+    }
+    __syncwarp();
+    // ---- refill ----
+    {
+      const bool     need = (path == -1);
+      const uint32_t k = fetchWork(need, workCounter, count);
+      if(need)
+      {
+        if(k == 0xFFFFFFFFu)
+          path = -2;
+        else
+        {
+          path = (int)q[k];
+          const float4 o = P.rayO[path];
+          const float4 d = P.rayD[path];
+          tmaxRay = d.w;
+          if(S.hasAlpha)
+            seed = seedIn = __float_as_uint(P.misc[path].w);
+          phase = 0;
+          T.init(S.bvh, xyz(o), xyz(d), 0.0f, tmaxRay, true, false, false, 0.f, 0u);
+        }
       }
     }
     if(__all_sync(0xffffffffu, path == -2))
       break;
-    while(path >= 0)
+    // ---- traverse: warp-uniform loop (all 32 lanes iterate, idle lanes are predicated off) until too few
+    //      lanes are still busy ----
+    for(;;)
     {
-      if(T.step())
-      {
-        T.flushCounters(&stats->nodesVisited, &stats->trisTested);
-        TraceHit res;
-        bool     done = false;
-        if(phase == 0)
-        {
-          ho = T.result();
-          if(S.hasAlpha)
-          {
-            // non-opaque candidates nearer than the opaque hit, front to back (raytracer_interface.h.slang:82-112)
-            phase = 1;
-            T.init(S.bvhAlpha, T.org, T.dir, 0.0f, (ho.slot != 0xFFFFFFFFu) ? ho.t : tmaxRay, true, false, false, 0.f, 0u);
-          }
-          else
-          {
-            res = ho;
-            done = true;
-          }
-        }
-        else
-        {
-          const TraceHit h = T.result();
-          if(h.slot == 0xFFFFFFFFu)
-          {
-            res = ho;
-            done = true;
-          }
-          else
-          {
-            const uint2               meta = S.triMeta[h.slot];
-            const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
-            const float               opacity = getOpacity(S, node, S.prims[node.renderPrimID], meta.y, f3(1.0f - h.u - h.v, h.u, h.v));
-            if(rnd(seed) <= opacity)
-            {
-              res = h;
-              done = true;
-            }
-            else
-              T.init(S.bvhAlpha, T.org, T.dir, 0.0f, T.tmax, true, false, true, h.t, h.gid);
-          }
-        }
-        if(done)
-        {
-          P.hit[path] = f4(res.t, res.u, res.v, __uint_as_float(res.slot));
-          if(seed != seedIn)
-            reinterpret_cast<uint32_t*>(&P.misc[path])[3] = seed;
-          path = -1;
-          break;
-        }
-      }
-      if(__popc(__activemask()) < kRefillThreshold)
+      if(path >= 0 && !travDone)
+        travDone = T.step(stack);
+      if(__popc(__ballot_sync(0xffffffffu, path >= 0 && !travDone)) < kRefillThreshold)
         break;
     }
   }
@@ -567,8 +581,10 @@ __global__ void __launch_bounds__(128) k_post(PathState P, DevScene S, const __g
   stageSrgbLut(S.lutSrgb);
   const uint32_t count = *cntIn;
   TravState      T;
+  uint2          stack[TravState::kStackSize];
   int            path = -1;  // -1: lane needs work, -2: queue exhausted
   int            phase = 0;  // 0: opaque occlusion query, 1: any-hit candidates front to back
+  bool           travDone = false;
   uint32_t       flags = 0, seed = 0;
   float3         total = f3(1.0f);
   bool           isInside = false;
@@ -576,9 +592,71 @@ __global__ void __launch_bounds__(128) k_post(PathState P, DevScene S, const __g
   for(;;)
   {
     __syncwarp();
-    // refill: paths without a shadow ray are finished on the spot and the lane fetches again
+    // ---- state machine for lanes whose shadow traversal completed (converged code) ----
+    if(path >= 0 && travDone)
+    {
+      travDone = false;
+      T.flushCounters(&stats->nodesVisited, &stats->trisTested);
+      bool done = false;
+      if(phase == 0)
+      {
+        if(T.best.slot != 0xFFFFFFFFu)
+        {
+          total = f3(0.0f);
+          done = true;
+        }
+        else if(S.hasAlpha)
+        {
+          phase = 1;
+          T.init(S.bvhAlpha, T.org, T.dir, 0.0f, T.tmax, false, false, false, 0.f, 0u);
+        }
+        else
+          done = true;
+      }
+      else
+      {
+        // 2. every non-opaque candidate, front to back (raytracer_interface.h.slang:149-179)
+        const TraceHit h = T.result();
+        if(h.slot == 0xFFFFFFFFu)
+          done = true;
+        else
+        {
+          const uint2               meta = S.triMeta[h.slot];
+          const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
+          const DevPrim&            prim = S.prims[node.renderPrimID];
+          const float3              bary = f3(1.0f - h.u - h.v, h.u, h.v);
+          const float               opacity = getOpacity(S, node, prim, meta.y, bary);
+          const float               r = rnd(seed);
+          if(r < opacity)
+          {
+            const float  seg = fmaxf(0.0f, h.t - prevHitT);
+            const float3 cur = getShadowTransmission(S, node, prim, meta.y, bary, seg, T.dir, isInside);
+            prevHitT = h.t;
+            total *= cur;
+            if(maxc(total) <= 0.01f)
+            {
+              total = f3(0.0f);
+              done = true;
+            }
+          }
+          if(!done)
+            T.init(S.bvhAlpha, T.org, T.dir, 0.0f, T.tmax, false, false, true, h.t, h.gid);
+        }
+      }
+      if(done)
+      {
+#ifdef B200PT_DEBUG
+        if((float)((uint32_t)path % (uint32_t)F.width) == F.pc.mouseCoord[0] && (float)(F.tileY0 + (uint32_t)path / (uint32_t)F.width) == F.pc.mouseCoord[1])
+          printf("DBG shadow o=%.9g %.9g %.9g d=%.9g %.9g %.9g tmax=%.9g T=%.9g %.9g %.9g\n", T.org.x, T.org.y, T.org.z, T.dir.x, T.dir.y, T.dir.z, T.tmax, total.x, total.y, total.z);
+#endif
+        finishPost(P, F, (uint32_t)path, flags, seed, true, total, qNext, cntNext, stats);
+        path = -1;
+      }
+    }
+    // ---- refill: paths without a shadow ray are finished on the spot and the lane fetches again ----
     for(;;)
     {
+      __syncwarp();
       const bool     need = (path == -1);
       const uint32_t k = fetchWork(need, workCounter, count);
       if(need)
@@ -610,75 +688,16 @@ __global__ void __launch_bounds__(128) k_post(PathState P, DevScene S, const __g
           }
         }
       }
-      __syncwarp();
       if(!__any_sync(0xffffffffu, path == -1))
         break;
     }
     if(__all_sync(0xffffffffu, path == -2))
       break;
-    while(path >= 0)
+    for(;;)
     {
-      if(T.step())
-      {
-        T.flushCounters(&stats->nodesVisited, &stats->trisTested);
-        bool done = false;
-        if(phase == 0)
-        {
-          if(T.best.slot != 0xFFFFFFFFu)
-          {
-            total = f3(0.0f);
-            done = true;
-          }
-          else if(S.hasAlpha)
-          {
-            phase = 1;
-            T.init(S.bvhAlpha, T.org, T.dir, 0.0f, T.tmax, false, false, false, 0.f, 0u);
-          }
-          else
-            done = true;
-        }
-        else
-        {
-          // 2. every non-opaque candidate, front to back (:149-179)
-          const TraceHit h = T.result();
-          if(h.slot == 0xFFFFFFFFu)
-            done = true;
-          else
-          {
-            const uint2               meta = S.triMeta[h.slot];
-            const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
-            const DevPrim&            prim = S.prims[node.renderPrimID];
-            const float3              bary = f3(1.0f - h.u - h.v, h.u, h.v);
-            const float               opacity = getOpacity(S, node, prim, meta.y, bary);
-            const float               r = rnd(seed);
-            if(r < opacity)
-            {
-              const float  seg = fmaxf(0.0f, h.t - prevHitT);
-              const float3 cur = getShadowTransmission(S, node, prim, meta.y, bary, seg, T.dir, isInside);
-              prevHitT = h.t;
-              total *= cur;
-              if(maxc(total) <= 0.01f)
-              {
-                total = f3(0.0f);
-                done = true;
-              }
-            }
-            if(!done)
-              T.init(S.bvhAlpha, T.org, T.dir, 0.0f, T.tmax, false, false, true, h.t, h.gid);
-          }
-        }
-        if(done)
-        {
-#ifdef B200PT_DEBUG
-          if((float)((uint32_t)path % (uint32_t)F.width) == F.pc.mouseCoord[0] && (float)(F.tileY0 + (uint32_t)path / (uint32_t)F.width) == F.pc.mouseCoord[1])
-            printf("DBG shadow o=%.9g %.9g %.9g d=%.9g %.9g %.9g tmax=%.9g T=%.9g %.9g %.9g\n", T.org.x, T.org.y, T.org.z, T.dir.x, T.dir.y, T.dir.z, T.tmax, total.x, total.y, total.z);
-#endif
-          finishPost(P, F, (uint32_t)path, flags, seed, true, total, qNext, cntNext, stats);
-          path = -1;
-          break;
-        }
-      }
-      if(__popc(__activemask()) < kRefillThreshold)
+      if(path >= 0 && !travDone)
+        travDone = T.step(stack);
+      if(__popc(__ballot_sync(0xffffffffu, path >= 0 && !travDone)) < kRefillThreshold)
         break;
     }
   }

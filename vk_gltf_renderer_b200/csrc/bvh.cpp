@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace pt {
@@ -112,17 +113,9 @@ struct Builder
       n2[j.node].box = bb;
       n2[j.node].first = j.first;
       n2[j.node].count = j.count;
-      if(j.count <= 3)
-      {
-        bool split = false;
-        if(j.count > 1)
-        {
-          // split tiny leaves only when it clearly pays (long thin triangles side by side)
-          split = false;
-        }
-        if(!split)
-          continue;
-      }
+      static const int kLeaf = getenv("BVH_LEAF") ? atoi(getenv("BVH_LEAF")) : 3;
+      if((int)j.count <= kLeaf)
+        continue;
       float bestCost = FLT_MAX;
       int   bestAxis = -1, bestBin = -1;
       for(int ax = 0; ax < 3; ax++)

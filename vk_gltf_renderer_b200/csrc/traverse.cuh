@@ -48,9 +48,9 @@ struct TravState
   uint32_t      loId, octInv4;
   bool          haveLo, cull, anyExit;
   TraceHit      best;
-  uint2         cur;
-  int           sp;
-  uint2         stack[24];
+  uint2         cur;   // current node group (x = child base, y = hit bits << 24 | imask)
+  uint2         tri;   // pending triangle group (x = triangle base, y = hit bits)
+  int           sp;    // entries on the caller-provided stack (kept OUT of this struct so the rest stays in registers)
 #ifdef B200PT_COUNT_TRAVERSAL
   unsigned int nodeCount, triCount;
 #endif
@@ -83,152 +83,168 @@ struct TravState
     best.u = best.v = 0.f;
     best.w0 = 0;
     cur = make_uint2(0u, 0x80000000u);
+    tri = make_uint2(0u, 0u);
     sp = 0;
 #ifdef B200PT_COUNT_TRAVERSAL
     nodeCount = triCount = 0;
 #endif
   }
 
-  // one node (or one postponed triangle group); returns true when the traversal is complete
-  PT_D bool step()
+  static constexpr int kStackSize = 28;
+
+  // One traversal step: (1) lanes without pending triangles open their next node, (2) lanes with pending
+  // triangles test ONE triangle each — but only when enough lanes of the warp have one (vote); otherwise the
+  // group is postponed onto the stack and node traversal continues (Ylitie et al. 2017, section 4.3).
+  // Returns true when the traversal is complete.  `stack` is per-thread scratch of kStackSize entries.
+  PT_D bool step(uint2* __restrict__ stack)
   {
-    uint2 triGroup;
-    if(cur.y & 0xff000000u)
+    // single exit: an early return inside the divergent regions would move their reconvergence point out of the
+    // caller's loop and the lanes of a warp would drift apart (measured: 8 of 32 lanes active)
+    bool done = false;
+    if(tri.y == 0)
     {
-      const uint32_t hitsImask = cur.y;
-      const int      childBit = 31 - __clz(hitsImask);
-      cur.y &= ~(1u << childBit);
-      if(cur.y & 0xff000000u)
+      if((cur.y & 0xff000000u) == 0)
       {
-        if(sp < 24)
-          stack[sp++] = cur;
+        if(sp == 0)
+          done = true;
+        else
+          cur = stack[--sp];
       }
-      const uint32_t slotIndex = (uint32_t)(childBit - 24) ^ (octInv4 & 0xffu);
-      const uint32_t relative = __popc(hitsImask & ~(0xffffffffu << slotIndex));
-      const uint32_t nodeIndex = cur.x + relative;
-#ifdef B200PT_COUNT_TRAVERSAL
-      nodeCount++;
-#endif
-      const float4 n0 = __ldg(&nodes[nodeIndex * 5 + 0]);
-      const float4 n1 = __ldg(&nodes[nodeIndex * 5 + 1]);
-      const float4 n2 = __ldg(&nodes[nodeIndex * 5 + 2]);
-      const float4 n3 = __ldg(&nodes[nodeIndex * 5 + 3]);
-      const float4 n4 = __ldg(&nodes[nodeIndex * 5 + 4]);
-
-      const uint32_t eImask = __float_as_uint(n0.w);
-      const float    adx = __uint_as_float(extractByte(eImask, 0) << 23) * idx;
-      const float    ady = __uint_as_float(extractByte(eImask, 1) << 23) * idy;
-      const float    adz = __uint_as_float(extractByte(eImask, 2) << 23) * idz;
-      const float    aox = (n0.x - org.x) * idx;
-      const float    aoy = (n0.y - org.y) * idy;
-      const float    aoz = (n0.z - org.z) * idz;
-
-      cur.x = __float_as_uint(n1.x);
-      triGroup.x = __float_as_uint(n1.y);
-
-      uint32_t hitMask = 0;
-#pragma unroll
-      for(int i = 0; i < 2; i++)
+      if(done)
       {
-        const uint32_t meta4 = __float_as_uint(i == 0 ? n1.z : n1.w);
-        const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t innerMask4 = signExtendS8x4(isInner4 << 3);
-        const uint32_t bitIndex4 = (meta4 ^ (octInv4 & innerMask4)) & 0x1f1f1f1fu;
-        const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
-
-        const uint32_t qlox = __float_as_uint(i == 0 ? n2.x : n2.y), qhix = __float_as_uint(i == 0 ? n2.z : n2.w);
-        const uint32_t qloy = __float_as_uint(i == 0 ? n3.x : n3.y), qhiy = __float_as_uint(i == 0 ? n3.z : n3.w);
-        const uint32_t qloz = __float_as_uint(i == 0 ? n4.x : n4.y), qhiz = __float_as_uint(i == 0 ? n4.z : n4.w);
-        const uint32_t xmin = dir.x < 0.f ? qhix : qlox, xmax = dir.x < 0.f ? qlox : qhix;
-        const uint32_t ymin = dir.y < 0.f ? qhiy : qloy, ymax = dir.y < 0.f ? qloy : qhiy;
-        const uint32_t zmin = dir.z < 0.f ? qhiz : qloz, zmax = dir.z < 0.f ? qloz : qhiz;
-#pragma unroll
-        for(int j = 0; j < 4; j++)
+      }
+      else if(cur.y & 0xff000000u)
+      {
+        const uint32_t hitsImask = cur.y;
+        const int      childBit = 31 - __clz(hitsImask);
+        cur.y &= ~(1u << childBit);
+        if(cur.y & 0xff000000u)
         {
-          const float tminx = fmaf((float)extractByte(xmin, j), adx, aox);
-          const float tminy = fmaf((float)extractByte(ymin, j), ady, aoy);
-          const float tminz = fmaf((float)extractByte(zmin, j), adz, aoz);
-          const float tmaxx = fmaf((float)extractByte(xmax, j), adx, aox);
-          const float tmaxy = fmaf((float)extractByte(ymax, j), ady, aoy);
-          const float tmaxz = fmaf((float)extractByte(zmax, j), adz, aoz);
-          const float tn = fmaxf(fmaxf(tminx, tminy), fmaxf(tminz, tLow));
-          const float tf = fminf(fminf(tmaxx, tmaxy), fminf(tmaxz, best.t));
-          // widen by a few ulp: keeps the box test conservative w.r.t. the triangle test
-          if(tn <= tf * 1.000001f)
+          if(sp < kStackSize)
+            stack[sp++] = cur;
+        }
+        const uint32_t slotIndex = (uint32_t)(childBit - 24) ^ (octInv4 & 0xffu);
+        const uint32_t relative = __popc(hitsImask & ~(0xffffffffu << slotIndex));
+        const uint32_t nodeIndex = cur.x + relative;
+#ifdef B200PT_COUNT_TRAVERSAL
+        nodeCount++;
+#endif
+        const float4 n0 = __ldg(&nodes[nodeIndex * 5 + 0]);
+        const float4 n1 = __ldg(&nodes[nodeIndex * 5 + 1]);
+        const float4 n2 = __ldg(&nodes[nodeIndex * 5 + 2]);
+        const float4 n3 = __ldg(&nodes[nodeIndex * 5 + 3]);
+        const float4 n4 = __ldg(&nodes[nodeIndex * 5 + 4]);
+
+        const uint32_t eImask = __float_as_uint(n0.w);
+        const float    adx = __uint_as_float(extractByte(eImask, 0) << 23) * idx;
+        const float    ady = __uint_as_float(extractByte(eImask, 1) << 23) * idy;
+        const float    adz = __uint_as_float(extractByte(eImask, 2) << 23) * idz;
+        const float    aox = (n0.x - org.x) * idx;
+        const float    aoy = (n0.y - org.y) * idy;
+        const float    aoz = (n0.z - org.z) * idz;
+
+        cur.x = __float_as_uint(n1.x);
+        tri.x = __float_as_uint(n1.y);
+
+        uint32_t hitMask = 0;
+#pragma unroll
+        for(int i = 0; i < 2; i++)
+        {
+          const uint32_t meta4 = __float_as_uint(i == 0 ? n1.z : n1.w);
+          const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+          const uint32_t innerMask4 = signExtendS8x4(isInner4 << 3);
+          const uint32_t bitIndex4 = (meta4 ^ (octInv4 & innerMask4)) & 0x1f1f1f1fu;
+          const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+
+          const uint32_t qlox = __float_as_uint(i == 0 ? n2.x : n2.y), qhix = __float_as_uint(i == 0 ? n2.z : n2.w);
+          const uint32_t qloy = __float_as_uint(i == 0 ? n3.x : n3.y), qhiy = __float_as_uint(i == 0 ? n3.z : n3.w);
+          const uint32_t qloz = __float_as_uint(i == 0 ? n4.x : n4.y), qhiz = __float_as_uint(i == 0 ? n4.z : n4.w);
+          const uint32_t xmin = dir.x < 0.f ? qhix : qlox, xmax = dir.x < 0.f ? qlox : qhix;
+          const uint32_t ymin = dir.y < 0.f ? qhiy : qloy, ymax = dir.y < 0.f ? qloy : qhiy;
+          const uint32_t zmin = dir.z < 0.f ? qhiz : qloz, zmax = dir.z < 0.f ? qloz : qhiz;
+#pragma unroll
+          for(int j = 0; j < 4; j++)
           {
-            const uint32_t childBits = extractByte(childBits4, j);
-            const uint32_t bitIndex = extractByte(bitIndex4, j);
-            hitMask |= childBits << bitIndex;
+            const float tminx = fmaf((float)extractByte(xmin, j), adx, aox);
+            const float tminy = fmaf((float)extractByte(ymin, j), ady, aoy);
+            const float tminz = fmaf((float)extractByte(zmin, j), adz, aoz);
+            const float tmaxx = fmaf((float)extractByte(xmax, j), adx, aox);
+            const float tmaxy = fmaf((float)extractByte(ymax, j), ady, aoy);
+            const float tmaxz = fmaf((float)extractByte(zmax, j), adz, aoz);
+            const float tn = fmaxf(fmaxf(tminx, tminy), fmaxf(tminz, tLow));
+            const float tf = fminf(fminf(tmaxx, tmaxy), fminf(tmaxz, best.t));
+            // widen by a few ulp: keeps the box test conservative w.r.t. the triangle test
+            const bool     in = tn <= tf * 1.000001f;
+            const uint32_t childBits = in ? extractByte(childBits4, j) : 0u;
+            hitMask |= childBits << extractByte(bitIndex4, j);
           }
         }
+        cur.y = (hitMask & 0xff000000u) | (eImask >> 24);
+        tri.y = hitMask & 0x00ffffffu;
       }
-      cur.y = (hitMask & 0xff000000u) | (eImask >> 24);
-      triGroup.y = hitMask & 0x00ffffffu;
-    }
-    else
-    {
-      triGroup = cur;
-      cur = make_uint2(0u, 0u);
+      else
+      {
+        // a postponed triangle group came off the stack
+        tri = cur;
+        cur = make_uint2(0u, 0u);
+      }
     }
 
-    // Triangle group.  The body is branch-free up to the final "closer hit" update: an early `continue`
-    // per rejection test lets lanes drift apart inside the loop (measured: 1 active lane per warp
-    // instruction), so every test is folded into one predicate and the lanes stay converged.
-    while(triGroup.y != 0)
+    // ---- triangle phase (one triangle per lane per step) ------------------------------------------------
+    const unsigned conv = __activemask();
+    const unsigned haveTri = __ballot_sync(conv, !done && tri.y != 0);
+    if(!done && tri.y != 0)
     {
-      const int triBit = 31 - __clz(triGroup.y);
-      triGroup.y &= ~(1u << triBit);
-      const uint32_t slot = triGroup.x + (uint32_t)triBit;
-#ifdef B200PT_COUNT_TRAVERSAL
-      triCount++;
-#endif
-      const float4 a = __ldg(&tris[slot * 3 + 0]);
-      const float4 b = __ldg(&tris[slot * 3 + 1]);
-      const float4 c = __ldg(&tris[slot * 3 + 2]);
-      const float3 v0 = f3(a.x, a.y, a.z), e1 = f3(b.x, b.y, b.z), e2 = f3(c.x, c.y, c.z);
-      // Moeller-Trumbore, explicit fma chain (bit-identical to oracle/pt_oracle.cpp intersectTri)
-      const float3   pvec = crossFma(dir, e2);
-      const float    det = dotFma(e1, pvec);
-      const float    inv = 1.0f / det;
-      const float3   tvec = org - v0;
-      const float    u = dotFma(tvec, pvec) * inv;
-      const float3   qvec = crossFma(tvec, e1);
-      const float    v = dotFma(dir, qvec) * inv;
-      const float    t = dotFma(e2, qvec) * inv;
-      const uint32_t w0 = __float_as_uint(a.w);
-      const uint32_t flags = w0 >> 28;
-      const uint32_t gid = __float_as_uint(c.w);
-      // det == 0 gives inf/NaN in u,v,t: every comparison below is then false except the ones guarded by `det != 0`
-      bool hit = (det != 0.0f) & (u >= 0.0f) & (u <= 1.0f) & (v >= 0.0f) & (u + v <= 1.0f) & (t > tmin) & (t < tmax);
-      const bool front = (flags & TRI_FLIPPED) ? (det < 0.0f) : (det > 0.0f);
-      hit &= !cull | ((flags & TRI_NOCULL) != 0) | front;
-      hit &= !haveLo | (t > loT) | ((t == loT) & (gid > loId));
-      hit &= (t < best.t) | ((t == best.t) & (gid < best.gid));
-      if(hit)
+      // postpone when few lanes would take part and this lane's current node group still has children to open
+      // (the group goes under the next node; `cur` only ever holds node groups)
+      if(__popc(haveTri) * 4 < __popc(conv) && (cur.y & 0xff000000u) != 0 && sp < kStackSize)
       {
-        best.t = t;
-        best.u = u;
-        best.v = v;
-        best.slot = slot;
-        best.gid = gid;
-        best.w0 = w0;
-        if(anyExit)
+        stack[sp++] = tri;
+        tri.y = 0;
+      }
+      else
+      {
+        const int triBit = 31 - __clz(tri.y);
+        tri.y &= ~(1u << triBit);
+        const uint32_t slot = tri.x + (uint32_t)triBit;
+#ifdef B200PT_COUNT_TRAVERSAL
+        triCount++;
+#endif
+        const float4 a = __ldg(&tris[slot * 3 + 0]);
+        const float4 b = __ldg(&tris[slot * 3 + 1]);
+        const float4 c = __ldg(&tris[slot * 3 + 2]);
+        const float3 v0 = f3(a.x, a.y, a.z), e1 = f3(b.x, b.y, b.z), e2 = f3(c.x, c.y, c.z);
+        // Moeller-Trumbore, explicit fma chain (bit-identical to oracle/pt_oracle.cpp intersectTri); branch-free
+        // up to the final update so the lanes stay converged
+        const float3   pvec = crossFma(dir, e2);
+        const float    det = dotFma(e1, pvec);
+        const float    inv = 1.0f / det;
+        const float3   tvec = org - v0;
+        const float    u = dotFma(tvec, pvec) * inv;
+        const float3   qvec = crossFma(tvec, e1);
+        const float    v = dotFma(dir, qvec) * inv;
+        const float    t = dotFma(e2, qvec) * inv;
+        const uint32_t w0 = __float_as_uint(a.w);
+        const uint32_t flags = w0 >> 28;
+        const uint32_t gid = __float_as_uint(c.w);
+        bool           hit = (det != 0.0f) & (u >= 0.0f) & (u <= 1.0f) & (v >= 0.0f) & (u + v <= 1.0f) & (t > tmin) & (t < tmax);
+        const bool     front = (flags & TRI_FLIPPED) ? (det < 0.0f) : (det > 0.0f);
+        hit &= !cull | ((flags & TRI_NOCULL) != 0) | front;
+        hit &= !haveLo | (t > loT) | ((t == loT) & (gid > loId));
+        hit &= (t < best.t) | ((t == best.t) & (gid < best.gid));
+        if(hit)
         {
-          // occlusion query satisfied: drop all pending work, the pop below reports completion
-          triGroup.y = 0;
-          cur.y = 0;
-          sp = 0;
+          best.t = t;
+          best.u = u;
+          best.v = v;
+          best.slot = slot;
+          best.gid = gid;
+          best.w0 = w0;
+          done = anyExit;  // occlusion query satisfied
         }
       }
     }
-
-    if((cur.y & 0xff000000u) == 0)
-    {
-      if(sp == 0)
-        return true;
-      cur = stack[--sp];
-    }
-    return false;
+    return done | ((tri.y == 0) & ((cur.y & 0xff000000u) == 0) & (sp == 0));
   }
 
   // the hit with (u,v) restored for mirrored instances
@@ -264,8 +280,9 @@ PT_D TraceHit traverseNext(const BvhView bvh, float3 org, float3 dir, float tmin
                            unsigned long long* nodeCounter = nullptr, unsigned long long* triCounter = nullptr)
 {
   TravState T;
+  uint2     stack[TravState::kStackSize];
   T.init(bvh, org, dir, tmin, tmax, CULL, ANY_EXIT, haveLo, loT, loId);
-  while(!T.step())
+  while(!T.step(stack))
   {
   }
   T.flushCounters(nodeCounter, triCounter);
