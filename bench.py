@@ -240,9 +240,9 @@ def main():
     from vk_gltf_renderer_b200.renderer import PathTracer, Resources
     scn, env = build_workload(args)
     W, H = args.width, args.height
-    rows_per = (H + world - 1) // world
-    y0 = rank * rows_per
-    rows = max(0, min(rows_per, H - y0))
+    from vk_gltf_renderer_b200 import tiling
+    rows_per = tiling.strip_rows(H, world)
+    y0, rows = tiling.partition_rows(H, world, rank)
     res = Resources(scene=scn, hdr_rgb=env, camera=scn.camera, size=(W, H), tile=(y0, rows))
     pt = PathTracer(local)
     pt.ptMaxDepth = args.depth

@@ -533,7 +533,9 @@ static inline void btdf_ggx_smith_eval(BsdfEvaluateData& d, const PbrMaterial& m
   const float3 h = compute_half_vector(d.k1, d.k2, mat.N, mat.ior1, mat.ior2, nk2, backside, thin);
   const float  nh = dot(mat.N, h);
   const float  k1h = dot(d.k1, h);
-  const float  k2h = dot(d.k2, h) * (backside ? -1.0f : 1.0f);
+  // thin-walled pseudo-BTDF: the half vector pairs k1 with the MIRRORED k2, so that is the direction whose
+  // cosine to h must be checked (keeps bsdfEvaluate consistent with what bsdfSample generates)
+  const float  k2h = (backside && thin) ? dot(d.k2 + mat.N * (nk2 + nk2), h) : dot(d.k2, h) * (backside ? -1.0f : 1.0f);
   if(nk1 <= 0.0f || nh <= 0.0f || k1h < 0.0f || k2h < 0.0f)
     return;
   float fr;

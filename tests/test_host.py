@@ -1,0 +1,79 @@
+"""CPU: host-side mirror of the reference's data preparation (loader, camera, HDR, synthetic scenes, tiling)."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+
+def test_box_glb_matches_reference_facts(box_scene):
+    """SURVEY.md Appendix B 'Box.glb facts': 24 vertices, 12 triangles, red dielectric, camera from node extras."""
+    s = box_scene
+    assert len(s.render_nodes) == 1 and len(s.render_prims) == 1 and len(s.materials) == 1
+    p = s.render_prims[0]
+    assert p["positions"].shape == (24, 3) and p["indices"].shape == (12, 3) and p["indices"].dtype == np.uint32
+    assert p["normals"] is not None and p["uv0"] is None and p["tangents"] is None
+    m = s.materials[0]
+    assert list(m.pbrBaseColorFactor) == pytest.approx([0.8, 0.0, 0.0, 1.0])
+    assert m.pbrMetallicFactor == 0.0 and m.pbrRoughnessFactor == 1.0 and m.alphaMode == 0 and m.doubleSided == 0
+    assert m.specularFactor == 1.0 and m.ior == 1.5 and m.pbrBaseColorTexture == 0
+    c = s.camera
+    assert c.eye.tolist() == pytest.approx([0, 0, 2.0905852]) and c.center.tolist() == [0, 0, 0]
+    assert c.yfov == pytest.approx(0.7853982)
+    assert len(s.texture_infos) == 1 and s.texture_infos[0].index == -1  # slot 0 = "no texture"
+
+
+def test_shader_ball_loads(shader_ball_scene):
+    s = shader_ball_scene
+    assert s.num_triangles() == 9450 and s.materials[0].doubleSided == 1
+    assert s.materials[0].pbrRoughnessFactor == pytest.approx(0.6)
+    assert s.render_prims[0]["uv0"] is not None
+
+
+def test_hdr_loader(std_env):
+    assert std_env.shape == (750, 1500, 3) and std_env.dtype == np.float32
+    assert np.isfinite(std_env).all() and std_env.min() >= 0 and 5 < std_env.max() < 100
+
+
+def test_camera_matrices_roundtrip(box_scene):
+    from vk_gltf_renderer_b200 import camera as cm
+    fi = cm.make_frame_info(box_scene.camera, 256, 256)
+    glm = lambda a: np.array(a[:], np.float64).reshape(4, 4).T
+    v, vi = glm(fi.viewMatrix), glm(fi.viewInv)
+    assert np.allclose(v @ vi, np.eye(4), atol=1e-5)
+    assert vi[:3, 3].tolist() == pytest.approx([0, 0, 2.0905852], abs=1e-5)
+    pc = cm.make_push_constant(box_scene.camera, 256, frame_count=0, total_samples=0)
+    assert pc.flags == 4 and pc.pixelAngle == pytest.approx(2 * math.tan(0.7853982 / 2) / 256, rel=1e-6)
+    assert pc.focalDistance == pytest.approx(2.0905852, rel=1e-6)
+    assert cm.make_push_constant(box_scene.camera, 256, frame_count=3, total_samples=3).flags == 0
+
+
+def test_texture_transform_matches_reference_quirk():
+    from vk_gltf_renderer_b200.scene import _tex_transform
+    t = _tex_transform({"extensions": {"KHR_texture_transform": {"offset": [0.1, 0.2], "rotation": 0.5, "scale": [2, 3]}}})
+    c, s = math.cos(0.5), math.sin(0.5)
+    assert t == pytest.approx((2 * c, -3 * s, 2 * s, 3 * c, 0.1, 0.2))
+
+
+def test_synth_sponza_is_deterministic_and_sized():
+    from vk_gltf_renderer_b200 import synth
+    a = synth.synth_sponza(tex_size=32, detail=0.02)
+    b = synth.synth_sponza(tex_size=32, detail=0.02)
+    assert a.num_triangles() == b.num_triangles() and len(a.materials) == 25
+    for pa, pb in zip(a.render_prims, b.render_prims):
+        assert np.array_equal(pa["positions"], pb["positions"])
+    assert np.array_equal(a.textures[0]["rgba8"], b.textures[0]["rgba8"])
+    st = synth.scene_from_state(synth.scene_state(a))
+    assert st.num_triangles() == a.num_triangles() and bytes(st.materials[3]) == bytes(a.materials[3])
+
+
+def test_tiling_partition_covers_the_frame():
+    from vk_gltf_renderer_b200 import tiling
+    for h, w in ((1080, 8), (7, 4), (1, 2), (2160, 8)):
+        rows = [tiling.partition_rows(h, w, r) for r in range(w)]
+        assert sum(n for _, n in rows) == h
+        y = 0
+        for y0, n in rows:
+            if n:
+                assert y0 == y
+                y += n

@@ -1,7 +1,7 @@
 """ctypes mirror of include/b200pt.h (the C-ABI structs).
 
-The same POD structs are consumed by the CUDA library (libb200pt.so) and — in tests only — by the
-CPU oracle (oracle/liboracle_pt.so), so both sides see byte-identical inputs.
+The POD structs are consumed by the CUDA library (libb200pt.so); the parity tests hand the very same bytes
+to their CPU checker, so both sides see identical inputs.
 
 Layouts follow the reference's host<->device structs:
   GltfRenderNode / GltfTextureInfo / GltfShadeMaterial / GltfLight  shaders/gltf_scene_io.h.slang:41-310

@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(128) k_trace(PathState P, DevScene S, const ui
     atomicAdd(&stats->closestRays, (unsigned long long)count);
 }
 
+template <uint32_t FEAT>
 __global__ void __launch_bounds__(128) k_shade(PathState P, DevScene S, const __grid_constant__ FrameParams F, const uint32_t* __restrict__ q,
                                                const uint32_t* __restrict__ cntIn, uint32_t* qPost, uint32_t* cntPost, uint32_t* qNext, uint32_t* cntNext, DevStats* stats)
 {
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(128) k_shade(PathState P, DevScene S, const __
     const int   materialIndex = max(0, node.materialID);
     const float texGrad = worldFoot * hit.texelDensity * F.pc.texGradScale;
     const b200pt_shade_material& gmat = S.mats[materialIndex];
-    PbrMaterial                  pbrMat = evaluateMaterial(S, gmat, hit, (flags & PF_INSIDE) != 0, texGrad);
+    PbrMaterial                  pbrMat = evaluateMaterial<FEAT>(S, gmat, hit, (flags & PF_INSIDE) != 0, texGrad);
 
     // firefly control: never get sharper than the roughest bounce so far (:267-268)
     misc.x = fmaxf(pbrMat.roughness.x, misc.x);
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(128) k_shade(PathState P, DevScene S, const __
     flags &= ~(PF_POST_VOLUME | PF_SHADOW_VALID | PF_SHADOW_INSIDE);
 
     // ---- in-volume segment (pathtrace_functions.h.slang:904-939, 605-672) ----
-    if(flags & PF_INSIDE)
+    if((FEAT & FEAT_VOLUME) && (flags & PF_INSIDE))
     {
       const VolumeMedium vm = unpackMedium(med);
       if(hasVolumeMedium(vm))
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(128) k_shade(PathState P, DevScene S, const __
             scatterBounces++;
             coneWidth += F.pc.pixelAngle * length(org - originBefore);
             // NEE at the scatter point (volumeScatterNEE)
-            const DirectLight dl = sampleLights(S, F, org, seed);
+            const DirectLight dl = sampleLights<FEAT>(S, F, org, seed);
             if(dl.pdf > 0.0f)
             {
               const float phasePdf = henyeyGreensteinPdf(dot(wi, dl.direction), vm.scatterAnisotropy);
@@ -437,7 +438,7 @@ __global__ void __launch_bounds__(128) k_shade(PathState P, DevScene S, const __
     coneWidth = worldFoot;
 
     // ---- next-event estimation: one light-or-environment sample, MIS (:316-351) ----
-    const DirectLight directLight = sampleLights(S, F, hit.pos, seed);
+    const DirectLight directLight = sampleLights<FEAT>(S, F, hit.pos, seed);
     const bool nextEventValid = (dot(directLight.direction, hit.nrm) > 0.0f || pbrMat.diffuseTransmissionFactor > 0.0f) && directLight.pdf != 0.0f;
     float3     contribution = f3(0.0f);
 #ifdef B200PT_DEBUG
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(128) k_shade(PathState P, DevScene S, const __
     if(nextEventValid)
     {
       const float    a = rnd(seed), b = rnd(seed), c = rnd(seed);
-      const BsdfEval ev = bsdfEvaluate(pbrMat, -dir, directLight.direction, f3(a, b, c));
+      const BsdfEval ev = bsdfEvaluate<FEAT>(pbrMat, -dir, directLight.direction, f3(a, b, c));
       if(ev.pdf > 0.0f)
       {
         const float  misWeight = (directLight.pdf == kDirac) ? 1.0f : directLight.pdf / (directLight.pdf + ev.pdf);
@@ -463,7 +464,7 @@ __global__ void __launch_bounds__(128) k_shade(PathState P, DevScene S, const __
     // ---- BSDF sampling: next direction + throughput (:357-416) ----
     {
       const float      a = rnd(seed), b = rnd(seed), c = rnd(seed);
-      const BsdfSample sd = bsdfSample(pbrMat, -dir, f3(a, b, c));
+      const BsdfSample sd = bsdfSample<FEAT>(pbrMat, -dir, f3(a, b, c));
 #ifdef B200PT_DEBUG
       if(dbgPixel)
         printf("DBG sample xi=%.9g %.9g %.9g k2=%.9g %.9g %.9g bop=%.9g %.9g %.9g pdf=%.9g ev=%d contrib=%.9g %.9g %.9g\n", a, b, c, sd.k2.x, sd.k2.y, sd.k2.z, sd.bsdf_over_pdf.x,
@@ -476,10 +477,10 @@ __global__ void __launch_bounds__(128) k_shade(PathState P, DevScene S, const __
       {
         const float3 offsetDir = dot(dir, hit.geonrm) > 0 ? hit.geonrm : -hit.geonrm;
         org = safeOffsetRay(hit.pos, offsetDir);
-        if(sd.event_type & BSDF_EVENT_TRANSMISSION)
+        if((FEAT & (FEAT_TRANSMISSION | FEAT_DIFFUSE_TRANSMISSION)) && (sd.event_type & BSDF_EVENT_TRANSMISSION))
         {
           flags ^= PF_INSIDE;
-          if(flags & PF_INSIDE)
+          if((FEAT & FEAT_VOLUME) && (flags & PF_INSIDE))
             med = packMedium(makeVolumeMedium(pbrMat), med.w >> 16);
         }
       }
@@ -816,7 +817,7 @@ __global__ void k_bsdf_eval(const float* __restrict__ in, uint32_t n, float* __r
     return;
   const float*      p = in + (size_t)i * 48;
   const PbrMaterial m = unpackTestMaterial(p);
-  const BsdfEval    d = bsdfEvaluate(m, f3(p[39], p[40], p[41]), f3(p[42], p[43], p[44]), f3(p[45], p[46], p[47]));
+  const BsdfEval    d = bsdfEvaluate<FEAT_ALL>(m, f3(p[39], p[40], p[41]), f3(p[42], p[43], p[44]), f3(p[45], p[46], p[47]));
   float*            q = out + (size_t)i * 8;
   q[0] = d.bsdf_diffuse.x;
   q[1] = d.bsdf_diffuse.y;
@@ -835,7 +836,7 @@ __global__ void k_bsdf_sample(const float* __restrict__ in, uint32_t n, float* _
     return;
   const float*      p = in + (size_t)i * 48;
   const PbrMaterial m = unpackTestMaterial(p);
-  const BsdfSample  d = bsdfSample(m, f3(p[39], p[40], p[41]), f3(p[45], p[46], p[47]));
+  const BsdfSample  d = bsdfSample<FEAT_ALL>(m, f3(p[39], p[40], p[41]), f3(p[45], p[46], p[47]));
   float*            q = out + (size_t)i * 8;
   q[0] = d.k2.x;
   q[1] = d.k2.y;
@@ -871,6 +872,8 @@ struct b200pt
   DevScene            S{};
   bool                haveScene = false;
   bool                hasVolume = false;
+  bool                leanShade = false;  // scene fits the FEAT_LEAN shade variant (scene_feature_detection analogue)
+  uint32_t            featureMask = 0;
   uint64_t            nodeBytes = 0, triBytes = 0;
   uint32_t            numNodes = 0, numTris = 0;
 
@@ -1189,6 +1192,32 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
     return rc;
   if((rc = upload(h, h->sceneAllocs, s->lights, s->numLights, &dLights)))
     return rc;
+  // which KHR_materials_* features do the scene's materials use (reference: src/scene_feature_detection.cpp)
+  {
+    uint32_t feat = s->numLights ? FEAT_LIGHTS : 0u;
+    for(uint32_t i = 0; i < s->numMaterials; i++)
+    {
+      const b200pt_shade_material& m = s->materials[i];
+      if(m.transmissionFactor > 0.0f || m.transmissionTexture)
+        feat |= FEAT_TRANSMISSION;
+      if(m.thicknessFactor > 0.0f || m.thicknessTexture || m.multiscatterColorFactor[0] > 0.0f || m.multiscatterColorFactor[1] > 0.0f || m.multiscatterColorFactor[2] > 0.0f)
+        feat |= FEAT_VOLUME;
+      if(m.diffuseTransmissionFactor > 0.0f || m.diffuseTransmissionTexture)
+        feat |= FEAT_DIFFUSE_TRANSMISSION;
+      if(m.clearcoatFactor > 0.0f)
+        feat |= FEAT_CLEARCOAT;
+      if(m.sheenColorFactor[0] != 0.0f || m.sheenColorFactor[1] != 0.0f || m.sheenColorFactor[2] != 0.0f)
+        feat |= FEAT_SHEEN;
+      if(m.iridescenceFactor > 0.0f)
+        feat |= FEAT_IRIDESCENCE;
+      if(m.anisotropyStrength > 0.0f)
+        feat |= FEAT_ANISOTROPY;
+      if(m.pbrModel == 1)
+        feat |= FEAT_SPECGLOSS;
+    }
+    h->featureMask = feat;
+    h->leanShade = (feat & ~(uint32_t)FEAT_LEAN) == 0;
+  }
   S.nodes = dNodes;
   S.mats = dMats;
   S.texInfos = dTi;
@@ -1678,7 +1707,12 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
         uint32_t* qT = h->dQ[cur];
         uint32_t* qN = h->dQ[1 - cur];
         timed(tTrace, [&] { k_trace<<<gridFor(h, 8), 128, 1024, st>>>(h->P, h->S, qT, &cntTrace[it], &workTrace[it], h->dStats); });
-        timed(tShade, [&] { k_shade<<<gridFor(h, 8), 128, 1024, st>>>(h->P, h->S, F, qT, &cntTrace[it], h->dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats); });
+        timed(tShade, [&] {
+          if(h->leanShade)
+            k_shade<FEAT_LEAN><<<gridFor(h, 8), 128, 1024, st>>>(h->P, h->S, F, qT, &cntTrace[it], h->dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats);
+          else
+            k_shade<FEAT_ALL><<<gridFor(h, 8), 128, 1024, st>>>(h->P, h->S, F, qT, &cntTrace[it], h->dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats);
+        });
         timed(tPost, [&] { k_post<<<gridFor(h, 8), 128, 1024, st>>>(h->P, h->S, F, h->dQ[2], &cntPost[it], &workPost[it], qN, &cntTrace[it + 1], h->dStats); });
         cur = 1 - cur;
       }

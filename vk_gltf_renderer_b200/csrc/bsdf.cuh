@@ -54,6 +54,26 @@ enum : int
   BSDF_EVENT_GLOSSY_TRANSMISSION = BSDF_EVENT_GLOSSY | BSDF_EVENT_TRANSMISSION,
 };
 
+// Per-scene kernel specialisation, like the reference's GLTF_USE_* shader variants
+// (src/scene_shader_macros.cpp:40-56, shaders/gltf_eval_config.h:47-91): a feature the scene's materials never
+// use is compiled out of the shade kernel.  Disabled features contribute exact zeros / identities, so the
+// lean and the full variant produce bit-identical results on scenes that fit the lean one.
+enum : uint32_t
+{
+  FEAT_TRANSMISSION = 1u << 0,
+  FEAT_VOLUME = 1u << 1,
+  FEAT_DIFFUSE_TRANSMISSION = 1u << 2,
+  FEAT_CLEARCOAT = 1u << 3,
+  FEAT_SHEEN = 1u << 4,
+  FEAT_IRIDESCENCE = 1u << 5,
+  FEAT_ANISOTROPY = 1u << 6,
+  FEAT_SPECGLOSS = 1u << 7,
+  FEAT_LIGHTS = 1u << 8,
+  FEAT_ALL = 0x1ffu,
+  // the variant Sponza / DamagedHelmet / Box class scenes run: metal-rough + specular + clearcoat + emissive + unlit
+  FEAT_LEAN = FEAT_CLEARCOAT,
+};
+
 enum : int
 {
   LOBE_DIFFUSE_REFLECTION = 0,
@@ -188,15 +208,16 @@ PT_D float3 cosineSampleHemisphere(float r1, float r2)
 PT_D float fresnelCosineApprox(float VdotN, float roughness) { return lerpf(VdotN, sqrtf(0.5f + 0.5f * VdotN), sqrtf(roughness)); }
 
 // picks ONE lobe from the layered weights (clearcoat over sheen over metal | dielectric{spec, transmission, diffuse})
+template <uint32_t FEAT>
 PT_D int findLobe(const PbrMaterial& mat, float VdotN, float rndVal)
 {
   float frCoat = 0.0f;
-  if(mat.clearcoat > 0.0f)
+  if((FEAT & FEAT_CLEARCOAT) && mat.clearcoat > 0.0f)
     frCoat = mat.clearcoat * iorFresnel(1.5f / mat.ior1, fresnelCosineApprox(VdotN, mat.clearcoatRoughness));
   float frDielectric = iorFresnel(mat.ior2 / mat.ior1, fresnelCosineApprox(VdotN, (mat.roughness.x + mat.roughness.y) * 0.5f));
   frDielectric *= mat.specular;
   float sheen = 0.0f;
-  if(mat.sheenColor.x != 0.0f || mat.sheenColor.y != 0.0f || mat.sheenColor.z != 0.0f)
+  if((FEAT & FEAT_SHEEN) && (mat.sheenColor.x != 0.0f || mat.sheenColor.y != 0.0f || mat.sheenColor.z != 0.0f))
   {
     sheen = powf(1.0f - fabsf(VdotN), mat.sheenRoughness);
     sheen = sheen / (sheen + 0.5f);
@@ -204,25 +225,39 @@ PT_D int findLobe(const PbrMaterial& mat, float VdotN, float rndVal)
   const float base = (1.0f - frCoat) * (1.0f - sheen);
   const float diel = base * (1.0f - mat.metallic);
   const float diffuse = diel * (1.0f - frDielectric) * (1.0f - mat.transmission);
-  // cumulative scan from the top lobe down (same order as the weights array walk)
-  float weight = diffuse * mat.diffuseTransmissionFactor;  // LOBE_DIFFUSE_TRANSMISSION
-  if(rndVal < weight)
-    return LOBE_DIFFUSE_TRANSMISSION;
-  weight += frCoat;
-  if(rndVal < weight)
-    return LOBE_CLEARCOAT_REFLECTION;
-  weight += (1.0f - frCoat) * sheen;
-  if(rndVal < weight)
-    return LOBE_SHEEN_REFLECTION;
+  // cumulative scan from the top lobe down (same order as the weights array walk); lobes of compiled-out
+  // features have weight exactly 0 and are skipped
+  float weight = 0.0f;
+  if(FEAT & FEAT_DIFFUSE_TRANSMISSION)
+  {
+    weight = diffuse * mat.diffuseTransmissionFactor;  // LOBE_DIFFUSE_TRANSMISSION
+    if(rndVal < weight)
+      return LOBE_DIFFUSE_TRANSMISSION;
+  }
+  if(FEAT & FEAT_CLEARCOAT)
+  {
+    weight += frCoat;
+    if(rndVal < weight)
+      return LOBE_CLEARCOAT_REFLECTION;
+  }
+  if(FEAT & FEAT_SHEEN)
+  {
+    weight += (1.0f - frCoat) * sheen;
+    if(rndVal < weight)
+      return LOBE_SHEEN_REFLECTION;
+  }
   weight += base * mat.metallic;
   if(rndVal < weight)
     return LOBE_METAL_REFLECTION;
   weight += diel * frDielectric;
   if(rndVal < weight)
     return LOBE_SPECULAR_REFLECTION;
-  weight += diel * (1.0f - frDielectric) * mat.transmission;
-  if(rndVal < weight)
-    return LOBE_SPECULAR_TRANSMISSION;
+  if(FEAT & FEAT_TRANSMISSION)
+  {
+    weight += diel * (1.0f - frDielectric) * mat.transmission;
+    if(rndVal < weight)
+      return LOBE_SPECULAR_TRANSMISSION;
+  }
   return LOBE_DIFFUSE_REFLECTION;
 }
 
@@ -281,6 +316,7 @@ struct BsdfSample
   int    event_type;
 };
 
+template <uint32_t FEAT>
 PT_D void ggxReflectEval(BsdfEval& d, const PbrMaterial& mat, const LobeFrame& fr, int lobe, float3 tint, float3 k1, float3 k2)
 {
   if(dot(k2, mat.Ng) <= 0.0f)
@@ -300,11 +336,12 @@ PT_D void ggxReflectEval(BsdfEval& d, const PbrMaterial& mat, const LobeFrame& f
   pdf *= 0.25f / (nk1 * nh);
   const float3 bsdf = f3((G1 * G2) * pdf);
   d.pdf = pdf * G1;
-  if(fr.iridescence > 0.0f)
+  if((FEAT & FEAT_IRIDESCENCE) && fr.iridescence > 0.0f)
     iridescenceTint(mat, lobe, k1h, tint);
   d.bsdf_glossy = bsdf * tint;
 }
 
+template <uint32_t FEAT>
 PT_D void ggxReflectSample(BsdfSample& d, const PbrMaterial& mat, const LobeFrame& fr, int lobe, float3 tint, float3 k1, float3 xi)
 {
   const float nk1 = fabsf(dot(k1, fr.N));
@@ -331,7 +368,7 @@ PT_D void ggxReflectSample(BsdfSample& d, const PbrMaterial& mat, const LobeFram
   d.bsdf_over_pdf = f3(G12 / G1);
   d.pdf = ggxD(f2(1.0f / fr.roughness.x, 1.0f / fr.roughness.y), h0) * G1;
   d.pdf *= 0.25f / (nk1 * h0.z);
-  if(fr.iridescence > 0.0f)
+  if((FEAT & FEAT_IRIDESCENCE) && fr.iridescence > 0.0f)
     iridescenceTint(mat, lobe, kh, tint);
   d.bsdf_over_pdf *= tint;
   d.event_type = BSDF_EVENT_GLOSSY_REFLECTION;
@@ -360,7 +397,8 @@ PT_D void ggxTransmitEval(BsdfEval& d, const PbrMaterial& mat, float3 tint, floa
   h = normalize(h);
   const float nh = dot(mat.N, h);
   const float k1h = dot(k1, h);
-  const float k2h = dot(k2, h) * (backside ? -1.0f : 1.0f);
+  // thin-walled pseudo-BTDF: the half vector pairs k1 with the MIRRORED k2, so that direction's cosine is checked
+  const float k2h = (backside && thin) ? dot(k2 + mat.N * (nk2 + nk2), h) : dot(k2, h) * (backside ? -1.0f : 1.0f);
   if(nk1 <= 0.0f || nh <= 0.0f || k1h < 0.0f || k2h < 0.0f)
     return;
   if(!backside)
@@ -512,13 +550,14 @@ PT_D void sheenSample(BsdfSample& d, const PbrMaterial& mat, float3 k1, float3 x
   d.event_type = BSDF_EVENT_GLOSSY_REFLECTION;
 }
 
+template <uint32_t FEAT>
 __device__ __noinline__ BsdfEval bsdfEvaluate(const PbrMaterial& mat, float3 k1, float3 k2, float3 xi)
 {
   BsdfEval d;
   d.bsdf_diffuse = f3(0.0f);
   d.bsdf_glossy = f3(0.0f);
   d.pdf = 0.0f;
-  const int lobe = findLobe(mat, dot(k1, mat.N), xi.z);
+  const int lobe = findLobe<FEAT>(mat, dot(k1, mat.N), xi.z);
   if(lobe == LOBE_DIFFUSE_REFLECTION)
   {
     if(dot(k2, mat.Ng) > 0.0f)
@@ -527,7 +566,7 @@ __device__ __noinline__ BsdfEval bsdfEvaluate(const PbrMaterial& mat, float3 k1,
       d.bsdf_diffuse = mat.baseColor * d.pdf;
     }
   }
-  else if(lobe == LOBE_DIFFUSE_TRANSMISSION)
+  else if((FEAT & FEAT_DIFFUSE_TRANSMISSION) && lobe == LOBE_DIFFUSE_TRANSMISSION)
   {
     if(dot(k2, mat.Ng) < 0.0f)
     {
@@ -535,19 +574,20 @@ __device__ __noinline__ BsdfEval bsdfEvaluate(const PbrMaterial& mat, float3 k1,
       d.bsdf_diffuse = mat.diffuseTransmissionColor * d.pdf;
     }
   }
-  else if(lobe == LOBE_SPECULAR_TRANSMISSION)
+  else if((FEAT & FEAT_TRANSMISSION) && lobe == LOBE_SPECULAR_TRANSMISSION)
     ggxTransmitEval(d, mat, mat.baseColor, k1, k2);
-  else if(lobe == LOBE_SHEEN_REFLECTION)
+  else if((FEAT & FEAT_SHEEN) && lobe == LOBE_SHEEN_REFLECTION)
     sheenEval(d, mat, k1, k2);
   else
   {
     const LobeFrame fr = lobeFrame(mat, lobe);
     const float3    tint = (lobe == LOBE_SPECULAR_REFLECTION) ? mat.specularColor : ((lobe == LOBE_METAL_REFLECTION) ? mat.baseColor : f3(1.0f));
-    ggxReflectEval(d, mat, fr, lobe, tint, k1, k2);
+    ggxReflectEval<FEAT>(d, mat, fr, lobe, tint, k1, k2);
   }
   return d;
 }
 
+template <uint32_t FEAT>
 __device__ __noinline__ BsdfSample bsdfSample(const PbrMaterial& mat, float3 k1, float3 xi)
 {
   BsdfSample d;
@@ -555,7 +595,7 @@ __device__ __noinline__ BsdfSample bsdfSample(const PbrMaterial& mat, float3 k1,
   d.bsdf_over_pdf = f3(0.0f);
   d.pdf = 0.0f;
   d.event_type = BSDF_EVENT_ABSORB;
-  const int lobe = findLobe(mat, dot(k1, mat.N), xi.z);
+  const int lobe = findLobe<FEAT>(mat, dot(k1, mat.N), xi.z);
   if(lobe == LOBE_DIFFUSE_REFLECTION || lobe == LOBE_DIFFUSE_TRANSMISSION)
   {
     const float  s = (lobe == LOBE_DIFFUSE_REFLECTION) ? 1.0f : -1.0f;
@@ -568,15 +608,15 @@ __device__ __noinline__ BsdfSample bsdfSample(const PbrMaterial& mat, float3 k1,
     else
       d.event_type = (dot(d.k2, mat.Ng) < 0.0f) ? BSDF_EVENT_DIFFUSE_TRANSMISSION : BSDF_EVENT_ABSORB;
   }
-  else if(lobe == LOBE_SPECULAR_TRANSMISSION)
+  else if((FEAT & FEAT_TRANSMISSION) && lobe == LOBE_SPECULAR_TRANSMISSION)
     ggxTransmitSample(d, mat, mat.baseColor, k1, xi);
-  else if(lobe == LOBE_SHEEN_REFLECTION)
+  else if((FEAT & FEAT_SHEEN) && lobe == LOBE_SHEEN_REFLECTION)
     sheenSample(d, mat, k1, xi);
   else
   {
     const LobeFrame fr = lobeFrame(mat, lobe);
     const float3    tint = (lobe == LOBE_SPECULAR_REFLECTION) ? mat.specularColor : ((lobe == LOBE_METAL_REFLECTION) ? mat.baseColor : f3(1.0f));
-    ggxReflectSample(d, mat, fr, lobe, tint, k1, xi);
+    ggxReflectSample<FEAT>(d, mat, fr, lobe, tint, k1, xi);
   }
   if(d.pdf <= 0.00001f || isnan(d.bsdf_over_pdf.x) || isnan(d.bsdf_over_pdf.y) || isnan(d.bsdf_over_pdf.z))
     d.event_type = BSDF_EVENT_ABSORB;

@@ -221,7 +221,7 @@ __device__ __noinline__ float4 sampleTexture(const DevTex& T, float2 uv, float2 
   return a * (1.0f - f) + b * f;
 }
 
-PT_D float4 getTexture(const DevScene& S, uint16_t slot, float2 tc0, float2 tc1, float texGrad)
+__device__ __noinline__ float4 getTexture(const DevScene& S, uint16_t slot, float2 tc0, float2 tc1, float texGrad)
 {
   const b200pt_texture_info ti = S.texInfos[slot];
   float2                    tt = ti.texCoord ? tc1 : tc0;
@@ -251,11 +251,12 @@ PT_D float3 multiToSingleScatterAlbedo(float3 rho)
   return f3(1.0f) - t * t;
 }
 
+template <uint32_t FEAT>
 PT_D PbrMaterial evaluateMaterial(const DevScene& S, const b200pt_shade_material& material, const HitState& hit, bool isInside, float texGrad)
 {
   PbrMaterial pbrMat;
 #define PT_TEX(slot) getTexture(S, material.slot, hit.uv0, hit.uv1, texGrad)
-  if(material.pbrModel == 1)
+  if((FEAT & FEAT_SPECGLOSS) && material.pbrModel == 1)
   {
     // KHR_materials_pbrSpecularGlossiness -> metallic-roughness (gltf_material_eval.h.slang:136-161,176-197)
     float4 diffuse = f4(material.pbrDiffuseFactor[0], material.pbrDiffuseFactor[1], material.pbrDiffuseFactor[2], material.pbrDiffuseFactor[3]) * hit.color;
@@ -326,7 +327,7 @@ PT_D PbrMaterial evaluateMaterial(const DevScene& S, const b200pt_shade_material
   pbrMat.attenuationColor = f3(material.attenuationColor[0], material.attenuationColor[1], material.attenuationColor[2]);
   pbrMat.attenuationDistance = material.attenuationDistance;
   pbrMat.thickness = material.thicknessFactor;
-  if(material.thicknessTexture > 0)
+  if((FEAT & FEAT_VOLUME) && material.thicknessTexture > 0)
     pbrMat.thickness *= PT_TEX(thicknessTexture).y;
 
   pbrMat.specularColor = f3(material.specularColorFactor[0], material.specularColorFactor[1], material.specularColorFactor[2]);
@@ -346,11 +347,11 @@ PT_D PbrMaterial evaluateMaterial(const DevScene& S, const b200pt_shade_material
   pbrMat.ior2 = ior2;
 
   pbrMat.transmission = material.transmissionFactor;
-  if(material.transmissionTexture > 0)
+  if((FEAT & FEAT_TRANSMISSION) && material.transmissionTexture > 0)
     pbrMat.transmission *= PT_TEX(transmissionTexture).x;
 
   pbrMat.scatterCoefficient = f3(0.0f);
-  if(material.multiscatterColorFactor[0] > 0.0f || material.multiscatterColorFactor[1] > 0.0f || material.multiscatterColorFactor[2] > 0.0f)
+  if((FEAT & FEAT_VOLUME) && (material.multiscatterColorFactor[0] > 0.0f || material.multiscatterColorFactor[1] > 0.0f || material.multiscatterColorFactor[2] > 0.0f))
   {
     const float3 ssa = multiToSingleScatterAlbedo(f3(material.multiscatterColorFactor[0], material.multiscatterColorFactor[1], material.multiscatterColorFactor[2]));
     const float3 att = -logv(vmax(pbrMat.attenuationColor, f3(0.001f))) / fmaxf(pbrMat.attenuationDistance, 0.001f);
@@ -361,11 +362,11 @@ PT_D PbrMaterial evaluateMaterial(const DevScene& S, const b200pt_shade_material
   pbrMat.clearcoat = material.clearcoatFactor;
   pbrMat.clearcoatRoughness = material.clearcoatRoughness;
   pbrMat.Nc = pbrMat.N;
-  if(material.clearcoatTexture > 0)
+  if((FEAT & FEAT_CLEARCOAT) && material.clearcoatTexture > 0)
     pbrMat.clearcoat *= PT_TEX(clearcoatTexture).x;
-  if(material.clearcoatRoughnessTexture > 0)
+  if((FEAT & FEAT_CLEARCOAT) && material.clearcoatRoughnessTexture > 0)
     pbrMat.clearcoatRoughness *= PT_TEX(clearcoatRoughnessTexture).y;
-  if(material.clearcoatNormalTexture > 0)
+  if((FEAT & FEAT_CLEARCOAT) && material.clearcoatNormalTexture > 0)
   {
     float3 nv = xyz(PT_TEX(clearcoatNormalTexture));
     nv = nv * 2.0f - f3(1.0f);
@@ -376,9 +377,9 @@ PT_D PbrMaterial evaluateMaterial(const DevScene& S, const b200pt_shade_material
   float iridescence = material.iridescenceFactor;
   float iridescenceThickness = material.iridescenceThicknessMaximum;
   pbrMat.iridescenceIor = material.iridescenceIor;
-  if(material.iridescenceTexture > 0)
+  if((FEAT & FEAT_IRIDESCENCE) && material.iridescenceTexture > 0)
     iridescence *= PT_TEX(iridescenceTexture).x;
-  if(material.iridescenceThicknessTexture > 0)
+  if((FEAT & FEAT_IRIDESCENCE) && material.iridescenceThicknessTexture > 0)
   {
     const float t = PT_TEX(iridescenceThicknessTexture).y;
     iridescenceThickness = lerpf(material.iridescenceThicknessMinimum, material.iridescenceThicknessMaximum, t);
@@ -387,7 +388,7 @@ PT_D PbrMaterial evaluateMaterial(const DevScene& S, const b200pt_shade_material
   pbrMat.iridescenceThickness = iridescenceThickness;
 
   float anisotropyStrength = material.anisotropyStrength;
-  if(anisotropyStrength > 0.0f)
+  if((FEAT & FEAT_ANISOTROPY) && anisotropyStrength > 0.0f)
   {
     float2 dir = f2(1.0f, 0.0f);
     if(material.anisotropyTexture > 0)
@@ -412,18 +413,18 @@ PT_D PbrMaterial evaluateMaterial(const DevScene& S, const b200pt_shade_material
   }
 
   pbrMat.sheenColor = f3(material.sheenColorFactor[0], material.sheenColorFactor[1], material.sheenColorFactor[2]);
-  if(material.sheenColorTexture > 0)
+  if((FEAT & FEAT_SHEEN) && material.sheenColorTexture > 0)
     pbrMat.sheenColor *= xyz(PT_TEX(sheenColorTexture));
   pbrMat.sheenRoughness = material.sheenRoughnessFactor;
-  if(material.sheenRoughnessTexture > 0)
+  if((FEAT & FEAT_SHEEN) && material.sheenRoughnessTexture > 0)
     pbrMat.sheenRoughness *= PT_TEX(sheenRoughnessTexture).w;
   pbrMat.sheenRoughness = fmaxf(PT_MICROFACET_MIN_ROUGHNESS, pbrMat.sheenRoughness);
 
   pbrMat.diffuseTransmissionFactor = material.diffuseTransmissionFactor;
-  if(material.diffuseTransmissionTexture > 0)
+  if((FEAT & FEAT_DIFFUSE_TRANSMISSION) && material.diffuseTransmissionTexture > 0)
     pbrMat.diffuseTransmissionFactor *= PT_TEX(diffuseTransmissionTexture).w;
   pbrMat.diffuseTransmissionColor = f3(material.diffuseTransmissionColor[0], material.diffuseTransmissionColor[1], material.diffuseTransmissionColor[2]);
-  if(material.diffuseTransmissionColorTexture > 0)
+  if((FEAT & FEAT_DIFFUSE_TRANSMISSION) && material.diffuseTransmissionColorTexture > 0)
     pbrMat.diffuseTransmissionColor *= xyz(PT_TEX(diffuseTransmissionColorTexture));
 #undef PT_TEX
   return pbrMat;
@@ -733,6 +734,7 @@ PT_D void techniqueProbabilities(const DevScene& S, const FrameParams& F, float&
   }
 }
 
+template <uint32_t FEAT>
 PT_D DirectLight sampleLights(const DevScene& S, const FrameParams& F, float3 pos, uint32_t& seed)
 {
   DirectLight dl;
@@ -747,7 +749,7 @@ PT_D DirectLight sampleLights(const DevScene& S, const FrameParams& F, float3 po
   if(lightWeight == 0.0f && envWeight == 0.0f)
     return dl;
   const bool sampleLight = (rnd(seed) < lightWeight);
-  if(sampleLight)
+  if((FEAT & FEAT_LIGHTS) && sampleLight)
   {
     const float         selectionPdf = 1.0f / (float)S.numLights;
     const int           lightIndex = min((int)(rnd(seed) * (float)S.numLights), S.numLights - 1);
