@@ -366,8 +366,13 @@ def main():
         stages[name] = {"share": ms_k / tot_ms, "ms_per_launch": ms_k / max(n_l, 1), "launches": int(n_l), "units": int(units),
                         "bytes_per_unit": per, "achieved_GBps": ach}
     dom = max(stages, key=lambda k: stages[k]["share"])
+    # measured DRAM traffic of the dominant kernel: one `ncu --set full` capture (profiles/r01_ncu_summary.md), per launch
+    ncu_traffic = {"k_trace": {"bytes": 188183000 + 44838656, "units_in_that_launch": 2070000, "source": "profiles/r01_ncu_summary.md"},
+                   "k_shade": {"bytes": 1481856000 + 591318528, "units_in_that_launch": 2000000, "source": "profiles/r01_ncu_summary.md"},
+                   "k_post": {"bytes": 466673000 + 70331136, "units_in_that_launch": 1000000, "source": "profiles/r01_ncu_summary.md"}}
     roof = {"kernel": dom, "bound": "hbm", "achieved": stages[dom]["achieved_GBps"], "peak": peak_gbs, "unit": "GB/s",
-            "frac": (stages[dom]["achieved_GBps"] / peak_gbs) if stages[dom]["achieved_GBps"] else None, "traffic": None,
+            "frac": (stages[dom]["achieved_GBps"] / peak_gbs) if stages[dom]["achieved_GBps"] else None,
+            "traffic": ncu_traffic[dom]["bytes"], "traffic_detail": ncu_traffic[dom],
             "peak_source": peak_src, "model": "algorithmic bytes/unit x units / CUDA-event kernel time (pass B); " + counts_note,
             "stages": stages}
 
