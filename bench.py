@@ -180,7 +180,7 @@ def cpu_baseline(args, scn, env, oracle=None, frame=0):
                     "spp_per_s_full_frame": (rows / args.height) / dt}, dt, rays
 
 
-def run_reference(args):
+def run_reference(args, emit):
     """--impl reference: the reference's own algorithm on the host cores (oracle port: the Vulkan-RT
     reference cannot be built or run here — DESIGN.md §Oracle)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -203,7 +203,7 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, scn, 1),
             "cpu_baseline": cb, "e2e": {"value": val, "unit": "Mray/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "note": "each step = the sample band of one 1080p frame on the host cores; Mray/s is size-independent"}
-    print(json.dumps(line))
+    emit(line)
 
 
 def traversal_counts(args, scn, env, device):
@@ -223,8 +223,16 @@ def traversal_counts(args, scn, env, device):
 
 def main():
     args = parse()
+    # the contract is ONE JSON line on stdout: libraries (NCCL banner, torch warnings) that print to fd 1 are sent to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, emit)
         return
     import torch
     import torch.distributed as dist
@@ -387,7 +395,7 @@ def main():
             "clocks": cl, "e2e": {"value": e2e_val, "unit": "Mray/s", "h2d_bytes_per_step": 396 + 48, "d2h_bytes_per_step": rows * W * 16 * world,
                                   "ms_per_step": 1e3 * float(dt.item()) / args.steps},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -35,7 +35,7 @@ _libs = {}
 def lib(count_traversal=False):
     """count_traversal=True loads the variant compiled with -DB200PT_COUNT_TRAVERSAL (per-ray node /
     triangle counters for the roofline model; never used for timing)."""
-    path = COUNT_LIB_PATH if count_traversal else LIB_PATH
+    path = COUNT_LIB_PATH if count_traversal else os.environ.get("B200PT_LIB", LIB_PATH)  # B200PT_LIB: tuning builds
     if path in _libs:
         return _libs[path]
     if not os.path.exists(path):

@@ -14,6 +14,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(256) k_raygen(PathState P, const __grid_consta
 // Persistent-warp scheme (Aila & Laine 2009 style): all 32 lanes of a warp reconverge at the fetch point
 // (__syncwarp), lanes that finished their ray take the next queue entries from a global cursor, then the
 // warp walks the tree until fewer than kRefillThreshold lanes are still busy and goes back to refill.
-constexpr int kRefillThreshold = 22;
+constexpr int kRefillThresholdDefault = 22;
 
 // full-warp fetch: every lane calls it; lanes with need==true receive the next queue slot or 0xFFFFFFFF
 __device__ __forceinline__ uint32_t fetchWork(bool need, uint32_t* workCounter, uint32_t count)
@@ -175,7 +176,7 @@ __device__ __forceinline__ uint32_t fetchWork(bool need, uint32_t* workCounter, 
 // the CONVERGED part of the loop (phase changes, stochastic alpha test, result write), never inside the
 // traversal loop, so the hot loop contains nothing but node / triangle steps.
 __global__ void __launch_bounds__(128) k_trace(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn,
-                                               uint32_t* workCounter, DevStats* stats)
+                                               uint32_t* workCounter, DevStats* stats, int refillThreshold, int postponeShift)
 {
   stageSrgbLut(S.lutSrgb);
   const uint32_t count = *cntIn;
@@ -272,8 +273,8 @@ __global__ void __launch_bounds__(128) k_trace(PathState P, DevScene S, const ui
     for(;;)
     {
       if(path >= 0 && !travDone)
-        travDone = T.step(stack);
-      if(__popc(__ballot_sync(0xffffffffu, path >= 0 && !travDone)) < kRefillThreshold)
+        travDone = T.step(stack, postponeShift);
+      if(__popc(__ballot_sync(0xffffffffu, path >= 0 && !travDone)) < refillThreshold)
         break;
     }
   }
@@ -281,8 +282,11 @@ __global__ void __launch_bounds__(128) k_trace(PathState P, DevScene S, const ui
     atomicAdd(&stats->closestRays, (unsigned long long)count);
 }
 
+#ifndef SHADE_MIN_BLOCKS
+#define SHADE_MIN_BLOCKS 4  // measured on B200: 3 -> 1.165 ms, 4 -> 1.017, 5 -> 1.029, 6 -> 1.064 per launch
+#endif
 template <uint32_t FEAT>
-__global__ void __launch_bounds__(128) k_shade(PathState P, DevScene S, const __grid_constant__ FrameParams F, const uint32_t* __restrict__ q,
+__global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(PathState P, DevScene S, const __grid_constant__ FrameParams F, const uint32_t* __restrict__ q,
                                                const uint32_t* __restrict__ cntIn, uint32_t* qPost, uint32_t* cntPost, uint32_t* qNext, uint32_t* cntNext, DevStats* stats)
 {
   stageSrgbLut(S.lutSrgb);
@@ -577,7 +581,8 @@ __device__ void finishPost(const PathState& P, const FrameParams& F, uint32_t i,
 }
 
 __global__ void __launch_bounds__(128) k_post(PathState P, DevScene S, const __grid_constant__ FrameParams F, const uint32_t* __restrict__ q,
-                                              const uint32_t* __restrict__ cntIn, uint32_t* workCounter, uint32_t* qNext, uint32_t* cntNext, DevStats* stats)
+                                              const uint32_t* __restrict__ cntIn, uint32_t* workCounter, uint32_t* qNext, uint32_t* cntNext, DevStats* stats,
+                                              int refillThreshold, int postponeShift)
 {
   stageSrgbLut(S.lutSrgb);
   const uint32_t count = *cntIn;
@@ -697,8 +702,8 @@ __global__ void __launch_bounds__(128) k_post(PathState P, DevScene S, const __g
     for(;;)
     {
       if(path >= 0 && !travDone)
-        travDone = T.step(stack);
-      if(__popc(__ballot_sync(0xffffffffu, path >= 0 && !travDone)) < kRefillThreshold)
+        travDone = T.step(stack, postponeShift);
+      if(__popc(__ballot_sync(0xffffffffu, path >= 0 && !travDone)) < refillThreshold)
         break;
     }
   }
@@ -872,6 +877,7 @@ struct b200pt
   DevScene            S{};
   bool                haveScene = false;
   bool                hasVolume = false;
+  int                 refillThreshold = kRefillThresholdDefault, postponeShift = 2;  // B200PT_REFILL / B200PT_POSTPONE env overrides (tuning)
   bool                leanShade = false;  // scene fits the FEAT_LEAN shade variant (scene_feature_detection analogue)
   uint32_t            featureMask = 0;
   uint64_t            nodeBytes = 0, triBytes = 0;
@@ -1111,6 +1117,10 @@ int b200pt_create(b200pt_t** out, int cuda_device)
     delete h;
     return B200PT_E_CUDA;
   }
+  if(const char* e = getenv("B200PT_REFILL"))
+    h->refillThreshold = atoi(e);
+  if(const char* e = getenv("B200PT_POSTPONE"))
+    h->postponeShift = atoi(e);
   cudaDeviceProp prop{};
   cudaGetDeviceProperties(&prop, cuda_device);
   h->numSMs = prop.multiProcessorCount;
@@ -1706,14 +1716,14 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
       {
         uint32_t* qT = h->dQ[cur];
         uint32_t* qN = h->dQ[1 - cur];
-        timed(tTrace, [&] { k_trace<<<gridFor(h, 8), 128, 1024, st>>>(h->P, h->S, qT, &cntTrace[it], &workTrace[it], h->dStats); });
+        timed(tTrace, [&] { k_trace<<<gridFor(h, 8), 128, 1024, st>>>(h->P, h->S, qT, &cntTrace[it], &workTrace[it], h->dStats, h->refillThreshold, h->postponeShift); });
         timed(tShade, [&] {
           if(h->leanShade)
             k_shade<FEAT_LEAN><<<gridFor(h, 8), 128, 1024, st>>>(h->P, h->S, F, qT, &cntTrace[it], h->dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats);
           else
             k_shade<FEAT_ALL><<<gridFor(h, 8), 128, 1024, st>>>(h->P, h->S, F, qT, &cntTrace[it], h->dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats);
         });
-        timed(tPost, [&] { k_post<<<gridFor(h, 8), 128, 1024, st>>>(h->P, h->S, F, h->dQ[2], &cntPost[it], &workPost[it], qN, &cntTrace[it + 1], h->dStats); });
+        timed(tPost, [&] { k_post<<<gridFor(h, 8), 128, 1024, st>>>(h->P, h->S, F, h->dQ[2], &cntPost[it], &workPost[it], qN, &cntTrace[it + 1], h->dStats, h->refillThreshold, h->postponeShift); });
         cur = 1 - cur;
       }
       if(!mayOverrun)

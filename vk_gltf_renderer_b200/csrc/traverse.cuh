@@ -96,7 +96,7 @@ struct TravState
   // triangles test ONE triangle each — but only when enough lanes of the warp have one (vote); otherwise the
   // group is postponed onto the stack and node traversal continues (Ylitie et al. 2017, section 4.3).
   // Returns true when the traversal is complete.  `stack` is per-thread scratch of kStackSize entries.
-  PT_D bool step(uint2* __restrict__ stack)
+  PT_D bool step(uint2* __restrict__ stack, int postponeShift = 2)
   {
     // single exit: an early return inside the divergent regions would move their reconvergence point out of the
     // caller's loop and the lanes of a warp would drift apart (measured: 8 of 32 lanes active)
@@ -197,7 +197,7 @@ struct TravState
     {
       // postpone when few lanes would take part and this lane's current node group still has children to open
       // (the group goes under the next node; `cur` only ever holds node groups)
-      if(__popc(haveTri) * 4 < __popc(conv) && (cur.y & 0xff000000u) != 0 && sp < kStackSize)
+      if((__popc(haveTri) << postponeShift) < __popc(conv) && (cur.y & 0xff000000u) != 0 && sp < kStackSize)
       {
         stack[sp++] = tri;
         tri.y = 0;
