@@ -93,7 +93,7 @@ def workload_config(args, scn, n_gpus):
     return {"workload": "SynthSponza(seed=1234) stand-in for Sponza, %dx%d, depth %d, 1 spp/frame, std_env.hdr, NEE+MIS"
                         % (args.width, args.height, args.depth),
             "triangles": scn.num_triangles(), "materials": len(scn.materials), "textures": len(scn.textures),
-            "texture_size": args.tex, "partition": "1 GPU" if n_gpus == 1 else "row strips x%d + NCCL all-gather/frame" % n_gpus,
+            "texture_size": args.tex, "partition": "1 GPU" if n_gpus == 1 else "interleaved row bands x%d, scene replicated, one NCCL all-gather of the RGBA32F tiles per frame" % n_gpus,
             "l2_policy": "working set (path state 11x16 B x 2.07M paths = 365 MB + 33 MB image) exceeds the 126 MB L2 every frame"}
 
 
@@ -249,9 +249,17 @@ def main():
     scn, env = build_workload(args)
     W, H = args.width, args.height
     from vk_gltf_renderer_b200 import tiling
-    rows_per = tiling.strip_rows(H, world)
-    y0, rows = tiling.partition_rows(H, world, rank)
-    res = Resources(scene=scn, hdr_rgb=env, camera=scn.camera, size=(W, H), tile=(y0, rows))
+    band = tiling.interleave_band(H, world)
+    if band:
+        # interleaved bands of `band` rows: every rank gets a fair mix of cheap (sky) and expensive (atrium) rows
+        rows_per = rows = H // world
+        y0 = 0
+        tile_spec = ("interleave", band, world, rank)
+    else:
+        rows_per = tiling.strip_rows(H, world)
+        y0, rows = tiling.partition_rows(H, world, rank)
+        tile_spec = (y0, rows)
+    res = Resources(scene=scn, hdr_rgb=env, camera=scn.camera, size=(W, H), tile=tile_spec)
     pt = PathTracer(local)
     pt.ptMaxDepth = args.depth
     pt.onAttach(res)
@@ -262,6 +270,7 @@ def main():
     pinned = torch.empty((rows, W, 4), dtype=torch.float32).pin_memory()
 
     frame = [-1]
+    image = [None]
 
     def step(gather=True):
         frame[0] += 1
@@ -270,6 +279,8 @@ def main():
         if world > 1 and gather:
             with torch.cuda.stream(stream):
                 dist.all_gather_into_tensor(full, tile)
+                if band:
+                    image[0] = tiling.deinterleave(full, H, world, band)  # rank-major bands -> image order (device copy)
 
     def barrier():
         torch.cuda.synchronize()

@@ -297,6 +297,12 @@ int b200pt_set_environment(b200pt_t* h, const float* rgb, int width, int height,
  * reference is single-GPU: pass 0,height).  Seeds always use global pixel coordinates. */
 int b200pt_resize(b200pt_t* h, int width, int height, int tile_y0, int tile_rows);
 
+/* Same as b200pt_resize, but the handle's tile is every `world`-th band of `band_rows` rows: global row
+ * y belongs to rank (y / band_rows) % world, local row l maps to y = ((l / band_rows) * world + rank) * band_rows
+ * + l % band_rows.  Interleaving balances expensive and cheap image regions across GPUs.
+ * height must be a multiple of band_rows * world.  Seeds still use global pixel coordinates. */
+int b200pt_resize_interleaved(b200pt_t* h, int width, int height, int band_rows, int world, int rank);
+
 /* BaseRenderer::onRender (reference src/renderer_pathtracer.cpp:500-614): one frame =
  * pc->numSamples paths per pixel accumulated into the RGBA32F image exactly like
  * processPixel (shaders/gltf_pathtrace.slang:546-630).  Asynchronous on the handle's stream. */

@@ -174,6 +174,18 @@ def test_multisample_frames_and_tiling(box_scene, std_env, oracle_mod):
     pt2, tile = render_headless(res, 3, ptMaxDepth=5, ptSamples=4)
     assert tile.shape == (24, 96, 4)
     assert np.array_equal(tile, img[16:40])
+    # interleaved bands (multi-GPU load balancing): rank r of 2 owns every other band of 4 rows
+    from vk_gltf_renderer_b200 import tiling
+    parts = []
+    for r in range(2):
+        res = Resources(scene=box_scene, hdr_rgb=std_env, camera=box_scene.camera, size=(96, 64), tile=("interleave", 4, 2, r))
+        _, t = render_headless(res, 3, ptMaxDepth=5, ptSamples=4)
+        assert np.array_equal(t, img[tiling.interleaved_rows(64, 2, r, 4)])
+        parts.append(t)
+    assert np.array_equal(tiling.deinterleave(np.concatenate(parts), 64, 2, 4), img)
+    res = Resources(scene=box_scene, hdr_rgb=std_env, camera=box_scene.camera, size=(96, 64), tile=("interleave", 5, 2, 0))
+    with pytest.raises(Exception):
+        render_headless(res, 1)
 
 
 def test_unsupported_paths_fail_loudly(box_scene, std_env):

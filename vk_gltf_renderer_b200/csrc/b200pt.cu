@@ -66,7 +66,7 @@ __device__ __forceinline__ void statAdd(unsigned long long* p, unsigned long lon
 __device__ void startSample(const PathState& P, const FrameParams& F, uint32_t i, uint32_t seed, float2 jitter, uint32_t sampleIdx)
 {
   const uint32_t x = i % (uint32_t)F.width;
-  const uint32_t y = (uint32_t)F.tileY0 + i / (uint32_t)F.width;
+  const uint32_t y = pixelRow(F, i);
   const Mat4&    projI = *reinterpret_cast<const Mat4*>(F.fi.projInv);
   const Mat4&    viewI = *reinterpret_cast<const Mat4*>(F.fi.viewInv);
   const bool     ortho = (F.fi.flags & B200PT_SCENE_IS_ORTHOGRAPHIC) != 0;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) k_raygen(PathState P, const __grid_consta
   for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < F.numPaths; i += stride)
   {
     const uint32_t x = i % (uint32_t)F.width;
-    const uint32_t y = (uint32_t)F.tileY0 + i / (uint32_t)F.width;
+    const uint32_t y = pixelRow(F, i);
     uint32_t       seed = xxhash32(x, y, (uint32_t)F.pc.frameCount);
     const float    u1 = rnd(seed), u2 = rnd(seed);
     // sampleGaussian (pathtrace_functions.h.slang:784-789), sigma = 0.4246609 px
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(PathState P, De
     const DevPrim             prim = S.prims[node.renderPrimID];
 #ifdef B200PT_DEBUG
     // reference analogue: doDebug at pushConst.mouseCoord (gltf_pathtrace.slang:553-557)
-    const bool dbgPixel = ((float)(i % (uint32_t)F.width) == F.pc.mouseCoord[0] && (float)(F.tileY0 + i / (uint32_t)F.width) == F.pc.mouseCoord[1]);
+    const bool dbgPixel = ((float)(i % (uint32_t)F.width) == F.pc.mouseCoord[0] && (float)pixelRow(F, i) == F.pc.mouseCoord[1]);
     if(dbgPixel)
       printf("DBG hit t=%.9g rnode=%d prim=%d bary=%.9g %.9g org=%.9g %.9g %.9g dir=%.9g %.9g %.9g seed=%u depth=%d\n", hitT, (int)(meta.x & 0x0fffffffu), (int)meta.y, hr.y, hr.z,
              org.x, org.y, org.z, dir.x, dir.y, dir.z, seed, (int)depth);
@@ -652,7 +652,7 @@ __global__ void __launch_bounds__(128) k_post(PathState P, DevScene S, const __g
       if(done)
       {
 #ifdef B200PT_DEBUG
-        if((float)((uint32_t)path % (uint32_t)F.width) == F.pc.mouseCoord[0] && (float)(F.tileY0 + (uint32_t)path / (uint32_t)F.width) == F.pc.mouseCoord[1])
+        if((float)((uint32_t)path % (uint32_t)F.width) == F.pc.mouseCoord[0] && (float)pixelRow(F, (uint32_t)path) == F.pc.mouseCoord[1])
           printf("DBG shadow o=%.9g %.9g %.9g d=%.9g %.9g %.9g tmax=%.9g T=%.9g %.9g %.9g\n", T.org.x, T.org.y, T.org.z, T.dir.x, T.dir.y, T.dir.z, T.tmax, total.x, total.y, total.z);
 #endif
         finishPost(P, F, (uint32_t)path, flags, seed, true, total, qNext, cntNext, stats);
@@ -890,6 +890,7 @@ struct b200pt
 
   // framebuffer + path pool
   int                width = 0, height = 0, tileY0 = 0, tileRows = 0;
+  int                bandRows = 0, bandWorld = 1, bandRank = 0;
   uint32_t           numPaths = 0;
   float4*            dAccumOwned = nullptr;
   float4*            dAccum = nullptr;
@@ -1531,6 +1532,9 @@ int b200pt_resize(b200pt_t* h, int width, int height, int tile_y0, int tile_rows
   h->height = height;
   h->tileY0 = tile_y0;
   h->tileRows = tile_rows;
+  h->bandRows = 0;
+  h->bandWorld = 1;
+  h->bandRank = 0;
   h->numPaths = (uint32_t)((size_t)width * tile_rows);
   const size_t n = h->numPaths;
   auto         alloc16 = [&](void** p) -> int {
@@ -1560,6 +1564,23 @@ int b200pt_resize(b200pt_t* h, int width, int height, int tile_y0, int tile_rows
   }
   CK(cudaMemsetAsync(h->dAccumOwned, 0, n * 16, h->stream));
   h->dAccum = h->dAccumOwned;
+  return B200PT_OK;
+}
+
+int b200pt_resize_interleaved(b200pt_t* h, int width, int height, int band_rows, int world, int rank)
+{
+  if(!h || width <= 0 || height <= 0 || band_rows <= 0 || world <= 0 || rank < 0 || rank >= world || height % (band_rows * world) != 0)
+  {
+    if(h)
+      h->err = "b200pt_resize_interleaved: height must be a multiple of band_rows * world, 0 <= rank < world";
+    return B200PT_E_INVALID;
+  }
+  const int rc = b200pt_resize(h, width, height, 0, height / world);
+  if(rc)
+    return rc;
+  h->bandRows = band_rows;
+  h->bandWorld = world;
+  h->bandRank = rank;
   return B200PT_OK;
 }
 
@@ -1668,6 +1689,9 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
   F.height = h->height;
   F.tileY0 = h->tileY0;
   F.tileRows = h->tileRows;
+  F.bandRows = h->bandRows;
+  F.bandWorld = h->bandWorld;
+  F.bandRank = h->bandRank;
   F.numPaths = h->numPaths;
 
   cudaStream_t st = h->stream;

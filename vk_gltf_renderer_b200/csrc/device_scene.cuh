@@ -62,8 +62,18 @@ struct FrameParams
   b200pt_push_constant pc;
   int                  width, height;
   int                  tileY0, tileRows;
+  int                  bandRows, bandWorld, bandRank;  // interleaved tiles: bandWorld > 1 (then tileY0 == 0)
   uint32_t             numPaths;  // tileRows * width
 };
+
+// global pixel row of path slot i (seeds always use global coordinates)
+PT_D uint32_t pixelRow(const FrameParams& F, uint32_t i)
+{
+  const uint32_t l = i / (uint32_t)F.width;
+  if(F.bandWorld <= 1)
+    return (uint32_t)F.tileY0 + l;
+  return ((l / (uint32_t)F.bandRows) * (uint32_t)F.bandWorld + (uint32_t)F.bandRank) * (uint32_t)F.bandRows + l % (uint32_t)F.bandRows;
+}
 
 // ---- wavefront path state (SoA, one slot per pixel of the tile) --------------------------------
 // 16-byte records so every access is one 128-bit load/store.

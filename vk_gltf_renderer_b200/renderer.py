@@ -41,7 +41,7 @@ class Resources:
     settings: Settings = field(default_factory=Settings)
     size: tuple = (1920, 1080)    # (width, height)
     frameCount: int = -1          # reset to -1, pre-incremented (src/renderer.cpp:1939-1977)
-    tile: tuple = None            # (y0, rows) for framebuffer tiling; None = full image
+    tile: tuple = None            # (y0, rows) strip, or ("interleave", band_rows, world, rank); None = full image
 
 
 class PathTracer:
@@ -115,8 +115,13 @@ class PathTracer:
 
     def onResize(self, cmd, size, resources):
         w, h = size
-        y0, rows = resources.tile if resources.tile else (0, h)
-        self._ck(self._L.b200pt_resize(self._h, w, h, y0, rows), "b200pt_resize")
+        if resources.tile and resources.tile[0] == "interleave":
+            _, band, world, rank = resources.tile
+            self._ck(self._L.b200pt_resize_interleaved(self._h, w, h, band, world, rank), "b200pt_resize_interleaved")
+            y0, rows = 0, h // world
+        else:
+            y0, rows = resources.tile if resources.tile else (0, h)
+            self._ck(self._L.b200pt_resize(self._h, w, h, y0, rows), "b200pt_resize")
         self._size = (w, h)
         self._tile = (y0, rows)
         resources.size = (w, h)

@@ -22,3 +22,30 @@ def partition_rows(height, world, rank):
 def assemble(gathered, height):
     """gathered: array/tensor [world * strip_rows, W, 4] -> [height, W, 4]."""
     return gathered[:height]
+
+
+# ---- interleaved bands: balances cheap (sky) and expensive (atrium floor) rows across ranks -------------------
+def interleave_band(height, world, max_band=8):
+    """largest band height <= max_band such that height is a multiple of band * world; None if there is none."""
+    if world <= 1 or height % world:
+        return None
+    per = height // world
+    for band in range(min(max_band, per), 0, -1):
+        if per % band == 0:
+            return band
+    return None
+
+
+def interleaved_rows(height, world, rank, band):
+    """global row index of every local row of `rank` (length height // world)."""
+    return [((l // band) * world + rank) * band + l % band for l in range(height // world)]
+
+
+def deinterleave(gathered, height, world, band):
+    """gathered: [world * (height // world), W, 4] in rank-major order -> [height, W, 4] in image order."""
+    per = height // world
+    nb = per // band
+    g = gathered.reshape(world, nb, band, *gathered.shape[1:])
+    perm = (1, 0, 2) + tuple(range(3, g.ndim))
+    g = g.permute(*perm) if hasattr(g, "permute") else g.transpose(perm)
+    return g.reshape(height, *gathered.shape[1:])
