@@ -1770,6 +1770,26 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
   }
   timed(tOther, [&] { k_accumulate<<<gridWide, 256, 0, st>>>(h->P, F, h->dAccum); });
   CK(cudaGetLastError());
+  if(h->profiling && getenv("B200PT_DUMP_ITERS"))
+  {
+    // tuning aid: per-iteration queue sizes and kernel times of this frame (stderr)
+    CK(cudaStreamSynchronize(st));
+    const int            n = pc->maxDepth < 64 ? pc->maxDepth : 64;
+    std::vector<uint32_t> c(2 * kMaxIters);
+    CK(cudaMemcpy(c.data(), h->dCounters, sizeof(uint32_t) * 2 * kMaxIters, cudaMemcpyDeviceToHost));
+    const size_t first = h->evUsed >= (size_t)(3 * pc->maxDepth + 2) ? h->evUsed - (size_t)(3 * pc->maxDepth + 2) : 0;
+    for(int it = 0; it < n; it++)
+    {
+      float ms[3] = {0, 0, 0};
+      for(int k = 0; k < 3; k++)
+      {
+        const size_t e = first + 1 + (size_t)it * 3 + k;
+        if(e < h->evUsed)
+          cudaEventElapsedTime(&ms[k], h->evPool[e].a, h->evPool[e].b);
+      }
+      fprintf(stderr, "iter %2d  trace %8u rays %.3f ms | shade %.3f ms | post %8u rays %.3f ms\n", it, c[it], ms[0], ms[1], c[kMaxIters + it], ms[2]);
+    }
+  }
   return B200PT_OK;
 }
 
