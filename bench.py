@@ -267,7 +267,7 @@ def main():
     tile = torch.zeros((rows_per, W, 4), dtype=torch.float32, device="cuda")
     pt.set_accum_device(tile.data_ptr(), rows * W * 4)
     full = torch.empty((world * rows_per, W, 4), dtype=torch.float32, device="cuda") if world > 1 else None
-    pinned = torch.empty((rows, W, 4), dtype=torch.float32).pin_memory()
+    pinned = [torch.empty((rows, W, 4), dtype=torch.float32).pin_memory() for _ in range(3)]
 
     frame = [-1]
     image = [None]
@@ -338,14 +338,28 @@ def main():
     pt.set_profiling(False)
 
     # ---- pass C: end to end through the public API with host buffers ----
-    def step_e2e():
+    # every step: submit the frame (444 B of frame constants go host->device as kernel arguments), then read the
+    # step's image back into pinned host memory.  The read-back is triple-buffered like the reference's staging
+    # ring: the copy of frame f is enqueued behind its accumulate, and the host consumes frame f-2 (waits for its
+    # copy, touches the pixels) while frames f-1 and f render.  The last frames are consumed before the clock stops.
+    checks = []
+
+    def consume(k):
+        pt.wait_read(k % 3)
+        checks.append(float(pinned[k % 3][0, 0, 3]))
+
+    def step_e2e(k):
         step()
-        pt._ck(pt._L.b200pt_read_accum(pt._h, pinned.data_ptr(), pinned.numel()), "b200pt_read_accum")
+        pt.read_accum_async(pinned[k % 3].data_ptr(), pinned[k % 3].numel(), k % 3)
+        if k > 1:
+            consume(k - 2)
     pt.reset_stats()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
+    for k in range(args.steps):
+        step_e2e(k)
+    for k in range(max(args.steps - 2, 0), args.steps):
+        consume(k)
     barrier()
     dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
     if world > 1:

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libb200pt.so")
 # every symbol include/b200pt.h declares
 EXPORTS = [
     "b200pt_create", "b200pt_destroy", "b200pt_abi_version", "b200pt_last_error", "b200pt_set_scene",
-    "b200pt_set_environment", "b200pt_resize", "b200pt_resize_interleaved", "b200pt_render_frame", "b200pt_synchronize",
+    "b200pt_set_environment", "b200pt_resize", "b200pt_resize_interleaved", "b200pt_read_accum_async", "b200pt_wait_read", "b200pt_set_frames_in_flight", "b200pt_render_frame", "b200pt_synchronize",
     "b200pt_get_accum_device", "b200pt_read_accum", "b200pt_set_accum_device", "b200pt_stream",
     "b200pt_get_stats", "b200pt_reset_stats", "b200pt_set_profiling", "b200pt_trace_closest",
     "b200pt_trace_shadow", "b200pt_bvh_info", "b200pt_bsdf_eval", "b200pt_bsdf_sample",
@@ -53,6 +53,9 @@ def lib(count_traversal=False):
     L.b200pt_set_environment.argtypes = [vp, f32p, i32, i32, C.POINTER(C.c_float)]
     L.b200pt_resize.argtypes = [vp, i32, i32, i32, i32]
     L.b200pt_resize_interleaved.argtypes = [vp, i32, i32, i32, i32, i32]
+    L.b200pt_read_accum_async.argtypes = [vp, vp, C.c_size_t, i32]
+    L.b200pt_wait_read.argtypes = [vp, i32]
+    L.b200pt_set_frames_in_flight.argtypes = [vp, i32]
     L.b200pt_render_frame.argtypes = [vp, C.POINTER(abi.FrameInfo), C.POINTER(abi.PushConstant)]
     L.b200pt_synchronize.argtypes = [vp]
     L.b200pt_get_accum_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]

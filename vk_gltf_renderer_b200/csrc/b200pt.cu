@@ -894,10 +894,27 @@ struct b200pt
   uint32_t           numPaths = 0;
   float4*            dAccumOwned = nullptr;
   float4*            dAccum = nullptr;
-  PathState          P{};
+  // Frames in flight (like the reference app's swapchain ring): every lane owns a stream, a path pool, queues and
+  // counters; frame f runs its bounces on lane f % numLanes and only k_accumulate runs on the main stream, in
+  // frame order.  The latency-bound tail of frame f (a few deep paths) overlaps the wide first bounces of f+1.
+  struct Lane
+  {
+    cudaStream_t stream = nullptr;
+    PathState    P{};
+    uint32_t*    dQ[3] = {nullptr, nullptr, nullptr};
+    uint32_t*    dCounters = nullptr;
+    uint32_t*    hCount = nullptr;   // pinned
+    cudaEvent_t  done = nullptr;     // lane stream: all bounces of the lane's frame enqueued before it
+    cudaEvent_t  freed = nullptr;    // main stream: k_accumulate has consumed the lane's pixSum
+    bool         busy = false;       // `freed` has been recorded at least once since the pool was (re)built
+  };
+  static constexpr int kMaxLanes = 4;
+  Lane               lanes[kMaxLanes];
+  int                numLanes = 3;   // measured on B200 (1080p bench): 1 -> 310, 2 -> 366, 3 -> 378 Mray/s; B200PT_FRAMES_IN_FLIGHT / b200pt_set_frames_in_flight
+  uint64_t           frameSerial = 0;
+  int                lastLane = -1;
+  cudaEvent_t        readDone[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<void*> poolAllocs;
-  uint32_t *         dQ[3] = {nullptr, nullptr, nullptr}, *dCounters = nullptr;
-  uint32_t*          hCount = nullptr;  // pinned
   DevStats*          dStats = nullptr;
   float*             dLutSrgb = nullptr;
 
@@ -961,8 +978,19 @@ void freeScene(b200pt* h)
   h->haveScene = false;
 }
 
+void syncAll(b200pt* h)
+{
+  for(int l = 0; l < b200pt::kMaxLanes; l++)
+    if(h->lanes[l].stream)
+      cudaStreamSynchronize(h->lanes[l].stream);
+  cudaStreamSynchronize(h->stream);
+}
+
 void freePool(b200pt* h)
 {
+  for(int l = 0; l < b200pt::kMaxLanes; l++)
+    h->lanes[l].busy = false;
+  h->lastLane = -1;
   for(void* p : h->poolAllocs)
     cudaFree(p);
   h->poolAllocs.clear();
@@ -973,7 +1001,7 @@ void flushEvents(b200pt* h)
 {
   if(h->evUsed == 0)
     return;
-  cudaStreamSynchronize(h->stream);
+  syncAll(h);
   for(size_t i = 0; i < h->evUsed; i++)
   {
     float ms = 0.f;
@@ -1127,8 +1155,17 @@ int b200pt_create(b200pt_t** out, int cuda_device)
   h->numSMs = prop.multiProcessorCount;
   cudaMalloc((void**)&h->dStats, sizeof(DevStats));
   cudaMemset(h->dStats, 0, sizeof(DevStats));
-  cudaMalloc((void**)&h->dCounters, sizeof(uint32_t) * 4 * kMaxIters);
-  cudaMallocHost((void**)&h->hCount, sizeof(uint32_t) * 4);
+  if(const char* e = getenv("B200PT_FRAMES_IN_FLIGHT"))
+    h->numLanes = std::min(std::max(atoi(e), 1), (int)b200pt::kMaxLanes);
+  for(int l = 0; l < b200pt::kMaxLanes; l++)
+  {
+    b200pt::Lane& L = h->lanes[l];
+    cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&L.freed, cudaEventDisableTiming);
+    cudaMalloc((void**)&L.dCounters, sizeof(uint32_t) * 4 * kMaxIters);
+    cudaMallocHost((void**)&L.hCount, sizeof(uint32_t) * 4);
+  }
   {
     float lutS[256];
     for(int i = 0; i < 256; i++)
@@ -1145,17 +1182,27 @@ void b200pt_destroy(b200pt_t* h)
   if(!h)
     return;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  syncAll(h);
   freeScene(h);
   freePool(h);
+  for(int k = 0; k < 4; k++)
+    if(h->readDone[k])
+      cudaEventDestroy(h->readDone[k]);
+  for(int l = 0; l < b200pt::kMaxLanes; l++)
+  {
+    b200pt::Lane& L = h->lanes[l];
+    cudaFree(L.dCounters);
+    cudaFreeHost(L.hCount);
+    cudaEventDestroy(L.done);
+    cudaEventDestroy(L.freed);
+    cudaStreamDestroy(L.stream);
+  }
   if(h->dEnv)
     cudaFree(h->dEnv);
   if(h->dEnvAccel)
     cudaFree(h->dEnvAccel);
   cudaFree(h->dStats);
   cudaFree(h->dLutSrgb);
-  cudaFree(h->dCounters);
-  cudaFreeHost(h->hCount);
   for(auto& e : h->evPool)
   {
     cudaEventDestroy(e.a);
@@ -1178,7 +1225,7 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
     return B200PT_E_INVALID;
   }
   CK(cudaSetDevice(h->device));
-  CK(cudaStreamSynchronize(h->stream));
+  syncAll(h);
   freeScene(h);
   DevScene& S = h->S;
   const int envW0 = S.envW, envH0 = S.envH;
@@ -1438,7 +1485,7 @@ int b200pt_set_environment(b200pt_t* h, const float* rgb, int w, int hh, float* 
   if(!h || !rgb || w <= 0 || hh <= 0)
     return B200PT_E_INVALID;
   CK(cudaSetDevice(h->device));
-  CK(cudaStreamSynchronize(h->stream));
+  syncAll(h);
   const size_t n = (size_t)w * hh;
   // importance = texel solid angle * max(r,g,b); Vose alias table; pdf stored in alpha
   // (nvvk::HdrIbl, external to the reference tree; call site src/renderer.cpp:1994-1996)
@@ -1526,7 +1573,7 @@ int b200pt_resize(b200pt_t* h, int width, int height, int tile_y0, int tile_rows
     return B200PT_E_INVALID;
   }
   CK(cudaSetDevice(h->device));
-  CK(cudaStreamSynchronize(h->stream));
+  syncAll(h);
   freePool(h);
   h->width = width;
   h->height = height;
@@ -1543,26 +1590,33 @@ int b200pt_resize(b200pt_t* h, int width, int height, int tile_y0, int tile_rows
     return 0;
   };
   int rc = 0;
-  rc |= alloc16((void**)&h->P.rayO);
-  rc |= alloc16((void**)&h->P.rayD);
-  rc |= alloc16((void**)&h->P.hit);
-  rc |= alloc16((void**)&h->P.thr);
-  rc |= alloc16((void**)&h->P.rad);
-  rc |= alloc16((void**)&h->P.misc);
-  rc |= alloc16((void**)&h->P.medium);
-  rc |= alloc16((void**)&h->P.pixSum);
-  rc |= alloc16((void**)&h->P.shO);
-  rc |= alloc16((void**)&h->P.shD);
-  rc |= alloc16((void**)&h->P.shC);
+  for(int l = 0; l < h->numLanes; l++)
+  {
+    b200pt::Lane& L = h->lanes[l];
+    rc |= alloc16((void**)&L.P.rayO);
+    rc |= alloc16((void**)&L.P.rayD);
+    rc |= alloc16((void**)&L.P.hit);
+    rc |= alloc16((void**)&L.P.thr);
+    rc |= alloc16((void**)&L.P.rad);
+    rc |= alloc16((void**)&L.P.misc);
+    rc |= alloc16((void**)&L.P.medium);
+    rc |= alloc16((void**)&L.P.pixSum);
+    rc |= alloc16((void**)&L.P.shO);
+    rc |= alloc16((void**)&L.P.shD);
+    rc |= alloc16((void**)&L.P.shC);
+    if(rc)
+      return B200PT_E_NOMEM;
+    for(int k = 0; k < 3; k++)
+    {
+      CK(cudaMalloc((void**)&L.dQ[k], n * sizeof(uint32_t)));
+      h->poolAllocs.push_back(L.dQ[k]);
+    }
+  }
   rc |= alloc16((void**)&h->dAccumOwned);
   if(rc)
     return B200PT_E_NOMEM;
-  for(int k = 0; k < 3; k++)
-  {
-    CK(cudaMalloc((void**)&h->dQ[k], n * sizeof(uint32_t)));
-    h->poolAllocs.push_back(h->dQ[k]);
-  }
   CK(cudaMemsetAsync(h->dAccumOwned, 0, n * 16, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   h->dAccum = h->dAccumOwned;
   return B200PT_OK;
 }
@@ -1623,12 +1677,55 @@ int b200pt_read_accum(b200pt_t* h, float* host, size_t num_floats)
   return B200PT_OK;
 }
 
+int b200pt_read_accum_async(b200pt_t* h, float* host, size_t num_floats, int slot)
+{
+  if(!h || h->numPaths == 0 || !host || num_floats < (size_t)h->numPaths * 4 || slot < 0 || slot >= 4)
+    return B200PT_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  if(!h->readDone[slot])
+    CK(cudaEventCreateWithFlags(&h->readDone[slot], cudaEventDisableTiming));
+  else
+    CK(cudaEventSynchronize(h->readDone[slot]));
+  CK(cudaMemcpyAsync(host, h->dAccum, (size_t)h->numPaths * 16, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaEventRecord(h->readDone[slot], h->stream));
+  return B200PT_OK;
+}
+
+int b200pt_wait_read(b200pt_t* h, int slot)
+{
+  if(!h || slot < 0 || slot >= 4)
+    return B200PT_E_INVALID;
+  if(h->readDone[slot])
+    CK(cudaEventSynchronize(h->readDone[slot]));
+  return B200PT_OK;
+}
+
+int b200pt_set_frames_in_flight(b200pt_t* h, int n)
+{
+  if(!h || n < 1 || n > b200pt::kMaxLanes)
+    return B200PT_E_INVALID;
+  if(n == h->numLanes)
+    return B200PT_OK;
+  h->numLanes = n;
+  if(h->numPaths == 0)
+    return B200PT_OK;
+  float4* const user = (h->dAccum != h->dAccumOwned) ? h->dAccum : nullptr;
+  int           rc;
+  if(h->bandWorld > 1)
+    rc = b200pt_resize_interleaved(h, h->width, h->height, h->bandRows, h->bandWorld, h->bandRank);
+  else
+    rc = b200pt_resize(h, h->width, h->height, h->tileY0, h->tileRows);
+  if(rc == B200PT_OK && user)
+    h->dAccum = user;
+  return rc;
+}
+
 int b200pt_synchronize(b200pt_t* h)
 {
   if(!h)
     return B200PT_E_INVALID;
   CK(cudaSetDevice(h->device));
-  CK(cudaStreamSynchronize(h->stream));
+  syncAll(h);
   return B200PT_OK;
 }
 
@@ -1694,12 +1791,20 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
   F.bandRank = h->bandRank;
   F.numPaths = h->numPaths;
 
-  cudaStream_t st = h->stream;
-  uint32_t*    cntTrace = h->dCounters;             // [kMaxIters]
-  uint32_t*    cntPost = h->dCounters + kMaxIters;  // [kMaxIters]
-  uint32_t*    workTrace = h->dCounters + 2 * kMaxIters;  // dynamic-fetch cursors of the persistent kernels
-  uint32_t*    workPost = h->dCounters + 3 * kMaxIters;
-  CK(cudaMemsetAsync(h->dCounters, 0, sizeof(uint32_t) * 4 * kMaxIters, st));
+  const int     laneIdx = (int)(h->frameSerial++ % (uint64_t)h->numLanes);
+  b200pt::Lane& L = h->lanes[laneIdx];
+  cudaStream_t  st = L.stream;
+  // the lane's pool is free once the accumulate of its previous frame ran; while profiling, frames are serialised
+  // (wait for the previous frame's accumulate) so per-kernel event times are not inflated by overlap
+  if(L.busy)
+    CK(cudaStreamWaitEvent(st, L.freed, 0));
+  if(h->profiling && h->lastLane >= 0 && h->lastLane != laneIdx)
+    CK(cudaStreamWaitEvent(st, h->lanes[h->lastLane].freed, 0));
+  uint32_t*    cntTrace = L.dCounters;             // [kMaxIters]
+  uint32_t*    cntPost = L.dCounters + kMaxIters;  // [kMaxIters]
+  uint32_t*    workTrace = L.dCounters + 2 * kMaxIters;  // dynamic-fetch cursors of the persistent kernels
+  uint32_t*    workPost = L.dCounters + 3 * kMaxIters;
+  CK(cudaMemsetAsync(L.dCounters, 0, sizeof(uint32_t) * 4 * kMaxIters, st));
 
   enum
   {
@@ -1725,7 +1830,7 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
   };
 
   const int gridWide = gridFor(h, 8);
-  timed(tOther, [&] { k_raygen<<<gridWide, 256, 0, st>>>(h->P, F, h->dQ[0], &cntTrace[0], h->dStats); });
+  timed(tOther, [&] { k_raygen<<<gridWide, 256, 0, st>>>(L.P, F, L.dQ[0], &cntTrace[0], h->dStats); });
 
   if(pc->maxDepth > 0)
   {
@@ -1738,23 +1843,23 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
     {
       for(int k = 0; k < remaining && it < kMaxIters - 1; k++, it++)
       {
-        uint32_t* qT = h->dQ[cur];
-        uint32_t* qN = h->dQ[1 - cur];
-        timed(tTrace, [&] { k_trace<<<gridFor(h, 8), 128, 1024, st>>>(h->P, h->S, qT, &cntTrace[it], &workTrace[it], h->dStats, h->refillThreshold, h->postponeShift); });
+        uint32_t* qT = L.dQ[cur];
+        uint32_t* qN = L.dQ[1 - cur];
+        timed(tTrace, [&] { k_trace<<<gridFor(h, 8), 128, 1024, st>>>(L.P, h->S, qT, &cntTrace[it], &workTrace[it], h->dStats, h->refillThreshold, h->postponeShift); });
         timed(tShade, [&] {
           if(h->leanShade)
-            k_shade<FEAT_LEAN><<<gridFor(h, 8), 128, 1024, st>>>(h->P, h->S, F, qT, &cntTrace[it], h->dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats);
+            k_shade<FEAT_LEAN><<<gridFor(h, 8), 128, 1024, st>>>(L.P, h->S, F, qT, &cntTrace[it], L.dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats);
           else
-            k_shade<FEAT_ALL><<<gridFor(h, 8), 128, 1024, st>>>(h->P, h->S, F, qT, &cntTrace[it], h->dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats);
+            k_shade<FEAT_ALL><<<gridFor(h, 8), 128, 1024, st>>>(L.P, h->S, F, qT, &cntTrace[it], L.dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats);
         });
-        timed(tPost, [&] { k_post<<<gridFor(h, 8), 128, 1024, st>>>(h->P, h->S, F, h->dQ[2], &cntPost[it], &workPost[it], qN, &cntTrace[it + 1], h->dStats, h->refillThreshold, h->postponeShift); });
+        timed(tPost, [&] { k_post<<<gridFor(h, 8), 128, 1024, st>>>(L.P, h->S, F, L.dQ[2], &cntPost[it], &workPost[it], qN, &cntTrace[it + 1], h->dStats, h->refillThreshold, h->postponeShift); });
         cur = 1 - cur;
       }
       if(!mayOverrun)
         break;
-      CK(cudaMemcpyAsync(h->hCount, &cntTrace[it], sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(L.hCount, &cntTrace[it], sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
-      if(h->hCount[0] == 0)
+      if(L.hCount[0] == 0)
         break;
       if(it >= kMaxIters - 1)
       {
@@ -1768,7 +1873,14 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
   {
     // maxDepth == 0: every sample is black (the while loop never runs)
   }
-  timed(tOther, [&] { k_accumulate<<<gridWide, 256, 0, st>>>(h->P, F, h->dAccum); });
+  // accumulate on the main stream, in frame order
+  CK(cudaEventRecord(L.done, st));
+  CK(cudaStreamWaitEvent(h->stream, L.done, 0));
+  st = h->stream;
+  timed(tOther, [&] { k_accumulate<<<gridWide, 256, 0, st>>>(L.P, F, h->dAccum); });
+  CK(cudaEventRecord(L.freed, st));
+  L.busy = true;
+  h->lastLane = laneIdx;
   CK(cudaGetLastError());
   if(h->profiling && getenv("B200PT_DUMP_ITERS"))
   {
@@ -1776,7 +1888,7 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
     CK(cudaStreamSynchronize(st));
     const int            n = pc->maxDepth < 64 ? pc->maxDepth : 64;
     std::vector<uint32_t> c(2 * kMaxIters);
-    CK(cudaMemcpy(c.data(), h->dCounters, sizeof(uint32_t) * 2 * kMaxIters, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(c.data(), L.dCounters, sizeof(uint32_t) * 2 * kMaxIters, cudaMemcpyDeviceToHost));
     const size_t first = h->evUsed >= (size_t)(3 * pc->maxDepth + 2) ? h->evUsed - (size_t)(3 * pc->maxDepth + 2) : 0;
     for(int it = 0; it < n; it++)
     {
@@ -1798,7 +1910,7 @@ int b200pt_get_stats(b200pt_t* h, b200pt_stats* out)
   if(!h || !out)
     return B200PT_E_INVALID;
   CK(cudaSetDevice(h->device));
-  CK(cudaStreamSynchronize(h->stream));
+  syncAll(h);
   DevStats d{};
   CK(cudaMemcpy(&d, h->dStats, sizeof(d), cudaMemcpyDeviceToHost));
   out->closestRays = d.closestRays;
@@ -1825,7 +1937,7 @@ int b200pt_reset_stats(b200pt_t* h)
   if(!h)
     return B200PT_E_INVALID;
   CK(cudaSetDevice(h->device));
-  CK(cudaStreamSynchronize(h->stream));
+  syncAll(h);
   CK(cudaMemset(h->dStats, 0, sizeof(DevStats)));
   flushEvents(h);
   for(int k = 0; k < 4; k++)

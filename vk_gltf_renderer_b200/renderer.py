@@ -158,6 +158,16 @@ class PathTracer:
         self._ck(self._L.b200pt_read_accum(self._h, out.ctypes.data_as(C.c_void_p), out.size), "b200pt_read_accum")
         return out
 
+    def read_accum_async(self, host_ptr, num_floats, slot):
+        """enqueue a copy of the image into (pinned) host memory; wait_read(slot) completes it."""
+        self._ck(self._L.b200pt_read_accum_async(self._h, host_ptr, num_floats, slot), "b200pt_read_accum_async")
+
+    def wait_read(self, slot):
+        self._ck(self._L.b200pt_wait_read(self._h, slot), "b200pt_wait_read")
+
+    def set_frames_in_flight(self, n):
+        self._ck(self._L.b200pt_set_frames_in_flight(self._h, n), "b200pt_set_frames_in_flight")
+
     def accum_device_ptr(self):
         p, n = C.c_void_p(), C.c_size_t()
         self._ck(self._L.b200pt_get_accum_device(self._h, C.byref(p), C.byref(n)), "b200pt_get_accum_device")
