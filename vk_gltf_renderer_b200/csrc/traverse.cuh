@@ -33,6 +33,9 @@ PT_D uint32_t signExtendS8x4(uint32_t x)
   return ((x >> 7) & 0x01010101u) * 0xffu;
 }
 
+// byte j of x as the float 32768 + b: PRMT puts the byte into bits 8..15 of 0x47000000 (= 32768.0f, ulp 2^-8)
+PT_D float biasedByte(uint32_t x, int j) { return __uint_as_float(__byte_perm(x, 0x47000000u, 0x7604u | ((uint32_t)j << 4))); }
+
 // One traversal in flight, resumable one node-step at a time (the persistent kernels interleave the
 // steps of 32 independent rays per warp and re-fill finished lanes from a global work counter).
 //   cull    : back-face culling per triangle flags (RAY_FLAG_CULL_BACK_FACING_TRIANGLES + instance cull-disable)
@@ -139,9 +142,17 @@ struct TravState
         const float    adx = __uint_as_float(extractByte(eImask, 0) << 23) * idx;
         const float    ady = __uint_as_float(extractByte(eImask, 1) << 23) * idy;
         const float    adz = __uint_as_float(extractByte(eImask, 2) << 23) * idz;
-        const float    aox = (n0.x - org.x) * idx;
-        const float    aoy = (n0.y - org.y) * idy;
-        const float    aoz = (n0.z - org.z) * idz;
+        // Quantised plane bytes become floats WITHOUT the conversion unit (48 I2F.U8 per node saturated the XU
+        // pipe, ncu: 65 % active, the busiest pipe): one PRMT drops byte b into the mantissa of 2^15, giving
+        // 32768 + b exactly, and the bias moves into the addend: t = (32768 + b) * ad + (ao - 32768 * ad).
+        // The addend's rounding error is at most |ad| / 512 (1/512 of a quantisation cell); the entry side is
+        // pulled back and the exit side pushed out by |ad| / 256, so the test stays conservative.
+        const float aox = fmaf(-32768.0f, adx, (n0.x - org.x) * idx);
+        const float aoy = fmaf(-32768.0f, ady, (n0.y - org.y) * idy);
+        const float aoz = fmaf(-32768.0f, adz, (n0.z - org.z) * idz);
+        const float aoxN = fmaf(-0.00390625f, fabsf(adx), aox), aoxF = fmaf(0.00390625f, fabsf(adx), aox);
+        const float aoyN = fmaf(-0.00390625f, fabsf(ady), aoy), aoyF = fmaf(0.00390625f, fabsf(ady), aoy);
+        const float aozN = fmaf(-0.00390625f, fabsf(adz), aoz), aozF = fmaf(0.00390625f, fabsf(adz), aoz);
 
         cur.x = __float_as_uint(n1.x);
         tri.x = __float_as_uint(n1.y);
@@ -165,12 +176,20 @@ struct TravState
 #pragma unroll
           for(int j = 0; j < 4; j++)
           {
-            const float tminx = fmaf((float)extractByte(xmin, j), adx, aox);
-            const float tminy = fmaf((float)extractByte(ymin, j), ady, aoy);
-            const float tminz = fmaf((float)extractByte(zmin, j), adz, aoz);
-            const float tmaxx = fmaf((float)extractByte(xmax, j), adx, aox);
-            const float tmaxy = fmaf((float)extractByte(ymax, j), ady, aoy);
-            const float tmaxz = fmaf((float)extractByte(zmax, j), adz, aoz);
+            const float tminx = fmaf(biasedByte(xmin, j), adx, aoxN);
+            const float tminy = fmaf(biasedByte(ymin, j), ady, aoyN);
+#ifdef B200PT_CVT_Z_I2F
+            const float tminz = fmaf((float)extractByte(zmin, j), adz, fmaf(32768.0f, adz, aozN));
+#else
+            const float tminz = fmaf(biasedByte(zmin, j), adz, aozN);
+#endif
+            const float tmaxx = fmaf(biasedByte(xmax, j), adx, aoxF);
+            const float tmaxy = fmaf(biasedByte(ymax, j), ady, aoyF);
+#ifdef B200PT_CVT_Z_I2F
+            const float tmaxz = fmaf((float)extractByte(zmax, j), adz, fmaf(32768.0f, adz, aozF));
+#else
+            const float tmaxz = fmaf(biasedByte(zmax, j), adz, aozF);
+#endif
             const float tn = fmaxf(fmaxf(tminx, tminy), fmaxf(tminz, tLow));
             const float tf = fminf(fminf(tmaxx, tmaxy), fminf(tmaxz, best.t));
             // widen by a few ulp: keeps the box test conservative w.r.t. the triangle test
