@@ -272,6 +272,16 @@ __global__ void __launch_bounds__(128) k_trace(PathState P, DevScene S, const ui
     //      lanes are still busy ----
     for(;;)
     {
+#ifdef B200PT_COUNT_TRAVERSAL
+      {
+        const unsigned busy = __ballot_sync(0xffffffffu, path >= 0 && !travDone);
+        if((threadIdx.x & 31) == 0)
+        {
+          atomicAdd(&stats->warpIters, 1ull);
+          atomicAdd(&stats->busyLaneIters, (unsigned long long)__popc(busy));
+        }
+      }
+#endif
       if(path >= 0 && !travDone)
         travDone = T.step(stack, postponeShift);
       if(__popc(__ballot_sync(0xffffffffu, path >= 0 && !travDone)) < refillThreshold)
@@ -701,6 +711,16 @@ __global__ void __launch_bounds__(128) k_post(PathState P, DevScene S, const __g
       break;
     for(;;)
     {
+#ifdef B200PT_COUNT_TRAVERSAL
+      {
+        const unsigned busy = __ballot_sync(0xffffffffu, path >= 0 && !travDone);
+        if((threadIdx.x & 31) == 0)
+        {
+          atomicAdd(&stats->warpIters, 1ull);
+          atomicAdd(&stats->busyLaneIters, (unsigned long long)__popc(busy));
+        }
+      }
+#endif
       if(path >= 0 && !travDone)
         travDone = T.step(stack, postponeShift);
       if(__popc(__ballot_sync(0xffffffffu, path >= 0 && !travDone)) < refillThreshold)
@@ -856,12 +876,6 @@ __global__ void k_bsdf_sample(const float* __restrict__ in, uint32_t n, float* _
 // -------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------
-struct TexRes
-{
-  cudaMipmappedArray_t arr = nullptr;
-  cudaTextureObject_t  obj = 0;
-};
-
 }  // namespace
 
 struct b200pt
@@ -873,7 +887,6 @@ struct b200pt
 
   // scene
   std::vector<void*>  sceneAllocs;
-  std::vector<TexRes> texRes;
   DevScene            S{};
   bool                haveScene = false;
   bool                hasVolume = false;
@@ -964,14 +977,6 @@ int upload(b200pt* h, std::vector<void*>& owner, const T* src, size_t count, T**
 
 void freeScene(b200pt* h)
 {
-  for(auto& t : h->texRes)
-  {
-    if(t.obj)
-      cudaDestroyTextureObject(t.obj);
-    if(t.arr)
-      cudaFreeMipmappedArray(t.arr);
-  }
-  h->texRes.clear();
   for(void* p : h->sceneAllocs)
     cudaFree(p);
   h->sceneAllocs.clear();
@@ -1080,34 +1085,27 @@ void buildMipChain(const b200pt_texture& src, MipChain& mc)
   }
 }
 
-int createTexture(b200pt* h, const b200pt_texture& src, const MipChain& mc, TexRes& out, DevTex& dev)
+// texels of one mip chain in the device layout: level after level, each as row-major 4x4-texel tiles
+// (levels narrower than 4 texels are padded; the padding is never addressed)
+void packTiled(const MipChain& mc, std::vector<uint32_t>& texels, uint32_t levelOfs[16])
 {
-  const int levels = (int)mc.level.size();
-  cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
-  CK(cudaMallocMipmappedArray(&out.arr, &fmt, make_cudaExtent((size_t)src.width, (size_t)src.height, 0), (unsigned)levels));
-  for(int l = 0; l < levels; l++)
+  for(size_t l = 0; l < mc.level.size() && l < 16; l++)
   {
-    cudaArray_t la;
-    CK(cudaGetMipmappedArrayLevel(&la, out.arr, (unsigned)l));
-    CK(cudaMemcpy2DToArray(la, 0, 0, mc.level[l].data(), (size_t)mc.w[l] * 4, (size_t)mc.w[l] * 4, (size_t)mc.h[l], cudaMemcpyHostToDevice));
+    const int w = mc.w[l], hh = mc.h[l], tpr = (w + 3) >> 2, tpc = (hh + 3) >> 2;
+    levelOfs[l] = (uint32_t)texels.size();
+    texels.resize(texels.size() + (size_t)tpr * tpc * 16, 0u);
+    uint32_t*       dst = texels.data() + levelOfs[l];
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(mc.level[l].data());
+    for(int y = 0; y < hh; y++)
+      for(int x = 0; x < w; x++)
+        dst[(((size_t)(y >> 2) * tpr + (x >> 2)) << 4) + ((y & 3) << 2) + (x & 3)] = src[(size_t)y * w + x];
   }
-  cudaResourceDesc rd{};
-  rd.resType = cudaResourceTypeMipmappedArray;
-  rd.res.mipmap.mipmap = out.arr;
-  cudaTextureDesc td{};
-  td.addressMode[0] = cudaAddressModeClamp;  // wrap / mirror are applied in software on integer texel coordinates
-  td.addressMode[1] = cudaAddressModeClamp;
-  td.filterMode = cudaFilterModePoint;
-  td.mipmapFilterMode = cudaFilterModePoint;
-  td.readMode = cudaReadModeElementType;
-  td.sRGB = 0;
-  td.normalizedCoords = 1;
-  td.maxAnisotropy = 1;
-  td.minMipmapLevelClamp = 0.f;
-  td.maxMipmapLevelClamp = (float)(levels - 1);
-  CK(cudaCreateTextureObject(&out.obj, &rd, &td, nullptr));
+}
+
+void describeTexture(const b200pt_texture& src, const MipChain& mc, DevTex& dev)
+{
+  const int levels = (int)std::min<size_t>(mc.level.size(), 16);
   // sampler quirks kept from getSampler (src/gltf_scene_vk.cpp:909-947): the mip mode follows magFilter
-  dev.obj = out.obj;
   dev.w0 = src.width;
   dev.h0 = src.height;
   dev.maxLevel = (float)(levels - 1);
@@ -1117,7 +1115,6 @@ int createTexture(b200pt* h, const b200pt_texture& src, const MipChain& mc, TexR
   dev.magLinear = (src.magFilter != 9728) ? 1 : 0;
   dev.minLinear = (src.minFilter == 9728 || src.minFilter == 9984 || src.minFilter == 9986) ? 0 : 1;
   dev.mipLinear = (src.magFilter != 9728) ? 1 : 0;
-  return 0;
 }
 
 int gridFor(const b200pt* h, int perSM) { return h->numSMs * perSM; }
@@ -1336,7 +1333,6 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
 
   // --- textures ---
   std::vector<DevTex> devTex(s->numTextures);
-  h->texRes.resize(s->numTextures);
   {
     for(uint32_t i = 0; i < s->numTextures; i++)
       if(s->textures[i].width <= 0 || s->textures[i].height <= 0 || !s->textures[i].rgba8)
@@ -1357,9 +1353,43 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
     job();
     for(auto& t : workers)
       t.join();
+    // one allocation for all texels, one table of level offsets
+    std::vector<uint32_t> levelOfs((size_t)s->numTextures * 16, 0u);
+    std::vector<size_t>   texBase(s->numTextures, 0);
+    size_t                total = 0;
+    std::vector<std::vector<uint32_t>> packed(s->numTextures);
+    {
+      std::atomic<uint32_t>    nextPack{0};
+      std::vector<std::thread> packers;
+      auto                     pjob = [&]() {
+        for(uint32_t i = nextPack.fetch_add(1); i < s->numTextures; i = nextPack.fetch_add(1))
+          packTiled(chains[i], packed[i], &levelOfs[(size_t)i * 16]);
+      };
+      for(unsigned t = 1; t < nt; t++)
+        packers.emplace_back(pjob);
+      pjob();
+      for(auto& t : packers)
+        t.join();
+    }
     for(uint32_t i = 0; i < s->numTextures; i++)
-      if((rc = createTexture(h, s->textures[i], chains[i], h->texRes[i], devTex[i])))
-        return rc;
+    {
+      texBase[i] = total;
+      total += packed[i].size();
+    }
+    uint32_t* dTexels = nullptr;
+    uint32_t* dLevelOfs = nullptr;
+    CK(cudaMalloc((void**)&dTexels, std::max<size_t>(total, 1) * sizeof(uint32_t)));
+    h->sceneAllocs.push_back(dTexels);
+    for(uint32_t i = 0; i < s->numTextures; i++)
+      CK(cudaMemcpy(dTexels + texBase[i], packed[i].data(), packed[i].size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if((rc = upload(h, h->sceneAllocs, levelOfs.data(), levelOfs.size(), &dLevelOfs)))
+      return rc;
+    for(uint32_t i = 0; i < s->numTextures; i++)
+    {
+      describeTexture(s->textures[i], chains[i], devTex[i]);
+      devTex[i].texels = reinterpret_cast<const uchar4*>(dTexels + texBase[i]);
+      devTex[i].levelOfs = dLevelOfs + (size_t)i * 16;
+    }
   }
   DevTex* dTex;
   if((rc = upload(h, h->sceneAllocs, devTex.data(), devTex.size(), &dTex)))
@@ -1919,6 +1949,11 @@ int b200pt_get_stats(b200pt_t* h, b200pt_stats* out)
   out->pathsStarted = d.pathsStarted;
   out->nodesVisited = d.nodesVisited;
   out->trisTested = d.trisTested;
+#ifdef B200PT_COUNT_TRAVERSAL
+  if(getenv("B200PT_DUMP_ITERS") && d.warpIters)
+    fprintf(stderr, "traversal loop: %llu warp iterations, busy lanes %.2f/32, node-phase lanes %.2f/32, triangle-phase lanes %.2f/32\n", d.warpIters,
+            (double)d.busyLaneIters / (double)d.warpIters, (double)d.nodesVisited / (double)d.warpIters, (double)d.trisTested / (double)d.warpIters);
+#endif
   flushEvents(h);
   out->msTraceClosest = h->msCat[0];
   out->msShade = h->msCat[1];

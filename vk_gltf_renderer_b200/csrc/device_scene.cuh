@@ -28,12 +28,17 @@ struct DevPrim
 
 struct DevTex
 {
-  cudaTextureObject_t obj;  // RGBA8 mip pyramid, point-sampled (filtering happens in fp32 in the kernel)
-  int                 w0, h0;
-  float               maxLevel;
-  int                 wrapS, wrapT;  // glTF enums
-  int                 srgb;
-  int                 magLinear, minLinear, mipLinear;
+  // RGBA8 mip pyramid in plain global memory, every level stored as 4x4-texel tiles (64 B: a bilinear footprint
+  // mostly stays inside one tile).  Filtering happens in fp32 in the kernel, so the texture unit would only ever
+  // point-sample -- and with one texture object per lane every TEX became a waterfall loop over the distinct
+  // handles in the warp (SASS: R2UR + BRA.U.ANY around each of the 24 fetches of a shaded hit).
+  const uchar4*   texels;
+  const uint32_t* levelOfs;  // texel offset of every level from `texels`
+  int             w0, h0;
+  float           maxLevel;
+  int             wrapS, wrapT;  // glTF enums
+  int             srgb;
+  int             magLinear, minLinear, mipLinear;
 };
 
 struct DevScene
@@ -114,6 +119,7 @@ struct Queues
 struct DevStats
 {
   unsigned long long closestRays, shadowRays, shadedHits, pathsStarted, nodesVisited, trisTested;
+  unsigned long long warpIters, busyLaneIters;  // counter build only: traversal-loop iterations per warp, busy lanes summed
 };
 
 }  // namespace pt

@@ -145,7 +145,9 @@ PT_D void stageSrgbLut(const float* __restrict__ lutGlobal)
 // used for the 2D-local fetch path only).  Hardware bilinear/trilinear blends use 8-bit fixed-point
 // weights; an alpha-MASK cutoff evaluated on such a blend flips at leaf silhouettes relative to the
 // fp32 definition and the paths diverge, so the exact definition is kept (measured: 1e-5 of rays).
-PT_D int wrapCoord(int i, int n, int mode)
+// (out of line: the generic modes are rare, and inlining their integer divisions into every texel fetch blew the
+// shade kernel up past the instruction cache -- ncu: 42 % of its stall samples were no_instruction)
+__device__ __noinline__ int wrapCoord(int i, int n, int mode)
 {
   if(mode == 33071)  // CLAMP_TO_EDGE
     return min(max(i, 0), n - 1);
@@ -158,12 +160,12 @@ PT_D int wrapCoord(int i, int n, int mode)
   return ((i % n) + n) % n;  // REPEAT
 }
 
-// texel (x, y) of `level`, coordinates already wrapped; point fetch at the texel centre
-PT_D float4 fetchTexel(const DevTex& T, float level, float invW, float invH, int x, int y)
+// texel (x, y) of one level (coordinates already wrapped); `lv` points at the level's first tile, tpr = tiles per row
+PT_D float4 fetchTexel(const uchar4* __restrict__ lv, int tpr, bool srgb, int x, int y)
 {
-  const uchar4 p = tex2DLod<uchar4>(T.obj, ((float)x + 0.5f) * invW, ((float)y + 0.5f) * invH, level);
+  const uchar4 p = __ldg(lv + (((y >> 2) * tpr + (x >> 2)) << 4) + ((y & 3) << 2) + (x & 3));
   const float  a = (float)p.w / 255.0f;
-  if(T.srgb)
+  if(srgb)
     return f4(s_lutSrgb[p.x], s_lutSrgb[p.y], s_lutSrgb[p.z], a);
   return f4((float)p.x / 255.0f, (float)p.y / 255.0f, (float)p.z / 255.0f, a);
 }
@@ -175,21 +177,27 @@ PT_D int wrapFast(int i, int n, int mode)
   return wrapCoord(i, n, mode);
 }
 
+#ifdef B200PT_NOINLINE_SAMPLELEVEL
+__device__ __noinline__ float4 sampleLevel(const DevTex& T, int level, float2 uv, bool linear)
+#else
 PT_D float4 sampleLevel(const DevTex& T, int level, float2 uv, bool linear)
+#endif
 {
-  const int   w = max(1, T.w0 >> level), h = max(1, T.h0 >> level);
-  const float invW = 1.0f / (float)w, invH = 1.0f / (float)h, lv = (float)level;
-  float       x = uv.x * (float)w, y = uv.y * (float)h;
+  const int     w = max(1, T.w0 >> level), h = max(1, T.h0 >> level);
+  const uchar4* lv = T.texels + __ldg(T.levelOfs + level);
+  const int     tpr = (w + 3) >> 2;
+  const bool    srgb = T.srgb != 0;
+  float         x = uv.x * (float)w, y = uv.y * (float)h;
   if(!linear)
-    return fetchTexel(T, lv, invW, invH, wrapFast((int)floorf(x), w, T.wrapS), wrapFast((int)floorf(y), h, T.wrapT));
+    return fetchTexel(lv, tpr, srgb, wrapFast((int)floorf(x), w, T.wrapS), wrapFast((int)floorf(y), h, T.wrapT));
   x -= 0.5f;
   y -= 0.5f;
   const float  fx0 = floorf(x), fy0 = floorf(y);
   const float  fx = x - fx0, fy = y - fy0;
   const int    x0 = wrapFast((int)fx0, w, T.wrapS), x1 = wrapFast((int)fx0 + 1, w, T.wrapS);
   const int    y0 = wrapFast((int)fy0, h, T.wrapT), y1 = wrapFast((int)fy0 + 1, h, T.wrapT);
-  const float4 a = fetchTexel(T, lv, invW, invH, x0, y0), b = fetchTexel(T, lv, invW, invH, x1, y0);
-  const float4 c = fetchTexel(T, lv, invW, invH, x0, y1), d = fetchTexel(T, lv, invW, invH, x1, y1);
+  const float4 a = fetchTexel(lv, tpr, srgb, x0, y0), b = fetchTexel(lv, tpr, srgb, x1, y0);
+  const float4 c = fetchTexel(lv, tpr, srgb, x0, y1), d = fetchTexel(lv, tpr, srgb, x1, y1);
   const float4 top = a * (1.0f - fx) + b * fx;
   const float4 bot = c * (1.0f - fx) + d * fx;
   return top * (1.0f - fy) + bot * fy;
