@@ -40,7 +40,14 @@ struct Node2
 {
   Box      box;
   uint32_t left = 0, right = 0;   // inner
-  uint32_t first = 0, count = 0;  // leaf when count > 0
+  uint32_t first = 0, count = 0;  // BVH2 leaf when count > 0 (one triangle unless the centroids coincide)
+  uint32_t nprims = 0;            // triangles below this node: order[first .. first + nprims)
+  // SAH-optimal collapse (Ylitie, Karras, Laine 2017, section 3): cost[i-1] = cheapest forest of <= i wide-BVH
+  // roots for this subtree; asLeaf = the single-root optimum is a leaf; splitK[i-1] = roots given to the left
+  // child (0 = "use i-1 roots instead")
+  float   cost[7];
+  uint8_t splitK[8];
+  bool    asLeaf = false;
 };
 
 struct Builder
@@ -80,7 +87,7 @@ struct Builder
     }
   }
 
-  // binned SAH, leaves of <= 3 triangles (a CWBVH child slot addresses at most 3)
+  // binned SAH down to single triangles; leaves of <= 3 triangles are formed by the collapse below
   void build2()
   {
     struct Job
@@ -113,8 +120,8 @@ struct Builder
       n2[j.node].box = bb;
       n2[j.node].first = j.first;
       n2[j.node].count = j.count;
-      static const int kLeaf = getenv("BVH_LEAF") ? atoi(getenv("BVH_LEAF")) : 3;
-      if((int)j.count <= kLeaf)
+      n2[j.node].nprims = j.count;
+      if(j.count <= 1)
         continue;
       float bestCost = FLT_MAX;
       int   bestAxis = -1, bestBin = -1;
@@ -234,7 +241,85 @@ void buildWideBvh(const std::vector<FlatTri>& tris, const std::vector<uint32_t>&
     out.boundsHi[a] = B.n2[0].box.hi[a];
   }
 
-  // ---- collapse to 8-wide + emit ---------------------------------------------------------------
+  // ---- SAH-optimal collapse: dynamic programme over the binary tree, children before parents -----------------
+  // (children are always created after their parent, so a reverse sweep sees them first)
+  const float kCostNode = 1.0f, kCostPrim = getenv("BVH_CPRIM") ? (float)atof(getenv("BVH_CPRIM")) : 0.4f;  // one node step ~ 270 SASS instructions, one triangle test ~ 110
+  const float invRootArea = 1.0f / std::max(B.n2[0].box.halfArea(), 1e-30f);
+  for(size_t ni = B.n2.size(); ni-- > 0;)
+  {
+    Node2&      n = B.n2[ni];
+    const float area = n.box.halfArea() * invRootArea;
+    const float leafCost = (n.nprims <= 3) ? area * (float)n.nprims * kCostPrim : FLT_MAX;
+    for(int i = 0; i < 8; i++)
+      n.splitK[i] = 0;
+    if(n.count > 0)
+    {
+      // BVH2 leaf (normally one triangle; coincident centroids can leave up to 3, larger groups were split in half)
+      for(int i = 0; i < 7; i++)
+        n.cost[i] = leafCost;
+      n.asLeaf = true;
+      continue;
+    }
+    const Node2 &L = B.n2[n.left], &R = B.n2[n.right];
+    auto         distribute = [&](int j, uint8_t& bestK) {
+      float best = FLT_MAX;
+      bestK = 1;
+      for(int k = 1; k < j; k++)
+      {
+        const float c = L.cost[std::min(k, 7) - 1] + R.cost[std::min(j - k, 7) - 1];
+        if(c < best)
+        {
+          best = c;
+          bestK = (uint8_t)k;
+        }
+      }
+      return best;
+    };
+    uint8_t     k8;
+    const float internalCost = distribute(8, k8) + area * kCostNode;
+    n.splitK[7] = k8;
+    n.asLeaf = leafCost <= internalCost;
+    n.cost[0] = std::min(leafCost, internalCost);
+    for(int i = 2; i <= 7; i++)
+    {
+      uint8_t     k;
+      const float d = distribute(i, k);
+      if(d < n.cost[i - 2])
+      {
+        n.cost[i - 1] = d;
+        n.splitK[i - 1] = k;
+      }
+      else
+      {
+        n.cost[i - 1] = n.cost[i - 2];
+        n.splitK[i - 1] = 0;
+      }
+    }
+  }
+  // roots of the cheapest forest of <= j wide nodes / leaves covering subtree n
+  struct Gather
+  {
+    const std::vector<Node2>& n2;
+    void run(uint32_t n, int j, uint32_t* out, int& cnt) const
+    {
+      const Node2& N = n2[n];
+      if(j <= 1 || N.count > 0)
+      {
+        out[cnt++] = n;
+        return;
+      }
+      const int k = N.splitK[j - 1];
+      if(k == 0)
+      {
+        run(n, j - 1, out, cnt);
+        return;
+      }
+      run(N.left, k, out, cnt);
+      run(N.right, j - k, out, cnt);
+    }
+  } gather{B.n2};
+
+  // ---- emit the wide nodes ----------------------------------------------------------------------
   struct Pending
   {
     uint32_t n2;     // BVH2 node this wide node covers
@@ -254,34 +339,16 @@ void buildWideBvh(const std::vector<FlatTri>& tris, const std::vector<uint32_t>&
     Pending pn = queue[qi++];
     out.maxDepth = std::max(out.maxDepth, pn.depth);
     const Node2& root = B.n2[pn.n2];
-    // gather up to 8 children: repeatedly open the inner child with the largest surface area
+    // children of this wide node = the optimal forest of <= 8 roots of the subtree (a root that is a single
+    // BVH2 leaf is wrapped in a wide node with one leaf child)
     uint32_t ch[8];
     int      nch = 0;
     if(root.count > 0)
       ch[nch++] = pn.n2;
     else
     {
-      ch[nch++] = root.left;
-      ch[nch++] = root.right;
-      while(nch < 8)
-      {
-        int   best = -1;
-        float bestA = -1.f;
-        for(int i = 0; i < nch; i++)
-        {
-          const Node2& c = B.n2[ch[i]];
-          if(c.count == 0 && c.box.halfArea() > bestA)
-          {
-            bestA = c.box.halfArea();
-            best = i;
-          }
-        }
-        if(best < 0)
-          break;
-        const Node2& c = B.n2[ch[best]];
-        ch[best] = c.left;
-        ch[nch++] = c.right;
-      }
+      gather.run(root.left, root.splitK[7], ch, nch);
+      gather.run(root.right, 8 - root.splitK[7], ch, nch);
     }
     // slot assignment: slot s is visited first by rays whose negative-direction bits equal s, so a
     // child far along +x wants bit 4 set, +y bit 2, +z bit 1 (greedy maximum of centroid . diagonal)
@@ -364,7 +431,7 @@ void buildWideBvh(const std::vector<FlatTri>& tris, const std::vector<uint32_t>&
         qlo[a][s] = (uint8_t)std::max(0, std::min(255, ql));
         qhi[a][s] = (uint8_t)std::max(0, std::min(255, qh));
       }
-      if(c.count == 0)
+      if(!c.asLeaf)
       {
         imask |= (uint8_t)(1u << s);
         meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
@@ -373,9 +440,9 @@ void buildWideBvh(const std::vector<FlatTri>& tris, const std::vector<uint32_t>&
       else
       {
         // unary count in the high 3 bits, triangle offset in the low 5
-        uint32_t bits = (c.count == 1) ? 1u : (c.count == 2 ? 3u : 7u);
+        uint32_t bits = (c.nprims == 1) ? 1u : (c.nprims == 2 ? 3u : 7u);
         meta[s] = (uint8_t)((bits << 5) | triCount);
-        for(uint32_t k = 0; k < c.count; k++)
+        for(uint32_t k = 0; k < c.nprims; k++)
         {
           const uint32_t local = B.order[c.first + k];
           const uint32_t gid = gids[local];
@@ -385,7 +452,7 @@ void buildWideBvh(const std::vector<FlatTri>& tris, const std::vector<uint32_t>&
           out.triMeta.push_back(T.rnode | (T.flags << 28));
           out.triMeta.push_back(T.prim);
         }
-        triCount += c.count;
+        triCount += c.nprims;
       }
     }
     // reserve the internal children (ascending slot order) and queue them
@@ -396,7 +463,7 @@ void buildWideBvh(const std::vector<FlatTri>& tris, const std::vector<uint32_t>&
       if(childAt[s] < 0)
         continue;
       const uint32_t cn = ch[childAt[s]];
-      if(B.n2[cn].count == 0)
+      if(!B.n2[cn].asLeaf)
         queue.push_back({cn, childBase + k++, pn.depth + 1});
     }
     float* N = &out.nodes[(size_t)pn.index * 20];
