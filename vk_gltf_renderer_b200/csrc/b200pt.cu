@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(128) k_trace(PathState P, DevScene S, const ui
   const uint32_t count = *cntIn;
   TravState      T;
   uint2          stack[TravState::kStackSize];
+  Cand           cand[kCand];
   int            path = -1;
   int            phase = 0;        // 0: opaque tree, 1: alpha (any-hit) tree
   bool           travDone = false;  // traversal finished, state machine pending
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(128) k_trace(PathState P, DevScene S, const ui
         {
           // non-opaque candidates nearer than the opaque hit, front to back (raytracer_interface.h.slang:82-112)
           phase = 1;
-          T.init(S.bvhAlpha, T.org, T.dir, 0.0f, (ho.slot != 0xFFFFFFFFu) ? ho.t : tmaxRay, true, false, false, 0.f, 0u);
+          T.init(S.bvhAlpha, T.org, T.dir, 0.0f, (ho.slot != 0xFFFFFFFFu) ? ho.t : tmaxRay, true, false, false, 0.f, 0u, true);
         }
         else
         {
@@ -216,24 +217,34 @@ __global__ void __launch_bounds__(128) k_trace(PathState P, DevScene S, const ui
       }
       else
       {
-        const TraceHit h = T.result();
-        if(h.slot == 0xFFFFFFFFu)
+        // the collected candidates, nearest first: one rand() each until one passes its alpha test
+        const int n = T.collectN;
+        for(int i = 0; i < n && !done; i++)
         {
-          res = ho;
-          done = true;
-        }
-        else
-        {
-          const uint2               meta = S.triMeta[h.slot];
+          const Cand                c = cand[i];
+          const uint2               meta = S.triMeta[c.slot];
+          const bool                flip = ((meta.x >> 28) & TRI_FLIPPED) != 0;  // mirrored instance: (u, v) swap back
+          const float               cu = flip ? c.v : c.u, cv = flip ? c.u : c.v;
           const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
-          const float               opacity = getOpacity(S, node, S.prims[node.renderPrimID], meta.y, f3(1.0f - h.u - h.v, h.u, h.v));
+          const float               opacity = getOpacity(S, node, S.prims[node.renderPrimID], meta.y, f3(1.0f - cu - cv, cu, cv));
           if(rnd(seed) <= opacity)
           {
-            res = h;
+            res.t = c.t;
+            res.u = cu;
+            res.v = cv;
+            res.slot = c.slot;
             done = true;
           }
+        }
+        if(!done)
+        {
+          if(n == kCand)
+            T.init(S.bvhAlpha, T.org, T.dir, 0.0f, T.tmax, true, false, true, cand[kCand - 1].t, cand[kCand - 1].gid, true);
           else
-            T.init(S.bvhAlpha, T.org, T.dir, 0.0f, T.tmax, true, false, true, h.t, h.gid);
+          {
+            res = ho;
+            done = true;
+          }
         }
       }
       if(done)
@@ -283,7 +294,7 @@ __global__ void __launch_bounds__(128) k_trace(PathState P, DevScene S, const ui
       }
 #endif
       if(path >= 0 && !travDone)
-        travDone = T.step(stack, postponeShift);
+        travDone = T.step(stack, postponeShift, cand);
       if(__popc(__ballot_sync(0xffffffffu, path >= 0 && !travDone)) < refillThreshold)
         break;
     }
@@ -598,6 +609,7 @@ __global__ void __launch_bounds__(128) k_post(PathState P, DevScene S, const __g
   const uint32_t count = *cntIn;
   TravState      T;
   uint2          stack[TravState::kStackSize];
+  Cand           cand[kCand];
   int            path = -1;  // -1: lane needs work, -2: queue exhausted
   int            phase = 0;  // 0: opaque occlusion query, 1: any-hit candidates front to back
   bool           travDone = false;
@@ -624,7 +636,7 @@ __global__ void __launch_bounds__(128) k_post(PathState P, DevScene S, const __g
         else if(S.hasAlpha)
         {
           phase = 1;
-          T.init(S.bvhAlpha, T.org, T.dir, 0.0f, T.tmax, false, false, false, 0.f, 0u);
+          T.init(S.bvhAlpha, T.org, T.dir, 0.0f, T.tmax, false, false, false, 0.f, 0u, true);
         }
         else
           done = true;
@@ -632,22 +644,23 @@ __global__ void __launch_bounds__(128) k_post(PathState P, DevScene S, const __g
       else
       {
         // 2. every non-opaque candidate, front to back (raytracer_interface.h.slang:149-179)
-        const TraceHit h = T.result();
-        if(h.slot == 0xFFFFFFFFu)
-          done = true;
-        else
+        const int n = T.collectN;
+        for(int i = 0; i < n && !done; i++)
         {
-          const uint2               meta = S.triMeta[h.slot];
+          const Cand                c = cand[i];
+          const uint2               meta = S.triMeta[c.slot];
+          const bool                flip = ((meta.x >> 28) & TRI_FLIPPED) != 0;
+          const float               cu = flip ? c.v : c.u, cv = flip ? c.u : c.v;
           const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
           const DevPrim&            prim = S.prims[node.renderPrimID];
-          const float3              bary = f3(1.0f - h.u - h.v, h.u, h.v);
+          const float3              bary = f3(1.0f - cu - cv, cu, cv);
           const float               opacity = getOpacity(S, node, prim, meta.y, bary);
           const float               r = rnd(seed);
           if(r < opacity)
           {
-            const float  seg = fmaxf(0.0f, h.t - prevHitT);
+            const float  seg = fmaxf(0.0f, c.t - prevHitT);
             const float3 cur = getShadowTransmission(S, node, prim, meta.y, bary, seg, T.dir, isInside);
-            prevHitT = h.t;
+            prevHitT = c.t;
             total *= cur;
             if(maxc(total) <= 0.01f)
             {
@@ -655,8 +668,13 @@ __global__ void __launch_bounds__(128) k_post(PathState P, DevScene S, const __g
               done = true;
             }
           }
-          if(!done)
-            T.init(S.bvhAlpha, T.org, T.dir, 0.0f, T.tmax, false, false, true, h.t, h.gid);
+        }
+        if(!done)
+        {
+          if(n == kCand)
+            T.init(S.bvhAlpha, T.org, T.dir, 0.0f, T.tmax, false, false, true, cand[kCand - 1].t, cand[kCand - 1].gid, true);
+          else
+            done = true;
         }
       }
       if(done)
@@ -722,7 +740,7 @@ __global__ void __launch_bounds__(128) k_post(PathState P, DevScene S, const __g
       }
 #endif
       if(path >= 0 && !travDone)
-        travDone = T.step(stack, postponeShift);
+        travDone = T.step(stack, postponeShift, cand);
       if(__popc(__ballot_sync(0xffffffffu, path >= 0 && !travDone)) < refillThreshold)
         break;
     }

@@ -20,6 +20,14 @@ struct TraceHit
   uint32_t w0;      // rnode | flags << 28
 };
 
+// one non-opaque candidate kept by a collecting traversal (see TravState::collectN)
+struct Cand
+{
+  float    t, u, v;
+  uint32_t slot, gid;
+};
+constexpr int kCand = 4;
+
 struct BvhView
 {
   const float4* __restrict__ nodes;  // 5 per node
@@ -54,12 +62,20 @@ struct TravState
   uint2         cur;   // current node group (x = child base, y = hit bits << 24 | imask)
   uint2         tri;   // pending triangle group (x = triangle base, y = hit bits)
   int           sp;    // entries on the caller-provided stack (kept OUT of this struct so the rest stays in registers)
+  // Collecting mode (any-hit candidates): instead of keeping only the nearest hit, the traversal keeps the kCand
+  // nearest hits after the lower bound, sorted by (t, id), in caller-provided scratch.  The kernels then run the
+  // stochastic alpha / transmission tests over them front to back -- the same sequence the restart-per-candidate
+  // formulation produces, with one tree walk per kCand candidates instead of one per candidate.  `best` holds the
+  // kCand-th candidate once the list is full, so node culling and the hit predicate need no extra code.
+  int           collectN;  // -1: nearest-hit mode, else number of candidates collected so far
 #ifdef B200PT_COUNT_TRAVERSAL
   unsigned int nodeCount, triCount;
 #endif
 
-  PT_D void init(const BvhView bvh, float3 o, float3 d, float tmin_, float tmax_, bool cull_, bool anyExit_, bool haveLo_, float loT_, uint32_t loId_)
+  PT_D void init(const BvhView bvh, float3 o, float3 d, float tmin_, float tmax_, bool cull_, bool anyExit_, bool haveLo_, float loT_, uint32_t loId_,
+                 bool collect_ = false)
   {
+    collectN = collect_ ? 0 : -1;
     nodes = bvh.nodes;
     tris = bvh.tris;
     org = o;
@@ -99,7 +115,7 @@ struct TravState
   // triangles test ONE triangle each — but only when enough lanes of the warp have one (vote); otherwise the
   // group is postponed onto the stack and node traversal continues (Ylitie et al. 2017, section 4.3).
   // Returns true when the traversal is complete.  `stack` is per-thread scratch of kStackSize entries.
-  PT_D bool step(uint2* __restrict__ stack, int postponeShift = 2)
+  PT_D bool step(uint2* __restrict__ stack, int postponeShift = 2, Cand* __restrict__ cand = nullptr)
   {
     // single exit: an early return inside the divergent regions would move their reconvergence point out of the
     // caller's loop and the lanes of a warp would drift apart (measured: 8 of 32 lanes active)
@@ -253,13 +269,39 @@ struct TravState
         hit &= (t < best.t) | ((t == best.t) & (gid < best.gid));
         if(hit)
         {
-          best.t = t;
-          best.u = u;
-          best.v = v;
-          best.slot = slot;
-          best.gid = gid;
-          best.w0 = w0;
-          done = anyExit;  // occlusion query satisfied
+          if(collectN >= 0)
+          {
+            // insertion sort by (t, id); a full list drops its last entry (the predicate above already
+            // guarantees the new hit sorts before it)
+            int pos = collectN < kCand ? collectN : kCand - 1;
+            while(pos > 0 && ((cand[pos - 1].t > t) | ((cand[pos - 1].t == t) & (cand[pos - 1].gid > gid))))
+            {
+              cand[pos] = cand[pos - 1];
+              pos--;
+            }
+            cand[pos].t = t;
+            cand[pos].u = u;
+            cand[pos].v = v;
+            cand[pos].slot = slot;
+            cand[pos].gid = gid;
+            if(collectN < kCand)
+              collectN++;
+            if(collectN == kCand)
+            {
+              best.t = cand[kCand - 1].t;
+              best.gid = cand[kCand - 1].gid;
+            }
+          }
+          else
+          {
+            best.t = t;
+            best.u = u;
+            best.v = v;
+            best.slot = slot;
+            best.gid = gid;
+            best.w0 = w0;
+            done = anyExit;  // occlusion query satisfied
+          }
         }
       }
     }
