@@ -26,7 +26,10 @@ struct Cand
   float    t, u, v;
   uint32_t slot, gid;
 };
-constexpr int kCand = 4;
+#ifndef B200PT_KCAND
+#define B200PT_KCAND 4
+#endif
+constexpr int kCand = B200PT_KCAND;
 
 struct BvhView
 {
