@@ -171,90 +171,56 @@ __device__ __forceinline__ uint32_t fetchWork(bool need, uint32_t* workCounter, 
   return k < count ? k : 0xFFFFFFFFu;
 }
 
-// IRaytracer::Trace for every path in the queue.
-// Per lane: path (-1 needs work, -2 exhausted), a resumable traversal, and a small state machine that runs in
-// the CONVERGED part of the loop (phase changes, stochastic alpha test, result write), never inside the
-// traversal loop, so the hot loop contains nothing but node / triangle steps.
+// IRaytracer::Trace, geometry part, for every path in the queue: closest FORCE_OPAQUE hit, then (scenes with
+// non-opaque triangles) the kCand nearest any-hit candidates in front of it.  The stochastic alpha tests need
+// textures and touch only the few lanes whose walk just ended -- inside this kernel they ran with ~2 of 32 lanes
+// active and took 17 % of its instructions / 26 % of its stall samples (ncu, profiles/) -- so they live in the
+// dense kernel k_alpha; this kernel only writes the candidates out.
+// Per lane: path (-1 needs work, -2 exhausted) and a resumable traversal; finished lanes are handled in the
+// converged part of the loop, never inside the traversal loop.
 #ifndef B200PT_TRACE_MINBLOCKS
 #define B200PT_TRACE_MINBLOCKS 6  // 80 registers: 6 blocks/SM; measured 470 -> 488 Mray/s against the unconstrained 96-register build
 #endif
 __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_trace(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn,
-                                               uint32_t* workCounter, DevStats* stats, int refillThreshold, int postponeShift)
+                                                                       uint32_t* workCounter, uint32_t* qAlpha, uint32_t* cntAlpha, DevStats* stats, int refillThreshold,
+                                                                       int postponeShift)
 {
-  stageSrgbLut(S.lutSrgb);
   const uint32_t count = *cntIn;
   TravState      T;
   uint2          stack[TravState::kStackSize];
   Cand           cand[kCand];
   int            path = -1;
-  int            phase = 0;        // 0: opaque tree, 1: alpha (any-hit) tree
-  bool           travDone = false;  // traversal finished, state machine pending
+  int            phase = 0;        // 0: opaque tree, 1: alpha (any-hit) tree, collecting
+  bool           travDone = false;  // traversal finished, write-out pending
   TraceHit       ho;
-  uint32_t       seed = 0, seedIn = 0;
   float          tmaxRay = 0.f;
   ho.slot = 0xFFFFFFFFu;
   for(;;)
   {
     __syncwarp();
-    // ---- state machine for lanes whose traversal completed ----
     if(path >= 0 && travDone)
     {
       travDone = false;
       T.flushCounters(&stats->nodesVisited, &stats->trisTested);
-      TraceHit res;
-      bool     done = false;
       if(phase == 0)
-      {
         ho = T.result();
-        if(S.hasAlpha)
-        {
-          // non-opaque candidates nearer than the opaque hit, front to back (raytracer_interface.h.slang:82-112)
-          phase = 1;
-          T.init(S.bvhAlpha, T.org, T.dir, 0.0f, (ho.slot != 0xFFFFFFFFu) ? ho.t : tmaxRay, true, false, false, 0.f, 0u, true);
-        }
-        else
-        {
-          res = ho;
-          done = true;
-        }
+      if(phase == 0 && S.hasAlpha)
+      {
+        // non-opaque candidates nearer than the opaque hit (raytracer_interface.h.slang:82-112)
+        phase = 1;
+        T.init(S.bvhAlpha, T.org, T.dir, 0.0f, (ho.slot != 0xFFFFFFFFu) ? ho.t : tmaxRay, true, false, false, 0.f, 0u, true);
       }
       else
       {
-        // the collected candidates, nearest first: one rand() each until one passes its alpha test
-        const int n = T.collectN;
-        for(int i = 0; i < n && !done; i++)
+        P.hit[path] = f4(ho.t, ho.u, ho.v, __uint_as_float(ho.slot));
+        const int n = (phase == 1) ? T.collectN : 0;
+        if(n > 0)
         {
-          const Cand                c = cand[i];
-          const uint2               meta = S.triMeta[c.slot];
-          const bool                flip = ((meta.x >> 28) & TRI_FLIPPED) != 0;  // mirrored instance: (u, v) swap back
-          const float               cu = flip ? c.v : c.u, cv = flip ? c.u : c.v;
-          const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
-          const float               opacity = getOpacity(S, node, S.prims[node.renderPrimID], meta.y, f3(1.0f - cu - cv, cu, cv));
-          if(rnd(seed) <= opacity)
-          {
-            res.t = c.t;
-            res.u = cu;
-            res.v = cv;
-            res.slot = c.slot;
-            done = true;
-          }
+          for(int i = 0; i < n; i++)
+            P.cand[i][path] = f4(cand[i].t, cand[i].u, cand[i].v, __uint_as_float(cand[i].slot));
+          P.candInfo[path] = make_uint2((uint32_t)n, cand[n - 1].gid);
+          queuePush(qAlpha, cntAlpha, (uint32_t)path);
         }
-        if(!done)
-        {
-          if(n == kCand)
-            T.init(S.bvhAlpha, T.org, T.dir, 0.0f, T.tmax, true, false, true, cand[kCand - 1].t, cand[kCand - 1].gid, true);
-          else
-          {
-            res = ho;
-            done = true;
-          }
-        }
-      }
-      if(done)
-      {
-        P.hit[path] = f4(res.t, res.u, res.v, __uint_as_float(res.slot));
-        if(seed != seedIn)
-          reinterpret_cast<uint32_t*>(&P.misc[path])[3] = seed;
         path = -1;
       }
     }
@@ -273,8 +239,6 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_trace(PathState
           const float4 o = P.rayO[path];
           const float4 d = P.rayD[path];
           tmaxRay = d.w;
-          if(S.hasAlpha)
-            seed = seedIn = __float_as_uint(P.misc[path].w);
           phase = 0;
           T.init(S.bvh, xyz(o), xyz(d), 0.0f, tmaxRay, true, false, false, 0.f, 0u);
         }
@@ -306,12 +270,177 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_trace(PathState
     atomicAdd(&stats->closestRays, (unsigned long long)count);
 }
 
+// Any-hit part of IRaytracer::Trace (SHADOW = false) and IRaytracer::TraceShadow (SHADOW = true): the candidates
+// the geometry kernel collected, nearest first, one rand() each (raytracer_interface.h.slang:82-112, 149-179, with
+// the order pinned to (t, triangle id)).
+//   Trace:       the first candidate that passes its alpha test replaces the opaque hit.
+//   TraceShadow: every candidate that passes multiplies the transmission (0 for MASK / opaque-ish materials);
+//                the result is folded into the path's pending NEE contribution.
+// Eight lanes per path: lane j evaluates the opacity of candidate j (the texture fetches -- the long latency chain
+// -- run in parallel), then all eight replay the same sequential decisions and lane 0 writes.  A path whose kCand
+// candidates are used up keeps walking the alpha tree kCand at a time right here (rare).
+template <bool SHADOW>
+__global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn)
+{
+  static_assert(kCand == 8, "eight lanes per path");
+  stageSrgbLut(S.lutSrgb);
+  const uint32_t count = *cntIn;
+  const int      lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3, base = lane & ~7;
+  const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
+  const uint32_t warpId = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  for(uint32_t k0 = warpId * 4u; k0 < count; k0 += warpsTotal * 4u)  // warp-uniform trip count
+  {
+    const uint32_t k = k0 + (uint32_t)grp;
+    const bool     valid = k < count;
+    uint32_t       path = 0;
+    uint2          info = make_uint2(0u, 0u);
+    if(valid)
+    {
+      path = q[k];
+      info = P.candInfo[path];
+    }
+    const int n = (int)(info.x & 0xffu);
+    // ---- lane j: candidate j and its opacity ----
+    float    ct = 0.f, cu = 0.f, cv = 0.f, op = 0.f;
+    uint32_t slot = 0;
+    if(sub < n)
+    {
+      const float4 c = P.cand[sub][path];
+      slot = __float_as_uint(c.w);
+      const uint2               meta = S.triMeta[slot];
+      const bool                flip = ((meta.x >> 28) & TRI_FLIPPED) != 0;  // mirrored instance: (u, v) swap back
+      const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
+      ct = c.x;
+      cu = flip ? c.z : c.y;
+      cv = flip ? c.y : c.z;
+      op = getOpacity(S, node, S.prims[node.renderPrimID], meta.y, f3(1.0f - cu - cv, cu, cv));
+    }
+    const uint32_t seedIn = valid ? __float_as_uint(P.misc[path].w) : 0u;
+    uint32_t       seed = seedIn;
+    if(!SHADOW)
+    {
+      int acc = -1;
+#pragma unroll
+      for(int i = 0; i < kCand; i++)
+      {
+        const float oi = __shfl_sync(0xffffffffu, op, base + i);
+        if(i < n && acc < 0 && rnd(seed) <= oi)
+          acc = i;
+      }
+      if(acc >= 0 && sub == acc)
+        P.hit[path] = f4(ct, cu, cv, __uint_as_float(slot));
+      const float    lastT = __shfl_sync(0xffffffffu, ct, base + kCand - 1);
+      if(acc < 0 && n == kCand)
+      {
+        // every collected candidate was rejected and there may be more: keep walking, kCand at a time
+        // (the eight lanes of the group do this redundantly, lane 0 writes)
+        const float4 o = P.rayO[path], d = P.rayD[path], ho = P.hit[path];
+        const float  tmax = (__float_as_uint(ho.w) != 0xFFFFFFFFu) ? ho.x : d.w;
+        float        loT = lastT;
+        uint32_t     loId = info.y;
+        Cand         cand[kCand];
+        bool         accepted = false;
+        for(;;)
+        {
+          const int m = collectNext(S.bvhAlpha, xyz(o), xyz(d), tmax, true, true, loT, loId, cand);
+          for(int i = 0; i < m && !accepted; i++)
+          {
+            const uint2               meta = S.triMeta[cand[i].slot];
+            const bool                flip = ((meta.x >> 28) & TRI_FLIPPED) != 0;
+            const float               u = flip ? cand[i].v : cand[i].u, v = flip ? cand[i].u : cand[i].v;
+            const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
+            const float               opacity = getOpacity(S, node, S.prims[node.renderPrimID], meta.y, f3(1.0f - u - v, u, v));
+            if(rnd(seed) <= opacity)
+            {
+              if(sub == 0)
+                P.hit[path] = f4(cand[i].t, u, v, __uint_as_float(cand[i].slot));
+              accepted = true;
+            }
+          }
+          if(accepted || m < kCand)
+            break;
+          loT = cand[kCand - 1].t;
+          loId = cand[kCand - 1].gid;
+        }
+      }
+    }
+    else
+    {
+      float3       total = f3(1.0f);
+      bool         done = false;
+      const float4 misc = valid ? P.misc[path] : f4(0, 0, 0, 0);
+      bool         isInside = (__float_as_uint(misc.z) & PF_SHADOW_INSIDE) != 0;
+      float        prevHitT = 0.f;
+      const float3 dir = valid ? xyz(P.shD[path]) : f3(0, 0, 1);
+      auto         accept = [&](uint32_t sl, float t, float u, float v) {
+        const uint2               meta = S.triMeta[sl];
+        const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
+        const float               seg = fmaxf(0.0f, t - prevHitT);
+        const float3              cur = getShadowTransmission(S, node, S.prims[node.renderPrimID], meta.y, f3(1.0f - u - v, u, v), seg, dir, isInside);
+        prevHitT = t;
+        total *= cur;
+        if(maxc(total) <= 0.01f)
+        {
+          total = f3(0.0f);
+          done = true;
+        }
+      };
+#pragma unroll
+      for(int i = 0; i < kCand; i++)
+      {
+        const float    oi = __shfl_sync(0xffffffffu, op, base + i);
+        const float    ti = __shfl_sync(0xffffffffu, ct, base + i);
+        const float    ui = __shfl_sync(0xffffffffu, cu, base + i);
+        const float    vi = __shfl_sync(0xffffffffu, cv, base + i);
+        const uint32_t si = __shfl_sync(0xffffffffu, slot, base + i);
+        if(i < n && !done && rnd(seed) < oi)
+          accept(si, ti, ui, vi);
+      }
+      const float lastT = __shfl_sync(0xffffffffu, ct, base + kCand - 1);
+      if(!done && n == kCand)
+      {
+        // more than kCand layers on the segment: keep walking, kCand at a time (rare)
+        const float4 so = P.shO[path];
+        float        loT = lastT;
+        uint32_t     loId = info.y;
+        Cand         cand[kCand];
+        while(!done)
+        {
+          const int m = collectNext(S.bvhAlpha, xyz(so), dir, so.w, false, true, loT, loId, cand);
+          for(int i = 0; i < m && !done; i++)
+          {
+            const uint2               meta = S.triMeta[cand[i].slot];
+            const bool                flip = ((meta.x >> 28) & TRI_FLIPPED) != 0;
+            const float               u = flip ? cand[i].v : cand[i].u, v = flip ? cand[i].u : cand[i].v;
+            const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
+            const float               opacity = getOpacity(S, node, S.prims[node.renderPrimID], meta.y, f3(1.0f - u - v, u, v));
+            if(rnd(seed) < opacity)
+              accept(cand[i].slot, cand[i].t, u, v);
+          }
+          if(m < kCand)
+            break;
+          loT = cand[kCand - 1].t;
+          loId = cand[kCand - 1].gid;
+        }
+      }
+      if(valid && sub == 0)
+      {
+        const float4 c = P.shC[path];
+        P.shC[path] = f4(xyz(c) * total, c.w);
+      }
+    }
+    if(valid && sub == 0 && seed != seedIn)
+      reinterpret_cast<uint32_t*>(&P.misc[path])[3] = seed;
+  }
+}
+
 #ifndef SHADE_MIN_BLOCKS
 #define SHADE_MIN_BLOCKS 4  // measured on B200: 3 -> 1.165 ms, 4 -> 1.017, 5 -> 1.029, 6 -> 1.064 per launch
 #endif
 template <uint32_t FEAT>
 __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(PathState P, DevScene S, const __grid_constant__ FrameParams F, const uint32_t* __restrict__ q,
-                                               const uint32_t* __restrict__ cntIn, uint32_t* qPost, uint32_t* cntPost, uint32_t* qNext, uint32_t* cntNext, DevStats* stats)
+                                               const uint32_t* __restrict__ cntIn, uint32_t* qPost, uint32_t* cntPost, uint32_t* qShadow, uint32_t* cntShadow,
+                                                                 uint32_t* qNext, uint32_t* cntNext, DevStats* stats)
 {
   stageSrgbLut(S.lutSrgb);
   const uint32_t count = *cntIn;
@@ -458,6 +587,8 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(PathState P, De
           P.rad[i] = f4(radiance, __uint_as_float(scatterBounces));
           P.misc[i] = f4(misc.x, misc.y, __uint_as_float(flags), __uint_as_float(seed));
           queuePush(qPost, cntPost, i);
+          if(flags & PF_SHADOW_VALID)
+            queuePush(qShadow, cntShadow, i);
           continue;
         }
       }
@@ -536,6 +667,8 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(PathState P, De
     P.misc[i] = f4(misc.x, misc.y, __uint_as_float(flags), __uint_as_float(seed));
     P.medium[i] = med;
     queuePush(qPost, cntPost, i);
+    if(flags & PF_SHADOW_VALID)
+      queuePush(qShadow, cntShadow, i);
   }
 }
 
@@ -604,96 +737,52 @@ __device__ void finishPost(const PathState& P, const FrameParams& F, uint32_t i,
   queuePush(qNext, cntNext, i);
 }
 
-__global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_post(PathState P, DevScene S, const __grid_constant__ FrameParams F, const uint32_t* __restrict__ q,
-                                              const uint32_t* __restrict__ cntIn, uint32_t* workCounter, uint32_t* qNext, uint32_t* cntNext, DevStats* stats,
-                                              int refillThreshold, int postponeShift)
+// IRaytracer::TraceShadow, geometry part, for every path with a pending NEE shadow ray: any FORCE_OPAQUE occluder
+// ends the query (raytracer_interface.h.slang:181-184), otherwise the kCand nearest non-opaque candidates are
+// written out for k_resolve.  Same persistent-warp scheme as k_trace.
+__global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn,
+                                                                        uint32_t* workCounter, uint32_t* qAlpha, uint32_t* cntAlpha, DevStats* stats,
+                                                                        int refillThreshold, int postponeShift)
 {
-  stageSrgbLut(S.lutSrgb);
   const uint32_t count = *cntIn;
   TravState      T;
   uint2          stack[TravState::kStackSize];
   Cand           cand[kCand];
   int            path = -1;  // -1: lane needs work, -2: queue exhausted
-  int            phase = 0;  // 0: opaque occlusion query, 1: any-hit candidates front to back
+  int            phase = 0;  // 0: opaque occlusion query, 1: any-hit candidates, collecting
   bool           travDone = false;
-  uint32_t       flags = 0, seed = 0;
-  float3         total = f3(1.0f);
-  bool           isInside = false;
-  float          prevHitT = 0.f;
   for(;;)
   {
     __syncwarp();
-    // ---- state machine for lanes whose shadow traversal completed (converged code) ----
     if(path >= 0 && travDone)
     {
       travDone = false;
       T.flushCounters(&stats->nodesVisited, &stats->trisTested);
-      bool done = false;
-      if(phase == 0)
+      if(phase == 0 && T.best.slot == 0xFFFFFFFFu && S.hasAlpha)
       {
-        if(T.best.slot != 0xFFFFFFFFu)
-        {
-          total = f3(0.0f);
-          done = true;
-        }
-        else if(S.hasAlpha)
-        {
-          phase = 1;
-          T.init(S.bvhAlpha, T.org, T.dir, 0.0f, T.tmax, false, false, false, 0.f, 0u, true);
-        }
-        else
-          done = true;
+        phase = 1;
+        T.init(S.bvhAlpha, T.org, T.dir, 0.0f, T.tmax, false, false, false, 0.f, 0u, true);
       }
       else
       {
-        // 2. every non-opaque candidate, front to back (raytracer_interface.h.slang:149-179)
-        const int n = T.collectN;
-        for(int i = 0; i < n && !done; i++)
+        uint2 info = make_uint2(0u, 0u);
+        if(phase == 0)
+          info.x = (T.best.slot != 0xFFFFFFFFu) ? 0x80000000u : 0u;
+        else
         {
-          const Cand                c = cand[i];
-          const uint2               meta = S.triMeta[c.slot];
-          const bool                flip = ((meta.x >> 28) & TRI_FLIPPED) != 0;
-          const float               cu = flip ? c.v : c.u, cv = flip ? c.u : c.v;
-          const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
-          const DevPrim&            prim = S.prims[node.renderPrimID];
-          const float3              bary = f3(1.0f - cu - cv, cu, cv);
-          const float               opacity = getOpacity(S, node, prim, meta.y, bary);
-          const float               r = rnd(seed);
-          if(r < opacity)
-          {
-            const float  seg = fmaxf(0.0f, c.t - prevHitT);
-            const float3 cur = getShadowTransmission(S, node, prim, meta.y, bary, seg, T.dir, isInside);
-            prevHitT = c.t;
-            total *= cur;
-            if(maxc(total) <= 0.01f)
-            {
-              total = f3(0.0f);
-              done = true;
-            }
-          }
+          const int n = T.collectN;
+          for(int i = 0; i < n; i++)
+            P.cand[i][path] = f4(cand[i].t, cand[i].u, cand[i].v, __uint_as_float(cand[i].slot));
+          info = make_uint2((uint32_t)n, n > 0 ? cand[n - 1].gid : 0u);
         }
-        if(!done)
-        {
-          if(n == kCand)
-            T.init(S.bvhAlpha, T.org, T.dir, 0.0f, T.tmax, false, false, true, cand[kCand - 1].t, cand[kCand - 1].gid, true);
-          else
-            done = true;
-        }
-      }
-      if(done)
-      {
-#ifdef B200PT_DEBUG
-        if((float)((uint32_t)path % (uint32_t)F.width) == F.pc.mouseCoord[0] && (float)pixelRow(F, (uint32_t)path) == F.pc.mouseCoord[1])
-          printf("DBG shadow o=%.9g %.9g %.9g d=%.9g %.9g %.9g tmax=%.9g T=%.9g %.9g %.9g\n", T.org.x, T.org.y, T.org.z, T.dir.x, T.dir.y, T.dir.z, T.tmax, total.x, total.y, total.z);
-#endif
-        finishPost(P, F, (uint32_t)path, flags, seed, true, total, qNext, cntNext, stats);
+        P.candInfo[path] = info;
+        if(info.x != 0u && info.x != 0x80000000u)
+          queuePush(qAlpha, cntAlpha, (uint32_t)path);
         path = -1;
       }
     }
-    // ---- refill: paths without a shadow ray are finished on the spot and the lane fetches again ----
-    for(;;)
+    __syncwarp();
     {
-      __syncwarp();
       const bool     need = (path == -1);
       const uint32_t k = fetchWork(need, workCounter, count);
       if(need)
@@ -703,30 +792,12 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_post(PathState 
         else
         {
           path = (int)q[k];
-          const float4 misc = P.misc[path];
-          flags = __float_as_uint(misc.z);
-          seed = __float_as_uint(misc.w);
-          if(!(flags & PF_SHADOW_VALID))
-          {
-            finishPost(P, F, (uint32_t)path, flags, seed, false, f3(1.0f), qNext, cntNext, stats);
-            path = -1;
-          }
-          else
-          {
-            const float4 so = P.shO[path];
-            const float4 sd = P.shD[path];
-            statAdd(&stats->shadowRays, 1ull);
-            phase = 0;
-            total = f3(1.0f);
-            isInside = (flags & PF_SHADOW_INSIDE) != 0;
-            prevHitT = 0.f;
-            // 1. any FORCE_OPAQUE occluder ends the query (raytracer_interface.h.slang:181-184)
-            T.init(S.bvh, xyz(so), xyz(sd), 0.0f, so.w, false, true, false, 0.f, 0u);
-          }
+          const float4 so = P.shO[path];
+          const float4 sd = P.shD[path];
+          phase = 0;
+          T.init(S.bvh, xyz(so), xyz(sd), 0.0f, so.w, false, true, false, 0.f, 0u);
         }
       }
-      if(!__any_sync(0xffffffffu, path == -1))
-        break;
     }
     if(__all_sync(0xffffffffu, path == -2))
       break;
@@ -747,6 +818,34 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_post(PathState 
       if(__popc(__ballot_sync(0xffffffffu, path >= 0 && !travDone)) < refillThreshold)
         break;
     }
+  }
+  if(blockIdx.x == 0 && threadIdx.x == 0)
+    atomicAdd(&stats->shadowRays, (unsigned long long)count);
+}
+
+// pathTrace() tail for every path that survived shading (gltf_pathtrace.slang:462-485), one thread per path: the
+// delayed NEE contribution (already scaled by the any-hit transmission in k_alpha<true>; an opaque occluder
+// zeroes it here), Russian roulette and depth++ in finishPost.
+__global__ void __launch_bounds__(256) k_resolve(PathState P, const __grid_constant__ FrameParams F, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn,
+                                                 uint32_t* qNext, uint32_t* cntNext, DevStats* stats)
+{
+  const uint32_t count = *cntIn;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for(uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
+  {
+    const uint32_t path = q[k];
+    const float4   misc = P.misc[path];
+    const uint32_t flags = __float_as_uint(misc.z);
+    const uint32_t seed = __float_as_uint(misc.w);
+    const bool     haveShadow = (flags & PF_SHADOW_VALID) != 0;
+    float3         vis = f3(1.0f);
+    if(haveShadow && (P.candInfo[path].x & 0x80000000u))
+      vis = f3(0.0f);
+#ifdef B200PT_DEBUG
+    if(haveShadow && (float)(path % (uint32_t)F.width) == F.pc.mouseCoord[0] && (float)pixelRow(F, path) == F.pc.mouseCoord[1])
+      printf("DBG shadow occluded=%d\n", (int)(vis.x == 0.0f));
+#endif
+    finishPost(P, F, path, flags, seed, haveShadow, vis, qNext, cntNext, stats);
   }
 }
 
@@ -935,7 +1034,7 @@ struct b200pt
   {
     cudaStream_t stream = nullptr;
     PathState    P{};
-    uint32_t*    dQ[3] = {nullptr, nullptr, nullptr};
+    uint32_t*    dQ[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // trace ping/pong, post, shadow, alpha
     uint32_t*    dCounters = nullptr;
     uint32_t*    hCount = nullptr;   // pinned
     cudaEvent_t  done = nullptr;     // lane stream: all bounces of the lane's frame enqueued before it
@@ -1181,7 +1280,7 @@ int b200pt_create(b200pt_t** out, int cuda_device)
     cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&L.freed, cudaEventDisableTiming);
-    cudaMalloc((void**)&L.dCounters, sizeof(uint32_t) * 4 * kMaxIters);
+    cudaMalloc((void**)&L.dCounters, sizeof(uint32_t) * 7 * kMaxIters);
     cudaMallocHost((void**)&L.hCount, sizeof(uint32_t) * 4);
   }
   {
@@ -1655,9 +1754,13 @@ int b200pt_resize(b200pt_t* h, int width, int height, int tile_y0, int tile_rows
     rc |= alloc16((void**)&L.P.shO);
     rc |= alloc16((void**)&L.P.shD);
     rc |= alloc16((void**)&L.P.shC);
+    for(int k = 0; k < kCand; k++)
+      rc |= alloc16((void**)&L.P.cand[k]);
     if(rc)
       return B200PT_E_NOMEM;
-    for(int k = 0; k < 3; k++)
+    CK(cudaMalloc((void**)&L.P.candInfo, n * sizeof(uint2)));
+    h->poolAllocs.push_back(L.P.candInfo);
+    for(int k = 0; k < 5; k++)
     {
       CK(cudaMalloc((void**)&L.dQ[k], n * sizeof(uint32_t)));
       h->poolAllocs.push_back(L.dQ[k]);
@@ -1855,7 +1958,10 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
   uint32_t*    cntPost = L.dCounters + kMaxIters;  // [kMaxIters]
   uint32_t*    workTrace = L.dCounters + 2 * kMaxIters;  // dynamic-fetch cursors of the persistent kernels
   uint32_t*    workPost = L.dCounters + 3 * kMaxIters;
-  CK(cudaMemsetAsync(L.dCounters, 0, sizeof(uint32_t) * 4 * kMaxIters, st));
+  uint32_t*    cntShadow = L.dCounters + 4 * kMaxIters;
+  uint32_t*    cntAlpha = L.dCounters + 5 * kMaxIters;
+  uint32_t*    cntAlphaS = L.dCounters + 6 * kMaxIters;
+  CK(cudaMemsetAsync(L.dCounters, 0, sizeof(uint32_t) * 7 * kMaxIters, st));
 
   enum
   {
@@ -1896,14 +2002,27 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
       {
         uint32_t* qT = L.dQ[cur];
         uint32_t* qN = L.dQ[1 - cur];
-        timed(tTrace, [&] { k_trace<<<gridFor(h, 8), 128, 1024, st>>>(L.P, h->S, qT, &cntTrace[it], &workTrace[it], h->dStats, h->refillThreshold, h->postponeShift); });
+        // geometry walks are persistent kernels; the texture-dependent any-hit tests and the path bookkeeping run
+        // as dense one-thread-per-path kernels (k_alpha, k_resolve) sized by the device-side queue counters
+        timed(tTrace, [&] {
+          k_trace<<<gridFor(h, 8), 128, 0, st>>>(L.P, h->S, qT, &cntTrace[it], &workTrace[it], L.dQ[4], &cntAlpha[it], h->dStats, h->refillThreshold, h->postponeShift);
+          if(h->S.hasAlpha)
+            k_alpha<false><<<gridFor(h, 8), 128, 1024, st>>>(L.P, h->S, L.dQ[4], &cntAlpha[it]);
+        });
         timed(tShade, [&] {
           if(h->leanShade)
-            k_shade<FEAT_LEAN><<<gridFor(h, 8), 128, 1024, st>>>(L.P, h->S, F, qT, &cntTrace[it], L.dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats);
+            k_shade<FEAT_LEAN><<<gridFor(h, 8), 128, 1024, st>>>(L.P, h->S, F, qT, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
           else
-            k_shade<FEAT_ALL><<<gridFor(h, 8), 128, 1024, st>>>(L.P, h->S, F, qT, &cntTrace[it], L.dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats);
+            k_shade<FEAT_ALL><<<gridFor(h, 8), 128, 1024, st>>>(L.P, h->S, F, qT, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
         });
-        timed(tPost, [&] { k_post<<<gridFor(h, 8), 128, 1024, st>>>(L.P, h->S, F, L.dQ[2], &cntPost[it], &workPost[it], qN, &cntTrace[it + 1], h->dStats, h->refillThreshold, h->postponeShift); });
+        timed(tPost, [&] {
+          k_shadow<<<gridFor(h, 8), 128, 0, st>>>(L.P, h->S, L.dQ[3], &cntShadow[it], &workPost[it], L.dQ[4], &cntAlphaS[it], h->dStats, h->refillThreshold,
+                                                  h->postponeShift);
+          if(h->S.hasAlpha)
+            k_alpha<true><<<gridFor(h, 8), 128, 1024, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS[it]);
+          k_resolve<<<gridFor(h, 4), 256, 0, st>>>(L.P, F, L.dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats);
+        });
+        h->kernelLaunches += h->S.hasAlpha ? 3 : 1;  // timed() counts one launch per stage
         cur = 1 - cur;
       }
       if(!mayOverrun)

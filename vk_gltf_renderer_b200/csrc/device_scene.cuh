@@ -13,6 +13,10 @@
 #include "../../include/b200pt.h"
 #include "traverse.cuh"
 
+#ifndef B200PT_KCAND
+#define B200PT_KCAND 8  // any-hit candidates kept per tree walk (traverse.cuh)
+#endif
+
 namespace pt {
 
 struct DevPrim
@@ -95,6 +99,11 @@ struct PathState
   float4*   shO;     // shadow ray origin.xyz | tmax
   float4*   shD;     // shadow ray direction.xyz | unused
   float4*   shC;     // NEE contribution.xyz | unused
+  // any-hit candidates of the ray last traced for the path (closest-hit ray, then the shadow ray): up to B200PT_KCAND
+  // nearest non-opaque hits as t | u | v | triangle slot, written by the traversal kernels and consumed by the
+  // dense alpha / resolve kernels
+  float4*   cand[B200PT_KCAND];
+  uint2*    candInfo;  // x: count (bit 31: an opaque occluder ended the shadow query) | y: global id of the last candidate
 };
 
 // flags word in misc.z

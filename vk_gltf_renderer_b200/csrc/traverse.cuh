@@ -27,7 +27,7 @@ struct Cand
   uint32_t slot, gid;
 };
 #ifndef B200PT_KCAND
-#define B200PT_KCAND 4
+#define B200PT_KCAND 8
 #endif
 constexpr int kCand = B200PT_KCAND;
 
@@ -337,6 +337,18 @@ struct TravState
 #endif
   }
 };
+
+// one collecting walk to completion: the up-to-kCand nearest hits after the lower bound, sorted, in `cand`
+PT_D int collectNext(const BvhView bvh, float3 org, float3 dir, float tmax, bool cull, bool haveLo, float loT, uint32_t loId, Cand* __restrict__ cand)
+{
+  TravState T;
+  uint2     stack[TravState::kStackSize];
+  T.init(bvh, org, dir, 0.0f, tmax, cull, false, haveLo, loT, loId, true);
+  while(!T.step(stack, 2, cand))
+  {
+  }
+  return T.collectN;
+}
 
 // run one traversal to completion (ray-level API kernels and the any-hit restart loops)
 template <bool CULL, bool ANY_EXIT>
