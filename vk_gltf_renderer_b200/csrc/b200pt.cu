@@ -183,8 +183,10 @@ __device__ __forceinline__ uint32_t fetchWork(bool need, uint32_t* workCounter, 
 #endif
 __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_trace(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn,
                                                                        uint32_t* workCounter, uint32_t* qAlpha, uint32_t* cntAlpha, DevStats* stats, int refillThreshold,
-                                                                       int postponeShift)
+                                                                       int postponeShift, int cont)
 {
+  // cont != 0: continuation round -- the paths in the queue had all kCand candidates rejected by k_alpha and
+  // resume the any-hit walk behind the last one (P.hit keeps the opaque hit, which still bounds the walk)
   const uint32_t count = *cntIn;
   TravState      T;
   uint2          stack[TravState::kStackSize];
@@ -212,7 +214,8 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_trace(PathState
       }
       else
       {
-        P.hit[path] = f4(ho.t, ho.u, ho.v, __uint_as_float(ho.slot));
+        if(!cont)
+          P.hit[path] = f4(ho.t, ho.u, ho.v, __uint_as_float(ho.slot));
         const int n = (phase == 1) ? T.collectN : 0;
         if(n > 0)
         {
@@ -239,8 +242,18 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_trace(PathState
           const float4 o = P.rayO[path];
           const float4 d = P.rayD[path];
           tmaxRay = d.w;
-          phase = 0;
-          T.init(S.bvh, xyz(o), xyz(d), 0.0f, tmaxRay, true, false, false, 0.f, 0u);
+          if(!cont)
+          {
+            phase = 0;
+            T.init(S.bvh, xyz(o), xyz(d), 0.0f, tmaxRay, true, false, false, 0.f, 0u);
+          }
+          else
+          {
+            const float4 hp = P.hit[path];
+            phase = 1;
+            T.init(S.bvhAlpha, xyz(o), xyz(d), 0.0f, (__float_as_uint(hp.w) != 0xFFFFFFFFu) ? hp.x : tmaxRay, true, false, true, P.cand[kCand - 1][path].x,
+                   P.candInfo[path].y, true);
+          }
         }
       }
     }
@@ -266,7 +279,7 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_trace(PathState
         break;
     }
   }
-  if(blockIdx.x == 0 && threadIdx.x == 0)
+  if(blockIdx.x == 0 && threadIdx.x == 0 && !cont)
     atomicAdd(&stats->closestRays, (unsigned long long)count);
 }
 
@@ -276,19 +289,22 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_trace(PathState
 //   Trace:       the first candidate that passes its alpha test replaces the opaque hit.
 //   TraceShadow: every candidate that passes multiplies the transmission (0 for MASK / opaque-ish materials);
 //                the result is folded into the path's pending NEE contribution.
-// Eight lanes per path: lane j evaluates the opacity of candidate j (the texture fetches -- the long latency chain
-// -- run in parallel), then all eight replay the same sequential decisions and lane 0 writes.  A path whose kCand
-// candidates are used up keeps walking the alpha tree kCand at a time right here (rare).
+// kCand lanes per path: lane j evaluates the opacity of candidate j (the texture fetches -- the long latency chain
+// -- run in parallel), then all of them replay the same sequential decisions and lane 0 writes.  A path whose
+// kCand candidates are used up goes to the continuation queue (another k_trace / k_shadow round resumes the walk
+// behind the last candidate); in the last round (qCont == nullptr) it keeps walking right here instead.
 template <bool SHADOW>
-__global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn)
+__global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn, uint32_t* qCont,
+                                               uint32_t* cntCont, int cont)
 {
-  static_assert(kCand == 8, "eight lanes per path");
+  static_assert(kCand == 4 || kCand == 8, "kCand lanes per path");
   stageSrgbLut(S.lutSrgb);
   const uint32_t count = *cntIn;
-  const int      lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3, base = lane & ~7;
+  constexpr int  G = kCand, PPW = 32 / kCand;  // lanes per path, paths per warp
+  const int      lane = threadIdx.x & 31, sub = lane % G, grp = lane / G, base = lane - sub;
   const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
   const uint32_t warpId = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  for(uint32_t k0 = warpId * 4u; k0 < count; k0 += warpsTotal * 4u)  // warp-uniform trip count
+  for(uint32_t k0 = warpId * (uint32_t)PPW; k0 < count; k0 += warpsTotal * (uint32_t)PPW)  // warp-uniform trip count
   {
     const uint32_t k = k0 + (uint32_t)grp;
     const bool     valid = k < count;
@@ -330,10 +346,15 @@ __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const ui
       if(acc >= 0 && sub == acc)
         P.hit[path] = f4(ct, cu, cv, __uint_as_float(slot));
       const float    lastT = __shfl_sync(0xffffffffu, ct, base + kCand - 1);
-      if(acc < 0 && n == kCand)
+      if(acc < 0 && n == kCand && qCont != nullptr)
+      {
+        if(sub == 0)
+          queuePush(qCont, cntCont, path);
+      }
+      else if(acc < 0 && n == kCand)
       {
         // every collected candidate was rejected and there may be more: keep walking, kCand at a time
-        // (the eight lanes of the group do this redundantly, lane 0 writes)
+        // (the lanes of the group do this redundantly, lane 0 writes)
         const float4 o = P.rayO[path], d = P.rayD[path], ho = P.hit[path];
         const float  tmax = (__float_as_uint(ho.w) != 0xFFFFFFFFu) ? ho.x : d.w;
         float        loT = lastT;
@@ -366,11 +387,14 @@ __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const ui
     }
     else
     {
-      float3       total = f3(1.0f);
-      bool         done = false;
+      // a continuation round resumes with the running transmission and segment start the previous round parked
+      // in P.hit (free between shading and the next k_trace)
+      const float4 saved = (valid && cont) ? P.hit[path] : f4(1.0f, 1.0f, 1.0f, 0.0f);
+      float3       total = xyz(saved);
+      float        prevHitT = saved.w;
+      bool         done = false, parked = false;
       const float4 misc = valid ? P.misc[path] : f4(0, 0, 0, 0);
       bool         isInside = (__float_as_uint(misc.z) & PF_SHADOW_INSIDE) != 0;
-      float        prevHitT = 0.f;
       const float3 dir = valid ? xyz(P.shD[path]) : f3(0, 0, 1);
       auto         accept = [&](uint32_t sl, float t, float u, float v) {
         const uint2               meta = S.triMeta[sl];
@@ -397,7 +421,18 @@ __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const ui
           accept(si, ti, ui, vi);
       }
       const float lastT = __shfl_sync(0xffffffffu, ct, base + kCand - 1);
-      if(!done && n == kCand)
+      if(!done && n == kCand && qCont != nullptr)
+      {
+        parked = true;
+        if(sub == 0)
+        {
+          P.hit[path] = f4(total, prevHitT);
+          const uint32_t fl = (__float_as_uint(misc.z) & ~PF_SHADOW_INSIDE) | (isInside ? PF_SHADOW_INSIDE : 0u);
+          reinterpret_cast<uint32_t*>(&P.misc[path])[2] = fl;
+          queuePush(qCont, cntCont, path);
+        }
+      }
+      else if(!done && n == kCand)
       {
         // more than kCand layers on the segment: keep walking, kCand at a time (rare)
         const float4 so = P.shO[path];
@@ -423,7 +458,7 @@ __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const ui
           loId = cand[kCand - 1].gid;
         }
       }
-      if(valid && sub == 0)
+      if(valid && sub == 0 && !parked)
       {
         const float4 c = P.shC[path];
         P.shC[path] = f4(xyz(c) * total, c.w);
@@ -742,7 +777,7 @@ __device__ void finishPost(const PathState& P, const FrameParams& F, uint32_t i,
 // written out for k_resolve.  Same persistent-warp scheme as k_trace.
 __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn,
                                                                         uint32_t* workCounter, uint32_t* qAlpha, uint32_t* cntAlpha, DevStats* stats,
-                                                                        int refillThreshold, int postponeShift)
+                                                                        int refillThreshold, int postponeShift, int cont)
 {
   const uint32_t count = *cntIn;
   TravState      T;
@@ -776,7 +811,8 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathStat
           info = make_uint2((uint32_t)n, n > 0 ? cand[n - 1].gid : 0u);
         }
         P.candInfo[path] = info;
-        if(info.x != 0u && info.x != 0x80000000u)
+        // (a continuation path always goes back to k_alpha: its running transmission is parked and must be folded)
+        if((info.x != 0u && info.x != 0x80000000u) || cont)
           queuePush(qAlpha, cntAlpha, (uint32_t)path);
         path = -1;
       }
@@ -794,8 +830,16 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathStat
           path = (int)q[k];
           const float4 so = P.shO[path];
           const float4 sd = P.shD[path];
-          phase = 0;
-          T.init(S.bvh, xyz(so), xyz(sd), 0.0f, so.w, false, true, false, 0.f, 0u);
+          if(!cont)
+          {
+            phase = 0;
+            T.init(S.bvh, xyz(so), xyz(sd), 0.0f, so.w, false, true, false, 0.f, 0u);
+          }
+          else
+          {
+            phase = 1;
+            T.init(S.bvhAlpha, xyz(so), xyz(sd), 0.0f, so.w, false, false, true, P.cand[kCand - 1][path].x, P.candInfo[path].y, true);
+          }
         }
       }
     }
@@ -819,7 +863,7 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathStat
         break;
     }
   }
-  if(blockIdx.x == 0 && threadIdx.x == 0)
+  if(blockIdx.x == 0 && threadIdx.x == 0 && !cont)
     atomicAdd(&stats->shadowRays, (unsigned long long)count);
 }
 
@@ -1034,7 +1078,7 @@ struct b200pt
   {
     cudaStream_t stream = nullptr;
     PathState    P{};
-    uint32_t*    dQ[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // trace ping/pong, post, shadow, alpha
+    uint32_t*    dQ[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // trace ping/pong, post, shadow, alpha, continuation
     uint32_t*    dCounters = nullptr;
     uint32_t*    hCount = nullptr;   // pinned
     cudaEvent_t  done = nullptr;     // lane stream: all bounces of the lane's frame enqueued before it
@@ -1280,7 +1324,7 @@ int b200pt_create(b200pt_t** out, int cuda_device)
     cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&L.freed, cudaEventDisableTiming);
-    cudaMalloc((void**)&L.dCounters, sizeof(uint32_t) * 7 * kMaxIters);
+    cudaMalloc((void**)&L.dCounters, sizeof(uint32_t) * 13 * kMaxIters);
     cudaMallocHost((void**)&L.hCount, sizeof(uint32_t) * 4);
   }
   {
@@ -1760,7 +1804,7 @@ int b200pt_resize(b200pt_t* h, int width, int height, int tile_y0, int tile_rows
       return B200PT_E_NOMEM;
     CK(cudaMalloc((void**)&L.P.candInfo, n * sizeof(uint2)));
     h->poolAllocs.push_back(L.P.candInfo);
-    for(int k = 0; k < 5; k++)
+    for(int k = 0; k < 6; k++)
     {
       CK(cudaMalloc((void**)&L.dQ[k], n * sizeof(uint32_t)));
       h->poolAllocs.push_back(L.dQ[k]);
@@ -1961,7 +2005,13 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
   uint32_t*    cntShadow = L.dCounters + 4 * kMaxIters;
   uint32_t*    cntAlpha = L.dCounters + 5 * kMaxIters;
   uint32_t*    cntAlphaS = L.dCounters + 6 * kMaxIters;
-  CK(cudaMemsetAsync(L.dCounters, 0, sizeof(uint32_t) * 7 * kMaxIters, st));
+  uint32_t*    cntCont = L.dCounters + 7 * kMaxIters;    // closest rays whose kCand candidates were all rejected
+  uint32_t*    cntAlpha1 = L.dCounters + 8 * kMaxIters;  // ... and their second batch of candidates
+  uint32_t*    cntContS = L.dCounters + 9 * kMaxIters;   // same for shadow rays
+  uint32_t*    cntAlphaS1 = L.dCounters + 10 * kMaxIters;
+  uint32_t*    workCont = L.dCounters + 11 * kMaxIters;
+  uint32_t*    workContS = L.dCounters + 12 * kMaxIters;
+  CK(cudaMemsetAsync(L.dCounters, 0, sizeof(uint32_t) * 13 * kMaxIters, st));
 
   enum
   {
@@ -2004,25 +2054,35 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
         uint32_t* qN = L.dQ[1 - cur];
         // geometry walks are persistent kernels; the texture-dependent any-hit tests and the path bookkeeping run
         // as dense one-thread-per-path kernels (k_alpha, k_resolve) sized by the device-side queue counters
+        const int gP = gridFor(h, 8);
         timed(tTrace, [&] {
-          k_trace<<<gridFor(h, 8), 128, 0, st>>>(L.P, h->S, qT, &cntTrace[it], &workTrace[it], L.dQ[4], &cntAlpha[it], h->dStats, h->refillThreshold, h->postponeShift);
+          k_trace<<<gP, 128, 0, st>>>(L.P, h->S, qT, &cntTrace[it], &workTrace[it], L.dQ[4], &cntAlpha[it], h->dStats, h->refillThreshold, h->postponeShift, 0);
           if(h->S.hasAlpha)
-            k_alpha<false><<<gridFor(h, 8), 128, 1024, st>>>(L.P, h->S, L.dQ[4], &cntAlpha[it]);
+          {
+            // any-hit: resolve kCand candidates, one continuation round for the paths that used them all up, then
+            // whatever is still undecided finishes inside the last k_alpha
+            k_alpha<false><<<gP, 128, 1024, st>>>(L.P, h->S, L.dQ[4], &cntAlpha[it], L.dQ[5], &cntCont[it], 0);
+            k_trace<<<gP, 128, 0, st>>>(L.P, h->S, L.dQ[5], &cntCont[it], &workCont[it], L.dQ[4], &cntAlpha1[it], h->dStats, h->refillThreshold, h->postponeShift, 1);
+            k_alpha<false><<<gP, 128, 1024, st>>>(L.P, h->S, L.dQ[4], &cntAlpha1[it], nullptr, nullptr, 1);
+          }
         });
         timed(tShade, [&] {
           if(h->leanShade)
-            k_shade<FEAT_LEAN><<<gridFor(h, 8), 128, 1024, st>>>(L.P, h->S, F, qT, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
+            k_shade<FEAT_LEAN><<<gP, 128, 1024, st>>>(L.P, h->S, F, qT, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
           else
-            k_shade<FEAT_ALL><<<gridFor(h, 8), 128, 1024, st>>>(L.P, h->S, F, qT, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
+            k_shade<FEAT_ALL><<<gP, 128, 1024, st>>>(L.P, h->S, F, qT, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
         });
         timed(tPost, [&] {
-          k_shadow<<<gridFor(h, 8), 128, 0, st>>>(L.P, h->S, L.dQ[3], &cntShadow[it], &workPost[it], L.dQ[4], &cntAlphaS[it], h->dStats, h->refillThreshold,
-                                                  h->postponeShift);
+          k_shadow<<<gP, 128, 0, st>>>(L.P, h->S, L.dQ[3], &cntShadow[it], &workPost[it], L.dQ[4], &cntAlphaS[it], h->dStats, h->refillThreshold, h->postponeShift, 0);
           if(h->S.hasAlpha)
-            k_alpha<true><<<gridFor(h, 8), 128, 1024, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS[it]);
+          {
+            k_alpha<true><<<gP, 128, 1024, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS[it], L.dQ[5], &cntContS[it], 0);
+            k_shadow<<<gP, 128, 0, st>>>(L.P, h->S, L.dQ[5], &cntContS[it], &workContS[it], L.dQ[4], &cntAlphaS1[it], h->dStats, h->refillThreshold, h->postponeShift, 1);
+            k_alpha<true><<<gP, 128, 1024, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS1[it], nullptr, nullptr, 1);
+          }
           k_resolve<<<gridFor(h, 4), 256, 0, st>>>(L.P, F, L.dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats);
         });
-        h->kernelLaunches += h->S.hasAlpha ? 3 : 1;  // timed() counts one launch per stage
+        h->kernelLaunches += h->S.hasAlpha ? 7 : 1;  // timed() counts one launch per stage
         cur = 1 - cur;
       }
       if(!mayOverrun)

@@ -14,7 +14,7 @@
 #include "traverse.cuh"
 
 #ifndef B200PT_KCAND
-#define B200PT_KCAND 8  // any-hit candidates kept per tree walk (traverse.cuh)
+#define B200PT_KCAND 4  // any-hit candidates kept per tree walk (traverse.cuh); 4 or 8 (k_alpha uses that many lanes per path)
 #endif
 
 namespace pt {

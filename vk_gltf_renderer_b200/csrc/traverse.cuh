@@ -27,7 +27,7 @@ struct Cand
   uint32_t slot, gid;
 };
 #ifndef B200PT_KCAND
-#define B200PT_KCAND 8
+#define B200PT_KCAND 4
 #endif
 constexpr int kCand = B200PT_KCAND;
 
