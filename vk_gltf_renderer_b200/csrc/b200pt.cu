@@ -1328,9 +1328,14 @@ int b200pt_create(b200pt_t** out, int cuda_device)
     cudaMallocHost((void**)&L.hCount, sizeof(uint32_t) * 4);
   }
   {
-    float lutS[256];
+    // [0..255]: sRGB decode; [256..511]: i / 255 (the UNORM decode, tabulated so that texel fetches do no divisions;
+    // same IEEE quotient the kernel's own `(float)i / 255.0f` would produce)
+    float lutS[512];
     for(int i = 0; i < 256; i++)
+    {
       lutS[i] = srgbToLinear((float)i / 255.0f);
+      lutS[256 + i] = (float)i / 255.0f;
+    }
     cudaMalloc((void**)&h->dLutSrgb, sizeof(lutS));
     cudaMemcpy(h->dLutSrgb, lutS, sizeof(lutS), cudaMemcpyHostToDevice);
   }
@@ -2061,24 +2066,24 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
           {
             // any-hit: resolve kCand candidates, one continuation round for the paths that used them all up, then
             // whatever is still undecided finishes inside the last k_alpha
-            k_alpha<false><<<gP, 128, 1024, st>>>(L.P, h->S, L.dQ[4], &cntAlpha[it], L.dQ[5], &cntCont[it], 0);
+            k_alpha<false><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlpha[it], L.dQ[5], &cntCont[it], 0);
             k_trace<<<gP, 128, 0, st>>>(L.P, h->S, L.dQ[5], &cntCont[it], &workCont[it], L.dQ[4], &cntAlpha1[it], h->dStats, h->refillThreshold, h->postponeShift, 1);
-            k_alpha<false><<<gP, 128, 1024, st>>>(L.P, h->S, L.dQ[4], &cntAlpha1[it], nullptr, nullptr, 1);
+            k_alpha<false><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlpha1[it], nullptr, nullptr, 1);
           }
         });
         timed(tShade, [&] {
           if(h->leanShade)
-            k_shade<FEAT_LEAN><<<gP, 128, 1024, st>>>(L.P, h->S, F, qT, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
+            k_shade<FEAT_LEAN><<<gP, 128, 2048, st>>>(L.P, h->S, F, qT, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
           else
-            k_shade<FEAT_ALL><<<gP, 128, 1024, st>>>(L.P, h->S, F, qT, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
+            k_shade<FEAT_ALL><<<gP, 128, 2048, st>>>(L.P, h->S, F, qT, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
         });
         timed(tPost, [&] {
           k_shadow<<<gP, 128, 0, st>>>(L.P, h->S, L.dQ[3], &cntShadow[it], &workPost[it], L.dQ[4], &cntAlphaS[it], h->dStats, h->refillThreshold, h->postponeShift, 0);
           if(h->S.hasAlpha)
           {
-            k_alpha<true><<<gP, 128, 1024, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS[it], L.dQ[5], &cntContS[it], 0);
+            k_alpha<true><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS[it], L.dQ[5], &cntContS[it], 0);
             k_shadow<<<gP, 128, 0, st>>>(L.P, h->S, L.dQ[5], &cntContS[it], &workContS[it], L.dQ[4], &cntAlphaS1[it], h->dStats, h->refillThreshold, h->postponeShift, 1);
-            k_alpha<true><<<gP, 128, 1024, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS1[it], nullptr, nullptr, 1);
+            k_alpha<true><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS1[it], nullptr, nullptr, 1);
           }
           k_resolve<<<gridFor(h, 4), 256, 0, st>>>(L.P, F, L.dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats);
         });
@@ -2190,7 +2195,7 @@ int b200pt_trace_closest(b200pt_t* h, const float* dev_rays, uint32_t n, float* 
     return B200PT_E_INVALID;
   CK(cudaSetDevice(h->device));
   if(n)
-    k_trace_rays<<<gridFor(h, 8), 128, 1024, h->stream>>>(h->S, reinterpret_cast<const float4*>(dev_rays), n, dev_hits, dev_seeds, h->dStats);
+    k_trace_rays<<<gridFor(h, 8), 128, 2048, h->stream>>>(h->S, reinterpret_cast<const float4*>(dev_rays), n, dev_hits, dev_seeds, h->dStats);
   CK(cudaGetLastError());
   h->kernelLaunches++;
   return B200PT_OK;
@@ -2202,7 +2207,7 @@ int b200pt_trace_shadow(b200pt_t* h, const float* dev_rays, uint32_t n, float* d
     return B200PT_E_INVALID;
   CK(cudaSetDevice(h->device));
   if(n)
-    k_shadow_rays<<<gridFor(h, 8), 128, 1024, h->stream>>>(h->S, reinterpret_cast<const float4*>(dev_rays), n, dev_transmission, dev_seeds, h->dStats);
+    k_shadow_rays<<<gridFor(h, 8), 128, 2048, h->stream>>>(h->S, reinterpret_cast<const float4*>(dev_rays), n, dev_transmission, dev_seeds, h->dStats);
   CK(cudaGetLastError());
   h->kernelLaunches++;
   return B200PT_OK;

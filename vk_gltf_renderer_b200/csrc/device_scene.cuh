@@ -61,7 +61,7 @@ struct DevScene
   const uint2*                 triMeta;   // per triangle slot: (rnode | flags<<28, primitiveID)
   const float4*                envRgba;  // lat-long radiance, pdf in .w
   const uint2*                 envAccel; // (alias, q bits)
-  const float*                 lutSrgb;  // 256-entry sRGB decode table (staged into shared memory per block)
+  const float*                 lutSrgb;  // 512 floats: sRGB decode table, then i/255 (staged into shared memory per block)
   int                          envW, envH;
 };
 

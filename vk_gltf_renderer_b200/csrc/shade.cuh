@@ -133,7 +133,7 @@ PT_D HitState getHitState(const DevPrim& P, float3 bary, const float* W2O, const
 extern __shared__ float s_lutSrgb[];
 PT_D void stageSrgbLut(const float* __restrict__ lutGlobal)
 {
-  for(int i = threadIdx.x; i < 256; i += blockDim.x)
+  for(int i = threadIdx.x; i < 512; i += blockDim.x)
     s_lutSrgb[i] = __ldg(lutGlobal + i);
   __syncthreads();
 }
@@ -164,10 +164,8 @@ __device__ __noinline__ int wrapCoord(int i, int n, int mode)
 PT_D float4 fetchTexel(const uchar4* __restrict__ lv, int tpr, bool srgb, int x, int y)
 {
   const uchar4 p = __ldg(lv + (((y >> 2) * tpr + (x >> 2)) << 4) + ((y & 3) << 2) + (x & 3));
-  const float  a = (float)p.w / 255.0f;
-  if(srgb)
-    return f4(s_lutSrgb[p.x], s_lutSrgb[p.y], s_lutSrgb[p.z], a);
-  return f4((float)p.x / 255.0f, (float)p.y / 255.0f, (float)p.z / 255.0f, a);
+  const float* lutRgb = srgb ? s_lutSrgb : s_lutSrgb + 256;  // second half: i / 255
+  return f4(lutRgb[p.x], lutRgb[p.y], lutRgb[p.z], s_lutSrgb[256 + p.w]);
 }
 
 PT_D int wrapFast(int i, int n, int mode)

@@ -319,6 +319,43 @@ def synth_glass(seed=1234, n=96, scatter=False):
     return scn
 
 
+def synth_layers(seed=1234, layers=14, tex_size=64, blend=False, tinted=False):
+    """`layers` parallel quads in front of a floor: MASK (or BLEND) noise alpha, optionally a stack of thin tinted
+    glass sheets.  Every camera / shadow ray meets more non-opaque candidates than one any-hit walk collects, so
+    the continuation rounds and the final in-kernel fallback of the any-hit kernels all run."""
+    rng = np.random.default_rng(seed)
+    scn = Scene()
+    a = value_noise(tex_size, 4, rng, 1)[..., 0]
+    rgba = np.concatenate([_u8(np.stack([0.3 + 0.6 * a, 0.8 - 0.5 * a, 0.4 + 0.2 * a], -1)), _u8(np.clip(a * 1.6 - 0.25, 0, 1))[..., None]], -1)
+    tex = scn.add_texture(rgba, srgb=True)
+    if tinted:
+        mat = scn.add_material(pbrBaseColorFactor=[0.9, 0.95, 0.8, 1], pbrRoughnessFactor=0.1, pbrMetallicFactor=0.0, transmissionFactor=0.9,
+                               thicknessFactor=0.0, ior=1.2, doubleSided=1)
+    else:
+        mat = scn.add_material(pbrBaseColorFactor=[1, 1, 1, 1], pbrRoughnessFactor=0.8, pbrMetallicFactor=0.0, alphaMode=2 if blend else 1,
+                               alphaCutoff=0.5, doubleSided=1, pbrBaseColorTexture=scn.add_texture_info(tex, 0))
+    for l in range(layers):
+        z = -0.15 * l
+
+        def quad(u, v, z=z, l=l):
+            return _xyz((u * 2 - 1) * 1.5 + 0.03 * l, 0.1 + v * 2.0, np.full_like(u, z))
+        pos, nrm, uv, tan, idx = param_surface(quad, 3, 3, (1.0 + 0.37 * l, 1.0 + 0.21 * l))
+        scn.add_node(scn.add_primitive(pos, idx, normals=nrm, uv0=uv, tangents=tan), mat)
+
+    def ground(u, v):
+        return _xyz((u * 2 - 1) * 5, np.zeros_like(u), (1 - v * 2) * 5)
+    gp, gn, guv, gt, gi = param_surface(ground, 4, 4, (2, 2))
+    gm = scn.add_material(pbrBaseColorFactor=[0.7, 0.7, 0.7, 1], pbrRoughnessFactor=0.9, pbrMetallicFactor=0.0)
+    scn.add_node(scn.add_primitive(gp, gi, normals=gn, uv0=guv, tangents=gt), gm)
+    cam = Camera()
+    cam.eye = np.array([0.4, 1.3, 3.0], np.float32)
+    cam.center = np.array([0.0, 1.0, -1.0], np.float32)
+    cam.yfov = math.radians(50.0)
+    cam.znear, cam.zfar = 0.05, 100.0
+    scn.camera = cam
+    return scn
+
+
 def triangle_soup(n, seed=1234, extent=1.0, size=0.15):
     """n random triangles in a cube: stress input for traversal parity tests."""
     rng = np.random.default_rng(seed)
