@@ -263,11 +263,19 @@ def main():
     pt = PathTracer(local)
     pt.ptMaxDepth = args.depth
     pt.onAttach(res)
+    # frames in flight: the per-rank path pool shrinks with the tile, so more lanes fit as N grows and they are what
+    # hides the latency-bound tails of a small tile (measured N=4: 3 lanes 1698, 4 -> 1832, 8 -> 2011 Mray/s)
+    lanes = 4 if world == 1 else 8
+    if not os.environ.get("B200PT_FRAMES_IN_FLIGHT"):
+        pt.set_frames_in_flight(lanes)
+    else:
+        lanes = int(os.environ["B200PT_FRAMES_IN_FLIGHT"])
     stream = torch.cuda.ExternalStream(pt.stream(), device=local)
     tile = torch.zeros((rows_per, W, 4), dtype=torch.float32, device="cuda")
     pt.set_accum_device(tile.data_ptr(), rows * W * 4)
     full = torch.empty((world * rows_per, W, 4), dtype=torch.float32, device="cuda") if world > 1 else None
-    pinned = [torch.empty((rows, W, 4), dtype=torch.float32).pin_memory() for _ in range(3)]
+    RING = 8  # read-back ring (one pinned image per frame in flight)
+    pinned = [torch.empty((rows, W, 4), dtype=torch.float32).pin_memory() for _ in range(RING)]
 
     frame = [-1]
     image = [None]
@@ -339,26 +347,28 @@ def main():
 
     # ---- pass C: end to end through the public API with host buffers ----
     # every step: submit the frame (444 B of frame constants go host->device as kernel arguments), then read the
-    # step's image back into pinned host memory.  The read-back is triple-buffered like the reference's staging
-    # ring: the copy of frame f is enqueued behind its accumulate, and the host consumes frame f-2 (waits for its
-    # copy, touches the pixels) while frames f-1 and f render.  The last frames are consumed before the clock stops.
+    # step's image back into pinned host memory.  The read-back is ring-buffered like the reference's staging
+    # ring: the copy of frame f is enqueued behind its accumulate, and the host consumes frame f-depth (waits for
+    # its copy, touches the pixels) while the newer frames render.  The last frames are consumed before the clock stops.
     checks = []
 
+    depth = min(lanes, RING) - 1  # the host consumes frame f-depth while frames f-depth+1 .. f render
+
     def consume(k):
-        pt.wait_read(k % 3)
-        checks.append(float(pinned[k % 3][0, 0, 3]))
+        pt.wait_read(k % RING)
+        checks.append(float(pinned[k % RING][0, 0, 3]))
 
     def step_e2e(k):
         step()
-        pt.read_accum_async(pinned[k % 3].data_ptr(), pinned[k % 3].numel(), k % 3)
-        if k > 1:
-            consume(k - 2)
+        pt.read_accum_async(pinned[k % RING].data_ptr(), pinned[k % RING].numel(), k % RING)
+        if k >= depth:
+            consume(k - depth)
     pt.reset_stats()
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
         step_e2e(k)
-    for k in range(max(args.steps - 2, 0), args.steps):
+    for k in range(max(args.steps - depth, 0), args.steps):
         consume(k)
     barrier()
     dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)

@@ -317,13 +317,13 @@ int b200pt_get_accum_device(b200pt_t* h, float** dev_rgba32f, size_t* num_floats
 int b200pt_read_accum(b200pt_t* h, float* host_rgba32f, size_t num_floats);
 
 /* Pipelined read-back: enqueue the copy of the image as of the frames submitted so far into (pinned) host memory
- * and return at once; b200pt_wait_read(slot) blocks until that copy has landed.  slot is 0..3; issuing a read on a
+ * and return at once; b200pt_wait_read(slot) blocks until that copy has landed.  slot is 0..7; issuing a read on a
  * slot first waits for the slot's previous read.  With frames in flight a caller reads frame f while frame f+1
  * renders (the reference's swapchain / staging-buffer ring plays this role, nvapp frames-in-flight). */
 int b200pt_read_accum_async(b200pt_t* h, float* host_rgba32f, size_t num_floats, int slot);
 int b200pt_wait_read(b200pt_t* h, int slot);
 
-/* Number of frames whose bounces may overlap on the device (1..4, default 3; 1 = strictly serial frames).
+/* Number of frames whose bounces may overlap on the device (1..8, default 4; 1 = strictly serial frames).
  * Each lane owns a path pool (176 B per pixel of the tile), so the pool is rebuilt: call before b200pt_resize
  * or expect the accumulation image to be cleared like a resize does. */
 int b200pt_set_frames_in_flight(b200pt_t* h, int n);

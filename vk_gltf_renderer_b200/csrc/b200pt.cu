@@ -1085,12 +1085,12 @@ struct b200pt
     cudaEvent_t  freed = nullptr;    // main stream: k_accumulate has consumed the lane's pixSum
     bool         busy = false;       // `freed` has been recorded at least once since the pool was (re)built
   };
-  static constexpr int kMaxLanes = 4;
+  static constexpr int kMaxLanes = 8;
   Lane               lanes[kMaxLanes];
-  int                numLanes = 3;   // measured on B200 (1080p bench): 1 -> 310, 2 -> 366, 3 -> 378 Mray/s; B200PT_FRAMES_IN_FLIGHT / b200pt_set_frames_in_flight
+  int                numLanes = 4;   // measured on B200 (1080p bench): 1 -> 310, 2 -> 366, 3 -> 378 Mray/s (first version); 3 -> 599, 4 -> 617, 6 -> 622 (now)
   uint64_t           frameSerial = 0;
   int                lastLane = -1;
-  cudaEvent_t        readDone[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t        readDone[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::vector<void*> poolAllocs;
   DevStats*          dStats = nullptr;
   float*             dLutSrgb = nullptr;
@@ -1351,7 +1351,7 @@ void b200pt_destroy(b200pt_t* h)
   syncAll(h);
   freeScene(h);
   freePool(h);
-  for(int k = 0; k < 4; k++)
+  for(int k = 0; k < 8; k++)
     if(h->readDone[k])
       cudaEventDestroy(h->readDone[k]);
   for(int l = 0; l < b200pt::kMaxLanes; l++)
@@ -1882,7 +1882,7 @@ int b200pt_read_accum(b200pt_t* h, float* host, size_t num_floats)
 
 int b200pt_read_accum_async(b200pt_t* h, float* host, size_t num_floats, int slot)
 {
-  if(!h || h->numPaths == 0 || !host || num_floats < (size_t)h->numPaths * 4 || slot < 0 || slot >= 4)
+  if(!h || h->numPaths == 0 || !host || num_floats < (size_t)h->numPaths * 4 || slot < 0 || slot >= 8)
     return B200PT_E_INVALID;
   CK(cudaSetDevice(h->device));
   if(!h->readDone[slot])
@@ -1896,7 +1896,7 @@ int b200pt_read_accum_async(b200pt_t* h, float* host, size_t num_floats, int slo
 
 int b200pt_wait_read(b200pt_t* h, int slot)
 {
-  if(!h || slot < 0 || slot >= 4)
+  if(!h || slot < 0 || slot >= 8)
     return B200PT_E_INVALID;
   if(h->readDone[slot])
     CK(cudaEventSynchronize(h->readDone[slot]));
