@@ -402,20 +402,26 @@ def main():
         closest_b = 32 + 24 + nn * NODE_BYTES + nt * TRI_BYTES
         shadow_b = 32 + 16 + nn * NODE_BYTES + nt * TRI_BYTES
     shade_b = 1100.0  # ~1.0-1.2 KB per shaded hit
+    # one entry per kernel kind; the tree walks carry the algorithmic-bytes model (node + triangle records a ray touches),
+    # the dense kernels are listed with their time share only
     for name, ms_k, n_l, units, per in (("k_trace", stB["msTraceClosest"], stB["launchesTraceClosest"], stB["closestRays"], closest_b),
                                         ("k_shade", stB["msShade"], stB["launchesShade"], stB["shadedHits"], shade_b),
-                                        ("k_post", stB["msTraceShadow"], stB["launchesTraceShadow"], stB["shadowRays"], shadow_b)):
+                                        ("k_shadow", stB["msTraceShadow"], stB["launchesTraceShadow"], stB["shadowRays"], shadow_b),
+                                        ("k_alpha", stB["msAnyHit"], stB["launchesAnyHit"], 0, None),
+                                        ("k_resolve", stB["msResolve"], stB["launchesResolve"], 0, None)):
         ach = (units * per / (ms_k * 1e-3) / 1e9) if (per and ms_k > 0) else None
         stages[name] = {"share": ms_k / tot_ms, "ms_per_launch": ms_k / max(n_l, 1), "launches": int(n_l), "units": int(units),
                         "bytes_per_unit": per, "achieved_GBps": ach}
     dom = max(stages, key=lambda k: stages[k]["share"])
-    # measured DRAM traffic of the dominant kernel: one `ncu --set full` capture (profiles/r01_ncu_summary.md), per launch
-    ncu_traffic = {"k_trace": {"bytes": 188183000 + 44838656, "units_in_that_launch": 2070000, "source": "profiles/r01_ncu_summary.md"},
-                   "k_shade": {"bytes": 1481856000 + 591318528, "units_in_that_launch": 2000000, "source": "profiles/r01_ncu_summary.md"},
-                   "k_post": {"bytes": 466673000 + 70331136, "units_in_that_launch": 1000000, "source": "profiles/r01_ncu_summary.md"}}
+    # measured DRAM traffic of the dominant kernel: one `ncu --set full` capture, per launch (profiles/ncu_traffic.json)
+    try:
+        ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        ncu_traffic = {}
+    tr = ncu_traffic.get(dom)
     roof = {"kernel": dom, "bound": "hbm", "achieved": stages[dom]["achieved_GBps"], "peak": peak_gbs, "unit": "GB/s",
             "frac": (stages[dom]["achieved_GBps"] / peak_gbs) if stages[dom]["achieved_GBps"] else None,
-            "traffic": ncu_traffic[dom]["bytes"], "traffic_detail": ncu_traffic[dom],
+            "traffic": tr["bytes"] if tr else None, "traffic_detail": tr,
             "peak_source": peak_src, "model": "algorithmic bytes/unit x units / CUDA-event kernel time (pass B); " + counts_note,
             "stages": stages}
 

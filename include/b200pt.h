@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200PT_ABI_VERSION 1
+#define B200PT_ABI_VERSION 2
 
 /* error codes */
 #define B200PT_OK 0
@@ -255,15 +255,19 @@ typedef struct b200pt_stats
   uint64_t pathsStarted;  /* samplePixel() calls                                   */
   uint64_t nodesVisited;  /* BVH nodes fetched (only when built with B200PT_COUNT_TRAVERSAL) */
   uint64_t trisTested;    /* triangles tested  (same)                              */
-  double   msTraceClosest; /* CUDA-event time inside closest-hit traversal kernels */
-  double   msTraceShadow;
-  double   msShade;
-  double   msOther;       /* raygen + accumulate + queue housekeeping              */
+  double   msTraceClosest; /* CUDA-event time inside k_trace, the closest-hit tree walks (profiling on) */
+  double   msTraceShadow;  /* k_shadow, the shadow-ray tree walks                                       */
+  double   msShade;        /* k_shade                                                                   */
+  double   msOther;       /* raygen + accumulate                                                        */
   double   msTotal;
   uint64_t kernelLaunches;
   uint64_t launchesTraceClosest; /* launches measured into msTraceClosest (profiling on) */
   uint64_t launchesShade;
   uint64_t launchesTraceShadow;
+  double   msAnyHit;       /* k_alpha: stochastic alpha / transmission tests on the collected candidates */
+  double   msResolve;      /* k_resolve: NEE contribution, Russian roulette, next-bounce queue           */
+  uint64_t launchesAnyHit;
+  uint64_t launchesResolve;
 } b200pt_stats;
 
 /* ---- lifecycle --------------------------------------------------------------------------- */

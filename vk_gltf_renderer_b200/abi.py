@@ -105,7 +105,8 @@ class Stats(C.Structure):
                 ("pathsStarted", C.c_uint64), ("nodesVisited", C.c_uint64), ("trisTested", C.c_uint64),
                 ("msTraceClosest", C.c_double), ("msTraceShadow", C.c_double), ("msShade", C.c_double),
                 ("msOther", C.c_double), ("msTotal", C.c_double), ("kernelLaunches", C.c_uint64),
-                ("launchesTraceClosest", C.c_uint64), ("launchesShade", C.c_uint64), ("launchesTraceShadow", C.c_uint64)]
+                ("launchesTraceClosest", C.c_uint64), ("launchesShade", C.c_uint64), ("launchesTraceShadow", C.c_uint64),
+                ("msAnyHit", C.c_double), ("msResolve", C.c_double), ("launchesAnyHit", C.c_uint64), ("launchesResolve", C.c_uint64)]
 
 
 # sizes fixed by the reference's layouts

@@ -469,19 +469,28 @@ __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const ui
   }
 }
 
+#ifndef SHADE_BLOCK
+#define SHADE_BLOCK 512  // measured: 128 -> 0.50 ms/launch, 256 + barrier 0.41, 512 no barrier 0.475, 512 + barrier 0.33
+#endif
+#ifndef SHADE_SYNC
+#define SHADE_SYNC 1
+#endif
 #ifndef SHADE_MIN_BLOCKS
 #define SHADE_MIN_BLOCKS 4  // measured on B200: 3 -> 1.165 ms, 4 -> 1.017, 5 -> 1.029, 6 -> 1.064 per launch
 #endif
 template <uint32_t FEAT>
-__global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(PathState P, DevScene S, const __grid_constant__ FrameParams F, const uint32_t* __restrict__ q,
+__global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BLOCK) k_shade(PathState P, DevScene S, const __grid_constant__ FrameParams F, const uint32_t* __restrict__ q,
                                                const uint32_t* __restrict__ cntIn, uint32_t* qPost, uint32_t* cntPost, uint32_t* qShadow, uint32_t* cntShadow,
                                                                  uint32_t* qNext, uint32_t* cntNext, DevStats* stats)
 {
   stageSrgbLut(S.lutSrgb);
   const uint32_t count = *cntIn;
   const uint32_t stride = gridDim.x * blockDim.x;
-  for(uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
-  {
+  // One path per thread per pass.  The kernel is ~12 000 straight-line instructions that every warp walks once per
+  // path, so it is bound by instruction fetch (ncu: no_instruction is its top stall, 20 % issue utilisation); the
+  // block-uniform loop with a barrier per pass keeps the warps of a block -- and with SHADE_BLOCK = 512 all four
+  // warps of a scheduler -- inside the same stretch of code so they share the fetched lines.
+  auto shadeOne = [&](const uint32_t k) {
     const uint32_t i = q[k];
     const float4   ro = P.rayO[i];
     const float4   rd = P.rayD[i];
@@ -511,7 +520,7 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(PathState P, De
         if(F.fi.flags & B200PT_SCENE_USE_SOLID_BACKGROUND)
         {
           finalizeSample(P, F, i, f3(F.fi.backgroundColor[0], F.fi.backgroundColor[1], F.fi.backgroundColor[2]), false, seed, sampleIdx, qNext, cntNext, stats);
-          continue;
+          return;
         }
       }
       const float3 edir = rotateAxis(dir, f3(0, 1, 0), -F.fi.envRotation);
@@ -525,7 +534,7 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(PathState P, De
       }
       radiance += throughput * misWeight * (xyz(env) * F.fi.envIntensity);
       finalizeSample(P, F, i, radiance, (flags & PF_SOLID) != 0, seed, sampleIdx, qNext, cntNext, stats);
-      continue;
+      return;
     }
 
     // ---- hit-attribute fetch ----
@@ -560,7 +569,7 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(PathState P, De
     {
       radiance += pbrMat.baseColor;
       finalizeSample(P, F, i, radiance, (flags & PF_SOLID) != 0, seed, sampleIdx, qNext, cntNext, stats);
-      continue;
+      return;
     }
 
     flags &= ~(PF_POST_VOLUME | PF_SHADOW_VALID | PF_SHADOW_INSIDE);
@@ -624,7 +633,7 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(PathState P, De
           queuePush(qPost, cntPost, i);
           if(flags & PF_SHADOW_VALID)
             queuePush(qShadow, cntShadow, i);
-          continue;
+          return;
         }
       }
     }
@@ -704,6 +713,14 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(PathState P, De
     queuePush(qPost, cntPost, i);
     if(flags & PF_SHADOW_VALID)
       queuePush(qShadow, cntShadow, i);
+  };
+  for(uint32_t base = blockIdx.x * blockDim.x; base < count; base += stride)
+  {
+#if SHADE_SYNC
+    __syncthreads();
+#endif
+    if(base + threadIdx.x < count)
+      shadeOne(base + threadIdx.x);
   }
 }
 
@@ -1105,8 +1122,8 @@ struct b200pt
   bool               profiling = false;
   std::vector<EvRec> evPool;
   size_t             evUsed = 0;
-  double             msCat[4] = {0, 0, 0, 0};  // 0 trace-closest, 1 shade, 2 shadow+RR, 3 other
-  uint64_t           launchesCat[4] = {0, 0, 0, 0};
+  double             msCat[6] = {0, 0, 0, 0, 0, 0};  // 0 k_trace, 1 k_shade, 2 k_shadow, 3 other, 4 k_alpha, 5 k_resolve
+  uint64_t           launchesCat[6] = {0, 0, 0, 0, 0, 0};
   uint64_t           kernelLaunches = 0;
 };
 
@@ -2023,7 +2040,9 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
     tTrace = 0,
     tShade = 1,
     tPost = 2,
-    tOther = 3
+    tOther = 3,
+    tAnyHit = 4,
+    tResolve = 5
   };
   auto timed = [&](int cat, auto&& launch) {
     if(h->profiling)
@@ -2060,34 +2079,31 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
         // geometry walks are persistent kernels; the texture-dependent any-hit tests and the path bookkeeping run
         // as dense one-thread-per-path kernels (k_alpha, k_resolve) sized by the device-side queue counters
         const int gP = gridFor(h, 8);
-        timed(tTrace, [&] {
-          k_trace<<<gP, 128, 0, st>>>(L.P, h->S, qT, &cntTrace[it], &workTrace[it], L.dQ[4], &cntAlpha[it], h->dStats, h->refillThreshold, h->postponeShift, 0);
-          if(h->S.hasAlpha)
-          {
-            // any-hit: resolve kCand candidates, one continuation round for the paths that used them all up, then
-            // whatever is still undecided finishes inside the last k_alpha
-            k_alpha<false><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlpha[it], L.dQ[5], &cntCont[it], 0);
-            k_trace<<<gP, 128, 0, st>>>(L.P, h->S, L.dQ[5], &cntCont[it], &workCont[it], L.dQ[4], &cntAlpha1[it], h->dStats, h->refillThreshold, h->postponeShift, 1);
-            k_alpha<false><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlpha1[it], nullptr, nullptr, 1);
-          }
-        });
+        // geometry walks are persistent kernels; the texture-dependent any-hit tests and the path bookkeeping run
+        // as dense kernels (k_alpha, k_resolve) sized by the device-side queue counters.  Any-hit: resolve kCand
+        // candidates, one continuation round for the paths that used them all up, then whatever is still
+        // undecided finishes inside the last k_alpha.
+        timed(tTrace, [&] { k_trace<<<gP, 128, 0, st>>>(L.P, h->S, qT, &cntTrace[it], &workTrace[it], L.dQ[4], &cntAlpha[it], h->dStats, h->refillThreshold, h->postponeShift, 0); });
+        if(h->S.hasAlpha)
+        {
+          timed(tAnyHit, [&] { k_alpha<false><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlpha[it], L.dQ[5], &cntCont[it], 0); });
+          timed(tTrace, [&] { k_trace<<<gP, 128, 0, st>>>(L.P, h->S, L.dQ[5], &cntCont[it], &workCont[it], L.dQ[4], &cntAlpha1[it], h->dStats, h->refillThreshold, h->postponeShift, 1); });
+          timed(tAnyHit, [&] { k_alpha<false><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlpha1[it], nullptr, nullptr, 1); });
+        }
         timed(tShade, [&] {
           if(h->leanShade)
-            k_shade<FEAT_LEAN><<<gP, 128, 2048, st>>>(L.P, h->S, F, qT, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
+            k_shade<FEAT_LEAN><<<gP * 128 / SHADE_BLOCK, SHADE_BLOCK, 2048, st>>>(L.P, h->S, F, qT, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
           else
-            k_shade<FEAT_ALL><<<gP, 128, 2048, st>>>(L.P, h->S, F, qT, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
+            k_shade<FEAT_ALL><<<gP * 128 / SHADE_BLOCK, SHADE_BLOCK, 2048, st>>>(L.P, h->S, F, qT, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
         });
-        timed(tPost, [&] {
-          k_shadow<<<gP, 128, 0, st>>>(L.P, h->S, L.dQ[3], &cntShadow[it], &workPost[it], L.dQ[4], &cntAlphaS[it], h->dStats, h->refillThreshold, h->postponeShift, 0);
-          if(h->S.hasAlpha)
-          {
-            k_alpha<true><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS[it], L.dQ[5], &cntContS[it], 0);
-            k_shadow<<<gP, 128, 0, st>>>(L.P, h->S, L.dQ[5], &cntContS[it], &workContS[it], L.dQ[4], &cntAlphaS1[it], h->dStats, h->refillThreshold, h->postponeShift, 1);
-            k_alpha<true><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS1[it], nullptr, nullptr, 1);
-          }
-          k_resolve<<<gridFor(h, 4), 256, 0, st>>>(L.P, F, L.dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats);
-        });
-        h->kernelLaunches += h->S.hasAlpha ? 7 : 1;  // timed() counts one launch per stage
+        timed(tPost, [&] { k_shadow<<<gP, 128, 0, st>>>(L.P, h->S, L.dQ[3], &cntShadow[it], &workPost[it], L.dQ[4], &cntAlphaS[it], h->dStats, h->refillThreshold, h->postponeShift, 0); });
+        if(h->S.hasAlpha)
+        {
+          timed(tAnyHit, [&] { k_alpha<true><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS[it], L.dQ[5], &cntContS[it], 0); });
+          timed(tPost, [&] { k_shadow<<<gP, 128, 0, st>>>(L.P, h->S, L.dQ[5], &cntContS[it], &workContS[it], L.dQ[4], &cntAlphaS1[it], h->dStats, h->refillThreshold, h->postponeShift, 1); });
+          timed(tAnyHit, [&] { k_alpha<true><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS1[it], nullptr, nullptr, 1); });
+        }
+        timed(tResolve, [&] { k_resolve<<<gridFor(h, 4), 256, 0, st>>>(L.P, F, L.dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats); });
         cur = 1 - cur;
       }
       if(!mayOverrun)
@@ -2124,17 +2140,20 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
     const int            n = pc->maxDepth < 64 ? pc->maxDepth : 64;
     std::vector<uint32_t> c(2 * kMaxIters);
     CK(cudaMemcpy(c.data(), L.dCounters, sizeof(uint32_t) * 2 * kMaxIters, cudaMemcpyDeviceToHost));
-    const size_t first = h->evUsed >= (size_t)(3 * pc->maxDepth + 2) ? h->evUsed - (size_t)(3 * pc->maxDepth + 2) : 0;
+    const size_t perIter = h->S.hasAlpha ? 11 : 5;
+    const size_t first = h->evUsed >= perIter * (size_t)pc->maxDepth + 2 ? h->evUsed - (perIter * (size_t)pc->maxDepth + 2) : 0;
     for(int it = 0; it < n; it++)
     {
-      float ms[3] = {0, 0, 0};
-      for(int k = 0; k < 3; k++)
+      float ms[6] = {0, 0, 0, 0, 0, 0};
+      for(size_t k = 0; k < perIter; k++)
       {
-        const size_t e = first + 1 + (size_t)it * 3 + k;
-        if(e < h->evUsed)
-          cudaEventElapsedTime(&ms[k], h->evPool[e].a, h->evPool[e].b);
+        const size_t e = first + 1 + (size_t)it * perIter + k;
+        float        t = 0.f;
+        if(e < h->evUsed && cudaEventElapsedTime(&t, h->evPool[e].a, h->evPool[e].b) == cudaSuccess)
+          ms[h->evPool[e].cat] += t;
       }
-      fprintf(stderr, "iter %2d  trace %8u rays %.3f ms | shade %.3f ms | post %8u rays %.3f ms\n", it, c[it], ms[0], ms[1], c[kMaxIters + it], ms[2]);
+      fprintf(stderr, "iter %2d  %8u rays  k_trace %.3f  k_alpha %.3f  k_shade %.3f | %8u paths  k_shadow %.3f  k_resolve %.3f ms\n", it, c[it], ms[0], ms[4], ms[1],
+              c[kMaxIters + it], ms[2], ms[5]);
     }
   }
   return B200PT_OK;
@@ -2164,7 +2183,11 @@ int b200pt_get_stats(b200pt_t* h, b200pt_stats* out)
   out->msShade = h->msCat[1];
   out->msTraceShadow = h->msCat[2];
   out->msOther = h->msCat[3];
-  out->msTotal = h->msCat[0] + h->msCat[1] + h->msCat[2] + h->msCat[3];
+  out->msAnyHit = h->msCat[4];
+  out->msResolve = h->msCat[5];
+  out->launchesAnyHit = h->launchesCat[4];
+  out->launchesResolve = h->launchesCat[5];
+  out->msTotal = h->msCat[0] + h->msCat[1] + h->msCat[2] + h->msCat[3] + h->msCat[4] + h->msCat[5];
   out->kernelLaunches = h->kernelLaunches;
   out->launchesTraceClosest = h->launchesCat[0];
   out->launchesShade = h->launchesCat[1];
@@ -2180,7 +2203,7 @@ int b200pt_reset_stats(b200pt_t* h)
   syncAll(h);
   CK(cudaMemset(h->dStats, 0, sizeof(DevStats)));
   flushEvents(h);
-  for(int k = 0; k < 4; k++)
+  for(int k = 0; k < 6; k++)
   {
     h->msCat[k] = 0;
     h->launchesCat[k] = 0;
