@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const ui
 #define SHADE_BLOCK 512  // measured: 128 -> 0.50 ms/launch, 256 + barrier 0.41, 512 no barrier 0.475, 512 + barrier 0.33
 #endif
 #ifndef SHADE_SYNC
-#define SHADE_SYNC 1
+#define SHADE_SYNC 1  // 0: none, 1: one barrier per pass, 2: also between the four sections of a pass (measured: no further gain)
 #endif
 #ifndef SHADE_MIN_BLOCKS
 #define SHADE_MIN_BLOCKS 4  // measured on B200: 3 -> 1.165 ms, 4 -> 1.017, 5 -> 1.029, 6 -> 1.064 per launch
@@ -490,26 +490,44 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
   // path, so it is bound by instruction fetch (ncu: no_instruction is its top stall, 20 % issue utilisation); the
   // block-uniform loop with a barrier per pass keeps the warps of a block -- and with SHADE_BLOCK = 512 all four
   // warps of a scheduler -- inside the same stretch of code so they share the fetched lines.
-  auto shadeOne = [&](const uint32_t k) {
-    const uint32_t i = q[k];
+  // pass state shared by the four sections of a pass (sections are separated by block barriers, see below)
+  uint32_t                  i = 0, flags = 0, seed = 0, scatterBounces = 0, sampleIdx = 0, depth = 0, slot = 0;
+  float4                    hr, misc;
+  uint4                     med;
+  float3                    org, dir, throughput, radiance;
+  float                     coneWidth = 0.f, lastSamplePdf = 0.f, hitT = 0.f, worldFoot = 0.f;
+  uint2                     meta;
+  const b200pt_render_node* nodeP = nullptr;
+  HitState                  hit;
+  PbrMaterial               pbrMat;
+  DirectLight               directLight;
+  bool                      nextEventValid = false;
+#ifdef B200PT_DEBUG
+  bool dbgPixel = false;
+#endif
+  // ---- section 1: path state, environment hit (path ends), hit attributes ----
+  auto shadeLoad = [&](const uint32_t k) -> bool {
+    i = q[k];
     const float4   ro = P.rayO[i];
     const float4   rd = P.rayD[i];
-    const float4   hr = P.hit[i];
+    hr = P.hit[i];
     float4         thr4 = P.thr[i];
     float4         rad4 = P.rad[i];
-    float4         misc = P.misc[i];
-    uint4          med = P.medium[i];
-    float3         org = xyz(ro), dir = xyz(rd);
-    float          coneWidth = ro.w;
-    float3         throughput = xyz(thr4), radiance = xyz(rad4);
-    float          lastSamplePdf = thr4.w;
-    uint32_t       flags = __float_as_uint(misc.z);
-    uint32_t       seed = __float_as_uint(misc.w);
-    uint32_t       scatterBounces = __float_as_uint(rad4.w);
-    const uint32_t sampleIdx = med.w >> 16;
-    uint32_t       depth = flags & PF_DEPTH_MASK;
-    const uint32_t slot = __float_as_uint(hr.w);
-    const float    hitT = hr.x;
+    misc = P.misc[i];
+    med = P.medium[i];
+    org = xyz(ro);
+    dir = xyz(rd);
+    coneWidth = ro.w;
+    throughput = xyz(thr4);
+    radiance = xyz(rad4);
+    lastSamplePdf = thr4.w;
+    flags = __float_as_uint(misc.z);
+    seed = __float_as_uint(misc.w);
+    scatterBounces = __float_as_uint(rad4.w);
+    sampleIdx = med.w >> 16;
+    depth = flags & PF_DEPTH_MASK;
+    slot = __float_as_uint(hr.w);
+    hitT = hr.x;
 
     if(slot == 0xFFFFFFFFu)
     {
@@ -520,7 +538,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
         if(F.fi.flags & B200PT_SCENE_USE_SOLID_BACKGROUND)
         {
           finalizeSample(P, F, i, f3(F.fi.backgroundColor[0], F.fi.backgroundColor[1], F.fi.backgroundColor[2]), false, seed, sampleIdx, qNext, cntNext, stats);
-          return;
+          return false;
         }
       }
       const float3 edir = rotateAxis(dir, f3(0, 1, 0), -F.fi.envRotation);
@@ -534,29 +552,35 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
       }
       radiance += throughput * misWeight * (xyz(env) * F.fi.envIntensity);
       finalizeSample(P, F, i, radiance, (flags & PF_SOLID) != 0, seed, sampleIdx, qNext, cntNext, stats);
-      return;
+      return false;
     }
 
     // ---- hit-attribute fetch ----
-    const uint2               meta = S.triMeta[slot];
-    const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
+    meta = S.triMeta[slot];
+    nodeP = &S.nodes[meta.x & 0x0fffffffu];
+    const b200pt_render_node& node = *nodeP;
     const DevPrim             prim = S.prims[node.renderPrimID];
 #ifdef B200PT_DEBUG
     // reference analogue: doDebug at pushConst.mouseCoord (gltf_pathtrace.slang:553-557)
-    const bool dbgPixel = ((float)(i % (uint32_t)F.width) == F.pc.mouseCoord[0] && (float)pixelRow(F, i) == F.pc.mouseCoord[1]);
+    dbgPixel = ((float)(i % (uint32_t)F.width) == F.pc.mouseCoord[0] && (float)pixelRow(F, i) == F.pc.mouseCoord[1]);
     if(dbgPixel)
       printf("DBG hit t=%.9g rnode=%d prim=%d bary=%.9g %.9g org=%.9g %.9g %.9g dir=%.9g %.9g %.9g seed=%u depth=%d\n", hitT, (int)(meta.x & 0x0fffffffu), (int)meta.y, hr.y, hr.z,
              org.x, org.y, org.z, dir.x, dir.y, dir.z, seed, (int)depth);
 #endif
     const float3              bary = f3(1.0f - hr.y - hr.z, hr.y, hr.z);
-    const HitState            hit = getHitState(prim, bary, node.worldToObject, node.objectToWorld, meta.y, dir);
+    hit = getHitState(prim, bary, node.worldToObject, node.objectToWorld, meta.y, dir);
     statAdd(&stats->shadedHits, 1ull);
+    return true;
+  };
+  // ---- section 2: material evaluation (three trilinear texture lookups), emission, unlit ----
+  auto shadeMaterial = [&]() -> bool {
+    const b200pt_render_node& node = *nodeP;
 
-    const float worldFoot = (coneWidth + F.pc.pixelAngle * hitT) / fmaxf(fabsf(dot(hit.geonrm, -dir)), 1e-3f);
+    worldFoot = (coneWidth + F.pc.pixelAngle * hitT) / fmaxf(fabsf(dot(hit.geonrm, -dir)), 1e-3f);
     const int   materialIndex = max(0, node.materialID);
     const float texGrad = worldFoot * hit.texelDensity * F.pc.texGradScale;
     const b200pt_shade_material& gmat = S.mats[materialIndex];
-    PbrMaterial                  pbrMat = evaluateMaterial<FEAT>(S, gmat, hit, (flags & PF_INSIDE) != 0, texGrad);
+    pbrMat = evaluateMaterial<FEAT>(S, gmat, hit, (flags & PF_INSIDE) != 0, texGrad);
 
     // firefly control: never get sharper than the roughest bounce so far (:267-268)
     misc.x = fmaxf(pbrMat.roughness.x, misc.x);
@@ -569,9 +593,13 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
     {
       radiance += pbrMat.baseColor;
       finalizeSample(P, F, i, radiance, (flags & PF_SOLID) != 0, seed, sampleIdx, qNext, cntNext, stats);
-      return;
+      return false;
     }
 
+    return true;
+  };
+  // ---- section 3: in-volume segment, light / environment sample ----
+  auto shadeLight = [&]() -> bool {
     flags &= ~(PF_POST_VOLUME | PF_SHADOW_VALID | PF_SHADOW_INSIDE);
 
     // ---- in-volume segment (pathtrace_functions.h.slang:904-939, 605-672) ----
@@ -633,7 +661,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
           queuePush(qPost, cntPost, i);
           if(flags & PF_SHADOW_VALID)
             queuePush(qShadow, cntShadow, i);
-          return;
+          return false;
         }
       }
     }
@@ -641,9 +669,13 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
     coneWidth = worldFoot;
 
     // ---- next-event estimation: one light-or-environment sample, MIS (:316-351) ----
-    const DirectLight directLight = sampleLights<FEAT>(S, F, hit.pos, seed);
-    const bool nextEventValid = (dot(directLight.direction, hit.nrm) > 0.0f || pbrMat.diffuseTransmissionFactor > 0.0f) && directLight.pdf != 0.0f;
-    float3     contribution = f3(0.0f);
+    directLight = sampleLights<FEAT>(S, F, hit.pos, seed);
+    nextEventValid = (dot(directLight.direction, hit.nrm) > 0.0f || pbrMat.diffuseTransmissionFactor > 0.0f) && directLight.pdf != 0.0f;
+    return true;
+  };
+  // ---- section 4: BSDF evaluation for the light sample, BSDF sampling, next ray + shadow ray ----
+  auto shadeBsdf = [&]() {
+    float3 contribution = f3(0.0f);
 #ifdef B200PT_DEBUG
     if(dbgPixel)
       printf("DBG shade pos=%.9g %.9g %.9g nrm=%.9g %.9g %.9g gn=%.9g %.9g %.9g N=%.9g %.9g %.9g rough=%.9g %.9g metal=%.9g base=%.9g %.9g %.9g L=%.9g %.9g %.9g lpdf=%.9g valid=%d seed=%u\n",
@@ -716,11 +748,27 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
   };
   for(uint32_t base = blockIdx.x * blockDim.x; base < count; base += stride)
   {
+    bool alive = base + threadIdx.x < count;
 #if SHADE_SYNC
     __syncthreads();
 #endif
-    if(base + threadIdx.x < count)
-      shadeOne(base + threadIdx.x);
+    if(alive)
+      alive = shadeLoad(base + threadIdx.x);
+#if SHADE_SYNC > 1
+    __syncthreads();
+#endif
+    if(alive)
+      alive = shadeMaterial();
+#if SHADE_SYNC > 1
+    __syncthreads();
+#endif
+    if(alive)
+      alive = shadeLight();
+#if SHADE_SYNC > 1
+    __syncthreads();
+#endif
+    if(alive)
+      shadeBsdf();
   }
 }
 
