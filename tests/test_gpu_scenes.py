@@ -246,3 +246,31 @@ def test_render_parity_deep_anyhit_layers(std_env, oracle_mod, kind):
     e = rel_rmse(img, ref)
     print("layers", kind, "rel RMSE", e)
     assert e <= 1e-3
+
+
+def test_cpp_host_headless_matches_python_host(box_scene, std_env, tmp_path):
+    """The C++ host mirror (host/b200pt_host.cpp: SceneData, Resources, PathTracer : BaseRenderer) driven by
+    b200pt_headless renders the image the Python mirror renders (camera matrices are computed independently in
+    double on both sides, so agreement is to rounding of the 396-byte frame constants, not bit-for-bit) and prints
+    the reference's HEADLESS_SUMMARY / BENCHMARK_JSON records."""
+    import json
+    import os
+    import subprocess
+    from vk_gltf_renderer_b200 import _lib
+    exe = os.path.join(os.path.dirname(_lib.LIB_PATH), "b200pt_headless")
+    assert os.path.exists(exe), "run __graft_entry__.build() first"
+    blob, raw = str(tmp_path / "box.b2sc"), str(tmp_path / "box.raw")
+    box_scene.save_blob(blob, std_env)
+    out = subprocess.run([exe, "--scene", blob, "--size", "96", "64", "--frames", "4", "--warmupFrames", "1", "--ptMaxDepth", "5", "--ptSamples", "2",
+                          "--outRaw", raw, "--out", str(tmp_path / "box.pfm")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    summary = [l for l in out.stdout.splitlines() if l.startswith("HEADLESS_SUMMARY ")]
+    record = [l for l in out.stdout.splitlines() if l.startswith("BENCHMARK_JSON ")]
+    assert len(summary) == 1 and "ptSamples=2" in summary[0] and "resolution=96x64" in summary[0] and "effective_spp=8" in summary[0]
+    rec = json.loads(record[0][len("BENCHMARK_JSON "):])
+    assert rec["type"] == "headless_summary" and rec["frames"] == 4 and rec["measured_frames"] == 3 and rec["closest_rays"] > 0
+    img = np.fromfile(raw, np.float32).reshape(64, 96, 4)
+    _, ref = _gpu_render(box_scene, std_env, 96, 64, 4, ptMaxDepth=5, ptSamples=2)
+    assert np.array_equal(img[..., 3], ref[..., 3])
+    assert rel_rmse(img, ref) <= 1e-4
+    assert os.path.getsize(tmp_path / "box.pfm") > 96 * 64 * 12

@@ -77,3 +77,29 @@ def test_tiling_partition_covers_the_frame():
             if n:
                 assert y0 == y
                 y += n
+
+
+def test_scene_blob_and_cpp_host_fail_loudly_without_gpu(tmp_path, box_scene, std_env):
+    """Scene.save_blob writes what host/b200pt_host.cpp loads; without a CUDA device the C++ headless driver exits
+    non-zero with the library's error (no CPU fallback anywhere).  On a GPU box the same command succeeds."""
+    import os
+    import struct
+    import subprocess
+    from vk_gltf_renderer_b200 import _lib
+    blob = str(tmp_path / "box.b2sc")
+    box_scene.save_blob(blob, std_env)
+    raw = open(blob, "rb").read()
+    assert raw[:4] == b"B2SC"
+    ver, nn, npr, nm, nti, nt, nl = struct.unpack("<7I", raw[4:32])
+    assert (ver, nn, npr, nm) == (1, len(box_scene.render_nodes), len(box_scene.render_prims), len(box_scene.materials))
+    assert len(raw) > std_env.size * 4
+    exe = os.path.join(os.path.dirname(_lib.LIB_PATH), "b200pt_headless")
+    if not os.path.exists(exe):
+        pytest.skip("b200pt_headless not built")
+    out = subprocess.run([exe, "--scene", blob, "--size", "32", "32", "--frames", "1"], capture_output=True, text=True, timeout=300)
+    if out.returncode != 0:
+        assert "b200pt_create failed" in out.stderr or "CUDA" in out.stderr
+    else:
+        assert "HEADLESS_SUMMARY" in out.stdout
+    bad = subprocess.run([exe, "--scene", str(tmp_path / "missing.b2sc")], capture_output=True, text=True, timeout=60)
+    assert bad.returncode != 0 and "cannot open" in bad.stderr

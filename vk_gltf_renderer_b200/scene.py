@@ -164,6 +164,51 @@ class Scene:
         return d
 
 
+    # ---- scene blob: what the C++ host (host/b200pt_host.cpp) loads ------------------------------------------
+    def save_blob(self, path, env_rgb=None):
+        """Serialise the scene (and optionally the HDR environment) into the little-endian "B2SC" blob the C++ host
+        reads: the C-ABI structs verbatim plus the attribute arrays.  Stands in for the reference's own loader,
+        whose output (SceneVk / MaterialCache arrays) is exactly this data."""
+        import struct
+        cam = self.camera
+        with open(path, "wb") as f:
+            f.write(b"B2SC")
+            f.write(struct.pack("<7I", 1, len(self.render_nodes), len(self.render_prims), len(self.materials), len(self.texture_infos),
+                                len(self.textures), len(self.lights)))
+            f.write(struct.pack("<I", 1 if cam.type == "orthographic" else 0))
+            f.write(np.asarray(list(cam.eye) + list(cam.center) + list(cam.up) + [cam.yfov, cam.znear, cam.zfar, getattr(cam, "xmag", 1.0),
+                                                                                    getattr(cam, "ymag", 1.0)], "<f4").tobytes())
+            for rn in self.render_nodes:
+                f.write(np.asarray(rn["objectToWorld"], "<f4").tobytes())
+                f.write(np.asarray(rn["worldToObject"], "<f4").tobytes())
+                f.write(struct.pack("<iiI", rn["materialID"], rn["renderPrimID"], 1 if rn.get("visible", True) else 0))
+            for p in self.render_prims:
+                names = ("normals", "uv0", "uv1", "tangents", "colors")
+                mask = sum(1 << i for i, n in enumerate(names) if p[n] is not None)
+                f.write(struct.pack("<3I", len(p["positions"]), len(p["indices"]), mask))
+                f.write(np.ascontiguousarray(p["positions"], "<f4").tobytes())
+                f.write(np.ascontiguousarray(p["indices"], "<u4").tobytes())
+                for n in names:
+                    if p[n] is not None:
+                        f.write(np.ascontiguousarray(p[n], "<u4" if n == "colors" else "<f4").tobytes())
+            for m in self.materials:
+                f.write(bytes(m))
+            for t in self.texture_infos:
+                f.write(bytes(t))
+            for t in self.textures:
+                h, w = t["rgba8"].shape[:2]
+                f.write(struct.pack("<7i", w, h, t["srgb"], t["wrapS"], t["wrapT"], t["magFilter"], t["minFilter"]))
+                f.write(np.ascontiguousarray(t["rgba8"], np.uint8).tobytes())
+            for l in self.lights:
+                f.write(bytes(l))
+            if env_rgb is None:
+                f.write(struct.pack("<2I", 0, 0))
+            else:
+                e = np.ascontiguousarray(env_rgb, "<f4")
+                f.write(struct.pack("<2I", e.shape[1], e.shape[0]))
+                f.write(e.tobytes())
+
+
 def _glm(m):
     """4x4 (row, col) math matrix -> glm column-major float32[16]."""
     return np.ascontiguousarray(np.asarray(m, np.float64).T.reshape(16), np.float32)
