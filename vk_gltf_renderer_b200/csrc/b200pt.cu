@@ -2,9 +2,12 @@
 //
 // Stage map (reference function -> kernel), SURVEY.md Appendix C:
 //   processPixel head / samplePixel / getRay      gltf_pathtrace.slang:546-581,502-530  -> k_raygen (+ regen in finalizeSample)
-//   IRaytracer::Trace                              raytracer_interface.h.slang:69-122    -> k_trace
+//   IRaytracer::Trace: tree walks                  raytracer_interface.h.slang:69-122    -> k_trace (persistent warps)
+//                      any-hit alpha tests         raytracer_interface.h.slang:82-112    -> k_alpha<false> (dense)
 //   pathTraceOneBounce                             gltf_pathtrace.slang:87-430           -> k_shade
-//   TraceShadow + RR + depth++ (pathTrace tail)    gltf_pathtrace.slang:462-485          -> k_post
+//   IRaytracer::TraceShadow: tree walks            raytracer_interface.h.slang:139-187   -> k_shadow (persistent warps)
+//                      any-hit transmission        raytracer_interface.h.slang:149-179   -> k_alpha<true> (dense)
+//   NEE add + RR + depth++ (pathTrace tail)        gltf_pathtrace.slang:462-485          -> k_resolve
 //   accumulation                                   gltf_pathtrace.slang:582-630          -> k_accumulate
 // One path slot per pixel; samples of a pixel within a frame run back to back in the same slot
 // (path regeneration) because the reference continues ONE rng stream across a pixel's samples.
