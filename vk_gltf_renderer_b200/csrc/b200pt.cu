@@ -1379,21 +1379,24 @@ int b200pt_create(b200pt_t** out, int cuda_device)
     h->refillThreshold = atoi(e);
   if(const char* e = getenv("B200PT_POSTPONE"))
     h->postponeShift = atoi(e);
+  bool ok = true;
+  auto need = [&](cudaError_t e) { ok = ok && (e == cudaSuccess); };
   cudaDeviceProp prop{};
-  cudaGetDeviceProperties(&prop, cuda_device);
-  h->numSMs = prop.multiProcessorCount;
-  cudaMalloc((void**)&h->dStats, sizeof(DevStats));
-  cudaMemset(h->dStats, 0, sizeof(DevStats));
+  need(cudaGetDeviceProperties(&prop, cuda_device));
+  h->numSMs = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+  need(cudaMalloc((void**)&h->dStats, sizeof(DevStats)));
+  if(ok)
+    need(cudaMemset(h->dStats, 0, sizeof(DevStats)));
   if(const char* e = getenv("B200PT_FRAMES_IN_FLIGHT"))
     h->numLanes = std::min(std::max(atoi(e), 1), (int)b200pt::kMaxLanes);
   for(int l = 0; l < b200pt::kMaxLanes; l++)
   {
     b200pt::Lane& L = h->lanes[l];
-    cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&L.freed, cudaEventDisableTiming);
-    cudaMalloc((void**)&L.dCounters, sizeof(uint32_t) * 13 * kMaxIters);
-    cudaMallocHost((void**)&L.hCount, sizeof(uint32_t) * 4);
+    need(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+    need(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+    need(cudaEventCreateWithFlags(&L.freed, cudaEventDisableTiming));
+    need(cudaMalloc((void**)&L.dCounters, sizeof(uint32_t) * 13 * kMaxIters));
+    need(cudaMallocHost((void**)&L.hCount, sizeof(uint32_t) * 4));
   }
   {
     // [0..255]: sRGB decode; [256..511]: i / 255 (the UNORM decode, tabulated so that texel fetches do no divisions;
@@ -1404,8 +1407,15 @@ int b200pt_create(b200pt_t** out, int cuda_device)
       lutS[i] = srgbToLinear((float)i / 255.0f);
       lutS[256 + i] = (float)i / 255.0f;
     }
-    cudaMalloc((void**)&h->dLutSrgb, sizeof(lutS));
-    cudaMemcpy(h->dLutSrgb, lutS, sizeof(lutS), cudaMemcpyHostToDevice);
+    need(cudaMalloc((void**)&h->dLutSrgb, sizeof(lutS)));
+    if(ok)
+      need(cudaMemcpy(h->dLutSrgb, lutS, sizeof(lutS), cudaMemcpyHostToDevice));
+  }
+  if(!ok)
+  {
+    cudaGetLastError();  // clear the sticky-free error state for the next attempt
+    b200pt_destroy(h);
+    return B200PT_E_CUDA;
   }
   *out = h;
   return B200PT_OK;
@@ -1426,10 +1436,14 @@ void b200pt_destroy(b200pt_t* h)
   {
     b200pt::Lane& L = h->lanes[l];
     cudaFree(L.dCounters);
-    cudaFreeHost(L.hCount);
-    cudaEventDestroy(L.done);
-    cudaEventDestroy(L.freed);
-    cudaStreamDestroy(L.stream);
+    if(L.hCount)
+      cudaFreeHost(L.hCount);
+    if(L.done)
+      cudaEventDestroy(L.done);
+    if(L.freed)
+      cudaEventDestroy(L.freed);
+    if(L.stream)
+      cudaStreamDestroy(L.stream);
   }
   if(h->dEnv)
     cudaFree(h->dEnv);
