@@ -103,3 +103,22 @@ def test_scene_blob_and_cpp_host_fail_loudly_without_gpu(tmp_path, box_scene, st
         assert "HEADLESS_SUMMARY" in out.stdout
     bad = subprocess.run([exe, "--scene", str(tmp_path / "missing.b2sc")], capture_output=True, text=True, timeout=60)
     assert bad.returncode != 0 and "cannot open" in bad.stderr
+
+
+def test_interleave_band_choices_and_bench_core_count():
+    """Band height: the largest <= 8 that tiles height / world; None when the height does not split evenly.
+    bench.usable_cores() never reports more than the scheduler affinity and at least one core."""
+    import sys
+    from vk_gltf_renderer_b200 import tiling
+    assert tiling.interleave_band(1080, 1) is None
+    assert tiling.interleave_band(1080, 2) == 6 and tiling.interleave_band(1080, 8) == 5 and tiling.interleave_band(2160, 8) == 6
+    assert tiling.interleave_band(37, 2) is None
+    for world in (2, 4, 8):
+        band = tiling.interleave_band(1080, world)
+        rows = [tiling.interleaved_rows(1080, world, r, band) for r in range(world)]
+        flat = sorted(y for rr in rows for y in rr)
+        assert flat == list(range(1080)) and all(len(rr) == 1080 // world for rr in rows)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    n = bench.usable_cores()
+    assert 1 <= n <= (os.cpu_count() or 1)

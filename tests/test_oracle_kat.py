@@ -213,3 +213,20 @@ def test_accumulation_is_running_mean(oracle_mod, box_scene, std_env):
     exp = (exp * np.float32(1) + frames[1] * np.float32(1)) / np.float32(2)
     exp = (exp * np.float32(2) + frames[2] * np.float32(1)) / np.float32(3)
     assert np.array_equal(acc, exp)
+
+
+def test_deep_layer_scenes_are_deterministic_and_stochastic(std_env, oracle_mod):
+    """The 14-layer any-hit stress scenes (used by the GPU continuation tests): the oracle is deterministic per
+    (pixel, frame) seed, frames differ (stochastic alpha), and MASK coverage lets some light through."""
+    from vk_gltf_renderer_b200 import synth
+    for kw in ({}, {"blend": True}, {"tinted": True}):
+        scn = synth.synth_layers(**kw)
+        o = oracle_mod.Oracle()
+        o.set_scene(scn)
+        o.set_environment(std_env)
+        a = oracle_mod.render(o, scn.camera, 64, 48, 2, max_depth=4)
+        b = oracle_mod.render(o, scn.camera, 64, 48, 2, max_depth=4)
+        c = oracle_mod.render(o, scn.camera, 64, 48, 3, max_depth=4)
+        assert np.array_equal(a, b) and np.isfinite(a).all()
+        assert not np.array_equal(a, c)
+        assert a[..., :3].mean() > 0.01
