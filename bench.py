@@ -94,7 +94,10 @@ def workload_config(args, scn, n_gpus):
                         % (args.width, args.height, args.depth),
             "triangles": scn.num_triangles(), "materials": len(scn.materials), "textures": len(scn.textures),
             "texture_size": args.tex, "partition": "1 GPU" if n_gpus == 1 else "interleaved row bands x%d, scene replicated, one NCCL all-gather of the RGBA32F tiles per frame" % n_gpus,
-            "l2_policy": "working set (path state 11x16 B x 2.07M paths = 365 MB + 33 MB image) exceeds the 126 MB L2 every frame"}
+            "l2_policy": "no explicit flush: every frame streams its lane's path state (248 B x %d paths per rank = %.0f MB) plus the %.0f MB image, "
+                         "and consecutive frames use different lanes; the working set exceeds the 126 MB L2 for N <= 4 "
+                         "(at N = 8 a rank's 64 MB tile state would fit, its 8 lanes together do not)"
+                         % (args.width * args.height // n_gpus, 248e-6 * args.width * args.height / n_gpus, 16e-6 * args.width * args.height)}
 
 
 class ClockSampler:
