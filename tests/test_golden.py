@@ -1,0 +1,106 @@
+"""Golden fixtures (tests/golden/*.npz, written by tests/golden/make_golden.py from the CPU oracle).
+
+CPU (-m "not gpu"): the oracle still reproduces every fixture bit for bit -- the restatement is pinned against its own
+recorded outputs, so a change to oracle/ that moves a number is caught even when the CUDA side moves with it.
+GPU (-m gpu): the CUDA path is compared with the COMMITTED vectors (no oracle call): images to 1e-3 relative RMSE with the
+solid-flag channel exact, ray hits / seeds / transmissions bit-exact, BSDF records to fp32 tolerance.
+
+The reference itself (Vulkan RT + nvpro_core2 shaders) cannot run offline and its tests hold no vectors for this path, so
+these are oracle vectors, not reference vectors: parity with the reference stays "unpinned" (DESIGN.md section 4)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import rel_rmse
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+sys.path.insert(0, GOLD)
+
+
+def _load(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def test_oracle_reproduces_golden_images(oracle_mod, box_scene, std_env):
+    from vk_gltf_renderer_b200 import synth
+    o = oracle_mod.Oracle()
+    o.set_scene(box_scene)
+    o.set_environment(std_env)
+    assert np.array_equal(oracle_mod.render(o, box_scene.camera, 64, 64, 2, max_depth=4), _load("box_64x64_f2_d4.npz")["image"])
+    lay = synth.synth_layers()
+    o = oracle_mod.Oracle()
+    o.set_scene(lay)
+    o.set_environment(std_env)
+    assert np.array_equal(oracle_mod.render(o, lay.camera, 48, 36, 2, max_depth=4), _load("layers_mask_48x36.npz")["image"])
+
+
+def test_oracle_reproduces_golden_rays_and_bsdf(oracle_mod):
+    import make_golden
+    g = _load("soup_rays_2k.npz")
+    o = oracle_mod.Oracle()
+    o.set_scene(make_golden.soup_scene())
+    rays, shadow, seeds = make_golden.soup_rays()
+    s = seeds.copy()
+    assert np.array_equal(o.trace_closest(rays, s).view(np.uint32), g["hits"].view(np.uint32)) and np.array_equal(s, g["seeds_after_closest"])
+    s = seeds.copy()
+    assert np.array_equal(o.trace_shadow(shadow, s), g["transmission"]) and np.array_equal(s, g["seeds_after_shadow"])
+    # the fixture exercises what it claims to: hits and misses, accepted and rejected alpha candidates, open and blocked segments
+    hit = g["hits"].view(np.int32)[:, 1] >= 0
+    assert 0.2 < hit.mean() < 0.98 and (g["seeds_after_closest"] != seeds).mean() > 0.2
+    assert 0.05 < (g["transmission"][:, 0] > 0).mean() < 0.95
+    b = _load("bsdf_256.npz")
+    assert np.array_equal(o.bsdf_eval(b["records"]), b["eval"]) and np.array_equal(o.bsdf_sample(b["records"]), b["sample"])
+
+
+@pytest.mark.gpu
+def test_cuda_matches_golden_images(box_scene, std_env):
+    from vk_gltf_renderer_b200 import synth
+    from vk_gltf_renderer_b200.renderer import Resources, render_headless
+    for scn, (w, h), name in ((box_scene, (64, 64), "box_64x64_f2_d4.npz"), (synth.synth_layers(), (48, 36), "layers_mask_48x36.npz")):
+        ref = _load(name)["image"]
+        _, img = render_headless(Resources(scene=scn, hdr_rgb=std_env, camera=scn.camera, size=(w, h)), 2, ptMaxDepth=4)
+        assert np.array_equal(img[..., 3], ref[..., 3])
+        assert rel_rmse(img, ref) <= 1e-3
+
+
+@pytest.mark.gpu
+def test_cuda_matches_golden_rays_and_bsdf(std_env):
+    import torch
+    import make_golden
+    from gpu_util import to_dev
+    from vk_gltf_renderer_b200.renderer import PathTracer, Resources
+    g = _load("soup_rays_2k.npz")
+    scn = make_golden.soup_scene()
+    pt = PathTracer(0)
+    pt.onAttach(Resources(scene=scn, hdr_rgb=std_env, camera=scn.camera, size=(16, 16)))
+    rays, shadow, seeds = make_golden.soup_rays()
+    d_rays, d_seeds = to_dev(rays), to_dev(seeds.copy())
+    d_hits = torch.empty((len(rays), 6), dtype=torch.float32, device="cuda")
+    pt.trace_closest(d_rays.data_ptr(), len(rays), d_hits.data_ptr(), d_seeds.data_ptr())
+    pt.synchronize()
+    got = d_hits.cpu().numpy()
+    assert np.array_equal(got.view(np.uint32)[:, 1:4], g["hits"].view(np.uint32)[:, 1:4])  # rnode / prim / triangle ids
+    assert np.array_equal(got[:, [0, 4, 5]], g["hits"][:, [0, 4, 5]])                            # t, u, v
+    assert np.array_equal(d_seeds.cpu().numpy(), g["seeds_after_closest"])
+    d_rays, d_seeds = to_dev(shadow), to_dev(seeds.copy())
+    d_t = torch.empty((len(rays), 3), dtype=torch.float32, device="cuda")
+    pt.trace_shadow(d_rays.data_ptr(), len(rays), d_t.data_ptr(), d_seeds.data_ptr())
+    pt.synchronize()
+    assert np.array_equal(d_t.cpu().numpy(), g["transmission"]) and np.array_equal(d_seeds.cpu().numpy(), g["seeds_after_shadow"])
+    b = _load("bsdf_256.npz")
+    d_in = torch.from_numpy(b["records"]).cuda()
+    d_out = torch.empty((len(b["records"]), 8), dtype=torch.float32, device="cuda")
+    pt.bsdf_eval(d_in.data_ptr(), len(b["records"]), d_out.data_ptr())
+    pt.synchronize()
+    bad = ~np.isclose(d_out.cpu().numpy(), b["eval"], rtol=2e-4, atol=1e-6).all(axis=1)
+    assert bad.sum() <= 1
+    pt.bsdf_sample(d_in.data_ptr(), len(b["records"]), d_out.data_ptr())
+    pt.synchronize()
+    got = d_out.cpu().numpy()
+    ev_ok = got[:, 7] == b["sample"][:, 7]
+    assert (~ev_ok).sum() <= 1
+    live = ev_ok & (b["sample"][:, 7] != 0)
+    assert (~np.isclose(got[live][:, :7], b["sample"][live][:, :7], rtol=5e-4, atol=2e-6).all(axis=1)).sum() <= 1
