@@ -1,0 +1,75 @@
+"""The DEVICE traversal source on the host (-m "not gpu"): csrc/traverse.cuh is compiled by g++ through tools/host_shim.h (one
+lane per warp) and checked against brute force by tools/host_traverse_check.cpp on the tree csrc/bvh.cpp builds -- nearest hit
+in (t, id) order bit for bit, any-exit occlusion, and the collecting walks (kCand nearest candidates, resumed behind the
+last one) that feed the any-hit kernels.  This is the same node decode (PRMT plane bytes, conservative slack), compressed
+stack and hit predicate the sm_100a kernels execute; what it cannot cover is warp-level scheduling."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "vk_gltf_renderer_b200", "csrc")
+CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
+
+
+@pytest.fixture(scope="module")
+def checker(tmp_path_factory):
+    if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    exe = str(tmp_path_factory.mktemp("hostcheck") / "host_traverse_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + CUDA_INC, "-o", exe, os.path.join(CSRC, "tools", "host_traverse_check.cpp"),
+                           os.path.join(CSRC, "bvh.cpp")])
+    return exe
+
+
+def _dump(path, tris, rays):
+    tr = np.concatenate([tris[:, 0], tris[:, 1] - tris[:, 0], tris[:, 2] - tris[:, 0]], 1).astype(np.float32)
+    with open(path, "wb") as f:
+        f.write(np.array([len(tr), len(rays)], np.uint32).tobytes())
+        f.write(tr.tobytes())
+        f.write(np.ascontiguousarray(rays, np.float32).tobytes())
+
+
+def _run(exe, path):
+    out = subprocess.run([exe, path], capture_output=True, text=True, timeout=600)
+    print(out.stdout)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "mismatches: nearest 0, any-exit 0, collecting 0" in out.stdout
+
+
+def test_device_traversal_source_vs_brute_force_soup(checker, tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from gpu_util import random_rays
+    rng = np.random.default_rng(3)
+    c = (rng.random((4000, 1, 3)) - 0.5) * 2
+    tris = c + (rng.random((4000, 3, 3)) - 0.5) * 0.3
+    _dump(str(tmp_path / "soup.bin"), tris, random_rays(6000, [-1, -1, -1], [1, 1, 1], seed=11))
+    _run(checker, str(tmp_path / "soup.bin"))
+
+
+def test_device_traversal_source_vs_brute_force_axis_aligned(checker, tmp_path):
+    """Flat boxes and grazing rays: a regular grid of axis-aligned quads (zero-thickness nodes, shared edges and vertices),
+    rays along the axes, along the planes, through vertices and edges, and starting on the surfaces."""
+    g = np.arange(-4, 5, dtype=np.float64) * 0.25
+    quads = []
+    for k, z in enumerate(g[::2]):                      # layers of z-planes, x-planes and y-planes
+        for x0 in g[:-1]:
+            for y0 in g[:-1]:
+                p = np.array([[x0, y0, z], [x0 + 0.25, y0, z], [x0 + 0.25, y0 + 0.25, z], [x0, y0 + 0.25, z]])
+                for perm in ((0, 1, 2), (2, 0, 1), (1, 2, 0))[k % 3:k % 3 + 1]:
+                    q = p[:, perm]
+                    quads.append([q[0], q[1], q[2]])
+                    quads.append([q[0], q[2], q[3]])
+    tris = np.array(quads)
+    rng = np.random.default_rng(5)
+    rays = np.zeros((5000, 8), np.float32)
+    o = rng.choice(g, size=(5000, 3)) + rng.choice([0.0, 0.0, 0.125, 1e-6], size=(5000, 3))   # on grid lines, cell centres, just off
+    d = rng.choice([-1.0, 0.0, 1.0, 0.5, -0.25], size=(5000, 3))
+    d[(d == 0).all(1)] = [0.0, 0.0, 1.0]
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 0:3], rays[:, 4:7], rays[:, 7] = o - 2.0 * d * (rng.random((5000, 1)) > 0.3), d, 1e32
+    _dump(str(tmp_path / "grid.bin"), tris, rays)
+    _run(checker, str(tmp_path / "grid.bin"))
