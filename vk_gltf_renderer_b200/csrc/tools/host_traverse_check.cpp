@@ -48,6 +48,7 @@ int main(int argc, char** argv)
   std::printf("tris %u nodes %u rays %u kCand %d\n", B.numTris, B.numNodes, nR, kCand);
 
   uint64_t bad1 = 0, bad2 = 0, bad3 = 0, hits = 0, listed = 0;
+  int      maxSp = 0;
   std::vector<BF> bf;
   for(uint32_t r = 0; r < nR; r++)
   {
@@ -72,8 +73,16 @@ int main(int argc, char** argv)
         bf.push_back(BF{t, i});
     }
     std::sort(bf.begin(), bf.end(), [](const BF& a, const BF& b) { return a.t < b.t || (a.t == b.t && a.gid < b.gid); });
-    // (1) nearest hit
-    const TraceHit h = traverseNext<false, false>(view, org, dir, tmin, tmax, false, 0.f, 0u);
+    // (1) nearest hit (stepped by hand to record the deepest stack the walk needed; kStackSize entries exist)
+    TraceHit h;
+    {
+      TravState T;
+      uint2     stack[TravState::kStackSize];
+      T.init(view, org, dir, tmin, tmax, false, false, false, 0.f, 0u);
+      while(!T.step(stack))
+        maxSp = std::max(maxSp, T.sp);
+      h = T.result();
+    }
     if(bf.empty() ? (h.slot != 0xFFFFFFFFu) : (h.slot == 0xFFFFFFFFu || __float_as_uint(h.t) != __float_as_uint(bf[0].t) || h.gid != bf[0].gid))
       bad1++;
     hits += !bf.empty();
@@ -104,7 +113,9 @@ int main(int argc, char** argv)
       listed += k;
     }
   }
-  std::printf("hit rate %.3f, %.2f candidates per ray | mismatches: nearest %llu, any-exit %llu, collecting %llu\n", (double)hits / nR, (double)listed / nR,
-              (unsigned long long)bad1, (unsigned long long)bad2, (unsigned long long)bad3);
+  std::printf("hit rate %.3f, %.2f candidates per ray, deepest stack %d of %d | mismatches: nearest %llu, any-exit %llu, collecting %llu\n", (double)hits / nR,
+              (double)listed / nR, maxSp, TravState::kStackSize, (unsigned long long)bad1, (unsigned long long)bad2, (unsigned long long)bad3);
+  if(maxSp >= TravState::kStackSize)
+    return 1;
   return (bad1 | bad2 | bad3) ? 1 : 0;
 }
