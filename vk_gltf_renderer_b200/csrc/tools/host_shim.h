@@ -1,6 +1,6 @@
 // host_shim.h — lets g++ compile the DEVICE traversal code (../traverse.cuh, ../vec.cuh) for the host, one "lane" at a
 // time, so that the exact source the sm_100a kernels run can be checked against brute force without a GPU
-// (tools/host_traverse_check.cpp, tests/test_host_traverse.py).  Only what traverse.cuh uses is provided.
+// (tools/host_traverse_check.cpp, tests/test_device_source_on_host.py).  Only what traverse.cuh uses is provided.
 #pragma once
 #include <cuda_runtime.h>  // vector types; __host__ / __device__ expand to nothing outside nvcc
 
@@ -11,6 +11,9 @@
 #ifndef __CUDACC__
 #ifndef __forceinline__
 #define __forceinline__ inline
+#endif
+#ifndef __noinline__
+#define __noinline__ __attribute__((noinline))
 #endif
 static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 static inline float    __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
@@ -29,6 +32,8 @@ static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s)
     r |= (uint32_t)((pool >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
   return r;
 }
+using std::isnan;
+using std::isinf;
 // one lane per "warp"
 static inline unsigned __activemask() { return 1u; }
 static inline unsigned __ballot_sync(unsigned, int pred) { return pred ? 1u : 0u; }
