@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200PT_ABI_VERSION 2
+#define B200PT_ABI_VERSION 3
 
 /* error codes */
 #define B200PT_OK 0
@@ -36,6 +36,7 @@ extern "C" {
 #define B200PT_E_CUDA -2        /* CUDA runtime error (see b200pt_last_error)        */
 #define B200PT_E_NOMEM -3       /* host or device allocation failed                  */
 #define B200PT_E_UNSUPPORTED -4 /* feature outside the built path (e.g. physical sky) */
+#define B200PT_E_DEVICE -5      /* a kernel raised a device-side error flag (traversal stack overflow): results incomplete */
 
 typedef struct b200pt b200pt_t; /* opaque renderer handle */
 

@@ -1,7 +1,8 @@
 """The DEVICE traversal source on the host (-m "not gpu"): csrc/traverse.cuh is compiled by g++ through tools/host_shim.h (one
-lane per warp) and checked against brute force by tools/host_traverse_check.cpp on the tree csrc/bvh.cpp builds -- nearest hit
-in (t, id) order bit for bit, any-exit occlusion, and the collecting walks (kCand nearest candidates, resumed behind the
-last one) that feed the any-hit kernels.  This is the same node decode (PRMT plane bytes, conservative slack), compressed
+lane per warp) and checked against brute force by tools/host_traverse_check.cpp on the tree csrc/bvh.cpp builds -- the single-tree
+closest walk (nearest opaque hit + the candidates in front of it, continuation walks resumed behind the last candidate and
+refining the opaque hit) and the shadow walk (opaque occluder anywhere on the segment, else every candidate in order), with a
+third and with seven eighths of the triangles flagged non-opaque.  This is the same node decode (PRMT plane bytes, conservative slack), compressed
 stack and hit predicate the sm_100a kernels execute; what it cannot cover is warp-level scheduling."""
 import os
 import subprocess
@@ -34,10 +35,11 @@ def _dump(path, tris, rays):
 
 
 def _run(exe, path):
-    out = subprocess.run([exe, path], capture_output=True, text=True, timeout=600)
-    print(out.stdout)
-    assert out.returncode == 0, out.stdout + out.stderr
-    assert "mismatches: nearest 0, any-exit 0, collecting 0" in out.stdout
+    for mod in ("3", "-8"):
+        out = subprocess.run([exe, path, "1000000", mod], capture_output=True, text=True, timeout=600)
+        print(out.stdout)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "mismatches: nearest opaque 0, shadow 0, candidates 0" in out.stdout
 
 
 def test_device_traversal_source_vs_brute_force_soup(checker, tmp_path):

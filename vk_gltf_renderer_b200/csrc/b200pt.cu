@@ -174,32 +174,43 @@ __device__ __forceinline__ uint32_t fetchWork(bool need, uint32_t* workCounter, 
   return k < count ? k : 0xFFFFFFFFu;
 }
 
-// IRaytracer::Trace, geometry part, for every path in the queue: closest FORCE_OPAQUE hit, then (scenes with
-// non-opaque triangles) the kCand nearest any-hit candidates in front of it.  The stochastic alpha tests need
-// textures and touch only the few lanes whose walk just ended -- inside this kernel they ran with ~2 of 32 lanes
-// active and took 17 % of its instructions / 26 % of its stall samples (ncu, profiles/) -- so they live in the
-// dense kernel k_alpha; this kernel only writes the candidates out.
+// IRaytracer::Trace, geometry part, for every path in the queue: ONE walk of the scene tree gives the closest
+// FORCE_OPAQUE hit and the kCand nearest any-hit candidates in front of it (traverse.cuh).  The stochastic alpha
+// tests need textures and touch only the few lanes whose walk just ended -- inside this kernel they ran with ~2 of
+// 32 lanes active and took 17 % of its instructions / 26 % of its stall samples (ncu, profiles/) -- so they live in
+// the dense kernel k_alpha; this kernel only writes the candidates out.
 // Per lane: path (-1 needs work, -2 exhausted) and a resumable traversal; finished lanes are handled in the
 // converged part of the loop, never inside the traversal loop.
+// mode: TRACE_CONT = continuation round (the paths in the queue had all kCand candidates rejected by k_alpha and resume
+// behind the last one; P.hit seeds the opaque bound and is refined), TRACE_TMIN = rayO.w carries tmin (ray-level API).
 #ifndef B200PT_TRACE_MINBLOCKS
 #define B200PT_TRACE_MINBLOCKS 6  // 80 registers: 6 blocks/SM; measured 470 -> 488 Mray/s against the unconstrained 96-register build
 #endif
+enum : int
+{
+  TRACE_CONT = 1,
+  TRACE_TMIN = 2,
+};
 __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_trace(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn,
                                                                        uint32_t* workCounter, uint32_t* qAlpha, uint32_t* cntAlpha, DevStats* stats, int refillThreshold,
-                                                                       int postponeShift, int cont)
+                                                                       int postponeShift, int mode)
 {
-  // cont != 0: continuation round -- the paths in the queue had all kCand candidates rejected by k_alpha and
-  // resume the any-hit walk behind the last one (P.hit keeps the opaque hit, which still bounds the walk)
-  const uint32_t count = *cntIn;
-  TravState      T;
-  uint2          stack[TravState::kStackSize];
-  Cand           cand[kCand];
-  int            path = -1;
-  int            phase = 0;        // 0: opaque tree, 1: alpha (any-hit) tree, collecting
-  bool           travDone = false;  // traversal finished, write-out pending
-  TraceHit       ho;
-  float          tmaxRay = 0.f;
-  ho.slot = 0xFFFFFFFFu;
+  __shared__ Cand s_cand[kCand * 128];  // candidate lists, one column per thread (20-byte stride: conflict-free)
+  Cand* const     cand = &s_cand[threadIdx.x];
+  constexpr int   cs = 128;
+  const bool      cont = (mode & TRACE_CONT) != 0;
+  const uint32_t  count = *cntIn;
+  TravState       T;
+#ifdef B200PT_SMEM_STACK
+  __shared__ uint2 s_stack[TravState::kStackSize * 128];
+  uint2* const     stack = &s_stack[threadIdx.x];
+  constexpr int    SS = 128;
+#else
+  uint2         stack[TravState::kStackSize];
+  constexpr int SS = 1;
+#endif
+  int             path = -1;
+  bool            travDone = false;  // traversal finished, write-out pending
   for(;;)
   {
     __syncwarp();
@@ -207,28 +218,24 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_trace(PathState
     {
       travDone = false;
       T.flushCounters(&stats->nodesVisited, &stats->trisTested);
-      if(phase == 0)
-        ho = T.result();
-      if(phase == 0 && S.hasAlpha)
+      const TraceHit ho = T.result();
+      P.hit[path] = f4(ho.t, ho.u, ho.v, __uint_as_float(ho.slot));
+      const int n = T.candidatesInFront(cand, cs);
+      if(n > 0)
       {
-        // non-opaque candidates nearer than the opaque hit (raytracer_interface.h.slang:82-112)
-        phase = 1;
-        T.init(S.bvhAlpha, T.org, T.dir, 0.0f, (ho.slot != 0xFFFFFFFFu) ? ho.t : tmaxRay, true, false, false, 0.f, 0u, true);
+#pragma unroll
+        for(int i = 0; i < kCand; i++)
+          if(i < n)
+          {
+            const Cand c = cand[i * cs];
+            P.cand[i][path] = f4(c.t, c.u, c.v, __uint_as_float(c.slot));
+          }
+        P.candInfo[path] = make_uint2((uint32_t)n, cand[(n - 1) * cs].gid);
+        queuePush(qAlpha, cntAlpha, (uint32_t)path);
       }
-      else
-      {
-        if(!cont)
-          P.hit[path] = f4(ho.t, ho.u, ho.v, __uint_as_float(ho.slot));
-        const int n = (phase == 1) ? T.collectN : 0;
-        if(n > 0)
-        {
-          for(int i = 0; i < n; i++)
-            P.cand[i][path] = f4(cand[i].t, cand[i].u, cand[i].v, __uint_as_float(cand[i].slot));
-          P.candInfo[path] = make_uint2((uint32_t)n, cand[n - 1].gid);
-          queuePush(qAlpha, cntAlpha, (uint32_t)path);
-        }
-        path = -1;
-      }
+      if(T.overflow)
+        atomicOr(&stats->errorFlags, 1ull);
+      path = -1;
     }
     __syncwarp();
     // ---- refill ----
@@ -244,18 +251,15 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_trace(PathState
           path = (int)q[k];
           const float4 o = P.rayO[path];
           const float4 d = P.rayD[path];
-          tmaxRay = d.w;
+          const float  tmin = (mode & TRACE_TMIN) ? o.w : 0.0f;
           if(!cont)
-          {
-            phase = 0;
-            T.init(S.bvh, xyz(o), xyz(d), 0.0f, tmaxRay, true, false, false, 0.f, 0u);
-          }
+            T.init(S.bvh, xyz(o), xyz(d), tmin, d.w, true, false, false, 0.f, 0u);
           else
           {
+            T.init(S.bvh, xyz(o), xyz(d), tmin, d.w, true, false, true, P.cand[kCand - 1][path].x, P.candInfo[path].y);
             const float4 hp = P.hit[path];
-            phase = 1;
-            T.init(S.bvhAlpha, xyz(o), xyz(d), 0.0f, (__float_as_uint(hp.w) != 0xFFFFFFFFu) ? hp.x : tmaxRay, true, false, true, P.cand[kCand - 1][path].x,
-                   P.candInfo[path].y, true);
+            if(__float_as_uint(hp.w) != 0xFFFFFFFFu)
+              T.seedOpaque(hp.x, hp.y, hp.z, __float_as_uint(hp.w));
           }
         }
       }
@@ -277,7 +281,7 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_trace(PathState
       }
 #endif
       if(path >= 0 && !travDone)
-        travDone = T.step(stack, postponeShift, cand);
+        travDone = T.step<SS>(stack, postponeShift, cand, cs);
       if(__popc(__ballot_sync(0xffffffffu, path >= 0 && !travDone)) < refillThreshold)
         break;
     }
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_trace(PathState
 // behind the last candidate); in the last round (qCont == nullptr) it keeps walking right here instead.
 template <bool SHADOW>
 __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn, uint32_t* qCont,
-                                               uint32_t* cntCont, int cont)
+                                               uint32_t* cntCont, DevStats* stats, int mode)
 {
   static_assert(kCand == 4 || kCand == 8, "kCand lanes per path");
   stageSrgbLut(S.lutSrgb);
@@ -356,17 +360,21 @@ __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const ui
       }
       else if(acc < 0 && n == kCand)
       {
-        // every collected candidate was rejected and there may be more: keep walking, kCand at a time
-        // (the lanes of the group do this redundantly, lane 0 writes)
-        const float4 o = P.rayO[path], d = P.rayD[path], ho = P.hit[path];
-        const float  tmax = (__float_as_uint(ho.w) != 0xFFFFFFFFu) ? ho.x : d.w;
-        float        loT = lastT;
-        uint32_t     loId = info.y;
-        Cand         cand[kCand];
-        bool         accepted = false;
+        // every collected candidate was rejected and there may be more: keep walking, kCand at a time (the lanes of
+        // the group do this redundantly, lane 0 writes).  Each walk also refines the opaque hit (traverse.cuh).
+        const float4 o = P.rayO[path], d = P.rayD[path], hp = P.hit[path];
+        const float  tmin = (mode & TRACE_TMIN) ? o.w : 0.0f;
+        TraceHit     opq;
+        opq.slot = 0xFFFFFFFFu;
+        if(__float_as_uint(hp.w) != 0xFFFFFFFFu)
+          opq = seedHit(S.bvh, hp.x, hp.y, hp.z, __float_as_uint(hp.w));
+        float    loT = lastT;
+        uint32_t loId = info.y;
+        Cand     cand[kCand];
+        bool     accepted = false, overflowed = false;
         for(;;)
         {
-          const int m = collectNext(S.bvhAlpha, xyz(o), xyz(d), tmax, true, true, loT, loId, cand);
+          const int m = walkCollect(S.bvh, xyz(o), xyz(d), tmin, d.w, true, false, true, loT, loId, opq, cand, &overflowed);
           for(int i = 0; i < m && !accepted; i++)
           {
             const uint2               meta = S.triMeta[cand[i].slot];
@@ -386,13 +394,20 @@ __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const ui
           loT = cand[kCand - 1].t;
           loId = cand[kCand - 1].gid;
         }
+        if(!accepted && sub == 0 && opq.slot != 0xFFFFFFFFu)
+        {
+          const TraceHit ho = unflipHit(opq);
+          P.hit[path] = f4(ho.t, ho.u, ho.v, __uint_as_float(ho.slot));
+        }
+        if(overflowed && sub == 0)
+          atomicOr(&stats->errorFlags, 1ull);
       }
     }
     else
     {
       // a continuation round resumes with the running transmission and segment start the previous round parked
       // in P.hit (free between shading and the next k_trace)
-      const float4 saved = (valid && cont) ? P.hit[path] : f4(1.0f, 1.0f, 1.0f, 0.0f);
+      const float4 saved = (valid && (mode & TRACE_CONT)) ? P.hit[path] : f4(1.0f, 1.0f, 1.0f, 0.0f);
       float3       total = xyz(saved);
       float        prevHitT = saved.w;
       bool         done = false, parked = false;
@@ -442,9 +457,18 @@ __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const ui
         float        loT = lastT;
         uint32_t     loId = info.y;
         Cand         cand[kCand];
+        bool         overflowed = false;
         while(!done)
         {
-          const int m = collectNext(S.bvhAlpha, xyz(so), dir, so.w, false, true, loT, loId, cand);
+          TraceHit opq;
+          opq.slot = 0xFFFFFFFFu;
+          const int m = walkCollect(S.bvh, xyz(so), dir, 0.0f, so.w, false, true, true, loT, loId, opq, cand, &overflowed);
+          if(opq.slot != 0xFFFFFFFFu)
+          {
+            // (the first walk of the segment found no opaque occluder, so none can turn up here)
+            total = f3(0.0f);
+            done = true;
+          }
           for(int i = 0; i < m && !done; i++)
           {
             const uint2               meta = S.triMeta[cand[i].slot];
@@ -460,6 +484,8 @@ __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const ui
           loT = cand[kCand - 1].t;
           loId = cand[kCand - 1].gid;
         }
+        if(overflowed && sub == 0)
+          atomicOr(&stats->errorFlags, 1ull);
       }
       if(valid && sub == 0 && !parked)
       {
@@ -840,20 +866,29 @@ __device__ void finishPost(const PathState& P, const FrameParams& F, uint32_t i,
   queuePush(qNext, cntNext, i);
 }
 
-// IRaytracer::TraceShadow, geometry part, for every path with a pending NEE shadow ray: any FORCE_OPAQUE occluder
-// ends the query (raytracer_interface.h.slang:181-184), otherwise the kCand nearest non-opaque candidates are
-// written out for k_resolve.  Same persistent-warp scheme as k_trace.
+// IRaytracer::TraceShadow, geometry part, for every path with a pending NEE shadow ray: ONE walk of the scene tree along
+// the whole segment; any FORCE_OPAQUE occluder ends the query (raytracer_interface.h.slang:181-184), otherwise the kCand
+// nearest non-opaque candidates are written out for k_alpha<true>.  Same persistent-warp scheme as k_trace.
 __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn,
                                                                         uint32_t* workCounter, uint32_t* qAlpha, uint32_t* cntAlpha, DevStats* stats,
-                                                                        int refillThreshold, int postponeShift, int cont)
+                                                                        int refillThreshold, int postponeShift, int mode)
 {
-  const uint32_t count = *cntIn;
-  TravState      T;
-  uint2          stack[TravState::kStackSize];
-  Cand           cand[kCand];
-  int            path = -1;  // -1: lane needs work, -2: queue exhausted
-  int            phase = 0;  // 0: opaque occlusion query, 1: any-hit candidates, collecting
-  bool           travDone = false;
+  __shared__ Cand s_cand[kCand * 128];
+  Cand* const     cand = &s_cand[threadIdx.x];
+  constexpr int   cs = 128;
+  const bool      cont = (mode & TRACE_CONT) != 0;
+  const uint32_t  count = *cntIn;
+  TravState       T;
+#ifdef B200PT_SMEM_STACK
+  __shared__ uint2 s_stack[TravState::kStackSize * 128];
+  uint2* const     stack = &s_stack[threadIdx.x];
+  constexpr int    SS = 128;
+#else
+  uint2         stack[TravState::kStackSize];
+  constexpr int SS = 1;
+#endif
+  int             path = -1;  // -1: lane needs work, -2: queue exhausted
+  bool            travDone = false;
   for(;;)
   {
     __syncwarp();
@@ -861,29 +896,28 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathStat
     {
       travDone = false;
       T.flushCounters(&stats->nodesVisited, &stats->trisTested);
-      if(phase == 0 && T.best.slot == 0xFFFFFFFFu && S.hasAlpha)
-      {
-        phase = 1;
-        T.init(S.bvhAlpha, T.org, T.dir, 0.0f, T.tmax, false, false, false, 0.f, 0u, true);
-      }
+      uint2 info = make_uint2(0u, 0u);
+      if(T.best.slot != 0xFFFFFFFFu)
+        info.x = 0x80000000u;  // an opaque occluder ended the query (raytracer_interface.h.slang:181-184)
       else
       {
-        uint2 info = make_uint2(0u, 0u);
-        if(phase == 0)
-          info.x = (T.best.slot != 0xFFFFFFFFu) ? 0x80000000u : 0u;
-        else
-        {
-          const int n = T.collectN;
-          for(int i = 0; i < n; i++)
-            P.cand[i][path] = f4(cand[i].t, cand[i].u, cand[i].v, __uint_as_float(cand[i].slot));
-          info = make_uint2((uint32_t)n, n > 0 ? cand[n - 1].gid : 0u);
-        }
-        P.candInfo[path] = info;
-        // (a continuation path always goes back to k_alpha: its running transmission is parked and must be folded)
-        if((info.x != 0u && info.x != 0x80000000u) || cont)
-          queuePush(qAlpha, cntAlpha, (uint32_t)path);
-        path = -1;
+        const int n = T.collectN;
+#pragma unroll
+        for(int i = 0; i < kCand; i++)
+          if(i < n)
+          {
+            const Cand c = cand[i * cs];
+            P.cand[i][path] = f4(c.t, c.u, c.v, __uint_as_float(c.slot));
+          }
+        info = make_uint2((uint32_t)n, n > 0 ? cand[(n - 1) * cs].gid : 0u);
       }
+      P.candInfo[path] = info;
+      // (a continuation path always goes back to k_alpha: its running transmission is parked and must be folded)
+      if((info.x != 0u && info.x != 0x80000000u) || cont)
+        queuePush(qAlpha, cntAlpha, (uint32_t)path);
+      if(T.overflow)
+        atomicOr(&stats->errorFlags, 1ull);
+      path = -1;
     }
     __syncwarp();
     {
@@ -899,15 +933,9 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathStat
           const float4 so = P.shO[path];
           const float4 sd = P.shD[path];
           if(!cont)
-          {
-            phase = 0;
             T.init(S.bvh, xyz(so), xyz(sd), 0.0f, so.w, false, true, false, 0.f, 0u);
-          }
           else
-          {
-            phase = 1;
-            T.init(S.bvhAlpha, xyz(so), xyz(sd), 0.0f, so.w, false, false, true, P.cand[kCand - 1][path].x, P.candInfo[path].y, true);
-          }
+            T.init(S.bvh, xyz(so), xyz(sd), 0.0f, so.w, false, true, true, P.cand[kCand - 1][path].x, P.candInfo[path].y);
         }
       }
     }
@@ -926,7 +954,7 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathStat
       }
 #endif
       if(path >= 0 && !travDone)
-        travDone = T.step(stack, postponeShift, cand);
+        travDone = T.step<SS>(stack, postponeShift, cand, cs);
       if(__popc(__ballot_sync(0xffffffffu, path >= 0 && !travDone)) < refillThreshold)
         break;
     }
@@ -980,54 +1008,71 @@ __global__ void __launch_bounds__(256) k_accumulate(PathState P, const __grid_co
   }
 }
 
-// ---- ray-level kernels (parity tests / traversal micro-benchmark) ---------------------------------
-__global__ void __launch_bounds__(128) k_trace_rays(DevScene S, const float4* __restrict__ rays, uint32_t n, float* __restrict__ hits, uint32_t* seeds, DevStats* stats)
+// ---- ray-level API (parity tests / traversal micro-benchmark): the rays run through the PRODUCTION kernels
+// (k_trace / k_shadow -> k_alpha -> continuation round -> k_alpha) on a scratch path pool -------------------------
+__global__ void __launch_bounds__(256) k_rays_load(PathState P, const float4* __restrict__ rays, uint32_t n, const uint32_t* __restrict__ seeds, uint32_t* q, uint32_t* cnt,
+                                                   int shadow)
 {
-  stageSrgbLut(S.lutSrgb);
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-  {
-    const float4   o = rays[i * 2], d = rays[i * 2 + 1];
-    uint32_t       seed = seeds ? seeds[i] : 0u;
-    const TraceHit h = traceClosest(S, xyz(o), xyz(d), o.w, d.w, seed, stats);
-    if(seeds)
-      seeds[i] = seed;
-    float* out = hits + (size_t)i * 6;
-    int    rnode = -1, rprim = -1, primId = -1;
-    float  t = kInfinite, u = 0.f, v = 0.f;
-    if(h.slot != 0xFFFFFFFFu)
-    {
-      const uint2 meta = S.triMeta[h.slot];
-      rnode = (int)(meta.x & 0x0fffffffu);
-      rprim = S.nodes[rnode].renderPrimID;
-      primId = (int)meta.y;
-      t = h.t;
-      u = h.u;
-      v = h.v;
-    }
-    out[0] = t;
-    out[1] = __int_as_float(rnode);
-    out[2] = __int_as_float(rprim);
-    out[3] = __int_as_float(primId);
-    out[4] = u;
-    out[5] = v;
-  }
-}
-
-__global__ void __launch_bounds__(128) k_shadow_rays(DevScene S, const float4* __restrict__ rays, uint32_t n, float* __restrict__ out, uint32_t* seeds, DevStats* stats)
-{
-  stageSrgbLut(S.lutSrgb);
   const uint32_t stride = gridDim.x * blockDim.x;
   for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
   {
     const float4 o = rays[i * 2], d = rays[i * 2 + 1];
-    uint32_t     seed = seeds ? seeds[i] : 0u;
-    const float3 T = traceShadow(S, xyz(o), xyz(d), d.w, seed, false, stats);
+    if(!shadow)
+    {
+      P.rayO[i] = o;  // .w = tmin (TRACE_TMIN)
+      P.rayD[i] = d;  // .w = tmax
+    }
+    else
+    {
+      P.shO[i] = f4(o.x, o.y, o.z, d.w);
+      P.shD[i] = f4(d.x, d.y, d.z, 0.0f);
+      P.shC[i] = f4(1.0f, 1.0f, 1.0f, 0.0f);
+    }
+    P.misc[i] = f4(0.0f, 0.0f, __uint_as_float(shadow ? PF_SHADOW_VALID : 0u), __uint_as_float(seeds ? seeds[i] : 0u));
+    P.candInfo[i] = make_uint2(0u, 0u);
+    q[i] = i;
+  }
+  if(blockIdx.x == 0 && threadIdx.x == 0)
+    *cnt = n;
+}
+
+__global__ void __launch_bounds__(256) k_rays_store(PathState P, DevScene S, uint32_t n, float* __restrict__ out, uint32_t* seeds, int shadow)
+{
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
     if(seeds)
-      seeds[i] = seed;
-    out[i * 3] = T.x;
-    out[i * 3 + 1] = T.y;
-    out[i * 3 + 2] = T.z;
+      seeds[i] = __float_as_uint(P.misc[i].w);
+    if(shadow)
+    {
+      const float4 c = P.shC[i];
+      const bool   occluded = (P.candInfo[i].x & 0x80000000u) != 0;
+      out[i * 3] = occluded ? 0.0f : c.x;
+      out[i * 3 + 1] = occluded ? 0.0f : c.y;
+      out[i * 3 + 2] = occluded ? 0.0f : c.z;
+      continue;
+    }
+    const float4   h = P.hit[i];
+    const uint32_t slot = __float_as_uint(h.w);
+    float*         o = out + (size_t)i * 6;
+    int            rnode = -1, rprim = -1, primId = -1;
+    float          t = kInfinite, u = 0.f, v = 0.f;
+    if(slot != 0xFFFFFFFFu)
+    {
+      const uint2 meta = S.triMeta[slot];
+      rnode = (int)(meta.x & 0x0fffffffu);
+      rprim = S.nodes[rnode].renderPrimID;
+      primId = (int)meta.y;
+      t = h.x;
+      u = h.y;
+      v = h.z;
+    }
+    o[0] = t;
+    o[1] = __int_as_float(rnode);
+    o[2] = __int_as_float(rprim);
+    o[3] = __int_as_float(primId);
+    o[4] = u;
+    o[5] = v;
   }
 }
 
@@ -1160,6 +1205,12 @@ struct b200pt
   int                lastLane = -1;
   cudaEvent_t        readDone[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::vector<void*> poolAllocs;
+  // scratch pool of the ray-level API (b200pt_trace_closest / b200pt_trace_shadow run the production kernels on it)
+  PathState          rayP{};
+  uint32_t*          rayQ[3] = {nullptr, nullptr, nullptr};  // rays, any-hit, continuation
+  uint32_t*          rayCounters = nullptr;                  // 8 words
+  uint32_t           rayCapacity = 0;
+  std::vector<void*> rayAllocs;
   DevStats*          dStats = nullptr;
   float*             dLutSrgb = nullptr;
 
@@ -1207,6 +1258,55 @@ int upload(b200pt* h, std::vector<void*>& owner, const T* src, size_t count, T**
   return 0;
 }
 
+// the SoA arrays of one path pool (device_scene.cuh: PathState) for n paths
+int allocPathState(b200pt* h, std::vector<void*>& owner, size_t n, PathState& P)
+{
+  P = PathState{};
+  float4** arrays[] = {&P.rayO, &P.rayD, &P.hit, &P.thr, &P.rad, &P.misc, reinterpret_cast<float4**>(&P.medium), &P.pixSum, &P.shO, &P.shD, &P.shC};
+  for(float4** a : arrays)
+  {
+    void* d = nullptr;
+    if(cudaMalloc(&d, std::max<size_t>(n, 1) * 16) != cudaSuccess)
+    {
+      cudaGetLastError();
+      h->err = "path pool: out of device memory";
+      return B200PT_E_NOMEM;
+    }
+    owner.push_back(d);
+    *a = reinterpret_cast<float4*>(d);
+  }
+  for(int k = 0; k < kCand; k++)
+  {
+    void* d = nullptr;
+    if(cudaMalloc(&d, std::max<size_t>(n, 1) * 16) != cudaSuccess)
+    {
+      cudaGetLastError();
+      h->err = "path pool: out of device memory";
+      return B200PT_E_NOMEM;
+    }
+    owner.push_back(d);
+    P.cand[k] = reinterpret_cast<float4*>(d);
+  }
+  void* d = nullptr;
+  if(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(uint2)) != cudaSuccess)
+  {
+    cudaGetLastError();
+    h->err = "path pool: out of device memory";
+    return B200PT_E_NOMEM;
+  }
+  owner.push_back(d);
+  P.candInfo = reinterpret_cast<uint2*>(d);
+  return B200PT_OK;
+}
+
+void freeRayPool(b200pt* h)
+{
+  for(void* p : h->rayAllocs)
+    cudaFree(p);
+  h->rayAllocs.clear();
+  h->rayCapacity = 0;
+}
+
 void freeScene(b200pt* h)
 {
   for(void* p : h->sceneAllocs)
@@ -1232,6 +1332,14 @@ void freePool(b200pt* h)
     cudaFree(p);
   h->poolAllocs.clear();
   h->dAccumOwned = nullptr;
+  h->dAccum = nullptr;
+  h->numPaths = 0;
+  for(int l = 0; l < b200pt::kMaxLanes; l++)
+  {
+    h->lanes[l].P = PathState{};
+    for(int k = 0; k < 6; k++)
+      h->lanes[l].dQ[k] = nullptr;
+  }
 }
 
 void flushEvents(b200pt* h)
@@ -1351,6 +1459,23 @@ void describeTexture(const b200pt_texture& src, const MipChain& mc, DevTex& dev)
 
 int gridFor(const b200pt* h, int perSM) { return h->numSMs * perSM; }
 
+// device-side error flags (DevStats::errorFlags) -> error code; the flag stays set until b200pt_reset_stats
+int checkDeviceErrors(b200pt* h)
+{
+  unsigned long long flags = 0;
+  if(cudaMemcpy(&flags, &h->dStats->errorFlags, sizeof(flags), cudaMemcpyDeviceToHost) != cudaSuccess)
+  {
+    h->err = "reading the device error flags failed";
+    return B200PT_E_CUDA;
+  }
+  if(flags & 1ull)
+  {
+    h->err = "a traversal stack overflowed: the BVH is deeper than the kernels' stack, results are incomplete";
+    return B200PT_E_DEVICE;
+  }
+  return B200PT_OK;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -1429,6 +1554,7 @@ void b200pt_destroy(b200pt_t* h)
   syncAll(h);
   freeScene(h);
   freePool(h);
+  freeRayPool(h);
   for(int k = 0; k < 8; k++)
     if(h->readDone[k])
       cudaEventDestroy(h->readDone[k]);
@@ -1504,6 +1630,14 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
     for(uint32_t i = 0; i < s->numMaterials; i++)
     {
       const b200pt_shade_material& m = s->materials[i];
+      // the 22 texture slots index GltfTextureInfo[] (0 = none, shaders/gltf_scene_io.h.slang:196-219)
+      const uint16_t* slots = &m.pbrBaseColorTexture;
+      for(int k = 0; k < 22; k++)
+        if(slots[k] != 0 && slots[k] >= s->numTextureInfos)
+        {
+          h->err = "b200pt_set_scene: material texture slot beyond numTextureInfos";
+          return B200PT_E_INVALID;
+        }
       if(m.transmissionFactor > 0.0f || m.transmissionTexture)
         feat |= FEAT_TRANSMISSION;
       if(m.thicknessFactor > 0.0f || m.thicknessTexture || m.multiscatterColorFactor[0] > 0.0f || m.multiscatterColorFactor[1] > 0.0f || m.multiscatterColorFactor[2] > 0.0f)
@@ -1662,13 +1796,22 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
       return B200PT_E_INVALID;
     }
     const b200pt_render_primitive& p = s->renderPrimitives[node.renderPrimID];
-    const b200pt_shade_material&   m = s->materials[std::min<uint32_t>((uint32_t)std::max(0, node.materialID), s->numMaterials - 1)];
+    if(node.materialID >= (int)s->numMaterials)
+    {
+      h->err = "render node references a missing material";
+      return B200PT_E_INVALID;
+    }
+    const b200pt_shade_material&   m = s->materials[(uint32_t)std::max(0, node.materialID)];
     uint32_t                       flags = 0;
     if(m.transmissionFactor == 0.0f && m.alphaMode == 0 && m.diffuseTransmissionFactor == 0.0f)
       flags |= TRI_OPAQUE;
     if(m.doubleSided == 1 || m.thicknessFactor > 0.0f || m.transmissionFactor > 0.0f)
       flags |= TRI_NOCULL;
-    if(m.thicknessFactor > 0.0f)
+    // a path can take more than maxDepth wavefront iterations exactly when k_shade can scatter inside a medium: that
+    // is gated on the medium's scatter coefficient (multiscatterColorFactor), not on thickness (makeVolumeMedium runs on
+    // every transmission event, pathtrace_functions.h.slang:118-140, 605-672)
+    if((m.transmissionFactor > 0.0f || m.transmissionTexture || m.diffuseTransmissionFactor > 0.0f || m.diffuseTransmissionTexture)
+       && (m.multiscatterColorFactor[0] > 0.0f || m.multiscatterColorFactor[1] > 0.0f || m.multiscatterColorFactor[2] > 0.0f))
       h->hasVolume = true;
     const float* a = node.objectToWorld;
     const float  det = a[0] * (a[5] * a[10] - a[9] * a[6]) - a[4] * (a[1] * a[10] - a[9] * a[2]) + a[8] * (a[1] * a[6] - a[5] * a[2]);
@@ -1679,6 +1822,11 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
       for(int k = 0; k < 3; k++)
       {
         const uint32_t vi = p.indices[t * 3 + k];
+        if(vi >= p.vertexCount)
+        {
+          h->err = "b200pt_set_scene: index beyond the primitive's vertex count";
+          return B200PT_E_INVALID;
+        }
         v[k] = xfPoint(a, f3(p.positions[vi * 3], p.positions[vi * 3 + 1], p.positions[vi * 3 + 2]));
       }
       FlatTri T;
@@ -1697,50 +1845,34 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
       flat.push_back(T);
     }
   }
-  // opaque and any-hit (non-opaque) geometry go into separate trees over ONE shared triangle array;
-  // the global triangle id (flatten order) stays the tie-break key in both
-  std::vector<FlatTri>  flatO, flatA;
-  std::vector<uint32_t> gidO, gidA;
+  // ONE tree over every triangle (opaque and any-hit geometry alike: the per-triangle TRI_OPAQUE flag decides what a
+  // geometric hit means, traverse.cuh); the global triangle id (flatten order) is the tie-break key
+  std::vector<uint32_t> gids(flat.size());
+  bool                  anyNonOpaque = false;
   for(uint32_t i = 0; i < (uint32_t)flat.size(); i++)
   {
-    if(flat[i].flags & TRI_OPAQUE)
-    {
-      flatO.push_back(flat[i]);
-      gidO.push_back(i);
-    }
-    else
-    {
-      flatA.push_back(flat[i]);
-      gidA.push_back(i);
-    }
+    gids[i] = i;
+    anyNonOpaque = anyNonOpaque || !(flat[i].flags & TRI_OPAQUE);
   }
-  WideBvh bvhO, bvhA;
-  buildWideBvh(flatO, gidO, 0u, bvhO);
-  buildWideBvh(flatA, gidA, bvhO.numTris, bvhA);
-  std::vector<float>    allTris(bvhO.tris);
-  std::vector<uint32_t> allMeta(bvhO.triMeta);
-  allTris.insert(allTris.end(), bvhA.tris.begin(), bvhA.tris.end());
-  allMeta.insert(allMeta.end(), bvhA.triMeta.begin(), bvhA.triMeta.end());
-  float *   dNodesO, *dNodesA, *dTris;
+  WideBvh bvh;
+  buildWideBvh(flat, gids, 0u, bvh);
+  float *   dBvhNodes, *dTris;
   uint32_t* dMeta;
-  if((rc = upload(h, h->sceneAllocs, bvhO.nodes.data(), bvhO.nodes.size(), &dNodesO)))
+  if((rc = upload(h, h->sceneAllocs, bvh.nodes.data(), bvh.nodes.size(), &dBvhNodes)))
     return rc;
-  if((rc = upload(h, h->sceneAllocs, bvhA.nodes.data(), bvhA.nodes.size(), &dNodesA)))
+  if((rc = upload(h, h->sceneAllocs, bvh.tris.data(), bvh.tris.size(), &dTris)))
     return rc;
-  if((rc = upload(h, h->sceneAllocs, allTris.data(), allTris.size(), &dTris)))
+  if((rc = upload(h, h->sceneAllocs, bvh.triMeta.data(), bvh.triMeta.size(), &dMeta)))
     return rc;
-  if((rc = upload(h, h->sceneAllocs, allMeta.data(), allMeta.size(), &dMeta)))
-    return rc;
-  S.bvh.nodes = reinterpret_cast<const float4*>(dNodesO);
+  S.bvh.nodes = reinterpret_cast<const float4*>(dBvhNodes);
   S.bvh.tris = reinterpret_cast<const float4*>(dTris);
-  S.bvhAlpha.nodes = reinterpret_cast<const float4*>(dNodesA);
-  S.bvhAlpha.tris = reinterpret_cast<const float4*>(dTris);
-  S.hasAlpha = flatA.empty() ? 0 : 1;
+  S.bvh.prmtPool = kPrmtPool;
+  S.hasAlpha = anyNonOpaque ? 1 : 0;
   S.triMeta = reinterpret_cast<const uint2*>(dMeta);
-  h->nodeBytes = (bvhO.nodes.size() + bvhA.nodes.size()) * sizeof(float);
-  h->triBytes = allTris.size() * sizeof(float);
-  h->numNodes = bvhO.numNodes + bvhA.numNodes;
-  h->numTris = bvhO.numTris + bvhA.numTris;
+  h->nodeBytes = bvh.nodes.size() * sizeof(float);
+  h->triBytes = bvh.tris.size() * sizeof(float);
+  h->numNodes = bvh.numNodes;
+  h->numTris = bvh.numTris;
   CK(cudaStreamSynchronize(h->stream));
   h->haveScene = true;
   return B200PT_OK;
@@ -1856,6 +1988,43 @@ int b200pt_resize(b200pt_t* h, int width, int height, int tile_y0, int tile_rows
   CK(cudaSetDevice(h->device));
   syncAll(h);
   freePool(h);
+  const size_t n = (size_t)width * tile_rows;
+  // nothing of the handle's geometry is committed before every allocation has succeeded: a failed resize leaves
+  // numPaths == 0 and null pointers, so later calls fail their guards instead of touching freed memory
+  auto fail = [&](int rc) {
+    freePool(h);
+    return rc;
+  };
+  for(int l = 0; l < h->numLanes; l++)
+  {
+    b200pt::Lane& L = h->lanes[l];
+    const int     rc = allocPathState(h, h->poolAllocs, n, L.P);
+    if(rc)
+      return fail(rc);
+    for(int k = 0; k < 6; k++)
+    {
+      if(cudaMalloc((void**)&L.dQ[k], n * sizeof(uint32_t)) != cudaSuccess)
+      {
+        cudaGetLastError();
+        L.dQ[k] = nullptr;
+        h->err = "path pool: out of device memory";
+        return fail(B200PT_E_NOMEM);
+      }
+      h->poolAllocs.push_back(L.dQ[k]);
+    }
+  }
+  if(cudaMalloc((void**)&h->dAccumOwned, n * 16) != cudaSuccess)
+  {
+    cudaGetLastError();
+    h->err = "accumulation image: out of device memory";
+    return fail(B200PT_E_NOMEM);
+  }
+  h->poolAllocs.push_back(h->dAccumOwned);
+  if(cudaMemsetAsync(h->dAccumOwned, 0, n * 16, h->stream) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess)
+  {
+    h->err = "b200pt_resize: clearing the accumulation image failed";
+    return fail(B200PT_E_CUDA);
+  }
   h->width = width;
   h->height = height;
   h->tileY0 = tile_y0;
@@ -1863,45 +2032,7 @@ int b200pt_resize(b200pt_t* h, int width, int height, int tile_y0, int tile_rows
   h->bandRows = 0;
   h->bandWorld = 1;
   h->bandRank = 0;
-  h->numPaths = (uint32_t)((size_t)width * tile_rows);
-  const size_t n = h->numPaths;
-  auto         alloc16 = [&](void** p) -> int {
-    CK(cudaMalloc(p, n * 16));
-    h->poolAllocs.push_back(*p);
-    return 0;
-  };
-  int rc = 0;
-  for(int l = 0; l < h->numLanes; l++)
-  {
-    b200pt::Lane& L = h->lanes[l];
-    rc |= alloc16((void**)&L.P.rayO);
-    rc |= alloc16((void**)&L.P.rayD);
-    rc |= alloc16((void**)&L.P.hit);
-    rc |= alloc16((void**)&L.P.thr);
-    rc |= alloc16((void**)&L.P.rad);
-    rc |= alloc16((void**)&L.P.misc);
-    rc |= alloc16((void**)&L.P.medium);
-    rc |= alloc16((void**)&L.P.pixSum);
-    rc |= alloc16((void**)&L.P.shO);
-    rc |= alloc16((void**)&L.P.shD);
-    rc |= alloc16((void**)&L.P.shC);
-    for(int k = 0; k < kCand; k++)
-      rc |= alloc16((void**)&L.P.cand[k]);
-    if(rc)
-      return B200PT_E_NOMEM;
-    CK(cudaMalloc((void**)&L.P.candInfo, n * sizeof(uint2)));
-    h->poolAllocs.push_back(L.P.candInfo);
-    for(int k = 0; k < 6; k++)
-    {
-      CK(cudaMalloc((void**)&L.dQ[k], n * sizeof(uint32_t)));
-      h->poolAllocs.push_back(L.dQ[k]);
-    }
-  }
-  rc |= alloc16((void**)&h->dAccumOwned);
-  if(rc)
-    return B200PT_E_NOMEM;
-  CK(cudaMemsetAsync(h->dAccumOwned, 0, n * 16, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  h->numPaths = (uint32_t)n;
   h->dAccum = h->dAccumOwned;
   return B200PT_OK;
 }
@@ -2011,7 +2142,7 @@ int b200pt_synchronize(b200pt_t* h)
     return B200PT_E_INVALID;
   CK(cudaSetDevice(h->device));
   syncAll(h);
-  return B200PT_OK;
+  return checkDeviceErrors(h);
 }
 
 int b200pt_set_profiling(b200pt_t* h, int enabled)
@@ -2151,9 +2282,9 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
         timed(tTrace, [&] { k_trace<<<gP, 128, 0, st>>>(L.P, h->S, qT, &cntTrace[it], &workTrace[it], L.dQ[4], &cntAlpha[it], h->dStats, h->refillThreshold, h->postponeShift, 0); });
         if(h->S.hasAlpha)
         {
-          timed(tAnyHit, [&] { k_alpha<false><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlpha[it], L.dQ[5], &cntCont[it], 0); });
+          timed(tAnyHit, [&] { k_alpha<false><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlpha[it], L.dQ[5], &cntCont[it], h->dStats, 0); });
           timed(tTrace, [&] { k_trace<<<gP, 128, 0, st>>>(L.P, h->S, L.dQ[5], &cntCont[it], &workCont[it], L.dQ[4], &cntAlpha1[it], h->dStats, h->refillThreshold, h->postponeShift, 1); });
-          timed(tAnyHit, [&] { k_alpha<false><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlpha1[it], nullptr, nullptr, 1); });
+          timed(tAnyHit, [&] { k_alpha<false><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlpha1[it], nullptr, nullptr, h->dStats, TRACE_CONT); });
         }
         timed(tShade, [&] {
           if(h->leanShade)
@@ -2164,9 +2295,9 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
         timed(tPost, [&] { k_shadow<<<gP, 128, 0, st>>>(L.P, h->S, L.dQ[3], &cntShadow[it], &workPost[it], L.dQ[4], &cntAlphaS[it], h->dStats, h->refillThreshold, h->postponeShift, 0); });
         if(h->S.hasAlpha)
         {
-          timed(tAnyHit, [&] { k_alpha<true><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS[it], L.dQ[5], &cntContS[it], 0); });
+          timed(tAnyHit, [&] { k_alpha<true><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS[it], L.dQ[5], &cntContS[it], h->dStats, 0); });
           timed(tPost, [&] { k_shadow<<<gP, 128, 0, st>>>(L.P, h->S, L.dQ[5], &cntContS[it], &workContS[it], L.dQ[4], &cntAlphaS1[it], h->dStats, h->refillThreshold, h->postponeShift, 1); });
-          timed(tAnyHit, [&] { k_alpha<true><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS1[it], nullptr, nullptr, 1); });
+          timed(tAnyHit, [&] { k_alpha<true><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS1[it], nullptr, nullptr, h->dStats, TRACE_CONT); });
         }
         timed(tResolve, [&] { k_resolve<<<gridFor(h, 4), 256, 0, st>>>(L.P, F, L.dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats); });
         cur = 1 - cur;
@@ -2277,28 +2408,90 @@ int b200pt_reset_stats(b200pt_t* h)
   return B200PT_OK;
 }
 
-int b200pt_trace_closest(b200pt_t* h, const float* dev_rays, uint32_t n, float* dev_hits, uint32_t* dev_seeds)
+// ray-level API: the rays run through the production kernels on a scratch pool (round 1 had separate restart-per-candidate
+// kernels here, so the ray-level parity tests did not cover the benchmarked code)
+static int ensureRayPool(b200pt_t* h, uint32_t n)
 {
-  if(!h || !h->haveScene || !dev_rays || !dev_hits)
+  if(n <= h->rayCapacity)
+    return B200PT_OK;
+  syncAll(h);
+  freeRayPool(h);
+  int rc = allocPathState(h, h->rayAllocs, n, h->rayP);
+  for(int k = 0; k < 3 && !rc; k++)
+  {
+    if(cudaMalloc((void**)&h->rayQ[k], (size_t)n * sizeof(uint32_t)) != cudaSuccess)
+      rc = B200PT_E_NOMEM;
+    else
+      h->rayAllocs.push_back(h->rayQ[k]);
+  }
+  if(!rc)
+  {
+    if(cudaMalloc((void**)&h->rayCounters, 8 * sizeof(uint32_t)) != cudaSuccess)
+      rc = B200PT_E_NOMEM;
+    else
+      h->rayAllocs.push_back(h->rayCounters);
+  }
+  if(rc)
+  {
+    cudaGetLastError();
+    freeRayPool(h);
+    h->err = "ray-level API: out of device memory";
+    return rc;
+  }
+  h->rayCapacity = n;
+  return B200PT_OK;
+}
+
+static int traceRays(b200pt_t* h, const float* dev_rays, uint32_t n, float* dev_out, uint32_t* dev_seeds, int shadow)
+{
+  if(!h || !h->haveScene || !dev_rays || !dev_out)
     return B200PT_E_INVALID;
   CK(cudaSetDevice(h->device));
-  if(n)
-    k_trace_rays<<<gridFor(h, 8), 128, 2048, h->stream>>>(h->S, reinterpret_cast<const float4*>(dev_rays), n, dev_hits, dev_seeds, h->dStats);
+  if(n == 0)
+    return B200PT_OK;
+  const int rc = ensureRayPool(h, n);
+  if(rc)
+    return rc;
+  cudaStream_t st = h->stream;
+  PathState&   P = h->rayP;
+  uint32_t*    c = h->rayCounters;  // [0] rays [1] any-hit [2] continuation [3] any-hit of the continuation [4..5] work cursors
+  CK(cudaMemsetAsync(c, 0, 8 * sizeof(uint32_t), st));
+  const int gP = gridFor(h, 8);
+  k_rays_load<<<gP, 256, 0, st>>>(P, reinterpret_cast<const float4*>(dev_rays), n, dev_seeds, h->rayQ[0], &c[0], shadow);
+  if(!shadow)
+  {
+    k_trace<<<gP, 128, 0, st>>>(P, h->S, h->rayQ[0], &c[0], &c[4], h->rayQ[1], &c[1], h->dStats, h->refillThreshold, h->postponeShift, TRACE_TMIN);
+    if(h->S.hasAlpha)
+    {
+      k_alpha<false><<<gP, 128, 2048, st>>>(P, h->S, h->rayQ[1], &c[1], h->rayQ[2], &c[2], h->dStats, TRACE_TMIN);
+      k_trace<<<gP, 128, 0, st>>>(P, h->S, h->rayQ[2], &c[2], &c[5], h->rayQ[1], &c[3], h->dStats, h->refillThreshold, h->postponeShift, TRACE_TMIN | TRACE_CONT);
+      k_alpha<false><<<gP, 128, 2048, st>>>(P, h->S, h->rayQ[1], &c[3], nullptr, nullptr, h->dStats, TRACE_TMIN | TRACE_CONT);
+    }
+  }
+  else
+  {
+    k_shadow<<<gP, 128, 0, st>>>(P, h->S, h->rayQ[0], &c[0], &c[4], h->rayQ[1], &c[1], h->dStats, h->refillThreshold, h->postponeShift, 0);
+    if(h->S.hasAlpha)
+    {
+      k_alpha<true><<<gP, 128, 2048, st>>>(P, h->S, h->rayQ[1], &c[1], h->rayQ[2], &c[2], h->dStats, 0);
+      k_shadow<<<gP, 128, 0, st>>>(P, h->S, h->rayQ[2], &c[2], &c[5], h->rayQ[1], &c[3], h->dStats, h->refillThreshold, h->postponeShift, TRACE_CONT);
+      k_alpha<true><<<gP, 128, 2048, st>>>(P, h->S, h->rayQ[1], &c[3], nullptr, nullptr, h->dStats, TRACE_CONT);
+    }
+  }
+  k_rays_store<<<gP, 256, 0, st>>>(P, h->S, n, dev_out, dev_seeds, shadow);
   CK(cudaGetLastError());
-  h->kernelLaunches++;
+  h->kernelLaunches += h->S.hasAlpha ? 6 : 3;
   return B200PT_OK;
+}
+
+int b200pt_trace_closest(b200pt_t* h, const float* dev_rays, uint32_t n, float* dev_hits, uint32_t* dev_seeds)
+{
+  return traceRays(h, dev_rays, n, dev_hits, dev_seeds, 0);
 }
 
 int b200pt_trace_shadow(b200pt_t* h, const float* dev_rays, uint32_t n, float* dev_transmission, uint32_t* dev_seeds)
 {
-  if(!h || !h->haveScene || !dev_rays || !dev_transmission)
-    return B200PT_E_INVALID;
-  CK(cudaSetDevice(h->device));
-  if(n)
-    k_shadow_rays<<<gridFor(h, 8), 128, 2048, h->stream>>>(h->S, reinterpret_cast<const float4*>(dev_rays), n, dev_transmission, dev_seeds, h->dStats);
-  CK(cudaGetLastError());
-  h->kernelLaunches++;
-  return B200PT_OK;
+  return traceRays(h, dev_rays, n, dev_transmission, dev_seeds, 1);
 }
 
 int b200pt_bsdf_eval(b200pt_t* h, const float* dev_in, uint32_t n, float* dev_out)

@@ -55,9 +55,8 @@ struct DevScene
   const b200pt_light*          lights;
   int                          numLights;
   int                          numTextures;
-  BvhView                      bvh;       // FORCE_OPAQUE triangles (no any-hit work)
-  BvhView                      bvhAlpha;  // non-opaque triangles (alpha / transmission candidates); shares the triangle array
-  int                          hasAlpha;  // bvhAlpha is non-empty
+  BvhView                      bvh;       // ONE tree over every triangle; TRI_OPAQUE per triangle decides hit vs any-hit candidate
+  int                          hasAlpha;  // the scene has non-opaque triangles (the any-hit kernels are launched)
   const uint2*                 triMeta;   // per triangle slot: (rnode | flags<<28, primitiveID)
   const float4*                envRgba;  // lat-long radiance, pdf in .w
   const uint2*                 envAccel; // (alias, q bits)
@@ -129,6 +128,7 @@ struct DevStats
 {
   unsigned long long closestRays, shadowRays, shadedHits, pathsStarted, nodesVisited, trisTested;
   unsigned long long warpIters, busyLaneIters;  // counter build only: traversal-loop iterations per warp, busy lanes summed
+  unsigned long long errorFlags;                // bit 0: a traversal stack overflowed (the walk was incomplete)
 };
 
 }  // namespace pt

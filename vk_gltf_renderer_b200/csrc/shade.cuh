@@ -517,79 +517,10 @@ PT_D float3 getShadowTransmission(const DevScene& S, const b200pt_render_node& n
 
 // ---- Trace / TraceShadow -------------------------------------------------------------------------
 // The reference leaves any-hit order to the hardware (raytracer_interface.h.slang:53).  Pinned here:
-//   Trace:       closest FORCE_OPAQUE hit (opaque tree) first, then the non-opaque candidates nearer
-//                than it front-to-back in (t, triangle id) order from the alpha tree, one rand() each.
+//   Trace:       closest FORCE_OPAQUE hit, then the non-opaque candidates nearer than it front-to-back in
+//                (t, triangle id) order, one rand() each.
 //   TraceShadow: any opaque occluder => 0 with no rand(); else every non-opaque candidate front-to-back.
-// Opaque and any-hit geometry live in separate trees, so the common (opaque) case is ONE traversal.
-PT_D TraceHit traceClosest(const DevScene& S, float3 org, float3 dir, float tmin, float tmax, uint32_t& seed, DevStats* stats)
-{
-  unsigned long long* nc = stats ? &stats->nodesVisited : nullptr;
-  unsigned long long* tc = stats ? &stats->trisTested : nullptr;
-  const TraceHit      ho = traverseNext<true, false>(S.bvh, org, dir, tmin, tmax, false, 0.f, 0u, nc, tc);
-  if(!S.hasAlpha)
-    return ho;
-  const float tlimit = (ho.slot != 0xFFFFFFFFu) ? ho.t : tmax;
-  bool        haveLo = false;
-  float       loT = 0.f;
-  uint32_t    loId = 0;
-  for(;;)
-  {
-    const TraceHit h = traverseNext<true, false>(S.bvhAlpha, org, dir, tmin, tlimit, haveLo, loT, loId, nc, tc);
-    if(h.slot == 0xFFFFFFFFu)
-      return ho;
-    const uint2               meta = S.triMeta[h.slot];
-    const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
-    const float               opacity = getOpacity(S, node, S.prims[node.renderPrimID], meta.y, f3(1.0f - h.u - h.v, h.u, h.v));
-    if(rnd(seed) <= opacity)
-      return h;
-    haveLo = true;
-    loT = h.t;
-    loId = h.gid;
-  }
-}
-
-PT_D float3 traceShadow(const DevScene& S, float3 org, float3 dir, float tmax, uint32_t& seed, bool initialInside, DevStats* stats)
-{
-  unsigned long long* nc = stats ? &stats->nodesVisited : nullptr;
-  unsigned long long* tc = stats ? &stats->trisTested : nullptr;
-  {
-    const TraceHit h = traverseNext<false, true>(S.bvh, org, dir, 0.0f, tmax, false, 0.f, 0u, nc, tc);
-    if(h.slot != 0xFFFFFFFFu)
-      return f3(0.0f);
-  }
-  float3 total = f3(1.0f);
-  if(!S.hasAlpha)
-    return total;
-  bool     isInside = initialInside;
-  float    prevHitT = 0.f;
-  bool     haveLo = false;
-  float    loT = 0.f;
-  uint32_t loId = 0;
-  for(;;)
-  {
-    const TraceHit h = traverseNext<false, false>(S.bvhAlpha, org, dir, 0.0f, tmax, haveLo, loT, loId, nc, tc);
-    if(h.slot == 0xFFFFFFFFu)
-      return total;
-    const uint2               meta = S.triMeta[h.slot];
-    const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
-    const DevPrim&            P = S.prims[node.renderPrimID];
-    const float3              bary = f3(1.0f - h.u - h.v, h.u, h.v);
-    const float               opacity = getOpacity(S, node, P, meta.y, bary);
-    const float               r = rnd(seed);
-    if(r < opacity)
-    {
-      const float  seg = fmaxf(0.0f, h.t - prevHitT);
-      const float3 cur = getShadowTransmission(S, node, P, meta.y, bary, seg, dir, isInside);
-      prevHitT = h.t;
-      total *= cur;
-      if(maxc(total) <= 0.01f)
-        return f3(0.0f);
-    }
-    haveLo = true;
-    loT = h.t;
-    loId = h.gid;
-  }
-}
+// Geometry: traverse.cuh (one walk per ray: k_trace / k_shadow); alpha tests + transmission: k_alpha (b200pt.cu).
 
 // ---- environment --------------------------------------------------------------------------------
 // lat-long lookup with fp32 bilinear weights (linear filter, level 0, repeat in u / clamp in v)

@@ -1,13 +1,17 @@
 // host_traverse_check.cpp — the device traversal source (traverse.cuh: node decode with the PRMT plane conversion, octant
-// order, compressed stack, postponed groups, nearest-hit and collecting modes, lower bounds) compiled for the host through
-// host_shim.h and checked against brute force over all triangles, on the tree the product's builder (bvh.cpp) makes.
+// order, compressed stack, postponed groups, single-tree closest / shadow walks with candidate lists, lower bounds, refinement
+// of the opaque hit in continuation walks) compiled for the host through host_shim.h and checked against brute force over all
+// triangles, on the tree the product's builder (bvh.cpp) makes.  A third of the triangles is flagged non-opaque.
 //
-//   host_traverse_check dump.bin        (dump format of scripts/dump_bvh_input.py: triangles + rays)
+//   host_traverse_check dump.bin [maxRays] [opaqueMod]       (dump format of scripts/dump_bvh_input.py: triangles + rays)
 //
-// Checks, per ray: (1) nearest hit: same (t, global id) as the brute-force minimum in (t, id) order, bit for bit (the triangle
-// test is the same fma chain); (2) any-exit query: hits iff any triangle hits; (3) collecting mode: the kCand nearest hits in
-// (t, id) order equal the head of the sorted brute-force list, and walking on with the last one as lower bound enumerates the
-// whole list in order -- the sequence the any-hit kernels consume.  Exit code 0 iff everything matches.
+// Checks, per ray, against the sorted brute-force hit list (the triangle test is the same fma chain, so bit for bit):
+// (1) closest protocol of k_trace / k_alpha with every candidate rejected: walks resumed behind the last candidate until a walk
+//     returns fewer than kCand; the candidates enumerated must be exactly the non-opaque hits in front of the nearest opaque hit,
+//     in (t, id) order, and the opaque hit the last walk reports must be the nearest opaque hit;
+// (2) shadow protocol of k_shadow / k_alpha: the first walk reports an occluder iff an opaque triangle is on the segment,
+//     otherwise the walks enumerate every non-opaque hit of the segment in order.
+// Exit code 0 iff everything matches and no walk came near the stack limit.
 #include "host_shim.h"
 
 #include <algorithm>
@@ -35,16 +39,20 @@ int main(int argc, char** argv)
   if(std::fread(tv.data(), 4, tv.size(), f) != tv.size() || std::fread(rv.data(), 4, rv.size(), f) != rv.size()) return 2;
   std::fclose(f);
   if(argc > 2) nR = std::min<uint32_t>(nR, (uint32_t)std::atoi(argv[2]));
+  // triangle i is opaque iff i % opaqueMod != 0 (default 3: a third non-opaque); a negative value flips it (|mod| 8: 7/8 non-opaque,
+  // deep candidate lists and many continuation walks)
+  const int opaqueMod = argc > 3 ? std::atoi(argv[3]) : 3;
+  auto isOpaque = [&](uint32_t i) { return opaqueMod > 0 ? (i % (uint32_t)opaqueMod) != 0 : (i % (uint32_t)(-opaqueMod)) == 0; };
   std::vector<FlatTri>  tris(nT);
   std::vector<uint32_t> gids(nT);
   for(uint32_t i = 0; i < nT; i++)
   {
     std::memcpy(tris[i].v0, &tv[i * 9], 12); std::memcpy(tris[i].e1, &tv[i * 9 + 3], 12); std::memcpy(tris[i].e2, &tv[i * 9 + 6], 12);
-    tris[i].rnode = 0; tris[i].prim = i; tris[i].flags = TRI_NOCULL; gids[i] = i;
+    tris[i].rnode = 0; tris[i].prim = i; tris[i].flags = TRI_NOCULL | (isOpaque(i) ? TRI_OPAQUE : 0u); gids[i] = i;
   }
   WideBvh B;
   buildWideBvh(tris, gids, 0, B);
-  BvhView view{reinterpret_cast<const float4*>(B.nodes.data()), reinterpret_cast<const float4*>(B.tris.data())};
+  BvhView view{reinterpret_cast<const float4*>(B.nodes.data()), reinterpret_cast<const float4*>(B.tris.data()), kPrmtPool};
   std::printf("tris %u nodes %u rays %u kCand %d\n", B.numTris, B.numNodes, nR, kCand);
 
   uint64_t bad1 = 0, bad2 = 0, bad3 = 0, hits = 0, listed = 0;
@@ -73,47 +81,78 @@ int main(int argc, char** argv)
         bf.push_back(BF{t, i});
     }
     std::sort(bf.begin(), bf.end(), [](const BF& a, const BF& b) { return a.t < b.t || (a.t == b.t && a.gid < b.gid); });
-    // (1) nearest hit (stepped by hand to record the deepest stack the walk needed; kStackSize entries exist)
-    TraceHit h;
-    {
-      TravState T;
-      uint2     stack[TravState::kStackSize];
-      T.init(view, org, dir, tmin, tmax, false, false, false, 0.f, 0u);
-      while(!T.step(stack))
-        maxSp = std::max(maxSp, T.sp);
-      h = T.result();
-    }
-    if(bf.empty() ? (h.slot != 0xFFFFFFFFu) : (h.slot == 0xFFFFFFFFu || __float_as_uint(h.t) != __float_as_uint(bf[0].t) || h.gid != bf[0].gid))
-      bad1++;
+    // expected: nearest opaque hit, non-opaque hits strictly in front of it
+    size_t firstOpaque = bf.size();
+    for(size_t k = 0; k < bf.size(); k++)
+      if(isOpaque(bf[k].gid))
+      {
+        firstOpaque = k;
+        break;
+      }
     hits += !bf.empty();
-    // (2) any-exit occlusion query
-    const TraceHit a = traverseNext<false, true>(view, org, dir, tmin, tmax, false, 0.f, 0u);
-    if((a.slot != 0xFFFFFFFFu) != !bf.empty())
-      bad2++;
-    // (3) collecting walks, kCand at a time, resumed behind the last candidate
+    // (1) closest protocol
     {
+      std::vector<BF> expect;
+      for(size_t k = 0; k < bf.size(); k++)
+        if(!isOpaque(bf[k].gid) && (firstOpaque == bf.size() || bf[k].t < bf[firstOpaque].t))
+          expect.push_back(bf[k]);
       Cand     cand[kCand];
+      TraceHit opq;
+      opq.slot = 0xFFFFFFFFu;
       size_t   k = 0;
-      bool     haveLo = false, ok = true;
+      bool     haveLo = false, ok = true, ovf = false;
       float    loT = 0.f;
       uint32_t loId = 0;
       for(;;)
       {
-        const int m = collectNext(view, org, dir, tmax, false, haveLo, loT, loId, cand);
+        const int m = walkCollect(view, org, dir, tmin, tmax, false, false, haveLo, loT, loId, opq, cand, &ovf, &maxSp);
         for(int i = 0; i < m && ok; i++, k++)
-          ok = k < bf.size() && __float_as_uint(cand[i].t) == __float_as_uint(bf[k].t) && cand[i].gid == bf[k].gid;
+          ok = k < expect.size() && __float_as_uint(cand[i].t) == __float_as_uint(expect[k].t) && cand[i].gid == expect[k].gid;
         if(!ok || m < kCand)
           break;
         haveLo = true;
         loT = cand[kCand - 1].t;
         loId = cand[kCand - 1].gid;
       }
-      if(!ok || k != bf.size())
+      if(!ok || k != expect.size() || ovf)
         bad3++;
       listed += k;
+      if(firstOpaque == bf.size() ? (opq.slot != 0xFFFFFFFFu)
+                                  : (opq.slot == 0xFFFFFFFFu || __float_as_uint(opq.t) != __float_as_uint(bf[firstOpaque].t) || opq.gid != bf[firstOpaque].gid))
+        bad1++;
+    }
+    // (2) shadow protocol
+    {
+      Cand     cand[kCand];
+      TraceHit opq;
+      opq.slot = 0xFFFFFFFFu;
+      bool     ovf = false;
+      int      m = walkCollect(view, org, dir, tmin, tmax, false, true, false, 0.f, 0u, opq, cand, &ovf, &maxSp);
+      if((opq.slot != 0xFFFFFFFFu) != (firstOpaque != bf.size()) || ovf)
+        bad2++;
+      else if(opq.slot == 0xFFFFFFFFu)
+      {
+        size_t k = 0;
+        bool   ok = true;
+        for(;;)
+        {
+          for(int i = 0; i < m && ok; i++, k++)
+            ok = k < bf.size() && __float_as_uint(cand[i].t) == __float_as_uint(bf[k].t) && cand[i].gid == bf[k].gid;
+          if(!ok || m < kCand)
+            break;
+          const float    loT = cand[kCand - 1].t;
+          const uint32_t loId = cand[kCand - 1].gid;
+          opq.slot = 0xFFFFFFFFu;
+          m = walkCollect(view, org, dir, tmin, tmax, false, true, true, loT, loId, opq, cand, &ovf, &maxSp);
+          if(opq.slot != 0xFFFFFFFFu)
+            ok = false;
+        }
+        if(!ok || k != bf.size() || ovf)
+          bad2++;
+      }
     }
   }
-  std::printf("hit rate %.3f, %.2f candidates per ray, deepest stack %d of %d | mismatches: nearest %llu, any-exit %llu, collecting %llu\n", (double)hits / nR,
+  std::printf("hit rate %.3f, %.2f candidates per ray, deepest stack %d of %d | mismatches: nearest opaque %llu, shadow %llu, candidates %llu\n", (double)hits / nR,
               (double)listed / nR, maxSp, TravState::kStackSize, (unsigned long long)bad1, (unsigned long long)bad2, (unsigned long long)bad3);
   if(maxSp >= TravState::kStackSize)
     return 1;

@@ -35,7 +35,9 @@ struct BvhView
 {
   const float4* __restrict__ nodes;  // 5 per node
   const float4* __restrict__ tris;   // 3 per triangle
+  uint32_t      prmtPool;            // 0x47000000 (see biasedByte): a kernel PARAMETER, so that ptxas cannot fold it
 };
+constexpr uint32_t kPrmtPool = 0x47000000u;
 
 PT_D uint32_t extractByte(uint32_t x, int i) { return (x >> (i * 8)) & 0xffu; }
 PT_D uint32_t signExtendS8x4(uint32_t x)
@@ -44,43 +46,92 @@ PT_D uint32_t signExtendS8x4(uint32_t x)
   return ((x >> 7) & 0x01010101u) * 0xffu;
 }
 
-// byte j of x as the float 32768 + b: PRMT puts the byte into bits 8..15 of 0x47000000 (= 32768.0f, ulp 2^-8)
-PT_D float biasedByte(uint32_t x, int j) { return __uint_as_float(__byte_perm(x, 0x47000000u, 0x7604u | ((uint32_t)j << 4))); }
+// byte J of x as the float 32768 + b: PRMT puts the byte into bits 8..15 of 0x47000000 (= 32768.0f, ulp 2^-8).
+// The constant comes in as a kernel parameter (BvhView::prmtPool) that ptxas cannot see through, and the selector is the
+// immediate: with both known, the constant became the immediate and the selector was re-materialised with one IMAD.U32 per
+// PRMT (SASS of round 1: 48 extra instructions per node; a `mov` in inline asm is folded by ptxas just the same).
+template <int J>
+PT_D float biasedByte(uint32_t x, uint32_t pool)
+{
+#ifdef __CUDA_ARCH__
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(pool), "n"(0x7604 | (J << 4)));
+  return __uint_as_float(r);
+#else
+  return __uint_as_float(__byte_perm(x, pool, 0x7604u | ((uint32_t)J << 4)));
+#endif
+}
+
+// (u, v) of a hit on a mirrored instance are stored swapped (the world-space winding was flipped at build time)
+PT_D TraceHit unflipHit(TraceHit h)
+{
+  if(h.slot != 0xFFFFFFFFu && ((h.w0 >> 28) & TRI_FLIPPED))
+  {
+    const float u = h.u;
+    h.u = h.v;
+    h.v = u;
+  }
+  return h;
+}
+
+// rebuilds the traversal's record of an opaque hit from what the path state keeps of it (t, un-flipped u / v, slot)
+PT_D TraceHit seedHit(const BvhView bvh, float t, float u, float v, uint32_t slot)
+{
+  TraceHit h;
+  h.t = t;
+  h.u = u;
+  h.v = v;
+  h.slot = slot;
+  h.w0 = __float_as_uint(__ldg(&bvh.tris[slot * 3 + 0]).w);
+  h.gid = __float_as_uint(__ldg(&bvh.tris[slot * 3 + 2]).w);
+  return unflipHit(h);  // swapping twice restores the traversal-order (u, v)
+}
 
 // One traversal in flight, resumable one node-step at a time (the persistent kernels interleave the
 // steps of 32 independent rays per warp and re-fill finished lanes from a global work counter).
+//
+// ONE tree holds every triangle; the per-triangle TRI_OPAQUE flag (getInstanceFlag, src/gltf_scene_rtx.cpp:271-295)
+// decides what a geometric hit means, so a ray is ONE walk (round 1 walked an opaque tree and then an any-hit tree):
+//   closest mode (IRaytracer::Trace, raytracer_interface.h.slang:69-122)
+//     opaque hit      -> nearest-hit update of `best` in (t, global id) order
+//     non-opaque hit  -> candidate for the stochastic alpha test: kept in a list of the kCand nearest ones, sorted by
+//                        (t, id), if it lies in front of the opaque hit found so far
+//     nodes are culled against bound = min(best.t, t of the kCand-th candidate once the list is full): every opaque
+//     hit nearer than the last kept candidate is found (so candidates behind the true opaque hit can be dropped at
+//     write-out and the list is then complete); when all kCand candidates lie in front, the any-hit kernel may reject
+//     them all and a continuation walk resumes behind the last one -- it refines `best` as well.
+//   shadow mode (IRaytracer::TraceShadow, :139-187, with the pinned order: any opaque occluder ends the query first)
+//     opaque hit      -> done (occluded)
+//     non-opaque hit  -> candidate list as above; the bound stays at the segment end, so the walk visits the whole
+//                        segment and an occluder behind the kept candidates is still found
 //   cull    : back-face culling per triangle flags (RAY_FLAG_CULL_BACK_FACING_TRIANGLES + instance cull-disable)
-//   anyExit : stop at the first accepted triangle (occlusion query against the opaque tree)
-//   lo      : only hits lexicographically after (loT, loId) in (t, global id) order count
+//   lo      : only hits lexicographically after (loT, loId) in (t, global id) order count (continuation walks)
 struct TravState
 {
   const float4* nodes;
   const float4* tris;
+  uint32_t      pool;
   float3        org, dir;
   float         idx, idy, idz;
-  float         tmin, tmax, tLow, loT;
+  float         tmin, tmax, tLow, loT, bound;
   uint32_t      loId, octInv4;
-  bool          haveLo, cull, anyExit;
+  bool          haveLo, cull, shadow;
+  bool          overflow;  // a push found the stack full: the walk is incomplete (surfaced as a device error flag)
   TraceHit      best;
   uint2         cur;   // current node group (x = child base, y = hit bits << 24 | imask)
   uint2         tri;   // pending triangle group (x = triangle base, y = hit bits)
   int           sp;    // entries on the caller-provided stack (kept OUT of this struct so the rest stays in registers)
-  // Collecting mode (any-hit candidates): instead of keeping only the nearest hit, the traversal keeps the kCand
-  // nearest hits after the lower bound, sorted by (t, id), in caller-provided scratch.  The kernels then run the
-  // stochastic alpha / transmission tests over them front to back -- the same sequence the restart-per-candidate
-  // formulation produces, with one tree walk per kCand candidates instead of one per candidate.  `best` holds the
-  // kCand-th candidate once the list is full, so node culling and the hit predicate need no extra code.
-  int           collectN;  // -1: nearest-hit mode, else number of candidates collected so far
+  int           collectN;  // candidates in the caller-provided list (sorted by (t, id))
 #ifdef B200PT_COUNT_TRAVERSAL
   unsigned int nodeCount, triCount;
 #endif
 
-  PT_D void init(const BvhView bvh, float3 o, float3 d, float tmin_, float tmax_, bool cull_, bool anyExit_, bool haveLo_, float loT_, uint32_t loId_,
-                 bool collect_ = false)
+  PT_D void init(const BvhView bvh, float3 o, float3 d, float tmin_, float tmax_, bool cull_, bool shadow_, bool haveLo_, float loT_, uint32_t loId_)
   {
-    collectN = collect_ ? 0 : -1;
+    collectN = 0;
     nodes = bvh.nodes;
     tris = bvh.tris;
+    pool = bvh.prmtPool;
     org = o;
     dir = d;
     const float ooeps = 1e-20f;
@@ -93,12 +144,14 @@ struct TravState
     octInv4 = ((d.x < 0.f ? 0u : 4u) | (d.y < 0.f ? 0u : 2u) | (d.z < 0.f ? 0u : 1u)) * 0x01010101u;
     tmin = tmin_;
     tmax = tmax_;
+    bound = tmax_;
     haveLo = haveLo_;
     loT = loT_;
     loId = loId_;
     tLow = haveLo_ ? fmaxf(tmin_, loT_) : tmin_;
     cull = cull_;
-    anyExit = anyExit_;
+    shadow = shadow_;
+    overflow = false;
     best.t = tmax_;
     best.slot = 0xFFFFFFFFu;
     best.gid = 0xFFFFFFFFu;
@@ -112,13 +165,31 @@ struct TravState
 #endif
   }
 
+  // continuation walk: the opaque hit an earlier walk of the same ray found (an upper bound, possibly not yet the nearest)
+  PT_D void seedOpaque(float t, float u, float v, uint32_t slot)
+  {
+    BvhView bv;
+    bv.nodes = nodes;
+    bv.tris = tris;
+    bv.prmtPool = pool;
+    best = seedHit(bv, t, u, v, slot);
+    bound = fminf(bound, t);
+  }
+
+#ifdef B200PT_SMEM_STACK
+  static constexpr int kStackSize = 24;  // 24 x 8 B x 128 threads = 24 KB of shared memory per block
+#else
   static constexpr int kStackSize = 28;
+#endif
 
   // One traversal step: (1) lanes without pending triangles open their next node, (2) lanes with pending
   // triangles test ONE triangle each — but only when enough lanes of the warp have one (vote); otherwise the
   // group is postponed onto the stack and node traversal continues (Ylitie et al. 2017, section 4.3).
-  // Returns true when the traversal is complete.  `stack` is per-thread scratch of kStackSize entries.
-  PT_D bool step(uint2* __restrict__ stack, int postponeShift = 2, Cand* __restrict__ cand = nullptr)
+  // Returns true when the traversal is complete.  `stack` is per-thread scratch of kStackSize entries (entry i at
+  // stack[i * SS]: local memory with SS = 1, or a shared-memory column), `cand` the candidate list (entry i at
+  // cand[i * cs]: the kernels keep it in shared memory, one column per thread).
+  template <int SS = 1>
+  PT_D bool step(uint2* __restrict__ stack, int postponeShift, Cand* __restrict__ cand, int cs)
   {
     // single exit: an early return inside the divergent regions would move their reconvergence point out of the
     // caller's loop and the lanes of a warp would drift apart (measured: 8 of 32 lanes active)
@@ -130,7 +201,7 @@ struct TravState
         if(sp == 0)
           done = true;
         else
-          cur = stack[--sp];
+          cur = stack[(--sp) * SS];
       }
       if(done)
       {
@@ -143,7 +214,9 @@ struct TravState
         if(cur.y & 0xff000000u)
         {
           if(sp < kStackSize)
-            stack[sp++] = cur;
+            stack[(sp++) * SS] = cur;
+          else
+            overflow = true;
         }
         const uint32_t slotIndex = (uint32_t)(childBit - 24) ^ (octInv4 & 0xffu);
         const uint32_t relative = __popc(hitsImask & ~(0xffffffffu << slotIndex));
@@ -172,6 +245,7 @@ struct TravState
         const float aoxN = fmaf(-0.00390625f, fabsf(adx), aox), aoxF = fmaf(0.00390625f, fabsf(adx), aox);
         const float aoyN = fmaf(-0.00390625f, fabsf(ady), aoy), aoyF = fmaf(0.00390625f, fabsf(ady), aoy);
         const float aozN = fmaf(-0.00390625f, fabsf(adz), aoz), aozF = fmaf(0.00390625f, fabsf(adz), aoz);
+        const uint32_t k47 = pool;
 
         cur.x = __float_as_uint(n1.x);
         tri.x = __float_as_uint(n1.y);
@@ -192,30 +266,26 @@ struct TravState
           const uint32_t xmin = dir.x < 0.f ? qhix : qlox, xmax = dir.x < 0.f ? qlox : qhix;
           const uint32_t ymin = dir.y < 0.f ? qhiy : qloy, ymax = dir.y < 0.f ? qloy : qhiy;
           const uint32_t zmin = dir.z < 0.f ? qhiz : qloz, zmax = dir.z < 0.f ? qloz : qhiz;
-#pragma unroll
-          for(int j = 0; j < 4; j++)
-          {
-            const float tminx = fmaf(biasedByte(xmin, j), adx, aoxN);
-            const float tminy = fmaf(biasedByte(ymin, j), ady, aoyN);
-#ifdef B200PT_CVT_Z_I2F
-            const float tminz = fmaf((float)extractByte(zmin, j), adz, fmaf(32768.0f, adz, aozN));
-#else
-            const float tminz = fmaf(biasedByte(zmin, j), adz, aozN);
-#endif
-            const float tmaxx = fmaf(biasedByte(xmax, j), adx, aoxF);
-            const float tmaxy = fmaf(biasedByte(ymax, j), ady, aoyF);
-#ifdef B200PT_CVT_Z_I2F
-            const float tmaxz = fmaf((float)extractByte(zmax, j), adz, fmaf(32768.0f, adz, aozF));
-#else
-            const float tmaxz = fmaf(biasedByte(zmax, j), adz, aozF);
-#endif
-            const float tn = fmaxf(fmaxf(tminx, tminy), fmaxf(tminz, tLow));
-            const float tf = fminf(fminf(tmaxx, tmaxy), fminf(tmaxz, best.t));
-            // widen by a few ulp: keeps the box test conservative w.r.t. the triangle test
-            const bool     in = tn <= tf * 1.000001f;
-            const uint32_t childBits = in ? extractByte(childBits4, j) : 0u;
-            hitMask |= childBits << extractByte(bitIndex4, j);
-          }
+#define PT_CHILD(J)                                                                                                        \
+  {                                                                                                                        \
+    const float tminx = fmaf(biasedByte<J>(xmin, k47), adx, aoxN);                                                       \
+    const float tminy = fmaf(biasedByte<J>(ymin, k47), ady, aoyN);                                                       \
+    const float tminz = fmaf(biasedByte<J>(zmin, k47), adz, aozN);                                                       \
+    const float tmaxx = fmaf(biasedByte<J>(xmax, k47), adx, aoxF);                                                       \
+    const float tmaxy = fmaf(biasedByte<J>(ymax, k47), ady, aoyF);                                                       \
+    const float tmaxz = fmaf(biasedByte<J>(zmax, k47), adz, aozF);                                                       \
+    const float tn = fmaxf(fmaxf(tminx, tminy), fmaxf(tminz, tLow));                                                       \
+    const float tf = fminf(fminf(tmaxx, tmaxy), fminf(tmaxz, bound));                                                      \
+    /* widen by a few ulp: keeps the box test conservative w.r.t. the triangle test */                                     \
+    const bool     in = tn <= tf * 1.000001f;                                                                              \
+    const uint32_t childBits = in ? extractByte(childBits4, J) : 0u;                                                       \
+    hitMask |= childBits << extractByte(bitIndex4, J);                                                                     \
+  }
+          PT_CHILD(0)
+          PT_CHILD(1)
+          PT_CHILD(2)
+          PT_CHILD(3)
+#undef PT_CHILD
         }
         cur.y = (hitMask & 0xff000000u) | (eImask >> 24);
         tri.y = hitMask & 0x00ffffffu;
@@ -237,7 +307,7 @@ struct TravState
       // (the group goes under the next node; `cur` only ever holds node groups)
       if((__popc(haveTri) << postponeShift) < __popc(conv) && (cur.y & 0xff000000u) != 0 && sp < kStackSize)
       {
-        stack[sp++] = tri;
+        stack[(sp++) * SS] = tri;
         tri.y = 0;
       }
       else
@@ -269,41 +339,59 @@ struct TravState
         const bool     front = (flags & TRI_FLIPPED) ? (det < 0.0f) : (det > 0.0f);
         hit &= !cull | ((flags & TRI_NOCULL) != 0) | front;
         hit &= !haveLo | (t > loT) | ((t == loT) & (gid > loId));
-        hit &= (t < best.t) | ((t == best.t) & (gid < best.gid));
         if(hit)
         {
-          if(collectN >= 0)
+          if(flags & TRI_OPAQUE)
           {
-            // insertion sort by (t, id); a full list drops its last entry (the predicate above already
-            // guarantees the new hit sorts before it)
-            int pos = collectN < kCand ? collectN : kCand - 1;
-            while(pos > 0 && ((cand[pos - 1].t > t) | ((cand[pos - 1].t == t) & (cand[pos - 1].gid > gid))))
+            if((t < best.t) | ((t == best.t) & (gid < best.gid)))
             {
-              cand[pos] = cand[pos - 1];
-              pos--;
-            }
-            cand[pos].t = t;
-            cand[pos].u = u;
-            cand[pos].v = v;
-            cand[pos].slot = slot;
-            cand[pos].gid = gid;
-            if(collectN < kCand)
-              collectN++;
-            if(collectN == kCand)
-            {
-              best.t = cand[kCand - 1].t;
-              best.gid = cand[kCand - 1].gid;
+              best.t = t;
+              best.u = u;
+              best.v = v;
+              best.slot = slot;
+              best.gid = gid;
+              best.w0 = w0;
+              if(shadow)
+                done = true;  // occlusion query satisfied
+              else
+                bound = fminf(bound, t);
             }
           }
           else
           {
-            best.t = t;
-            best.u = u;
-            best.v = v;
-            best.slot = slot;
-            best.gid = gid;
-            best.w0 = w0;
-            done = anyExit;  // occlusion query satisfied
+            // candidate for the any-hit kernel: in front of the opaque hit (closest mode) and, once the list is full,
+            // in front of its last entry
+            bool keep = shadow | (t < best.t);
+            if(collectN == kCand)
+            {
+              const float    lt = cand[(kCand - 1) * cs].t;
+              const uint32_t lg = cand[(kCand - 1) * cs].gid;
+              keep &= (t < lt) | ((t == lt) & (gid < lg));
+            }
+            if(keep)
+            {
+              // insertion sort by (t, id); a full list drops its last entry
+              int pos = collectN < kCand ? collectN : kCand - 1;
+              while(pos > 0)
+              {
+                const Cand p = cand[(pos - 1) * cs];
+                if(!((p.t > t) | ((p.t == t) & (p.gid > gid))))
+                  break;
+                cand[pos * cs] = p;
+                pos--;
+              }
+              Cand nc;
+              nc.t = t;
+              nc.u = u;
+              nc.v = v;
+              nc.slot = slot;
+              nc.gid = gid;
+              cand[pos * cs] = nc;
+              if(collectN < kCand)
+                collectN++;
+              if(collectN == kCand && !shadow)
+                bound = fminf(bound, cand[(kCand - 1) * cs].t);
+            }
           }
         }
       }
@@ -311,16 +399,16 @@ struct TravState
     return done | ((tri.y == 0) & ((cur.y & 0xff000000u) == 0) & (sp == 0));
   }
 
-  // the hit with (u,v) restored for mirrored instances
-  PT_D TraceHit result() const
+  // the opaque hit with (u,v) restored for mirrored instances
+  PT_D TraceHit result() const { return unflipHit(best); }
+
+  // closest mode: candidates in front of the opaque hit (the list is sorted, so a prefix of it)
+  PT_D int candidatesInFront(const Cand* __restrict__ cand, int cs) const
   {
-    TraceHit h = best;
-    if(h.slot != 0xFFFFFFFFu && ((h.w0 >> 28) & TRI_FLIPPED))
-    {
-      h.u = best.v;
-      h.v = best.u;
-    }
-    return h;
+    int n = 0;
+    while(n < collectN && (best.slot == 0xFFFFFFFFu || cand[n * cs].t < best.t))
+      n++;
+    return n;
   }
 
   PT_D void flushCounters(unsigned long long* nodeCounter, unsigned long long* triCounter)
@@ -338,31 +426,30 @@ struct TravState
   }
 };
 
-// one collecting walk to completion: the up-to-kCand nearest hits after the lower bound, sorted, in `cand`
-PT_D int collectNext(const BvhView bvh, float3 org, float3 dir, float tmax, bool cull, bool haveLo, float loT, uint32_t loId, Cand* __restrict__ cand)
+// One complete walk on one lane (the any-hit kernels' rare in-kernel fallback; the host-side check of this source):
+// the up-to-kCand nearest candidates behind the lower bound, sorted, in `cand`; `opq` carries the opaque hit in and out
+// (closest mode: refined; shadow mode: slot != miss means occluded).  Returns the number of candidates that count
+// (closest mode: those in front of the opaque hit).  *overflowed is OR-ed with the stack-overflow flag.
+PT_D int walkCollect(const BvhView bvh, float3 org, float3 dir, float tmin, float tmax, bool cull, bool shadow, bool haveLo, float loT, uint32_t loId, TraceHit& opq,
+                     Cand* __restrict__ cand, bool* overflowed = nullptr, int* deepest = nullptr)
 {
   TravState T;
   uint2     stack[TravState::kStackSize];
-  T.init(bvh, org, dir, 0.0f, tmax, cull, false, haveLo, loT, loId, true);
-  while(!T.step(stack, 2, cand))
+  T.init(bvh, org, dir, tmin, tmax, cull, shadow, haveLo, loT, loId);
+  if(opq.slot != 0xFFFFFFFFu)
   {
+    T.best = opq;
+    T.bound = fminf(T.bound, opq.t);
   }
-  return T.collectN;
-}
-
-// run one traversal to completion (ray-level API kernels and the any-hit restart loops)
-template <bool CULL, bool ANY_EXIT>
-PT_D TraceHit traverseNext(const BvhView bvh, float3 org, float3 dir, float tmin, float tmax, bool haveLo, float loT, uint32_t loId,
-                           unsigned long long* nodeCounter = nullptr, unsigned long long* triCounter = nullptr)
-{
-  TravState T;
-  uint2     stack[TravState::kStackSize];
-  T.init(bvh, org, dir, tmin, tmax, CULL, ANY_EXIT, haveLo, loT, loId);
-  while(!T.step(stack))
+  while(!T.step(stack, 2, cand, 1))
   {
+    if(deepest && T.sp > *deepest)
+      *deepest = T.sp;
   }
-  T.flushCounters(nodeCounter, triCounter);
-  return T.result();
+  if(overflowed && T.overflow)
+    *overflowed = true;
+  opq = T.best;
+  return shadow ? T.collectN : T.candidatesInFront(cand, 1);
 }
 
 }  // namespace pt

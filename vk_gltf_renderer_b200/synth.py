@@ -356,6 +356,136 @@ def synth_layers(seed=1234, layers=14, tex_size=64, blend=False, tinted=False):
     return scn
 
 
+def _sphere(cx, cy, cz, r, n=24, uv_scale=(2, 1)):
+    def f(u, v):
+        th, a = v * math.pi, u * 2 * math.pi
+        return _xyz(cx + r * np.sin(th) * np.cos(a), cy - r * np.cos(th), cz - r * np.sin(th) * np.sin(a))
+    return param_surface(f, n, n // 2, uv_scale)
+
+
+def _light(kind, position=(0, 0, 0), direction=(0, -1, 0), color=(1, 1, 1), intensity=1.0, radius=0.0, rng=0.0, inner=0.0, outer=math.pi / 4,
+           angular_size=0.0):
+    """GltfLight the way SceneVk::updateRenderLightsBuffer fills it (src/gltf_scene_vk.cpp:1354-1394): type 1 directional
+    (angularSizeOrInvRange = angular size), 2 spot, 3 point (angularSizeOrInvRange = 1 / range)."""
+    from . import abi
+    L = abi.Light()
+    d = np.asarray(direction, np.float64)
+    d = d / np.linalg.norm(d)
+    L.direction[:] = d.tolist()
+    L.position[:] = list(position)
+    L.color[:] = list(color)
+    L.intensity = intensity
+    L.radius = radius
+    L.type = {"directional": 1, "spot": 2, "point": 3}[kind]
+    L.innerAngle, L.outerAngle = inner, outer
+    L.angularSizeOrInvRange = angular_size if kind == "directional" else (1.0 / rng if rng > 0 else 0.0)
+    return L
+
+
+def synth_lit(seed=1234, tex_size=64):
+    """Punctual lights (KHR_lights_punctual as the reference uploads them): a point light with radius 0 and one with a radius
+    (sphere light, sampled), a spot light with a range, a directional light with and one without angular size, over a textured
+    floor with three spheres (dielectric, metal, clearcoat).  Exercises sampleLights' light branch, singleLightContribution,
+    the light/environment technique MIS and shadow rays of finite length (FEAT_LIGHTS)."""
+    rng = np.random.default_rng(seed)
+    scn = Scene()
+    base, mr, nm = make_texture_set(tex_size, rng, (0.75, 0.7, 0.6))
+    tb, tm, tn = scn.add_texture(base, srgb=True), scn.add_texture(mr), scn.add_texture(nm)
+    floor = scn.add_material(pbrBaseColorFactor=[1, 1, 1, 1], pbrRoughnessFactor=1.0, pbrMetallicFactor=0.2,
+                             pbrBaseColorTexture=scn.add_texture_info(tb), pbrMetallicRoughnessTexture=scn.add_texture_info(tm),
+                             normalTexture=scn.add_texture_info(tn))
+
+    def ground(u, v):
+        return _xyz((u * 2 - 1) * 5, np.zeros_like(u), (1 - v * 2) * 5)
+    scn.add_node(scn.add_primitive(*_split(param_surface(ground, 6, 6, (3, 3)))), floor)
+    mats = [scn.add_material(pbrBaseColorFactor=[0.8, 0.25, 0.2, 1], pbrRoughnessFactor=0.45, pbrMetallicFactor=0.0),
+            scn.add_material(pbrBaseColorFactor=[0.95, 0.8, 0.4, 1], pbrRoughnessFactor=0.25, pbrMetallicFactor=1.0),
+            scn.add_material(pbrBaseColorFactor=[0.1, 0.3, 0.7, 1], pbrRoughnessFactor=0.6, pbrMetallicFactor=0.0, clearcoatFactor=1.0, clearcoatRoughness=0.05)]
+    for k, m in enumerate(mats):
+        scn.add_node(scn.add_primitive(*_split(_sphere(-1.6 + 1.6 * k, 0.6, 0.2 * k, 0.6))), m)
+    scn.lights = [
+        _light("point", position=(-2.0, 2.2, 1.5), color=(1.0, 0.9, 0.8), intensity=18.0),
+        _light("point", position=(1.5, 1.6, 1.8), color=(0.6, 0.8, 1.0), intensity=12.0, radius=0.25),
+        _light("spot", position=(0.0, 3.5, 0.5), direction=(0.1, -1.0, -0.1), color=(1, 1, 1), intensity=40.0, rng=9.0, inner=0.25, outer=0.55),
+        _light("directional", direction=(-0.4, -1.0, -0.3), color=(1.0, 0.95, 0.9), intensity=1.5, angular_size=0.06),
+        _light("directional", direction=(0.6, -0.7, 0.2), color=(0.4, 0.5, 0.7), intensity=0.7),
+    ]
+    cam = Camera()
+    cam.eye = np.array([0.3, 2.2, 5.0], np.float32)
+    cam.center = np.array([0.0, 0.5, 0.0], np.float32)
+    cam.yfov = math.radians(45.0)
+    cam.znear, cam.zfar = 0.05, 100.0
+    scn.camera = cam
+    return scn
+
+
+def synth_material_zoo(seed=1234, tex_size=64):
+    """One sphere per KHR_materials_* extension, every extension WITH its textures (all 22 slots of GltfShadeMaterial that
+    the path tracer reads are bound somewhere; gltf_material_eval.h.slang:168-457), plus KHR_texture_transform, TEXCOORD_1 and
+    vertex colours: sheen, iridescence (+ thickness texture), anisotropy (+ direction texture), specular / specular colour,
+    clearcoat (+ roughness + normal), transmission texture + thickness texture (volume), diffuse transmission (+ colour),
+    pbrSpecularGlossiness, emissive texture, BLEND alpha.  Runs the FEAT_ALL shade variant."""
+    rng = np.random.default_rng(seed)
+    scn = Scene()
+
+    def noise_rgba(srgb=False, lo=0.15, hi=1.0, alpha=None):
+        n = value_noise(tex_size, 5, rng, 4)
+        a = lo + (hi - lo) * n
+        if alpha is not None:
+            a[..., 3] = alpha
+        return scn.add_texture(_u8(a), srgb=srgb)
+    base, mr, nm = make_texture_set(tex_size, rng, (0.8, 0.8, 0.8))
+    t_base, t_mr, t_nm = scn.add_texture(base, srgb=True), scn.add_texture(mr), scn.add_texture(nm)
+    xf = (0.8, 0.3, -0.3, 0.8, 0.1, 0.2)  # KHR_texture_transform as the 2x3 matrix the loader would write
+
+    def ti(tex, texcoord=0, transform=False):
+        return scn.add_texture_info(tex, texcoord, xf if transform else (1, 0, 0, 1, 0, 0))
+    mats = [
+        dict(pbrBaseColorFactor=[0.35, 0.1, 0.4, 1], pbrRoughnessFactor=0.8, pbrMetallicFactor=0.0, sheenColorFactor=[0.9, 0.8, 1.0], sheenRoughnessFactor=0.6,
+             sheenColorTexture=ti(noise_rgba(True)), sheenRoughnessTexture=ti(noise_rgba())),
+        dict(pbrBaseColorFactor=[0.9, 0.9, 0.9, 1], pbrRoughnessFactor=0.3, pbrMetallicFactor=1.0, iridescenceFactor=1.0, iridescenceIor=1.35,
+             iridescenceThicknessMinimum=150.0, iridescenceThicknessMaximum=650.0, iridescenceTexture=ti(noise_rgba(lo=0.5)),
+             iridescenceThicknessTexture=ti(noise_rgba(), 1)),
+        dict(pbrBaseColorFactor=[0.8, 0.6, 0.3, 1], pbrRoughnessFactor=0.35, pbrMetallicFactor=1.0, anisotropyStrength=0.8,
+             anisotropyRotation=[math.sin(0.6), math.cos(0.6)], anisotropyTexture=ti(noise_rgba(lo=0.2), transform=True)),
+        dict(pbrBaseColorFactor=[0.2, 0.5, 0.3, 1], pbrRoughnessFactor=0.4, pbrMetallicFactor=0.0, specularFactor=0.8, specularColorFactor=[1.0, 0.7, 0.5],
+             specularTexture=ti(noise_rgba(lo=0.4)), specularColorTexture=ti(noise_rgba(True, lo=0.4)), pbrBaseColorTexture=ti(t_base),
+             pbrMetallicRoughnessTexture=ti(t_mr), normalTexture=ti(t_nm), normalTextureScale=0.8),
+        dict(pbrBaseColorFactor=[0.7, 0.1, 0.1, 1], pbrRoughnessFactor=0.5, pbrMetallicFactor=0.0, clearcoatFactor=0.9, clearcoatRoughness=0.3,
+             clearcoatTexture=ti(noise_rgba(lo=0.5)), clearcoatRoughnessTexture=ti(noise_rgba()), clearcoatNormalTexture=ti(t_nm)),
+        dict(pbrBaseColorFactor=[0.9, 0.95, 1.0, 1], pbrRoughnessFactor=0.1, pbrMetallicFactor=0.0, transmissionFactor=0.95, ior=1.45, thicknessFactor=0.8,
+             attenuationColor=[0.6, 0.85, 0.7], attenuationDistance=0.7, transmissionTexture=ti(noise_rgba(lo=0.6)), thicknessTexture=ti(noise_rgba(lo=0.5))),
+        dict(pbrBaseColorFactor=[0.8, 0.8, 0.3, 1], pbrRoughnessFactor=0.7, pbrMetallicFactor=0.0, diffuseTransmissionFactor=0.7,
+             diffuseTransmissionColor=[0.9, 0.6, 0.4], diffuseTransmissionTexture=ti(noise_rgba(lo=0.5)), diffuseTransmissionColorTexture=ti(noise_rgba(True, lo=0.4)),
+             doubleSided=1),
+        dict(pbrModel=1, pbrDiffuseFactor=[0.7, 0.5, 0.4, 1], pbrSpecularFactor=[0.6, 0.6, 0.6], pbrGlossinessFactor=0.8,
+             pbrDiffuseTexture=ti(noise_rgba(True, lo=0.3, alpha=1.0)), pbrSpecularGlossinessTexture=ti(noise_rgba(True, lo=0.0, hi=0.9))),
+        dict(pbrBaseColorFactor=[0.2, 0.2, 0.2, 1], pbrRoughnessFactor=0.6, pbrMetallicFactor=0.0, emissiveFactor=[2.0, 1.2, 0.4], emissiveTexture=ti(noise_rgba(True, lo=0.0))),
+        dict(pbrBaseColorFactor=[0.3, 0.6, 0.9, 0.6], pbrRoughnessFactor=0.5, pbrMetallicFactor=0.0, alphaMode=2, doubleSided=1, pbrBaseColorTexture=ti(noise_rgba(True, lo=0.3))),
+    ]
+    ids = [scn.add_material(**m) for m in mats]
+    for k, m in enumerate(ids):
+        pos, nrm, uv, tan, idx = _sphere(-2.4 + 1.2 * (k % 5), 0.55 + 1.25 * (k // 5), -0.3 * (k // 5), 0.5, n=20)
+        uv1 = uv[:, ::-1] * 0.7 + 0.1
+        col = None
+        if k == 0:  # vertex colours (COLOR_0 as packed unorm4x8)
+            c = _u8(np.concatenate([0.6 + 0.4 * rng.random((len(pos), 3)), np.ones((len(pos), 1))], 1)).astype(np.uint32)
+            col = c[:, 0] | (c[:, 1] << 8) | (c[:, 2] << 16) | (c[:, 3] << 24)
+        scn.add_node(scn.add_primitive(pos, idx, normals=nrm, uv0=uv, uv1=uv1, tangents=tan, colors=col), m)
+
+    def ground(u, v):
+        return _xyz((u * 2 - 1) * 6, np.zeros_like(u), (1 - v * 2) * 6)
+    gm = scn.add_material(pbrBaseColorFactor=[0.6, 0.6, 0.6, 1], pbrRoughnessFactor=0.8, pbrMetallicFactor=0.0, pbrBaseColorTexture=ti(t_base, transform=True))
+    scn.add_node(scn.add_primitive(*_split(param_surface(ground, 6, 6, (3, 3)))), gm)
+    cam = Camera()
+    cam.eye = np.array([0.0, 1.6, 5.6], np.float32)
+    cam.center = np.array([0.0, 1.1, 0.0], np.float32)
+    cam.yfov = math.radians(45.0)
+    cam.znear, cam.zfar = 0.05, 100.0
+    scn.camera = cam
+    return scn
+
+
 def triangle_soup(n, seed=1234, extent=1.0, size=0.15):
     """n random triangles in a cube: stress input for traversal parity tests."""
     rng = np.random.default_rng(seed)
