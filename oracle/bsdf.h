@@ -406,7 +406,9 @@ static inline void computeLobeWeights(const PbrMaterial& mat, float VdotN, float
   w[LOBE_DIFFUSE_REFLECTION] = diffuse * (1.0f - mat.diffuseTransmissionFactor);
 }
 
-static inline int findLobe(const PbrMaterial& mat, float VdotN, float rndVal)
+// lobeU: position of rndVal inside the chosen lobe's probability interval, in [0, 1): a fresh uniform number (the
+// dispersive transmission lobe picks its colour channel with it)
+static inline int findLobe(const PbrMaterial& mat, float VdotN, float rndVal, float& lobeU)
 {
   float w[LOBE_COUNT];
   computeLobeWeights(mat, VdotN, w);
@@ -414,11 +416,27 @@ static inline int findLobe(const PbrMaterial& mat, float VdotN, float rndVal)
   float weight = 0.0f;
   while(--lobe > 0)
   {
+    const float prev = weight;
     weight += w[lobe];
     if(rndVal < weight)
+    {
+      lobeU = (rndVal - prev) / w[lobe];
       break;
+    }
   }
   return lobe;  // falls through to LOBE_DIFFUSE_REFLECTION
+}
+
+// KHR_materials_dispersion: one colour channel per refraction event, per-channel index of refraction as the reference's
+// rasteriser defines it (shaders/gltf_raster.slang:204-208), weight 3 for the channel followed.  (nvshaders body of this
+// branch is external to the reference tree: restated from the extension's definition, unpinned.)
+static inline float3 applyDispersion(PbrMaterial& mat, float lobeU)
+{
+  const int   channel = std::min((int)(lobeU * 3.0f), 2);
+  const float spread = (float)(channel - 1) * 0.025f * mat.dispersion;
+  mat.ior1 = mat.ior1 + (mat.ior1 - 1.0f) * spread;
+  mat.ior2 = mat.ior2 + (mat.ior2 - 1.0f) * spread;
+  return f3(channel == 0 ? 3.0f : 0.0f, channel == 1 ? 3.0f : 0.0f, channel == 2 ? 3.0f : 0.0f);
 }
 
 // ---- diffuse ----------------------------------------------------------------------------------
@@ -684,7 +702,8 @@ static inline void bsdfEvaluate(BsdfEvaluateData& d, const PbrMaterial& matIn)
 {
   PbrMaterial mat = matIn;
   const float VdotN = dot(d.k1, mat.N);
-  const int   lobe = findLobe(mat, VdotN, d.xi.z);
+  float       lobeU = 0.0f;
+  const int   lobe = findLobe(mat, VdotN, d.xi.z, lobeU);
   d.bsdf_diffuse = f3(0.0f);
   d.bsdf_glossy = f3(0.0f);
   d.pdf = 0.0f;
@@ -700,7 +719,14 @@ static inline void bsdfEvaluate(BsdfEvaluateData& d, const PbrMaterial& matIn)
       brdf_ggx_smith_eval(d, mat, LOBE_SPECULAR_REFLECTION, mat.specularColor);
       break;
     case LOBE_SPECULAR_TRANSMISSION:
-      btdf_ggx_smith_eval(d, mat, mat.baseColor);
+      if(mat.dispersion > 0.0f)
+      {
+        const float3 base = mat.baseColor;
+        const float3 w = applyDispersion(mat, lobeU);
+        btdf_ggx_smith_eval(d, mat, base * w);
+      }
+      else
+        btdf_ggx_smith_eval(d, mat, mat.baseColor);
       break;
     case LOBE_METAL_REFLECTION:
       brdf_ggx_smith_eval(d, mat, LOBE_METAL_REFLECTION, mat.baseColor);
@@ -719,7 +745,8 @@ static inline void bsdfSample(BsdfSampleData& d, const PbrMaterial& matIn)
 {
   PbrMaterial mat = matIn;
   const float VdotN = dot(d.k1, mat.N);
-  const int   lobe = findLobe(mat, VdotN, d.xi.z);
+  float       lobeU = 0.0f;
+  const int   lobe = findLobe(mat, VdotN, d.xi.z, lobeU);
   d.pdf = 0.0f;
   d.bsdf_over_pdf = f3(0.0f);
   d.event_type = BSDF_EVENT_ABSORB;
@@ -736,7 +763,14 @@ static inline void bsdfSample(BsdfSampleData& d, const PbrMaterial& matIn)
       brdf_ggx_smith_sample(d, mat, LOBE_SPECULAR_REFLECTION, mat.specularColor);
       break;
     case LOBE_SPECULAR_TRANSMISSION:
-      btdf_ggx_smith_sample(d, mat, mat.baseColor);
+      if(mat.dispersion > 0.0f)
+      {
+        const float3 base = mat.baseColor;
+        const float3 w = applyDispersion(mat, lobeU);
+        btdf_ggx_smith_sample(d, mat, base * w);
+      }
+      else
+        btdf_ggx_smith_sample(d, mat, mat.baseColor);
       break;
     case LOBE_METAL_REFLECTION:
       brdf_ggx_smith_sample(d, mat, LOBE_METAL_REFLECTION, mat.baseColor);

@@ -1109,6 +1109,8 @@ __device__ PbrMaterial unpackTestMaterial(const float* p)
   m.diffuseTransmissionColor = f3(p[36], p[37], p[38]);
   m.scatterCoefficient = f3(0.0f);
   m.scatterAnisotropy = 0.0f;
+  m.dispersion = 0.0f;
+  m.retroreflection = 0.0f;
   return m;
 }
 
@@ -1638,6 +1640,11 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
           h->err = "b200pt_set_scene: material texture slot beyond numTextureInfos";
           return B200PT_E_INVALID;
         }
+      if(m.retroreflectionFactor > 0.0f)
+      {
+        h->err = "b200pt_set_scene: KHR_materials_retroreflection is not built (its lobe lives in nvshaders, external to the reference tree)";
+        return B200PT_E_UNSUPPORTED;
+      }
       if(m.transmissionFactor > 0.0f || m.transmissionTexture)
         feat |= FEAT_TRANSMISSION;
       if(m.thicknessFactor > 0.0f || m.thicknessTexture || m.multiscatterColorFactor[0] > 0.0f || m.multiscatterColorFactor[1] > 0.0f || m.multiscatterColorFactor[2] > 0.0f)

@@ -38,6 +38,8 @@ struct PbrMaterial
   float3 diffuseTransmissionColor;
   float3 scatterCoefficient;
   float  scatterAnisotropy;
+  float  dispersion;       // KHR_materials_dispersion (gltf_material_eval.h.slang:426-428)
+  float  retroreflection;  // KHR_materials_retroreflection: carried like the reference does; b200pt_set_scene rejects factors > 0
 };
 
 enum : int
@@ -208,8 +210,10 @@ PT_D float3 cosineSampleHemisphere(float r1, float r2)
 PT_D float fresnelCosineApprox(float VdotN, float roughness) { return lerpf(VdotN, sqrtf(0.5f + 0.5f * VdotN), sqrtf(roughness)); }
 
 // picks ONE lobe from the layered weights (clearcoat over sheen over metal | dielectric{spec, transmission, diffuse})
+// lobeU: where inside the chosen lobe's probability interval rndVal fell, in [0, 1) -- a fresh uniform number that the
+// transmission lobe uses to pick the colour channel of a dispersive refraction (only written for that lobe)
 template <uint32_t FEAT>
-PT_D int findLobe(const PbrMaterial& mat, float VdotN, float rndVal)
+PT_D int findLobe(const PbrMaterial& mat, float VdotN, float rndVal, float& lobeU)
 {
   float frCoat = 0.0f;
   if((FEAT & FEAT_CLEARCOAT) && mat.clearcoat > 0.0f)
@@ -254,11 +258,31 @@ PT_D int findLobe(const PbrMaterial& mat, float VdotN, float rndVal)
     return LOBE_SPECULAR_REFLECTION;
   if(FEAT & FEAT_TRANSMISSION)
   {
-    weight += diel * (1.0f - frDielectric) * mat.transmission;
+    const float wT = diel * (1.0f - frDielectric) * mat.transmission;
+    const float prev = weight;
+    weight += wT;
     if(rndVal < weight)
+    {
+      lobeU = (rndVal - prev) / wT;
       return LOBE_SPECULAR_TRANSMISSION;
+    }
   }
   return LOBE_DIFFUSE_REFLECTION;
+}
+
+// KHR_materials_dispersion on the specular-transmission lobe.  Per-channel index of refraction as the reference's own
+// rasteriser defines it (shaders/gltf_raster.slang:204-208: halfSpread = (ior - 1) * 0.025 * dispersion, iors = {ior -
+// halfSpread, ior, ior + halfSpread} for R, G, B); the path tracer follows ONE channel per refraction event, picked
+// uniformly with lobeU, and weights it by 3 (an unbiased estimate of the three-channel sum).  The nvshaders body of
+// this branch is not in the reference tree (unpinned like the rest of the BSDF stack).
+PT_D float3 applyDispersion(PbrMaterial& mat, float lobeU)
+{
+  const int   c3 = (int)(lobeU * 3.0f);
+  const int   channel = c3 < 2 ? c3 : 2;
+  const float spread = (float)(channel - 1) * 0.025f * mat.dispersion;
+  mat.ior1 = mat.ior1 + (mat.ior1 - 1.0f) * spread;  // the side that is air (ior 1) stays 1
+  mat.ior2 = mat.ior2 + (mat.ior2 - 1.0f) * spread;
+  return f3(channel == 0 ? 3.0f : 0.0f, channel == 1 ? 3.0f : 0.0f, channel == 2 ? 3.0f : 0.0f);
 }
 
 PT_D void iridescenceTint(const PbrMaterial& mat, int lobe, float kh, float3& tint)
@@ -557,7 +581,8 @@ __device__ __noinline__ BsdfEval bsdfEvaluate(const PbrMaterial& mat, float3 k1,
   d.bsdf_diffuse = f3(0.0f);
   d.bsdf_glossy = f3(0.0f);
   d.pdf = 0.0f;
-  const int lobe = findLobe<FEAT>(mat, dot(k1, mat.N), xi.z);
+  float     lobeU = 0.0f;
+  const int lobe = findLobe<FEAT>(mat, dot(k1, mat.N), xi.z, lobeU);
   if(lobe == LOBE_DIFFUSE_REFLECTION)
   {
     if(dot(k2, mat.Ng) > 0.0f)
@@ -575,7 +600,16 @@ __device__ __noinline__ BsdfEval bsdfEvaluate(const PbrMaterial& mat, float3 k1,
     }
   }
   else if((FEAT & FEAT_TRANSMISSION) && lobe == LOBE_SPECULAR_TRANSMISSION)
-    ggxTransmitEval(d, mat, mat.baseColor, k1, k2);
+  {
+    if(mat.dispersion > 0.0f)
+    {
+      PbrMaterial  md = mat;
+      const float3 w = applyDispersion(md, lobeU);
+      ggxTransmitEval(d, md, mat.baseColor * w, k1, k2);
+    }
+    else
+      ggxTransmitEval(d, mat, mat.baseColor, k1, k2);
+  }
   else if((FEAT & FEAT_SHEEN) && lobe == LOBE_SHEEN_REFLECTION)
     sheenEval(d, mat, k1, k2);
   else
@@ -595,7 +629,8 @@ __device__ __noinline__ BsdfSample bsdfSample(const PbrMaterial& mat, float3 k1,
   d.bsdf_over_pdf = f3(0.0f);
   d.pdf = 0.0f;
   d.event_type = BSDF_EVENT_ABSORB;
-  const int lobe = findLobe<FEAT>(mat, dot(k1, mat.N), xi.z);
+  float     lobeU = 0.0f;
+  const int lobe = findLobe<FEAT>(mat, dot(k1, mat.N), xi.z, lobeU);
   if(lobe == LOBE_DIFFUSE_REFLECTION || lobe == LOBE_DIFFUSE_TRANSMISSION)
   {
     const float  s = (lobe == LOBE_DIFFUSE_REFLECTION) ? 1.0f : -1.0f;
@@ -609,7 +644,16 @@ __device__ __noinline__ BsdfSample bsdfSample(const PbrMaterial& mat, float3 k1,
       d.event_type = (dot(d.k2, mat.Ng) < 0.0f) ? BSDF_EVENT_DIFFUSE_TRANSMISSION : BSDF_EVENT_ABSORB;
   }
   else if((FEAT & FEAT_TRANSMISSION) && lobe == LOBE_SPECULAR_TRANSMISSION)
-    ggxTransmitSample(d, mat, mat.baseColor, k1, xi);
+  {
+    if(mat.dispersion > 0.0f)
+    {
+      PbrMaterial  md = mat;
+      const float3 w = applyDispersion(md, lobeU);
+      ggxTransmitSample(d, md, mat.baseColor * w, k1, xi);
+    }
+    else
+      ggxTransmitSample(d, mat, mat.baseColor, k1, xi);
+  }
   else if((FEAT & FEAT_SHEEN) && lobe == LOBE_SHEEN_REFLECTION)
     sheenSample(d, mat, k1, xi);
   else

@@ -309,7 +309,8 @@ PT_D PbrMaterial evaluateMaterial(const DevScene& S, const b200pt_shade_material
     pbrMat.roughness = f2(roughness * roughness, roughness * roughness);
     pbrMat.metallic = clampf(metallic, 0.0f, 1.0f);
   }
-  // (occlusion is fetched by the reference but never used by the path tracer: skipped)
+  // occlusion (gltf_material_eval.h.slang:228-233) is fetched by the reference but never read by the path tracer
+  // (only the rasteriser's ambient term uses it): not evaluated here, no effect on the image
 
   pbrMat.N = hit.nrm;
   pbrMat.T = hit.tangent;
@@ -432,6 +433,11 @@ PT_D PbrMaterial evaluateMaterial(const DevScene& S, const b200pt_shade_material
   pbrMat.diffuseTransmissionColor = f3(material.diffuseTransmissionColor[0], material.diffuseTransmissionColor[1], material.diffuseTransmissionColor[2]);
   if((FEAT & FEAT_DIFFUSE_TRANSMISSION) && material.diffuseTransmissionColorTexture > 0)
     pbrMat.diffuseTransmissionColor *= xyz(PT_TEX(diffuseTransmissionColorTexture));
+  // KHR_materials_dispersion (gltf_material_eval.h.slang:426-428); evaluated on the specular-transmission lobe (bsdf.cuh)
+  pbrMat.dispersion = (FEAT & FEAT_TRANSMISSION) ? material.dispersion : 0.0f;
+  // KHR_materials_retroreflection (:447-452): the lobe itself lives in nvshaders (external, not restated): scenes that
+  // use it are rejected by b200pt_set_scene, so the factor is always 0 here
+  pbrMat.retroreflection = 0.0f;
 #undef PT_TEX
   return pbrMat;
 }

@@ -49,6 +49,8 @@ static PbrMaterial unpack(const float* p)
   m.diffuseTransmissionColor = f3(p[36], p[37], p[38]);
   m.scatterCoefficient = f3(0.0f);
   m.scatterAnisotropy = 0.0f;
+  m.dispersion = 0.0f;
+  m.retroreflection = 0.0f;
   return m;
 }
 

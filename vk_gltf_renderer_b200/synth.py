@@ -289,7 +289,7 @@ def _split(t):
 # ------------------------------------------------------------------------------------------------
 # SynthGlass: transmission + volume stand-in for DragonDispersion
 # ------------------------------------------------------------------------------------------------
-def synth_glass(seed=1234, n=96, scatter=False):
+def synth_glass(seed=1234, n=96, scatter=False, dispersion=0.0):
     rng = np.random.default_rng(seed)
     scn = Scene()
     k = rng.random(6) * 6.28
@@ -302,7 +302,7 @@ def synth_glass(seed=1234, n=96, scatter=False):
     glass = scn.add_material(pbrBaseColorFactor=[1, 1, 1, 1], pbrRoughnessFactor=0.05, pbrMetallicFactor=0.0,
                              transmissionFactor=1.0, thicknessFactor=1.0, attenuationDistance=0.5,
                              attenuationColor=[0.85, 0.35, 0.25], ior=1.5,
-                             multiscatterColorFactor=[0.6, 0.6, 0.6] if scatter else [0, 0, 0], scatterAnisotropy=0.3)
+                             multiscatterColorFactor=[0.6, 0.6, 0.6] if scatter else [0, 0, 0], scatterAnisotropy=0.3, dispersion=dispersion)
     scn.add_node(scn.add_primitive(pos, idx, normals=nrm, uv0=uv, tangents=tan), glass)
 
     def ground(u, v):
