@@ -29,3 +29,12 @@ done
 if [ -n "$NCU_LIGHT" ]; then
   B200PT_FRAMES_IN_FLIGHT=1 ncu --metrics gpu__time_duration.sum,smsp__thread_inst_executed_per_inst_executed.ratio,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:'k_(trace|shadow|shade|alpha)' -c 60 --csv --log-file gpurun_out/${TAG}_ncu_light.csv python bench.py --steps 1 --warmup 1 --profile-only > gpurun_out/${TAG}_ncu_light.log 2>&1
 fi
+if [ -n "$TIMELINE" ]; then
+  B200PT_TIMELINE=$PWD/gpurun_out/${TAG}_timeline.csv python bench.py --steps 12 --warmup 4 --profile-only > gpurun_out/${TAG}_timeline.log 2>&1
+  for f in gpurun_out/${TAG}_timeline.csv.*; do python scripts/timeline_summary.py $f 6; done
+fi
+if [ -n "$NCU_FULL" ]; then
+  # one bounce-1 launch of the kernels named in $NCU_FULL (regex), full sections + source counters
+  B200PT_FRAMES_IN_FLIGHT=1 ncu --set full --import-source on --clock-control none -k regex:"$NCU_FULL" --launch-skip ${NCU_SKIP:-2} -c ${NCU_COUNT:-1} -f -o gpurun_out/${TAG}_full python bench.py --steps 1 --warmup 1 --profile-only > gpurun_out/${TAG}_ncu_full.log 2>&1
+  ls -la gpurun_out/${TAG}_full.ncu-rep
+fi

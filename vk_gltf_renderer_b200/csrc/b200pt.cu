@@ -12,6 +12,7 @@
 // One path slot per pixel; samples of a pixel within a frame run back to back in the same slot
 // (path regeneration) because the reference continues ONE rng stream across a pixel's samples.
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -305,6 +306,10 @@ __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const ui
                                                uint32_t* cntCont, DevStats* stats, int mode)
 {
   static_assert(kCand == 4 || kCand == 8, "kCand lanes per path");
+  // candidate slots index the triangle array of the tree that produced them: the merged tree for closest-hit rays,
+  // the split opaque / non-opaque arrays for shadow rays
+  const uint2* __restrict__ triMeta = SHADOW ? S.triMetaS : S.triMeta;
+  constexpr int             KF = 16;  // candidates per walk of the in-kernel fallback (its list lives in local memory)
   stageSrgbLut(S.lutSrgb);
   const uint32_t count = *cntIn;
   constexpr int  G = kCand, PPW = 32 / kCand;  // lanes per path, paths per warp
@@ -330,7 +335,7 @@ __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const ui
     {
       const float4 c = P.cand[sub][path];
       slot = __float_as_uint(c.w);
-      const uint2               meta = S.triMeta[slot];
+      const uint2               meta = triMeta[slot];
       const bool                flip = ((meta.x >> 28) & TRI_FLIPPED) != 0;  // mirrored instance: (u, v) swap back
       const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
       ct = c.x;
@@ -370,14 +375,14 @@ __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const ui
           opq = seedHit(S.bvh, hp.x, hp.y, hp.z, __float_as_uint(hp.w));
         float    loT = lastT;
         uint32_t loId = info.y;
-        Cand     cand[kCand];
+        Cand     cand[KF];
         bool     accepted = false, overflowed = false;
         for(;;)
         {
-          const int m = walkCollect(S.bvh, xyz(o), xyz(d), tmin, d.w, true, false, true, loT, loId, opq, cand, &overflowed);
+          const int m = walkCollect<KF>(S.bvh, xyz(o), xyz(d), tmin, d.w, true, false, true, true, loT, loId, opq, cand, &overflowed);
           for(int i = 0; i < m && !accepted; i++)
           {
-            const uint2               meta = S.triMeta[cand[i].slot];
+            const uint2               meta = triMeta[cand[i].slot];
             const bool                flip = ((meta.x >> 28) & TRI_FLIPPED) != 0;
             const float               u = flip ? cand[i].v : cand[i].u, v = flip ? cand[i].u : cand[i].v;
             const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
@@ -389,10 +394,10 @@ __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const ui
               accepted = true;
             }
           }
-          if(accepted || m < kCand)
+          if(accepted || m < KF)
             break;
-          loT = cand[kCand - 1].t;
-          loId = cand[kCand - 1].gid;
+          loT = cand[KF - 1].t;
+          loId = cand[KF - 1].gid;
         }
         if(!accepted && sub == 0 && opq.slot != 0xFFFFFFFFu)
         {
@@ -415,7 +420,7 @@ __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const ui
       bool         isInside = (__float_as_uint(misc.z) & PF_SHADOW_INSIDE) != 0;
       const float3 dir = valid ? xyz(P.shD[path]) : f3(0, 0, 1);
       auto         accept = [&](uint32_t sl, float t, float u, float v) {
-        const uint2               meta = S.triMeta[sl];
+        const uint2               meta = triMeta[sl];
         const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
         const float               seg = fmaxf(0.0f, t - prevHitT);
         const float3              cur = getShadowTransmission(S, node, S.prims[node.renderPrimID], meta.y, f3(1.0f - u - v, u, v), seg, dir, isInside);
@@ -456,13 +461,13 @@ __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const ui
         const float4 so = P.shO[path];
         float        loT = lastT;
         uint32_t     loId = info.y;
-        Cand         cand[kCand];
+        Cand         cand[KF];
         bool         overflowed = false;
         while(!done)
         {
           TraceHit opq;
           opq.slot = 0xFFFFFFFFu;
-          const int m = walkCollect(S.bvh, xyz(so), dir, 0.0f, so.w, false, true, true, loT, loId, opq, cand, &overflowed);
+          const int m = walkCollect<KF>(S.bvhA, xyz(so), dir, 0.0f, so.w, false, true, true, true, loT, loId, opq, cand, &overflowed);
           if(opq.slot != 0xFFFFFFFFu)
           {
             // (the first walk of the segment found no opaque occluder, so none can turn up here)
@@ -471,7 +476,7 @@ __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const ui
           }
           for(int i = 0; i < m && !done; i++)
           {
-            const uint2               meta = S.triMeta[cand[i].slot];
+            const uint2               meta = triMeta[cand[i].slot];
             const bool                flip = ((meta.x >> 28) & TRI_FLIPPED) != 0;
             const float               u = flip ? cand[i].v : cand[i].u, v = flip ? cand[i].u : cand[i].v;
             const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
@@ -479,10 +484,10 @@ __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const ui
             if(rnd(seed) < opacity)
               accept(cand[i].slot, cand[i].t, u, v);
           }
-          if(m < kCand)
+          if(m < KF)
             break;
-          loT = cand[kCand - 1].t;
-          loId = cand[kCand - 1].gid;
+          loT = cand[KF - 1].t;
+          loId = cand[KF - 1].gid;
         }
         if(overflowed && sub == 0)
           atomicOr(&stats->errorFlags, 1ull);
@@ -888,6 +893,7 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathStat
   constexpr int SS = 1;
 #endif
   int             path = -1;  // -1: lane needs work, -2: queue exhausted
+  int             phase = 0;  // 0: occlusion query against the opaque-only tree, 1: candidates from the non-opaque tree
   bool            travDone = false;
   for(;;)
   {
@@ -896,28 +902,37 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathStat
     {
       travDone = false;
       T.flushCounters(&stats->nodesVisited, &stats->trisTested);
-      uint2 info = make_uint2(0u, 0u);
-      if(T.best.slot != 0xFFFFFFFFu)
-        info.x = 0x80000000u;  // an opaque occluder ended the query (raytracer_interface.h.slang:181-184)
-      else
-      {
-        const int n = T.collectN;
-#pragma unroll
-        for(int i = 0; i < kCand; i++)
-          if(i < n)
-          {
-            const Cand c = cand[i * cs];
-            P.cand[i][path] = f4(c.t, c.u, c.v, __uint_as_float(c.slot));
-          }
-        info = make_uint2((uint32_t)n, n > 0 ? cand[(n - 1) * cs].gid : 0u);
-      }
-      P.candInfo[path] = info;
-      // (a continuation path always goes back to k_alpha: its running transmission is parked and must be folded)
-      if((info.x != 0u && info.x != 0x80000000u) || cont)
-        queuePush(qAlpha, cntAlpha, (uint32_t)path);
       if(T.overflow)
         atomicOr(&stats->errorFlags, 1ull);
-      path = -1;
+      if(phase == 0 && T.best.slot == 0xFFFFFFFFu && S.hasAlpha)
+      {
+        // no opaque occluder: the non-opaque candidates of the segment, nearest first
+        phase = 1;
+        T.init(S.bvhA, T.org, T.dir, 0.0f, T.tmax, false, true, false, 0.f, 0u, true);
+      }
+      else
+      {
+        uint2 info = make_uint2(0u, 0u);
+        if(T.best.slot != 0xFFFFFFFFu)
+          info.x = 0x80000000u;  // an opaque occluder ended the query (raytracer_interface.h.slang:181-184)
+        else
+        {
+          const int n = T.collectN;
+#pragma unroll
+          for(int i = 0; i < kCand; i++)
+            if(i < n)
+            {
+              const Cand c = cand[i * cs];
+              P.cand[i][path] = f4(c.t, c.u, c.v, __uint_as_float(c.slot));
+            }
+          info = make_uint2((uint32_t)n, n > 0 ? cand[(n - 1) * cs].gid : 0u);
+        }
+        P.candInfo[path] = info;
+        // (a continuation path always goes back to k_alpha: its running transmission is parked and must be folded)
+        if((info.x != 0u && info.x != 0x80000000u) || cont)
+          queuePush(qAlpha, cntAlpha, (uint32_t)path);
+        path = -1;
+      }
     }
     __syncwarp();
     {
@@ -933,9 +948,15 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathStat
           const float4 so = P.shO[path];
           const float4 sd = P.shD[path];
           if(!cont)
-            T.init(S.bvh, xyz(so), xyz(sd), 0.0f, so.w, false, true, false, 0.f, 0u);
+          {
+            phase = 0;
+            T.init(S.bvhO, xyz(so), xyz(sd), 0.0f, so.w, false, true, false, 0.f, 0u, false);
+          }
           else
-            T.init(S.bvh, xyz(so), xyz(sd), 0.0f, so.w, false, true, true, P.cand[kCand - 1][path].x, P.candInfo[path].y);
+          {
+            phase = 1;
+            T.init(S.bvhA, xyz(so), xyz(sd), 0.0f, so.w, false, true, true, P.cand[kCand - 1][path].x, P.candInfo[path].y, true);
+          }
         }
       }
     }
@@ -1222,8 +1243,14 @@ struct b200pt
   {
     cudaEvent_t a, b;
     int         cat;
+    int         lane;  // timeline: stream the launch went to (-1 main)
+    uint64_t    frame;
   };
   bool               profiling = false;
+  // B200PT_TIMELINE=<file>: event pairs around every launch WITHOUT serialising the frames in flight; flushEvents appends
+  // "frame,lane,stage,start_ms,end_ms" rows (times relative to tlBase) -- the per-rank timeline of a real run
+  FILE*              timeline = nullptr;
+  cudaEvent_t        tlBase = nullptr;
   std::vector<EvRec> evPool;
   size_t             evUsed = 0;
   double             msCat[6] = {0, 0, 0, 0, 0, 0};  // 0 k_trace, 1 k_shade, 2 k_shadow, 3 other, 4 k_alpha, 5 k_resolve
@@ -1349,6 +1376,7 @@ void flushEvents(b200pt* h)
   if(h->evUsed == 0)
     return;
   syncAll(h);
+  static const char* const kStage[6] = {"k_trace", "k_shade", "k_shadow", "other", "k_alpha", "k_resolve"};
   for(size_t i = 0; i < h->evUsed; i++)
   {
     float ms = 0.f;
@@ -1357,7 +1385,15 @@ void flushEvents(b200pt* h)
       h->msCat[h->evPool[i].cat] += ms;
       h->launchesCat[h->evPool[i].cat]++;
     }
+    if(h->timeline && h->tlBase)
+    {
+      float t0 = 0.f, t1 = 0.f;
+      if(cudaEventElapsedTime(&t0, h->tlBase, h->evPool[i].a) == cudaSuccess && cudaEventElapsedTime(&t1, h->tlBase, h->evPool[i].b) == cudaSuccess)
+        fprintf(h->timeline, "%llu,%d,%s,%.4f,%.4f\n", (unsigned long long)h->evPool[i].frame, h->evPool[i].lane, kStage[h->evPool[i].cat], t0, t1);
+    }
   }
+  if(h->timeline)
+    fflush(h->timeline);
   h->evUsed = 0;
 }
 
@@ -1516,6 +1552,25 @@ int b200pt_create(b200pt_t** out, int cuda_device)
     need(cudaMemset(h->dStats, 0, sizeof(DevStats)));
   if(const char* e = getenv("B200PT_FRAMES_IN_FLIGHT"))
     h->numLanes = std::min(std::max(atoi(e), 1), (int)b200pt::kMaxLanes);
+  if(const char* e = getenv("B200PT_TIMELINE"))
+  {
+    // one file per process (ranks of a multi-GPU run append their pid)
+    const std::string path = std::string(e) + "." + std::to_string((long long)getpid());
+    h->timeline = fopen(path.c_str(), "w");
+    if(h->timeline)
+    {
+      fprintf(h->timeline, "frame,lane,stage,start_ms,end_ms\n");
+      need(cudaEventCreate(&h->tlBase));
+      need(cudaEventRecord(h->tlBase, h->stream));
+      h->evPool.resize(16384);
+      for(auto& ev : h->evPool)
+      {
+        need(cudaEventCreate(&ev.a));
+        need(cudaEventCreate(&ev.b));
+        ev.cat = 3;
+      }
+    }
+  }
   for(int l = 0; l < b200pt::kMaxLanes; l++)
   {
     b200pt::Lane& L = h->lanes[l];
@@ -1579,11 +1634,16 @@ void b200pt_destroy(b200pt_t* h)
     cudaFree(h->dEnvAccel);
   cudaFree(h->dStats);
   cudaFree(h->dLutSrgb);
+  flushEvents(h);
   for(auto& e : h->evPool)
   {
     cudaEventDestroy(e.a);
     cudaEventDestroy(e.b);
   }
+  if(h->tlBase)
+    cudaEventDestroy(h->tlBase);
+  if(h->timeline)
+    fclose(h->timeline);
   cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1861,8 +1921,39 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
     gids[i] = i;
     anyNonOpaque = anyNonOpaque || !(flat[i].flags & TRI_OPAQUE);
   }
-  WideBvh bvh;
-  buildWideBvh(flat, gids, 0u, bvh);
+  // closest-hit rays walk the merged tree; shadow rays walk an opaque-only tree first (any hit ends the query, occluded
+  // rays never meet the foliage boxes) and the non-opaque tree after it (traverse.cuh).  The three builds run in parallel.
+  WideBvh bvh, bvhO, bvhA;
+  {
+    std::vector<FlatTri>  flatO, flatA;
+    std::vector<uint32_t> gidO, gidA;
+    if(anyNonOpaque)
+      for(uint32_t i = 0; i < (uint32_t)flat.size(); i++)
+      {
+        if(flat[i].flags & TRI_OPAQUE)
+        {
+          flatO.push_back(flat[i]);
+          gidO.push_back(i);
+        }
+        else
+        {
+          flatA.push_back(flat[i]);
+          gidA.push_back(i);
+        }
+      }
+    std::thread tO, tA;
+    if(anyNonOpaque)
+    {
+      tO = std::thread([&] { buildWideBvh(flatO, gidO, 0u, bvhO); });
+      tA = std::thread([&] { buildWideBvh(flatA, gidA, (uint32_t)flatO.size(), bvhA); });
+    }
+    buildWideBvh(flat, gids, 0u, bvh);
+    if(anyNonOpaque)
+    {
+      tO.join();
+      tA.join();
+    }
+  }
   float *   dBvhNodes, *dTris;
   uint32_t* dMeta;
   if((rc = upload(h, h->sceneAllocs, bvh.nodes.data(), bvh.nodes.size(), &dBvhNodes)))
@@ -1876,9 +1967,37 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
   S.bvh.prmtPool = kPrmtPool;
   S.hasAlpha = anyNonOpaque ? 1 : 0;
   S.triMeta = reinterpret_cast<const uint2*>(dMeta);
-  h->nodeBytes = bvh.nodes.size() * sizeof(float);
-  h->triBytes = bvh.tris.size() * sizeof(float);
-  h->numNodes = bvh.numNodes;
+  S.bvhO = S.bvh;
+  S.bvhA = S.bvh;
+  S.triMetaS = S.triMeta;
+  uint64_t splitNodeBytes = 0, splitTriBytes = 0;
+  if(anyNonOpaque)
+  {
+    std::vector<float>    trisS(bvhO.tris);
+    std::vector<uint32_t> metaS(bvhO.triMeta);
+    trisS.insert(trisS.end(), bvhA.tris.begin(), bvhA.tris.end());
+    metaS.insert(metaS.end(), bvhA.triMeta.begin(), bvhA.triMeta.end());
+    float *   dNodesO, *dNodesA, *dTrisS;
+    uint32_t* dMetaS;
+    if((rc = upload(h, h->sceneAllocs, bvhO.nodes.data(), bvhO.nodes.size(), &dNodesO)))
+      return rc;
+    if((rc = upload(h, h->sceneAllocs, bvhA.nodes.data(), bvhA.nodes.size(), &dNodesA)))
+      return rc;
+    if((rc = upload(h, h->sceneAllocs, trisS.data(), trisS.size(), &dTrisS)))
+      return rc;
+    if((rc = upload(h, h->sceneAllocs, metaS.data(), metaS.size(), &dMetaS)))
+      return rc;
+    S.bvhO.nodes = reinterpret_cast<const float4*>(dNodesO);
+    S.bvhO.tris = reinterpret_cast<const float4*>(dTrisS);
+    S.bvhA.nodes = reinterpret_cast<const float4*>(dNodesA);
+    S.bvhA.tris = reinterpret_cast<const float4*>(dTrisS);
+    S.triMetaS = reinterpret_cast<const uint2*>(dMetaS);
+    splitNodeBytes = (bvhO.nodes.size() + bvhA.nodes.size()) * sizeof(float);
+    splitTriBytes = trisS.size() * sizeof(float);
+  }
+  h->nodeBytes = bvh.nodes.size() * sizeof(float) + splitNodeBytes;
+  h->triBytes = bvh.tris.size() * sizeof(float) + splitTriBytes;
+  h->numNodes = bvh.numNodes + (anyNonOpaque ? bvhO.numNodes + bvhA.numNodes : 0u);
   h->numTris = bvh.numTris;
   CK(cudaStreamSynchronize(h->stream));
   h->haveScene = true;
@@ -2247,13 +2366,16 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
     tAnyHit = 4,
     tResolve = 5
   };
+  const uint64_t frameNo = h->frameSerial - 1;
   auto timed = [&](int cat, auto&& launch) {
-    if(h->profiling)
+    if(h->profiling || h->timeline)
     {
       if(h->evUsed == h->evPool.size())
         flushEvents(h);
       b200pt::EvRec& r = h->evPool[h->evUsed++];
       r.cat = cat;
+      r.lane = (st == h->stream) ? -1 : laneIdx;
+      r.frame = frameNo;
       cudaEventRecord(r.a, st);
       launch();
       cudaEventRecord(r.b, st);

@@ -55,9 +55,12 @@ struct DevScene
   const b200pt_light*          lights;
   int                          numLights;
   int                          numTextures;
-  BvhView                      bvh;       // ONE tree over every triangle; TRI_OPAQUE per triangle decides hit vs any-hit candidate
+  BvhView                      bvh;       // closest-hit walks: ONE tree over every triangle; TRI_OPAQUE per triangle decides hit vs candidate
+  BvhView                      bvhO;      // shadow walks, phase 0: FORCE_OPAQUE triangles only (any hit ends the query)
+  BvhView                      bvhA;      // shadow walks, phase 1: non-opaque triangles only (candidates); shares bvhO's triangle array
   int                          hasAlpha;  // the scene has non-opaque triangles (the any-hit kernels are launched)
-  const uint2*                 triMeta;   // per triangle slot: (rnode | flags<<28, primitiveID)
+  const uint2*                 triMeta;   // per triangle slot of `bvh`: (rnode | flags<<28, primitiveID)
+  const uint2*                 triMetaS;  // per triangle slot of bvhO / bvhA (== triMeta in scenes without non-opaque triangles)
   const float4*                envRgba;  // lat-long radiance, pdf in .w
   const uint2*                 envAccel; // (alias, q bits)
   const float*                 lutSrgb;  // 512 floats: sRGB decode table, then i/255 (staged into shared memory per block)

@@ -105,7 +105,7 @@ int main(int argc, char** argv)
       uint32_t loId = 0;
       for(;;)
       {
-        const int m = walkCollect(view, org, dir, tmin, tmax, false, false, haveLo, loT, loId, opq, cand, &ovf, &maxSp);
+        const int m = walkCollect(view, org, dir, tmin, tmax, false, false, true, haveLo, loT, loId, opq, cand, &ovf, &maxSp);
         for(int i = 0; i < m && ok; i++, k++)
           ok = k < expect.size() && __float_as_uint(cand[i].t) == __float_as_uint(expect[k].t) && cand[i].gid == expect[k].gid;
         if(!ok || m < kCand)
@@ -127,7 +127,7 @@ int main(int argc, char** argv)
       TraceHit opq;
       opq.slot = 0xFFFFFFFFu;
       bool     ovf = false;
-      int      m = walkCollect(view, org, dir, tmin, tmax, false, true, false, 0.f, 0u, opq, cand, &ovf, &maxSp);
+      int      m = walkCollect(view, org, dir, tmin, tmax, false, true, false, false, 0.f, 0u, opq, cand, &ovf, &maxSp);
       if((opq.slot != 0xFFFFFFFFu) != (firstOpaque != bf.size()) || ovf)
         bad2++;
       else if(opq.slot == 0xFFFFFFFFu)
@@ -143,7 +143,7 @@ int main(int argc, char** argv)
           const float    loT = cand[kCand - 1].t;
           const uint32_t loId = cand[kCand - 1].gid;
           opq.slot = 0xFFFFFFFFu;
-          m = walkCollect(view, org, dir, tmin, tmax, false, true, true, loT, loId, opq, cand, &ovf, &maxSp);
+          m = walkCollect(view, org, dir, tmin, tmax, false, true, false, true, loT, loId, opq, cand, &ovf, &maxSp);
           if(opq.slot != 0xFFFFFFFFu)
             ok = false;
         }

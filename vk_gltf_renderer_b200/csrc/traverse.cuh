@@ -102,8 +102,11 @@ PT_D TraceHit seedHit(const BvhView bvh, float t, float u, float v, uint32_t slo
 //     them all and a continuation walk resumes behind the last one -- it refines `best` as well.
 //   shadow mode (IRaytracer::TraceShadow, :139-187, with the pinned order: any opaque occluder ends the query first)
 //     opaque hit      -> done (occluded)
-//     non-opaque hit  -> candidate list as above; the bound stays at the segment end, so the walk visits the whole
-//                        segment and an occluder behind the kept candidates is still found
+//     non-opaque hit  -> candidate list as above; the bound stays at the segment end (an occluder behind the kept
+//                        candidates must still be found) unless the tree holds no opaque triangle (`shrink`).
+//     Measured on the bench scene: shadow walks of the merged tree cost twice the round-1 pair of walks (opaque-only
+//     tree with any-exit, then the any-hit tree with a shrinking bound: occluded rays never meet the foliage boxes), so
+//     k_shadow keeps two trees and only k_trace walks the merged one.
 //   cull    : back-face culling per triangle flags (RAY_FLAG_CULL_BACK_FACING_TRIANGLES + instance cull-disable)
 //   lo      : only hits lexicographically after (loT, loId) in (t, global id) order count (continuation walks)
 struct TravState
@@ -115,7 +118,7 @@ struct TravState
   float         idx, idy, idz;
   float         tmin, tmax, tLow, loT, bound;
   uint32_t      loId, octInv4;
-  bool          haveLo, cull, shadow;
+  bool          haveLo, cull, shadow, shrink;
   bool          overflow;  // a push found the stack full: the walk is incomplete (surfaced as a device error flag)
   TraceHit      best;
   uint2         cur;   // current node group (x = child base, y = hit bits << 24 | imask)
@@ -126,8 +129,10 @@ struct TravState
   unsigned int nodeCount, triCount;
 #endif
 
-  PT_D void init(const BvhView bvh, float3 o, float3 d, float tmin_, float tmax_, bool cull_, bool shadow_, bool haveLo_, float loT_, uint32_t loId_)
+  PT_D void init(const BvhView bvh, float3 o, float3 d, float tmin_, float tmax_, bool cull_, bool shadow_, bool haveLo_, float loT_, uint32_t loId_,
+                 bool shrink_ = true)
   {
+    shrink = shrink_ || !shadow_;
     collectN = 0;
     nodes = bvh.nodes;
     tris = bvh.tris;
@@ -188,7 +193,7 @@ struct TravState
   // Returns true when the traversal is complete.  `stack` is per-thread scratch of kStackSize entries (entry i at
   // stack[i * SS]: local memory with SS = 1, or a shared-memory column), `cand` the candidate list (entry i at
   // cand[i * cs]: the kernels keep it in shared memory, one column per thread).
-  template <int SS = 1>
+  template <int SS = 1, int KC = kCand>
   PT_D bool step(uint2* __restrict__ stack, int postponeShift, Cand* __restrict__ cand, int cs)
   {
     // single exit: an early return inside the divergent regions would move their reconvergence point out of the
@@ -362,16 +367,16 @@ struct TravState
             // candidate for the any-hit kernel: in front of the opaque hit (closest mode) and, once the list is full,
             // in front of its last entry
             bool keep = shadow | (t < best.t);
-            if(collectN == kCand)
+            if(collectN == KC)
             {
-              const float    lt = cand[(kCand - 1) * cs].t;
-              const uint32_t lg = cand[(kCand - 1) * cs].gid;
+              const float    lt = cand[(KC - 1) * cs].t;
+              const uint32_t lg = cand[(KC - 1) * cs].gid;
               keep &= (t < lt) | ((t == lt) & (gid < lg));
             }
             if(keep)
             {
               // insertion sort by (t, id); a full list drops its last entry
-              int pos = collectN < kCand ? collectN : kCand - 1;
+              int pos = collectN < KC ? collectN : KC - 1;
               while(pos > 0)
               {
                 const Cand p = cand[(pos - 1) * cs];
@@ -387,10 +392,10 @@ struct TravState
               nc.slot = slot;
               nc.gid = gid;
               cand[pos * cs] = nc;
-              if(collectN < kCand)
+              if(collectN < KC)
                 collectN++;
-              if(collectN == kCand && !shadow)
-                bound = fminf(bound, cand[(kCand - 1) * cs].t);
+              if(collectN == KC && shrink)
+                bound = fminf(bound, cand[(KC - 1) * cs].t);
             }
           }
         }
@@ -427,21 +432,22 @@ struct TravState
 };
 
 // One complete walk on one lane (the any-hit kernels' rare in-kernel fallback; the host-side check of this source):
-// the up-to-kCand nearest candidates behind the lower bound, sorted, in `cand`; `opq` carries the opaque hit in and out
+// the up-to-KC nearest candidates behind the lower bound, sorted, in `cand`; `opq` carries the opaque hit in and out
 // (closest mode: refined; shadow mode: slot != miss means occluded).  Returns the number of candidates that count
 // (closest mode: those in front of the opaque hit).  *overflowed is OR-ed with the stack-overflow flag.
-PT_D int walkCollect(const BvhView bvh, float3 org, float3 dir, float tmin, float tmax, bool cull, bool shadow, bool haveLo, float loT, uint32_t loId, TraceHit& opq,
-                     Cand* __restrict__ cand, bool* overflowed = nullptr, int* deepest = nullptr)
+template <int KC = kCand>
+PT_D int walkCollect(const BvhView bvh, float3 org, float3 dir, float tmin, float tmax, bool cull, bool shadow, bool shrink, bool haveLo, float loT, uint32_t loId,
+                     TraceHit& opq, Cand* __restrict__ cand, bool* overflowed = nullptr, int* deepest = nullptr)
 {
   TravState T;
   uint2     stack[TravState::kStackSize];
-  T.init(bvh, org, dir, tmin, tmax, cull, shadow, haveLo, loT, loId);
+  T.init(bvh, org, dir, tmin, tmax, cull, shadow, haveLo, loT, loId, shrink);
   if(opq.slot != 0xFFFFFFFFu)
   {
     T.best = opq;
     T.bound = fminf(T.bound, opq.t);
   }
-  while(!T.step(stack, 2, cand, 1))
+  while(!T.template step<1, KC>(stack, 2, cand, 1))
   {
     if(deepest && T.sp > *deepest)
       *deepest = T.sp;
