@@ -360,6 +360,185 @@ def _tex_transform(tinfo):
     return (sx * c, -sy * s, sx * s, sy * c, ox, oy)
 
 
+def populate_shade_material(sm, add_texture_info):
+    """tinygltf::Material (here: the glTF JSON dict) -> GltfShadeMaterial, field by field like
+    MaterialCache::populateShaderMaterial (src/gltf_material_cache.cpp:63-233).  `add_texture_info(index, texCoord,
+    uvTransform)` appends a GltfTextureInfo and returns its slot (> 0; slot 0 is the "no texture" sentinel)."""
+    def handle(mat, slot, tinfo):
+        if tinfo is not None and tinfo.get("index", -1) != -1:
+            setattr(mat, slot, add_texture_info(tinfo["index"], tinfo.get("texCoord", 0), _tex_transform(tinfo)))
+
+    m = default_material()
+    am = sm.get("alphaMode", "OPAQUE")
+    m.alphaMode = 0 if am == "OPAQUE" else (1 if am == "MASK" else 2)
+    m.alphaCutoff = sm.get("alphaCutoff", 0.5)
+    m.doubleSided = 1 if sm.get("doubleSided", False) else 0
+    pbr = sm.get("pbrMetallicRoughness", {})
+    m.pbrBaseColorFactor[:] = pbr.get("baseColorFactor", [1, 1, 1, 1])
+    m.pbrMetallicFactor = pbr.get("metallicFactor", 1.0)
+    m.pbrRoughnessFactor = pbr.get("roughnessFactor", 1.0)
+    m.normalTextureScale = (sm.get("normalTexture") or {}).get("scale", 1.0)
+    m.occlusionStrength = (sm.get("occlusionTexture") or {}).get("strength", 1.0)
+    m.emissiveFactor[:] = sm.get("emissiveFactor", [0, 0, 0])
+    handle(m, "emissiveTexture", sm.get("emissiveTexture"))
+    handle(m, "normalTexture", sm.get("normalTexture"))
+    handle(m, "pbrBaseColorTexture", pbr.get("baseColorTexture"))
+    handle(m, "pbrMetallicRoughnessTexture", pbr.get("metallicRoughnessTexture"))
+    handle(m, "occlusionTexture", sm.get("occlusionTexture"))
+    ex = sm.get("extensions", {})
+    e = ex.get("KHR_materials_transmission", {})
+    m.transmissionFactor = e.get("transmissionFactor", 0.0)
+    handle(m, "transmissionTexture", e.get("transmissionTexture"))
+    m.ior = ex.get("KHR_materials_ior", {}).get("ior", 1.5)
+    e = ex.get("KHR_materials_volume", {})
+    m.attenuationColor[:] = e.get("attenuationColor", [1, 1, 1])
+    m.thicknessFactor = e.get("thicknessFactor", 0.0)
+    m.attenuationDistance = min(e.get("attenuationDistance", float(np.finfo(np.float32).max)),
+                                float(np.finfo(np.float32).max))
+    handle(m, "thicknessTexture", e.get("thicknessTexture"))
+    e = ex.get("KHR_materials_clearcoat", {})
+    m.clearcoatFactor = e.get("clearcoatFactor", 0.0)
+    m.clearcoatRoughness = e.get("clearcoatRoughnessFactor", 0.0)
+    handle(m, "clearcoatRoughnessTexture", e.get("clearcoatRoughnessTexture"))
+    handle(m, "clearcoatTexture", e.get("clearcoatTexture"))
+    handle(m, "clearcoatNormalTexture", e.get("clearcoatNormalTexture"))
+    e = ex.get("KHR_materials_specular", {})
+    m.specularFactor = e.get("specularFactor", 1.0)
+    m.specularColorFactor[:] = e.get("specularColorFactor", [1, 1, 1])
+    handle(m, "specularTexture", e.get("specularTexture"))
+    handle(m, "specularColorTexture", e.get("specularColorTexture"))
+    strength = ex.get("KHR_materials_emissive_strength", {}).get("emissiveStrength", 1.0)
+    for k in range(3):
+        m.emissiveFactor[k] = m.emissiveFactor[k] * strength
+    m.unlit = 1 if "KHR_materials_unlit" in ex else 0
+    e = ex.get("KHR_materials_iridescence", {})
+    m.iridescenceFactor = e.get("iridescenceFactor", 0.0)
+    m.iridescenceIor = e.get("iridescenceIor", 1.3)
+    m.iridescenceThicknessMinimum = e.get("iridescenceThicknessMinimum", 100.0)
+    m.iridescenceThicknessMaximum = e.get("iridescenceThicknessMaximum", 400.0)
+    handle(m, "iridescenceTexture", e.get("iridescenceTexture"))
+    handle(m, "iridescenceThicknessTexture", e.get("iridescenceThicknessTexture"))
+    e = ex.get("KHR_materials_anisotropy", {})
+    rot = e.get("anisotropyRotation", 0.0)
+    m.anisotropyRotation[:] = [math.sin(rot), math.cos(rot)]
+    m.anisotropyStrength = e.get("anisotropyStrength", 0.0)
+    handle(m, "anisotropyTexture", e.get("anisotropyTexture"))
+    e = ex.get("KHR_materials_sheen", {})
+    m.sheenColorFactor[:] = e.get("sheenColorFactor", [0, 0, 0])
+    m.sheenRoughnessFactor = e.get("sheenRoughnessFactor", 0.0)
+    handle(m, "sheenColorTexture", e.get("sheenColorTexture"))
+    handle(m, "sheenRoughnessTexture", e.get("sheenRoughnessTexture"))
+    m.dispersion = ex.get("KHR_materials_dispersion", {}).get("dispersion", 0.0)
+    if "KHR_materials_pbrSpecularGlossiness" in ex:
+        e = ex["KHR_materials_pbrSpecularGlossiness"]
+        m.pbrModel = 1
+        m.pbrDiffuseFactor[:] = e.get("diffuseFactor", [1, 1, 1, 1])
+        m.pbrSpecularFactor[:] = e.get("specularFactor", [1, 1, 1])
+        m.pbrGlossinessFactor = e.get("glossinessFactor", 1.0)
+        handle(m, "pbrDiffuseTexture", e.get("diffuseTexture"))
+        handle(m, "pbrSpecularGlossinessTexture", e.get("specularGlossinessTexture"))
+    e = ex.get("KHR_materials_diffuse_transmission", {})
+    m.diffuseTransmissionFactor = e.get("diffuseTransmissionFactor", 0.0)
+    m.diffuseTransmissionColor[:] = e.get("diffuseTransmissionColorFactor", [1, 1, 1])
+    handle(m, "diffuseTransmissionTexture", e.get("diffuseTransmissionTexture"))
+    handle(m, "diffuseTransmissionColorTexture", e.get("diffuseTransmissionColorTexture"))
+    e = ex.get("KHR_materials_retroreflection", {})
+    m.retroreflectionFactor = e.get("retroreflectionFactor", 0.0)
+    handle(m, "retroreflectionTexture", e.get("retroreflectionTexture"))
+    e = ex.get("KHR_materials_volume_scatter", {})
+    m.multiscatterColorFactor[:] = e.get("multiscatterColorFactor", e.get("multiscatterColor", [0, 0, 0]))
+    m.scatterAnisotropy = e.get("scatterAnisotropy", 0.0)
+    return m
+
+
+class MaterialCache:
+    """Host mirror of nvvkgltf::MaterialCache (src/gltf_material_cache.{hpp,cpp}): the GltfShadeMaterial[] and
+    GltfTextureInfo[] arrays the path tracer consumes, rebuilt from the glTF materials, with in-place updates that report
+    whether the set of bound textures (the array topology) changed.  Pinned by the reference's own expectations
+    (tests/test_material_cache.cpp:24-176) in tests/test_material_cache.py."""
+
+    class UpdateResult:
+        def __init__(self, topology_changed=False, span=None):
+            self.topologyChanged = topology_changed
+            self.span = span  # (first, count) of the materials rewritten, None = nothing
+
+        def hasAny(self):
+            return self.span is not None
+
+    def __init__(self):
+        self.clear()
+
+    def clear(self):
+        self._materials = []
+        self._texture_infos = []
+        self._sources = []
+
+    def _add_ti(self, index, texcoord, uv_transform):
+        ti = abi.TextureInfo()
+        ti.index = index
+        ti.texCoord = min(texcoord, 1)  # the shaders know TEXCOORD_0 and TEXCOORD_1 only
+        ti.uvTransform[:] = list(uv_transform)
+        self._texture_infos.append(ti)
+        return len(self._texture_infos) - 1
+
+    def buildFromMaterials(self, materials):
+        self.clear()
+        sentinel = abi.TextureInfo()
+        sentinel.index = -1
+        sentinel.uvTransform[:] = [1, 0, 0, 1, 0, 0]
+        self._texture_infos = [sentinel]  # slot 0: "no texture"
+        for sm in materials:
+            self._materials.append(populate_shade_material(sm, self._add_ti))
+            self._sources.append(sm)
+
+    @staticmethod
+    def _bound_slots(m):
+        return tuple(getattr(m, n) > 0 for n in abi.MATERIAL_TEXTURE_SLOTS)
+
+    def updateMaterial(self, index, sm):
+        if index < 0 or index >= len(self._materials):
+            return MaterialCache.UpdateResult(False, None)
+        before = self._bound_slots(self._materials[index])
+        scratch = []
+
+        def probe(i, tc, xf):
+            scratch.append((i, tc, xf))
+            return len(scratch)
+        after = self._bound_slots(populate_shade_material(sm, probe))
+        if after != before:
+            # a texture was added or removed: every slot index behind it moves -> rebuild (the reference re-creates the arrays)
+            srcs = list(self._sources)
+            srcs[index] = sm
+            self.buildFromMaterials(srcs)
+            return MaterialCache.UpdateResult(True, (0, len(self._materials)))
+        # same topology: rewrite the material in place; its texture infos keep their slots and are refreshed
+        old = self._materials[index]
+        rec = []
+
+        def record(i, tc, xf):
+            rec.append((i, tc, xf))
+            return len(rec)
+        new = populate_shade_material(sm, record)  # texture slots hold the visit number 1..n
+        for n in abi.MATERIAL_TEXTURE_SLOTS:
+            k = getattr(new, n)
+            if k > 0:
+                slot = getattr(old, n)
+                i, tc, xf = rec[k - 1]
+                ti = self._texture_infos[slot]
+                ti.index, ti.texCoord = i, min(tc, 1)
+                ti.uvTransform[:] = list(xf)
+                setattr(new, n, slot)
+        self._materials[index] = new
+        self._sources[index] = sm
+        return MaterialCache.UpdateResult(False, (index, 1))
+
+    def getShadeMaterials(self):
+        return self._materials
+
+    def getTextureInfos(self):
+        return self._texture_infos
+
+
 def load_gltf(path):
     g = _Gltf(path)
     j = g.json
@@ -423,93 +602,9 @@ def load_gltf(path):
                         magFilter=smp.get("magFilter", -1), minFilter=smp.get("minFilter", -1))
 
     # ---- materials (MaterialCache::buildFromMaterials) ----
-    def handle(mat, slot, tinfo):
-        if tinfo is not None and tinfo.get("index", -1) != -1:
-            setattr(mat, slot, scn.add_texture_info(tinfo["index"], tinfo.get("texCoord", 0), _tex_transform(tinfo)))
-
     src_mats = j.get("materials", []) or [{}]
     for sm in src_mats:
-        m = default_material()
-        am = sm.get("alphaMode", "OPAQUE")
-        m.alphaMode = 0 if am == "OPAQUE" else (1 if am == "MASK" else 2)
-        m.alphaCutoff = sm.get("alphaCutoff", 0.5)
-        m.doubleSided = 1 if sm.get("doubleSided", False) else 0
-        pbr = sm.get("pbrMetallicRoughness", {})
-        m.pbrBaseColorFactor[:] = pbr.get("baseColorFactor", [1, 1, 1, 1])
-        m.pbrMetallicFactor = pbr.get("metallicFactor", 1.0)
-        m.pbrRoughnessFactor = pbr.get("roughnessFactor", 1.0)
-        m.normalTextureScale = (sm.get("normalTexture") or {}).get("scale", 1.0)
-        m.occlusionStrength = (sm.get("occlusionTexture") or {}).get("strength", 1.0)
-        m.emissiveFactor[:] = sm.get("emissiveFactor", [0, 0, 0])
-        handle(m, "emissiveTexture", sm.get("emissiveTexture"))
-        handle(m, "normalTexture", sm.get("normalTexture"))
-        handle(m, "pbrBaseColorTexture", pbr.get("baseColorTexture"))
-        handle(m, "pbrMetallicRoughnessTexture", pbr.get("metallicRoughnessTexture"))
-        handle(m, "occlusionTexture", sm.get("occlusionTexture"))
-        ex = sm.get("extensions", {})
-        e = ex.get("KHR_materials_transmission", {})
-        m.transmissionFactor = e.get("transmissionFactor", 0.0)
-        handle(m, "transmissionTexture", e.get("transmissionTexture"))
-        m.ior = ex.get("KHR_materials_ior", {}).get("ior", 1.5)
-        e = ex.get("KHR_materials_volume", {})
-        m.attenuationColor[:] = e.get("attenuationColor", [1, 1, 1])
-        m.thicknessFactor = e.get("thicknessFactor", 0.0)
-        m.attenuationDistance = min(e.get("attenuationDistance", float(np.finfo(np.float32).max)),
-                                    float(np.finfo(np.float32).max))
-        handle(m, "thicknessTexture", e.get("thicknessTexture"))
-        e = ex.get("KHR_materials_clearcoat", {})
-        m.clearcoatFactor = e.get("clearcoatFactor", 0.0)
-        m.clearcoatRoughness = e.get("clearcoatRoughnessFactor", 0.0)
-        handle(m, "clearcoatRoughnessTexture", e.get("clearcoatRoughnessTexture"))
-        handle(m, "clearcoatTexture", e.get("clearcoatTexture"))
-        handle(m, "clearcoatNormalTexture", e.get("clearcoatNormalTexture"))
-        e = ex.get("KHR_materials_specular", {})
-        m.specularFactor = e.get("specularFactor", 1.0)
-        m.specularColorFactor[:] = e.get("specularColorFactor", [1, 1, 1])
-        handle(m, "specularTexture", e.get("specularTexture"))
-        handle(m, "specularColorTexture", e.get("specularColorTexture"))
-        strength = ex.get("KHR_materials_emissive_strength", {}).get("emissiveStrength", 1.0)
-        for k in range(3):
-            m.emissiveFactor[k] = m.emissiveFactor[k] * strength
-        m.unlit = 1 if "KHR_materials_unlit" in ex else 0
-        e = ex.get("KHR_materials_iridescence", {})
-        m.iridescenceFactor = e.get("iridescenceFactor", 0.0)
-        m.iridescenceIor = e.get("iridescenceIor", 1.3)
-        m.iridescenceThicknessMinimum = e.get("iridescenceThicknessMinimum", 100.0)
-        m.iridescenceThicknessMaximum = e.get("iridescenceThicknessMaximum", 400.0)
-        handle(m, "iridescenceTexture", e.get("iridescenceTexture"))
-        handle(m, "iridescenceThicknessTexture", e.get("iridescenceThicknessTexture"))
-        e = ex.get("KHR_materials_anisotropy", {})
-        rot = e.get("anisotropyRotation", 0.0)
-        m.anisotropyRotation[:] = [math.sin(rot), math.cos(rot)]
-        m.anisotropyStrength = e.get("anisotropyStrength", 0.0)
-        handle(m, "anisotropyTexture", e.get("anisotropyTexture"))
-        e = ex.get("KHR_materials_sheen", {})
-        m.sheenColorFactor[:] = e.get("sheenColorFactor", [0, 0, 0])
-        m.sheenRoughnessFactor = e.get("sheenRoughnessFactor", 0.0)
-        handle(m, "sheenColorTexture", e.get("sheenColorTexture"))
-        handle(m, "sheenRoughnessTexture", e.get("sheenRoughnessTexture"))
-        m.dispersion = ex.get("KHR_materials_dispersion", {}).get("dispersion", 0.0)
-        if "KHR_materials_pbrSpecularGlossiness" in ex:
-            e = ex["KHR_materials_pbrSpecularGlossiness"]
-            m.pbrModel = 1
-            m.pbrDiffuseFactor[:] = e.get("diffuseFactor", [1, 1, 1, 1])
-            m.pbrSpecularFactor[:] = e.get("specularFactor", [1, 1, 1])
-            m.pbrGlossinessFactor = e.get("glossinessFactor", 1.0)
-            handle(m, "pbrDiffuseTexture", e.get("diffuseTexture"))
-            handle(m, "pbrSpecularGlossinessTexture", e.get("specularGlossinessTexture"))
-        e = ex.get("KHR_materials_diffuse_transmission", {})
-        m.diffuseTransmissionFactor = e.get("diffuseTransmissionFactor", 0.0)
-        m.diffuseTransmissionColor[:] = e.get("diffuseTransmissionColorFactor", [1, 1, 1])
-        handle(m, "diffuseTransmissionTexture", e.get("diffuseTransmissionTexture"))
-        handle(m, "diffuseTransmissionColorTexture", e.get("diffuseTransmissionColorTexture"))
-        e = ex.get("KHR_materials_retroreflection", {})
-        m.retroreflectionFactor = e.get("retroreflectionFactor", 0.0)
-        handle(m, "retroreflectionTexture", e.get("retroreflectionTexture"))
-        e = ex.get("KHR_materials_volume_scatter", {})
-        m.multiscatterColorFactor[:] = e.get("multiscatterColorFactor", e.get("multiscatterColor", [0, 0, 0]))
-        m.scatterAnisotropy = e.get("scatterAnisotropy", 0.0)
-        scn.materials.append(m)
+        scn.materials.append(populate_shade_material(sm, scn.add_texture_info))
 
     # ---- unique primitives (Scene::buildPrimitiveKeyMap) ----
     prim_map = {}
