@@ -321,6 +321,14 @@ int b200pt_synchronize(b200pt_t* h);
 int b200pt_get_accum_device(b200pt_t* h, float** dev_rgba32f, size_t* num_floats);
 int b200pt_read_accum(b200pt_t* h, float* host_rgba32f, size_t num_floats);
 
+/* gBuffers[eImgSelection] + the depth image, written on the first frame of an accumulation only (the frame whose push
+ * constants carry B200PT_PT_FIRST_FRAME; reference shaders/gltf_pathtrace.slang:604-616): per pixel of the tile the object
+ * id of the selection ray (pixel centre, IRaytracer::TraceLow: all geometry opaque, no culling; render node index + 1,
+ * 0 = miss; traceSelectionRay, shaders/pathtrace_functions.h.slang:813-820) and the NDC depth (Vulkan [0,1], 1 = far / miss)
+ * of the last sample's first hit.  Either pointer may be NULL. */
+int b200pt_read_selection(b200pt_t* h, uint32_t* host_object_ids, float* host_ndc_depth, size_t num_pixels);
+int b200pt_get_selection_device(b200pt_t* h, uint32_t** dev_object_ids, float** dev_ndc_depth);
+
 /* Pipelined read-back: enqueue the copy of the image as of the frames submitted so far into (pinned) host memory
  * and return at once; b200pt_wait_read(slot) blocks until that copy has landed.  slot is 0..7; issuing a read on a
  * slot first waits for the slot's previous read.  With frames in flight a caller reads frame f while frame f+1

@@ -1819,7 +1819,19 @@ static float2 sampleGaussian(float2 u)
 }
 
 // processPixel (gltf_pathtrace.slang:546-630); accum is the tile's RGBA32F image
-static void processPixel(const Ctx& c, int x, int y, float* px)
+// TraceLow (raytracer_interface.h.slang:124-137): every triangle opaque, no culling -> nearest hit of both trees
+static int traceLowObjectId(Oracle& o, const Ray& ray)
+{
+  Hit  ho, ha;
+  const bool a = nextHit(o, o.treeOpaque, ray, false, 0.f, 0u, false, ho);
+  const bool b = !o.treeAlpha.bvh.empty() && nextHit(o, o.treeAlpha, ray, false, 0.f, 0u, false, ha);
+  if(!a && !b)
+    return 0;
+  const Hit& h = (a && (!b || ho.t < ha.t || (ho.t == ha.t && ho.tri < ha.tri))) ? ho : ha;
+  return (int)o.tris[h.tri].rnode + 1;
+}
+
+static void processPixel(const Ctx& c, int x, int y, float* px, uint32_t* objectId = nullptr, float* ndcDepth = nullptr)
 {
   const float2 imageSize = f2(c.fi->imageSize[0], c.fi->imageSize[1]);
   const float2 samplePos = f2((float)x, (float)y);
@@ -1844,6 +1856,25 @@ static void processPixel(const Ctx& c, int x, int y, float* px)
     pixelColor += sr.radiance;
   }
   pixelColor = pixelColor / (float)c.pc->numSamples;
+  if(firstFrame && (objectId || ndcDepth))
+  {
+    // gltf_pathtrace.slang:600-616: NDC depth of the LAST sample's first hit, object id of the selection ray
+    const bool hasSolidHit = sr.radiance.w > 0.0f;
+    float      d = 1.0f;
+    if(hasSolidHit)
+    {
+      const float4 clip = mul_vM(f4(sr.hitPosition.x, sr.hitPosition.y, sr.hitPosition.z, 1.0f), *(const mat4*)c.fi->viewProjMatrix);
+      d = clip.z / clip.w;
+    }
+    if(ndcDepth)
+      *ndcDepth = d;
+    if(objectId)
+    {
+      const bool ortho = (c.fi->flags & B200PT_SCENE_IS_ORTHOGRAPHIC) != 0;
+      const Ray  ray = getRay(samplePos, f2(0.5f, 0.5f), imageSize, *(const mat4*)c.fi->projInv, *(const mat4*)c.fi->viewInv, ortho);
+      *objectId = (uint32_t)traceLowObjectId(*c.o, ray);
+    }
+  }
   if(firstFrame)
   {
     px[0] = pixelColor.x;
@@ -1992,7 +2023,16 @@ int oracle_get_environment(void* h, float* rgba, uint32_t* alias, float* q)
 }
 
 // renders rows [y0, y0+rows) of the frame into accum (rows x width x 4 floats, tile-local)
+int oracle_render_frame_aux(void* h, const b200pt_frame_info* fi, const b200pt_push_constant* pc, float* accum, uint32_t* objectId, float* ndcDepth, int y0, int rows,
+                            int nthreads);
 int oracle_render_frame(void* h, const b200pt_frame_info* fi, const b200pt_push_constant* pc, float* accum, int y0, int rows, int nthreads)
+{
+  return oracle_render_frame_aux(h, fi, pc, accum, nullptr, nullptr, y0, rows, nthreads);
+}
+
+// objectId / ndcDepth (rows x width, tile-local, may be null): the frame-0 outputs of processPixel
+int oracle_render_frame_aux(void* h, const b200pt_frame_info* fi, const b200pt_push_constant* pc, float* accum, uint32_t* objectId, float* ndcDepth, int y0, int rows,
+                            int nthreads)
 {
   Oracle& o = *(Oracle*)h;
   if(!(fi->flags & B200PT_SCENE_USE_HDR_ENVIRONMENT) || o.envW == 0)
@@ -2011,7 +2051,7 @@ int oracle_render_frame(void* h, const b200pt_frame_info* fi, const b200pt_push_
       if(r >= rows)
         break;
       for(int x = 0; x < W; x++)
-        processPixel(c, x, y0 + r, accum + ((size_t)r * W + x) * 4);
+        processPixel(c, x, y0 + r, accum + ((size_t)r * W + x) * 4, objectId ? objectId + (size_t)r * W + x : nullptr, ndcDepth ? ndcDepth + (size_t)r * W + x : nullptr);
     }
     o.stats.merge();
   };

@@ -129,3 +129,33 @@ def test_malformed_scene_is_rejected(box_scene, std_env):
         pt = PathTracer(0)
         with pytest.raises(B200PTError):
             pt.onAttach(Resources(scene=scn, hdr_rgb=std_env, camera=scn.camera, size=(16, 16)))
+
+
+def test_selection_ids_and_ndc_depth_of_frame_zero(std_env, oracle_mod):
+    """traceSelectionRay / TraceLow (pixel-centre ray, every triangle opaque, no culling -> render node + 1) and the NDC depth
+    of the first hit, written on the first frame of an accumulation (gltf_pathtrace.slang:604-616,
+    raytracer_interface.h.slang:124-137): ids exact, depth to rounding, on a scene with MASK foliage in front of walls
+    (the selection ray stops at a leaf quad the alpha test lets the camera ray pass) and one with several samples per pixel."""
+    from vk_gltf_renderer_b200 import camera as cm, synth
+    from vk_gltf_renderer_b200.renderer import PathTracer, Resources
+    for scn, spp in ((synth.synth_sponza(tex_size=64, detail=0.05), 1), (synth.synth_material_zoo(), 3)):
+        w, h = 160, 96
+        o = _oracle(oracle_mod, scn, std_env)
+        fi = cm.make_frame_info(scn.camera, w, h)
+        pc = cm.make_push_constant(scn.camera, h, frame_count=0, total_samples=0, num_samples=spp, max_depth=4)
+        acc = np.zeros((h, w, 4), np.float32)
+        ids_ref, depth_ref = np.zeros((h, w), np.uint32), np.zeros((h, w), np.float32)
+        o.render_frame(fi, pc, acc, object_id=ids_ref, ndc_depth=depth_ref)
+        res = Resources(scene=scn, hdr_rgb=std_env, camera=scn.camera, size=(w, h))
+        pt = PathTracer(0)
+        pt.ptMaxDepth, pt.ptSamples = 4, spp
+        pt.onAttach(res)
+        for f in range(3):  # later frames must leave the frame-0 images alone
+            res.frameCount = f
+            pt.onRender(None, res)
+        ids, depth = pt.read_selection()
+        assert np.array_equal(ids, ids_ref)
+        assert np.allclose(depth, depth_ref, rtol=0, atol=2e-6)
+        assert 0 < (ids == 0).mean() < 0.9 and len(np.unique(ids)) > 3
+        assert ((depth > 0) & (depth <= 1)).all() and (depth[ids_ref == 0] == 1.0).mean() > 0.5
+        pt.onDetach(res)

@@ -104,6 +104,8 @@ __device__ void startSample(const PathState& P, const FrameParams& F, uint32_t i
   P.rad[i] = f4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
   P.misc[i] = f4(0.0f, 0.0f, __uint_as_float(PF_SOLID), __uint_as_float(seed));
   P.medium[i] = make_uint4(0u, 0u, 0u, sampleIdx << 16);
+  if(F.pc.flags & B200PT_PT_FIRST_FRAME)
+    P.firstHit[i] = f4(1e34f, 1e34f, 1e34f, 1.0f);  // PathTracerState::firstHitPos sentinel, pt.solid = true
 }
 
 // end of one samplePixel(): firefly clamp, add to the pixel sum, start the pixel's next sample if any
@@ -569,6 +571,8 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
       if(depth == 0)
       {
         flags &= ~PF_SOLID;  // tryPrimaryMissBackplate: pt.solid = false
+        if(F.pc.flags & B200PT_PT_FIRST_FRAME)
+          P.firstHit[i] = f4(dir, 0.0f);  // pt.firstHitPos = ray.Direction (pathtrace_functions.h.slang:950)
         if(F.fi.flags & B200PT_SCENE_USE_SOLID_BACKGROUND)
         {
           finalizeSample(P, F, i, f3(F.fi.backgroundColor[0], F.fi.backgroundColor[1], F.fi.backgroundColor[2]), false, seed, sampleIdx, qNext, cntNext, stats);
@@ -620,6 +624,10 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
     misc.x = fmaxf(pbrMat.roughness.x, misc.x);
     misc.y = fmaxf(pbrMat.roughness.y, misc.y);
     pbrMat.roughness = f2(misc.x, misc.y);
+
+    // first-hit capture for the NDC depth output of frame 0 (gltf_pathtrace.slang:228-232)
+    if(depth == 0 && (F.pc.flags & B200PT_PT_FIRST_FRAME))
+      P.firstHit[i] = f4(hit.pos, 1.0f);
 
     radiance += pbrMat.emissive * throughput;
 
@@ -1010,15 +1018,30 @@ __global__ void __launch_bounds__(256) k_resolve(PathState P, const __grid_const
   }
 }
 
-// processPixel tail: mean over the frame's samples + running mean over frames (gltf_pathtrace.slang:596,619-630)
-__global__ void __launch_bounds__(256) k_accumulate(PathState P, const __grid_constant__ FrameParams F, float4* __restrict__ accum)
+// processPixel tail: mean over the frame's samples + running mean over frames (gltf_pathtrace.slang:596,619-630); on the
+// first frame also the NDC depth of the last sample's first hit (:600-616; Vulkan [0,1] range, 1 = far / miss)
+__global__ void __launch_bounds__(256) k_accumulate(PathState P, const __grid_constant__ FrameParams F, float4* __restrict__ accum, float* __restrict__ ndcDepth)
 {
   const uint32_t stride = gridDim.x * blockDim.x;
   for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < F.numPaths; i += stride)
   {
     const float4 c = P.pixSum[i] / (float)F.pc.numSamples;
     if(F.pc.flags & B200PT_PT_FIRST_FRAME)
+    {
       accum[i] = c;
+      if(ndcDepth)
+      {
+        const float4 fh = P.firstHit[i];
+        float        d = 1.0f;
+        if(fh.w > 0.0f)
+        {
+          const Mat4&  vp = *reinterpret_cast<const Mat4*>(F.fi.viewProjMatrix);
+          const float4 clip = mul_vM(f4(fh.x, fh.y, fh.z, 1.0f), vp);
+          d = clip.z / clip.w;
+        }
+        ndcDepth[i] = d;
+      }
+    }
     else
     {
       const float  total = (float)F.pc.totalSamples, n = (float)F.pc.numSamples;
@@ -1026,6 +1049,46 @@ __global__ void __launch_bounds__(256) k_accumulate(PathState P, const __grid_co
       const float4 old = accum[i];
       accum[i] = f4((old.x * total + c.x * n) / after, (old.y * total + c.y * n) / after, (old.z * total + c.z * n) / after, (old.w * total + c.w * n) / after);
     }
+  }
+}
+
+// traceSelectionRay (pathtrace_functions.h.slang:813-820) for every pixel of the first frame: the pixel-centre ray
+// (no jitter, no depth of field), IRaytracer::TraceLow semantics (raytracer_interface.h.slang:124-137: every triangle
+// opaque, no culling), object id = render node + 1, 0 on a miss.  One walk per thread; runs once per accumulation.
+__global__ void __launch_bounds__(128) k_select(DevScene S, const __grid_constant__ FrameParams F, uint32_t* __restrict__ objectId, DevStats* stats)
+{
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const Mat4&    projI = *reinterpret_cast<const Mat4*>(F.fi.projInv);
+  const Mat4&    viewI = *reinterpret_cast<const Mat4*>(F.fi.viewInv);
+  const bool     ortho = (F.fi.flags & B200PT_SCENE_IS_ORTHOGRAPHIC) != 0;
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < F.numPaths; i += stride)
+  {
+    const uint32_t x = i % (uint32_t)F.width;
+    const uint32_t y = pixelRow(F, i);
+    const float2   clip = f2(((float)x + 0.5f) / F.fi.imageSize[0] * 2.0f - 1.0f, ((float)y + 0.5f) / F.fi.imageSize[1] * 2.0f - 1.0f);
+    float4         vc = mul_vM(f4(clip.x, clip.y, -1.0f, 1.0f), projI);
+    vc = vc / vc.w;
+    float3 org, dir;
+    if(ortho)
+    {
+      org = xyz(mul_vM(vc, viewI));
+      dir = normalize(xyz(mul_vM(f4(0, 0, -1, 0), viewI)));
+    }
+    else
+    {
+      org = f3(viewI.m[12], viewI.m[13], viewI.m[14]);
+      dir = normalize(xyz(mul_vM(vc, viewI)) - org);
+    }
+    TravState T;
+    uint2     stack[TravState::kStackSize];
+    Cand      cand[1];
+    T.init(S.bvh, org, dir, 0.0f, kInfinite, false, false, false, 0.f, 0u);
+    while(!T.step<1, 1, true>(stack, 2, cand, 1))
+    {
+    }
+    if(T.overflow)
+      atomicOr(&stats->errorFlags, 1ull);
+    objectId[i] = (T.best.slot != 0xFFFFFFFFu) ? (S.triMeta[T.best.slot].x & 0x0fffffffu) + 1u : 0u;
   }
 }
 
@@ -1207,6 +1270,8 @@ struct b200pt
   uint32_t           numPaths = 0;
   float4*            dAccumOwned = nullptr;
   float4*            dAccum = nullptr;
+  uint32_t*          dSelect = nullptr;  // frame-0 outputs (gltf_pathtrace.slang:610-616): object id per pixel ...
+  float*             dNdcDepth = nullptr;  // ... and NDC depth of the first hit
   // Frames in flight (like the reference app's swapchain ring): every lane owns a stream, a path pool, queues and
   // counters; frame f runs its bounces on lane f % numLanes and only k_accumulate runs on the main stream, in
   // frame order.  The latency-bound tail of frame f (a few deep paths) overlaps the wide first bounces of f+1.
@@ -1291,7 +1356,7 @@ int upload(b200pt* h, std::vector<void*>& owner, const T* src, size_t count, T**
 int allocPathState(b200pt* h, std::vector<void*>& owner, size_t n, PathState& P)
 {
   P = PathState{};
-  float4** arrays[] = {&P.rayO, &P.rayD, &P.hit, &P.thr, &P.rad, &P.misc, reinterpret_cast<float4**>(&P.medium), &P.pixSum, &P.shO, &P.shD, &P.shC};
+  float4** arrays[] = {&P.rayO, &P.rayD, &P.hit, &P.thr, &P.rad, &P.misc, reinterpret_cast<float4**>(&P.medium), &P.pixSum, &P.shO, &P.shD, &P.shC, &P.firstHit};
   for(float4** a : arrays)
   {
     void* d = nullptr;
@@ -1362,6 +1427,8 @@ void freePool(b200pt* h)
   h->poolAllocs.clear();
   h->dAccumOwned = nullptr;
   h->dAccum = nullptr;
+  h->dSelect = nullptr;
+  h->dNdcDepth = nullptr;
   h->numPaths = 0;
   for(int l = 0; l < b200pt::kMaxLanes; l++)
   {
@@ -2146,7 +2213,24 @@ int b200pt_resize(b200pt_t* h, int width, int height, int tile_y0, int tile_rows
     return fail(B200PT_E_NOMEM);
   }
   h->poolAllocs.push_back(h->dAccumOwned);
-  if(cudaMemsetAsync(h->dAccumOwned, 0, n * 16, h->stream) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess)
+  if(cudaMalloc((void**)&h->dSelect, n * 4) != cudaSuccess)
+  {
+    cudaGetLastError();
+    h->dSelect = nullptr;
+    h->err = "selection image: out of device memory";
+    return fail(B200PT_E_NOMEM);
+  }
+  h->poolAllocs.push_back(h->dSelect);
+  if(cudaMalloc((void**)&h->dNdcDepth, n * 4) != cudaSuccess)
+  {
+    cudaGetLastError();
+    h->dNdcDepth = nullptr;
+    h->err = "depth image: out of device memory";
+    return fail(B200PT_E_NOMEM);
+  }
+  h->poolAllocs.push_back(h->dNdcDepth);
+  if(cudaMemsetAsync(h->dSelect, 0, n * 4, h->stream) != cudaSuccess || cudaMemsetAsync(h->dNdcDepth, 0, n * 4, h->stream) != cudaSuccess
+     || cudaMemsetAsync(h->dAccumOwned, 0, n * 16, h->stream) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess)
   {
     h->err = "b200pt_resize: clearing the accumulation image failed";
     return fail(B200PT_E_CUDA);
@@ -2216,6 +2300,30 @@ int b200pt_read_accum(b200pt_t* h, float* host, size_t num_floats)
   CK(cudaSetDevice(h->device));
   CK(cudaMemcpyAsync(host, h->dAccum, (size_t)h->numPaths * 16, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  return B200PT_OK;
+}
+
+int b200pt_read_selection(b200pt_t* h, uint32_t* host_object_ids, float* host_ndc_depth, size_t num_pixels)
+{
+  if(!h || h->numPaths == 0 || num_pixels < (size_t)h->numPaths || (!host_object_ids && !host_ndc_depth))
+    return B200PT_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  if(host_object_ids)
+    CK(cudaMemcpyAsync(host_object_ids, h->dSelect, (size_t)h->numPaths * 4, cudaMemcpyDeviceToHost, h->stream));
+  if(host_ndc_depth)
+    CK(cudaMemcpyAsync(host_ndc_depth, h->dNdcDepth, (size_t)h->numPaths * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return B200PT_OK;
+}
+
+int b200pt_get_selection_device(b200pt_t* h, uint32_t** dev_object_ids, float** dev_ndc_depth)
+{
+  if(!h || h->numPaths == 0)
+    return B200PT_E_INVALID;
+  if(dev_object_ids)
+    *dev_object_ids = h->dSelect;
+  if(dev_ndc_depth)
+    *dev_ndc_depth = h->dNdcDepth;
   return B200PT_OK;
 }
 
@@ -2453,7 +2561,9 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
   CK(cudaEventRecord(L.done, st));
   CK(cudaStreamWaitEvent(h->stream, L.done, 0));
   st = h->stream;
-  timed(tOther, [&] { k_accumulate<<<gridWide, 256, 0, st>>>(L.P, F, h->dAccum); });
+  if(pc->flags & B200PT_PT_FIRST_FRAME)
+    timed(tOther, [&] { k_select<<<gridFor(h, 8), 128, 0, st>>>(h->S, F, h->dSelect, h->dStats); });
+  timed(tOther, [&] { k_accumulate<<<gridWide, 256, 0, st>>>(L.P, F, h->dAccum, h->dNdcDepth); });
   CK(cudaEventRecord(L.freed, st));
   L.busy = true;
   h->lastLane = laneIdx;

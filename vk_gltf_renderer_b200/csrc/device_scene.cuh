@@ -101,6 +101,7 @@ struct PathState
   float4*   shO;     // shadow ray origin.xyz | tmax
   float4*   shD;     // shadow ray direction.xyz | unused
   float4*   shC;     // NEE contribution.xyz | unused
+  float4*   firstHit;  // first frame only: world position of the sample's first surface hit | 1 (primary miss: direction | 0)
   // any-hit candidates of the ray last traced for the path (closest-hit ray, then the shadow ray): up to B200PT_KCAND
   // nearest non-opaque hits as t | u | v | triangle slot, written by the traversal kernels and consumed by the
   // dense alpha / resolve kernels

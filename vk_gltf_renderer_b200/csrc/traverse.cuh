@@ -193,7 +193,8 @@ struct TravState
   // Returns true when the traversal is complete.  `stack` is per-thread scratch of kStackSize entries (entry i at
   // stack[i * SS]: local memory with SS = 1, or a shared-memory column), `cand` the candidate list (entry i at
   // cand[i * cs]: the kernels keep it in shared memory, one column per thread).
-  template <int SS = 1, int KC = kCand>
+  // FORCE_OPAQUE: every triangle counts as opaque (IRaytracer::TraceLow, RAY_FLAG_FORCE_OPAQUE: the selection ray)
+  template <int SS = 1, int KC = kCand, bool FORCE_OPAQUE = false>
   PT_D bool step(uint2* __restrict__ stack, int postponeShift, Cand* __restrict__ cand, int cs)
   {
     // single exit: an early return inside the divergent regions would move their reconvergence point out of the
@@ -346,7 +347,7 @@ struct TravState
         hit &= !haveLo | (t > loT) | ((t == loT) & (gid > loId));
         if(hit)
         {
-          if(flags & TRI_OPAQUE)
+          if(FORCE_OPAQUE || (flags & TRI_OPAQUE))
           {
             if((t < best.t) | ((t == best.t) & (gid < best.gid)))
             {

@@ -158,6 +158,16 @@ class PathTracer:
         self._ck(self._L.b200pt_read_accum(self._h, out.ctypes.data_as(C.c_void_p), out.size), "b200pt_read_accum")
         return out
 
+    def read_selection(self):
+        """gBuffers[eImgSelection] (object id per pixel, render node + 1, 0 = miss) and the NDC depth image, as the first
+        frame of the current accumulation wrote them (gltf_pathtrace.slang:604-616)."""
+        w, _ = self._size
+        rows = self._tile[1]
+        ids = np.empty((rows, w), np.uint32)
+        depth = np.empty((rows, w), np.float32)
+        self._ck(self._L.b200pt_read_selection(self._h, ids.ctypes.data_as(C.c_void_p), depth.ctypes.data_as(C.c_void_p), ids.size), "b200pt_read_selection")
+        return ids, depth
+
     def read_accum_async(self, host_ptr, num_floats, slot):
         """enqueue a copy of the image into (pinned) host memory; wait_read(slot) completes it."""
         self._ck(self._L.b200pt_read_accum_async(self._h, host_ptr, num_floats, slot), "b200pt_read_accum_async")
