@@ -261,7 +261,7 @@ def test_cpp_host_headless_matches_python_host(box_scene, std_env, tmp_path):
     assert os.path.exists(exe), "run __graft_entry__.build() first"
     blob, raw = str(tmp_path / "box.b2sc"), str(tmp_path / "box.raw")
     box_scene.save_blob(blob, std_env)
-    out = subprocess.run([exe, "--scene", blob, "--size", "96", "64", "--frames", "4", "--warmupFrames", "1", "--ptMaxDepth", "5", "--ptSamples", "2",
+    out = subprocess.run([exe, "--scene", blob, "--size", "96", "64", "--frames", "4", "--ptMaxDepth", "5", "--ptSamples", "2",
                           "--outRaw", raw, "--out", str(tmp_path / "box.pfm")], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     summary = [l for l in out.stdout.splitlines() if l.startswith("HEADLESS_SUMMARY ")]
@@ -274,3 +274,45 @@ def test_cpp_host_headless_matches_python_host(box_scene, std_env, tmp_path):
     assert np.array_equal(img[..., 3], ref[..., 3])
     assert rel_rmse(img, ref) <= 1e-4
     assert os.path.getsize(tmp_path / "box.pfm") > 96 * 64 * 12
+
+
+HARNESS_KEYS = ("frames", "maxFrames", "ptSamples", "effective_spp", "measured_effective_spp", "resolution_w", "resolution_h", "wall_ms", "ms_per_frame",
+                "total_wall_ms", "total_ms_per_frame", "warmup_frames", "measured_frames", "throughput_MSps", "spp_per_sec")
+
+
+def test_headless_accepts_the_reference_harness_command_line(box_scene, std_env, tmp_path):
+    """The exact argument list utils/benchmark/benchmark_runner.py:164-198 spawns (--headless --size W H --frames N --maxFrames N
+    --ptSamples S --ptAdaptiveSampling 0 --renderSystem 0 --envSystem 1 --scenefile X.glb --hdrfile Y.hdr): the .glb and .hdr are
+    loaded directly, the first BENCHMARK_JSON record with "schema":1 is the headless_summary carrying every key the reference's
+    parser reads (utils/benchmark/benchmark_results.py:147-170), frame 1 is warm-up (src/benchmarking.hpp:128), and the image is
+    the one the Python host renders from the same files.  The log is kept under gpurun_out/ for the CPU-side parser test."""
+    import json
+    import os
+    import shutil
+    import subprocess
+    from vk_gltf_renderer_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(os.path.dirname(_lib.LIB_PATH), "b200pt_headless")
+    raw = str(tmp_path / "box.raw")
+    cmd = [exe, "--headless", "--size", "96", "64", "--frames", "6", "--maxFrames", "6", "--ptSamples", "2", "--ptAdaptiveSampling", "0", "--renderSystem", "0",
+           "--envSystem", "1", "--scenefile", os.path.join(root, "tests", "assets", "Box.glb"), "--hdrfile", os.path.join(root, "tests", "assets", "std_env.hdr"),
+           "--ptMaxDepth", "5", "--outRaw", raw]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout
+    recs = [json.loads(l[l.find("BENCHMARK_JSON ") + 15:]) for l in out.stdout.splitlines() if "BENCHMARK_JSON " in l]
+    recs = [r for r in recs if r.get("schema") == 1]
+    summary = [r for r in recs if r["type"] == "headless_summary"][0]
+    assert all(k in summary for k in HARNESS_KEYS)
+    assert summary["frames"] == 6 and summary["maxFrames"] == 6 and summary["ptSamples"] == 2 and summary["effective_spp"] == 12
+    assert summary["warmup_frames"] == 1 and summary["measured_frames"] == 5 and summary["measured_effective_spp"] == 10
+    assert summary["resolution_w"] == 96 and summary["resolution_h"] == 64 and summary["throughput_MSps"] > 0
+    assert any(l.startswith("HEADLESS_SUMMARY ") for l in out.stdout.splitlines())
+    img = np.fromfile(raw, np.float32).reshape(64, 96, 4)
+    _, ref = _gpu_render(box_scene, std_env, 96, 64, 6, ptMaxDepth=5, ptSamples=2)
+    assert np.array_equal(img[..., 3], ref[..., 3]) and rel_rmse(img, ref) <= 1e-4
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(root, "gpurun_out", "headless_box_harness.log"), "w") as f:
+        f.write(out.stdout)
+    # flags of the reference app that mean nothing here are skipped, a different render system is an error
+    out = subprocess.run(cmd[:-2] + ["--vsync", "0", "--renderSystem", "1"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert out.returncode != 0 and "renderSystem" in out.stdout

@@ -122,3 +122,38 @@ def test_interleave_band_choices_and_bench_core_count():
     import bench
     n = bench.usable_cores()
     assert 1 <= n <= (os.cpu_count() or 1)
+
+
+def test_adaptive_sampling_controller_follows_the_reference_rules():
+    """PathTracer::updateAdaptiveSampling (src/renderer_pathtracer.cpp:1326-1374): reset to 1 at frame 0, untouched before frame 5,
+    +1 below 80 % of the target frame time, -1 above 110 %, clamped to [1, 100]; off = never touched."""
+    from vk_gltf_renderer_b200.renderer import PathTracer, Resources
+    pt = PathTracer.__new__(PathTracer)
+    pt.ptAdaptiveSampling, pt.ptPerformanceTarget, pt.ptSamples, pt.last_frame_gpu_ms = True, 1, 7, None
+    res = Resources()
+    res.frameCount = 0
+    pt.updateAdaptiveSampling(res)
+    assert pt.ptSamples == 1
+    pt.last_frame_gpu_ms = 5.0
+    for f in range(1, 5):
+        res.frameCount = f
+        pt.updateAdaptiveSampling(res)
+    assert pt.ptSamples == 1                       # first frames: hands off
+    for f in range(5, 9):
+        res.frameCount = f
+        pt.updateAdaptiveSampling(res)             # 5 ms << 0.8 * 33.3 ms: headroom
+    assert pt.ptSamples == 5
+    pt.last_frame_gpu_ms = 30.0                    # inside [0.8, 1.1] x target: hold
+    pt.updateAdaptiveSampling(res)
+    assert pt.ptSamples == 5
+    pt.last_frame_gpu_ms = 40.0                    # > 1.1 x 33.3 ms: back off
+    for _ in range(10):
+        pt.updateAdaptiveSampling(res)
+    assert pt.ptSamples == 1
+    pt.ptPerformanceTarget, pt.last_frame_gpu_ms, pt.ptSamples = 3, 1.0, 99
+    pt.updateAdaptiveSampling(res)
+    pt.updateAdaptiveSampling(res)
+    assert pt.ptSamples == 100 and pt.getTargetFrameTimeMs() == 100.0
+    pt.ptAdaptiveSampling, pt.ptSamples = False, 4
+    pt.updateAdaptiveSampling(res)
+    assert pt.ptSamples == 4

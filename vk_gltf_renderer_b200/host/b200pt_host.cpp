@@ -399,8 +399,30 @@ void PathTracer::onResize(int width, int height, Resources& res)
   res.height = height;
 }
 
+void PathTracer::updateAdaptiveSampling(const Resources& res)
+{
+  constexpr int kMin = 1, kMax = 100;  // MIN_/MAX_SAMPLES_PER_PIXEL
+  if(!ptAdaptiveSampling)
+    return;
+  if(res.frameCount == 0)
+  {
+    ptSamples = kMin;  // the accumulation restarted
+    return;
+  }
+  if(res.frameCount < 5 || lastFrameGpuMs < 0.0)
+    return;
+  static const double kTarget[4] = {1000.0 / 60.0, 1000.0 / 30.0, 1000.0 / 15.0, 1000.0 / 10.0};
+  const double        target = kTarget[std::min(std::max(ptPerformanceTarget, 0), 3)];
+  if(lastFrameGpuMs < target * 0.8 && ptSamples < kMax)
+    ptSamples++;
+  else if(lastFrameGpuMs > target * 1.1 && ptSamples > kMin)
+    ptSamples--;
+  ptSamples = std::min(std::max(ptSamples, kMin), kMax);
+}
+
 void PathTracer::onRender(Resources& res)
 {
+  updateAdaptiveSampling(res);
   if(res.frameCount == 0)
     m_totalSamplesAccumulated = 0;
   const b200pt_frame_info fi = makeFrameInfo(res.camera, m_width, m_height, res.settings);
@@ -418,6 +440,8 @@ void PathTracer::registerParameters(std::map<std::string, std::string>& registry
   registry["ptAperture"] = std::to_string(ptAperture);
   registry["ptFocalDistance"] = std::to_string(ptFocalDistance);
   registry["ptAutoFocus"] = ptAutoFocus ? "1" : "0";
+  registry["ptAdaptiveSampling"] = ptAdaptiveSampling ? "1" : "0";
+  registry["ptPerformanceTarget"] = std::to_string(ptPerformanceTarget);
 }
 
 bool PathTracer::setParameter(const std::string& name, const std::string& value)
@@ -436,6 +460,10 @@ bool PathTracer::setParameter(const std::string& name, const std::string& value)
     ptFocalDistance = std::stof(value);
   else if(name == "ptAutoFocus")
     ptAutoFocus = std::stoi(value) != 0;
+  else if(name == "ptAdaptiveSampling")
+    ptAdaptiveSampling = std::stoi(value) != 0;
+  else if(name == "ptPerformanceTarget")
+    ptPerformanceTarget = std::stoi(value);
   else
     return false;
   return true;

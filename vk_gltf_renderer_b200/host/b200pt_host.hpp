@@ -127,6 +127,11 @@ public:
   float ptAperture      = 0.0f;
   float ptFocalDistance = 0.0f;
   bool  ptAutoFocus     = true;
+  // adaptive sampling (reference src/renderer_pathtracer.hpp:158-199): OFF by default here (the harness passes 0)
+  bool   ptAdaptiveSampling  = false;
+  int    ptPerformanceTarget = 1;      // 0: 60 FPS, 1: 30, 2: 15, 3: 10
+  double lastFrameGpuMs      = -1.0;   // GPU time of the previous frame's path-trace section, < 0 = unknown
+  void   updateAdaptiveSampling(const Resources& res);  // src/renderer_pathtracer.cpp:1326-1374
 
   b200pt_push_constant m_pushConst{};
   int                  m_totalSamplesAccumulated = 0;

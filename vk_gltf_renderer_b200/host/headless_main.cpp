@@ -1,17 +1,25 @@
 // headless_main.cpp — stand-in for `vk_gltf_renderer --headless --frames N --ptSamples S …` (reference src/main.cpp:133-136,
 // headless flow src/renderer.cpp:1939-1977, summary lines src/benchmarking.cpp:245-305) on top of the C++ host mirror.
 //
-//   b200pt_headless --scene scene.b2sc [--size W H] [--frames N] [--warmupFrames K] [--ptMaxDepth D] [--ptSamples S] …
-//                   [--device G] [--framesInFlight L] [--out image.pfm]
+// Accepts the command line the reference's benchmark harness spawns (utils/benchmark/benchmark_runner.py:164-198):
+//   b200pt_headless --headless --size W H --frames N --maxFrames N --ptSamples S --ptAdaptiveSampling 0 --renderSystem 0
+//                   --envSystem 1 --scenefile scene.glb [--hdrfile env.hdr] [extra args]
+// plus  --scene scene.b2sc  (a pre-converted blob), --warmupFrames K, --device G, --framesInFlight L, --out image.pfm,
+// --outRaw image.f32.  A .gltf / .glb scene is converted on the fly by the package's own loader
+// (python -m vk_gltf_renderer_b200.convert).  Flags of the reference application that have no meaning for this backend are
+// skipped with a note on stderr; --renderSystem other than 0 (path tracer) and --envSystem 0 (physical sky) are errors.
 //
-// Prints the reference's two record kinds so its benchmark tooling can read them: a human-readable
-// "HEADLESS_SUMMARY key=value …" line and a "BENCHMARK_JSON {…}" line with the same keys, plus the ray counters the
-// reference lacks.  The image written by --out is the RGBA32F accumulation buffer (what the reference tonemaps) as PFM.
+// Prints the reference's record kinds so its benchmark tooling reads them unchanged (utils/benchmark/benchmark_results.py):
+// "HEADLESS_PROGRESS …" / "HEADLESS_SUMMARY key=value …" lines and "BENCHMARK_JSON {"schema":1, …}" records with the same
+// keys, plus the ray counters the reference lacks.  Like the reference, the first frame is warm-up and excluded from the
+// measured window (kHeadlessWarmupFrames = 1, src/benchmarking.hpp:128), and maxFrames is raised to the number of frames
+// (alignMaxFramesForHeadless).  The image written by --out is the RGBA32F accumulation buffer (what the reference tonemaps).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unistd.h>
 
 #include "b200pt_host.hpp"
 
@@ -43,10 +51,50 @@ static void writeRaw(const std::string& path, const std::vector<float>& rgba)
   std::fclose(f);
 }
 
+static bool endsWith(const std::string& s, const char* suffix)
+{
+  const size_t n = std::strlen(suffix);
+  return s.size() >= n && s.compare(s.size() - n, n, suffix) == 0;
+}
+
+// .gltf / .glb (+ .hdr) -> temporary B2SC blob through the package's loader; returns the blob path
+static std::string convertScene(const std::string& gltf, const std::string& hdrFile)
+{
+  char self[4096];
+  const ssize_t n = readlink("/proc/self/exe", self, sizeof(self) - 1);
+  if(n <= 0)
+    throw Error("cannot locate the executable (needed to find the vk_gltf_renderer_b200 package)");
+  self[n] = 0;
+  std::string pkgDir(self);
+  pkgDir = pkgDir.substr(0, pkgDir.find_last_of('/'));                  // .../vk_gltf_renderer_b200
+  const std::string root = pkgDir.substr(0, pkgDir.find_last_of('/'));  // repo root (PYTHONPATH)
+  char              tmpl[] = "/tmp/b200pt_scene_XXXXXX";
+  const int         fd = mkstemp(tmpl);
+  if(fd < 0)
+    throw Error("cannot create a temporary scene blob");
+  close(fd);
+  auto quote = [](const std::string& p) {
+    std::string q = "'";
+    for(char c : p)
+      q += (c == '\'') ? std::string("'\\''") : std::string(1, c);
+    return q + "'";
+  };
+  const char*       py = std::getenv("B200PT_PYTHON");
+  const std::string cmd = "PYTHONPATH=" + quote(root) + ":\"$PYTHONPATH\" " + std::string(py ? py : "python3") + " -m vk_gltf_renderer_b200.convert " + quote(gltf) + " "
+                          + quote(tmpl) + (hdrFile.empty() ? std::string() : " --hdr " + quote(hdrFile)) + " 1>&2";
+  if(std::system(cmd.c_str()) != 0)
+  {
+    unlink(tmpl);
+    throw Error("scene conversion failed: " + cmd);
+  }
+  return tmpl;
+}
+
 int main(int argc, char** argv)
 {
-  std::string scenePath, outPath, rawPath;
-  int         width = 1920, height = 1080, frames = 16, warmupFrames = 0, framesInFlight = 0;
+  std::string scenePath, hdrPath, outPath, rawPath, tmpBlob;
+  int         width = 1920, height = 1080, frames = 16, warmupFrames = 1, framesInFlight = 0;  // warm-up: src/benchmarking.hpp:128
+  int         adaptiveSampling = 0;
   Resources   res;
   PathTracer  pt;
   try
@@ -59,8 +107,23 @@ int main(int argc, char** argv)
           throw Error("missing value after " + a);
         return argv[++i];
       };
-      if(a == "--scene")
+      if(a == "--scene" || a == "--scenefile")
         scenePath = next();
+      else if(a == "--hdrfile")
+        hdrPath = next();
+      else if(a == "--headless")
+      {
+      }
+      else if(a == "--renderSystem")
+      {
+        if(std::stoi(next()) != 0)
+          throw Error("--renderSystem: only 0 (path tracer) is this backend's path");
+      }
+      else if(a == "--ptAdaptiveSampling")
+      {
+        adaptiveSampling = std::stoi(next());
+        pt.ptAdaptiveSampling = adaptiveSampling != 0;
+      }
       else if(a == "--size")
       {
         width = std::stoi(next());
@@ -91,14 +154,36 @@ int main(int argc, char** argv)
         if(!pt.setParameter(a.substr(2), next()))
           throw Error("unknown parameter " + a);
       }
+      else if(a.rfind("--", 0) == 0)
+      {
+        // a flag of the reference application without meaning here: skip it and its value(s)
+        std::fprintf(stderr, "b200pt_headless: ignoring %s", a.c_str());
+        while(i + 1 < argc && std::strncmp(argv[i + 1], "--", 2) != 0)
+          std::fprintf(stderr, " %s", argv[++i]);
+        std::fprintf(stderr, "\n");
+      }
       else
         throw Error("unknown argument " + a);
     }
+    (void)adaptiveSampling;  // 0 in every harness run; the controller itself lives in PathTracer::updateAdaptiveSampling
     if(scenePath.empty())
-      throw Error("usage: b200pt_headless --scene scene.b2sc [--size W H] [--frames N] [--pt<Name> value] [--out image.pfm]");
+      throw Error("usage: b200pt_headless --scenefile scene.glb|scene.b2sc [--hdrfile env.hdr] [--size W H] [--frames N] [--pt<Name> value] [--out image.pfm]");
+    // alignMaxFramesForHeadless (src/benchmarking.hpp:112): accumulation keeps refining for the whole capture
+    if(res.settings.maxFrames < frames)
+      res.settings.maxFrames = frames;
+    warmupFrames = std::min(warmupFrames, std::max(frames - 1, 0));
+    if(endsWith(scenePath, ".gltf") || endsWith(scenePath, ".glb"))
+    {
+      tmpBlob = convertScene(scenePath, hdrPath);
+      scenePath = tmpBlob;
+    }
+    else if(!hdrPath.empty())
+      std::fprintf(stderr, "b200pt_headless: --hdrfile is read during glTF conversion only; a .b2sc blob carries its own environment\n");
 
     SceneData scene;
     scene.load(scenePath);
+    if(!tmpBlob.empty())
+      unlink(tmpBlob.c_str());
     res.scene = &scene;
     res.camera = scene.camera;
     res.width = width;
@@ -128,6 +213,15 @@ int main(int argc, char** argv)
       }
       res.frameCount++;
       pt.onRender(res);
+      if((f + 1) % 50 == 0 && f + 1 < frames)
+      {
+        // progress records like updateHeadlessProgressIfNeeded (src/benchmarking.cpp:215-238), every 50 frames; the
+        // frames are only SUBMITTED at this point (frames in flight), like the reference's app_frame counter
+        const double el = std::chrono::duration<double, std::milli>(clock::now() - t0).count();
+        std::printf("HEADLESS_PROGRESS app_frame %d/%d (%.0f%%) elapsed_ms=%.1f ms_per_frame=%.2f\n", f + 1, frames, 100.0 * (f + 1) / frames, el, el / (f + 1));
+        std::printf("BENCHMARK_JSON {\"schema\":1,\"type\":\"headless_progress\",\"app_frame\":%d,\"frames\":%d,\"percent\":%.3f,\"elapsed_ms\":%.3f,\"ms_per_frame\":%.3f}\n",
+                    f + 1, frames, 100.0 * (f + 1) / frames, el, el / (f + 1));
+      }
     }
     pt.synchronize();
     const auto   t1 = clock::now();

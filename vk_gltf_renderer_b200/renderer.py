@@ -63,6 +63,12 @@ class PathTracer:
         self.m_pushConst = abi.PushConstant()
         self.hdr_integral = None
         self._attached = False
+        # adaptive sampling (reference src/renderer_pathtracer.hpp:158-199, .cpp:1326-1374).  The reference defaults to ON for
+        # interactive use and its benchmark harness passes --ptAdaptiveSampling 0; this mirror defaults to OFF so that a
+        # frame's sample count never depends on timing unless asked for.
+        self.ptAdaptiveSampling = False
+        self.ptPerformanceTarget = 1  # 0 interactive (60 FPS), 1 balanced (30), 2 quality (15), 3 max quality (10)
+        self.last_frame_gpu_ms = None  # GPU time of the previous frame's path-trace section (the reference reads its profiler)
 
     # -- error plumbing (reference: NVVK_CHECK aborts; here: exceptions carrying b200pt_last_error) --
     def _ck(self, rc, what):
@@ -73,7 +79,7 @@ class PathTracer:
     def registerParameters(self, registry):
         """nvutils::ParameterRegistry analogue: registry is any dict-like; names as the reference CLI."""
         for name in ("ptMaxDepth", "ptSamples", "ptFireflyClamp", "ptTexGradScale", "ptAperture",
-                     "ptFocalDistance", "ptAutoFocus"):
+                     "ptFocalDistance", "ptAutoFocus", "ptAdaptiveSampling", "ptPerformanceTarget"):
             registry[name] = (self, name)
 
     # -- BaseRenderer virtuals --------------------------------------------------------------------
@@ -126,10 +132,35 @@ class PathTracer:
         self._tile = (y0, rows)
         resources.size = (w, h)
 
+    MIN_SAMPLES_PER_PIXEL, MAX_SAMPLES_PER_PIXEL = 1, 100
+
+    def getTargetFrameTimeMs(self):
+        return {0: 1000.0 / 60.0, 1: 1000.0 / 30.0, 2: 1000.0 / 15.0, 3: 1000.0 / 10.0}.get(self.ptPerformanceTarget, 1000.0 / 30.0)
+
+    def updateAdaptiveSampling(self, resources):
+        """PathTracer::updateAdaptiveSampling (src/renderer_pathtracer.cpp:1326-1374): samples per pixel follow the measured
+        GPU time of the path-trace section -- reset to 1 when the accumulation restarts, hands off during the first 5 frames,
+        +1 with more than 20 % headroom under the target frame time, -1 when more than 10 % over, clamped to [1, 100]."""
+        if not self.ptAdaptiveSampling or self.last_frame_gpu_ms is None and resources.frameCount != 0:
+            return
+        if resources.frameCount == 0:
+            self.ptSamples = self.MIN_SAMPLES_PER_PIXEL
+            return
+        if resources.frameCount < 5:
+            return
+        target = self.getTargetFrameTimeMs()
+        if self.last_frame_gpu_ms < target * 0.8 and self.ptSamples < self.MAX_SAMPLES_PER_PIXEL:
+            self.ptSamples += 1
+        elif self.last_frame_gpu_ms > target * 1.1 and self.ptSamples > self.MIN_SAMPLES_PER_PIXEL:
+            self.ptSamples -= 1
+        self.ptSamples = min(max(self.ptSamples, self.MIN_SAMPLES_PER_PIXEL), self.MAX_SAMPLES_PER_PIXEL)
+
     def onRender(self, cmd, resources):
-        """One frame: setupPushConstant (renderer_pathtracer.cpp:1496-1574) + dispatch + updateStatistics."""
+        """One frame: updateAdaptiveSampling + setupPushConstant (renderer_pathtracer.cpp:553,1496-1574) + dispatch +
+        updateStatistics."""
         w, h = self._size
         s = resources.settings
+        self.updateAdaptiveSampling(resources)
         if resources.frameCount == 0:
             self.m_totalSamplesAccumulated = 0
         fi = cam_mod.make_frame_info(resources.camera, w, h, use_hdr=(s.envSystem == 1), env_rotation=s.hdrEnvRotation,
@@ -231,7 +262,8 @@ def render_headless(resources, frames, *, pt=None, device=0, **pt_params):
             setattr(pt, k, v)
         pt.onAttach(resources)
     resources.frameCount = -1
-    for _ in range(min(frames, max(resources.settings.maxFrames, frames))):
+    # (the headless run raises maxFrames to the frame count: BenchmarkController::alignMaxFramesForHeadless, so no cap applies)
+    for _ in range(frames):
         resources.frameCount += 1
         pt.onRender(None, resources)
     img = pt.read_accum()
