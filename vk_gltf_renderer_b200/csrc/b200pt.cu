@@ -1676,6 +1676,7 @@ void b200pt_destroy(b200pt_t* h)
     return;
   cudaSetDevice(h->device);
   syncAll(h);
+  flushEvents(h);  // (writes the tail of a B200PT_TIMELINE dump; needs the lane streams alive)
   freeScene(h);
   freePool(h);
   freeRayPool(h);
@@ -1701,7 +1702,6 @@ void b200pt_destroy(b200pt_t* h)
     cudaFree(h->dEnvAccel);
   cudaFree(h->dStats);
   cudaFree(h->dLutSrgb);
-  flushEvents(h);
   for(auto& e : h->evPool)
   {
     cudaEventDestroy(e.a);
