@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_trace(PathState
       T.flushCounters(&stats->nodesVisited, &stats->trisTested);
       const TraceHit ho = T.result();
       P.hit[path] = f4(ho.t, ho.u, ho.v, __uint_as_float(ho.slot));
+      T.sortCandidates(cand, cs);
       const int n = T.candidatesInFront(cand, cs);
       if(n > 0)
       {
@@ -925,6 +926,7 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathStat
           info.x = 0x80000000u;  // an opaque occluder ended the query (raytracer_interface.h.slang:181-184)
         else
         {
+          T.sortCandidates(cand, cs);
           const int n = T.collectN;
 #pragma unroll
           for(int i = 0; i < kCand; i++)
