@@ -223,7 +223,6 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_trace(PathState
       T.flushCounters(&stats->nodesVisited, &stats->trisTested);
       const TraceHit ho = T.result();
       P.hit[path] = f4(ho.t, ho.u, ho.v, __uint_as_float(ho.slot));
-      T.sortCandidates(cand, cs);
       const int n = T.candidatesInFront(cand, cs);
       if(n > 0)
       {
@@ -332,19 +331,22 @@ __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const ui
     }
     const int n = (int)(info.x & 0xffu);
     // ---- lane j: candidate j and its opacity ----
-    float    ct = 0.f, cu = 0.f, cv = 0.f, op = 0.f;
+    float    ct = 0.f, cu = 0.f, cv = 0.f, op = 0.f, transmission = 0.f;
     uint32_t slot = 0;
     if(sub < n)
     {
       const float4 c = P.cand[sub][path];
       slot = __float_as_uint(c.w);
-      const uint2               meta = triMeta[slot];
-      const bool                flip = ((meta.x >> 28) & TRI_FLIPPED) != 0;  // mirrored instance: (u, v) swap back
-      const b200pt_render_node& node = S.nodes[meta.x & 0x0fffffffu];
+      // the triangle's pre-gathered alpha record: candidate -> (index ->) record -> texels
+      const uint32_t ri = SHADOW ? slot - S.alphaBaseS : __ldg(&S.alphaIdx[slot]);
+      const uint32_t w0 = __float_as_uint(__ldg(&(SHADOW ? S.bvhA.tris : S.bvh.tris)[slot * 3 + 0]).w);
+      const bool     flip = ((w0 >> 28) & TRI_FLIPPED) != 0;  // mirrored instance: (u, v) swap back
+      const AlphaRec rec = loadAlphaRec(S.alphaRecs + ri);
       ct = c.x;
       cu = flip ? c.z : c.y;
       cv = flip ? c.y : c.z;
-      op = getOpacity(S, node, S.prims[node.renderPrimID], meta.y, f3(1.0f - cu - cv, cu, cv));
+      op = opacityFromRecord(rec, f3(1.0f - cu - cv, cu, cv));
+      transmission = rec.transmission;
     }
     const uint32_t seedIn = valid ? __float_as_uint(P.misc[path].w) : 0u;
     uint32_t       seed = seedIn;
@@ -443,8 +445,20 @@ __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const ui
         const float    ui = __shfl_sync(0xffffffffu, cu, base + i);
         const float    vi = __shfl_sync(0xffffffffu, cv, base + i);
         const uint32_t si = __shfl_sync(0xffffffffu, slot, base + i);
+        const float    tr = __shfl_sync(0xffffffffu, transmission, base + i);
         if(i < n && !done && rnd(seed) < oi)
-          accept(si, ti, ui, vi);
+        {
+          if(tr <= 0.01f)
+          {
+            // getShadowTransmission returns 0 for a non-transmissive material (alpha-tested foliage): the ray is blocked
+            // (same result as accept(), without its gathers)
+            prevHitT = ti;
+            total = f3(0.0f);
+            done = true;
+          }
+          else
+            accept(si, ti, ui, vi);
+        }
       }
       const float lastT = __shfl_sync(0xffffffffu, ct, base + kCand - 1);
       if(!done && n == kCand && qCont != nullptr)
@@ -926,7 +940,6 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathStat
           info.x = 0x80000000u;  // an opaque occluder ended the query (raytracer_interface.h.slang:181-184)
         else
         {
-          T.sortCandidates(cand, cs);
           const int n = T.collectN;
 #pragma unroll
           for(int i = 0; i < kCand; i++)
@@ -1854,6 +1867,7 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
 
   // --- textures ---
   std::vector<DevTex> devTex(s->numTextures);
+  std::vector<const uchar4*> texLevel0(s->numTextures, nullptr);  // level-0 texels (device), for the alpha-triangle records
   {
     for(uint32_t i = 0; i < s->numTextures; i++)
       if(s->textures[i].width <= 0 || s->textures[i].height <= 0 || !s->textures[i].rgba8)
@@ -1909,6 +1923,7 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
     {
       describeTexture(s->textures[i], chains[i], devTex[i]);
       devTex[i].texels = reinterpret_cast<const uchar4*>(dTexels + texBase[i]);
+      texLevel0[i] = devTex[i].texels + levelOfs[(size_t)i * 16];
       devTex[i].levelOfs = dLevelOfs + (size_t)i * 16;
     }
   }
@@ -2063,6 +2078,79 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
     S.triMetaS = reinterpret_cast<const uint2*>(dMetaS);
     splitNodeBytes = (bvhO.nodes.size() + bvhA.nodes.size()) * sizeof(float);
     splitTriBytes = trisS.size() * sizeof(float);
+  }
+  // ---- alpha-triangle records (device_scene.cuh: AlphaRec), one per non-opaque triangle in bvhA's leaf order ----
+  S.alphaRecs = nullptr;
+  S.alphaIdx = nullptr;
+  S.alphaBaseS = 0;
+  if(anyNonOpaque)
+  {
+    const uint32_t        nA = bvhA.numTris;
+    std::vector<AlphaRec> recs(nA);
+    std::vector<uint32_t> recOfGid(flat.size(), 0xFFFFFFFFu);
+    for(uint32_t k = 0; k < nA; k++)
+    {
+      uint32_t gid;
+      memcpy(&gid, &bvhA.tris[(size_t)k * 12 + 11], 4);
+      recOfGid[gid] = k;
+      const FlatTri&                 T = flat[gid];
+      const b200pt_render_node&      node = s->renderNodes[T.rnode];
+      const b200pt_render_primitive& p = s->renderPrimitives[node.renderPrimID];
+      const b200pt_shade_material&   m = s->materials[(uint32_t)std::max(0, node.materialID)];
+      AlphaRec                       r{};
+      r.modeFlags = (uint32_t)m.alphaMode & 3u;
+      r.cutoff = m.alphaCutoff;
+      r.transmission = m.transmissionFactor;
+      const bool     specGloss = m.pbrModel == 1;
+      const uint16_t slot = specGloss ? m.pbrDiffuseTexture : m.pbrBaseColorTexture;
+      r.factor = specGloss ? m.pbrDiffuseFactor[3] : m.pbrBaseColorFactor[3];
+      const uint32_t i0 = p.indices[T.prim * 3], i1 = p.indices[T.prim * 3 + 1], i2 = p.indices[T.prim * 3 + 2];
+      if(slot > 0)
+      {
+        const b200pt_texture_info& ti = s->textureInfos[slot];
+        const float*               uv = ti.texCoord ? p.texCoords[1] : p.texCoords[0];
+        if(uv)
+        {
+          const uint32_t vi[3] = {i0, i1, i2};
+          for(int c = 0; c < 3; c++)
+          {
+            r.uv[c * 2] = uv[vi[c] * 2];
+            r.uv[c * 2 + 1] = uv[vi[c] * 2 + 1];
+          }
+        }
+        if(ti.index >= 0 && (uint32_t)ti.index < s->numTextures)
+        {
+          r.lv0 = texLevel0[ti.index];
+          r.w0 = devTex[ti.index].w0;
+          r.h0 = devTex[ti.index].h0;
+          r.wrap = ((uint32_t)devTex[ti.index].wrapS & 0xffffu) | ((uint32_t)devTex[ti.index].wrapT << 16);
+          if(devTex[ti.index].magLinear)
+            r.modeFlags |= 4u;
+        }
+      }
+      if(p.colors)
+      {
+        r.modeFlags |= 8u;
+        r.colA = (p.colors[i0] >> 24) | ((p.colors[i1] >> 24) << 8) | ((p.colors[i2] >> 24) << 16);
+      }
+      recs[k] = r;
+    }
+    std::vector<uint32_t> idxOfSlot(bvh.numTris, 0xFFFFFFFFu);
+    for(uint32_t k = 0; k < bvh.numTris; k++)
+    {
+      uint32_t gid;
+      memcpy(&gid, &bvh.tris[(size_t)k * 12 + 11], 4);
+      idxOfSlot[k] = recOfGid[gid];
+    }
+    AlphaRec* dRecs;
+    uint32_t* dIdx;
+    if((rc = upload(h, h->sceneAllocs, recs.data(), recs.size(), &dRecs)))
+      return rc;
+    if((rc = upload(h, h->sceneAllocs, idxOfSlot.data(), idxOfSlot.size(), &dIdx)))
+      return rc;
+    S.alphaRecs = dRecs;
+    S.alphaIdx = dIdx;
+    S.alphaBaseS = bvhO.numTris;
   }
   h->nodeBytes = bvh.nodes.size() * sizeof(float) + splitNodeBytes;
   h->triBytes = bvh.tris.size() * sizeof(float) + splitTriBytes;

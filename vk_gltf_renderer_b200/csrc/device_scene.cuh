@@ -45,6 +45,24 @@ struct DevTex
   int             magLinear, minLinear, mipLinear;
 };
 
+// Everything the stochastic alpha test of ONE non-opaque triangle needs (getOpacity, pathtrace_functions.h.slang:189-260),
+// gathered at scene build: 64 B = four 128-bit loads, against the nine dependent gathers of the generic path (candidate ->
+// triMeta -> render node -> primitive -> indices -> uv -> material -> texture info -> texture descriptor) that made the
+// any-hit kernels latency-bound (ncu r01: long_scoreboard 20-27 warps per issue).
+struct AlphaRec
+{
+  float         uv[6];        // the three vertices' texture coordinates of the set the alpha texture reads ((0,0) if absent)
+  const uchar4* lv0;          // level-0 texels of the base-colour / diffuse texture (tiled), nullptr = no texture (alpha 1)
+  int           w0, h0;
+  uint32_t      wrap;         // wrapS | wrapT << 16 (glTF enums)
+  float         factor;       // pbrBaseColorFactor.a (pbrDiffuseFactor.a for specular-glossiness)
+  float         cutoff;
+  uint32_t      modeFlags;    // bits 0-1 alphaMode, bit 2 magnification filter is linear, bit 3 vertex colours present
+  uint32_t      colA;         // vertex colour alphas: a0 | a1 << 8 | a2 << 16 (UNORM8)
+  float         transmission; // material.transmissionFactor (<= 0.01: a passing candidate blocks the shadow ray)
+};
+static_assert(sizeof(AlphaRec) == 64, "AlphaRec is four 16-byte loads");
+
 struct DevScene
 {
   const b200pt_render_node*    nodes;
@@ -61,6 +79,9 @@ struct DevScene
   int                          hasAlpha;  // the scene has non-opaque triangles (the any-hit kernels are launched)
   const uint2*                 triMeta;   // per triangle slot of `bvh`: (rnode | flags<<28, primitiveID)
   const uint2*                 triMetaS;  // per triangle slot of bvhO / bvhA (== triMeta in scenes without non-opaque triangles)
+  const AlphaRec*              alphaRecs; // one per non-opaque triangle, in bvhA's leaf order
+  const uint32_t*              alphaIdx;  // per triangle slot of `bvh`: index into alphaRecs (0xFFFFFFFF for opaque triangles)
+  uint32_t                     alphaBaseS; // first non-opaque slot of the split triangle array: record = slot - alphaBaseS
   const float4*                envRgba;  // lat-long radiance, pdf in .w
   const uint2*                 envAccel; // (alias, q bits)
   const float*                 lutSrgb;  // 512 floats: sRGB decode table, then i/255 (staged into shared memory per block)

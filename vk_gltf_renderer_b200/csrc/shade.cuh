@@ -474,6 +474,63 @@ PT_D float getOpacity(const DevScene& S, const b200pt_render_node& node, const D
   return a;
 }
 
+PT_D AlphaRec loadAlphaRec(const AlphaRec* __restrict__ p)
+{
+  // four 128-bit loads
+  const float4* q = reinterpret_cast<const float4*>(p);
+  union
+  {
+    float4   v[4];
+    AlphaRec r;
+  } u;
+  u.v[0] = __ldg(q + 0);
+  u.v[1] = __ldg(q + 1);
+  u.v[2] = __ldg(q + 2);
+  u.v[3] = __ldg(q + 3);
+  return u.r;
+}
+
+// getOpacity from the pre-gathered record: the same arithmetic, operation by operation, as the generic function above
+// (interpolated uv, level-0 fetch with the magnification filter, vertex-colour alpha, MASK cutoff)
+PT_D float opacityFromRecord(const AlphaRec& r, float3 bary)
+{
+  const uint32_t mode = r.modeFlags & 3u;
+  if(mode == 0u)
+    return 1.0f;
+  float a = r.factor;
+  if(r.lv0 != nullptr)
+  {
+    const float2 uv = f2(r.uv[0], r.uv[1]) * bary.x + f2(r.uv[2], r.uv[3]) * bary.y + f2(r.uv[4], r.uv[5]) * bary.z;
+    const int    w = r.w0, h = r.h0, tpr = (w + 3) >> 2;
+    const int    wrapS = (int)(r.wrap & 0xffffu), wrapT = (int)(r.wrap >> 16);
+    float        x = uv.x * (float)w, y = uv.y * (float)h;
+    auto         alphaAt = [&](int tx, int ty) { return s_lutSrgb[256 + __ldg(r.lv0 + (((ty >> 2) * tpr + (tx >> 2)) << 4) + ((ty & 3) << 2) + (tx & 3)).w]; };
+    if(!(r.modeFlags & 4u))
+      a *= alphaAt(wrapFast((int)floorf(x), w, wrapS), wrapFast((int)floorf(y), h, wrapT));
+    else
+    {
+      x -= 0.5f;
+      y -= 0.5f;
+      const float fx0 = floorf(x), fy0 = floorf(y);
+      const float fx = x - fx0, fy = y - fy0;
+      const int   x0 = wrapFast((int)fx0, w, wrapS), x1 = wrapFast((int)fx0 + 1, w, wrapS);
+      const int   y0 = wrapFast((int)fy0, h, wrapT), y1 = wrapFast((int)fy0 + 1, h, wrapT);
+      const float ta = alphaAt(x0, y0), tb = alphaAt(x1, y0), tc = alphaAt(x0, y1), td = alphaAt(x1, y1);
+      const float top = ta * (1.0f - fx) + tb * fx;
+      const float bot = tc * (1.0f - fx) + td * fx;
+      a *= top * (1.0f - fy) + bot * fy;
+    }
+  }
+  if(r.modeFlags & 8u)
+  {
+    const float a0 = (float)(r.colA & 0xffu) / 255.0f, a1 = (float)((r.colA >> 8) & 0xffu) / 255.0f, a2 = (float)((r.colA >> 16) & 0xffu) / 255.0f;
+    a *= a0 * bary.x + a1 * bary.y + a2 * bary.z;
+  }
+  if(mode == 1u)
+    return a >= r.cutoff ? 1.0f : 0.0f;
+  return a;
+}
+
 PT_D float3 getShadowTransmission(const DevScene& S, const b200pt_render_node& node, const DevPrim& P, uint32_t triangleID, float3 bary, float hitT, float3 rayDir, bool& isInside)
 {
   const b200pt_shade_material& mat = S.mats[max(0, node.materialID)];

@@ -365,53 +365,38 @@ struct TravState
           }
           else
           {
-            // candidate for the any-hit kernel: in front of the opaque hit (closest mode).  The list is kept UNSORTED
-            // during the walk (ncu source view of the sorted-insertion version: its 55 instructions ran in nearly every
-            // iteration of the loop with 1.5 lanes active, 9 % of the kernel): appending is 5 stores; only a full list pays
-            // for finding its farthest entry.  sortCandidates() orders the list once, at write-out.
-            if(shadow | (t < best.t))
+            // candidate for the any-hit kernel: in front of the opaque hit (closest mode) and, once the list is full,
+            // in front of its last entry
+            bool keep = shadow | (t < best.t);
+            if(collectN == KC)
             {
-              int at = collectN;
-              if(collectN == KC)
+              const float    lt = cand[(KC - 1) * cs].t;
+              const uint32_t lg = cand[(KC - 1) * cs].gid;
+              keep &= (t < lt) | ((t == lt) & (gid < lg));
+            }
+            if(keep)
+            {
+              // insertion sort by (t, id); a full list drops its last entry
+              int pos = collectN < KC ? collectN : KC - 1;
+              while(pos > 0)
               {
-                // full: the new hit replaces the farthest entry if it sorts before it in (t, id) order
-                int      far = 0;
-                float    ft = cand[0].t;
-                uint32_t fg = cand[0].gid;
-#pragma unroll 1
-                for(int i = 1; i < KC; i++)
-                {
-                  const float    ti = cand[i * cs].t;
-                  const uint32_t gi = cand[i * cs].gid;
-                  if((ti > ft) | ((ti == ft) & (gi > fg)))
-                  {
-                    far = i;
-                    ft = ti;
-                    fg = gi;
-                  }
-                }
-                at = ((t < ft) | ((t == ft) & (gid < fg))) ? far : -1;
+                const Cand p = cand[(pos - 1) * cs];
+                if(!((p.t > t) | ((p.t == t) & (p.gid > gid))))
+                  break;
+                cand[pos * cs] = p;
+                pos--;
               }
-              if(at >= 0)
-              {
-                Cand nc;
-                nc.t = t;
-                nc.u = u;
-                nc.v = v;
-                nc.slot = slot;
-                nc.gid = gid;
-                cand[at * cs] = nc;
-                if(collectN < KC)
-                  collectN++;
-                if(collectN == KC && shrink)
-                {
-                  float ft = cand[0].t;
-#pragma unroll 1
-                  for(int i = 1; i < KC; i++)
-                    ft = fmaxf(ft, cand[i * cs].t);
-                  bound = fminf(bound, ft);
-                }
-              }
+              Cand nc;
+              nc.t = t;
+              nc.u = u;
+              nc.v = v;
+              nc.slot = slot;
+              nc.gid = gid;
+              cand[pos * cs] = nc;
+              if(collectN < KC)
+                collectN++;
+              if(collectN == KC && shrink)
+                bound = fminf(bound, cand[(KC - 1) * cs].t);
             }
           }
         }
@@ -423,35 +408,7 @@ struct TravState
   // the opaque hit with (u,v) restored for mirrored instances
   PT_D TraceHit result() const { return unflipHit(best); }
 
-  // orders the candidate list by (t, global id) (selection sort in place: the list is short and this runs once per walk)
-  PT_D void sortCandidates(Cand* __restrict__ cand, int cs) const
-  {
-    for(int i = 0; i + 1 < collectN; i++)
-    {
-      int      m = i;
-      float    mt = cand[i * cs].t;
-      uint32_t mg = cand[i * cs].gid;
-      for(int j = i + 1; j < collectN; j++)
-      {
-        const float    tj = cand[j * cs].t;
-        const uint32_t gj = cand[j * cs].gid;
-        if((tj < mt) | ((tj == mt) & (gj < mg)))
-        {
-          m = j;
-          mt = tj;
-          mg = gj;
-        }
-      }
-      if(m != i)
-      {
-        const Cand a = cand[i * cs], b = cand[m * cs];
-        cand[i * cs] = b;
-        cand[m * cs] = a;
-      }
-    }
-  }
-
-  // closest mode, after sortCandidates: candidates in front of the opaque hit (a prefix of the sorted list)
+  // closest mode: candidates in front of the opaque hit (the list is sorted, so a prefix of it)
   PT_D int candidatesInFront(const Cand* __restrict__ cand, int cs) const
   {
     int n = 0;
@@ -499,7 +456,6 @@ PT_D int walkCollect(const BvhView bvh, float3 org, float3 dir, float tmin, floa
   if(overflowed && T.overflow)
     *overflowed = true;
   opq = T.best;
-  T.sortCandidates(cand, 1);
   return shadow ? T.collectN : T.candidatesInFront(cand, 1);
 }
 
