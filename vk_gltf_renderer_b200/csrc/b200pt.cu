@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
     meta = S.triMeta[slot];
     nodeP = &S.nodes[meta.x & 0x0fffffffu];
     const b200pt_render_node& node = *nodeP;
-    const DevPrim             prim = S.prims[node.renderPrimID];
+    const ShadeRec            srec = loadShadeRec(S.shadeRecs + __ldg(&S.shadeIdx[slot]));
 #ifdef B200PT_DEBUG
     // reference analogue: doDebug at pushConst.mouseCoord (gltf_pathtrace.slang:553-557)
     dbgPixel = ((float)(i % (uint32_t)F.width) == F.pc.mouseCoord[0] && (float)pixelRow(F, i) == F.pc.mouseCoord[1]);
@@ -621,7 +621,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
              org.x, org.y, org.z, dir.x, dir.y, dir.z, seed, (int)depth);
 #endif
     const float3              bary = f3(1.0f - hr.y - hr.z, hr.y, hr.z);
-    hit = getHitState(prim, bary, node.worldToObject, node.objectToWorld, meta.y, dir);
+    hit = getHitState(srec, bary, node.worldToObject, node.objectToWorld, dir);
     statAdd(&stats->shadedHits, 1ull);
     return true;
   };
@@ -2079,6 +2079,75 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
     splitNodeBytes = (bvhO.nodes.size() + bvhA.nodes.size()) * sizeof(float);
     splitTriBytes = trisS.size() * sizeof(float);
   }
+  // ---- per-triangle attribute records for getHitState (device_scene.cuh: ShadeRec), per render primitive ----
+  {
+    std::vector<uint32_t> recBase(s->numRenderPrimitives, 0);
+    size_t                total = 0;
+    for(uint32_t i = 0; i < s->numRenderPrimitives; i++)
+    {
+      recBase[i] = (uint32_t)total;
+      total += s->renderPrimitives[i].triangleCount;
+    }
+    std::vector<ShadeRec> recs(total);
+    for(uint32_t i = 0; i < s->numRenderPrimitives; i++)
+    {
+      const b200pt_render_primitive& p = s->renderPrimitives[i];
+      for(uint32_t t = 0; t < p.triangleCount; t++)
+      {
+        ShadeRec& r = recs[recBase[i] + t];
+        float*    f = reinterpret_cast<float*>(&r);  // 48 floats, layout: device_scene.cuh ShadeRec
+        memset(f, 0, sizeof(ShadeRec));
+        const uint32_t flags = (p.normals ? 1u : 0u) | (p.texCoords[0] ? 2u : 0u) | (p.texCoords[1] ? 4u : 0u) | (p.colors ? 8u : 0u) | (p.tangents ? 16u : 0u);
+        memcpy(&f[3], &flags, 4);
+        uint32_t vi[3];
+        for(int c = 0; c < 3; c++)
+        {
+          vi[c] = p.indices[t * 3 + c];
+          if(vi[c] >= p.vertexCount)
+          {
+            h->err = "b200pt_set_scene: index beyond the primitive's vertex count";
+            return B200PT_E_INVALID;
+          }
+          memcpy(&f[c * 4], &p.positions[vi[c] * 3], 12);                 // v[0..2].xyz
+          if(p.normals)
+            memcpy(&f[12 + c * 4], &p.normals[vi[c] * 3], 12);            // v[3..5].xyz
+          if(p.colors)
+            memcpy(&f[7 + c * 4], &p.colors[vi[c]], 4);                   // v[1].w, v[2].w, v[3].w
+          if(p.tangents)
+            memcpy(&f[36 + c * 4], &p.tangents[vi[c] * 4], 16);           // v[9..11]
+        }
+        if(p.texCoords[0])
+        {
+          f[19] = p.texCoords[0][vi[0] * 2];                               // v[4].w
+          f[23] = p.texCoords[0][vi[0] * 2 + 1];                           // v[5].w
+          memcpy(&f[24], &p.texCoords[0][vi[1] * 2], 8);                   // v[6].xy
+          memcpy(&f[26], &p.texCoords[0][vi[2] * 2], 8);                   // v[6].zw
+        }
+        if(p.texCoords[1])
+        {
+          memcpy(&f[28], &p.texCoords[1][vi[0] * 2], 8);                   // v[7].xy
+          memcpy(&f[30], &p.texCoords[1][vi[1] * 2], 8);                   // v[7].zw
+          memcpy(&f[32], &p.texCoords[1][vi[2] * 2], 8);                   // v[8].xy
+        }
+      }
+    }
+    std::vector<uint32_t> idxOfSlot(bvh.numTris, 0u);
+    for(uint32_t k = 0; k < bvh.numTris; k++)
+    {
+      uint32_t gid;
+      memcpy(&gid, &bvh.tris[(size_t)k * 12 + 11], 4);
+      idxOfSlot[k] = recBase[s->renderNodes[flat[gid].rnode].renderPrimID] + flat[gid].prim;
+    }
+    ShadeRec* dRecs;
+    uint32_t* dIdx;
+    if((rc = upload(h, h->sceneAllocs, recs.data(), recs.size(), &dRecs)))
+      return rc;
+    if((rc = upload(h, h->sceneAllocs, idxOfSlot.data(), idxOfSlot.size(), &dIdx)))
+      return rc;
+    S.shadeRecs = dRecs;
+    S.shadeIdx = dIdx;
+  }
+
   // ---- alpha-triangle records (device_scene.cuh: AlphaRec), one per non-opaque triangle in bvhA's leaf order ----
   S.alphaRecs = nullptr;
   S.alphaIdx = nullptr;

@@ -63,6 +63,20 @@ struct AlphaRec
 };
 static_assert(sizeof(AlphaRec) == 64, "AlphaRec is four 16-byte loads");
 
+// The vertex attributes of ONE triangle of a render primitive, gathered at scene build (object space, shared by all
+// instances of the primitive): twelve 128-bit loads instead of the dependent chain index -> 3 vertices x {position, normal,
+// uv0, uv1, colour, tangent} of narrow loads that getHitState (get_hit.h.slang:59-173) otherwise walks.
+struct ShadeRec
+{
+  // twelve float4, laid out so that every attribute is read by named components (no address arithmetic on the device):
+  //   v[0] = pos0.xyz | flags      v[1] = pos1.xyz | col0     v[2] = pos2.xyz | col1     v[3] = nrm0.xyz | col2
+  //   v[4] = nrm1.xyz | uv0[0].x   v[5] = nrm2.xyz | uv0[0].y v[6] = uv0[1].xy, uv0[2].xy
+  //   v[7] = uv1[0].xy, uv1[1].xy  v[8] = uv1[2].xy | 0 | 0   v[9..11] = tangent 0..2 (xyzw)
+  // flags: bit 0 normals, 1 uv0, 2 uv1, 3 colours, 4 tangents present (else the reference's fallbacks apply)
+  float4 v[12];
+};
+static_assert(sizeof(ShadeRec) == 192, "ShadeRec is twelve 16-byte loads");
+
 struct DevScene
 {
   const b200pt_render_node*    nodes;
@@ -79,6 +93,8 @@ struct DevScene
   int                          hasAlpha;  // the scene has non-opaque triangles (the any-hit kernels are launched)
   const uint2*                 triMeta;   // per triangle slot of `bvh`: (rnode | flags<<28, primitiveID)
   const uint2*                 triMetaS;  // per triangle slot of bvhO / bvhA (== triMeta in scenes without non-opaque triangles)
+  const ShadeRec*              shadeRecs; // one per triangle of every render primitive
+  const uint32_t*              shadeIdx;  // per triangle slot of `bvh`: index into shadeRecs
   const AlphaRec*              alphaRecs; // one per non-opaque triangle, in bvhA's leaf order
   const uint32_t*              alphaIdx;  // per triangle slot of `bvh`: index into alphaRecs (0xFFFFFFFF for opaque triangles)
   uint32_t                     alphaBaseS; // first non-opaque slot of the split triangle array: record = slot - alphaBaseS

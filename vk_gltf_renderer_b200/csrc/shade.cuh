@@ -53,11 +53,24 @@ struct HitState
   float  texelDensity;
 };
 
-PT_D HitState getHitState(const DevPrim& P, float3 bary, const float* W2O, const float* O2W, uint32_t triangleID, float3 rayDir)
+PT_D ShadeRec loadShadeRec(const ShadeRec* __restrict__ p)
 {
-  HitState     hit;
-  const uint3  tri = loadTri(P, triangleID);
-  const float3 pos0 = ld3(P.pos, tri.x), pos1 = ld3(P.pos, tri.y), pos2 = ld3(P.pos, tri.z);
+  const float4* q = reinterpret_cast<const float4*>(p);
+  ShadeRec      r;
+#pragma unroll
+  for(int i = 0; i < 12; i++)
+    r.v[i] = __ldg(q + i);
+  return r;
+}
+
+// getHitState (get_hit.h.slang:59-173) on the triangle's pre-gathered attribute record: the arithmetic is the reference's,
+// statement by statement; only where the vertex data comes from differs (device_scene.cuh: ShadeRec)
+PT_D HitState getHitState(const ShadeRec& R, float3 bary, const float* W2O, const float* O2W, float3 rayDir)
+{
+  HitState       hit;
+  const uint32_t flags = __float_as_uint(R.v[0].w);
+  const bool     hasNrm = (flags & 1u) != 0, hasUv0 = (flags & 2u) != 0, hasUv1 = (flags & 4u) != 0, hasCol = (flags & 8u) != 0, hasTan = (flags & 16u) != 0;
+  const float3   pos0 = xyz(R.v[0]), pos1 = xyz(R.v[1]), pos2 = xyz(R.v[2]);
   const float3 position = pos0 * bary.x + pos1 * bary.y + pos2 * bary.z;
   hit.pos = xfPoint(O2W, position);
 
@@ -65,11 +78,11 @@ PT_D HitState getHitState(const DevPrim& P, float3 bary, const float* W2O, const
   hit.geonrm = normalize(xfNormal(W2O, geoNormal));
 
   float3 nrm0 = geoNormal, nrm1 = geoNormal, nrm2 = geoNormal, normal = geoNormal;
-  if(P.nrm != nullptr)
+  if(hasNrm)
   {
-    nrm0 = ld3(P.nrm, tri.x);
-    nrm1 = ld3(P.nrm, tri.y);
-    nrm2 = ld3(P.nrm, tri.z);
+    nrm0 = xyz(R.v[3]);
+    nrm1 = xyz(R.v[4]);
+    nrm2 = xyz(R.v[5]);
     normal = nrm0 * bary.x + nrm1 * bary.y + nrm2 * bary.z;
   }
   hit.nrm = normalize(xfNormal(W2O, normal));
@@ -80,11 +93,11 @@ PT_D HitState getHitState(const DevPrim& P, float3 bary, const float* W2O, const
   const float3 shadowPos = pointOffset(position, pos0, pos1, pos2, nrm0 * sideFlip, nrm1 * sideFlip, nrm2 * sideFlip, bary);
   hit.shadowPos = xfPoint(O2W, shadowPos);
 
-  hit.uv0 = interpTexCoord(P, 0, tri, bary);
-  hit.uv1 = interpTexCoord(P, 1, tri, bary);
-  if(P.uv0 != nullptr)
+  const float2 t0 = f2(R.v[4].w, R.v[5].w), t1 = f2(R.v[6].x, R.v[6].y), t2 = f2(R.v[6].z, R.v[6].w);
+  hit.uv0 = hasUv0 ? t0 * bary.x + t1 * bary.y + t2 * bary.z : f2(0.0f, 0.0f);
+  hit.uv1 = hasUv1 ? f2(R.v[7].x, R.v[7].y) * bary.x + f2(R.v[7].z, R.v[7].w) * bary.y + f2(R.v[8].x, R.v[8].y) * bary.z : f2(0.0f, 0.0f);
+  if(hasUv0)
   {
-    const float2 t0 = ld2(P.uv0, tri.x), t1 = ld2(P.uv0, tri.y), t2 = ld2(P.uv0, tri.z);
     const float3 we1 = xfVector(O2W, pos1 - pos0);
     const float3 we2 = xfVector(O2W, pos2 - pos0);
     const float  wArea = length(cross(we1, we2));
@@ -95,14 +108,16 @@ PT_D HitState getHitState(const DevPrim& P, float3 bary, const float* W2O, const
   else
     hit.texelDensity = 0.0f;
 
-  hit.color = interpColor(P, tri, bary);
+  hit.color = hasCol ? unpackUnorm4x8(__float_as_uint(R.v[1].w)) * bary.x + unpackUnorm4x8(__float_as_uint(R.v[2].w)) * bary.y
+                           + unpackUnorm4x8(__float_as_uint(R.v[3].w)) * bary.z
+                     : f4(1, 1, 1, 1);
 
   float4 tng0, tng1, tng2;
-  if(P.tan != nullptr)
+  if(hasTan)
   {
-    tng0 = ld4(P.tan, tri.x);
-    tng1 = ld4(P.tan, tri.y);
-    tng2 = ld4(P.tan, tri.z);
+    tng0 = R.v[9];
+    tng1 = R.v[10];
+    tng2 = R.v[11];
   }
   else
   {

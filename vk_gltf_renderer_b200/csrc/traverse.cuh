@@ -46,19 +46,35 @@ PT_D uint32_t signExtendS8x4(uint32_t x)
   return ((x >> 7) & 0x01010101u) * 0xffu;
 }
 
-// byte J of x as the float 32768 + b: PRMT puts the byte into bits 8..15 of 0x47000000 (= 32768.0f, ulp 2^-8).
-// The constant comes in as a kernel parameter (BvhView::prmtPool) that ptxas cannot see through, and the selector is the
-// immediate: with both known, the constant became the immediate and the selector was re-materialised with one IMAD.U32 per
-// PRMT (SASS of round 1: 48 extra instructions per node; a `mov` in inline asm is folded by ptxas just the same).
+// Byte J of x as a float WITHOUT the conversion unit and WITHOUT the ALU pipe.  History: 48 I2F.U8 per node saturated the XU
+// pipe (r01); one PRMT per byte (byte into the mantissa of 2^15) moved the work to the ALU pipe, which then became the
+// kernel's limiter (ncu r02c: pipe_alu 62 % of peak, issue 67 %, math_pipe_throttle; per child 14 ALU-pipe instructions against
+// 7 on the FMA pipe).  tools/pipe_probe.cu on the B200: IDP.4A issues on the IMAD pipe, which overlaps BOTH the ALU pipe
+// (PRMT / LOP3 / FMNMX) and the FFMA pipe.  So: dp4a(x, 64 << 8J, 0x48000000) adds b * 64 to the bit pattern of 2^17 = 131072.0f
+// (mantissa ulp 2^-6), giving 131072 + b exactly, in one IMAD-pipe instruction.  The bias moves into the addend:
+// t = (131072 + b) * ad + (ao - 131072 * ad); the addend's rounding error is at most |ad| / 128, the test widens by |ad| / 64.
+#ifdef B200PT_PRMT_DECODE
+constexpr float kByteBias = 32768.0f, kByteSlack = 0.00390625f;
+#else
+constexpr float kByteBias = 131072.0f, kByteSlack = 0.015625f;
+#endif
 template <int J>
 PT_D float biasedByte(uint32_t x, uint32_t pool)
 {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && defined(B200PT_PRMT_DECODE)
+  // (round-2 first version, kept for A/B: PRMT with the constant pool in a register the compiler cannot fold -- with both PRMT
+  // operands constant, the selector was re-materialised by one IMAD.U32 per PRMT)
   uint32_t r;
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(pool), "n"(0x7604 | (J << 4)));
   return __uint_as_float(r);
-#else
+#elif defined(__CUDA_ARCH__)
+  (void)pool;
+  return __uint_as_float(__dp4a(x, 64u << (8 * J), 0x48000000u));
+#elif defined(B200PT_PRMT_DECODE)
   return __uint_as_float(__byte_perm(x, pool, 0x7604u | ((uint32_t)J << 4)));
+#else
+  (void)pool;
+  return __uint_as_float(0x48000000u + 64u * ((x >> (8 * J)) & 0xffu));
 #endif
 }
 
@@ -240,17 +256,13 @@ struct TravState
         const float    adx = __uint_as_float(extractByte(eImask, 0) << 23) * idx;
         const float    ady = __uint_as_float(extractByte(eImask, 1) << 23) * idy;
         const float    adz = __uint_as_float(extractByte(eImask, 2) << 23) * idz;
-        // Quantised plane bytes become floats WITHOUT the conversion unit (48 I2F.U8 per node saturated the XU
-        // pipe, ncu: 65 % active, the busiest pipe): one PRMT drops byte b into the mantissa of 2^15, giving
-        // 32768 + b exactly, and the bias moves into the addend: t = (32768 + b) * ad + (ao - 32768 * ad).
-        // The addend's rounding error is at most |ad| / 512 (1/512 of a quantisation cell); the entry side is
-        // pulled back and the exit side pushed out by |ad| / 256, so the test stays conservative.
-        const float aox = fmaf(-32768.0f, adx, (n0.x - org.x) * idx);
-        const float aoy = fmaf(-32768.0f, ady, (n0.y - org.y) * idy);
-        const float aoz = fmaf(-32768.0f, adz, (n0.z - org.z) * idz);
-        const float aoxN = fmaf(-0.00390625f, fabsf(adx), aox), aoxF = fmaf(0.00390625f, fabsf(adx), aox);
-        const float aoyN = fmaf(-0.00390625f, fabsf(ady), aoy), aoyF = fmaf(0.00390625f, fabsf(ady), aoy);
-        const float aozN = fmaf(-0.00390625f, fabsf(adz), aoz), aozF = fmaf(0.00390625f, fabsf(adz), aoz);
+        // quantised plane bytes -> floats with the bias folded into the addend, conservative slack (see biasedByte)
+        const float aox = fmaf(-kByteBias, adx, (n0.x - org.x) * idx);
+        const float aoy = fmaf(-kByteBias, ady, (n0.y - org.y) * idy);
+        const float aoz = fmaf(-kByteBias, adz, (n0.z - org.z) * idz);
+        const float aoxN = fmaf(-kByteSlack, fabsf(adx), aox), aoxF = fmaf(kByteSlack, fabsf(adx), aox);
+        const float aoyN = fmaf(-kByteSlack, fabsf(ady), aoy), aoyF = fmaf(kByteSlack, fabsf(ady), aoy);
+        const float aozN = fmaf(-kByteSlack, fabsf(adz), aoz), aozF = fmaf(kByteSlack, fabsf(adz), aoz);
         const uint32_t k47 = pool;
 
         cur.x = __float_as_uint(n1.x);
