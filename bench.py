@@ -40,7 +40,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "Mray/s @1080p SynthSponza (Sponza stand-in), depth 12, NEE+MIS, HDR env"
+METRIC = "Mray/s @1080p SynthSponza (Sponza stand-in), depth 12, NEE+MIS, HDR env"  # config 3; CONFIG_SCENES has the others
 NODE_BYTES, TRI_BYTES = 80, 48
 
 
@@ -50,24 +50,42 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--width", type=int, default=1920)
-    ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--depth", type=int, default=12)
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config (1-based like SURVEY.md section 8d): 3 = Sponza 1080p depth 12 (the headline metric, default), "
+                         "2 = DamagedHelmet-class 1080p depth 8, 4 = DragonDispersion-class glass 1080p depth 32, 5 = Sponza 3840x2160 (8 ranks)")
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--depth", type=int, default=0)
     ap.add_argument("--tex", type=int, default=2048)
     ap.add_argument("--detail", type=float, default=1.0)
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the frame the CPU baseline renders (0 = sized for ~12 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="warm-up + K steps only (for runs under ncu); prints no bench line")
-    return ap.parse_args()
+    a = ap.parse_args()
+    w, h, d = {2: (1920, 1080, 8), 3: (1920, 1080, 12), 4: (1920, 1080, 32), 5: (3840, 2160, 12)}[a.config]
+    a.width, a.height, a.depth = a.width or w, a.height or h, a.depth or d
+    return a
+
+
+CONFIG_SCENES = {
+    2: ("SynthHelmet(seed=1234): 46 080-triangle single mesh, one material with base colour / metallic-roughness / normal / emissive textures "
+        "(stand-in for DamagedHelmet)", "Mray/s @1080p SynthHelmet (DamagedHelmet stand-in), depth 8, NEE+MIS, HDR env"),
+    3: ("SynthSponza(seed=1234) stand-in for Sponza", "Mray/s @1080p SynthSponza (Sponza stand-in), depth 12, NEE+MIS, HDR env"),
+    4: ("SynthGlass(seed=1234): 399 424-triangle displaced sphere, transmission 1, thickness 1, attenuationDistance 0.5, dispersion 20 "
+        "(stand-in for DragonDispersion)", "Mray/s @1080p SynthGlass (DragonDispersion stand-in), depth 32, NEE+MIS, HDR env"),
+    5: ("SynthSponza(seed=1234) stand-in for Sponza", "Mray/s @2160p SynthSponza (Sponza stand-in), depth 12, NEE+MIS, HDR env"),
+}
 
 
 def build_workload(args):
-    """SynthSponza is deterministic in (seed, tex, detail); the generated arrays are cached as a pickle under
-    the system temp dir so the N=1,2,4,8 and reference-arm invocations on one box generate it once."""
+    """The synthetic scenes are deterministic in (seed, tex, detail); the generated arrays are cached as a pickle under
+    the system temp dir so the N=1,2,4,8 and reference-arm invocations on one box generate them once."""
     import pickle
     from vk_gltf_renderer_b200 import hdr, synth
     env = hdr.load_hdr(os.path.join(ROOT, "tests", "assets", "std_env.hdr"))
-    cache = os.path.join(tempfile.gettempdir(), "b200pt_synthsponza_s1234_t%d_d%g.pkl" % (args.tex, args.detail))
+    cfg = getattr(args, "config", 3)
+    name = {2: "synthhelmet", 3: "synthsponza", 4: "synthglass", 5: "synthsponza"}[cfg]
+    cache = os.path.join(tempfile.gettempdir(), "b200pt_%s_s1234_t%d_d%g.pkl" % (name, args.tex, args.detail))
     rank = int(os.environ.get("RANK", "0"))
     scn = None
     if os.path.exists(cache):
@@ -77,7 +95,12 @@ def build_workload(args):
         except Exception:
             scn = None
     if scn is None:
-        scn = synth.synth_sponza(seed=1234, tex_size=args.tex, detail=args.detail)
+        if cfg == 2:
+            scn = synth.synth_helmet(seed=1234, tex_size=args.tex)
+        elif cfg == 4:
+            scn = synth.synth_glass(seed=1234, n=632, dispersion=20.0)
+        else:
+            scn = synth.synth_sponza(seed=1234, tex_size=args.tex, detail=args.detail)
         if rank == 0:
             try:
                 tmp = cache + ".%d.tmp" % os.getpid()
@@ -90,10 +113,12 @@ def build_workload(args):
 
 
 def workload_config(args, scn, n_gpus):
-    return {"workload": "SynthSponza(seed=1234) stand-in for Sponza, %dx%d, depth %d, 1 spp/frame, std_env.hdr, NEE+MIS"
-                        % (args.width, args.height, args.depth),
+    return {"workload": "%s, %dx%d, depth %d, 1 spp/frame, std_env.hdr, NEE+MIS"
+                        % (CONFIG_SCENES[getattr(args, "config", 3)][0], args.width, args.height, args.depth),
+            "baseline_config": getattr(args, "config", 3),
             "triangles": scn.num_triangles(), "materials": len(scn.materials), "textures": len(scn.textures),
-            "texture_size": args.tex, "partition": "1 GPU" if n_gpus == 1 else "interleaved row bands x%d, scene replicated, one NCCL all-gather of the RGBA32F tiles per frame" % n_gpus,
+            "texture_size": args.tex, "partition": "1 GPU" if n_gpus == 1 else "interleaved row bands x%d, scene replicated; %d consecutive frames run as one wavefront per rank (b200pt_set_frame_batch) "
+                         "and ONE NCCL all-gather of the RGBA32F tiles per batch (accumulation is linear: SURVEY.md section 8e)" % (n_gpus, n_gpus),
             "l2_policy": "no explicit flush: every frame streams its lane's path state (248 B x %d paths per rank = %.0f MB) plus the %.0f MB image, "
                          "and consecutive frames use different lanes; the working set exceeds the 126 MB L2 for N <= 4 "
                          "(at N = 8 a rank's 64 MB tile state would fit, its 8 lanes together do not)"
@@ -221,7 +246,7 @@ def run_reference(args, emit):
         tot_r += rays
     val = tot_r / tot_t / 1e6
     cb["value"] = val
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mray/s", "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": CONFIG_SCENES[args.config][1], "value": val, "unit": "Mray/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, scn, 1),
             "cpu_baseline": cb, "e2e": {"value": val, "unit": "Mray/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -286,32 +311,46 @@ def main():
     pt = PathTracer(local)
     pt.ptMaxDepth = args.depth
     pt.onAttach(res)
-    # frames in flight: the per-rank path pool shrinks with the tile, so more lanes fit as N grows and they are what
-    # hides the latency-bound tails of a small tile (measured N=4: 3 lanes 1698, 4 -> 1832, 8 -> 2011 Mray/s)
-    lanes = 4 if world == 1 else 8
-    if not os.environ.get("B200PT_FRAMES_IN_FLIGHT"):
-        pt.set_frames_in_flight(lanes)
-    else:
+    # Frames in flight hide the latency-bound tails of a frame behind the wide bounces of the next ones.  At N > 1 a rank's tile
+    # is 1/N of the frame: N consecutive frames run as ONE wavefront (b200pt_set_frame_batch), which gives every kernel the size
+    # of a single-GPU frame and divides the launches per frame by N (round 1, per-frame launches: 0.61 efficiency at N = 8).
+    lanes = 4
+    batch = world
+    if os.environ.get("B200PT_FRAMES_IN_FLIGHT"):
         lanes = int(os.environ["B200PT_FRAMES_IN_FLIGHT"])
+    if os.environ.get("B200PT_FRAME_BATCH"):
+        batch = int(os.environ["B200PT_FRAME_BATCH"])
+    pt.set_frames_in_flight(lanes)
+    pt.set_frame_batch(batch)
     stream = torch.cuda.ExternalStream(pt.stream(), device=local)
     tile = torch.zeros((rows_per, W, 4), dtype=torch.float32, device="cuda")
     pt.set_accum_device(tile.data_ptr(), rows * W * 4)
     full = torch.empty((world * rows_per, W, 4), dtype=torch.float32, device="cuda") if world > 1 else None
-    RING = 8  # read-back ring (one pinned image per frame in flight)
-    pinned = [torch.empty((rows, W, 4), dtype=torch.float32).pin_memory() for _ in range(RING)]
+    RING = 8  # read-back ring (one pinned image per frame / batch in flight)
+    pinned = [torch.empty((H if world > 1 else rows, W, 4), dtype=torch.float32).pin_memory() for _ in range(RING if (world == 1 or rank == 0) else 0)]
 
     frame = [-1]
     image = [None]
+    pending = [0]
 
-    def step(gather=True):
+    def finish_batch():
+        """the frames submitted since the last call are enqueued (flush) and, at N > 1, the tiles all-gathered into the image"""
+        if pending[0] == 0:
+            return
+        pending[0] = 0
+        pt.flush()
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(full, tile)
+                image[0] = tiling.deinterleave(full, H, world, band) if band else full  # rank-major bands -> image order (device copy)
+
+    def step():
         frame[0] += 1
         res.frameCount = frame[0]
         pt.onRender(None, res)
-        if world > 1 and gather:
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(full, tile)
-                if band:
-                    image[0] = tiling.deinterleave(full, H, world, band)  # rank-major bands -> image order (device copy)
+        pending[0] += 1
+        if pending[0] >= batch:
+            finish_batch()
 
     def barrier():
         torch.cuda.synchronize()
@@ -326,6 +365,7 @@ def main():
         e0.record(stream)
         for _ in range(n):
             fn()
+        finish_batch()  # a partial last batch belongs to the timed steps
         e1.record(stream)
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -345,10 +385,12 @@ def main():
     if args.profile_only:
         for _ in range(args.warmup + args.steps):
             step()
+        finish_batch()
         barrier()
         return
     for _ in range(max(args.warmup, 3)):
         step()
+    finish_batch()
     # ---- pass A: device-timed throughput (headline `value`) ----
     clocks = ClockSampler(local)
     if rank == 0:
@@ -374,25 +416,61 @@ def main():
     # ring: the copy of frame f is enqueued behind its accumulate, and the host consumes frame f-depth (waits for
     # its copy, touches the pixels) while the newer frames render.  The last frames are consumed before the clock stops.
     checks = []
+    depth = min(lanes, RING) - 1  # the host consumes image k-depth while the newer ones render
 
-    depth = min(lanes, RING) - 1  # the host consumes frame f-depth while frames f-depth+1 .. f render
+    if world == 1:
+        def consume(k):
+            pt.wait_read(k % RING)
+            checks.append(float(pinned[k % RING][0, 0, 3]))
 
-    def consume(k):
-        pt.wait_read(k % RING)
-        checks.append(float(pinned[k % RING][0, 0, 3]))
+        def step_e2e(k):
+            step()
+            pt.read_accum_async(pinned[k % RING].data_ptr(), pinned[k % RING].numel(), k % RING)
+            if k >= depth:
+                consume(k - depth)
+        n_reads = args.steps
+    else:
+        # N > 1: after every batch rank 0 reads the GATHERED full-resolution image back (the frame the metric describes);
+        # the other ranks only take part in the gather
+        copies = []
 
-    def step_e2e(k):
-        step()
-        pt.read_accum_async(pinned[k % RING].data_ptr(), pinned[k % RING].numel(), k % RING)
-        if k >= depth:
-            consume(k - depth)
+        def consume(k):
+            copies[k].synchronize()
+            checks.append(float(pinned[k % RING][0, 0, 3]))
+
+        def step_e2e(k):
+            step()
+            if pending[0] == 0 and rank == 0:  # a batch just completed and was gathered
+                j = len(copies)
+                with torch.cuda.stream(stream):
+                    pinned[j % RING].copy_(image[0], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(stream)
+                copies.append(ev)
+                if j >= depth:
+                    consume(j - depth)
+        n_reads = None
     pt.reset_stats()
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
         step_e2e(k)
-    for k in range(max(args.steps - depth, 0), args.steps):
-        consume(k)
+    if world == 1:
+        for k in range(max(args.steps - depth, 0), args.steps):
+            consume(k)
+    else:
+        if pending[0]:
+            finish_batch()
+            if rank == 0:
+                with torch.cuda.stream(stream):
+                    pinned[len(copies) % RING].copy_(image[0], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(stream)
+                copies.append(ev)
+        if rank == 0:
+            for j in range(max(len(copies) - depth, 0), len(copies)):
+                consume(j)
+            n_reads = len(copies)
     barrier()
     dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -452,12 +530,15 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         _, cb, _, _ = cpu_baseline(args, scn, env)
 
-    line = {"metric": METRIC, "value": value, "unit": "Mray/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+    line = {"metric": CONFIG_SCENES[args.config][1], "value": value, "unit": "Mray/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, scn, world), "spp_per_s": spp_per_s,
             "throughput_MSps": W * H * spp_per_s / 1e6, "rays_per_sample": rays_total / (args.steps * W * H),
-            "clocks": cl, "e2e": {"value": e2e_val, "unit": "Mray/s", "h2d_bytes_per_step": 396 + 48, "d2h_bytes_per_step": rows * W * 16 * world,
+            "clocks": cl, "e2e": {"value": e2e_val, "unit": "Mray/s", "h2d_bytes_per_step": 396 + 48,
+                                  "d2h_bytes_per_step": (H * W * 16 * n_reads) // max(args.steps, 1),
+                                  "d2h_note": "N = 1: the accumulation image after every frame; N > 1: rank 0 reads the gathered full image once per batch",
                                   "ms_per_step": 1e3 * float(dt.item()) / args.steps},
+            "frames_in_flight": lanes, "frame_batch": batch,
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb}
     emit(line)
     if world > 1:

@@ -341,6 +341,18 @@ int b200pt_wait_read(b200pt_t* h, int slot);
  * or expect the accumulation image to be cleared like a resize does. */
 int b200pt_set_frames_in_flight(b200pt_t* h, int n);
 
+/* Frame batching: up to n (1..16, default 1 = off) consecutive b200pt_render_frame calls whose frame constants are identical and
+ * whose push constants only advance the way the host loop advances them (frameCount + 1, totalSamples + numSamples; the
+ * first-frame flag on the first only) are collected and run as ONE wavefront of n x pixels paths; the frames are folded into
+ * the image in frame order, so the result is bit-identical to unbatched rendering.  A call that does not continue the
+ * pending batch flushes it first; b200pt_flush, b200pt_synchronize, the read_* / get_stats / set_* / resize calls flush too.
+ * Until then the pending frames are NOT enqueued: a caller that orders its own stream work behind the image (b200pt_stream)
+ * must call b200pt_flush first.  Purpose: a multi-GPU tile is 1/N of the frame; batching N frames gives its kernels the size
+ * of a single-GPU frame and divides the kernel launches per frame by N (SURVEY.md section 8e "batch several spp per frame on
+ * multi-GPU").  Like b200pt_set_frames_in_flight it rebuilds the path pool (n x 264 B per pixel and lane) and clears the image. */
+int b200pt_set_frame_batch(b200pt_t* h, int n);
+int b200pt_flush(b200pt_t* h);
+
 /* Let the caller own the accumulation storage (e.g. a torch tensor that NCCL all-gathers):
  * dev_rgba32f must hold tile_rows*width*4 floats on the handle's device. NULL restores the
  * internal buffer. */

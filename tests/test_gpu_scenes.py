@@ -316,3 +316,52 @@ def test_headless_accepts_the_reference_harness_command_line(box_scene, std_env,
     # flags of the reference app that mean nothing here are skipped, a different render system is an error
     out = subprocess.run(cmd[:-2] + ["--vsync", "0", "--renderSystem", "1"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert out.returncode != 0 and "renderSystem" in out.stdout
+
+
+def test_frame_batching_is_bit_identical(std_env):
+    """b200pt_set_frame_batch: B consecutive frames of a static camera run as one wavefront and fold into the image in frame
+    order -- every image the unbatched renderer produces at a batch boundary (and at an explicit flush inside a batch) comes
+    out bit for bit, with textures, MASK foliage (any-hit candidates, continuation rounds) and 2 samples per pixel; the frame-0
+    selection / depth outputs come from the first frame only; a camera change mid-batch flushes the pending frames first."""
+    from vk_gltf_renderer_b200 import synth
+    from vk_gltf_renderer_b200.renderer import PathTracer, Resources
+    scn = synth.synth_sponza(tex_size=128, detail=0.05)
+
+    def run(batch, lanes, frames, spp=2):
+        res = Resources(scene=scn, hdr_rgb=std_env, camera=scn.camera, size=(160, 96))
+        pt = PathTracer(0)
+        pt.ptMaxDepth, pt.ptSamples = 6, spp
+        pt.onAttach(res)
+        pt.set_frames_in_flight(lanes)
+        pt.set_frame_batch(batch)
+        snaps = {}
+        for f in range(frames):
+            res.frameCount = f
+            pt.onRender(None, res)
+            if f in (2, 6, frames - 1):
+                snaps[f] = pt.read_accum()  # flushes a partial batch
+        ids, depth = pt.read_selection()
+        st = pt.stats()
+        pt.onDetach(res)
+        return snaps, ids, depth, st
+    ref, ids0, d0, st0 = run(1, 2, 11)
+    for batch, lanes in ((4, 1), (3, 2), (8, 2)):
+        got, ids, d, st = run(batch, lanes, 11)
+        for f in ref:
+            assert np.array_equal(got[f], ref[f]), (batch, lanes, f)
+        assert np.array_equal(ids, ids0) and np.array_equal(d, d0)
+        assert st["closestRays"] == st0["closestRays"] and st["shadowRays"] == st0["shadowRays"] and st["kernelLaunches"] < st0["kernelLaunches"]
+    # a frame that does not continue the pending batch (the accumulation restarts) flushes it and starts a new one
+    res = Resources(scene=scn, hdr_rgb=std_env, camera=scn.camera, size=(160, 96))
+    pt = PathTracer(0)
+    pt.ptMaxDepth = 6
+    pt.onAttach(res)
+    pt.set_frame_batch(4)
+    for f in (0, 1, 0, 1, 2):
+        res.frameCount = f
+        pt.onRender(None, res)
+    a = pt.read_accum()
+    pt.onDetach(res)
+    res = Resources(scene=scn, hdr_rgb=std_env, camera=scn.camera, size=(160, 96))
+    pt2, b = _gpu_render(scn, std_env, 160, 96, 3, ptMaxDepth=6)
+    assert np.array_equal(a, b)

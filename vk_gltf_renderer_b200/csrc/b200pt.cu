@@ -69,8 +69,9 @@ __device__ __forceinline__ void statAdd(unsigned long long* p, unsigned long lon
 // -------------------------------------------------------------------------------------------------
 __device__ void startSample(const PathState& P, const FrameParams& F, uint32_t i, uint32_t seed, float2 jitter, uint32_t sampleIdx)
 {
-  const uint32_t x = i % (uint32_t)F.width;
-  const uint32_t y = pixelRow(F, i);
+  const uint32_t px = pixelOf(F, i);
+  const uint32_t x = px % (uint32_t)F.width;
+  const uint32_t y = pixelRow(F, px);
   const Mat4&    projI = *reinterpret_cast<const Mat4*>(F.fi.projInv);
   const Mat4&    viewI = *reinterpret_cast<const Mat4*>(F.fi.viewInv);
   const bool     ortho = (F.fi.flags & B200PT_SCENE_IS_ORTHOGRAPHIC) != 0;
@@ -104,7 +105,7 @@ __device__ void startSample(const PathState& P, const FrameParams& F, uint32_t i
   P.rad[i] = f4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
   P.misc[i] = f4(0.0f, 0.0f, __uint_as_float(PF_SOLID), __uint_as_float(seed));
   P.medium[i] = make_uint4(0u, 0u, 0u, sampleIdx << 16);
-  if(F.pc.flags & B200PT_PT_FIRST_FRAME)
+  if(isFirstFrame(F, i))
     P.firstHit[i] = f4(1e34f, 1e34f, 1e34f, 1.0f);  // PathTracerState::firstHitPos sentinel, pt.solid = true
 }
 
@@ -135,9 +136,10 @@ __global__ void __launch_bounds__(256) k_raygen(PathState P, const __grid_consta
   const uint32_t stride = gridDim.x * blockDim.x;
   for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < F.numPaths; i += stride)
   {
-    const uint32_t x = i % (uint32_t)F.width;
-    const uint32_t y = pixelRow(F, i);
-    uint32_t       seed = xxhash32(x, y, (uint32_t)F.pc.frameCount);
+    const uint32_t px = pixelOf(F, i);
+    const uint32_t x = px % (uint32_t)F.width;
+    const uint32_t y = pixelRow(F, px);
+    uint32_t       seed = xxhash32(x, y, (uint32_t)F.pc.frameCount + frameOf(F, i));
     const float    u1 = rnd(seed), u2 = rnd(seed);
     // sampleGaussian (pathtrace_functions.h.slang:784-789), sigma = 0.4246609 px
     const float  rr = sqrtf(-2.0f * logf(fmaxf(1e-38f, u1)));
@@ -586,7 +588,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
       if(depth == 0)
       {
         flags &= ~PF_SOLID;  // tryPrimaryMissBackplate: pt.solid = false
-        if(F.pc.flags & B200PT_PT_FIRST_FRAME)
+        if(isFirstFrame(F, i))
           P.firstHit[i] = f4(dir, 0.0f);  // pt.firstHitPos = ray.Direction (pathtrace_functions.h.slang:950)
         if(F.fi.flags & B200PT_SCENE_USE_SOLID_BACKGROUND)
         {
@@ -615,7 +617,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
     const ShadeRec            srec = loadShadeRec(S.shadeRecs + __ldg(&S.shadeIdx[slot]));
 #ifdef B200PT_DEBUG
     // reference analogue: doDebug at pushConst.mouseCoord (gltf_pathtrace.slang:553-557)
-    dbgPixel = ((float)(i % (uint32_t)F.width) == F.pc.mouseCoord[0] && (float)pixelRow(F, i) == F.pc.mouseCoord[1]);
+    dbgPixel = ((float)(pixelOf(F, i) % (uint32_t)F.width) == F.pc.mouseCoord[0] && (float)pixelRow(F, pixelOf(F, i)) == F.pc.mouseCoord[1]);
     if(dbgPixel)
       printf("DBG hit t=%.9g rnode=%d prim=%d bary=%.9g %.9g org=%.9g %.9g %.9g dir=%.9g %.9g %.9g seed=%u depth=%d\n", hitT, (int)(meta.x & 0x0fffffffu), (int)meta.y, hr.y, hr.z,
              org.x, org.y, org.z, dir.x, dir.y, dir.z, seed, (int)depth);
@@ -641,7 +643,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
     pbrMat.roughness = f2(misc.x, misc.y);
 
     // first-hit capture for the NDC depth output of frame 0 (gltf_pathtrace.slang:228-232)
-    if(depth == 0 && (F.pc.flags & B200PT_PT_FIRST_FRAME))
+    if(depth == 0 && isFirstFrame(F, i))
       P.firstHit[i] = f4(hit.pos, 1.0f);
 
     radiance += pbrMat.emissive * throughput;
@@ -1026,7 +1028,7 @@ __global__ void __launch_bounds__(256) k_resolve(PathState P, const __grid_const
     if(haveShadow && (P.candInfo[path].x & 0x80000000u))
       vis = f3(0.0f);
 #ifdef B200PT_DEBUG
-    if(haveShadow && (float)(path % (uint32_t)F.width) == F.pc.mouseCoord[0] && (float)pixelRow(F, path) == F.pc.mouseCoord[1])
+    if(haveShadow && (float)(pixelOf(F, path) % (uint32_t)F.width) == F.pc.mouseCoord[0] && (float)pixelRow(F, pixelOf(F, path)) == F.pc.mouseCoord[1])
       printf("DBG shadow occluded=%d\n", (int)(vis.x == 0.0f));
 #endif
     finishPost(P, F, path, flags, seed, haveShadow, vis, qNext, cntNext, stats);
@@ -1038,32 +1040,41 @@ __global__ void __launch_bounds__(256) k_resolve(PathState P, const __grid_const
 __global__ void __launch_bounds__(256) k_accumulate(PathState P, const __grid_constant__ FrameParams F, float4* __restrict__ accum, float* __restrict__ ndcDepth)
 {
   const uint32_t stride = gridDim.x * blockDim.x;
-  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < F.numPaths; i += stride)
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < F.pixels; i += stride)
   {
-    const float4 c = P.pixSum[i] / (float)F.pc.numSamples;
-    if(F.pc.flags & B200PT_PT_FIRST_FRAME)
+    float4 img = f4(0.f, 0.f, 0.f, 0.f);
+    // the frames of a batch are folded in frame order, each with the sample counts its own push constants would have carried
+    for(int b = 0; b < F.batch; b++)
     {
-      accum[i] = c;
-      if(ndcDepth)
+      const float4 c = P.pixSum[i + (uint32_t)b * F.pixels] / (float)F.pc.numSamples;
+      if(b == 0 && (F.pc.flags & B200PT_PT_FIRST_FRAME))
       {
-        const float4 fh = P.firstHit[i];
-        float        d = 1.0f;
-        if(fh.w > 0.0f)
+        img = c;
+        if(ndcDepth)
         {
-          const Mat4&  vp = *reinterpret_cast<const Mat4*>(F.fi.viewProjMatrix);
-          const float4 clip = mul_vM(f4(fh.x, fh.y, fh.z, 1.0f), vp);
-          d = clip.z / clip.w;
+          const float4 fh = P.firstHit[i];
+          float        d = 1.0f;
+          if(fh.w > 0.0f)
+          {
+            const Mat4&  vp = *reinterpret_cast<const Mat4*>(F.fi.viewProjMatrix);
+            const float4 clip = mul_vM(f4(fh.x, fh.y, fh.z, 1.0f), vp);
+            d = clip.z / clip.w;
+          }
+          ndcDepth[i] = d;
         }
-        ndcDepth[i] = d;
+      }
+      else
+      {
+        if(b == 0)
+          img = accum[i];
+        const int    totalSamples = F.pc.totalSamples + b * F.pc.numSamples;
+        const float  total = (float)totalSamples, n = (float)F.pc.numSamples;
+        const float  after = (float)(totalSamples + F.pc.numSamples);
+        const float4 old = img;
+        img = f4((old.x * total + c.x * n) / after, (old.y * total + c.y * n) / after, (old.z * total + c.z * n) / after, (old.w * total + c.w * n) / after);
       }
     }
-    else
-    {
-      const float  total = (float)F.pc.totalSamples, n = (float)F.pc.numSamples;
-      const float  after = (float)(F.pc.totalSamples + F.pc.numSamples);
-      const float4 old = accum[i];
-      accum[i] = f4((old.x * total + c.x * n) / after, (old.y * total + c.y * n) / after, (old.z * total + c.z * n) / after, (old.w * total + c.w * n) / after);
-    }
+    accum[i] = img;
   }
 }
 
@@ -1076,7 +1087,7 @@ __global__ void __launch_bounds__(128) k_select(DevScene S, const __grid_constan
   const Mat4&    projI = *reinterpret_cast<const Mat4*>(F.fi.projInv);
   const Mat4&    viewI = *reinterpret_cast<const Mat4*>(F.fi.viewInv);
   const bool     ortho = (F.fi.flags & B200PT_SCENE_IS_ORTHOGRAPHIC) != 0;
-  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < F.numPaths; i += stride)
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < F.pixels; i += stride)
   {
     const uint32_t x = i % (uint32_t)F.width;
     const uint32_t y = pixelRow(F, i);
@@ -1303,6 +1314,13 @@ struct b200pt
   };
   static constexpr int kMaxLanes = 8;
   Lane               lanes[kMaxLanes];
+  // frame batching (b200pt_set_frame_batch): up to `batch` consecutive frames of a static camera are collected and run as one
+  // wavefront of batch x pixels paths (a multi-GPU tile is 1/N of the frame: batching N frames gives its kernels the size of a
+  // single-GPU frame and divides the launches per frame by N)
+  int                   batch = 1;
+  int                   pendingCount = 0;
+  b200pt_frame_info     pendingFi{};
+  b200pt_push_constant  pendingPc{};  // the FIRST pending frame's constants
   int                numLanes = 4;   // measured on B200 (1080p bench): 1 -> 310, 2 -> 366, 3 -> 378 Mray/s (first version); 3 -> 599, 4 -> 617, 6 -> 622 (now)
   uint64_t           frameSerial = 0;
   int                lastLane = -1;
@@ -1579,6 +1597,13 @@ void describeTexture(const b200pt_texture& src, const MipChain& mc, DevTex& dev)
 
 int gridFor(const b200pt* h, int perSM) { return h->numSMs * perSM; }
 
+}  // namespace
+extern "C" {
+static int launchFrames(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_push_constant* pc, int count);
+static int flushPending(b200pt_t* h);
+}
+namespace {
+
 // device-side error flags (DevStats::errorFlags) -> error code; the flag stays set until b200pt_reset_stats
 int checkDeviceErrors(b200pt* h)
 {
@@ -1743,6 +1768,11 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
     return B200PT_E_INVALID;
   }
   CK(cudaSetDevice(h->device));
+  {
+    const int frc = flushPending(h);
+    if(frc)
+      return frc;
+  }
   syncAll(h);
   freeScene(h);
   DevScene& S = h->S;
@@ -2250,6 +2280,11 @@ int b200pt_set_environment(b200pt_t* h, const float* rgb, int w, int hh, float* 
   if(!h || !rgb || w <= 0 || hh <= 0)
     return B200PT_E_INVALID;
   CK(cudaSetDevice(h->device));
+  {
+    const int frc = flushPending(h);
+    if(frc)
+      return frc;
+  }
   syncAll(h);
   const size_t n = (size_t)w * hh;
   // importance = texel solid angle * max(r,g,b); Vose alias table; pdf stored in alpha
@@ -2338,9 +2373,15 @@ int b200pt_resize(b200pt_t* h, int width, int height, int tile_y0, int tile_rows
     return B200PT_E_INVALID;
   }
   CK(cudaSetDevice(h->device));
+  {
+    const int frc = flushPending(h);
+    if(frc)
+      return frc;
+  }
   syncAll(h);
   freePool(h);
-  const size_t n = (size_t)width * tile_rows;
+  const size_t n = (size_t)width * tile_rows;          // pixels of the tile: image-sized buffers
+  const size_t nPool = n * (size_t)std::max(h->batch, 1);  // path slots per lane
   // nothing of the handle's geometry is committed before every allocation has succeeded: a failed resize leaves
   // numPaths == 0 and null pointers, so later calls fail their guards instead of touching freed memory
   auto fail = [&](int rc) {
@@ -2350,12 +2391,12 @@ int b200pt_resize(b200pt_t* h, int width, int height, int tile_y0, int tile_rows
   for(int l = 0; l < h->numLanes; l++)
   {
     b200pt::Lane& L = h->lanes[l];
-    const int     rc = allocPathState(h, h->poolAllocs, n, L.P);
+    const int     rc = allocPathState(h, h->poolAllocs, nPool, L.P);
     if(rc)
       return fail(rc);
     for(int k = 0; k < 6; k++)
     {
-      if(cudaMalloc((void**)&L.dQ[k], n * sizeof(uint32_t)) != cudaSuccess)
+      if(cudaMalloc((void**)&L.dQ[k], nPool * sizeof(uint32_t)) != cudaSuccess)
       {
         cudaGetLastError();
         L.dQ[k] = nullptr;
@@ -2432,6 +2473,11 @@ int b200pt_set_accum_device(b200pt_t* h, float* dev, size_t num_floats)
     h->dAccum = h->dAccumOwned;
     return B200PT_OK;
   }
+  {
+    const int frc = flushPending(h);
+    if(frc)
+      return frc;
+  }
   if(num_floats < (size_t)h->numPaths * 4)
   {
     h->err = "b200pt_set_accum_device: buffer too small";
@@ -2457,6 +2503,11 @@ int b200pt_read_accum(b200pt_t* h, float* host, size_t num_floats)
   if(!h || h->numPaths == 0 || !host || num_floats < (size_t)h->numPaths * 4)
     return B200PT_E_INVALID;
   CK(cudaSetDevice(h->device));
+  {
+    const int frc = flushPending(h);
+    if(frc)
+      return frc;
+  }
   CK(cudaMemcpyAsync(host, h->dAccum, (size_t)h->numPaths * 16, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return B200PT_OK;
@@ -2467,6 +2518,11 @@ int b200pt_read_selection(b200pt_t* h, uint32_t* host_object_ids, float* host_nd
   if(!h || h->numPaths == 0 || num_pixels < (size_t)h->numPaths || (!host_object_ids && !host_ndc_depth))
     return B200PT_E_INVALID;
   CK(cudaSetDevice(h->device));
+  {
+    const int frc = flushPending(h);
+    if(frc)
+      return frc;
+  }
   if(host_object_ids)
     CK(cudaMemcpyAsync(host_object_ids, h->dSelect, (size_t)h->numPaths * 4, cudaMemcpyDeviceToHost, h->stream));
   if(host_ndc_depth)
@@ -2491,6 +2547,11 @@ int b200pt_read_accum_async(b200pt_t* h, float* host, size_t num_floats, int slo
   if(!h || h->numPaths == 0 || !host || num_floats < (size_t)h->numPaths * 4 || slot < 0 || slot >= 8)
     return B200PT_E_INVALID;
   CK(cudaSetDevice(h->device));
+  {
+    const int frc = flushPending(h);
+    if(frc)
+      return frc;
+  }
   if(!h->readDone[slot])
     CK(cudaEventCreateWithFlags(&h->readDone[slot], cudaEventDisableTiming));
   else
@@ -2529,11 +2590,41 @@ int b200pt_set_frames_in_flight(b200pt_t* h, int n)
   return rc;
 }
 
+int b200pt_set_frame_batch(b200pt_t* h, int n)
+{
+  if(!h || n < 1 || n > 16)
+    return B200PT_E_INVALID;
+  if(n == h->batch)
+    return B200PT_OK;
+  {
+    const int frc = flushPending(h);
+    if(frc)
+      return frc;
+  }
+  h->batch = n;
+  if(h->numPaths == 0)
+    return B200PT_OK;
+  float4* const user = (h->dAccum != h->dAccumOwned) ? h->dAccum : nullptr;
+  int           rc;
+  if(h->bandWorld > 1)
+    rc = b200pt_resize_interleaved(h, h->width, h->height, h->bandRows, h->bandWorld, h->bandRank);
+  else
+    rc = b200pt_resize(h, h->width, h->height, h->tileY0, h->tileRows);
+  if(rc == B200PT_OK && user)
+    h->dAccum = user;
+  return rc;
+}
+
 int b200pt_synchronize(b200pt_t* h)
 {
   if(!h)
     return B200PT_E_INVALID;
   CK(cudaSetDevice(h->device));
+  {
+    const int frc = flushPending(h);
+    if(frc)
+      return frc;
+  }
   syncAll(h);
   return checkDeviceErrors(h);
 }
@@ -2543,6 +2634,11 @@ int b200pt_set_profiling(b200pt_t* h, int enabled)
   if(!h)
     return B200PT_E_INVALID;
   CK(cudaSetDevice(h->device));
+  {
+    const int frc = flushPending(h);
+    if(frc)
+      return frc;
+  }
   flushEvents(h);
   h->profiling = enabled != 0;
   if(h->profiling && h->evPool.empty())
@@ -2587,6 +2683,54 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
     h->err = "b200pt_render_frame: bad numSamples / maxDepth / imageSize";
     return B200PT_E_INVALID;
   }
+  if(h->batch <= 1)
+    return launchFrames(h, fi, pc, 1);
+  // frame batching: collect consecutive frames of a static camera (same frame constants; push constants that differ only by
+  // the frame / sample counters advancing like the host loop advances them) and run them as one wavefront
+  if(h->pendingCount > 0)
+  {
+    const b200pt_push_constant& p0 = h->pendingPc;
+    b200pt_push_constant        expect = p0;
+    expect.frameCount = p0.frameCount + h->pendingCount;
+    expect.totalSamples = p0.totalSamples + h->pendingCount * p0.numSamples;
+    expect.flags = p0.flags & ~B200PT_PT_FIRST_FRAME;
+    if(memcmp(&h->pendingFi, fi, sizeof(*fi)) != 0 || memcmp(&expect, pc, sizeof(*pc)) != 0)
+    {
+      const int rc = flushPending(h);
+      if(rc)
+        return rc;
+    }
+  }
+  if(h->pendingCount == 0)
+  {
+    h->pendingFi = *fi;
+    h->pendingPc = *pc;
+  }
+  h->pendingCount++;
+  if(h->pendingCount >= h->batch)
+    return flushPending(h);
+  return B200PT_OK;
+}
+
+static int flushPending(b200pt_t* h)
+{
+  if(h->pendingCount == 0)
+    return B200PT_OK;
+  const int n = h->pendingCount;
+  h->pendingCount = 0;
+  return launchFrames(h, &h->pendingFi, &h->pendingPc, n);
+}
+
+int b200pt_flush(b200pt_t* h)
+{
+  if(!h)
+    return B200PT_E_INVALID;
+  return flushPending(h);
+}
+
+// enqueues the launch chain of `count` consecutive frames (count > 1: one batched wavefront, FrameParams::batch)
+static int launchFrames(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_push_constant* pc, int count)
+{
   CK(cudaSetDevice(h->device));
   FrameParams F;
   F.fi = *fi;
@@ -2598,7 +2742,9 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
   F.bandRows = h->bandRows;
   F.bandWorld = h->bandWorld;
   F.bandRank = h->bandRank;
-  F.numPaths = h->numPaths;
+  F.pixels = h->numPaths;
+  F.batch = count;
+  F.numPaths = h->numPaths * (uint32_t)count;
 
   const int     laneIdx = (int)(h->frameSerial++ % (uint64_t)h->numLanes);
   b200pt::Lane& L = h->lanes[laneIdx];
@@ -2758,6 +2904,11 @@ int b200pt_get_stats(b200pt_t* h, b200pt_stats* out)
   if(!h || !out)
     return B200PT_E_INVALID;
   CK(cudaSetDevice(h->device));
+  {
+    const int frc = flushPending(h);
+    if(frc)
+      return frc;
+  }
   syncAll(h);
   DevStats d{};
   CK(cudaMemcpy(&d, h->dStats, sizeof(d), cudaMemcpyDeviceToHost));
@@ -2794,6 +2945,11 @@ int b200pt_reset_stats(b200pt_t* h)
   if(!h)
     return B200PT_E_INVALID;
   CK(cudaSetDevice(h->device));
+  {
+    const int frc = flushPending(h);
+    if(frc)
+      return frc;
+  }
   syncAll(h);
   CK(cudaMemset(h->dStats, 0, sizeof(DevStats)));
   flushEvents(h);

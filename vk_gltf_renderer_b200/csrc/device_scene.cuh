@@ -111,13 +111,23 @@ struct FrameParams
   int                  width, height;
   int                  tileY0, tileRows;
   int                  bandRows, bandWorld, bandRank;  // interleaved tiles: bandWorld > 1 (then tileY0 == 0)
-  uint32_t             numPaths;  // tileRows * width
+  uint32_t             numPaths;  // path slots of this launch chain = pixels * batch
+  // Frame batching (b200pt_set_frame_batch): `batch` consecutive frames of a static camera run as ONE wavefront.  Slot i
+  // belongs to pixel i % pixels of frame pc.frameCount + i / pixels; pc holds the FIRST frame's constants, frame b adds b to
+  // frameCount and b * numSamples to totalSamples (what the host loop would have passed, src/renderer_pathtracer.cpp:1496-1574).
+  uint32_t             pixels;    // tileRows * width
+  int                  batch;     // >= 1
 };
 
-// global pixel row of path slot i (seeds always use global coordinates)
-PT_D uint32_t pixelRow(const FrameParams& F, uint32_t i)
+PT_D uint32_t pixelOf(const FrameParams& F, uint32_t i) { return F.batch > 1 ? i % F.pixels : i; }
+PT_D uint32_t frameOf(const FrameParams& F, uint32_t i) { return F.batch > 1 ? i / F.pixels : 0u; }
+// the slot renders the first frame of an accumulation (its sample overwrites the image, frame-0 outputs are written)
+PT_D bool isFirstFrame(const FrameParams& F, uint32_t i) { return (F.pc.flags & B200PT_PT_FIRST_FRAME) != 0 && (F.batch <= 1 || i < F.pixels); }
+
+// global pixel row of tile pixel p (seeds always use global coordinates)
+PT_D uint32_t pixelRow(const FrameParams& F, uint32_t p)
 {
-  const uint32_t l = i / (uint32_t)F.width;
+  const uint32_t l = p / (uint32_t)F.width;
   if(F.bandWorld <= 1)
     return (uint32_t)F.tileY0 + l;
   return ((l / (uint32_t)F.bandRows) * (uint32_t)F.bandWorld + (uint32_t)F.bandRank) * (uint32_t)F.bandRows + l % (uint32_t)F.bandRows;

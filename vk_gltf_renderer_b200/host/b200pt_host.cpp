@@ -480,6 +480,10 @@ void PathTracer::synchronize() { check(b200pt_synchronize(m_h), "b200pt_synchron
 
 void PathTracer::setFramesInFlight(int n) { check(b200pt_set_frames_in_flight(m_h, n), "b200pt_set_frames_in_flight"); }
 
+void PathTracer::setFrameBatch(int n) { check(b200pt_set_frame_batch(m_h, n), "b200pt_set_frame_batch"); }
+
+void PathTracer::flush() { check(b200pt_flush(m_h), "b200pt_flush"); }
+
 b200pt_stats PathTracer::stats()
 {
   b200pt_stats s{};

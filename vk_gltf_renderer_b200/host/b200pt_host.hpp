@@ -141,6 +141,8 @@ public:
   std::vector<float> readAccum();
   void               synchronize();
   void               setFramesInFlight(int n);
+  void               setFrameBatch(int n);  // b200pt_set_frame_batch
+  void               flush();               // b200pt_flush
   b200pt_stats       stats();
   void               resetStats();
   b200pt_t*          handle() { return m_h; }

@@ -94,7 +94,7 @@ int main(int argc, char** argv)
 {
   std::string scenePath, hdrPath, outPath, rawPath, tmpBlob;
   int         width = 1920, height = 1080, frames = 16, warmupFrames = 1, framesInFlight = 0;  // warm-up: src/benchmarking.hpp:128
-  int         adaptiveSampling = 0;
+  int         adaptiveSampling = 0, frameBatch = 0;
   Resources   res;
   PathTracer  pt;
   try
@@ -137,6 +137,8 @@ int main(int argc, char** argv)
         res.cudaDevice = std::stoi(next());
       else if(a == "--framesInFlight")
         framesInFlight = std::stoi(next());
+      else if(a == "--frameBatch")
+        frameBatch = std::stoi(next());
       else if(a == "--maxFrames")
         res.settings.maxFrames = std::stoi(next());
       else if(a == "--hdrEnvIntensity")
@@ -197,6 +199,8 @@ int main(int argc, char** argv)
     pt.onAttach(res);
     if(framesInFlight > 0)
       pt.setFramesInFlight(framesInFlight);
+    if(frameBatch > 0)
+      pt.setFrameBatch(frameBatch);
 
     // frame loop with the reference's warm-up split (benchmarking.cpp: measured timer starts after warmupFrames)
     using clock = std::chrono::steady_clock;

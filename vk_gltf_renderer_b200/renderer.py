@@ -209,6 +209,13 @@ class PathTracer:
     def set_frames_in_flight(self, n):
         self._ck(self._L.b200pt_set_frames_in_flight(self._h, n), "b200pt_set_frames_in_flight")
 
+    def set_frame_batch(self, n):
+        """collect up to n consecutive frames of a static camera into one wavefront (include/b200pt.h)"""
+        self._ck(self._L.b200pt_set_frame_batch(self._h, n), "b200pt_set_frame_batch")
+
+    def flush(self):
+        self._ck(self._L.b200pt_flush(self._h), "b200pt_flush")
+
     def accum_device_ptr(self):
         p, n = C.c_void_p(), C.c_size_t()
         self._ck(self._L.b200pt_get_accum_device(self._h, C.byref(p), C.byref(n)), "b200pt_get_accum_device")

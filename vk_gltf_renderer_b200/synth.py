@@ -356,6 +356,40 @@ def synth_layers(seed=1234, layers=14, tex_size=64, blend=False, tinted=False):
     return scn
 
 
+def synth_helmet(seed=1234, tex_size=2048):
+    """Stand-in for DamagedHelmet (BASELINE config 2; the Khronos asset is not available offline): ONE mesh of 46 080 triangles with
+    ONE material that binds base colour (sRGB), metallic-roughness, normal and emissive textures of tex_size^2, floating in the
+    environment (no floor), camera framing it like the sample viewer does."""
+    rng = np.random.default_rng(seed)
+    scn = Scene()
+    k = rng.random(8) * 6.28
+
+    def shell(u, v):
+        th, a = v * math.pi, u * 2 * math.pi
+        r = 1.0 + 0.10 * np.sin(4 * a + k[0]) * np.sin(3 * th + k[1]) + 0.05 * np.sin(9 * a + k[2]) * np.sin(7 * th + k[3]) + 0.02 * np.sin(23 * a + k[4]) * np.sin(19 * th + k[5])
+        return _xyz(r * np.sin(th) * np.cos(a), -r * np.cos(th), -r * np.sin(th) * np.sin(a) * 1.15)
+    pos, nrm, uv, tan, idx = param_surface(shell, 160, 144, (2, 1))
+    assert len(idx) == 46080
+    base, mr, nm = make_texture_set(tex_size, rng, (0.62, 0.58, 0.52))
+    em = np.zeros((tex_size, tex_size, 4), np.uint8)
+    glow = value_noise(tex_size, 5, rng, 1)[..., 0] > 0.72
+    em[glow] = (40, 160, 255, 255)
+    em[..., 3] = 255
+    mat = scn.add_material(pbrBaseColorFactor=[1, 1, 1, 1], pbrRoughnessFactor=1.0, pbrMetallicFactor=1.0, emissiveFactor=[1.0, 1.0, 1.0],
+                           pbrBaseColorTexture=scn.add_texture_info(scn.add_texture(base, srgb=True)),
+                           pbrMetallicRoughnessTexture=scn.add_texture_info(scn.add_texture(mr)),
+                           normalTexture=scn.add_texture_info(scn.add_texture(nm)),
+                           emissiveTexture=scn.add_texture_info(scn.add_texture(em, srgb=True)))
+    scn.add_node(scn.add_primitive(pos, idx, normals=nrm, uv0=uv, tangents=tan), mat)
+    cam = Camera()
+    cam.eye = np.array([0.0, 0.3, 3.4], np.float32)
+    cam.center = np.array([0.0, 0.0, 0.0], np.float32)
+    cam.yfov = math.radians(45.0)
+    cam.znear, cam.zfar = 0.05, 100.0
+    scn.camera = cam
+    return scn
+
+
 def _sphere(cx, cy, cz, r, n=24, uv_scale=(2, 1)):
     def f(u, v):
         th, a = v * math.pi, u * 2 * math.pi
