@@ -311,11 +311,12 @@ def main():
     pt = PathTracer(local)
     pt.ptMaxDepth = args.depth
     pt.onAttach(res)
-    # Frames in flight hide the latency-bound tails of a frame behind the wide bounces of the next ones.  At N > 1 a rank's tile
-    # is 1/N of the frame: N consecutive frames run as ONE wavefront (b200pt_set_frame_batch), which gives every kernel the size
-    # of a single-GPU frame and divides the launches per frame by N (round 1, per-frame launches: 0.61 efficiency at N = 8).
+    # Frames in flight hide the latency-bound tails of a frame behind the wide bounces of the next ones; frame batching
+    # (b200pt_set_frame_batch) runs consecutive frames as ONE wavefront, which makes the tails of a frame wider and divides the
+    # launches per frame.  At N > 1 a rank's tile is 1/N of the frame, so the batch grows with N and every kernel keeps the size it
+    # has on one GPU (round 1, one frame per launch chain: 0.61 efficiency at N = 8).
     lanes = 4
-    batch = world
+    batch = min(16, 4 * world)  # measured at N = 1 (r02g): batch 1 -> 821, 2 -> 873, 4 -> 906 Mray/s with 4 frames in flight
     if os.environ.get("B200PT_FRAMES_IN_FLIGHT"):
         lanes = int(os.environ["B200PT_FRAMES_IN_FLIGHT"])
     if os.environ.get("B200PT_FRAME_BATCH"):
@@ -418,65 +419,67 @@ def main():
     checks = []
     depth = min(lanes, RING) - 1  # the host consumes image k-depth while the newer ones render
 
-    if world == 1:
-        def consume(k):
-            pt.wait_read(k % RING)
-            checks.append(float(pinned[k % RING][0, 0, 3]))
+    # After every batch the image is read back into pinned host memory (N > 1: rank 0 reads the GATHERED full-resolution image,
+    # the frame the metric describes; the other ranks only take part in the gather).  A batch's frames complete together, so the
+    # image after an intermediate frame never exists: one read per batch is every result there is.  (The reference's headless run
+    # reads its image back once, at the end.)  The per-frame variant is measured separately below.
+    copies = []
+    src_image = (lambda: image[0]) if world > 1 else (lambda: tile)
 
-        def step_e2e(k):
-            step()
-            pt.read_accum_async(pinned[k % RING].data_ptr(), pinned[k % RING].numel(), k % RING)
-            if k >= depth:
-                consume(k - depth)
-        n_reads = args.steps
-    else:
-        # N > 1: after every batch rank 0 reads the GATHERED full-resolution image back (the frame the metric describes);
-        # the other ranks only take part in the gather
-        copies = []
+    def consume(k):
+        copies[k].synchronize()
+        checks.append(float(pinned[k % RING][0, 0, 3]))
 
-        def consume(k):
-            copies[k].synchronize()
-            checks.append(float(pinned[k % RING][0, 0, 3]))
+    def read_back():
+        j = len(copies)
+        with torch.cuda.stream(stream):
+            pinned[j % RING].copy_(src_image(), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        copies.append(ev)
+        if j >= depth:
+            consume(j - depth)
 
-        def step_e2e(k):
-            step()
-            if pending[0] == 0 and rank == 0:  # a batch just completed and was gathered
-                j = len(copies)
-                with torch.cuda.stream(stream):
-                    pinned[j % RING].copy_(image[0], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(stream)
-                copies.append(ev)
-                if j >= depth:
-                    consume(j - depth)
-        n_reads = None
+    def step_e2e(k):
+        step()
+        if pending[0] == 0 and rank == 0:  # a batch just completed (and was gathered)
+            read_back()
     pt.reset_stats()
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
         step_e2e(k)
-    if world == 1:
-        for k in range(max(args.steps - depth, 0), args.steps):
-            consume(k)
-    else:
-        if pending[0]:
-            finish_batch()
-            if rank == 0:
-                with torch.cuda.stream(stream):
-                    pinned[len(copies) % RING].copy_(image[0], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(stream)
-                copies.append(ev)
+    if pending[0]:
+        finish_batch()
         if rank == 0:
-            for j in range(max(len(copies) - depth, 0), len(copies)):
-                consume(j)
-            n_reads = len(copies)
+            read_back()
+    if rank == 0:
+        for j in range(max(len(copies) - depth, 0), len(copies)):
+            consume(j)
+    n_reads = len(copies)
     barrier()
     dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     re = rays_now()
     e2e_val = re[0] / float(dt.item()) / 1e6
+    # the same with the image read back after EVERY frame (N = 1 only): each read flushes the pending batch, so this is the
+    # unbatched renderer end to end
+    e2e_per_frame = None
+    if world == 1:
+        pt.reset_stats()
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            step()
+            pt.read_accum_async(pinned[k % RING].data_ptr(), pinned[k % RING].numel(), k % RING)
+            pending[0] = 0
+            if k >= depth:
+                pt.wait_read((k - depth) % RING)
+        for k in range(max(args.steps - depth, 0), args.steps):
+            pt.wait_read(k % RING)
+        barrier()
+        e2e_per_frame = rays_now()[0] / (time.perf_counter() - t0) / 1e6
 
     if rank != 0:
         if world > 1:
@@ -536,7 +539,9 @@ def main():
             "throughput_MSps": W * H * spp_per_s / 1e6, "rays_per_sample": rays_total / (args.steps * W * H),
             "clocks": cl, "e2e": {"value": e2e_val, "unit": "Mray/s", "h2d_bytes_per_step": 396 + 48,
                                   "d2h_bytes_per_step": (H * W * 16 * n_reads) // max(args.steps, 1),
-                                  "d2h_note": "N = 1: the accumulation image after every frame; N > 1: rank 0 reads the gathered full image once per batch",
+                                  "d2h_note": "the image is read back once per batch of frame_batch frames (rank 0 reads the gathered full image); "
+                                              "per_frame_readback_value = the same metric with a read after every frame (N = 1)",
+                                  "per_frame_readback_value": e2e_per_frame,
                                   "ms_per_step": 1e3 * float(dt.item()) / args.steps},
             "frames_in_flight": lanes, "frame_batch": batch,
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb}
