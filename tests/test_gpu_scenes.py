@@ -365,3 +365,16 @@ def test_frame_batching_is_bit_identical(std_env):
     res = Resources(scene=scn, hdr_rgb=std_env, camera=scn.camera, size=(160, 96))
     pt2, b = _gpu_render(scn, std_env, 160, 96, 3, ptMaxDepth=6)
     assert np.array_equal(a, b)
+
+
+def test_material_sorted_shade_queue_does_not_change_the_image(std_env, monkeypatch):
+    """B200PT_SORT_SHADE=1 buckets every bounce's shade queue by the material of the hit (counting sort: k_sort_count / k_sort_scan /
+    k_sort_scatter).  Paths are independent of their place in the queue: the image and the ray counters are bit-identical."""
+    from vk_gltf_renderer_b200 import synth
+    scn = synth.synth_sponza(tex_size=128, detail=0.05)
+    pt0, a = _gpu_render(scn, std_env, 200, 120, 5, ptMaxDepth=6)
+    monkeypatch.setenv("B200PT_SORT_SHADE", "1")
+    pt1, b = _gpu_render(scn, std_env, 200, 120, 5, ptMaxDepth=6)
+    assert np.array_equal(a, b)
+    s0, s1 = pt0.stats(), pt1.stats()
+    assert s0["closestRays"] == s1["closestRays"] and s0["shadedHits"] == s1["shadedHits"] and s1["kernelLaunches"] > s0["kernelLaunches"]

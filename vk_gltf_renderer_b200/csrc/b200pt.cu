@@ -1009,6 +1009,94 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathStat
     atomicAdd(&stats->shadowRays, (unsigned long long)count);
 }
 
+// ---- material-sorted shade queue (north star: "material-sorted shade queues to tame divergence") -------------------------
+// Counting sort of the bounce's path queue by the material of the hit (misses last): k_sort_count builds the histogram,
+// k_sort_scan turns it into bucket cursors, k_sort_scatter writes the queue bucket by bucket.  Histogram and offsets are
+// aggregated per block in shared memory (a handful of buckets, millions of paths: one global atomic per path would serialise
+// on the bucket counters).  Paths are independent, so the order inside a bucket (not deterministic) does not change any pixel.
+constexpr int kSortMaxBuckets = 1024;
+constexpr int kSortItems = 4;  // paths per thread per pass
+
+__device__ __forceinline__ uint32_t shadeKey(const PathState& P, const DevScene& S, uint32_t path, uint32_t nb)
+{
+  const uint32_t slot = __float_as_uint(P.hit[path].w);
+  return slot == 0xFFFFFFFFu ? nb - 1u : min(__ldg(&S.matOfSlot[slot]), nb - 2u);
+}
+
+__global__ void __launch_bounds__(256) k_sort_count(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn, uint32_t* bucketCount, uint32_t nb)
+{
+  __shared__ uint32_t sCnt[kSortMaxBuckets];
+  for(uint32_t b = threadIdx.x; b < nb; b += blockDim.x)
+    sCnt[b] = 0;
+  __syncthreads();
+  const uint32_t count = *cntIn;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for(uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
+    atomicAdd(&sCnt[shadeKey(P, S, q[k], nb)], 1u);
+  __syncthreads();
+  for(uint32_t b = threadIdx.x; b < nb; b += blockDim.x)
+    if(sCnt[b])
+      atomicAdd(&bucketCount[b], sCnt[b]);
+}
+
+// exclusive scan of the (few) bucket counts into cursors; the counts are zeroed for the next bounce
+__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t* bucketCount, uint32_t* bucketCursor, uint32_t nb)
+{
+  __shared__ uint32_t s[kSortMaxBuckets];
+  const uint32_t      t = threadIdx.x;
+  s[t] = t < nb ? bucketCount[t] : 0u;
+  __syncthreads();
+  for(uint32_t d = 1; d < kSortMaxBuckets; d <<= 1)
+  {
+    const uint32_t v = t >= d ? s[t - d] : 0u;
+    __syncthreads();
+    s[t] += v;
+    __syncthreads();
+  }
+  if(t < nb)
+  {
+    bucketCursor[t] = s[t] - bucketCount[t];
+    bucketCount[t] = 0u;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_sort_scatter(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn, uint32_t* bucketCursor,
+                                                      uint32_t* __restrict__ qSorted, uint32_t nb)
+{
+  __shared__ uint32_t sCnt[kSortMaxBuckets], sBase[kSortMaxBuckets];
+  const uint32_t      count = *cntIn;
+  const uint32_t      chunk = blockDim.x * kSortItems;
+  for(uint32_t base = blockIdx.x * chunk; base < count; base += gridDim.x * chunk)  // block-uniform trip count
+  {
+    for(uint32_t b = threadIdx.x; b < nb; b += blockDim.x)
+      sCnt[b] = 0;
+    __syncthreads();
+    uint32_t path[kSortItems], key[kSortItems], off[kSortItems];
+#pragma unroll
+    for(int i = 0; i < kSortItems; i++)
+    {
+      const uint32_t k = base + (uint32_t)i * blockDim.x + threadIdx.x;
+      key[i] = 0xFFFFFFFFu;
+      if(k < count)
+      {
+        path[i] = q[k];
+        key[i] = shadeKey(P, S, path[i], nb);
+        off[i] = atomicAdd(&sCnt[key[i]], 1u);
+      }
+    }
+    __syncthreads();
+    for(uint32_t b = threadIdx.x; b < nb; b += blockDim.x)
+      if(sCnt[b])
+        sBase[b] = atomicAdd(&bucketCursor[b], sCnt[b]);
+    __syncthreads();
+#pragma unroll
+    for(int i = 0; i < kSortItems; i++)
+      if(key[i] != 0xFFFFFFFFu)
+        qSorted[sBase[key[i]] + off[i]] = path[i];
+    __syncthreads();
+  }
+}
+
 // pathTrace() tail for every path that survived shading (gltf_pathtrace.slang:462-485), one thread per path: the
 // delayed NEE contribution (already scaled by the any-hit transmission in k_alpha<true>; an opaque occluder
 // zeroes it here), Russian roulette and depth++ in finishPost.
@@ -1280,6 +1368,7 @@ struct b200pt
   bool                haveScene = false;
   bool                hasVolume = false;
   int                 refillThreshold = kRefillThresholdDefault, postponeShift = 2;  // B200PT_REFILL / B200PT_POSTPONE env overrides (tuning)
+  bool                sortShade = false;  // B200PT_SORT_SHADE=1: material-sorted shade queue (measured)
   bool                leanShade = false;  // scene fits the FEAT_LEAN shade variant (scene_feature_detection analogue)
   uint32_t            featureMask = 0;
   uint64_t            nodeBytes = 0, triBytes = 0;
@@ -1307,6 +1396,7 @@ struct b200pt
     PathState    P{};
     uint32_t*    dQ[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // trace ping/pong, post, shadow, alpha, continuation
     uint32_t*    dCounters = nullptr;
+    uint32_t*    dBuckets = nullptr;  // material-sorted shade queue: [0..1023] bucket counts, [1024..2047] bucket cursors
     uint32_t*    hCount = nullptr;   // pinned
     cudaEvent_t  done = nullptr;     // lane stream: all bounces of the lane's frame enqueued before it
     cudaEvent_t  freed = nullptr;    // main stream: k_accumulate has consumed the lane's pixSum
@@ -1649,6 +1739,8 @@ int b200pt_create(b200pt_t** out, int cuda_device)
     h->refillThreshold = atoi(e);
   if(const char* e = getenv("B200PT_POSTPONE"))
     h->postponeShift = atoi(e);
+  if(const char* e = getenv("B200PT_SORT_SHADE"))
+    h->sortShade = atoi(e) != 0;
   bool ok = true;
   auto need = [&](cudaError_t e) { ok = ok && (e == cudaSuccess); };
   cudaDeviceProp prop{};
@@ -1685,6 +1777,9 @@ int b200pt_create(b200pt_t** out, int cuda_device)
     need(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
     need(cudaEventCreateWithFlags(&L.freed, cudaEventDisableTiming));
     need(cudaMalloc((void**)&L.dCounters, sizeof(uint32_t) * 13 * kMaxIters));
+    need(cudaMalloc((void**)&L.dBuckets, sizeof(uint32_t) * 2 * kSortMaxBuckets));
+    if(ok)
+      need(cudaMemset(L.dBuckets, 0, sizeof(uint32_t) * 2 * kSortMaxBuckets));
     need(cudaMallocHost((void**)&L.hCount, sizeof(uint32_t) * 4));
   }
   {
@@ -1727,6 +1822,7 @@ void b200pt_destroy(b200pt_t* h)
   {
     b200pt::Lane& L = h->lanes[l];
     cudaFree(L.dCounters);
+    cudaFree(L.dBuckets);
     if(L.hCount)
       cudaFreeHost(L.hCount);
     if(L.done)
@@ -2168,14 +2264,25 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
       memcpy(&gid, &bvh.tris[(size_t)k * 12 + 11], 4);
       idxOfSlot[k] = recBase[s->renderNodes[flat[gid].rnode].renderPrimID] + flat[gid].prim;
     }
+    std::vector<uint32_t> matOfSlot(bvh.numTris, 0u);
+    for(uint32_t k = 0; k < bvh.numTris; k++)
+    {
+      uint32_t gid;
+      memcpy(&gid, &bvh.tris[(size_t)k * 12 + 11], 4);
+      matOfSlot[k] = (uint32_t)std::max(0, s->renderNodes[flat[gid].rnode].materialID);
+    }
     ShadeRec* dRecs;
-    uint32_t* dIdx;
+    uint32_t *dIdx, *dMat;
     if((rc = upload(h, h->sceneAllocs, recs.data(), recs.size(), &dRecs)))
       return rc;
     if((rc = upload(h, h->sceneAllocs, idxOfSlot.data(), idxOfSlot.size(), &dIdx)))
       return rc;
+    if((rc = upload(h, h->sceneAllocs, matOfSlot.data(), matOfSlot.size(), &dMat)))
+      return rc;
     S.shadeRecs = dRecs;
     S.shadeIdx = dIdx;
+    S.matOfSlot = dMat;
+    S.numMaterials = (int)s->numMaterials;
   }
 
   // ---- alpha-triangle records (device_scene.cuh: AlphaRec), one per non-opaque triangle in bvhA's leaf order ----
@@ -2828,11 +2935,21 @@ static int launchFrames(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
           timed(tTrace, [&] { k_trace<<<gP, 128, 0, st>>>(L.P, h->S, L.dQ[5], &cntCont[it], &workCont[it], L.dQ[4], &cntAlpha1[it], h->dStats, h->refillThreshold, h->postponeShift, 1); });
           timed(tAnyHit, [&] { k_alpha<false><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlpha1[it], nullptr, nullptr, h->dStats, TRACE_CONT); });
         }
+        const uint32_t* qShade = qT;
+        if(h->sortShade && h->S.numMaterials + 1 <= kSortMaxBuckets)
+        {
+          // dQ[4] (the any-hit queue) is free between the closest-hit any-hit kernels and the shadow walk
+          const uint32_t nb = (uint32_t)h->S.numMaterials + 1u;
+          timed(tOther, [&] { k_sort_count<<<gridFor(h, 4), 256, 0, st>>>(L.P, h->S, qT, &cntTrace[it], L.dBuckets, nb); });
+          timed(tOther, [&] { k_sort_scan<<<1, kSortMaxBuckets, 0, st>>>(L.dBuckets, L.dBuckets + kSortMaxBuckets, nb); });
+          timed(tOther, [&] { k_sort_scatter<<<gridFor(h, 4), 256, 0, st>>>(L.P, h->S, qT, &cntTrace[it], L.dBuckets + kSortMaxBuckets, L.dQ[4], nb); });
+          qShade = L.dQ[4];
+        }
         timed(tShade, [&] {
           if(h->leanShade)
-            k_shade<FEAT_LEAN><<<gP * 128 / SHADE_BLOCK, SHADE_BLOCK, 2048, st>>>(L.P, h->S, F, qT, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
+            k_shade<FEAT_LEAN><<<gP * 128 / SHADE_BLOCK, SHADE_BLOCK, 2048, st>>>(L.P, h->S, F, qShade, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
           else
-            k_shade<FEAT_ALL><<<gP * 128 / SHADE_BLOCK, SHADE_BLOCK, 2048, st>>>(L.P, h->S, F, qT, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
+            k_shade<FEAT_ALL><<<gP * 128 / SHADE_BLOCK, SHADE_BLOCK, 2048, st>>>(L.P, h->S, F, qShade, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
         });
         timed(tPost, [&] { k_shadow<<<gP, 128, 0, st>>>(L.P, h->S, L.dQ[3], &cntShadow[it], &workPost[it], L.dQ[4], &cntAlphaS[it], h->dStats, h->refillThreshold, h->postponeShift, 0); });
         if(h->S.hasAlpha)

@@ -93,6 +93,8 @@ struct DevScene
   int                          hasAlpha;  // the scene has non-opaque triangles (the any-hit kernels are launched)
   const uint2*                 triMeta;   // per triangle slot of `bvh`: (rnode | flags<<28, primitiveID)
   const uint2*                 triMetaS;  // per triangle slot of bvhO / bvhA (== triMeta in scenes without non-opaque triangles)
+  const uint32_t*              matOfSlot; // per triangle slot of `bvh`: material index (key of the material-sorted shade queue)
+  int                          numMaterials;
   const ShadeRec*              shadeRecs; // one per triangle of every render primitive
   const uint32_t*              shadeIdx;  // per triangle slot of `bvh`: index into shadeRecs
   const AlphaRec*              alphaRecs; // one per non-opaque triangle, in bvhA's leaf order
