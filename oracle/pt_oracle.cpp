@@ -1583,6 +1583,36 @@ static PathStepResult pathTraceOneBounce(const Ctx& c, Ray& ray, uint32_t& seed,
   Trace(o, ray, payload, seed);
 
   const bool firstRay = (pt.surfaceDepth == 0);
+  const bool meshHit = payload.hitT != INFINITE_F;
+  // checkInfinitePlaneIntersection (pathtrace_functions.h.slang:556-585): the plane y = infinitePlaneDistance, hit from above only,
+  // when it is nearer than the geometry hit
+  bool     hitInfinitePlane = false;
+  HitState planeHit{};
+  if(c.fi->flags & B200PT_SCENE_USE_INFINITE_PLANE)
+  {
+    const float3 normal = f3(0, 1, 0);
+    const float  planeHeight = c.fi->infinitePlaneDistance;
+    if(!(ray.o.y <= planeHeight))
+    {
+      const float Dn = dot(ray.d, normal);
+      if(!(fabsf(Dn) <= 1e-6f))
+      {
+        const float On = dot(ray.o, normal);
+        const float intersectionDist = (-On + planeHeight) / Dn;
+        if(!(intersectionDist <= 0.0f || intersectionDist >= payload.hitT))
+        {
+          payload.hitT = intersectionDist;
+          planeHit.pos = ray.o + ray.d * payload.hitT;
+          planeHit.shadowPos = planeHit.pos;
+          planeHit.nrm = normal;
+          planeHit.geonrm = normal;
+          planeHit.tangent = f3(1, 0, 0);
+          planeHit.bitangent = f3(0, 0, 1);
+          hitInfinitePlane = true;
+        }
+      }
+    }
+  }
   if(payload.hitT == INFINITE_F)
   {
     if(firstRay)
@@ -1607,10 +1637,15 @@ static PathStepResult pathTraceOneBounce(const Ctx& c, Ray& ray, uint32_t& seed,
   if(dbgPixel)
     fprintf(stderr, "DBG hit t=%.9g rnode=%d prim=%d bary=%.9g %.9g org=%.9g %.9g %.9g dir=%.9g %.9g %.9g seed=%u depth=%d\n", payload.hitT, payload.rnodeID,
             payload.primitiveID, payload.bx, payload.by, ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, seed, pt.surfaceDepth);
-  const b200pt_render_node& renderNode = o.nodes[payload.rnodeID];
-  const Prim&               P = o.prims[payload.rprimID];
-  const float3              barys = f3(1.0f - payload.bx - payload.by, payload.bx, payload.by);
-  HitState hit = getHitState(P, barys, *(const mat4*)renderNode.worldToObject, *(const mat4*)renderNode.objectToWorld, (uint32_t)payload.primitiveID, ray.d);
+  HitState hit = planeHit;
+  if(!hitInfinitePlane)
+  {
+    const b200pt_render_node& rn = o.nodes[payload.rnodeID];
+    const Prim&               P = o.prims[payload.rprimID];
+    const float3              barys = f3(1.0f - payload.bx - payload.by, payload.bx, payload.by);
+    hit = getHitState(P, barys, *(const mat4*)rn.worldToObject, *(const mat4*)rn.objectToWorld, (uint32_t)payload.primitiveID, ray.d);
+  }
+  (void)meshHit;
   tls.shadedHits++;
 
   // rayConeWorldFootprint
@@ -1620,19 +1655,39 @@ static PathStepResult pathTraceOneBounce(const Ctx& c, Ray& ray, uint32_t& seed,
     worldFoot = w / fmaxf(fabsf(dot(hit.geonrm, -ray.d)), 1e-3f);
   }
 
-  const int materialIndex = std::max(0, renderNode.materialID);
-  float     texGrad = worldFoot * hit.texelDensity * c.pc->texGradScale;
-  MeshState mesh;
-  mesh.N = hit.nrm;
-  mesh.T = hit.tangent;
-  mesh.B = hit.bitangent;
-  mesh.Ng = hit.geonrm;
-  mesh.tc[0] = hit.uv[0];
-  mesh.tc[1] = hit.uv[1];
-  mesh.isInside = pt.isInside;
-  mesh.texGrad = texGrad;
-  mesh.baseColorVertexMul = hit.color;
-  PbrMaterial pbrMat = evaluateMaterial(o, o.mats[materialIndex], mesh);
+  int         materialIndex = -1;
+  PbrMaterial pbrMat;
+  if(hitInfinitePlane)
+  {
+    // gltf_pathtrace.slang:169-173: the plane's material replaces the hit's (defaultPbrMaterial(baseColor, metallic, roughness, N, Ng):
+    // nvshaders, external -- restated: GGX alpha = roughness^2 like evaluateMaterial, tangent frame from the normal)
+    pbrMat = defaultPbrMaterial();
+    pbrMat.baseColor = f3(c.fi->infinitePlaneBaseColor[0], c.fi->infinitePlaneBaseColor[1], c.fi->infinitePlaneBaseColor[2]);
+    pbrMat.metallic = c.fi->infinitePlaneMetallic;
+    const float r = c.fi->infinitePlaneRoughness;
+    pbrMat.roughness = f2(r * r, r * r);
+    pbrMat.N = hit.nrm;
+    pbrMat.Ng = hit.nrm;
+    pbrMat.Nc = hit.nrm;
+    pbrMat.T = xyz(makeFastTangent(hit.nrm));
+    pbrMat.B = cross(pbrMat.N, pbrMat.T);
+  }
+  else
+  {
+    materialIndex = std::max(0, o.nodes[payload.rnodeID].materialID);
+    float     texGrad = worldFoot * hit.texelDensity * c.pc->texGradScale;
+    MeshState mesh;
+    mesh.N = hit.nrm;
+    mesh.T = hit.tangent;
+    mesh.B = hit.bitangent;
+    mesh.Ng = hit.geonrm;
+    mesh.tc[0] = hit.uv[0];
+    mesh.tc[1] = hit.uv[1];
+    mesh.isInside = pt.isInside;
+    mesh.texGrad = texGrad;
+    mesh.baseColorVertexMul = hit.color;
+    pbrMat = evaluateMaterial(o, o.mats[materialIndex], mesh);
+  }
 
   if(firstRay)
     pt.firstHitPos = hit.pos;
@@ -1642,7 +1697,7 @@ static PathStepResult pathTraceOneBounce(const Ctx& c, Ray& ray, uint32_t& seed,
 
   pt.radiance += pbrMat.emissive * pt.throughput;
 
-  if(o.mats[materialIndex].unlit > 0)
+  if(materialIndex >= 0 && o.mats[materialIndex].unlit > 0)
   {
     pt.radiance += pbrMat.baseColor;
     return eBreak;
@@ -2037,7 +2092,7 @@ int oracle_render_frame_aux(void* h, const b200pt_frame_info* fi, const b200pt_p
   Oracle& o = *(Oracle*)h;
   if(!(fi->flags & B200PT_SCENE_USE_HDR_ENVIRONMENT) || o.envW == 0)
     return B200PT_E_UNSUPPORTED;
-  if(fi->flags & B200PT_SCENE_USE_INFINITE_PLANE)
+  if(fi->flags & B200PT_SCENE_INFINITE_PLANE_SHADOW_CATCHER)
     return B200PT_E_UNSUPPORTED;
   Ctx       c{&o, fi, pc};
   const int W = (int)fi->imageSize[0];

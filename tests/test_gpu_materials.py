@@ -159,3 +159,35 @@ def test_selection_ids_and_ndc_depth_of_frame_zero(std_env, oracle_mod):
         assert 0 < (ids == 0).mean() < 0.9 and len(np.unique(ids)) > 3
         assert ((depth > 0) & (depth <= 1)).all() and (depth[ids_ref == 0] == 1.0).mean() > 0.5
         pt.onDetach(res)
+
+
+def test_render_parity_infinite_plane(std_env, oracle_mod):
+    """--useInfinitePlane: the ground plane y = infinitePlaneDistance with its own base colour / metallic / roughness catches the
+    rays that pass the geometry (checkInfinitePlaneIntersection, pathtrace_functions.h.slang:556-585; material swap
+    gltf_pathtrace.slang:165-173): stream-replicated parity with the oracle, the plane is visible, and the shadow-catcher mode is
+    refused instead of ignored."""
+    from vk_gltf_renderer_b200 import synth
+    from vk_gltf_renderer_b200.renderer import B200PTError, PathTracer, Resources
+    scn = synth.synth_material_zoo()
+    scn.render_nodes = scn.render_nodes[:-1]  # drop the zoo's own floor: the infinite plane takes its place
+    kw = dict(infinite_plane=True, plane_distance=-0.02, plane_color=(0.7, 0.5, 0.3), plane_metallic=0.1, plane_roughness=0.4)
+    o = _oracle(oracle_mod, scn, std_env)
+    ref = oracle_mod.render(o, scn.camera, 192, 128, 8, max_depth=6, **kw)
+    res = Resources(scene=scn, hdr_rgb=std_env, camera=scn.camera, size=(192, 128))
+    res.settings.useInfinitePlane, res.settings.infinitePlaneDistance = True, -0.02
+    res.settings.infinitePlaneBaseColor, res.settings.infinitePlaneMetallic, res.settings.infinitePlaneRoughness = (0.7, 0.5, 0.3), 0.1, 0.4
+    from vk_gltf_renderer_b200.renderer import render_headless
+    pt, img = render_headless(res, 8, ptMaxDepth=6)
+    e = rel_rmse(img, ref)
+    print("infinite plane rel RMSE", e)
+    assert e <= 1e-3
+    assert np.array_equal(img[..., 3] > 0, ref[..., 3] > 0)
+    st, so = pt.stats(), o.stats()
+    assert st["closestRays"] == so["closestRays"] and st["shadedHits"] == so["shadedHits"]
+    res2 = Resources(scene=scn, hdr_rgb=std_env, camera=scn.camera, size=(192, 128))
+    _, bare = render_headless(res2, 2, ptMaxDepth=6)
+    assert (img[100:, :, 3] > 0).mean() > 0.9 and (bare[100:, :, 3] > 0).mean() < 0.6   # the lower image rows now hit the plane
+    res.settings.isShadowCatcher = True
+    res.frameCount = 0
+    with pytest.raises(B200PTError):
+        pt.onRender(None, res)

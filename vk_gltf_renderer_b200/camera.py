@@ -67,7 +67,8 @@ def _glm(m):
 
 
 def make_frame_info(cam, width, height, *, use_hdr=True, env_rotation=0.0, env_intensity=1.0, env_blur=0.0,
-                    solid_background=False, background=(0, 0, 0)):
+                    solid_background=False, background=(0, 0, 0), infinite_plane=False, plane_distance=0.0,
+                    plane_color=(0.5, 0.5, 0.5), plane_metallic=0.0, plane_roughness=0.5, shadow_catcher=False):
     """SceneFrameInfo as filled at src/renderer.cpp:677-700 (projection uses the *window* aspect)."""
     view = look_at(cam.eye, cam.center, cam.up)
     if cam.type == "orthographic":
@@ -84,16 +85,18 @@ def make_frame_info(cam, width, height, *, use_hdr=True, env_rotation=0.0, env_i
     fi.imageSize[:] = [float(width), float(height)]
     fi.flags = ((abi.SCENE_IS_ORTHOGRAPHIC if cam.type == "orthographic" else 0)
                 | (abi.SCENE_USE_SOLID_BACKGROUND if solid_background else 0)
-                | (abi.SCENE_USE_HDR_ENVIRONMENT if use_hdr else 0))
+                | (abi.SCENE_USE_HDR_ENVIRONMENT if use_hdr else 0)
+                | (abi.SCENE_USE_INFINITE_PLANE if infinite_plane else 0)
+                | (abi.SCENE_INFINITE_PLANE_SHADOW_CATCHER if (infinite_plane and shadow_catcher) else 0))
     fi.envRotation = env_rotation
     fi.envBlur = env_blur
     fi.envIntensity = env_intensity
     fi.backgroundColor[:] = list(background)
     fi.visualization = 0
-    fi.infinitePlaneDistance = 0.0
-    fi.infinitePlaneBaseColor[:] = [0.5, 0.5, 0.5]
-    fi.infinitePlaneMetallic = 0.0
-    fi.infinitePlaneRoughness = 0.5
+    fi.infinitePlaneDistance = plane_distance
+    fi.infinitePlaneBaseColor[:] = list(plane_color)
+    fi.infinitePlaneMetallic = plane_metallic
+    fi.infinitePlaneRoughness = plane_roughness
     fi.shadowCatcherDarkenAmount = 0.0
     return fi
 

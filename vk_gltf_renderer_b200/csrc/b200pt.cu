@@ -555,6 +555,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
   PbrMaterial               pbrMat;
   DirectLight               directLight;
   bool                      nextEventValid = false;
+  bool                      onPlane = false;  // the ray met the infinite ground plane in front of the geometry
 #ifdef B200PT_DEBUG
   bool dbgPixel = false;
 #endif
@@ -581,6 +582,41 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
     depth = flags & PF_DEPTH_MASK;
     slot = __float_as_uint(hr.w);
     hitT = hr.x;
+
+    // ---- infinite ground plane (checkInfinitePlaneIntersection, pathtrace_functions.h.slang:556-585): y = infinitePlaneDistance,
+    //      hit from above only, when it lies in front of the geometry hit ----
+    onPlane = false;
+    if(F.fi.flags & B200PT_SCENE_USE_INFINITE_PLANE)
+    {
+      const float3 normal = f3(0, 1, 0);
+      const float  planeHeight = F.fi.infinitePlaneDistance;
+      const float  tGeom = (slot == 0xFFFFFFFFu) ? kInfinite : hitT;
+      if(!(org.y <= planeHeight))
+      {
+        const float Dn = dot(dir, normal);
+        if(!(fabsf(Dn) <= 1e-6f))
+        {
+          const float On = dot(org, normal);
+          const float intersectionDist = (-On + planeHeight) / Dn;
+          if(!(intersectionDist <= 0.0f || intersectionDist >= tGeom))
+          {
+            onPlane = true;
+            hitT = intersectionDist;
+            hit.pos = org + dir * hitT;
+            hit.shadowPos = hit.pos;
+            hit.nrm = normal;
+            hit.geonrm = normal;
+            hit.tangent = f3(1, 0, 0);
+            hit.bitangent = f3(0, 0, 1);
+            hit.color = f4(1, 1, 1, 1);
+            hit.uv0 = hit.uv1 = f2(0.0f, 0.0f);
+            hit.texelDensity = 0.0f;
+            statAdd(&stats->shadedHits, 1ull);
+            return true;
+          }
+        }
+      }
+    }
 
     if(slot == 0xFFFFFFFFu)
     {
@@ -629,13 +665,32 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
   };
   // ---- section 2: material evaluation (three trilinear texture lookups), emission, unlit ----
   auto shadeMaterial = [&]() -> bool {
-    const b200pt_render_node& node = *nodeP;
-
     worldFoot = (coneWidth + F.pc.pixelAngle * hitT) / fmaxf(fabsf(dot(hit.geonrm, -dir)), 1e-3f);
-    const int   materialIndex = max(0, node.materialID);
-    const float texGrad = worldFoot * hit.texelDensity * F.pc.texGradScale;
-    const b200pt_shade_material& gmat = S.mats[materialIndex];
-    pbrMat = evaluateMaterial<FEAT>(S, gmat, hit, (flags & PF_INSIDE) != 0, texGrad);
+    int unlit = 0;
+    if(onPlane)
+    {
+      // gltf_pathtrace.slang:169-173: defaultPbrMaterial(infinitePlaneBaseColor, metallic, roughness, N, N) (nvshaders, external:
+      // restated -- GGX alpha = roughness^2 like evaluateMaterial, tangent frame from the normal; same in the oracle)
+      pbrMat = defaultPbrMaterial();
+      pbrMat.baseColor = f3(F.fi.infinitePlaneBaseColor[0], F.fi.infinitePlaneBaseColor[1], F.fi.infinitePlaneBaseColor[2]);
+      pbrMat.metallic = F.fi.infinitePlaneMetallic;
+      const float r = F.fi.infinitePlaneRoughness;
+      pbrMat.roughness = f2(r * r, r * r);
+      pbrMat.N = hit.nrm;
+      pbrMat.Ng = hit.nrm;
+      pbrMat.Nc = hit.nrm;
+      pbrMat.T = xyz(makeFastTangent(hit.nrm));
+      pbrMat.B = cross(pbrMat.N, pbrMat.T);
+    }
+    else
+    {
+      const b200pt_render_node&    node = *nodeP;
+      const int                    materialIndex = max(0, node.materialID);
+      const float                  texGrad = worldFoot * hit.texelDensity * F.pc.texGradScale;
+      const b200pt_shade_material& gmat = S.mats[materialIndex];
+      pbrMat = evaluateMaterial<FEAT>(S, gmat, hit, (flags & PF_INSIDE) != 0, texGrad);
+      unlit = gmat.unlit;
+    }
 
     // firefly control: never get sharper than the roughest bounce so far (:267-268)
     misc.x = fmaxf(pbrMat.roughness.x, misc.x);
@@ -648,7 +703,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
 
     radiance += pbrMat.emissive * throughput;
 
-    if(gmat.unlit > 0)
+    if(unlit > 0)
     {
       radiance += pbrMat.baseColor;
       finalizeSample(P, F, i, radiance, (flags & PF_SOLID) != 0, seed, sampleIdx, qNext, cntNext, stats);
@@ -2775,9 +2830,9 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
     h->err = "b200pt_render_frame: only the HDR environment (--envSystem 1) is built; physical sky is out of scope";
     return B200PT_E_UNSUPPORTED;
   }
-  if(fi->flags & B200PT_SCENE_USE_INFINITE_PLANE)
+  if(fi->flags & B200PT_SCENE_INFINITE_PLANE_SHADOW_CATCHER)
   {
-    h->err = "b200pt_render_frame: infinite plane / shadow catcher is not built";
+    h->err = "b200pt_render_frame: the shadow-catcher mode of the infinite plane is not built (handleShadowCatcher needs nvshaders' bsdfSampleSimple)";
     return B200PT_E_UNSUPPORTED;
   }
   if(pc->flags & (B200PT_PT_USE_DLSS | B200PT_PT_USE_OPTIX_DENOISER))

@@ -42,6 +42,44 @@ struct PbrMaterial
   float  retroreflection;  // KHR_materials_retroreflection: carried like the reference does; b200pt_set_scene rejects factors > 0
 };
 
+// defaultPbrMaterial() (nvshaders pbr_material_types, external; restated like oracle/bsdf.h)
+PT_D PbrMaterial defaultPbrMaterial()
+{
+  PbrMaterial m;
+  m.baseColor = f3(1.0f);
+  m.opacity = 1.0f;
+  m.roughness = f2(1.0f, 1.0f);
+  m.metallic = 1.0f;
+  m.emissive = f3(0.0f);
+  m.N = f3(0, 0, 1);
+  m.T = f3(1, 0, 0);
+  m.B = f3(0, 1, 0);
+  m.Ng = f3(0, 0, 1);
+  m.ior1 = 1.0f;
+  m.ior2 = 1.5f;
+  m.specular = 1.0f;
+  m.specularColor = f3(1.0f);
+  m.transmission = 0.0f;
+  m.attenuationColor = f3(1.0f);
+  m.attenuationDistance = 1.0f;
+  m.thickness = 0.0f;
+  m.clearcoat = 0.0f;
+  m.clearcoatRoughness = 0.01f;
+  m.Nc = f3(0, 0, 1);
+  m.iridescence = 0.0f;
+  m.iridescenceIor = 1.5f;
+  m.iridescenceThickness = 0.1f;
+  m.sheenColor = f3(0.0f);
+  m.sheenRoughness = 0.0f;
+  m.diffuseTransmissionFactor = 0.0f;
+  m.diffuseTransmissionColor = f3(1.0f);
+  m.scatterCoefficient = f3(0.0f);
+  m.scatterAnisotropy = 0.0f;
+  m.dispersion = 0.0f;
+  m.retroreflection = 0.0f;
+  return m;
+}
+
 enum : int
 {
   BSDF_EVENT_ABSORB = 0,

@@ -305,13 +305,16 @@ b200pt_frame_info makeFrameInfo(const Camera& cam, int width, int height, const 
   fi.imageSize[0] = (float)width;
   fi.imageSize[1] = (float)height;
   fi.flags = (cam.orthographic ? B200PT_SCENE_IS_ORTHOGRAPHIC : 0) | (s.useSolidBackground ? B200PT_SCENE_USE_SOLID_BACKGROUND : 0)
-             | (s.envSystem == 1 ? B200PT_SCENE_USE_HDR_ENVIRONMENT : 0);
+             | (s.envSystem == 1 ? B200PT_SCENE_USE_HDR_ENVIRONMENT : 0) | (s.useInfinitePlane ? B200PT_SCENE_USE_INFINITE_PLANE : 0)
+             | ((s.useInfinitePlane && s.isShadowCatcher) ? B200PT_SCENE_INFINITE_PLANE_SHADOW_CATCHER : 0);  // src/renderer.cpp:688-690
   fi.envRotation = s.hdrEnvRotation;
   fi.envBlur = s.hdrBlur;
   fi.envIntensity = s.hdrEnvIntensity;
   std::memcpy(fi.backgroundColor, s.solidBackgroundColor, 12);
-  fi.infinitePlaneBaseColor[0] = fi.infinitePlaneBaseColor[1] = fi.infinitePlaneBaseColor[2] = 0.5f;
-  fi.infinitePlaneRoughness = 0.5f;
+  fi.infinitePlaneDistance = s.infinitePlaneDistance;
+  std::memcpy(fi.infinitePlaneBaseColor, s.infinitePlaneBaseColor, 12);
+  fi.infinitePlaneMetallic = s.infinitePlaneMetallic;
+  fi.infinitePlaneRoughness = s.infinitePlaneRoughness;
   return fi;
 }
 

@@ -34,6 +34,13 @@ struct Settings
   bool  useSolidBackground  = false;
   float solidBackgroundColor[3] = {0.f, 0.f, 0.f};
   int   maxFrames           = 500;
+  // infinite ground plane (src/resources.hpp:111-116); the shadow-catcher mode is not built (the frame call fails)
+  bool  useInfinitePlane       = false;
+  bool  isShadowCatcher        = false;
+  float infinitePlaneDistance  = 0.0f;
+  float infinitePlaneBaseColor[3] = {0.5f, 0.5f, 0.5f};
+  float infinitePlaneMetallic  = 0.0f;
+  float infinitePlaneRoughness = 0.5f;
 };
 
 // what nvutils::CameraManipulator hands the renderer (external to the reference tree): look-at + lens

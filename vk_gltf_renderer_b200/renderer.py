@@ -31,6 +31,12 @@ class Settings:
     useSolidBackground: bool = False
     solidBackgroundColor: tuple = (0.0, 0.0, 0.0)
     maxFrames: int = 500
+    useInfinitePlane: bool = False   # src/resources.hpp:111-116
+    isShadowCatcher: bool = False    # (not built: B200PT_E_UNSUPPORTED)
+    infinitePlaneDistance: float = 0.0
+    infinitePlaneBaseColor: tuple = (0.5, 0.5, 0.5)
+    infinitePlaneMetallic: float = 0.0
+    infinitePlaneRoughness: float = 0.5
 
 
 @dataclass
@@ -165,7 +171,9 @@ class PathTracer:
             self.m_totalSamplesAccumulated = 0
         fi = cam_mod.make_frame_info(resources.camera, w, h, use_hdr=(s.envSystem == 1), env_rotation=s.hdrEnvRotation,
                                      env_intensity=s.hdrEnvIntensity, env_blur=s.hdrBlur,
-                                     solid_background=s.useSolidBackground, background=s.solidBackgroundColor)
+                                     solid_background=s.useSolidBackground, background=s.solidBackgroundColor,
+                                     infinite_plane=s.useInfinitePlane, plane_distance=s.infinitePlaneDistance, plane_color=s.infinitePlaneBaseColor,
+                                     plane_metallic=s.infinitePlaneMetallic, plane_roughness=s.infinitePlaneRoughness, shadow_catcher=s.isShadowCatcher)
         pc = cam_mod.make_push_constant(resources.camera, h, frame_count=resources.frameCount,
                                         total_samples=self.m_totalSamplesAccumulated, num_samples=self.ptSamples,
                                         max_depth=self.ptMaxDepth, firefly_clamp=self.ptFireflyClamp,
