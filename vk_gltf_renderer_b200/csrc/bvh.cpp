@@ -350,48 +350,136 @@ void buildWideBvh(const std::vector<FlatTri>& tris, const std::vector<uint32_t>&
       gather.run(root.left, root.splitK[7], ch, nch);
       gather.run(root.right, 8 - root.splitK[7], ch, nch);
     }
-    // slot assignment: slot s is visited first by rays whose negative-direction bits equal s, so a
-    // child far along +x wants bit 4 set, +y bit 2, +z bit 1 (greedy maximum of centroid . diagonal)
-    const Box& nb = root.box;
-    float      cx = 0.5f * (nb.lo[0] + nb.hi[0]), cy = 0.5f * (nb.lo[1] + nb.hi[1]), cz = 0.5f * (nb.lo[2] + nb.hi[2]);
-    float      cost[8][8];
-    for(int i = 0; i < nch; i++)
-    {
-      const Box& b = B.n2[ch[i]].box;
-      float      dx = 0.5f * (b.lo[0] + b.hi[0]) - cx, dy = 0.5f * (b.lo[1] + b.hi[1]) - cy, dz = 0.5f * (b.lo[2] + b.hi[2]) - cz;
-      for(int s = 0; s < 8; s++)
-        cost[i][s] = dx * ((s & 4) ? 1.f : -1.f) + dy * ((s & 2) ? 1.f : -1.f) + dz * ((s & 1) ? 1.f : -1.f);
-    }
-    int  slotOf[8];
-    int  childAt[8];
-    bool cu[8] = {false, false, false, false, false, false, false, false};
+    // Slot assignment + per-node AXIS MAP.  The kernel visits the inner children of a node in descending (slot ^ oct) order,
+    // where bit k of `oct` is the sign of the ray direction along the axis that bit k of the slot index stands for.  Ylitie et
+    // al. fix that to (x, y, z); here every node chooses which axis each of its three slot bits follows (27 maps, two or three
+    // bits may share an axis and then rank the children along it), which orders children that are spread along one or two axes
+    // correctly for every ray (offline, tools/order_exp.cpp on the bench scene: 15.4 -> 14.0 nodes and 8.4 -> 7.5 triangle tests
+    // per ray).  For each map the children are assigned to slots by the optimal assignment of centroid offsets (subset DP), and
+    // the map whose order agrees best with the true front-to-back order over 26 sample directions wins.  6 bits per node (axis of
+    // bit 0 | bit 1 << 2 | bit 2 << 4), stored above the 26-bit child base.  BVH_AXISMAP=0: the fixed (z, y, x) map of round 1.
+    static const bool useAxisMaps = !(getenv("BVH_AXISMAP") && atoi(getenv("BVH_AXISMAP")) == 0);
+    int               childAt[8];
     for(int s = 0; s < 8; s++)
       childAt[s] = -1;
-    for(int k = 0; k < nch; k++)
+    uint32_t axisMap = 2u | (1u << 2) | (0u << 4);  // bit 0 -> z, bit 1 -> y, bit 2 -> x
     {
-      float best = -FLT_MAX;
-      int   bi = -1, bs = -1;
+      float cen[8][3], mid[3];
       for(int i = 0; i < nch; i++)
+        for(int a3 = 0; a3 < 3; a3++)
+          cen[i][a3] = 0.5f * (B.n2[ch[i]].box.lo[a3] + B.n2[ch[i]].box.hi[a3]);
+      for(int a3 = 0; a3 < 3; a3++)
       {
-        if(cu[i])
-          continue;
-        for(int s = 0; s < 8; s++)
+        float lo = FLT_MAX, hi = -FLT_MAX;
+        for(int i = 0; i < nch; i++)
         {
-          if(childAt[s] >= 0)
-            continue;
-          if(cost[i][s] > best)
+          lo = std::min(lo, cen[i][a3]);
+          hi = std::max(hi, cen[i][a3]);
+        }
+        mid[a3] = 0.5f * (lo + hi);
+      }
+      double bestScore = -1.0;
+      int    bestCode[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for(int map = 0; map < 27; map++)
+      {
+        const int ax[3] = {map % 3, (map / 3) % 3, map / 9};  // axis of slot bit 0, 1, 2
+        if(!useAxisMaps && !(ax[0] == 2 && ax[1] == 1 && ax[2] == 0))
+          continue;
+        // bits on the same axis form a binary rank along it: the higher bit is the more significant one
+        float w[3];
+        for(int bt = 0; bt < 3; bt++)
+        {
+          int lower = 0;
+          for(int b2 = 0; b2 < bt; b2++)
+            lower += ax[b2] == ax[bt];
+          w[bt] = (float)(1 << lower);
+        }
+        float cost[8][8];
+        for(int i = 0; i < nch; i++)
+          for(int sl = 0; sl < 8; sl++)
           {
-            best = cost[i][s];
-            bi = i;
-            bs = s;
+            float v = 0.f;
+            for(int bt = 0; bt < 3; bt++)
+              v += (((sl >> bt) & 1) ? 1.f : -1.f) * w[bt] * (cen[i][ax[bt]] - mid[ax[bt]]);
+            cost[i][sl] = v;
+          }
+        // optimal assignment of the children (in order) to distinct slots: DP over the set of used slots
+        float   best[256];
+        uint8_t from[8][256];
+        for(int m = 0; m < 256; m++)
+          best[m] = -FLT_MAX;
+        best[0] = 0.f;
+        for(int m = 0; m < 256; m++)
+        {
+          const int i = __builtin_popcount((unsigned)m);
+          if(i >= nch || best[m] == -FLT_MAX)
+            continue;
+          for(int sl = 0; sl < 8; sl++)
+          {
+            if(m & (1 << sl))
+              continue;
+            const int   nm = m | (1 << sl);
+            const float v = best[m] + cost[i][sl];
+            if(v > best[nm])
+            {
+              best[nm] = v;
+              from[i][nm] = (uint8_t)sl;
+            }
           }
         }
+        int   bm = -1;
+        float bv = -FLT_MAX;
+        for(int m = 0; m < 256; m++)
+          if(__builtin_popcount((unsigned)m) == nch && best[m] > bv)
+          {
+            bv = best[m];
+            bm = m;
+          }
+        int code[8];
+        for(int i = nch - 1, m = bm; i >= 0; i--)
+        {
+          code[i] = from[i][m];
+          m &= ~(1 << code[i]);
+        }
+        // agreement of the visiting order with the front-to-back order of the centroids over the 26 directions of the cube
+        double score = 0.0;
+        for(int dxi = -1; dxi <= 1; dxi++)
+          for(int dyi = -1; dyi <= 1; dyi++)
+            for(int dzi = -1; dzi <= 1; dzi++)
+            {
+              if(!dxi && !dyi && !dzi)
+                continue;
+              const float d[3] = {(float)dxi, (float)dyi, (float)dzi};
+              int         eff = 0;
+              for(int bt = 0; bt < 3; bt++)
+                if(d[ax[bt]] >= 0.f)
+                  eff |= 1 << bt;
+              for(int i = 0; i < nch; i++)
+                for(int j = i + 1; j < nch; j++)
+                {
+                  const float pi = cen[i][0] * d[0] + cen[i][1] * d[1] + cen[i][2] * d[2], pj = cen[j][0] * d[0] + cen[j][1] * d[1] + cen[j][2] * d[2];
+                  if(pi == pj)
+                  {
+                    score += 0.5;
+                    continue;
+                  }
+                  const bool iFirst = (code[i] ^ eff) > (code[j] ^ eff);  // visited first = larger (slot ^ oct)
+                  score += ((pi < pj) == iFirst) ? 1.0 : 0.0;
+                }
+            }
+        if(ax[0] == 2 && ax[1] == 1 && ax[2] == 0)
+          score *= 1.0000001;  // ties go to the standard map
+        if(score > bestScore)
+        {
+          bestScore = score;
+          axisMap = (uint32_t)ax[0] | ((uint32_t)ax[1] << 2) | ((uint32_t)ax[2] << 4);
+          memcpy(bestCode, code, sizeof(code));
+        }
       }
-      cu[bi] = true;
-      slotOf[bi] = bs;
-      childAt[bs] = bi;
+      for(int i = 0; i < nch; i++)
+        childAt[bestCode[i]] = i;
     }
-    (void)slotOf;
+    const Box& nb = root.box;
 
     // quantisation frame
     float    p[3] = {nb.lo[0], nb.lo[1], nb.lo[2]};
@@ -471,7 +559,7 @@ void buildWideBvh(const std::vector<FlatTri>& tris, const std::vector<uint32_t>&
     N[1] = p[1];
     N[2] = p[2];
     N[3] = u2f(eb[0] | (eb[1] << 8) | (eb[2] << 16) | ((uint32_t)imask << 24));
-    N[4] = u2f(childBase);
+    N[4] = u2f(childBase | (axisMap << 26));  // child base (26 bits) | axis map (6 bits)
     N[5] = u2f(triBase);
     N[6] = u2f((uint32_t)meta[0] | ((uint32_t)meta[1] << 8) | ((uint32_t)meta[2] << 16) | ((uint32_t)meta[3] << 24));
     N[7] = u2f((uint32_t)meta[4] | ((uint32_t)meta[5] << 8) | ((uint32_t)meta[6] << 16) | ((uint32_t)meta[7] << 24));

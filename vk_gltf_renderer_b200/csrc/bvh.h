@@ -32,7 +32,7 @@ struct FlatTri
 
 // Node = 80 B = 5 x 16 B:
 //   n0 = (p.x, p.y, p.z, ex | ey<<8 | ez<<16 | imask<<24)
-//   n1 = (childBase, triBase, meta[0..3], meta[4..7])
+//   n1 = (childBase | axisMap << 26, triBase, meta[0..3], meta[4..7])   axisMap: which axis each slot bit follows (bvh.cpp)
 //   n2 = (qlo_x[0..3], qlo_x[4..7], qhi_x[0..3], qhi_x[4..7]);  n3 = y;  n4 = z
 // Triangle = 48 B = 3 x 16 B: (v0.xyz, rnode | flags<<28) (e1.xyz, prim) (e2.xyz, globalId)
 struct WideBvh

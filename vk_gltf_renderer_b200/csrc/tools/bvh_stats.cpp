@@ -42,7 +42,7 @@ int main(int argc, char** argv)
     float org[3] = {R[0], R[1], R[2]}, dir[3] = {R[4], R[5], R[6]}, tmin = R[3], best = R[7];
     float id[3];
     for(int a = 0; a < 3; a++) { float d = fabsf(dir[a]) > 1e-20f ? dir[a] : copysignf(1e-20f, dir[a]); id[a] = 1.0f / d; }
-    uint32_t octInv = (dir[0] < 0 ? 0 : 4) | (dir[1] < 0 ? 0 : 2) | (dir[2] < 0 ? 0 : 1);
+    const uint32_t dsign = (dir[0] < 0 ? 0 : 1) | (dir[1] < 0 ? 0 : 2) | (dir[2] < 0 ? 0 : 4);
     struct G { uint32_t x, y; float tn[8]; float gmin; };
     G stack[64]; int sp = 0; G cur{0, 0x80000000u, {0, 0, 0, 0, 0, 0, 0, 0}, 0.f};
     static const int stale = getenv("STALE") ? atoi(getenv("STALE")) : 0;
@@ -76,14 +76,16 @@ int main(int argc, char** argv)
           stack[sp++] = cur;
         }
         cur.gmin = -1.f;  // the freshly opened node's own group is tested child by child
-        uint32_t slot = (uint32_t)(cb - 24) ^ octInv;
+        uint32_t slot = (uint32_t)(cb - 24) ^ ((him >> 8) & 7u);
         uint32_t rel = __builtin_popcount(him & ~(0xffffffffu << slot));
         const float* N = &B.nodes[(size_t)(cur.x + rel) * 20];
         nodes++;
         uint32_t eim = fu(N[3]);
         float ad[3], ao[3];
         for(int a = 0; a < 3; a++) { ad[a] = uf(((eim >> (8 * a)) & 0xff) << 23) * id[a]; ao[a] = (N[a] - org[a]) * id[a]; }
-        cur.x = fu(N[4]); tg.x = fu(N[5]);
+        const uint32_t amap = fu(N[4]) >> 26;
+        const uint32_t octInv = ((dsign >> (amap & 3)) & 1) | (((dsign >> ((amap >> 2) & 3)) & 1) << 1) | (((dsign >> (amap >> 4)) & 1) << 2);
+        cur.x = fu(N[4]) & 0x03ffffffu; tg.x = fu(N[5]);
         uint32_t hm = 0;
         for(int c = 0; c < 8; c++)
         {
@@ -99,7 +101,7 @@ int main(int argc, char** argv)
           }
           if(tn <= tf * 1.000001f) { hm |= childBits << bitIndex; if(inner) cur.tn[bitIndex - 24] = tn; }
         }
-        cur.y = (hm & 0xff000000u) | (eim >> 24); tg.y = hm & 0x00ffffffu;
+        cur.y = (hm & 0xff000000u) | (octInv << 8) | (eim >> 24); tg.y = hm & 0x00ffffffu;
       }
       else { tg = cur; cur = G{0, 0, {0, 0, 0, 0, 0, 0, 0, 0}, 0.f}; }
       while(tg.y)

@@ -47,7 +47,7 @@ int main(int argc, char** argv)
       Child k{}; k.inner = (meta & (meta << 1)) & 0x10;
       for(int a = 0; a < 3; a++) { uint32_t lo = (fu(N[8 + a * 4 + c / 4]) >> (8 * (c % 4))) & 0xff, hi = (fu(N[8 + a * 4 + 2 + c / 4]) >> (8 * (c % 4))) & 0xff;
         k.lo[a] = N[a] + lo * sc[a]; k.hi[a] = N[a] + hi * sc[a]; }
-      if(k.inner) k.node = fu(N[4]) + (uint32_t)__builtin_popcount(imask & ((1u << c) - 1u)); else { k.triBase = fu(N[5]) + (meta & 0x1f); k.triBits = (meta >> 5) & 7; }
+      if(k.inner) k.node = (fu(N[4]) & 0x03ffffffu) + (uint32_t)__builtin_popcount(imask & ((1u << c) - 1u)); else { k.triBase = fu(N[5]) + (meta & 0x1f); k.triBits = (meta >> 5) & 7; }
       k.code = c;  // octant scheme: slot index
       I.ch.push_back(k);
     }

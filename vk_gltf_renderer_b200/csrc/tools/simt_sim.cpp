@@ -96,7 +96,7 @@ static bool nodePhase(Lane& L)
     }
     if(tn <= tf * 1.000001f) { hm |= childBits << bitIndex; if(inner) tnOf[bitIndex - 24] = tn; }
   }
-  L.cur.x = fu(N[4]);
+  L.cur.x = (fu(N[4]) & 0x03ffffffu);
   L.cur.y = (hm & 0xff000000u) | (eim >> 24);
   // gmin for the remainder this group will leave behind once its first child is taken
   {

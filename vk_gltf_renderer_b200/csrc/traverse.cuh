@@ -133,7 +133,7 @@ struct TravState
   float3        org, dir;
   float         idx, idy, idz;
   float         tmin, tmax, tLow, loT, bound;
-  uint32_t      loId, octInv4;
+  uint32_t      loId, dsign;  // dsign: bit a set if the direction component along axis a (0 x, 1 y, 2 z) is >= 0
   bool          haveLo, cull, shadow, shrink;
   bool          overflow;  // a push found the stack full: the walk is incomplete (surfaced as a device error flag)
   TraceHit      best;
@@ -162,7 +162,7 @@ struct TravState
     idx = 1.0f / dx;
     idy = 1.0f / dy;
     idz = 1.0f / dz;
-    octInv4 = ((d.x < 0.f ? 0u : 4u) | (d.y < 0.f ? 0u : 2u) | (d.z < 0.f ? 0u : 1u)) * 0x01010101u;
+    dsign = (d.x < 0.f ? 0u : 1u) | (d.y < 0.f ? 0u : 2u) | (d.z < 0.f ? 0u : 4u);
     tmin = tmin_;
     tmax = tmax_;
     bound = tmax_;
@@ -240,7 +240,7 @@ struct TravState
           else
             overflow = true;
         }
-        const uint32_t slotIndex = (uint32_t)(childBit - 24) ^ (octInv4 & 0xffu);
+        const uint32_t slotIndex = (uint32_t)(childBit - 24) ^ ((hitsImask >> 8) & 7u);  // the group carries its node's octant mask
         const uint32_t relative = __popc(hitsImask & ~(0xffffffffu << slotIndex));
         const uint32_t nodeIndex = cur.x + relative;
 #ifdef B200PT_COUNT_TRAVERSAL
@@ -265,7 +265,12 @@ struct TravState
         const float aozN = fmaf(-kByteSlack, fabsf(adz), aoz), aozF = fmaf(kByteSlack, fabsf(adz), aoz);
         const uint32_t k47 = pool;
 
-        cur.x = __float_as_uint(n1.x);
+        // per-node axis map (bvh.cpp): bit k of the node's octant mask is the direction sign along the axis slot bit k follows
+        const uint32_t n1x = __float_as_uint(n1.x);
+        const uint32_t amap = n1x >> 26;
+        const uint32_t octN = ((dsign >> (amap & 3u)) & 1u) | (((dsign >> ((amap >> 2) & 3u)) & 1u) << 1) | (((dsign >> (amap >> 4)) & 1u) << 2);
+        const uint32_t octInv4 = octN * 0x01010101u;
+        cur.x = n1x & 0x03ffffffu;
         tri.x = __float_as_uint(n1.y);
 
         uint32_t hitMask = 0;
@@ -305,7 +310,7 @@ struct TravState
           PT_CHILD(3)
 #undef PT_CHILD
         }
-        cur.y = (hitMask & 0xff000000u) | (eImask >> 24);
+        cur.y = (hitMask & 0xff000000u) | (octN << 8) | (eImask >> 24);
         tri.y = hitMask & 0x00ffffffu;
       }
       else
