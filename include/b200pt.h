@@ -290,6 +290,13 @@ const char* b200pt_last_error(const b200pt_t* h);
  * world-space triangles of every visible render node, creates bindless texture objects. */
 int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* scene);
 
+/* Animation feed, rigid part: the render nodes' transforms changed (same nodes, same primitives and materials; the reference
+ * updates its TLAS instance matrices and refits: SceneRtx::updateTopLevelAS, src/gltf_scene_rtx.cpp:416-503).  nodes must hold
+ * the scene's numRenderNodes entries with the new objectToWorld / worldToObject.  Every triangle record is recomputed on the
+ * device and the wide BVHs are refitted bottom-up (topology kept); a refitted tree answers every ray exactly like a freshly
+ * built one.  Synchronous. */
+int b200pt_update_transforms(b200pt_t* h, const b200pt_render_node* nodes, uint32_t num_nodes);
+
 /* nvvk::HdrIbl::loadEnvironment (external; reference call site src/renderer.cpp:1994-1996):
  * takes the decoded lat-long image (RGB float, row 0 = +Y pole), builds the alias table
  * (EnvAccel) and stores the per-texel pdf in alpha.  Returns the integral the reference exposes

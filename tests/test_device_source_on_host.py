@@ -102,3 +102,23 @@ def test_device_bsdf_source_matches_oracle_bit_for_bit(tmp_path, oracle_mod):
     print(out.stdout)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "eval mismatches 0, sample mismatches 0" in out.stdout
+
+
+def test_device_refit_source_vs_brute_force(tmp_path):
+    """csrc/refit.cuh (re-quantisation of a node from its children's boxes, bottom-up by level) compiled for the host: after a third
+    of the triangles moved, the refitted tree -- walked by the device traversal source -- returns the brute-force nearest hit over
+    the moved triangles for every ray, bit for bit (tools/host_refit_check.cpp)."""
+    if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from gpu_util import random_rays
+    exe = str(tmp_path / "host_refit_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + CUDA_INC, "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(CSRC, "tools", "host_refit_check.cpp"), os.path.join(CSRC, "bvh.cpp")])
+    rng = np.random.default_rng(3)
+    c = (rng.random((3000, 1, 3)) - 0.5) * 2
+    tris = c + (rng.random((3000, 3, 3)) - 0.5) * 0.3
+    _dump(str(tmp_path / "soup.bin"), tris, random_rays(4000, [-1, -1, -1], [1, 1, 1], seed=11))
+    out = subprocess.run([exe, str(tmp_path / "soup.bin")], capture_output=True, text=True, timeout=600)
+    print(out.stdout)
+    assert out.returncode == 0 and "mismatches after refit: 0" in out.stdout, out.stdout + out.stderr

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "bvh.h"
+#include "refit.cuh"
 #include "shade.cuh"
 
 using namespace pt;
@@ -1261,6 +1262,21 @@ __global__ void __launch_bounds__(128) k_select(DevScene S, const __grid_constan
   }
 }
 
+// ---- BVH refit after a transform update (refit.cuh) ------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_refit_tris(float* tris, uint2* triMeta, uint32_t n, const b200pt_render_node* nodes, const DevPrim* prims)
+{
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    refitTriangle(i, tris, triMeta, nodes, prims);
+}
+
+__global__ void __launch_bounds__(128) k_refit_level(float* nodes, const float* tris, float4* nodeBox, uint32_t first, uint32_t count)
+{
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+    refitNode(first + i, nodes, tris, nodeBox);
+}
+
 // ---- ray-level API (parity tests / traversal micro-benchmark): the rays run through the PRODUCTION kernels
 // (k_trace / k_shadow -> k_alpha -> continuation round -> k_alpha) on a scratch path pool -------------------------
 __global__ void __launch_bounds__(256) k_rays_load(PathState P, const float4* __restrict__ rays, uint32_t n, const uint32_t* __restrict__ seeds, uint32_t* q, uint32_t* cnt,
@@ -1428,6 +1444,20 @@ struct b200pt
   uint32_t            featureMask = 0;
   uint64_t            nodeBytes = 0, triBytes = 0;
   uint32_t            numNodes = 0, numTris = 0;
+  // writable views of the trees for b200pt_update_transforms (refit): [0] merged, [1] opaque-only, [2] non-opaque
+  struct TreeDev
+  {
+    float*                                     nodes = nullptr;
+    float*                                     tris = nullptr;   // the triangle array the tree indexes ([1] and [2] share one)
+    uint2*                                     meta = nullptr;
+    float4*                                    nodeBox = nullptr;  // 2 per node: world-space box (refit scratch)
+    uint32_t                                   numNodes = 0, numTriSlots = 0;
+    std::vector<std::pair<uint32_t, uint32_t>> levels;  // (first node, count) per depth: builders emit breadth first
+  };
+  TreeDev             tree[3];
+  uint32_t            numSceneNodes = 0;
+  b200pt_render_node* dNodesW = nullptr;  // == S.nodes, writable
+  const DevPrim*      dPrimsW = nullptr;
 
   // env
   float4* dEnv = nullptr;
@@ -2235,6 +2265,33 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
   S.bvhO = S.bvh;
   S.bvhA = S.bvh;
   S.triMetaS = S.triMeta;
+  // breadth-first level ranges of a tree (the builder emits level by level, so every level is one contiguous index range)
+  auto levelsOf = [](const WideBvh& t) {
+    std::vector<std::pair<uint32_t, uint32_t>> lv;
+    uint32_t                                   first = 0, count = 1;
+    while(count)
+    {
+      lv.push_back({first, count});
+      uint32_t next = 0;
+      for(uint32_t n = first; n < first + count; n++)
+      {
+        uint32_t w;
+        memcpy(&w, &t.nodes[(size_t)n * 20 + 3], 4);
+        next += (uint32_t)__builtin_popcount(w >> 24);
+      }
+      first += count;
+      count = next;
+    }
+    return lv;
+  };
+  for(auto& t : h->tree)
+    t = b200pt::TreeDev();
+  h->tree[0].nodes = dBvhNodes;
+  h->tree[0].tris = dTris;
+  h->tree[0].meta = reinterpret_cast<uint2*>(dMeta);
+  h->tree[0].numNodes = bvh.numNodes;
+  h->tree[0].numTriSlots = bvh.numTris;
+  h->tree[0].levels = levelsOf(bvh);
   uint64_t splitNodeBytes = 0, splitTriBytes = 0;
   if(anyNonOpaque)
   {
@@ -2259,7 +2316,28 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
     S.triMetaS = reinterpret_cast<const uint2*>(dMetaS);
     splitNodeBytes = (bvhO.nodes.size() + bvhA.nodes.size()) * sizeof(float);
     splitTriBytes = trisS.size() * sizeof(float);
+    h->tree[1].nodes = dNodesO;
+    h->tree[1].tris = dTrisS;
+    h->tree[1].meta = reinterpret_cast<uint2*>(dMetaS);
+    h->tree[1].numNodes = bvhO.numNodes;
+    h->tree[1].numTriSlots = bvhO.numTris + bvhA.numTris;  // the shared array is refitted once, through this entry
+    h->tree[1].levels = levelsOf(bvhO);
+    h->tree[2].nodes = dNodesA;
+    h->tree[2].tris = dTrisS;
+    h->tree[2].meta = nullptr;
+    h->tree[2].numNodes = bvhA.numNodes;
+    h->tree[2].numTriSlots = 0;
+    h->tree[2].levels = levelsOf(bvhA);
   }
+  for(auto& t : h->tree)
+    if(t.nodes)
+    {
+      CK(cudaMalloc((void**)&t.nodeBox, (size_t)std::max(t.numNodes, 1u) * 2 * sizeof(float4)));
+      h->sceneAllocs.push_back(t.nodeBox);
+    }
+  h->numSceneNodes = s->numRenderNodes;
+  h->dNodesW = dNodes;
+  h->dPrimsW = dPrims;
   // ---- per-triangle attribute records for getHitState (device_scene.cuh: ShadeRec), per render primitive ----
   {
     std::vector<uint32_t> recBase(s->numRenderPrimitives, 0);
@@ -2434,6 +2512,51 @@ int b200pt_bvh_info(b200pt_t* h, uint64_t* node_bytes, uint64_t* tri_bytes, uint
     *num_nodes = h->numNodes;
   if(num_tris)
     *num_tris = h->numTris;
+  return B200PT_OK;
+}
+
+int b200pt_update_transforms(b200pt_t* h, const b200pt_render_node* nodes, uint32_t num_nodes)
+{
+  if(!h || !h->haveScene || !nodes || num_nodes != h->numSceneNodes)
+  {
+    if(h)
+      h->err = "b200pt_update_transforms: needs the scene's render-node count (materials / primitives of the nodes must not change)";
+    return B200PT_E_INVALID;
+  }
+  CK(cudaSetDevice(h->device));
+  {
+    const int frc = flushPending(h);
+    if(frc)
+      return frc;
+  }
+  syncAll(h);
+  cudaStream_t st = h->stream;
+  CK(cudaMemcpyAsync(h->dNodesW, nodes, (size_t)num_nodes * sizeof(b200pt_render_node), cudaMemcpyHostToDevice, st));
+  for(int t = 0; t < 3; t++)
+  {
+    b200pt::TreeDev& T = h->tree[t];
+    if(!T.nodes)
+      continue;
+    if(T.numTriSlots)
+    {
+      k_refit_tris<<<gridFor(h, 4), 256, 0, st>>>(T.tris, T.meta, T.numTriSlots, h->dNodesW, h->dPrimsW);
+      h->kernelLaunches++;
+    }
+  }
+  for(int t = 0; t < 3; t++)
+  {
+    b200pt::TreeDev& T = h->tree[t];
+    if(!T.nodes)
+      continue;
+    for(size_t l = T.levels.size(); l-- > 0;)
+    {
+      const uint32_t count = T.levels[l].second;
+      k_refit_level<<<(count + 127) / 128, 128, 0, st>>>(T.nodes, T.tris, T.nodeBox, T.levels[l].first, count);
+      h->kernelLaunches++;
+    }
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
   return B200PT_OK;
 }
 

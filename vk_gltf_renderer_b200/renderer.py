@@ -118,6 +118,19 @@ class PathTracer:
         d = resources.scene.desc()
         self._ck(self._L.b200pt_set_scene(self._h, C.byref(d)), "b200pt_set_scene")
 
+    def update_transforms(self, resources):
+        """the render nodes of resources.scene moved (same nodes / primitives / materials): refit instead of a rebuild
+        (SceneRtx::updateTopLevelAS analogue, b200pt_update_transforms)"""
+        scn = resources.scene
+        n = len(scn.render_nodes)
+        arr = (abi.RenderNode * max(n, 1))()
+        for i, rn in enumerate(scn.render_nodes):
+            arr[i].objectToWorld[:] = np.asarray(rn["objectToWorld"], np.float32).tolist()
+            arr[i].worldToObject[:] = np.asarray(rn["worldToObject"], np.float32).tolist()
+            arr[i].materialID = rn["materialID"]
+            arr[i].renderPrimID = rn["renderPrimID"]
+        self._ck(self._L.b200pt_update_transforms(self._h, arr, n), "b200pt_update_transforms")
+
     def setEnvironment(self, rgb):
         rgb = np.ascontiguousarray(rgb, np.float32)
         integral = C.c_float()
