@@ -290,6 +290,14 @@ const char* b200pt_last_error(const b200pt_t* h);
  * world-space triangles of every visible render node, creates bindless texture objects. */
 int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* scene);
 
+/* Which builder b200pt_set_scene uses for the three trees (closest-hit, opaque-only, non-opaque): 0 = the host builder (binned
+ * SAH + optimal 8-wide collapse + axis maps, csrc/bvh.cpp; default, the better tree), 1 = the DEVICE builder (LBVH: Morton sort,
+ * Karras hierarchy, bottom-up fit, level-wise collapse, csrc/lbvh.cuh; built in milliseconds, ~20-30 % more node visits).
+ * Either tree can be refitted by b200pt_update_transforms.  Takes effect at the next b200pt_set_scene.  Reference: SceneRtx's
+ * driver-side BLAS / TLAS builds, src/gltf_scene_rtx.cpp:173-388.  b200pt_bvh_build_ms: wall time of the last scene's builds. */
+int b200pt_set_bvh_builder(b200pt_t* h, int kind);
+int b200pt_bvh_build_ms(b200pt_t* h, double* ms);
+
 /* Animation feed, rigid part: the render nodes' transforms changed (same nodes, same primitives and materials; the reference
  * updates its TLAS instance matrices and refits: SceneRtx::updateTopLevelAS, src/gltf_scene_rtx.cpp:416-503).  nodes must hold
  * the scene's numRenderNodes entries with the new objectToWorld / worldToObject.  Every triangle record is recomputed on the

@@ -122,3 +122,24 @@ def test_device_refit_source_vs_brute_force(tmp_path):
     out = subprocess.run([exe, str(tmp_path / "soup.bin")], capture_output=True, text=True, timeout=600)
     print(out.stdout)
     assert out.returncode == 0 and "mismatches after refit: 0" in out.stdout, out.stdout + out.stderr
+
+
+def test_device_lbvh_build_source_vs_brute_force(tmp_path):
+    """csrc/lbvh.cuh (the DEVICE builder: Morton keys, bitonic sort, Karras radix tree, bottom-up fit, level-wise collapse into
+    compressed 8-wide nodes) run on the host thread after thread: every triangle of the subset is emitted once and the tree --
+    walked by the device traversal source -- returns the brute-force nearest hit for every ray, bit for bit
+    (tools/host_lbvh_check.cpp)."""
+    if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from gpu_util import random_rays
+    exe = str(tmp_path / "host_lbvh_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + CUDA_INC, "-I" + os.path.join(ROOT, "include"), "-o", exe, os.path.join(CSRC, "tools", "host_lbvh_check.cpp")])
+    rng = np.random.default_rng(7)
+    c = (rng.random((5000, 1, 3)) - 0.5) * 2
+    tris = c + (rng.random((5000, 3, 3)) - 0.5) * 0.25
+    tris[:40] = tris[0]  # coincident triangles: identical Morton codes, unique keys by index
+    _dump(str(tmp_path / "soup.bin"), tris, random_rays(4000, [-1, -1, -1], [1, 1, 1], seed=13))
+    out = subprocess.run([exe, str(tmp_path / "soup.bin")], capture_output=True, text=True, timeout=600)
+    print(out.stdout)
+    assert out.returncode == 0 and "mismatches: 0" in out.stdout, out.stdout + out.stderr

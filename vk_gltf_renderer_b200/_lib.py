@@ -18,7 +18,7 @@ EXPORTS = [
     "b200pt_get_accum_device", "b200pt_read_accum", "b200pt_set_accum_device", "b200pt_stream",
     "b200pt_get_stats", "b200pt_reset_stats", "b200pt_set_profiling", "b200pt_trace_closest",
     "b200pt_trace_shadow", "b200pt_bvh_info", "b200pt_bsdf_eval", "b200pt_bsdf_sample",
-    "b200pt_read_selection", "b200pt_get_selection_device", "b200pt_set_frame_batch", "b200pt_flush", "b200pt_update_transforms",
+    "b200pt_read_selection", "b200pt_get_selection_device", "b200pt_set_frame_batch", "b200pt_flush", "b200pt_update_transforms", "b200pt_set_bvh_builder", "b200pt_bvh_build_ms",
 ]
 
 
@@ -75,6 +75,8 @@ def lib(count_traversal=False):
     L.b200pt_read_selection.argtypes = [vp, vp, vp, C.c_size_t]
     L.b200pt_set_frame_batch.argtypes = [vp, i32]
     L.b200pt_flush.argtypes = [vp]
+    L.b200pt_set_bvh_builder.argtypes = [vp, i32]
+    L.b200pt_bvh_build_ms.argtypes = [vp, C.POINTER(C.c_double)]
     L.b200pt_update_transforms.argtypes = [vp, C.POINTER(abi.RenderNode), u32]
     L.b200pt_get_selection_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     for name in EXPORTS:

@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -25,7 +26,7 @@
 #include <vector>
 
 #include "bvh.h"
-#include "refit.cuh"
+#include "lbvh.cuh"
 #include "shade.cuh"
 
 using namespace pt;
@@ -1262,6 +1263,44 @@ __global__ void __launch_bounds__(128) k_select(DevScene S, const __grid_constan
   }
 }
 
+// ---- BVH construction on the device (lbvh.cuh) --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_lbvh_bounds(LbvhWork W)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < W.m)
+    lbvhBounds(i, W);
+}
+__global__ void __launch_bounds__(256) k_lbvh_morton(LbvhWork W)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < W.M)
+    lbvhMorton(i, W);
+}
+__global__ void __launch_bounds__(256) k_lbvh_bitonic(unsigned long long* keys, uint32_t n, uint32_t j, uint32_t k)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if(t < n)
+    bitonicStep(t, keys, j, k);
+}
+__global__ void __launch_bounds__(256) k_lbvh_hierarchy(LbvhWork W)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i + 1 < W.m)
+    lbvhHierarchy(i, W);
+}
+__global__ void __launch_bounds__(256) k_lbvh_fit(LbvhWork W)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < W.m)
+    lbvhFit(i, W);
+}
+__global__ void __launch_bounds__(128) k_lbvh_emit(LbvhWork W, const int2* queueIn, uint32_t count, int2* queueOut)
+{
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if(q < count)
+    lbvhEmit(q, W, queueIn, queueOut);
+}
+
 // ---- BVH refit after a transform update (refit.cuh) ------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_refit_tris(float* tris, uint2* triMeta, uint32_t n, const b200pt_render_node* nodes, const DevPrim* prims)
 {
@@ -1439,6 +1478,8 @@ struct b200pt
   bool                haveScene = false;
   bool                hasVolume = false;
   int                 refillThreshold = kRefillThresholdDefault, postponeShift = 2;  // B200PT_REFILL / B200PT_POSTPONE env overrides (tuning)
+  int                 bvhBuilder = 0;  // 0: host SAH builder (bvh.cpp), 1: device LBVH (lbvh.cuh); b200pt_set_bvh_builder / B200PT_BVH_BUILDER
+  double              bvhBuildMs = 0.0;  // wall time of the last scene's tree builds
   bool                sortShade = false;  // B200PT_SORT_SHADE=1: material-sorted shade queue (measured)
   bool                leanShade = false;  // scene fits the FEAT_LEAN shade variant (scene_feature_detection analogue)
   uint32_t            featureMask = 0;
@@ -1599,6 +1640,123 @@ int allocPathState(b200pt* h, std::vector<void*>& owner, size_t n, PathState& P)
   owner.push_back(d);
   P.candInfo = reinterpret_cast<uint2*>(d);
   return B200PT_OK;
+}
+
+// Builds one compressed wide BVH over `m` of the scene's triangles ON THE DEVICE (lbvh.cuh) and brings it back in the host
+// builder's format, so that everything downstream of the builders (uploads, record tables, refit levels) is shared.
+// dInRec: 12 floats per global triangle in flatten order; dSubset: m global ids or nullptr.
+int buildWideBvhGpu(b200pt* h, const float* dInRec, const uint32_t* dSubset, uint32_t m, uint32_t triBaseOffset, WideBvh& out)
+{
+  out = WideBvh();
+  out.numTris = m;
+  if(m == 0)
+  {
+    out.nodes.assign(20, 0.f);
+    out.numNodes = 1;
+    return B200PT_OK;
+  }
+  uint32_t M = 1;
+  while(M < m)
+    M <<= 1;
+  std::vector<void*> tmp;
+  auto               dalloc = [&](size_t bytes) -> void* {
+    void* p = nullptr;
+    if(cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return nullptr;
+    }
+    tmp.push_back(p);
+    return p;
+  };
+  auto cleanup = [&](int rc) {
+    for(void* p : tmp)
+      cudaFree(p);
+    if(rc)
+      h->err = "GPU BVH build failed (allocation or launch)";
+    return rc;
+  };
+  LbvhWork W{};
+  W.m = m;
+  W.M = M;
+  W.inRec = dInRec;
+  W.subset = dSubset;
+  W.triBaseOffset = triBaseOffset;
+  W.primLo = (float4*)dalloc((size_t)m * 16);
+  W.primHi = (float4*)dalloc((size_t)m * 16);
+  W.keys = (unsigned long long*)dalloc((size_t)M * 8);
+  W.left = (int*)dalloc((size_t)m * 4);
+  W.right = (int*)dalloc((size_t)m * 4);
+  W.parentI = (int*)dalloc((size_t)m * 4);
+  W.parentL = (int*)dalloc((size_t)m * 4);
+  W.first = (uint32_t*)dalloc((size_t)m * 4);
+  W.last = (uint32_t*)dalloc((size_t)m * 4);
+  W.boxLo = (float4*)dalloc((size_t)m * 16);
+  W.boxHi = (float4*)dalloc((size_t)m * 16);
+  W.visits = (uint32_t*)dalloc((size_t)m * 4);
+  W.cbounds = (int*)dalloc(6 * 4);
+  W.nodes = (float*)dalloc(((size_t)m + 1) * 80);
+  W.tris = (float*)dalloc((size_t)m * 48);
+  W.triMeta = (uint32_t*)dalloc((size_t)m * 8);
+  W.counters = (uint32_t*)dalloc(4 * 4);
+  int2* queue[2] = {(int2*)dalloc(((size_t)m + 1) * 8), (int2*)dalloc(((size_t)m + 1) * 8)};
+  if(!W.primLo || !W.primHi || !W.keys || !W.left || !W.right || !W.parentI || !W.parentL || !W.first || !W.last || !W.boxLo || !W.boxHi || !W.visits || !W.cbounds
+     || !W.nodes || !W.tris || !W.triMeta || !W.counters || !queue[0] || !queue[1])
+    return cleanup(B200PT_E_NOMEM);
+  cudaStream_t st = h->stream;
+  const int    cbInit[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000};
+  const uint32_t cnt0[4] = {1u, 0u, 0u, 0u};  // wide node 0 is the root
+  bool         ok = cudaMemcpyAsync(W.cbounds, cbInit, sizeof(cbInit), cudaMemcpyHostToDevice, st) == cudaSuccess;
+  ok = ok && cudaMemcpyAsync(W.counters, cnt0, sizeof(cnt0), cudaMemcpyHostToDevice, st) == cudaSuccess;
+  ok = ok && cudaMemsetAsync(W.visits, 0, (size_t)m * 4, st) == cudaSuccess;
+  ok = ok && cudaMemsetAsync(W.nodes, 0, ((size_t)m + 1) * 80, st) == cudaSuccess;
+  if(!ok)
+    return cleanup(B200PT_E_CUDA);
+  const uint32_t gm = (m + 255) / 256, gM = (M + 255) / 256;
+  k_lbvh_bounds<<<gm, 256, 0, st>>>(W);
+  k_lbvh_morton<<<gM, 256, 0, st>>>(W);
+  for(uint32_t k = 2; k <= M; k <<= 1)
+    for(uint32_t j = k >> 1; j > 0; j >>= 1)
+      k_lbvh_bitonic<<<gM, 256, 0, st>>>(W.keys, M, j, k);
+  if(m >= 2)
+  {
+    k_lbvh_hierarchy<<<gm, 256, 0, st>>>(W);
+    k_lbvh_fit<<<gm, 256, 0, st>>>(W);
+  }
+  h->kernelLaunches += 4;
+  // collapse + emit, level by level
+  const int2 rootEntry = make_int2(m >= 2 ? 0 : ~0, 0);
+  if(cudaMemcpyAsync(queue[0], &rootEntry, sizeof(rootEntry), cudaMemcpyHostToDevice, st) != cudaSuccess)
+    return cleanup(B200PT_E_CUDA);
+  uint32_t count = 1, depth = 0;
+  int      cur = 0;
+  while(count)
+  {
+    const uint32_t zero = 0;
+    if(cudaMemcpyAsync(&W.counters[2], &zero, 4, cudaMemcpyHostToDevice, st) != cudaSuccess)
+      return cleanup(B200PT_E_CUDA);
+    k_lbvh_emit<<<(count + 127) / 128, 128, 0, st>>>(W, queue[cur], count, queue[1 - cur]);
+    h->kernelLaunches++;
+    if(cudaMemcpyAsync(&count, &W.counters[2], 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+      return cleanup(B200PT_E_CUDA);
+    cur = 1 - cur;
+    depth++;
+    if(depth > 64)
+      return cleanup(B200PT_E_CUDA);
+  }
+  uint32_t cnt[2] = {0, 0};
+  if(cudaMemcpy(cnt, W.counters, 8, cudaMemcpyDeviceToHost) != cudaSuccess || cnt[1] != m || cnt[0] == 0 || cnt[0] > m + 1)
+    return cleanup(B200PT_E_CUDA);
+  out.numNodes = cnt[0];
+  out.maxDepth = depth;
+  out.nodes.resize((size_t)cnt[0] * 20);
+  out.tris.resize((size_t)m * 12);
+  out.triMeta.resize((size_t)m * 2);
+  if(cudaMemcpy(out.nodes.data(), W.nodes, out.nodes.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess
+     || cudaMemcpy(out.tris.data(), W.tris, out.tris.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess
+     || cudaMemcpy(out.triMeta.data(), W.triMeta, out.triMeta.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return cleanup(B200PT_E_CUDA);
+  return cleanup(B200PT_OK);
 }
 
 void freeRayPool(b200pt* h)
@@ -1826,6 +1984,8 @@ int b200pt_create(b200pt_t** out, int cuda_device)
     h->postponeShift = atoi(e);
   if(const char* e = getenv("B200PT_SORT_SHADE"))
     h->sortShade = atoi(e) != 0;
+  if(const char* e = getenv("B200PT_BVH_BUILDER"))
+    h->bvhBuilder = (strcmp(e, "gpu") == 0 || strcmp(e, "1") == 0) ? 1 : 0;
   bool ok = true;
   auto need = [&](cudaError_t e) { ok = ok && (e == cudaSuccess); };
   cudaDeviceProp prop{};
@@ -2236,18 +2396,62 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
           gidA.push_back(i);
         }
       }
-    std::thread tO, tA;
-    if(anyNonOpaque)
+    const auto tBuild0 = std::chrono::steady_clock::now();
+    if(h->bvhBuilder == 1)
     {
-      tO = std::thread([&] { buildWideBvh(flatO, gidO, 0u, bvhO); });
-      tA = std::thread([&] { buildWideBvh(flatA, gidA, (uint32_t)flatO.size(), bvhA); });
+      // device LBVH: the flattened records go up once (flatten order = global id order), the subsets as id lists
+      std::vector<float> rec(flat.size() * 12);
+      for(size_t i = 0; i < flat.size(); i++)
+      {
+        const FlatTri& T = flat[i];
+        float*         R = &rec[i * 12];
+        const uint32_t w0 = T.rnode | (T.flags << 28), prim = T.prim, gid = (uint32_t)i;
+        memcpy(R, T.v0, 12);
+        memcpy(R + 3, &w0, 4);
+        memcpy(R + 4, T.e1, 12);
+        memcpy(R + 7, &prim, 4);
+        memcpy(R + 8, T.e2, 12);
+        memcpy(R + 11, &gid, 4);
+      }
+      float *   dRec = nullptr;
+      uint32_t *dO = nullptr, *dA = nullptr;
+      std::vector<void*> tmpAllocs;
+      if((rc = upload(h, tmpAllocs, rec.data(), rec.size(), &dRec)) == 0 && anyNonOpaque)
+      {
+        rc = upload(h, tmpAllocs, gidO.data(), gidO.size(), &dO);
+        if(!rc)
+          rc = upload(h, tmpAllocs, gidA.data(), gidA.size(), &dA);
+      }
+      if(!rc)
+        rc = buildWideBvhGpu(h, dRec, nullptr, (uint32_t)flat.size(), 0u, bvh);
+      if(!rc && anyNonOpaque)
+      {
+        rc = buildWideBvhGpu(h, dRec, dO, (uint32_t)gidO.size(), 0u, bvhO);
+        if(!rc)
+          rc = buildWideBvhGpu(h, dRec, dA, (uint32_t)gidA.size(), (uint32_t)gidO.size(), bvhA);
+      }
+      cudaStreamSynchronize(h->stream);
+      for(void* p : tmpAllocs)
+        cudaFree(p);
+      if(rc)
+        return rc;
     }
-    buildWideBvh(flat, gids, 0u, bvh);
-    if(anyNonOpaque)
+    else
     {
-      tO.join();
-      tA.join();
+      std::thread tO, tA;
+      if(anyNonOpaque)
+      {
+        tO = std::thread([&] { buildWideBvh(flatO, gidO, 0u, bvhO); });
+        tA = std::thread([&] { buildWideBvh(flatA, gidA, (uint32_t)flatO.size(), bvhA); });
+      }
+      buildWideBvh(flat, gids, 0u, bvh);
+      if(anyNonOpaque)
+      {
+        tO.join();
+        tA.join();
+      }
     }
+    h->bvhBuildMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tBuild0).count();
   }
   float *   dBvhNodes, *dTris;
   uint32_t* dMeta;
@@ -2512,6 +2716,22 @@ int b200pt_bvh_info(b200pt_t* h, uint64_t* node_bytes, uint64_t* tri_bytes, uint
     *num_nodes = h->numNodes;
   if(num_tris)
     *num_tris = h->numTris;
+  return B200PT_OK;
+}
+
+int b200pt_set_bvh_builder(b200pt_t* h, int kind)
+{
+  if(!h || (kind != 0 && kind != 1))
+    return B200PT_E_INVALID;
+  h->bvhBuilder = kind;
+  return B200PT_OK;
+}
+
+int b200pt_bvh_build_ms(b200pt_t* h, double* ms)
+{
+  if(!h || !ms || !h->haveScene)
+    return B200PT_E_INVALID;
+  *ms = h->bvhBuildMs;
   return B200PT_OK;
 }
 

@@ -34,6 +34,11 @@ static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s)
 }
 using std::isnan;
 using std::isinf;
+// sequential stand-ins for the atomics of the build kernels (the host harness runs the "threads" one after another)
+template <typename T>
+static inline T atomicAdd(T* p, T v) { const T o = *p; *p = o + v; return o; }
+static inline int atomicMin(int* p, int v) { const int o = *p; if(v < o) *p = v; return o; }
+static inline int atomicMax(int* p, int v) { const int o = *p; if(v > o) *p = v; return o; }
 // one lane per "warp"
 static inline unsigned __activemask() { return 1u; }
 static inline unsigned __ballot_sync(unsigned, int pred) { return pred ? 1u : 0u; }

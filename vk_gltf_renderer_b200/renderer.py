@@ -118,6 +118,15 @@ class PathTracer:
         d = resources.scene.desc()
         self._ck(self._L.b200pt_set_scene(self._h, C.byref(d)), "b200pt_set_scene")
 
+    def set_bvh_builder(self, kind):
+        """0: host SAH builder, 1: device LBVH builder (takes effect at the next onSceneInvalidated)"""
+        self._ck(self._L.b200pt_set_bvh_builder(self._h, kind), "b200pt_set_bvh_builder")
+
+    def bvh_build_ms(self):
+        ms = C.c_double()
+        self._ck(self._L.b200pt_bvh_build_ms(self._h, C.byref(ms)), "b200pt_bvh_build_ms")
+        return ms.value
+
     def update_transforms(self, resources):
         """the render nodes of resources.scene moved (same nodes / primitives / materials): refit instead of a rebuild
         (SceneRtx::updateTopLevelAS analogue, b200pt_update_transforms)"""
