@@ -522,7 +522,10 @@ def main():
         ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
     except Exception:
         ncu_traffic = {}
-    tr = ncu_traffic.get(dom)
+    tr = ncu_traffic.get(dom) if (args.config == 3 and world == 1) else None  # the capture is of the default workload
+    if tr:
+        tr = dict(tr, note="dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` capture named in "
+                           "`source` (taken with this build under the profiler, not during this run)")
     roof = {"kernel": dom, "bound": "hbm", "achieved": stages[dom]["achieved_GBps"], "peak": peak_gbs, "unit": "GB/s",
             "frac": (stages[dom]["achieved_GBps"] / peak_gbs) if stages[dom]["achieved_GBps"] else None,
             "traffic": tr["bytes"] if tr else None, "traffic_detail": tr,
