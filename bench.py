@@ -316,7 +316,9 @@ def main():
     # launches per frame.  At N > 1 a rank's tile is 1/N of the frame, so the batch grows with N and every kernel keeps the size it
     # has on one GPU (round 1, one frame per launch chain: 0.61 efficiency at N = 8).
     lanes = 4
-    batch = min(16, 4 * world)  # measured at N = 1 (r02g): batch 1 -> 821, 2 -> 873, 4 -> 906 Mray/s with 4 frames in flight
+    # measured at N = 1 (r02m, frames in flight 4): batch 1 -> 821 (r02g), 4 -> 926, 6 -> 949, 8 -> 947 Mray/s.  The batch grows with N so
+    # that a rank's wavefront stays as large as on one GPU, but never beyond half the timed steps (two wavefronts overlap their tails)
+    batch = max(1, min(8 * world, 64, (args.steps + 1) // 2))
     if os.environ.get("B200PT_FRAMES_IN_FLIGHT"):
         lanes = int(os.environ["B200PT_FRAMES_IN_FLIGHT"])
     if os.environ.get("B200PT_FRAME_BATCH"):

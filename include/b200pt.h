@@ -356,7 +356,7 @@ int b200pt_wait_read(b200pt_t* h, int slot);
  * or expect the accumulation image to be cleared like a resize does. */
 int b200pt_set_frames_in_flight(b200pt_t* h, int n);
 
-/* Frame batching: up to n (1..16, default 1 = off) consecutive b200pt_render_frame calls whose frame constants are identical and
+/* Frame batching: up to n (1..64, default 1 = off) consecutive b200pt_render_frame calls whose frame constants are identical and
  * whose push constants only advance the way the host loop advances them (frameCount + 1, totalSamples + numSamples; the
  * first-frame flag on the first only) are collected and run as ONE wavefront of n x pixels paths; the frames are folded into
  * the image in frame order, so the result is bit-identical to unbatched rendering.  A call that does not continue the

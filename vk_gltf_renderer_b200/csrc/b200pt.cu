@@ -3097,7 +3097,7 @@ int b200pt_set_frames_in_flight(b200pt_t* h, int n)
 
 int b200pt_set_frame_batch(b200pt_t* h, int n)
 {
-  if(!h || n < 1 || n > 16)
+  if(!h || n < 1 || n > 64)
     return B200PT_E_INVALID;
   if(n == h->batch)
     return B200PT_OK;

@@ -58,6 +58,17 @@ constexpr float kByteBias = 32768.0f, kByteSlack = 0.00390625f;
 #else
 constexpr float kByteBias = 131072.0f, kByteSlack = 0.015625f;
 #endif
+// byte J of x as an integer; B200PT_DP4A_EXTRACT: with IDP.4A on the IMAD pipe instead of SHF + LOP3 on the ALU pipe
+template <int J>
+PT_D uint32_t extractByteJ(uint32_t x)
+{
+#if defined(__CUDA_ARCH__) && defined(B200PT_DP4A_EXTRACT)
+  return __dp4a(x, 1u << (8 * J), 0u);
+#else
+  return (x >> (8 * J)) & 0xffu;
+#endif
+}
+
 template <int J>
 PT_D float biasedByte(uint32_t x, uint32_t pool)
 {
@@ -301,8 +312,8 @@ struct TravState
     const float tf = fminf(fminf(tmaxx, tmaxy), fminf(tmaxz, bound));                                                      \
     /* widen by a few ulp: keeps the box test conservative w.r.t. the triangle test */                                     \
     const bool     in = tn <= tf * 1.000001f;                                                                              \
-    const uint32_t childBits = in ? extractByte(childBits4, J) : 0u;                                                       \
-    hitMask |= childBits << extractByte(bitIndex4, J);                                                                     \
+    const uint32_t childBits = in ? extractByteJ<J>(childBits4) : 0u;                                                      \
+    hitMask |= childBits << extractByteJ<J>(bitIndex4);                                                                    \
   }
           PT_CHILD(0)
           PT_CHILD(1)
