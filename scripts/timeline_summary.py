@@ -23,7 +23,8 @@ def main():
         print("empty timeline")
         return
     frames = sorted({r[0] for r in rows})
-    keep = set(frames[skip:-1]) if len(frames) > skip + 2 else set(frames)
+    # (a 'frame' is one launch chain = one batch of frames; the first ones are warm-up)
+    keep = set(frames[skip:-1]) if len(frames) > skip + 3 else (set(frames[skip:]) if len(frames) > skip else set(frames))
     rows = [r for r in rows if r[0] in keep]
     t0, t1 = min(r[3] for r in rows), max(r[4] for r in rows)
     n_frames = len(keep)
@@ -40,7 +41,7 @@ def main():
         cur += d
         last = t
     span = t1 - t0
-    print(f"{path}: {n_frames} frames, {len(rows)} launches, span {span:.2f} ms = {span / n_frames:.3f} ms/frame")
+    print(f"{path}: {n_frames} launch chains (batches), {len(rows)} launches, span {span:.2f} ms = {span / n_frames:.3f} ms per chain")
     print(f"  some kernel of ours running: {100 * busy / span:.1f} % of the span; mean kernels in flight {depth_time / span:.2f}")
     per = defaultdict(lambda: [0.0, 0])
     for r in rows:
