@@ -191,7 +191,7 @@ __device__ __forceinline__ uint32_t fetchWork(bool need, uint32_t* workCounter, 
 // mode: TRACE_CONT = continuation round (the paths in the queue had all kCand candidates rejected by k_alpha and resume
 // behind the last one; P.hit seeds the opaque bound and is refined), TRACE_TMIN = rayO.w carries tmin (ray-level API).
 #ifndef B200PT_TRACE_MINBLOCKS
-#define B200PT_TRACE_MINBLOCKS 6  // 80 registers: 6 blocks/SM; measured 470 -> 488 Mray/s against the unconstrained 96-register build
+#define B200PT_TRACE_MINBLOCKS 7  // 72 registers: 7 blocks/SM.  Measured (r02o, batched build): 6 blocks / 80 registers 944, 7 / 72 967 Mray/s (round 1: 5 -> 6 +4 %)
 #endif
 enum : int
 {
