@@ -1074,12 +1074,20 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathStat
 constexpr int kSortMaxBuckets = 1024;
 constexpr int kSortItems = 4;  // paths per thread per pass
 
+// KEY 0: material of the hit (shade queue); KEY 1: direction octant of the path's next ray (trace queue, experiment B200PT_SORT_RAYS)
+template <int KEY>
 __device__ __forceinline__ uint32_t shadeKey(const PathState& P, const DevScene& S, uint32_t path, uint32_t nb)
 {
+  if(KEY == 1)
+  {
+    const float4 d = P.rayD[path];
+    return (d.x < 0.f ? 0u : 4u) | (d.y < 0.f ? 0u : 2u) | (d.z < 0.f ? 0u : 1u);
+  }
   const uint32_t slot = __float_as_uint(P.hit[path].w);
   return slot == 0xFFFFFFFFu ? nb - 1u : min(__ldg(&S.matOfSlot[slot]), nb - 2u);
 }
 
+template <int KEY>
 __global__ void __launch_bounds__(256) k_sort_count(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn, uint32_t* bucketCount, uint32_t nb)
 {
   __shared__ uint32_t sCnt[kSortMaxBuckets];
@@ -1089,7 +1097,7 @@ __global__ void __launch_bounds__(256) k_sort_count(PathState P, DevScene S, con
   const uint32_t count = *cntIn;
   const uint32_t stride = gridDim.x * blockDim.x;
   for(uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
-    atomicAdd(&sCnt[shadeKey(P, S, q[k], nb)], 1u);
+    atomicAdd(&sCnt[shadeKey<KEY>(P, S, q[k], nb)], 1u);
   __syncthreads();
   for(uint32_t b = threadIdx.x; b < nb; b += blockDim.x)
     if(sCnt[b])
@@ -1117,6 +1125,7 @@ __global__ void __launch_bounds__(1024) k_sort_scan(uint32_t* bucketCount, uint3
   }
 }
 
+template <int KEY>
 __global__ void __launch_bounds__(256) k_sort_scatter(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn, uint32_t* bucketCursor,
                                                       uint32_t* __restrict__ qSorted, uint32_t nb)
 {
@@ -1137,7 +1146,7 @@ __global__ void __launch_bounds__(256) k_sort_scatter(PathState P, DevScene S, c
       if(k < count)
       {
         path[i] = q[k];
-        key[i] = shadeKey(P, S, path[i], nb);
+        key[i] = shadeKey<KEY>(P, S, path[i], nb);
         off[i] = atomicAdd(&sCnt[key[i]], 1u);
       }
     }
@@ -1480,7 +1489,9 @@ struct b200pt
   int                 refillThreshold = kRefillThresholdDefault, postponeShift = 2;  // B200PT_REFILL / B200PT_POSTPONE env overrides (tuning)
   int                 bvhBuilder = 0;  // 0: host SAH builder (bvh.cpp), 1: device LBVH (lbvh.cuh); b200pt_set_bvh_builder / B200PT_BVH_BUILDER
   double              bvhBuildMs = 0.0;  // wall time of the last scene's tree builds
-  bool                sortShade = false;  // B200PT_SORT_SHADE=1: material-sorted shade queue (measured)
+  int                 walkGridPerSM = 8, shadeGridPerSM = 2;  // CTAs per SM of the persistent walk / shade grids (B200PT_WALK_GRID, B200PT_SHADE_GRID)
+  bool                sortShade = false;
+  bool                sortRays = false;   // B200PT_SORT_RAYS=1 (experiment): trace queue bucketed by ray direction octant  // B200PT_SORT_SHADE=1: material-sorted shade queue (measured)
   bool                leanShade = false;  // scene fits the FEAT_LEAN shade variant (scene_feature_detection analogue)
   uint32_t            featureMask = 0;
   uint64_t            nodeBytes = 0, triBytes = 0;
@@ -1984,6 +1995,12 @@ int b200pt_create(b200pt_t** out, int cuda_device)
     h->postponeShift = atoi(e);
   if(const char* e = getenv("B200PT_SORT_SHADE"))
     h->sortShade = atoi(e) != 0;
+  if(const char* e = getenv("B200PT_SORT_RAYS"))
+    h->sortRays = atoi(e) != 0;
+  if(const char* e = getenv("B200PT_WALK_GRID"))
+    h->walkGridPerSM = std::min(std::max(atoi(e), 1), 32);
+  if(const char* e = getenv("B200PT_SHADE_GRID"))
+    h->shadeGridPerSM = std::min(std::max(atoi(e), 1), 8);
   if(const char* e = getenv("B200PT_BVH_BUILDER"))
     h->bvhBuilder = (strcmp(e, "gpu") == 0 || strcmp(e, "1") == 0) ? 1 : 0;
   bool ok = true;
@@ -3322,15 +3339,26 @@ static int launchFrames(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
         // geometry walks are persistent kernels; the texture-dependent any-hit tests and the path bookkeeping run
         // as dense one-thread-per-path kernels (k_alpha, k_resolve) sized by the device-side queue counters
         const int gP = gridFor(h, 8);
+        const int gW = gridFor(h, h->walkGridPerSM);  // persistent walk kernels
+        const int gS = gridFor(h, h->shadeGridPerSM);  // persistent shade kernel (512-thread CTAs, one resident per SM)
         // geometry walks are persistent kernels; the texture-dependent any-hit tests and the path bookkeeping run
         // as dense kernels (k_alpha, k_resolve) sized by the device-side queue counters.  Any-hit: resolve kCand
         // candidates, one continuation round for the paths that used them all up, then whatever is still
         // undecided finishes inside the last k_alpha.
-        timed(tTrace, [&] { k_trace<<<gP, 128, 0, st>>>(L.P, h->S, qT, &cntTrace[it], &workTrace[it], L.dQ[4], &cntAlpha[it], h->dStats, h->refillThreshold, h->postponeShift, 0); });
+        const uint32_t* qWalk = qT;
+        if(h->sortRays && it > 0)
+        {
+          // experiment: the trace queue bucketed by direction octant (dQ[3], the shadow queue, is free until k_shade writes it)
+          timed(tOther, [&] { k_sort_count<1><<<gridFor(h, 4), 256, 0, st>>>(L.P, h->S, qT, &cntTrace[it], L.dBuckets, 8u); });
+          timed(tOther, [&] { k_sort_scan<<<1, kSortMaxBuckets, 0, st>>>(L.dBuckets, L.dBuckets + kSortMaxBuckets, 8u); });
+          timed(tOther, [&] { k_sort_scatter<1><<<gridFor(h, 4), 256, 0, st>>>(L.P, h->S, qT, &cntTrace[it], L.dBuckets + kSortMaxBuckets, L.dQ[3], 8u); });
+          qWalk = L.dQ[3];
+        }
+        timed(tTrace, [&] { k_trace<<<gW, 128, 0, st>>>(L.P, h->S, qWalk, &cntTrace[it], &workTrace[it], L.dQ[4], &cntAlpha[it], h->dStats, h->refillThreshold, h->postponeShift, 0); });
         if(h->S.hasAlpha)
         {
           timed(tAnyHit, [&] { k_alpha<false><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlpha[it], L.dQ[5], &cntCont[it], h->dStats, 0); });
-          timed(tTrace, [&] { k_trace<<<gP, 128, 0, st>>>(L.P, h->S, L.dQ[5], &cntCont[it], &workCont[it], L.dQ[4], &cntAlpha1[it], h->dStats, h->refillThreshold, h->postponeShift, 1); });
+          timed(tTrace, [&] { k_trace<<<gW, 128, 0, st>>>(L.P, h->S, L.dQ[5], &cntCont[it], &workCont[it], L.dQ[4], &cntAlpha1[it], h->dStats, h->refillThreshold, h->postponeShift, 1); });
           timed(tAnyHit, [&] { k_alpha<false><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlpha1[it], nullptr, nullptr, h->dStats, TRACE_CONT); });
         }
         const uint32_t* qShade = qT;
@@ -3338,22 +3366,22 @@ static int launchFrames(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
         {
           // dQ[4] (the any-hit queue) is free between the closest-hit any-hit kernels and the shadow walk
           const uint32_t nb = (uint32_t)h->S.numMaterials + 1u;
-          timed(tOther, [&] { k_sort_count<<<gridFor(h, 4), 256, 0, st>>>(L.P, h->S, qT, &cntTrace[it], L.dBuckets, nb); });
+          timed(tOther, [&] { k_sort_count<0><<<gridFor(h, 4), 256, 0, st>>>(L.P, h->S, qT, &cntTrace[it], L.dBuckets, nb); });
           timed(tOther, [&] { k_sort_scan<<<1, kSortMaxBuckets, 0, st>>>(L.dBuckets, L.dBuckets + kSortMaxBuckets, nb); });
-          timed(tOther, [&] { k_sort_scatter<<<gridFor(h, 4), 256, 0, st>>>(L.P, h->S, qT, &cntTrace[it], L.dBuckets + kSortMaxBuckets, L.dQ[4], nb); });
+          timed(tOther, [&] { k_sort_scatter<0><<<gridFor(h, 4), 256, 0, st>>>(L.P, h->S, qT, &cntTrace[it], L.dBuckets + kSortMaxBuckets, L.dQ[4], nb); });
           qShade = L.dQ[4];
         }
         timed(tShade, [&] {
           if(h->leanShade)
-            k_shade<FEAT_LEAN><<<gP * 128 / SHADE_BLOCK, SHADE_BLOCK, 2048, st>>>(L.P, h->S, F, qShade, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
+            k_shade<FEAT_LEAN><<<gS, SHADE_BLOCK, 2048, st>>>(L.P, h->S, F, qShade, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
           else
-            k_shade<FEAT_ALL><<<gP * 128 / SHADE_BLOCK, SHADE_BLOCK, 2048, st>>>(L.P, h->S, F, qShade, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
+            k_shade<FEAT_ALL><<<gS, SHADE_BLOCK, 2048, st>>>(L.P, h->S, F, qShade, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
         });
-        timed(tPost, [&] { k_shadow<<<gP, 128, 0, st>>>(L.P, h->S, L.dQ[3], &cntShadow[it], &workPost[it], L.dQ[4], &cntAlphaS[it], h->dStats, h->refillThreshold, h->postponeShift, 0); });
+        timed(tPost, [&] { k_shadow<<<gW, 128, 0, st>>>(L.P, h->S, L.dQ[3], &cntShadow[it], &workPost[it], L.dQ[4], &cntAlphaS[it], h->dStats, h->refillThreshold, h->postponeShift, 0); });
         if(h->S.hasAlpha)
         {
           timed(tAnyHit, [&] { k_alpha<true><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS[it], L.dQ[5], &cntContS[it], h->dStats, 0); });
-          timed(tPost, [&] { k_shadow<<<gP, 128, 0, st>>>(L.P, h->S, L.dQ[5], &cntContS[it], &workContS[it], L.dQ[4], &cntAlphaS1[it], h->dStats, h->refillThreshold, h->postponeShift, 1); });
+          timed(tPost, [&] { k_shadow<<<gW, 128, 0, st>>>(L.P, h->S, L.dQ[5], &cntContS[it], &workContS[it], L.dQ[4], &cntAlphaS1[it], h->dStats, h->refillThreshold, h->postponeShift, 1); });
           timed(tAnyHit, [&] { k_alpha<true><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS1[it], nullptr, nullptr, h->dStats, TRACE_CONT); });
         }
         timed(tResolve, [&] { k_resolve<<<gridFor(h, 4), 256, 0, st>>>(L.P, F, L.dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats); });
