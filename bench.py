@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--depth", type=int, default=0)
+    ap.add_argument("--omm", type=int, default=int(os.environ.get("B200PT_BENCH_OMM", "0")),
+                    help="bake opacity micromaps of this subdivision level for the alpha-MASK triangles of the scene (0 = the asset as it is, without)")
     ap.add_argument("--tex", type=int, default=2048)
     ap.add_argument("--detail", type=float, default=1.0)
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the frame the CPU baseline renders (0 = sized for ~12 s)")
@@ -109,6 +111,11 @@ def build_workload(args):
                 os.replace(tmp, cache)
             except Exception:
                 pass
+    scn.omm_stats = None
+    if getattr(args, "omm", 0) > 0:
+        # the offline bake an asset with EXT_mesh_opacity_micromap went through (vk_gltf_renderer_b200/omm.py); untimed, like scene loading
+        from vk_gltf_renderer_b200 import omm
+        scn.omm_stats = omm.bake_opacity_micromaps(scn, level=args.omm)
     return scn, env
 
 
@@ -117,7 +124,7 @@ def workload_config(args, scn, n_gpus):
                         % (CONFIG_SCENES[getattr(args, "config", 3)][0], args.width, args.height, args.depth),
             "baseline_config": getattr(args, "config", 3),
             "triangles": scn.num_triangles(), "materials": len(scn.materials), "textures": len(scn.textures),
-            "texture_size": args.tex, "partition": "1 GPU" if n_gpus == 1 else "interleaved row bands x%d, scene replicated; %d consecutive frames run as one wavefront per rank (b200pt_set_frame_batch) "
+            "texture_size": args.tex, "opacity_micromaps": getattr(scn, "omm_stats", None), "partition": "1 GPU" if n_gpus == 1 else "interleaved row bands x%d, scene replicated; %d consecutive frames run as one wavefront per rank (b200pt_set_frame_batch) "
                          "and ONE NCCL all-gather of the RGBA32F tiles per batch (accumulation is linear: SURVEY.md section 8e)" % (n_gpus, n_gpus),
             "l2_policy": "no explicit flush: every frame streams its lane's path state (248 B x %d paths per rank = %.0f MB) plus the %.0f MB image, "
                          "and consecutive frames use different lanes; the working set exceeds the 126 MB L2 for N <= 4 "

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200PT_ABI_VERSION 3
+#define B200PT_ABI_VERSION 4
 
 /* error codes */
 #define B200PT_OK 0
@@ -289,6 +289,51 @@ const char* b200pt_last_error(const b200pt_t* h);
  * (renderer_pathtracer.hpp:72).  Copies all arrays to HBM, builds the software wide BVH over the
  * world-space triangles of every visible render node, creates bindless texture objects. */
 int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* scene);
+
+/* ---- opacity micromaps (reference: src/gltf_scene_omm.{hpp,cpp} -- EXT_mesh_opacity_micromap uploaded as VK_EXT_opacity_micromap
+ * build input and attached to the BLAS geometry, gltf_scene_rtx.cpp; docs/RENDERING_ARCHITECTURE.md:65-78) ------------------------
+ * The arrays are the extension's own: `data` = packed opacity states in the Vulkan micro-triangle order ("bird curve",
+ * VK_EXT_opacity_micromap bary2index), `triangles` = VkMicromapTriangleEXT records.  What the RT cores do with them, the software
+ * walk does: a micro-triangle whose state is OPAQUE is committed like a FORCE_OPAQUE triangle, a TRANSPARENT one is culled, both
+ * WITHOUT the any-hit alpha evaluation and its rand() (raytracer_interface.h.slang:93-100); the two UNKNOWN states still go through
+ * the any-hit path.  Nothing is baked here: the host hands over what the asset carries (vk_gltf_renderer_b200/omm.py can bake the
+ * arrays from a MASK texture for assets that have none). */
+#define B200PT_OMM_FORMAT_2_STATE 1 /* VK_OPACITY_MICROMAP_FORMAT_2_STATE_EXT: 1 bit, 0 transparent / 1 opaque                   */
+#define B200PT_OMM_FORMAT_4_STATE 2 /* VK_OPACITY_MICROMAP_FORMAT_4_STATE_EXT: 2 bits, + 2 unknown-transparent / 3 unknown-opaque */
+#define B200PT_OMM_INDEX_FULLY_TRANSPARENT (-1) /* VK_OPACITY_MICROMAP_SPECIAL_INDEX_*_EXT */
+#define B200PT_OMM_INDEX_FULLY_OPAQUE (-2)
+#define B200PT_OMM_INDEX_FULLY_UNKNOWN_TRANSPARENT (-3)
+#define B200PT_OMM_INDEX_FULLY_UNKNOWN_OPAQUE (-4)
+#define B200PT_OMM_MAX_LEVEL 12
+
+typedef struct b200pt_micromap_triangle /* VkMicromapTriangleEXT */
+{
+  uint32_t dataOffset; /* bytes into b200pt_micromap::data */
+  uint16_t subdivisionLevel;
+  uint16_t format;
+} b200pt_micromap_triangle;
+
+typedef struct b200pt_micromap /* one entry of the extension's root micromaps[] (gltf_scene_omm.cpp:180-250) */
+{
+  const uint8_t*                  data;
+  uint64_t                        dataSize;
+  const b200pt_micromap_triangle* triangles;
+  uint32_t                        numTriangles;
+} b200pt_micromap;
+
+typedef struct b200pt_primitive_omm /* SceneOmm::PrimitiveOmm (gltf_scene_omm.hpp:52-60): keyed by renderPrimID */
+{
+  uint32_t       renderPrimID;
+  uint32_t       micromap;     /* index into micromaps[]                                                          */
+  uint32_t       baseTriangle; /* micromapBaseTriangle, added to every non-negative index                         */
+  const int32_t* indices;      /* one per triangle of the primitive (or a special index < 0); NULL = identity     */
+  uint32_t       numIndices;   /* length of `indices` (>= the primitive's triangleCount), 0 with NULL             */
+} b200pt_primitive_omm;
+
+/* SceneOmm::create.  Copies the arrays; they take effect at the next b200pt_set_scene (like SceneRtx consuming them at BLAS build).
+ * num_prims == 0 removes them.  B200PT_E_INVALID on out-of-range indices / offsets, formats other than the two above or levels
+ * beyond B200PT_OMM_MAX_LEVEL (checked again against the primitives' triangle counts in b200pt_set_scene). */
+int b200pt_set_opacity_micromaps(b200pt_t* h, const b200pt_micromap* micromaps, uint32_t num_micromaps, const b200pt_primitive_omm* prims, uint32_t num_prims);
 
 /* Which builder b200pt_set_scene uses for the three trees (closest-hit, opaque-only, non-opaque): 0 = the host builder (binned
  * SAH + optimal 8-wide collapse + axis maps, csrc/bvh.cpp; default, the better tree), 1 = the DEVICE builder (LBVH: Morton sort,

@@ -33,6 +33,7 @@ def lib():
         L.oracle_create.restype = C.c_void_p
         L.oracle_destroy.argtypes = [C.c_void_p]
         L.oracle_set_scene.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_set_opacity_micromaps.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.oracle_set_environment.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.oracle_get_environment.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_render_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -83,6 +84,9 @@ class Oracle:
         rc = self.L.oracle_set_scene(self.h, C.byref(d))
         if rc:
             raise RuntimeError(f"oracle_set_scene failed: {rc}")
+        mm, nmm, po, npo, keep = scene.omm_desc()
+        if self.L.oracle_set_opacity_micromaps(self.h, C.byref(mm), nmm, C.byref(po), npo):
+            raise RuntimeError("oracle_set_opacity_micromaps failed")
 
     def set_environment(self, rgb):
         rgb = np.ascontiguousarray(rgb, np.float32)

@@ -126,6 +126,21 @@ struct Oracle
     std::vector<BvhNode>  bvh;
   };
   Tree treeOpaque, treeAlpha;  // FORCE_OPAQUE triangles / any-hit (non-opaque) triangles
+  // opacity micromaps (src/gltf_scene_omm.cpp: the asset's EXT_mesh_opacity_micromap arrays), keyed by render primitive
+  struct Micromap
+  {
+    std::vector<uint8_t>                  data;
+    std::vector<b200pt_micromap_triangle> tris;
+  };
+  struct PrimOmm
+  {
+    uint32_t             micromap = 0, base = 0;
+    bool                 hasIdx = false;
+    std::vector<int32_t> idx;
+  };
+  std::vector<Micromap> micromaps;
+  std::vector<PrimOmm>  primOmm;      // one per linked primitive
+  std::vector<int>      ommOfPrim;    // renderPrimID -> primOmm index, -1 = none (sized lazily)
   // environment
   int                   envW = 0, envH = 0;
   std::vector<float>    envRgba;
@@ -611,9 +626,87 @@ static inline bool slab(const BvhNode& N, const Ray& r, float3 invD, float tmax,
   return t0 <= t1;
 }
 
+// -------------------------------------------------------------------------------------------------
+// opacity micromaps: what the hardware traversal does with them (docs/RENDERING_ARCHITECTURE.md:65-78,
+// raytracer_interface.h.slang:93-100): an OPAQUE micro-triangle is a committed hit without an any-hit
+// invocation, a TRANSPARENT one is culled, the UNKNOWN states are any-hit candidates as before.
+// Micro-triangle order: VK_EXT_opacity_micromap bary2index (specification text, restated; unpinned).
+// -------------------------------------------------------------------------------------------------
+enum
+{
+  OMM_TRANSPARENT = 0,
+  OMM_OPAQUE = 1,
+  OMM_UNKNOWN = 2
+};
+
+static uint32_t ommInterleave(uint32_t x)
+{
+  uint32_t r = 0;
+  for(int b = 0; b < 16; b++)
+    r |= ((x >> b) & 1u) << (2 * b);
+  return r;
+}
+
+static uint32_t ommBary2Index(float u, float v, uint32_t level)
+{
+  u = std::min(std::max(u, 0.0f), 1.0f);
+  v = std::min(std::max(v, 0.0f), 1.0f);
+  const uint32_t n = 1u << level;
+  const float    fu = u * (float)n, fv = v * (float)n;
+  uint32_t       iu = (uint32_t)fu, iv = (uint32_t)fv;
+  const float    uf = fu - (float)iu, vf = fv - (float)iv;
+  iu = std::min(iu, n - 1u);
+  iv = std::min(iv, n - 1u);
+  const uint32_t iuv = iu + iv;
+  if(iuv >= n)
+    iu -= iuv - n + 1u;
+  uint32_t iw = ~(iu + iv);
+  if(uf + vf >= 1.0f && iuv < n - 1u)
+    --iw;
+  const uint32_t b0 = ~(iu ^ iw) & (n - 1u);
+  const uint32_t t = (iu ^ iv) & b0;
+  uint32_t       f = t;
+  f ^= f >> 1;
+  f ^= f >> 2;
+  f ^= f >> 4;
+  f ^= f >> 8;
+  const uint32_t b1 = ((f ^ iu) & ~b0) | t;
+  return ommInterleave(b0) | (ommInterleave(b1) << 1);
+}
+
+// state of the micro-triangle of flattened triangle T under barycentrics (u, v) (weights of the primitive's 2nd / 3rd vertex)
+static int ommState(const Oracle& o, const FlatTri& T, float u, float v)
+{
+  if(o.primOmm.empty())
+    return OMM_UNKNOWN;
+  const uint32_t prim = (uint32_t)o.nodes[T.rnode].renderPrimID;
+  const int      k = prim < o.ommOfPrim.size() ? o.ommOfPrim[prim] : -1;
+  if(k < 0)
+    return OMM_UNKNOWN;
+  const Oracle::PrimOmm& po = o.primOmm[(size_t)k];
+  const int32_t          idx = po.hasIdx ? po.idx[T.prim] : (int32_t)T.prim;
+  if(idx == B200PT_OMM_INDEX_FULLY_TRANSPARENT)
+    return OMM_TRANSPARENT;
+  if(idx == B200PT_OMM_INDEX_FULLY_OPAQUE)
+    return OMM_OPAQUE;
+  if(idx < 0)
+    return OMM_UNKNOWN;
+  const Oracle::Micromap&         M = o.micromaps[po.micromap];
+  const b200pt_micromap_triangle& R = M.tris[(size_t)idx + po.base];
+  const uint32_t                  m = ommBary2Index(u, v, R.subdivisionLevel);
+  if(R.format == B200PT_OMM_FORMAT_4_STATE)
+  {
+    const uint32_t st = (M.data[R.dataOffset + (m >> 2)] >> ((m & 3u) * 2u)) & 3u;
+    return st < 2u ? (int)st : OMM_UNKNOWN;
+  }
+  return (int)((M.data[R.dataOffset + (m >> 3)] >> (m & 7u)) & 1u);
+}
+
 // closest hit with (t,id) strictly greater than (loT, loId) in lexicographic order, t in (tmin,tmax).
+// ommWant >= 0: only hits whose micro-triangle state is `ommWant` count (the others are skipped).
 // cull: apply back-face culling (closest-hit rays) honouring TRI_NOCULL.
-static bool nextHit(const Oracle& scene, const Oracle::Tree& o, const Ray& r, bool cull, float loT, uint32_t loId, bool haveLo, Hit& best, bool anyExit = false)
+static bool nextHit(const Oracle& scene, const Oracle::Tree& o, const Ray& r, bool cull, float loT, uint32_t loId, bool haveLo, Hit& best, bool anyExit = false,
+                    int ommWant = -1)
 {
   if(o.bvh.empty())
     return false;
@@ -651,6 +744,10 @@ static bool nextHit(const Oracle& scene, const Oracle::Tree& o, const Ray& r, bo
         if(!(t > r.tmin && t < r.tmax))
           continue;
         if(haveLo && !(t > loT || (t == loT && id > loId)))
+          continue;
+        if(ommWant >= 0 && !(t < best.t || (t == best.t && id < best.tri)))
+          continue;
+        if(ommWant >= 0 && ommState(scene, T, (T.flags & TRI_FLIPPED) ? v : u, (T.flags & TRI_FLIPPED) ? u : v) != ommWant)
           continue;
         if(t < best.t || (t == best.t && id < best.tri))
         {
@@ -1177,7 +1274,22 @@ static void Trace(Oracle& o, const Ray& ray, HitPayload& p, uint32_t& seed)
   // 1. closest FORCE_OPAQUE hit
   Hit  ho;
   bool haveOpaque = nextHit(o, o.treeOpaque, ray, true, 0.f, 0u, false, ho);
-  // 2. non-opaque candidates nearer than it, front to back (stochastic alpha, :104-111)
+  const bool omm = !o.primOmm.empty();
+  if(omm && !o.treeAlpha.bvh.empty())
+  {
+    // 1b. a hit on an OPAQUE micro-triangle of an alpha-tested triangle is committed the same way (no any-hit, no rand())
+    // (ties at the same t go to the smaller triangle id, like every other comparison of the walk)
+    Ray r1 = ray;
+    if(haveOpaque)
+      r1.tmax = nextafterf(ho.t, INFINITE_F);
+    Hit hm;
+    if(nextHit(o, o.treeAlpha, r1, true, 0.f, 0u, false, hm, false, OMM_OPAQUE) && (!haveOpaque || hm.t < ho.t || (hm.t == ho.t && hm.tri < ho.tri)))
+    {
+      ho = hm;
+      haveOpaque = true;
+    }
+  }
+  // 2. non-opaque candidates nearer than it, front to back (stochastic alpha, :104-111); with micromaps only the UNKNOWN ones
   if(!o.treeAlpha.bvh.empty())
   {
     Ray r2 = ray;
@@ -1189,7 +1301,7 @@ static void Trace(Oracle& o, const Ray& ray, HitPayload& p, uint32_t& seed)
     for(;;)
     {
       Hit h;
-      if(!nextHit(o, o.treeAlpha, r2, true, loT, loId, haveLo, h))
+      if(!nextHit(o, o.treeAlpha, r2, true, loT, loId, haveLo, h, false, omm ? OMM_UNKNOWN : -1))
         break;
       const FlatTri&            T = o.tris[h.tri];
       const b200pt_render_node& node = o.nodes[T.rnode];
@@ -1221,6 +1333,14 @@ static float3 TraceShadow(Oracle& o, const Ray& ray, uint32_t& seed, bool initia
   float3 total = f3(1.0f);
   if(o.treeAlpha.bvh.empty())
     return total;
+  const bool omm = !o.primOmm.empty();
+  if(omm)
+  {
+    // an OPAQUE micro-triangle anywhere on the segment is a committed hit as well (:181-184)
+    Hit h;
+    if(nextHit(o, o.treeAlpha, ray, false, 0.f, 0u, false, h, true, OMM_OPAQUE))
+      return f3(0.0f);
+  }
   // 2. every non-opaque candidate, front to back (:149-179)
   bool     isInside = initialInside;
   float    prevHitT = 0.f;
@@ -1230,7 +1350,7 @@ static float3 TraceShadow(Oracle& o, const Ray& ray, uint32_t& seed, bool initia
   for(;;)
   {
     Hit h;
-    if(!nextHit(o, o.treeAlpha, ray, false, loT, loId, haveLo, h))
+    if(!nextHit(o, o.treeAlpha, ray, false, loT, loId, haveLo, h, false, omm ? OMM_UNKNOWN : -1))
       return total;
     const FlatTri&            T = o.tris[h.tri];
     const b200pt_render_node& node = o.nodes[T.rnode];
@@ -1954,6 +2074,39 @@ static void processPixel(const Ctx& c, int x, int y, float* px, uint32_t* object
 // C API (ctypes; tests only)
 // =================================================================================================
 extern "C" {
+
+// SceneOmm::create analogue (src/gltf_scene_omm.cpp): same arrays as b200pt_set_opacity_micromaps; call before or after oracle_set_scene
+int oracle_set_opacity_micromaps(void* h, const b200pt_micromap* micromaps, uint32_t numMicromaps, const b200pt_primitive_omm* prims, uint32_t numPrims)
+{
+  Oracle& o = *(Oracle*)h;
+  o.micromaps.clear();
+  o.primOmm.clear();
+  o.ommOfPrim.clear();
+  if(numPrims == 0)
+    return 0;
+  o.micromaps.resize(numMicromaps);
+  for(uint32_t m = 0; m < numMicromaps; m++)
+  {
+    o.micromaps[m].data.assign(micromaps[m].data, micromaps[m].data + micromaps[m].dataSize);
+    o.micromaps[m].tris.assign(micromaps[m].triangles, micromaps[m].triangles + micromaps[m].numTriangles);
+  }
+  for(uint32_t i = 0; i < numPrims; i++)
+  {
+    if(prims[i].micromap >= numMicromaps)
+      return -1;
+    Oracle::PrimOmm po;
+    po.micromap = prims[i].micromap;
+    po.base = prims[i].baseTriangle;
+    po.hasIdx = prims[i].indices != nullptr;
+    if(prims[i].indices)
+      po.idx.assign(prims[i].indices, prims[i].indices + prims[i].numIndices);
+    if(o.ommOfPrim.size() <= prims[i].renderPrimID)
+      o.ommOfPrim.resize((size_t)prims[i].renderPrimID + 1, -1);
+    o.ommOfPrim[prims[i].renderPrimID] = (int)o.primOmm.size();
+    o.primOmm.push_back(std::move(po));
+  }
+  return 0;
+}
 
 void* oracle_create() { return new Oracle(); }
 void  oracle_destroy(void* h) { delete(Oracle*)h; }

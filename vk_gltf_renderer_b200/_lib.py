@@ -19,6 +19,7 @@ EXPORTS = [
     "b200pt_get_stats", "b200pt_reset_stats", "b200pt_set_profiling", "b200pt_trace_closest",
     "b200pt_trace_shadow", "b200pt_bvh_info", "b200pt_bsdf_eval", "b200pt_bsdf_sample",
     "b200pt_read_selection", "b200pt_get_selection_device", "b200pt_set_frame_batch", "b200pt_flush", "b200pt_update_transforms", "b200pt_set_bvh_builder", "b200pt_bvh_build_ms",
+    "b200pt_set_opacity_micromaps",
 ]
 
 
@@ -51,6 +52,7 @@ def lib(count_traversal=False):
     L.b200pt_last_error.argtypes = [vp]
     L.b200pt_last_error.restype = C.c_char_p
     L.b200pt_set_scene.argtypes = [vp, C.POINTER(abi.SceneDesc)]
+    L.b200pt_set_opacity_micromaps.argtypes = [vp, C.POINTER(abi.Micromap), u32, C.POINTER(abi.PrimitiveOmm), u32]
     L.b200pt_set_environment.argtypes = [vp, f32p, i32, i32, C.POINTER(C.c_float)]
     L.b200pt_resize.argtypes = [vp, i32, i32, i32, i32]
     L.b200pt_resize_interleaved.argtypes = [vp, i32, i32, i32, i32, i32]

@@ -109,6 +109,27 @@ class Stats(C.Structure):
                 ("msAnyHit", C.c_double), ("msResolve", C.c_double), ("launchesAnyHit", C.c_uint64), ("launchesResolve", C.c_uint64)]
 
 
+class MicromapTriangle(C.Structure):
+    """VkMicromapTriangleEXT (b200pt_micromap_triangle)"""
+    _fields_ = [("dataOffset", C.c_uint32), ("subdivisionLevel", C.c_uint16), ("format", C.c_uint16)]
+
+
+MICROMAP_TRIANGLE_DTYPE = np.dtype([("dataOffset", "<u4"), ("subdivisionLevel", "<u2"), ("format", "<u2")])
+
+
+class Micromap(C.Structure):
+    _fields_ = [("data", c_u8_p), ("dataSize", C.c_uint64), ("triangles", C.POINTER(MicromapTriangle)), ("numTriangles", C.c_uint32)]
+
+
+class PrimitiveOmm(C.Structure):
+    _fields_ = [("renderPrimID", C.c_uint32), ("micromap", C.c_uint32), ("baseTriangle", C.c_uint32),
+                ("indices", C.POINTER(C.c_int32)), ("numIndices", C.c_uint32)]
+
+
+OMM_FORMAT_2_STATE, OMM_FORMAT_4_STATE = 1, 2
+OMM_INDEX_FULLY_TRANSPARENT, OMM_INDEX_FULLY_OPAQUE, OMM_INDEX_FULLY_UNKNOWN_TRANSPARENT, OMM_INDEX_FULLY_UNKNOWN_OPAQUE = -1, -2, -3, -4
+assert C.sizeof(MicromapTriangle) == 8
+
 # sizes fixed by the reference's layouts (SURVEY.md §8a)
 assert C.sizeof(RenderNode) == 136
 assert C.sizeof(TextureInfo) == 32

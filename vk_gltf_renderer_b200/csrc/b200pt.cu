@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_trace(PathState
       }
 #endif
       if(path >= 0 && !travDone)
-        travDone = T.step<SS>(stack, postponeShift, cand, cs);
+        travDone = T.step<SS>(stack, postponeShift, cand, cs, S.bvh.ommRef, S.bvh.ommData);
       if(__popc(__ballot_sync(0xffffffffu, path >= 0 && !travDone)) < refillThreshold)
         break;
     }
@@ -989,8 +989,10 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathStat
       if(phase == 0 && T.best.slot == 0xFFFFFFFFu && S.hasAlpha)
       {
         // no opaque occluder: the non-opaque candidates of the segment, nearest first
+        // With opacity micromaps an OPAQUE micro-triangle anywhere on the segment ends the query like a FORCE_OPAQUE occluder
+        // (a committed hit, raytracer_interface.h.slang:181-184), so the walk must not stop looking behind the 4th candidate.
         phase = 1;
-        T.init(S.bvhA, T.org, T.dir, 0.0f, T.tmax, false, true, false, 0.f, 0u, true);
+        T.init(S.bvhA, T.org, T.dir, 0.0f, T.tmax, false, true, false, 0.f, 0u, S.bvhA.ommRef == nullptr);
       }
       else
       {
@@ -1057,7 +1059,7 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathStat
       }
 #endif
       if(path >= 0 && !travDone)
-        travDone = T.step<SS>(stack, postponeShift, cand, cs);
+        travDone = T.step<SS>(stack, postponeShift, cand, cs, S.bvhA.ommRef, S.bvhA.ommData);  // (only non-opaque triangles consult it: phase 1)
       if(__popc(__ballot_sync(0xffffffffu, path >= 0 && !travDone)) < refillThreshold)
         break;
     }
@@ -1483,6 +1485,21 @@ struct b200pt
 
   // scene
   std::vector<void*>  sceneAllocs;
+  // opacity micromaps as handed over by b200pt_set_opacity_micromaps (host copies; consumed by the next b200pt_set_scene)
+  struct OmmHost
+  {
+    std::vector<uint8_t>                  data;
+    std::vector<b200pt_micromap_triangle> tris;
+  };
+  struct PrimOmmHost
+  {
+    uint32_t             prim = 0, micromap = 0, base = 0;
+    bool                 hasIdx = false;
+    std::vector<int32_t> idx;
+  };
+  std::vector<OmmHost>     omms;
+  std::vector<PrimOmmHost> primOmms;
+  uint32_t                 ommTriangles = 0;  // non-opaque triangles of the scene that got a micromap / special state
   DevScene            S{};
   bool                haveScene = false;
   bool                hasVolume = false;
@@ -2481,6 +2498,8 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
   S.bvh.nodes = reinterpret_cast<const float4*>(dBvhNodes);
   S.bvh.tris = reinterpret_cast<const float4*>(dTris);
   S.bvh.prmtPool = kPrmtPool;
+  S.bvh.ommRef = nullptr;
+  S.bvh.ommData = nullptr;
   S.hasAlpha = anyNonOpaque ? 1 : 0;
   S.triMeta = reinterpret_cast<const uint2*>(dMeta);
   S.bvhO = S.bvh;
@@ -2712,6 +2731,74 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
     S.alphaIdx = dIdx;
     S.alphaBaseS = bvhO.numTris;
   }
+  // ---- opacity micromaps (omm.cuh): one reference word per triangle slot of the merged tree and of the shadow rays' arrays ----
+  h->ommTriangles = 0;
+  if(anyNonOpaque && !h->primOmms.empty())
+  {
+    std::vector<uint8_t>  data;
+    std::vector<uint32_t> dataBase(h->omms.size());
+    for(size_t m = 0; m < h->omms.size(); m++)
+    {
+      dataBase[m] = (uint32_t)data.size();
+      data.insert(data.end(), h->omms[m].data.begin(), h->omms[m].data.end());
+    }
+    data.resize(data.size() + 4, 0);  // (never read: keeps the allocation non-empty)
+    std::vector<int> ommOfPrim(s->numRenderPrimitives, -1);
+    for(size_t k = 0; k < h->primOmms.size(); k++)
+    {
+      const auto& po = h->primOmms[k];
+      if(po.prim >= s->numRenderPrimitives)
+      {
+        h->err = "b200pt_set_scene: opacity micromap linked to a render primitive out of range";
+        return B200PT_E_INVALID;
+      }
+      const uint32_t nTri = s->renderPrimitives[po.prim].triangleCount;
+      if(po.hasIdx ? po.idx.size() < nTri : (uint64_t)po.base + nTri > h->omms[po.micromap].tris.size())
+      {
+        h->err = "b200pt_set_scene: opacity micromap does not cover its primitive's triangles";
+        return B200PT_E_INVALID;
+      }
+      ommOfPrim[po.prim] = (int)k;
+    }
+    uint32_t linked = 0;
+    auto     refOf = [&](uint32_t w0, uint32_t primTri) -> uint32_t {
+      const uint32_t unknown = pt::kOmmNoLookup | (uint32_t)pt::OMM_UNKNOWN;
+      if((w0 >> 28) & TRI_OPAQUE)
+        return unknown;  // FORCE_OPAQUE instance: the walk never asks
+      const int k = ommOfPrim[(uint32_t)s->renderNodes[w0 & 0x0fffffffu].renderPrimID];
+      if(k < 0)
+        return unknown;
+      const auto& po = h->primOmms[(size_t)k];
+      const int32_t idx = po.hasIdx ? po.idx[primTri] : (int32_t)primTri;
+      linked++;
+      if(idx == B200PT_OMM_INDEX_FULLY_TRANSPARENT)
+        return pt::kOmmNoLookup | (uint32_t)pt::OMM_TRANSPARENT;
+      if(idx == B200PT_OMM_INDEX_FULLY_OPAQUE)
+        return pt::kOmmNoLookup | (uint32_t)pt::OMM_OPAQUE;
+      if(idx < 0)
+        return unknown;
+      const b200pt_micromap_triangle& T = h->omms[po.micromap].tris[(size_t)idx + po.base];
+      return ((uint32_t)T.subdivisionLevel << 28) | (T.format == B200PT_OMM_FORMAT_4_STATE ? (1u << 27) : 0u) | (dataBase[po.micromap] + T.dataOffset);
+    };
+    std::vector<uint32_t> ref(bvh.numTris), refS((size_t)bvhO.numTris + bvhA.numTris, pt::kOmmNoLookup | (uint32_t)pt::OMM_UNKNOWN);
+    for(uint32_t k = 0; k < bvh.numTris; k++)
+      ref[k] = refOf(bvh.triMeta[(size_t)k * 2], bvh.triMeta[(size_t)k * 2 + 1]);
+    h->ommTriangles = linked;
+    for(uint32_t k = 0; k < bvhA.numTris; k++)
+      refS[(size_t)bvhO.numTris + k] = refOf(bvhA.triMeta[(size_t)k * 2], bvhA.triMeta[(size_t)k * 2 + 1]);
+    uint8_t*  dData;
+    uint32_t *dRef, *dRefS;
+    if((rc = upload(h, h->sceneAllocs, data.data(), data.size(), &dData)))
+      return rc;
+    if((rc = upload(h, h->sceneAllocs, ref.data(), ref.size(), &dRef)))
+      return rc;
+    if((rc = upload(h, h->sceneAllocs, refS.data(), refS.size(), &dRefS)))
+      return rc;
+    S.bvh.ommRef = dRef;
+    S.bvh.ommData = dData;
+    S.bvhA.ommRef = dRefS;
+    S.bvhA.ommData = dData;
+  }
   h->nodeBytes = bvh.nodes.size() * sizeof(float) + splitNodeBytes;
   h->triBytes = bvh.tris.size() * sizeof(float) + splitTriBytes;
   h->numNodes = bvh.numNodes + (anyNonOpaque ? bvhO.numNodes + bvhA.numNodes : 0u);
@@ -2733,6 +2820,71 @@ int b200pt_bvh_info(b200pt_t* h, uint64_t* node_bytes, uint64_t* tri_bytes, uint
     *num_nodes = h->numNodes;
   if(num_tris)
     *num_tris = h->numTris;
+  return B200PT_OK;
+}
+
+int b200pt_set_opacity_micromaps(b200pt_t* h, const b200pt_micromap* micromaps, uint32_t num_micromaps, const b200pt_primitive_omm* prims, uint32_t num_prims)
+{
+  if(!h || (num_micromaps && !micromaps) || (num_prims && !prims))
+    return B200PT_E_INVALID;
+  std::vector<b200pt_t::OmmHost>     omms(num_prims ? num_micromaps : 0u);
+  std::vector<b200pt_t::PrimOmmHost> po(num_prims);
+  uint64_t                           total = 0;
+  for(size_t m = 0; m < omms.size(); m++)
+  {
+    const b200pt_micromap& M = micromaps[m];
+    if((M.dataSize && !M.data) || (M.numTriangles && !M.triangles))
+    {
+      h->err = "b200pt_set_opacity_micromaps: micromap with a null array";
+      return B200PT_E_INVALID;
+    }
+    for(uint32_t t = 0; t < M.numTriangles; t++)
+    {
+      const b200pt_micromap_triangle& T = M.triangles[t];
+      if((T.format != B200PT_OMM_FORMAT_2_STATE && T.format != B200PT_OMM_FORMAT_4_STATE) || T.subdivisionLevel > B200PT_OMM_MAX_LEVEL)
+      {
+        h->err = "b200pt_set_opacity_micromaps: micromap triangle with an unknown format or a subdivision level above 12";
+        return B200PT_E_INVALID;
+      }
+      const uint64_t bits = (1ull << (2 * T.subdivisionLevel)) * (T.format == B200PT_OMM_FORMAT_4_STATE ? 2u : 1u);
+      if((uint64_t)T.dataOffset + (bits + 7) / 8 > M.dataSize)
+      {
+        h->err = "b200pt_set_opacity_micromaps: micromap triangle data beyond dataSize";
+        return B200PT_E_INVALID;
+      }
+    }
+    omms[m].data.assign(M.data, M.data + M.dataSize);
+    omms[m].tris.assign(M.triangles, M.triangles + M.numTriangles);
+    total += M.dataSize;
+  }
+  if(total >= (1ull << 27))
+  {
+    h->err = "b200pt_set_opacity_micromaps: more than 128 MiB of micromap data";
+    return B200PT_E_UNSUPPORTED;
+  }
+  for(uint32_t i = 0; i < num_prims; i++)
+  {
+    const b200pt_primitive_omm& P = prims[i];
+    if(P.micromap >= num_micromaps || (P.numIndices && !P.indices))
+    {
+      h->err = "b200pt_set_opacity_micromaps: primitive linkage references a micromap out of range";
+      return B200PT_E_INVALID;
+    }
+    po[i].prim = P.renderPrimID;
+    po[i].micromap = P.micromap;
+    po[i].base = P.baseTriangle;
+    po[i].hasIdx = P.indices != nullptr;
+    if(P.indices)
+      po[i].idx.assign(P.indices, P.indices + P.numIndices);
+    for(int32_t v : po[i].idx)
+      if(v < B200PT_OMM_INDEX_FULLY_UNKNOWN_OPAQUE || (v >= 0 && (uint64_t)v + P.baseTriangle >= micromaps[P.micromap].numTriangles))
+      {
+        h->err = "b200pt_set_opacity_micromaps: micromap index out of range";
+        return B200PT_E_INVALID;
+      }
+  }
+  h->omms.swap(omms);
+  h->primOmms.swap(po);
   return B200PT_OK;
 }
 
@@ -3372,7 +3524,9 @@ static int launchFrames(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
           qShade = L.dQ[4];
         }
         timed(tShade, [&] {
-          if(h->leanShade)
+          if(h->featureMask == 0)
+            k_shade<0u><<<gS, SHADE_BLOCK, 2048, st>>>(L.P, h->S, F, qShade, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
+          else if(h->leanShade)
             k_shade<FEAT_LEAN><<<gS, SHADE_BLOCK, 2048, st>>>(L.P, h->S, F, qShade, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
           else
             k_shade<FEAT_ALL><<<gS, SHADE_BLOCK, 2048, st>>>(L.P, h->S, F, qShade, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);

@@ -7,6 +7,7 @@
 // front-to-back iterations of that query, which makes the result independent of tree layout.
 #pragma once
 #include "bvh.h"
+#include "omm.cuh"
 #include "vec.cuh"
 
 namespace pt {
@@ -36,6 +37,9 @@ struct BvhView
   const float4* __restrict__ nodes;  // 5 per node
   const float4* __restrict__ tris;   // 3 per triangle
   uint32_t      prmtPool;            // 0x47000000 (see biasedByte): a kernel PARAMETER, so that ptxas cannot fold it
+  // opacity micromaps (omm.cuh): one reference word per triangle slot of THIS tree and the packed states; nullptr = the scene has none
+  const uint32_t* __restrict__ ommRef = nullptr;
+  const uint8_t* __restrict__ ommData = nullptr;
 };
 constexpr uint32_t kPrmtPool = 0x47000000u;
 
@@ -219,7 +223,8 @@ struct TravState
   // cand[i * cs]: the kernels keep it in shared memory, one column per thread).
   // FORCE_OPAQUE: every triangle counts as opaque (IRaytracer::TraceLow, RAY_FLAG_FORCE_OPAQUE: the selection ray)
   template <int SS = 1, int KC = kCand, bool FORCE_OPAQUE = false>
-  PT_D bool step(uint2* __restrict__ stack, int postponeShift, Cand* __restrict__ cand, int cs)
+  PT_D bool step(uint2* __restrict__ stack, int postponeShift, Cand* __restrict__ cand, int cs, const uint32_t* __restrict__ ommRef = nullptr,
+                 const uint8_t* __restrict__ ommData = nullptr)
   {
     // single exit: an early return inside the divergent regions would move their reconvergence point out of the
     // caller's loop and the lanes of a warp would drift apart (measured: 8 of 32 lanes active)
@@ -370,9 +375,19 @@ struct TravState
         const bool     front = (flags & TRI_FLIPPED) ? (det < 0.0f) : (det > 0.0f);
         hit &= !cull | ((flags & TRI_NOCULL) != 0) | front;
         hit &= !haveLo | (t > loT) | ((t == loT) & (gid > loId));
+        bool opq = FORCE_OPAQUE || (flags & TRI_OPAQUE) != 0;
+        if(!FORCE_OPAQUE && hit && !opq && ommRef != nullptr)
+        {
+          // what the RT cores do with an opacity micromap: the micro-triangle under the hit decides -- OPAQUE is committed like a
+          // FORCE_OPAQUE triangle, TRANSPARENT is culled, only UNKNOWN becomes an any-hit candidate (omm.cuh)
+          const bool fl = (flags & TRI_FLIPPED) != 0;  // mirrored instance: the record's 2nd / 3rd vertex are swapped
+          const int  st = ommStateOf(__ldg(&ommRef[slot]), fl ? v : u, fl ? u : v, [&](uint32_t o) { return (uint32_t)__ldg(&ommData[o]); });
+          opq = st == OMM_OPAQUE;
+          hit = st != OMM_TRANSPARENT;
+        }
         if(hit)
         {
-          if(FORCE_OPAQUE || (flags & TRI_OPAQUE))
+          if(opq)
           {
             if((t < best.t) | ((t == best.t) & (gid < best.gid)))
             {
@@ -473,7 +488,7 @@ PT_D int walkCollect(const BvhView bvh, float3 org, float3 dir, float tmin, floa
     T.best = opq;
     T.bound = fminf(T.bound, opq.t);
   }
-  while(!T.template step<1, KC>(stack, 2, cand, 1))
+  while(!T.template step<1, KC>(stack, 2, cand, 1, bvh.ommRef, bvh.ommData))
   {
     if(deepest && T.sp > *deepest)
       *deepest = T.sp;

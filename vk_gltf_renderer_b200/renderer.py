@@ -116,6 +116,9 @@ class PathTracer:
 
     def onSceneInvalidated(self, resources):
         d = resources.scene.desc()
+        # SceneOmm::create before SceneRtx's BLAS build (reference renderer: gltf_scene_vk.cpp owns SceneOmm)
+        mm, nmm, po, npo, keep = resources.scene.omm_desc()
+        self._ck(self._L.b200pt_set_opacity_micromaps(self._h, mm, nmm, po, npo), "b200pt_set_opacity_micromaps")
         self._ck(self._L.b200pt_set_scene(self._h, C.byref(d)), "b200pt_set_scene")
 
     def set_bvh_builder(self, kind):

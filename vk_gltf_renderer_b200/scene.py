@@ -53,6 +53,9 @@ class Scene:
         self.texture_infos[0].uvTransform[:] = [1, 0, 0, 1, 0, 0]
         self.textures = []            # list of dict(rgba8 u8[H,W,4], srgb, wrapS, wrapT, magFilter, minFilter)
         self.lights = []              # list of abi.Light
+        # EXT_mesh_opacity_micromap (reference src/gltf_scene_omm.cpp): root micromaps[] and the per-primitive linkage
+        self.micromaps = []           # list of dict(data u8[N], triangles abi.MICROMAP_TRIANGLE_DTYPE[M])
+        self.prim_omms = []           # list of dict(renderPrimID, micromap, baseTriangle, indices i32[T] | None)
         self.camera = None
         self._keep = []
 
@@ -117,6 +120,28 @@ class Scene:
         self.render_nodes.append(dict(objectToWorld=_glm(m), worldToObject=_glm(np.linalg.inv(m)),
                                       materialID=material_id, renderPrimID=prim_id, visible=visible))
         return len(self.render_nodes) - 1
+
+    def omm_desc(self):
+        """(micromaps array, count, primitive linkage array, count, keep-alive) for b200pt_set_opacity_micromaps"""
+        keep = []
+        mm = (abi.Micromap * max(len(self.micromaps), 1))()
+        for i, m in enumerate(self.micromaps):
+            data = np.ascontiguousarray(m["data"], np.uint8)
+            tris = np.ascontiguousarray(m["triangles"], abi.MICROMAP_TRIANGLE_DTYPE)
+            keep += [data, tris]
+            mm[i].data = data.ctypes.data_as(abi.c_u8_p)
+            mm[i].dataSize = data.size
+            mm[i].triangles = tris.ctypes.data_as(C.POINTER(abi.MicromapTriangle))
+            mm[i].numTriangles = tris.size
+        po = (abi.PrimitiveOmm * max(len(self.prim_omms), 1))()
+        for i, p in enumerate(self.prim_omms):
+            po[i].renderPrimID, po[i].micromap, po[i].baseTriangle = p["renderPrimID"], p["micromap"], p.get("baseTriangle", 0)
+            if p.get("indices") is not None:
+                idx = np.ascontiguousarray(p["indices"], np.int32)
+                keep.append(idx)
+                po[i].indices = idx.ctypes.data_as(C.POINTER(C.c_int32))
+                po[i].numIndices = idx.size
+        return mm, len(self.micromaps), po, len(self.prim_omms), keep
 
     # -- ctypes view ---------------------------------------------------------------------------
     def desc(self):
