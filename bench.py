@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--depth", type=int, default=0)
     ap.add_argument("--omm", type=int, default=int(os.environ.get("B200PT_BENCH_OMM", "0")),
                     help="bake opacity micromaps of this subdivision level for the alpha-MASK triangles of the scene (0 = the asset as it is, without)")
+    ap.add_argument("--no-omm-pass", action="store_true", help="skip the extra timed pass with baked opacity micromaps (configs 3 / 5, --omm 0)")
     ap.add_argument("--tex", type=int, default=2048)
     ap.add_argument("--detail", type=float, default=1.0)
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the frame the CPU baseline renders (0 = sized for ~12 s)")
@@ -490,6 +491,30 @@ def main():
         barrier()
         e2e_per_frame = rays_now()[0] / (time.perf_counter() - t0) / 1e6
 
+    # ---- pass D: the same steps on the same scene carrying opacity micromaps (an asset with EXT_mesh_opacity_micromap: the walk
+    # resolves OPAQUE / TRANSPARENT micro-triangles itself, csrc/omm.cuh).  Reported beside the headline, never as it: the stand-in
+    # asset, like the Sponza it stands for, has no micromaps.
+    omm_extra = None
+    if args.omm == 0 and not args.no_omm_pass and args.config in (3, 5):
+        from vk_gltf_renderer_b200 import omm as ommod
+        t_b = time.perf_counter()
+        st_omm = ommod.bake_opacity_micromaps(scn, level=5)
+        bake_s = time.perf_counter() - t_b
+        if st_omm["triangles"]:
+            barrier()
+            pt.onSceneInvalidated(res)  # SceneOmm::create + the tree build that consumes it
+            for _ in range(max(args.warmup, 3)):
+                step()
+            finish_batch()
+            pt.reset_stats()
+            ms_o = timed(args.steps, step)
+            r_o = rays_now()
+            omm_extra = {"value": r_o[0] / (ms_o * 1e-3) / 1e6, "unit": "Mray/s", "ms_per_step": ms_o / args.steps, "subdivision_level": 5,
+                         "alpha_triangles": st_omm["triangles"], "unknown_fraction": st_omm["unknown"] / max(st_omm["micro"], 1), "bake_s": bake_s,
+                         "note": "same scene, camera, steps and batching with opacity micromaps baked from the MASK texture (vk_gltf_renderer_b200/omm.py, "
+                                 "untimed like the BVH build); rays per frame are the same, the any-hit work is what shrinks; parity: tests/test_gpu_omm.py"}
+        scn.micromaps, scn.prim_omms, scn._keep = [], [], []  # the counters and the CPU baseline below see the asset as it is
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -556,7 +581,7 @@ def main():
                                   "per_frame_readback_value": e2e_per_frame,
                                   "ms_per_step": 1e3 * float(dt.item()) / args.steps},
             "frames_in_flight": lanes, "frame_batch": batch,
-            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb}
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb, "with_opacity_micromaps": omm_extra}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

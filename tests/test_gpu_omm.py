@@ -86,7 +86,7 @@ def test_trace_parity_micromaps_on_deep_layers(std_env, oracle_mod):
     o = oracle_mod.Oracle()
     o.set_scene(scn)
     ref, s_ref, ref_t, ss_ref = _trace_both(pt, o, rays, seeds, tmax=0.7)
-    assert (s_ref != seeds).mean() > 0.1 and 0.01 < (ref_t[:, 0] > 0).mean() < 0.99 and (ss_ref != seeds).mean() > 0.05
+    assert (s_ref != seeds).mean() > 0.1 and 0.01 < (ref_t[:, 0] > 0).mean() < 0.99 and (ss_ref != seeds).mean() > 0.01
 
 
 def test_render_parity_with_baked_micromaps(std_env, oracle_mod):

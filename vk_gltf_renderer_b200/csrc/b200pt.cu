@@ -198,6 +198,7 @@ enum : int
   TRACE_CONT = 1,
   TRACE_TMIN = 2,
 };
+template <bool OMM>
 __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_trace(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn,
                                                                        uint32_t* workCounter, uint32_t* qAlpha, uint32_t* cntAlpha, DevStats* stats, int refillThreshold,
                                                                        int postponeShift, int mode)
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_trace(PathState
       }
 #endif
       if(path >= 0 && !travDone)
-        travDone = T.step<SS>(stack, postponeShift, cand, cs, S.bvh.ommRef, S.bvh.ommData);
+        travDone = T.step<SS, kCand, false, OMM>(stack, postponeShift, cand, cs, S.bvh.ommRef, S.bvh.ommData);
       if(__popc(__ballot_sync(0xffffffffu, path >= 0 && !travDone)) < refillThreshold)
         break;
     }
@@ -956,6 +957,7 @@ __device__ void finishPost(const PathState& P, const FrameParams& F, uint32_t i,
 // IRaytracer::TraceShadow, geometry part, for every path with a pending NEE shadow ray: ONE walk of the scene tree along
 // the whole segment; any FORCE_OPAQUE occluder ends the query (raytracer_interface.h.slang:181-184), otherwise the kCand
 // nearest non-opaque candidates are written out for k_alpha<true>.  Same persistent-warp scheme as k_trace.
+template <bool OMM>
 __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn,
                                                                         uint32_t* workCounter, uint32_t* qAlpha, uint32_t* cntAlpha, DevStats* stats,
                                                                         int refillThreshold, int postponeShift, int mode)
@@ -992,7 +994,7 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathStat
         // With opacity micromaps an OPAQUE micro-triangle anywhere on the segment ends the query like a FORCE_OPAQUE occluder
         // (a committed hit, raytracer_interface.h.slang:181-184), so the walk must not stop looking behind the 4th candidate.
         phase = 1;
-        T.init(S.bvhA, T.org, T.dir, 0.0f, T.tmax, false, true, false, 0.f, 0u, S.bvhA.ommRef == nullptr);
+        T.init(S.bvhA, T.org, T.dir, 0.0f, T.tmax, false, true, false, 0.f, 0u, !OMM);
       }
       else
       {
@@ -1059,7 +1061,7 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathStat
       }
 #endif
       if(path >= 0 && !travDone)
-        travDone = T.step<SS>(stack, postponeShift, cand, cs, S.bvhA.ommRef, S.bvhA.ommData);  // (only non-opaque triangles consult it: phase 1)
+        travDone = T.step<SS, kCand, false, OMM>(stack, postponeShift, cand, cs, S.bvhA.ommRef, S.bvhA.ommData);  // (only non-opaque triangles consult it: phase 1)
       if(__popc(__ballot_sync(0xffffffffu, path >= 0 && !travDone)) < refillThreshold)
         break;
     }
@@ -1067,6 +1069,16 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathStat
   if(blockIdx.x == 0 && threadIdx.x == 0 && !cont)
     atomicAdd(&stats->shadowRays, (unsigned long long)count);
 }
+
+// the walk kernels have an instantiation for scenes with opacity micromaps (omm.cuh) and one without the lookup
+#define WALK_KERNEL(K, grid, ...)                  \
+  do                                               \
+  {                                                \
+    if(omm)                                        \
+      K<true><<<grid, 128, 0, st>>>(__VA_ARGS__);  \
+    else                                           \
+      K<false><<<grid, 128, 0, st>>>(__VA_ARGS__); \
+  } while(0)
 
 // ---- material-sorted shade queue (north star: "material-sorted shade queues to tame divergence") -------------------------
 // Counting sort of the bounce's path queue by the material of the hit (misses last): k_sort_count builds the histogram,
@@ -1485,6 +1497,9 @@ struct b200pt
 
   // scene
   std::vector<void*>  sceneAllocs;
+  const void*         treeBase = nullptr;  // the trees' node + triangle arrays (one allocation) and their size: the L2 window
+  size_t              treeBytes = 0;
+  int                 l2Window = 1;        // B200PT_L2_WINDOW=0: no persisting-L2 window over the trees
   // opacity micromaps as handed over by b200pt_set_opacity_micromaps (host copies; consumed by the next b200pt_set_scene)
   struct OmmHost
   {
@@ -2012,6 +2027,8 @@ int b200pt_create(b200pt_t** out, int cuda_device)
     h->postponeShift = atoi(e);
   if(const char* e = getenv("B200PT_SORT_SHADE"))
     h->sortShade = atoi(e) != 0;
+  if(const char* e = getenv("B200PT_L2_WINDOW"))
+    h->l2Window = atoi(e);
   if(const char* e = getenv("B200PT_SORT_RAYS"))
     h->sortRays = atoi(e) != 0;
   if(const char* e = getenv("B200PT_WALK_GRID"))
@@ -2487,12 +2504,36 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
     }
     h->bvhBuildMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tBuild0).count();
   }
-  float *   dBvhNodes, *dTris;
+  // The node and triangle arrays of all three trees live in ONE allocation, so that a single L2 access-policy window can pin them
+  // (setTreeWindow below): the walks re-read these few tens of MB all the time while every bounce streams GBs of path state past them.
+  std::vector<float> trisS, packed;
+  size_t             offTris = 0, offNodesO = 0, offNodesA = 0, offTrisS = 0;
+  {
+    auto place = [&](const std::vector<float>& v) {
+      const size_t at = packed.size();
+      packed.insert(packed.end(), v.begin(), v.end());
+      packed.resize((packed.size() + 31) & ~(size_t)31, 0.0f);  // 128-byte granules
+      return at;
+    };
+    place(bvh.nodes);
+    offTris = place(bvh.tris);
+    if(anyNonOpaque)
+    {
+      trisS = bvhO.tris;
+      trisS.insert(trisS.end(), bvhA.tris.begin(), bvhA.tris.end());
+      offNodesO = place(bvhO.nodes);
+      offNodesA = place(bvhA.nodes);
+      offTrisS = place(trisS);
+    }
+  }
+  float *   dPacked, *dBvhNodes, *dTris;
   uint32_t* dMeta;
-  if((rc = upload(h, h->sceneAllocs, bvh.nodes.data(), bvh.nodes.size(), &dBvhNodes)))
+  if((rc = upload(h, h->sceneAllocs, packed.data(), packed.size(), &dPacked)))
     return rc;
-  if((rc = upload(h, h->sceneAllocs, bvh.tris.data(), bvh.tris.size(), &dTris)))
-    return rc;
+  dBvhNodes = dPacked;
+  dTris = dPacked + offTris;
+  h->treeBase = dPacked;
+  h->treeBytes = packed.size() * sizeof(float);
   if((rc = upload(h, h->sceneAllocs, bvh.triMeta.data(), bvh.triMeta.size(), &dMeta)))
     return rc;
   S.bvh.nodes = reinterpret_cast<const float4*>(dBvhNodes);
@@ -2535,18 +2576,10 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
   uint64_t splitNodeBytes = 0, splitTriBytes = 0;
   if(anyNonOpaque)
   {
-    std::vector<float>    trisS(bvhO.tris);
     std::vector<uint32_t> metaS(bvhO.triMeta);
-    trisS.insert(trisS.end(), bvhA.tris.begin(), bvhA.tris.end());
     metaS.insert(metaS.end(), bvhA.triMeta.begin(), bvhA.triMeta.end());
-    float *   dNodesO, *dNodesA, *dTrisS;
+    float *   dNodesO = dPacked + offNodesO, *dNodesA = dPacked + offNodesA, *dTrisS = dPacked + offTrisS;
     uint32_t* dMetaS;
-    if((rc = upload(h, h->sceneAllocs, bvhO.nodes.data(), bvhO.nodes.size(), &dNodesO)))
-      return rc;
-    if((rc = upload(h, h->sceneAllocs, bvhA.nodes.data(), bvhA.nodes.size(), &dNodesA)))
-      return rc;
-    if((rc = upload(h, h->sceneAllocs, trisS.data(), trisS.size(), &dTrisS)))
-      return rc;
     if((rc = upload(h, h->sceneAllocs, metaS.data(), metaS.size(), &dMetaS)))
       return rc;
     S.bvhO.nodes = reinterpret_cast<const float4*>(dNodesO);
@@ -2805,6 +2838,30 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
   h->numTris = bvh.numTris;
   CK(cudaStreamSynchronize(h->stream));
   h->haveScene = true;
+  // Persisting-L2 window over the trees on every stream that runs walks (cudaAccessPolicyWindow: lines of the window are kept, the
+  // path-state traffic around them is what gets evicted).  hitRatio shrinks when the trees are larger than the carve-out.
+  if(h->l2Window && h->treeBytes)
+  {
+    int maxPersist = 0, maxWindow = 0;
+    cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
+    cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
+    if(maxPersist > 0 && maxWindow > 0)
+    {
+      const size_t carve = std::min<size_t>((size_t)maxPersist, std::max<size_t>(h->treeBytes, (size_t)1 << 20));
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+      cudaStreamAttrValue attr{};
+      attr.accessPolicyWindow.base_ptr = const_cast<void*>(h->treeBase);
+      attr.accessPolicyWindow.num_bytes = std::min<size_t>(h->treeBytes, (size_t)maxWindow);
+      attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)attr.accessPolicyWindow.num_bytes);
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+      for(int l = 0; l < b200pt::kMaxLanes; l++)
+        if(h->lanes[l].stream)
+          cudaStreamSetAttribute(h->lanes[l].stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+      cudaGetLastError();  // (a refused window is not an error: the walks run without it)
+    }
+  }
   return B200PT_OK;
 }
 
@@ -3491,7 +3548,8 @@ static int launchFrames(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
         // geometry walks are persistent kernels; the texture-dependent any-hit tests and the path bookkeeping run
         // as dense one-thread-per-path kernels (k_alpha, k_resolve) sized by the device-side queue counters
         const int gP = gridFor(h, 8);
-        const int gW = gridFor(h, h->walkGridPerSM);  // persistent walk kernels
+        const int  gW = gridFor(h, h->walkGridPerSM);  // persistent walk kernels
+        const bool omm = h->S.bvh.ommRef != nullptr;  // scenes with opacity micromaps run the walk kernels' OMM instantiation
         const int gS = gridFor(h, h->shadeGridPerSM);  // persistent shade kernel (512-thread CTAs, one resident per SM)
         // geometry walks are persistent kernels; the texture-dependent any-hit tests and the path bookkeeping run
         // as dense kernels (k_alpha, k_resolve) sized by the device-side queue counters.  Any-hit: resolve kCand
@@ -3506,11 +3564,11 @@ static int launchFrames(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
           timed(tOther, [&] { k_sort_scatter<1><<<gridFor(h, 4), 256, 0, st>>>(L.P, h->S, qT, &cntTrace[it], L.dBuckets + kSortMaxBuckets, L.dQ[3], 8u); });
           qWalk = L.dQ[3];
         }
-        timed(tTrace, [&] { k_trace<<<gW, 128, 0, st>>>(L.P, h->S, qWalk, &cntTrace[it], &workTrace[it], L.dQ[4], &cntAlpha[it], h->dStats, h->refillThreshold, h->postponeShift, 0); });
+        timed(tTrace, [&] { WALK_KERNEL(k_trace, gW, L.P, h->S, qWalk, &cntTrace[it], &workTrace[it], L.dQ[4], &cntAlpha[it], h->dStats, h->refillThreshold, h->postponeShift, 0); });
         if(h->S.hasAlpha)
         {
           timed(tAnyHit, [&] { k_alpha<false><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlpha[it], L.dQ[5], &cntCont[it], h->dStats, 0); });
-          timed(tTrace, [&] { k_trace<<<gW, 128, 0, st>>>(L.P, h->S, L.dQ[5], &cntCont[it], &workCont[it], L.dQ[4], &cntAlpha1[it], h->dStats, h->refillThreshold, h->postponeShift, 1); });
+          timed(tTrace, [&] { WALK_KERNEL(k_trace, gW, L.P, h->S, L.dQ[5], &cntCont[it], &workCont[it], L.dQ[4], &cntAlpha1[it], h->dStats, h->refillThreshold, h->postponeShift, 1); });
           timed(tAnyHit, [&] { k_alpha<false><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlpha1[it], nullptr, nullptr, h->dStats, TRACE_CONT); });
         }
         const uint32_t* qShade = qT;
@@ -3531,11 +3589,11 @@ static int launchFrames(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
           else
             k_shade<FEAT_ALL><<<gS, SHADE_BLOCK, 2048, st>>>(L.P, h->S, F, qShade, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
         });
-        timed(tPost, [&] { k_shadow<<<gW, 128, 0, st>>>(L.P, h->S, L.dQ[3], &cntShadow[it], &workPost[it], L.dQ[4], &cntAlphaS[it], h->dStats, h->refillThreshold, h->postponeShift, 0); });
+        timed(tPost, [&] { WALK_KERNEL(k_shadow, gW, L.P, h->S, L.dQ[3], &cntShadow[it], &workPost[it], L.dQ[4], &cntAlphaS[it], h->dStats, h->refillThreshold, h->postponeShift, 0); });
         if(h->S.hasAlpha)
         {
           timed(tAnyHit, [&] { k_alpha<true><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS[it], L.dQ[5], &cntContS[it], h->dStats, 0); });
-          timed(tPost, [&] { k_shadow<<<gW, 128, 0, st>>>(L.P, h->S, L.dQ[5], &cntContS[it], &workContS[it], L.dQ[4], &cntAlphaS1[it], h->dStats, h->refillThreshold, h->postponeShift, 1); });
+          timed(tPost, [&] { WALK_KERNEL(k_shadow, gW, L.P, h->S, L.dQ[5], &cntContS[it], &workContS[it], L.dQ[4], &cntAlphaS1[it], h->dStats, h->refillThreshold, h->postponeShift, 1); });
           timed(tAnyHit, [&] { k_alpha<true><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS1[it], nullptr, nullptr, h->dStats, TRACE_CONT); });
         }
         timed(tResolve, [&] { k_resolve<<<gridFor(h, 4), 256, 0, st>>>(L.P, F, L.dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats); });
@@ -3707,25 +3765,26 @@ static int traceRays(b200pt_t* h, const float* dev_rays, uint32_t n, float* dev_
   PathState&   P = h->rayP;
   uint32_t*    c = h->rayCounters;  // [0] rays [1] any-hit [2] continuation [3] any-hit of the continuation [4..5] work cursors
   CK(cudaMemsetAsync(c, 0, 8 * sizeof(uint32_t), st));
-  const int gP = gridFor(h, 8);
+  const int  gP = gridFor(h, 8);
+  const bool omm = h->S.bvh.ommRef != nullptr;
   k_rays_load<<<gP, 256, 0, st>>>(P, reinterpret_cast<const float4*>(dev_rays), n, dev_seeds, h->rayQ[0], &c[0], shadow);
   if(!shadow)
   {
-    k_trace<<<gP, 128, 0, st>>>(P, h->S, h->rayQ[0], &c[0], &c[4], h->rayQ[1], &c[1], h->dStats, h->refillThreshold, h->postponeShift, TRACE_TMIN);
+    WALK_KERNEL(k_trace, gP, P, h->S, h->rayQ[0], &c[0], &c[4], h->rayQ[1], &c[1], h->dStats, h->refillThreshold, h->postponeShift, TRACE_TMIN);
     if(h->S.hasAlpha)
     {
       k_alpha<false><<<gP, 128, 2048, st>>>(P, h->S, h->rayQ[1], &c[1], h->rayQ[2], &c[2], h->dStats, TRACE_TMIN);
-      k_trace<<<gP, 128, 0, st>>>(P, h->S, h->rayQ[2], &c[2], &c[5], h->rayQ[1], &c[3], h->dStats, h->refillThreshold, h->postponeShift, TRACE_TMIN | TRACE_CONT);
+      WALK_KERNEL(k_trace, gP, P, h->S, h->rayQ[2], &c[2], &c[5], h->rayQ[1], &c[3], h->dStats, h->refillThreshold, h->postponeShift, TRACE_TMIN | TRACE_CONT);
       k_alpha<false><<<gP, 128, 2048, st>>>(P, h->S, h->rayQ[1], &c[3], nullptr, nullptr, h->dStats, TRACE_TMIN | TRACE_CONT);
     }
   }
   else
   {
-    k_shadow<<<gP, 128, 0, st>>>(P, h->S, h->rayQ[0], &c[0], &c[4], h->rayQ[1], &c[1], h->dStats, h->refillThreshold, h->postponeShift, 0);
+    WALK_KERNEL(k_shadow, gP, P, h->S, h->rayQ[0], &c[0], &c[4], h->rayQ[1], &c[1], h->dStats, h->refillThreshold, h->postponeShift, 0);
     if(h->S.hasAlpha)
     {
       k_alpha<true><<<gP, 128, 2048, st>>>(P, h->S, h->rayQ[1], &c[1], h->rayQ[2], &c[2], h->dStats, 0);
-      k_shadow<<<gP, 128, 0, st>>>(P, h->S, h->rayQ[2], &c[2], &c[5], h->rayQ[1], &c[3], h->dStats, h->refillThreshold, h->postponeShift, TRACE_CONT);
+      WALK_KERNEL(k_shadow, gP, P, h->S, h->rayQ[2], &c[2], &c[5], h->rayQ[1], &c[3], h->dStats, h->refillThreshold, h->postponeShift, TRACE_CONT);
       k_alpha<true><<<gP, 128, 2048, st>>>(P, h->S, h->rayQ[1], &c[3], nullptr, nullptr, h->dStats, TRACE_CONT);
     }
   }

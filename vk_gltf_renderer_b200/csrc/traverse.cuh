@@ -222,7 +222,8 @@ struct TravState
   // stack[i * SS]: local memory with SS = 1, or a shared-memory column), `cand` the candidate list (entry i at
   // cand[i * cs]: the kernels keep it in shared memory, one column per thread).
   // FORCE_OPAQUE: every triangle counts as opaque (IRaytracer::TraceLow, RAY_FLAG_FORCE_OPAQUE: the selection ray)
-  template <int SS = 1, int KC = kCand, bool FORCE_OPAQUE = false>
+  // OMM: the scene carries opacity micromaps (a separate instantiation, so that scenes without them run the walk without the lookup)
+  template <int SS = 1, int KC = kCand, bool FORCE_OPAQUE = false, bool OMM = false>
   PT_D bool step(uint2* __restrict__ stack, int postponeShift, Cand* __restrict__ cand, int cs, const uint32_t* __restrict__ ommRef = nullptr,
                  const uint8_t* __restrict__ ommData = nullptr)
   {
@@ -376,7 +377,7 @@ struct TravState
         hit &= !cull | ((flags & TRI_NOCULL) != 0) | front;
         hit &= !haveLo | (t > loT) | ((t == loT) & (gid > loId));
         bool opq = FORCE_OPAQUE || (flags & TRI_OPAQUE) != 0;
-        if(!FORCE_OPAQUE && hit && !opq && ommRef != nullptr)
+        if(OMM && !FORCE_OPAQUE && hit && !opq && ommRef != nullptr)
         {
           // what the RT cores do with an opacity micromap: the micro-triangle under the hit decides -- OPAQUE is committed like a
           // FORCE_OPAQUE triangle, TRANSPARENT is culled, only UNKNOWN becomes an any-hit candidate (omm.cuh)
@@ -488,7 +489,7 @@ PT_D int walkCollect(const BvhView bvh, float3 org, float3 dir, float tmin, floa
     T.best = opq;
     T.bound = fminf(T.bound, opq.t);
   }
-  while(!T.template step<1, KC>(stack, 2, cand, 1, bvh.ommRef, bvh.ommData))
+  while(!T.template step<1, KC, false, true>(stack, 2, cand, 1, bvh.ommRef, bvh.ommData))
   {
     if(deepest && T.sp > *deepest)
       *deepest = T.sp;
