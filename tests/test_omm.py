@@ -154,3 +154,70 @@ def test_special_indices_and_two_state_format(oracle_mod, std_env):
     assert np.array_equal(s, seeds) and on_prim.sum() > 20
     u, v = h[on_prim, 4], h[on_prim, 5]
     assert np.all((u <= 0.5 + 1e-6) & (v <= 0.5 + 1e-6) & (u + v >= 0.5 - 1e-6))   # only the centre micro-triangle is ever hit
+
+
+def test_loader_reads_ext_mesh_opacity_micromap(tmp_path, oracle_mod):
+    """A .gltf carrying EXT_mesh_opacity_micromap (what src/gltf_scene_omm.cpp:140-391 parses): root micromaps[] with data /
+    triangles bufferViews (one with a byteStride) and the per-primitive micromap / micromapBaseTriangle / micromapIndices (uint16:
+    0xFFFF = FULLY_TRANSPARENT, like a VkIndexType).  The loaded scene drives the oracle: triangle 0 of the quad is culled, on
+    triangle 1 only the centre micro-triangle (level 1, 1-bit format) stops a ray."""
+    import base64
+    import json
+    from vk_gltf_renderer_b200 import scene as scn_mod
+    pos = np.array([[-1, -1, 0], [1, -1, 0], [1, 1, 0], [-1, 1, 0]], np.float32)
+    idx = np.array([0, 1, 2, 0, 2, 3], np.uint16)
+    tri_recs = np.zeros(2, np.dtype([("dataOffset", "<u4"), ("level", "<u2"), ("fmt", "<u2"), ("pad", "<u4")]))   # stride 12
+    tri_recs[1] = (1, 1, abi.OMM_FORMAT_2_STATE, 0)
+    tri_recs[0] = (0, 0, abi.OMM_FORMAT_2_STATE, 0)
+    data = np.array([0b1, 0b0010], np.uint8)
+    mm_idx = np.array([0xFFFF, 0], np.uint16)           # triangle 0: special index -1; triangle 1: record 0 + base 1
+    chunks, views = [], []
+
+    def add(b, **kw):
+        off = sum(len(c) for c in chunks)
+        chunks.append(b + b"\0" * ((-len(b)) % 4))
+        views.append(dict(buffer=0, byteOffset=off, byteLength=len(b), **kw))
+        return len(views) - 1
+    v_pos, v_idx, v_data, v_tri, v_mmi = add(pos.tobytes()), add(idx.tobytes()), add(data.tobytes()), add(tri_recs.tobytes(), byteStride=12), add(mm_idx.tobytes())
+    blob = b"".join(chunks)
+    doc = {
+        "asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+        "extensionsUsed": ["EXT_mesh_opacity_micromap"],
+        "extensions": {"EXT_mesh_opacity_micromap": {"micromaps": [
+            {"data": v_data, "triangles": v_tri, "usageCounts": [1, 1], "usageLevels": [0, 1], "usageFormats": [1, 1]},
+            {"data": v_data, "triangles": v_tri, "usageCounts": [2]}]}},           # second entry: missing fields -> skipped
+        "materials": [{"alphaMode": "MASK", "alphaCutoff": 0.5, "doubleSided": True}],
+        "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "indices": 1, "material": 0,
+                                    "extensions": {"EXT_mesh_opacity_micromap": {"micromap": 0, "micromapBaseTriangle": 1, "micromapIndices": 2}}}]}],
+        "buffers": [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}],
+        "bufferViews": views,
+        "accessors": [{"bufferView": v_pos, "componentType": 5126, "count": 4, "type": "VEC3", "min": [-1, -1, 0], "max": [1, 1, 0]},
+                      {"bufferView": v_idx, "componentType": 5123, "count": 6, "type": "SCALAR"},
+                      {"bufferView": v_mmi, "componentType": 5123, "count": 2, "type": "SCALAR"}],
+    }
+    path = tmp_path / "quad_omm.gltf"
+    path.write_text(json.dumps(doc))
+    scn = scn_mod.load_gltf(str(path))
+    assert len(scn.micromaps) == 1 and len(scn.prim_omms) == 1
+    assert scn.micromaps[0]["triangles"].tolist() == [(0, 0, 1), (1, 1, 1)] and scn.micromaps[0]["data"].tolist() == [1, 2]
+    po = scn.prim_omms[0]
+    assert po["baseTriangle"] == 1 and po["indices"].tolist() == [-1, 0] and po["micromap"] == 0
+    o = oracle_mod.Oracle()
+    o.set_scene(scn)
+    rng = np.random.default_rng(4)
+    n = 4000
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:2] = rng.uniform(-1, 1, (n, 2))
+    rays[:, 2] = 2.0
+    rays[:, 4:7] = [0, 0, -1]
+    rays[:, 7] = 1e30
+    seeds = np.arange(n, dtype=np.uint32)
+    s = seeds.copy()
+    h = o.trace_closest(rays, s)
+    hit = h[:, 0] < 1e30
+    x, y = rays[:, 0], rays[:, 1]
+    # triangle 1 = (v0, v2, v3): u = weight of v2, v = weight of v3; x = -1 + 2u, y = -1 + 2u + 2v; centre micro-triangle: u,v <= 1/2 <= u+v
+    u, v = (x + 1) / 2, (y - x) / 2
+    expect = (y > x) & (u <= 0.5) & (v <= 0.5) & (u + v >= 0.5)
+    margin = np.minimum.reduce([np.abs(y - x), np.abs(u - 0.5), np.abs(v - 0.5), np.abs(u + v - 0.5)]) > 1e-4
+    assert np.array_equal(hit[margin], expect[margin]) and np.array_equal(s, seeds) and 0.05 < hit.mean() < 0.3

@@ -24,7 +24,7 @@ import numpy as np
 
 from . import abi
 
-_COMP = {5120: np.int8, 5121: np.uint8, 5122: np.int16, 5123: np.uint16, 5125: np.uint32, 5126: np.float32}
+_COMP = {5120: np.int8, 5121: np.uint8, 5122: np.int16, 5123: np.uint16, 5124: np.int32, 5125: np.uint32, 5126: np.float32}
 _NCOMP = {"SCALAR": 1, "VEC2": 2, "VEC3": 3, "VEC4": 4, "MAT2": 4, "MAT3": 9, "MAT4": 16}
 
 
@@ -301,6 +301,18 @@ class _Gltf:
                 data = open(os.path.join(self.dir, uri), "rb").read()
             self._buffers[i] = data
         return self._buffers[i]
+
+    def view_bytes(self, idx):
+        """raw bytes of a bufferView (None when the index or its buffer is out of range)"""
+        views = self.json.get("bufferViews", [])
+        if not (isinstance(idx, int) and 0 <= idx < len(views)):
+            return None
+        bv = views[idx]
+        if not (0 <= bv.get("buffer", -1) < len(self.json.get("buffers", []))):
+            return None
+        buf = self.buffer(bv["buffer"])
+        off = bv.get("byteOffset", 0)
+        return bytes(buf[off: off + bv["byteLength"]]), bv.get("byteStride", 0)
 
     def accessor(self, idx, normalize=True):
         """Decode an accessor to float32 (normalized ints -> [0,1]/[-1,1]) or its integer type.
@@ -664,6 +676,52 @@ def load_gltf(path):
                 uv1=g.accessor(at["TEXCOORD_1"]) if "TEXCOORD_1" in at else None,
                 tangents=g.accessor(at["TANGENT"]) if "TANGENT" in at else None,
                 colors=colors)
+
+    # ---- EXT_mesh_opacity_micromap (SceneOmm::create, src/gltf_scene_omm.cpp:140-391): root micromaps[] + per-primitive linkage.
+    # Malformed entries are skipped with the reference's rules (missing required field, bad bufferView, misaligned usage arrays,
+    # negative base triangle, bad indices accessor); rendering then falls back to the regular alpha path for those primitives.
+    omm_root = j.get("extensions", {}).get("EXT_mesh_opacity_micromap")
+    if isinstance(omm_root, dict) and isinstance(omm_root.get("micromaps"), list):
+        slot_of = {}
+        for i, mm in enumerate(omm_root["micromaps"]):
+            if not all(k in mm for k in ("data", "triangles", "usageCounts", "usageLevels", "usageFormats")):
+                continue
+            uc, ul, uf = mm["usageCounts"], mm["usageLevels"], mm["usageFormats"]
+            if not (isinstance(uc, list) and isinstance(ul, list) and isinstance(uf, list) and len(uc) == len(ul) == len(uf)):
+                continue
+            dv, tv = g.view_bytes(mm["data"]), g.view_bytes(mm["triangles"])
+            if dv is None or tv is None:
+                continue
+            stride = tv[1] or 8
+            raw = np.frombuffer(tv[0], np.uint8)
+            n = len(raw) // stride if stride > 8 else len(raw) // 8
+            if stride > 8:
+                raw = np.ascontiguousarray(raw[: n * stride].reshape(n, stride)[:, :8]).reshape(-1)
+            tris = np.frombuffer(raw[: n * 8].tobytes(), abi.MICROMAP_TRIANGLE_DTYPE)
+            slot_of[i] = len(scn.micromaps)
+            scn.micromaps.append(dict(data=np.frombuffer(dv[0], np.uint8).copy(), triangles=tris.copy()))
+        linked = set()
+        for mesh in j.get("meshes", []):
+            for p in mesh["primitives"]:
+                ext = p.get("extensions", {}).get("EXT_mesh_opacity_micromap")
+                if p.get("mode", 4) != 4 or not isinstance(ext, dict) or "micromap" not in ext:
+                    continue
+                pid = prim_map[prim_key(p)]
+                if ext["micromap"] not in slot_of or pid in linked:
+                    continue
+                base = ext.get("micromapBaseTriangle", 0)
+                if base < 0:
+                    continue
+                idx = None
+                if "micromapIndices" in ext:
+                    ai = ext["micromapIndices"]
+                    if not (isinstance(ai, int) and 0 <= ai < len(j.get("accessors", []))):
+                        continue
+                    raw_idx = np.ascontiguousarray(g.accessor(ai, normalize=False).reshape(-1))
+                    # the index buffer is typed like a VkIndexType: the special indices are -1..-4 in the accessor's own width
+                    idx = raw_idx.view(np.dtype("i%d" % raw_idx.dtype.itemsize)).astype(np.int32)
+                linked.add(pid)
+                scn.prim_omms.append(dict(renderPrimID=pid, micromap=slot_of[ext["micromap"]], baseTriangle=int(base), indices=idx))
 
     # ---- scene graph (Scene::parseScene) ----
     nodes = j.get("nodes", [])
