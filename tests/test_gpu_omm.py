@@ -160,3 +160,27 @@ def test_micromap_arguments_are_validated(std_env):
             _attach(scn, std_env, (16, 16))
     scn.micromaps, scn.prim_omms = [], []
     _attach(scn, std_env, (16, 16))
+
+
+def test_cpp_host_hands_the_micromaps_over(std_env, tmp_path):
+    """The scene blob carries the EXT_mesh_opacity_micromap arrays; the C++ host (SceneData + PathTracer::onSceneInvalidated) passes
+    them to b200pt_set_opacity_micromaps unless --useOpacityMicromap 0 (src/main.cpp:114-115): the two headless images equal the
+    Python host's renders with and without the arrays."""
+    import os
+    import subprocess
+    from vk_gltf_renderer_b200 import _lib, omm, synth
+    exe = os.path.join(os.path.dirname(_lib.LIB_PATH), "b200pt_headless")
+    scn = synth.synth_sponza(tex_size=256, detail=0.05)
+    _, ref_plain = _gpu_render(scn, std_env, 160, 96, 4, ptMaxDepth=5)
+    omm.bake_opacity_micromaps(scn, level=4)
+    _, ref_omm = _gpu_render(scn, std_env, 160, 96, 4, ptMaxDepth=5)
+    assert not np.array_equal(ref_plain, ref_omm)
+    blob = str(tmp_path / "atrium.b2sc")
+    scn.save_blob(blob, std_env)
+    for flag, ref in (("1", ref_omm), ("0", ref_plain)):
+        raw = str(tmp_path / ("img%s.raw" % flag))
+        out = subprocess.run([exe, "--scene", blob, "--size", "160", "96", "--frames", "4", "--ptMaxDepth", "5", "--useOpacityMicromap", flag, "--outRaw", raw],
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr
+        img = np.fromfile(raw, np.float32).reshape(96, 160, 4)
+        assert np.array_equal(img[..., 3], ref[..., 3]) and rel_rmse(img, ref) <= 1e-4

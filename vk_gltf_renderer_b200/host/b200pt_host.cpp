@@ -22,6 +22,15 @@ struct Reader
     if(!f)
       throw Error("cannot open scene blob " + path);
   }
+  bool tryRaw(void* dst, size_t bytes)  // false at a clean end of file
+  {
+    f.read(static_cast<char*>(dst), (std::streamsize)bytes);
+    if(f.gcount() == 0)
+      return false;
+    if((size_t)f.gcount() != bytes)
+      throw Error("scene blob truncated");
+    return true;
+  }
   void raw(void* dst, size_t bytes)
   {
     f.read(static_cast<char*>(dst), (std::streamsize)bytes);
@@ -132,6 +141,39 @@ void SceneData::load(const std::string& path)
   hdrWidth = (int)r.pod<uint32_t>();
   hdrHeight = (int)r.pod<uint32_t>();
   r.vec(hdrRgb, (size_t)hdrWidth * (size_t)hdrHeight * 3);
+  // optional: the asset's EXT_mesh_opacity_micromap arrays (what SceneOmm::create uploads, src/gltf_scene_omm.cpp)
+  m_ommData.clear();
+  m_ommTris.clear();
+  m_ommIdx.clear();
+  m_micromaps.clear();
+  m_primOmms.clear();
+  char tag[4];
+  if(r.tryRaw(tag, 4))
+  {
+    if(std::memcmp(tag, "OMM1", 4) != 0)
+      throw Error("unknown trailing section in scene blob");
+    const uint32_t nMm = r.pod<uint32_t>(), nLinks = r.pod<uint32_t>();
+    m_ommData.resize(nMm);
+    m_ommTris.resize(nMm);
+    m_micromaps.assign(nMm, b200pt_micromap{});
+    for(uint32_t i = 0; i < nMm; i++)
+    {
+      const uint64_t nData = r.pod<uint64_t>();
+      const uint32_t nTris = r.pod<uint32_t>();
+      r.vec(m_ommData[i], (size_t)nData);
+      r.vec(m_ommTris[i], nTris);
+      m_micromaps[i] = b200pt_micromap{m_ommData[i].data(), nData, m_ommTris[i].data(), nTris};
+    }
+    m_ommIdx.resize(nLinks);
+    m_primOmms.assign(nLinks, b200pt_primitive_omm{});
+    for(uint32_t i = 0; i < nLinks; i++)
+    {
+      uint32_t h[4];
+      r.raw(h, sizeof(h));
+      r.vec(m_ommIdx[i], h[3]);
+      m_primOmms[i] = b200pt_primitive_omm{h[0], h[1], h[2], h[3] ? m_ommIdx[i].data() : nullptr, h[3]};
+    }
+  }
 }
 
 b200pt_scene_desc SceneData::desc() const
@@ -381,6 +423,11 @@ void PathTracer::onDetach(Resources&)
 void PathTracer::onSceneInvalidated(Resources& res)
 {
   const b200pt_scene_desc d = res.scene->desc();
+  // SceneOmm::create precedes the BLAS build; --useOpacityMicromap 0 skips the subsystem (src/main.cpp:114-115,349)
+  const bool omm = res.settings.useOpacityMicromap && !res.scene->primitiveOmms().empty();
+  check(b200pt_set_opacity_micromaps(m_h, res.scene->micromaps().data(), omm ? (uint32_t)res.scene->micromaps().size() : 0u,
+                                     res.scene->primitiveOmms().data(), omm ? (uint32_t)res.scene->primitiveOmms().size() : 0u),
+        "b200pt_set_opacity_micromaps");
   check(b200pt_set_scene(m_h, &d), "b200pt_set_scene");
 }
 

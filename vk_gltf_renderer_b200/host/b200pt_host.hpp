@@ -41,6 +41,7 @@ struct Settings
   float infinitePlaneBaseColor[3] = {0.5f, 0.5f, 0.5f};
   float infinitePlaneMetallic  = 0.0f;
   float infinitePlaneRoughness = 0.5f;
+  bool  useOpacityMicromap     = true;  // --useOpacityMicromap (src/main.cpp:114-115): consume EXT_mesh_opacity_micromap when the asset has it
 };
 
 // what nvutils::CameraManipulator hands the renderer (external to the reference tree): look-at + lens
@@ -62,6 +63,9 @@ public:
   std::vector<float> hdrRgb;           // optional environment carried by the blob
   int                hdrWidth = 0, hdrHeight = 0;
   size_t             triangleCount() const;
+  // EXT_mesh_opacity_micromap arrays carried by the blob (empty when the asset has none)
+  const std::vector<b200pt_micromap>&      micromaps() const { return m_micromaps; }
+  const std::vector<b200pt_primitive_omm>& primitiveOmms() const { return m_primOmms; }
 
 private:
   struct Prim
@@ -78,6 +82,11 @@ private:
   std::vector<std::vector<uint8_t>>    m_texPixels;
   std::vector<b200pt_texture>          m_textures;
   std::vector<b200pt_light>            m_lights;
+  std::vector<std::vector<uint8_t>>                  m_ommData;
+  std::vector<std::vector<b200pt_micromap_triangle>> m_ommTris;
+  std::vector<std::vector<int32_t>>                  m_ommIdx;
+  std::vector<b200pt_micromap>                       m_micromaps;
+  std::vector<b200pt_primitive_omm>                  m_primOmms;
 };
 
 // the subset of the reference's Resources the path tracer touches

@@ -147,6 +147,8 @@ int main(int argc, char** argv)
         res.settings.hdrEnvRotation = std::stof(next());
       else if(a == "--envSystem")
         res.settings.envSystem = std::stoi(next());
+      else if(a == "--useOpacityMicromap")
+        res.settings.useOpacityMicromap = std::stoi(next()) != 0;
       else if(a == "--out")
         outPath = next();
       else if(a == "--outRaw")

@@ -232,6 +232,21 @@ class Scene:
                 e = np.ascontiguousarray(env_rgb, "<f4")
                 f.write(struct.pack("<2I", e.shape[1], e.shape[0]))
                 f.write(e.tobytes())
+            # optional trailing section: the EXT_mesh_opacity_micromap arrays (SceneOmm's input)
+            if self.prim_omms:
+                f.write(b"OMM1")
+                f.write(struct.pack("<2I", len(self.micromaps), len(self.prim_omms)))
+                for m in self.micromaps:
+                    data = np.ascontiguousarray(m["data"], np.uint8)
+                    tris = np.ascontiguousarray(m["triangles"], abi.MICROMAP_TRIANGLE_DTYPE)
+                    f.write(struct.pack("<QI", data.size, tris.size))
+                    f.write(data.tobytes())
+                    f.write(tris.tobytes())
+                for po in self.prim_omms:
+                    idx = None if po.get("indices") is None else np.ascontiguousarray(po["indices"], "<i4")
+                    f.write(struct.pack("<4I", po["renderPrimID"], po["micromap"], po.get("baseTriangle", 0), 0 if idx is None else idx.size))
+                    if idx is not None:
+                        f.write(idx.tobytes())
 
 
 def _glm(m):
