@@ -35,8 +35,10 @@ def _dump(path, tris, rays):
 
 
 def _run(exe, path):
-    for mod in ("3", "-8"):
-        out = subprocess.run([exe, path, "1000000", mod], capture_output=True, text=True, timeout=600)
+    # (opaque modulus, opacity-micromap level): the last two runs give every non-opaque triangle a synthetic micromap (csrc/omm.cuh):
+    # OPAQUE micro-triangles must behave like opaque triangles, TRANSPARENT ones like no triangle, in both protocols
+    for mod, omm in (("3", "0"), ("-8", "0"), ("3", "3"), ("-8", "2")):
+        out = subprocess.run([exe, path, "1000000", mod, omm], capture_output=True, text=True, timeout=600)
         print(out.stdout)
         assert out.returncode == 0, out.stdout + out.stderr
         assert "mismatches: nearest opaque 0, shadow 0, candidates 0" in out.stdout

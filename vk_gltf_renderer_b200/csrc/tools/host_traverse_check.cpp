@@ -3,7 +3,11 @@
 // of the opaque hit in continuation walks) compiled for the host through host_shim.h and checked against brute force over all
 // triangles, on the tree the product's builder (bvh.cpp) makes.  A third of the triangles is flagged non-opaque.
 //
-//   host_traverse_check dump.bin [maxRays] [opaqueMod]       (dump format of scripts/dump_bvh_input.py: triangles + rays)
+//   host_traverse_check dump.bin [maxRays] [opaqueMod] [ommLevel]   (dump format of scripts/dump_bvh_input.py: triangles + rays)
+//
+// ommLevel > 0: every non-opaque triangle gets an opacity micromap of that subdivision level (4-state format, states from a hash of
+// triangle and micro-triangle index; every 7th triangle a FULLY_TRANSPARENT / FULLY_OPAQUE special state instead) and the walks run
+// with the lookup of omm.cuh: an OPAQUE micro-triangle must behave like an opaque triangle, a TRANSPARENT one like no triangle.
 //
 // Checks, per ray, against the sorted brute-force hit list (the triangle test is the same fma chain, so bit for bit):
 // (1) closest protocol of k_trace / k_alpha with every candidate rejected: walks resumed behind the last candidate until a walk
@@ -27,6 +31,7 @@ struct BF
 {
   float    t;
   uint32_t gid;
+  int      kind;  // 1 opaque / committed, 2 any-hit candidate (hits on TRANSPARENT micro-triangles are not listed)
 };
 
 int main(int argc, char** argv)
@@ -53,6 +58,54 @@ int main(int argc, char** argv)
   WideBvh B;
   buildWideBvh(tris, gids, 0, B);
   BvhView view{reinterpret_cast<const float4*>(B.nodes.data()), reinterpret_cast<const float4*>(B.tris.data()), kPrmtPool};
+  // synthetic micromaps
+  const uint32_t        ommLevel = argc > 4 ? (uint32_t)std::atoi(argv[4]) : 0u;
+  std::vector<uint8_t>  ommData;
+  std::vector<uint32_t> ommRefOfGid(nT, kOmmNoLookup | (uint32_t)OMM_UNKNOWN), ommRef;
+  auto                  hash = [](uint32_t a, uint32_t b) {
+    uint32_t h = a * 2654435761u ^ (b + 0x9e3779b9u) * 2246822519u;
+    h ^= h >> 15;
+    h *= 3266489917u;
+    h ^= h >> 13;
+    return h;
+  };
+  if(ommLevel)
+  {
+    const uint32_t micro = 1u << (2 * ommLevel), bytes = (micro * 2 + 7) / 8;
+    for(uint32_t i = 0; i < nT; i++)
+    {
+      if(isOpaque(i))
+        continue;
+      if(i % 7 == 0)
+      {
+        ommRefOfGid[i] = kOmmNoLookup | (uint32_t)((i / 7) & 1u ? OMM_OPAQUE : OMM_TRANSPARENT);
+        continue;
+      }
+      ommRefOfGid[i] = (ommLevel << 28) | (1u << 27) | (uint32_t)ommData.size();
+      const size_t at = ommData.size();
+      ommData.resize(at + bytes, 0);
+      for(uint32_t m = 0; m < micro; m++)
+        ommData[at + (m >> 2)] |= (uint8_t)((hash(i, m) & 3u) << ((m & 3u) * 2u));
+    }
+    ommData.resize(ommData.size() + 4, 0);
+    ommRef.resize(B.numTris);
+    for(uint32_t k = 0; k < B.numTris; k++)
+    {
+      uint32_t gid;
+      std::memcpy(&gid, &B.tris[(size_t)k * 12 + 11], 4);
+      ommRef[k] = ommRefOfGid[gid];
+    }
+    view.ommRef = ommRef.data();
+    view.ommData = ommData.data();
+  }
+  // how the walk must see a hit: 1 opaque (committed), 0 absent, 2 any-hit candidate
+  auto effective = [&](uint32_t gid, float u, float v) -> int {
+    if(isOpaque(gid))
+      return 1;
+    if(!ommLevel)
+      return 2;
+    return ommStateOf(ommRefOfGid[gid], u, v, [&](uint32_t o) { return (uint32_t)ommData[o]; });
+  };
   std::printf("tris %u nodes %u rays %u kCand %d\n", B.numTris, B.numNodes, nR, kCand);
 
   uint64_t bad1 = 0, bad2 = 0, bad3 = 0, hits = 0, listed = 0;
@@ -78,13 +131,17 @@ int main(int argc, char** argv)
       const float  v = dotFma(dir, qvec) * inv;
       const float  t = dotFma(e2, qvec) * inv;
       if((det != 0.0f) & (u >= 0.0f) & (u <= 1.0f) & (v >= 0.0f) & (u + v <= 1.0f) & (t > tmin) & (t < tmax))
-        bf.push_back(BF{t, i});
+      {
+        const int kind = effective(i, u, v);
+        if(kind != OMM_TRANSPARENT)
+          bf.push_back(BF{t, i, kind});
+      }
     }
     std::sort(bf.begin(), bf.end(), [](const BF& a, const BF& b) { return a.t < b.t || (a.t == b.t && a.gid < b.gid); });
     // expected: nearest opaque hit, non-opaque hits strictly in front of it
     size_t firstOpaque = bf.size();
     for(size_t k = 0; k < bf.size(); k++)
-      if(isOpaque(bf[k].gid))
+      if(bf[k].kind == 1)
       {
         firstOpaque = k;
         break;
@@ -94,7 +151,7 @@ int main(int argc, char** argv)
     {
       std::vector<BF> expect;
       for(size_t k = 0; k < bf.size(); k++)
-        if(!isOpaque(bf[k].gid) && (firstOpaque == bf.size() || bf[k].t < bf[firstOpaque].t))
+        if(bf[k].kind == 2 && (firstOpaque == bf.size() || bf[k].t < bf[firstOpaque].t))
           expect.push_back(bf[k]);
       Cand     cand[kCand];
       TraceHit opq;
