@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200PT_ABI_VERSION 4
+#define B200PT_ABI_VERSION 5
 
 /* error codes */
 #define B200PT_OK 0
@@ -349,6 +349,52 @@ int b200pt_bvh_build_ms(b200pt_t* h, double* ms);
  * device and the wide BVHs are refitted bottom-up (topology kept); a refitted tree answers every ray exactly like a freshly
  * built one.  Synchronous. */
 int b200pt_update_transforms(b200pt_t* h, const b200pt_render_node* nodes, uint32_t num_nodes);
+
+/* Animation feed, deforming part: morph-target blending and skeletal skinning of render primitives' vertex arrays ON THE DEVICE
+ * (shaders/morph.comp.slang:29-70, shaders/skinning.comp.slang:27-70, push constants shaders/animation_io.h.slang:29-59), as
+ * SceneAnimationVk::createAnimationResources / cmdUpdateAnimation drive them (src/gltf_scene_animation_vk.cpp:120-260, 396-592).
+ *
+ * b200pt_set_animation uploads the static inputs once (base arrays, deltas, weights / joints; all copied) for the primitives of
+ * the CURRENT scene (call it after b200pt_set_scene; the next b200pt_set_scene drops them).  vertexCount must equal the
+ * primitive's.  Normals / tangents are processed only when the task AND the primitive carry them (shader: hasNormals /
+ * hasTangents, host: vb.normal.buffer / vb.tangent.buffer).
+ *
+ * b200pt_animate is one cmdUpdateAnimation: the per-frame inputs are the concatenations, in task order, of every morph
+ * task's target weights (mesh.weights, :445-458), every skin task's joint matrices (glm mat4 bytes, 16 floats per joint:
+ * inverse(meshNode) * jointNode * inverseBind, :470-483) and normal matrices (glm mat3 bytes, 9 floats per joint:
+ * transpose(inverse(mat3(joint)))).  All morph kernels run, then all skin kernels (a primitive that is both morphed and skinned
+ * is skinned from its morphed arrays, :545-556), the per-triangle shade records of the touched primitives are re-gathered, and
+ * the trees are refitted like b200pt_update_transforms does (the BLAS update the reference records next).  Synchronous.
+ * Arithmetic order is pinned in csrc/animate.cuh and restated in oracle/animation.py. */
+typedef struct b200pt_morph_task /* MorphPushConstant minus the per-frame / output pointers */
+{
+  uint32_t     renderPrimID;
+  uint32_t     vertexCount;
+  uint32_t     numTargets;
+  uint32_t     _pad;
+  const float* basePositions;  /* vertexCount x 3                                  */
+  const float* baseNormals;    /* vertexCount x 3 or NULL                          */
+  const float* baseTangents;   /* vertexCount x 4 or NULL                          */
+  const float* positionDeltas; /* numTargets x vertexCount x 3                     */
+  const float* normalDeltas;   /* numTargets x vertexCount x 3 or NULL             */
+  const float* tangentDeltas;  /* numTargets x vertexCount x 3 or NULL             */
+} b200pt_morph_task;
+
+typedef struct b200pt_skin_task /* SkinPushConstant minus the per-frame / output pointers */
+{
+  uint32_t       renderPrimID;
+  uint32_t       vertexCount;
+  uint32_t       numJoints;
+  uint32_t       _pad;
+  const float*   basePositions; /* vertexCount x 3                                 */
+  const float*   baseNormals;   /* vertexCount x 3 or NULL                         */
+  const float*   baseTangents;  /* vertexCount x 4 or NULL                         */
+  const float*   weights;       /* vertexCount x 4 (WEIGHTS_0)                     */
+  const int32_t* joints;        /* vertexCount x 4 (JOINTS_0 widened to int32)     */
+} b200pt_skin_task;
+
+int b200pt_set_animation(b200pt_t* h, const b200pt_morph_task* morphs, uint32_t num_morphs, const b200pt_skin_task* skins, uint32_t num_skins);
+int b200pt_animate(b200pt_t* h, const float* morph_weights, const float* joint_matrices, const float* normal_matrices);
 
 /* nvvk::HdrIbl::loadEnvironment (external; reference call site src/renderer.cpp:1994-1996):
  * takes the decoded lat-long image (RGB float, row 0 = +Y pole), builds the alias table

@@ -1,0 +1,137 @@
+"""Animation feed without a GPU: the numpy restatement of the reference's morph / skinning compute shaders
+(oracle/animation.py; shaders/morph.comp.slang:29-70, shaders/skinning.comp.slang:27-70) against analytic known answers, and
+the DEVICE source (csrc/animate.cuh, the bodies of k_morph / k_skin) compiled for the host and compared with it bit for bit."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "vk_gltf_renderer_b200", "csrc")
+CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
+sys.path.insert(0, ROOT)
+
+
+def _glm(m):
+    """mathematical 4x4 / 3x3 -> glm byte order [c, r]"""
+    return np.asarray(m, np.float64).T.astype(np.float32)
+
+
+def test_skinning_known_answers():
+    """one joint with weight 1 is a rigid transform of positions, the inverse-transpose on normals, the upper 3x3 on tangents
+    (w kept); an identity skeleton reproduces the base mesh; influences with weight 0, a negative joint or a joint beyond the
+    skin are skipped (skinning.comp.slang:49-52)."""
+    from oracle import animation as A
+    rng = np.random.default_rng(0)
+    V = 200
+    p = rng.normal(size=(V, 3)).astype(np.float32)
+    n = rng.normal(size=(V, 3)).astype(np.float32)
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    t = np.concatenate([np.cross(n, [0.3, 0.5, 0.8]), np.where(rng.random((V, 1)) < 0.5, -1.0, 1.0)], 1).astype(np.float32)
+    c, s = np.cos(0.9), np.sin(0.9)
+    M = np.array([[c, -s, 0, 0.5], [s, c, 0, -0.25], [0, 0, 1.7, 0.1], [0, 0, 0, 1.0]])
+    jm = np.stack([_glm(M), _glm(np.eye(4))])
+    nm = np.stack([_glm(np.linalg.inv(M[:3, :3]).T), _glm(np.eye(3))])
+    w = np.zeros((V, 4), np.float32)
+    j = np.zeros((V, 4), np.int32)
+    w[:, 0] = 1.0
+    w[:, 1], j[:, 1] = 0.0, 1       # weight 0: skipped
+    w[:, 2], j[:, 2] = 0.7, -1      # negative joint: skipped
+    w[:, 3], j[:, 3] = 0.4, 2       # beyond the skin (2 joints): skipped
+    sp, sn, st = A.skin(p, n, t, w, j, jm, nm)
+    ref_p = (p.astype(np.float64) @ M[:3, :3].T + M[:3, 3])
+    assert np.allclose(sp, ref_p, rtol=0, atol=2e-6)
+    ref_n = n.astype(np.float64) @ np.linalg.inv(M[:3, :3])
+    ref_n /= np.linalg.norm(ref_n, axis=1, keepdims=True)
+    assert np.allclose(sn, ref_n, atol=2e-6)
+    ref_t = t[:, :3].astype(np.float64) @ M[:3, :3].T
+    ref_t /= np.linalg.norm(ref_t, axis=1, keepdims=True)
+    assert np.allclose(st[:, :3], ref_t, atol=2e-6) and np.array_equal(st[:, 3], t[:, 3])
+    # identity skeleton, weights summing to 1 over two joints: the base mesh up to rounding of the weighted sum
+    w2 = np.zeros((V, 4), np.float32)
+    w2[:, 0], w2[:, 1] = 0.25, 0.75
+    j2 = np.zeros((V, 4), np.int32)
+    j2[:, 1] = 1
+    ident = np.stack([_glm(np.eye(4))] * 2), np.stack([_glm(np.eye(3))] * 2)
+    sp2, sn2, _ = A.skin(p, n, t, w2, j2, *ident)
+    assert np.allclose(sp2, p, atol=1e-6) and np.allclose(sn2, n, atol=1e-6)
+
+
+def test_morph_known_answers():
+    """weights of 0 skip their target (morph.comp.slang:45-47): all-zero weights return the base positions bit for bit and
+    normalised base normals; one target with weight 1 adds exactly its deltas; tangent.w passes through."""
+    from oracle import animation as A
+    rng = np.random.default_rng(1)
+    V = 150
+    p = rng.normal(size=(V, 3)).astype(np.float32)
+    n = (rng.normal(size=(V, 3)) * 3).astype(np.float32)
+    t = rng.normal(size=(V, 4)).astype(np.float32)
+    dp, dn, dt = (rng.normal(size=(3, V, 3)).astype(np.float32) for _ in range(3))
+    pos, nrm, tan = A.morph(p, n, t, dp, dn, dt, [0.0, 0.0, 0.0])
+    assert np.array_equal(pos, p)
+    assert np.allclose(np.linalg.norm(nrm, axis=1), 1.0, atol=1e-6) and np.allclose(nrm, n / np.linalg.norm(n, axis=1, keepdims=True), atol=1e-6)
+    assert np.array_equal(tan[:, 3], t[:, 3])
+    pos, nrm, tan = A.morph(p, n, t, dp, dn, dt, [0.0, 1.0, 0.0])
+    assert np.array_equal(pos, p + dp[1])
+    pos, nrm, tan = A.morph(p, None, None, dp, dn, dt, [0.5, 0.0, -2.0])
+    assert nrm is None and tan is None
+    assert np.array_equal(pos, (p + np.float32(0.5) * dp[0]) + np.float32(-2.0) * dp[2])
+
+
+def _write_task(path, kind, V, K, bp, bn, bt, rest, dn=None, dt=None):
+    with open(path, "wb") as f:
+        f.write(np.array([kind, V, K, bn is not None, bt is not None, dn is not None, dt is not None], np.uint32).tobytes())
+        for a in (bp, bn, bt):
+            if a is not None:
+                f.write(np.ascontiguousarray(a, np.float32).tobytes())
+        for a in rest:
+            if a is not None:
+                f.write(np.ascontiguousarray(a).tobytes())
+
+
+def test_device_animation_source_matches_the_oracle(tmp_path):
+    """csrc/animate.cuh compiled for the host (tools/host_animate_check.cpp): the morph and skin bodies the sm_100a kernels run
+    give the same bits as oracle/animation.py on every task and pose of the animated test scene, including the morph -> skin
+    composition of the banner."""
+    if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    from oracle import animation as A
+    from vk_gltf_renderer_b200 import synth
+    exe = str(tmp_path / "host_animate_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I" + CUDA_INC, "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(CSRC, "tools", "host_animate_check.cpp")])
+    scn, morphs, skins, pose = synth.synth_animated()
+
+    def run(kind, V, K, bp, bn, bt, rest, dn=None, dt=None):
+        _write_task(str(tmp_path / "task.bin"), kind, V, K, bp, bn, bt, rest, dn, dt)
+        subprocess.check_call([exe, str(tmp_path / "task.bin"), str(tmp_path / "out.bin")], stdout=subprocess.DEVNULL)
+        raw = np.fromfile(str(tmp_path / "out.bin"), np.float32)
+        pos, o = raw[:V * 3].reshape(V, 3), V * 3
+        nrm = tan = None
+        if bn is not None:
+            nrm, o = raw[o:o + V * 3].reshape(V, 3), o + V * 3
+        if bt is not None:
+            tan = raw[o:o + V * 4].reshape(V, 4)
+        return pos, nrm, tan
+
+    def same(a, b):
+        return (a is None and b is None) or np.array_equal(np.asarray(a, np.float32).view(np.uint32), np.asarray(b, np.float32).view(np.uint32))
+    for k in range(3):
+        mw, jm, nm = pose(k)
+        morphed = {}
+        for t, w in zip(morphs, mw):
+            V = len(t.base_positions)
+            got = run(0, V, len(w), t.base_positions, t.base_normals, t.base_tangents, [t.position_deltas, t.normal_deltas, t.tangent_deltas, w],
+                      t.normal_deltas, t.tangent_deltas)
+            ref = A.morph(t.base_positions, t.base_normals, t.base_tangents, t.position_deltas, t.normal_deltas, t.tangent_deltas, w)
+            assert all(same(g, r) for g, r in zip(got, ref)), ("morph", k, t.render_prim)
+            morphed[t.render_prim] = ref
+        for t, m, n_ in zip(skins, jm, nm):
+            bp, bn, bt = morphed.get(t.render_prim, (t.base_positions, t.base_normals, t.base_tangents))
+            V = len(bp)
+            got = run(1, V, t.num_joints, bp, bn, bt, [np.asarray(t.weights, np.float32), np.asarray(t.joints, np.int32), m, n_])
+            ref = A.skin(bp, bn, bt, t.weights, t.joints, m, n_)
+            assert all(same(g, r) for g, r in zip(got, ref)), ("skin", k, t.render_prim)
+            assert np.isfinite(ref[0]).all()

@@ -126,6 +126,22 @@ class PrimitiveOmm(C.Structure):
                 ("indices", C.POINTER(C.c_int32)), ("numIndices", C.c_uint32)]
 
 
+class MorphTask(C.Structure):
+    """b200pt_morph_task (MorphPushConstant minus the per-frame / output pointers, shaders/animation_io.h.slang:45-59)"""
+    _fields_ = [("renderPrimID", C.c_uint32), ("vertexCount", C.c_uint32), ("numTargets", C.c_uint32), ("_pad", C.c_uint32),
+                ("basePositions", c_float_p), ("baseNormals", c_float_p), ("baseTangents", c_float_p),
+                ("positionDeltas", c_float_p), ("normalDeltas", c_float_p), ("tangentDeltas", c_float_p)]
+
+
+class SkinTask(C.Structure):
+    """b200pt_skin_task (SkinPushConstant minus the per-frame / output pointers, shaders/animation_io.h.slang:29-43)"""
+    _fields_ = [("renderPrimID", C.c_uint32), ("vertexCount", C.c_uint32), ("numJoints", C.c_uint32), ("_pad", C.c_uint32),
+                ("basePositions", c_float_p), ("baseNormals", c_float_p), ("baseTangents", c_float_p),
+                ("weights", c_float_p), ("joints", C.POINTER(C.c_int32))]
+
+
+assert C.sizeof(MorphTask) == 64 and C.sizeof(SkinTask) == 56
+
 OMM_FORMAT_2_STATE, OMM_FORMAT_4_STATE = 1, 2
 OMM_INDEX_FULLY_TRANSPARENT, OMM_INDEX_FULLY_OPAQUE, OMM_INDEX_FULLY_UNKNOWN_TRANSPARENT, OMM_INDEX_FULLY_UNKNOWN_OPAQUE = -1, -2, -3, -4
 assert C.sizeof(MicromapTriangle) == 8

@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "bvh.h"
+#include "animate.cuh"
 #include "lbvh.cuh"
 #include "shade.cuh"
 
@@ -1339,6 +1340,29 @@ __global__ void __launch_bounds__(128) k_refit_level(float* nodes, const float* 
     refitNode(first + i, nodes, tris, nodeBox);
 }
 
+// ---- animation feed (animate.cuh): morph.comp.slang / skinning.comp.slang, one thread per vertex like the reference's
+// ANIMATION_WORKGROUP_SIZE = 256 dispatches; HBM-bound (<= 72 B read + 40 B written per vertex, matrices stay in L1) -------------
+__global__ void __launch_bounds__(256) k_morph(MorphTaskDev T)
+{
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if(v < T.vertexCount)
+    morphVertex(T, v);
+}
+
+__global__ void __launch_bounds__(256) k_skin(SkinTaskDev T)
+{
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if(v < T.vertexCount)
+    skinVertex(T, v);
+}
+
+__global__ void __launch_bounds__(256) k_regather_shade(ShadeRec* recs, DevPrim P, uint32_t triCount)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if(t < triCount)
+    regatherShadeRec(recs + t, P, t);
+}
+
 // ---- ray-level API (parity tests / traversal micro-benchmark): the rays run through the PRODUCTION kernels
 // (k_trace / k_shadow -> k_alpha -> continuation round -> k_alpha) on a scratch path pool -------------------------
 __global__ void __launch_bounds__(256) k_rays_load(PathState P, const float4* __restrict__ rays, uint32_t n, const uint32_t* __restrict__ seeds, uint32_t* q, uint32_t* cnt,
@@ -1542,6 +1566,22 @@ struct b200pt
   uint32_t            numSceneNodes = 0;
   b200pt_render_node* dNodesW = nullptr;  // == S.nodes, writable
   const DevPrim*      dPrimsW = nullptr;
+  // animation feed (b200pt_set_animation / b200pt_animate): host copy of every primitive's device arrays + sizes, the writable
+  // shade records, the uploaded static task inputs and the per-frame buffers (m_morphWeightsBuffer / m_jointMatricesBuffer /
+  // m_normalMatricesBuffer of SceneAnimationVk, with per-task offsets)
+  struct PrimHost
+  {
+    DevPrim  d{};
+    uint32_t vertexCount = 0, triCount = 0, recBase = 0;
+  };
+  std::vector<PrimHost>     primHost;
+  ShadeRec*                 dShadeRecsW = nullptr;
+  std::vector<void*>        animAllocs;
+  std::vector<MorphTaskDev> morphTasks;
+  std::vector<SkinTaskDev>  skinTasks;
+  std::vector<uint32_t>     morphPrim, skinPrim;  // renderPrimID per task
+  float *                   dMorphWeights = nullptr, *dJointMats = nullptr, *dNormalMats = nullptr;
+  size_t                    numMorphWeights = 0, numJoints = 0;
 
   // env
   float4* dEnv = nullptr;
@@ -1810,11 +1850,27 @@ void freeRayPool(b200pt* h)
   h->rayCapacity = 0;
 }
 
+void freeAnimation(b200pt* h)
+{
+  for(void* p : h->animAllocs)
+    cudaFree(p);
+  h->animAllocs.clear();
+  h->morphTasks.clear();
+  h->skinTasks.clear();
+  h->morphPrim.clear();
+  h->skinPrim.clear();
+  h->dMorphWeights = h->dJointMats = h->dNormalMats = nullptr;
+  h->numMorphWeights = h->numJoints = 0;
+}
+
 void freeScene(b200pt* h)
 {
+  freeAnimation(h);
   for(void* p : h->sceneAllocs)
     cudaFree(p);
   h->sceneAllocs.clear();
+  h->primHost.clear();
+  h->dShadeRecsW = nullptr;
   h->haveScene = false;
 }
 
@@ -2286,6 +2342,13 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
   if((rc = upload(h, h->sceneAllocs, prims.data(), prims.size(), &dPrims)))
     return rc;
   S.prims = dPrims;
+  h->primHost.resize(s->numRenderPrimitives);
+  for(uint32_t i = 0; i < s->numRenderPrimitives; i++)
+  {
+    h->primHost[i].d = prims[i];
+    h->primHost[i].vertexCount = s->renderPrimitives[i].vertexCount;
+    h->primHost[i].triCount = s->renderPrimitives[i].triangleCount;
+  }
 
   // --- textures ---
   std::vector<DevTex> devTex(s->numTextures);
@@ -2687,6 +2750,9 @@ int b200pt_set_scene(b200pt_t* h, const b200pt_scene_desc* s)
       return rc;
     S.shadeRecs = dRecs;
     S.shadeIdx = dIdx;
+    h->dShadeRecsW = dRecs;
+    for(uint32_t i = 0; i < s->numRenderPrimitives; i++)
+      h->primHost[i].recBase = recBase[i];
     S.matOfSlot = dMat;
     S.numMaterials = (int)s->numMaterials;
   }
@@ -2961,23 +3027,11 @@ int b200pt_bvh_build_ms(b200pt_t* h, double* ms)
   return B200PT_OK;
 }
 
-int b200pt_update_transforms(b200pt_t* h, const b200pt_render_node* nodes, uint32_t num_nodes)
+// triangle records recomputed from the primitives' current vertices and the nodes' current transforms, then every tree
+// refitted bottom-up (refit.cuh); synchronous
+static int refitTrees(b200pt_t* h)
 {
-  if(!h || !h->haveScene || !nodes || num_nodes != h->numSceneNodes)
-  {
-    if(h)
-      h->err = "b200pt_update_transforms: needs the scene's render-node count (materials / primitives of the nodes must not change)";
-    return B200PT_E_INVALID;
-  }
-  CK(cudaSetDevice(h->device));
-  {
-    const int frc = flushPending(h);
-    if(frc)
-      return frc;
-  }
-  syncAll(h);
   cudaStream_t st = h->stream;
-  CK(cudaMemcpyAsync(h->dNodesW, nodes, (size_t)num_nodes * sizeof(b200pt_render_node), cudaMemcpyHostToDevice, st));
   for(int t = 0; t < 3; t++)
   {
     b200pt::TreeDev& T = h->tree[t];
@@ -3004,6 +3058,227 @@ int b200pt_update_transforms(b200pt_t* h, const b200pt_render_node* nodes, uint3
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(st));
   return B200PT_OK;
+}
+
+int b200pt_update_transforms(b200pt_t* h, const b200pt_render_node* nodes, uint32_t num_nodes)
+{
+  if(!h || !h->haveScene || !nodes || num_nodes != h->numSceneNodes)
+  {
+    if(h)
+      h->err = "b200pt_update_transforms: needs the scene's render-node count (materials / primitives of the nodes must not change)";
+    return B200PT_E_INVALID;
+  }
+  CK(cudaSetDevice(h->device));
+  {
+    const int frc = flushPending(h);
+    if(frc)
+      return frc;
+  }
+  syncAll(h);
+  cudaStream_t st = h->stream;
+  CK(cudaMemcpyAsync(h->dNodesW, nodes, (size_t)num_nodes * sizeof(b200pt_render_node), cudaMemcpyHostToDevice, st));
+  return refitTrees(h);
+}
+
+int b200pt_set_animation(b200pt_t* h, const b200pt_morph_task* morphs, uint32_t num_morphs, const b200pt_skin_task* skins, uint32_t num_skins)
+{
+  if(!h || !h->haveScene || (num_morphs && !morphs) || (num_skins && !skins))
+  {
+    if(h)
+      h->err = "b200pt_set_animation: needs a scene (b200pt_set_scene first) and task arrays";
+    return B200PT_E_INVALID;
+  }
+  CK(cudaSetDevice(h->device));
+  {
+    const int frc = flushPending(h);
+    if(frc)
+      return frc;
+  }
+  syncAll(h);
+  freeAnimation(h);
+  auto fail = [&](const char* msg) {
+    freeAnimation(h);
+    h->err = msg;
+    return B200PT_E_INVALID;
+  };
+  int rc;
+  for(uint32_t i = 0; i < num_morphs; i++)
+  {
+    const b200pt_morph_task& m = morphs[i];
+    if(m.renderPrimID >= h->primHost.size())
+      return fail("b200pt_set_animation: morph task for a render primitive out of range");
+    const b200pt::PrimHost& P = h->primHost[m.renderPrimID];
+    if(m.vertexCount != P.vertexCount || !m.basePositions || (m.numTargets && !m.positionDeltas))
+      return fail("b200pt_set_animation: morph task needs base positions, position deltas and the primitive's vertex count");
+    MorphTaskDev T{};
+    T.vertexCount = m.vertexCount;
+    T.numTargets = m.numTargets;
+    const size_t nv = m.vertexCount, nd = (size_t)m.numTargets * m.vertexCount * 3;
+    float*       d;
+    if((rc = upload(h, h->animAllocs, m.basePositions, nv * 3, &d)))
+      return rc;
+    T.basePos = d;
+    if(m.baseNormals && P.d.nrm)
+    {
+      if((rc = upload(h, h->animAllocs, m.baseNormals, nv * 3, &d)))
+        return rc;
+      T.baseNrm = d;
+    }
+    if(m.baseTangents && P.d.tan)
+    {
+      if((rc = upload(h, h->animAllocs, m.baseTangents, nv * 4, &d)))
+        return rc;
+      T.baseTan = d;
+    }
+    if((rc = upload(h, h->animAllocs, m.positionDeltas, nd, &d)))
+      return rc;
+    T.dPos = d;
+    if(m.normalDeltas && T.baseNrm)
+    {
+      if((rc = upload(h, h->animAllocs, m.normalDeltas, nd, &d)))
+        return rc;
+      T.dNrm = d;
+    }
+    if(m.tangentDeltas && T.baseTan)
+    {
+      if((rc = upload(h, h->animAllocs, m.tangentDeltas, nd, &d)))
+        return rc;
+      T.dTan = d;
+    }
+    T.outPos = const_cast<float*>(P.d.pos);
+    T.outNrm = const_cast<float*>(P.d.nrm);
+    T.outTan = const_cast<float*>(P.d.tan);
+    h->numMorphWeights += m.numTargets;
+    h->morphTasks.push_back(T);
+    h->morphPrim.push_back(m.renderPrimID);
+  }
+  for(uint32_t i = 0; i < num_skins; i++)
+  {
+    const b200pt_skin_task& k = skins[i];
+    if(k.renderPrimID >= h->primHost.size())
+      return fail("b200pt_set_animation: skin task for a render primitive out of range");
+    const b200pt::PrimHost& P = h->primHost[k.renderPrimID];
+    if(k.vertexCount != P.vertexCount || !k.basePositions || !k.weights || !k.joints || k.numJoints == 0)
+      return fail("b200pt_set_animation: skin task needs base positions, weights, joints and the primitive's vertex count");
+    SkinTaskDev  T{};
+    const size_t nv = k.vertexCount;
+    T.vertexCount = k.vertexCount;
+    T.numJoints = k.numJoints;
+    float* d;
+    int*   di;
+    if((rc = upload(h, h->animAllocs, k.basePositions, nv * 3, &d)))
+      return rc;
+    T.basePos = d;
+    if(k.baseNormals && P.d.nrm)
+    {
+      if((rc = upload(h, h->animAllocs, k.baseNormals, nv * 3, &d)))
+        return rc;
+      T.baseNrm = d;
+    }
+    if(k.baseTangents && P.d.tan)
+    {
+      if((rc = upload(h, h->animAllocs, k.baseTangents, nv * 4, &d)))
+        return rc;
+      T.baseTan = d;
+    }
+    if((rc = upload(h, h->animAllocs, k.weights, nv * 4, &d)))
+      return rc;
+    T.weights = d;
+    if((rc = upload(h, h->animAllocs, k.joints, nv * 4, &di)))
+      return rc;
+    T.joints = di;
+    T.outPos = const_cast<float*>(P.d.pos);
+    T.outNrm = const_cast<float*>(P.d.nrm);
+    T.outTan = const_cast<float*>(P.d.tan);
+    h->numJoints += k.numJoints;
+    h->skinTasks.push_back(T);
+    h->skinPrim.push_back(k.renderPrimID);
+  }
+  // the per-frame buffers, sized once (createAnimationResources: totalJointMatBytes / totalNormalMatBytes / morph weights)
+  CK(cudaMalloc((void**)&h->dMorphWeights, std::max<size_t>(h->numMorphWeights, 1) * sizeof(float)));
+  h->animAllocs.push_back(h->dMorphWeights);
+  CK(cudaMalloc((void**)&h->dJointMats, std::max<size_t>(h->numJoints, 1) * 16 * sizeof(float)));
+  h->animAllocs.push_back(h->dJointMats);
+  CK(cudaMalloc((void**)&h->dNormalMats, std::max<size_t>(h->numJoints, 1) * 9 * sizeof(float)));
+  h->animAllocs.push_back(h->dNormalMats);
+  size_t wOfs = 0, jOfs = 0;
+  for(auto& T : h->morphTasks)
+  {
+    T.weights = h->dMorphWeights + wOfs;
+    wOfs += T.numTargets;
+  }
+  for(auto& T : h->skinTasks)
+  {
+    T.jointMatrices = h->dJointMats + jOfs * 16;
+    T.normalMatrices = h->dNormalMats + jOfs * 9;
+    jOfs += T.numJoints;
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return B200PT_OK;
+}
+
+int b200pt_animate(b200pt_t* h, const float* morph_weights, const float* joint_matrices, const float* normal_matrices)
+{
+  if(!h || !h->haveScene || (h->morphTasks.empty() && h->skinTasks.empty()) || (h->numMorphWeights && !morph_weights)
+     || (h->numJoints && (!joint_matrices || !normal_matrices)))
+  {
+    if(h)
+      h->err = "b200pt_animate: needs b200pt_set_animation and the per-frame weights / joint matrices / normal matrices of its tasks";
+    return B200PT_E_INVALID;
+  }
+  CK(cudaSetDevice(h->device));
+  {
+    const int frc = flushPending(h);
+    if(frc)
+      return frc;
+  }
+  syncAll(h);
+  cudaStream_t st = h->stream;
+  // Phase 1 (gltf_scene_animation_vk.cpp:430-494): one upload of all per-frame data
+  if(h->numMorphWeights)
+    CK(cudaMemcpyAsync(h->dMorphWeights, morph_weights, h->numMorphWeights * sizeof(float), cudaMemcpyHostToDevice, st));
+  if(h->numJoints)
+  {
+    CK(cudaMemcpyAsync(h->dJointMats, joint_matrices, h->numJoints * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->dNormalMats, normal_matrices, h->numJoints * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  // Phase 2 (:497-533): morph
+  std::vector<uint8_t> touched(h->primHost.size(), 0), morphed(h->primHost.size(), 0);
+  for(size_t i = 0; i < h->morphTasks.size(); i++)
+  {
+    const MorphTaskDev& T = h->morphTasks[i];
+    if(T.numTargets == 0)
+      continue;  // (:508) nothing to blend: the vertex buffers keep what they hold
+    k_morph<<<(T.vertexCount + 255) / 256, 256, 0, st>>>(T);
+    h->kernelLaunches++;
+    touched[h->morphPrim[i]] = morphed[h->morphPrim[i]] = 1;
+  }
+  // Phase 3 (:536-582): skin; a primitive morphed above is skinned from its own (morphed) arrays
+  for(size_t i = 0; i < h->skinTasks.size(); i++)
+  {
+    SkinTaskDev T = h->skinTasks[i];
+    if(morphed[h->skinPrim[i]])
+    {
+      const DevPrim& P = h->primHost[h->skinPrim[i]].d;
+      T.basePos = P.pos;
+      T.baseNrm = P.nrm ? P.nrm : T.baseNrm;
+      T.baseTan = P.tan ? P.tan : T.baseTan;
+    }
+    k_skin<<<(T.vertexCount + 255) / 256, 256, 0, st>>>(T);
+    h->kernelLaunches++;
+    touched[h->skinPrim[i]] = 1;
+  }
+  // the per-triangle shade records of the touched primitives follow their vertex arrays
+  for(size_t p = 0; p < touched.size(); p++)
+    if(touched[p] && h->primHost[p].triCount)
+    {
+      const b200pt::PrimHost& P = h->primHost[p];
+      k_regather_shade<<<(P.triCount + 255) / 256, 256, 0, st>>>(h->dShadeRecsW + P.recBase, P.d, P.triCount);
+      h->kernelLaunches++;
+    }
+  CK(cudaGetLastError());
+  // the BLAS update the reference records after the compute barrier (:586-590): triangle records + bottom-up refit
+  return refitTrees(h);
 }
 
 int b200pt_set_environment(b200pt_t* h, const float* rgb, int w, int hh, float* integral_out)

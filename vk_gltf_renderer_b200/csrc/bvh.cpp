@@ -99,7 +99,9 @@ struct Builder
     n2.push_back(Node2());
     std::vector<Job> stack;
     stack.push_back({0, 0, (uint32_t)tris.size()});
-    const int NB = 16;
+    // SAH bins per axis (BVH_BINS=8..64 for builder experiments; 16 is what every measurement in profiles/ used unless it says otherwise)
+    static const int NB = std::max(4, std::min(64, getenv("BVH_BINS") ? atoi(getenv("BVH_BINS")) : 16));
+    const int        kMaxBins = 64;
     while(!stack.empty())
     {
       Job j = stack.back();
@@ -130,8 +132,8 @@ struct Builder
         float e = cb.hi[ax] - cb.lo[ax];
         if(!(e > 0.f))
           continue;
-        Box      bins[NB];
-        uint32_t cnt[NB];
+        Box      bins[kMaxBins];
+        uint32_t cnt[kMaxBins];
         for(int b = 0; b < NB; b++)
         {
           bins[b].reset();
@@ -145,8 +147,8 @@ struct Builder
           cnt[b]++;
           bins[b].grow(tbox[t]);
         }
-        float    rArea[NB];
-        uint32_t rCnt[NB];
+        float    rArea[kMaxBins];
+        uint32_t rCnt[kMaxBins];
         Box      acc;
         acc.reset();
         uint32_t c = 0;

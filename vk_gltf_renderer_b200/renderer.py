@@ -143,6 +143,36 @@ class PathTracer:
             arr[i].renderPrimID = rn["renderPrimID"]
         self._ck(self._L.b200pt_update_transforms(self._h, arr, n), "b200pt_update_transforms")
 
+    def set_animation(self, morph_tasks=(), skin_tasks=()):
+        """SceneAnimationVk::createAnimationResources analogue (b200pt_set_animation): uploads the static inputs of the morph /
+        skin tasks (vk_gltf_renderer_b200.animation.MorphTask / SkinTask) of the current scene."""
+        f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+        keep = []
+        mt = (abi.MorphTask * max(len(morph_tasks), 1))()
+        for i, t in enumerate(morph_tasks):
+            arrs = [f32(t.base_positions), f32(t.base_normals), f32(t.base_tangents), f32(t.position_deltas), f32(t.normal_deltas), f32(t.tangent_deltas)]
+            keep.append(arrs)
+            mt[i].renderPrimID, mt[i].vertexCount, mt[i].numTargets = t.render_prim, arrs[0].shape[0], arrs[3].shape[0]
+            (mt[i].basePositions, mt[i].baseNormals, mt[i].baseTangents, mt[i].positionDeltas, mt[i].normalDeltas, mt[i].tangentDeltas) = [abi.fptr(a) for a in arrs]
+        sk = (abi.SkinTask * max(len(skin_tasks), 1))()
+        for i, t in enumerate(skin_tasks):
+            arrs = [f32(t.base_positions), f32(t.base_normals), f32(t.base_tangents), f32(t.weights)]
+            j = np.ascontiguousarray(t.joints, np.int32)
+            keep.append((arrs, j))
+            sk[i].renderPrimID, sk[i].vertexCount, sk[i].numJoints = t.render_prim, arrs[0].shape[0], t.num_joints
+            sk[i].basePositions, sk[i].baseNormals, sk[i].baseTangents, sk[i].weights = [abi.fptr(a) for a in arrs]
+            sk[i].joints = j.ctypes.data_as(C.POINTER(C.c_int32))
+        self._ck(self._L.b200pt_set_animation(self._h, mt, len(morph_tasks), sk, len(skin_tasks)), "b200pt_set_animation")
+        self._anim = (list(morph_tasks), list(skin_tasks))
+
+    def animate(self, morph_weights=(), joint_matrices=(), normal_matrices=()):
+        """one SceneAnimationVk::cmdUpdateAnimation (b200pt_animate): per morph task its target weights, per skin task its joint
+        matrices [numJoints, 4, 4] (glm column-major: element [j, c, r]) and normal matrices [numJoints, 3, 3]; vertex arrays,
+        shade records and trees are updated on the device."""
+        cat = lambda xs, n: np.ascontiguousarray(np.concatenate([np.asarray(x, np.float32).reshape(-1) for x in xs]) if len(xs) else np.zeros(n, np.float32), np.float32)
+        w, jm, nm = cat(morph_weights, 1), cat(joint_matrices, 16), cat(normal_matrices, 9)
+        self._ck(self._L.b200pt_animate(self._h, w.ctypes.data_as(C.c_void_p), jm.ctypes.data_as(C.c_void_p), nm.ctypes.data_as(C.c_void_p)), "b200pt_animate")
+
     def setEnvironment(self, rgb):
         rgb = np.ascontiguousarray(rgb, np.float32)
         integral = C.c_float()

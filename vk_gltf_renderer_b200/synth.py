@@ -520,6 +520,117 @@ def synth_material_zoo(seed=1234, tex_size=64):
     return scn
 
 
+def synth_animated(seed=1234, tex_size=64):
+    """Deforming geometry for the animation feed (b200pt_set_animation / b200pt_animate; shaders/skinning.comp.slang,
+    shaders/morph.comp.slang): a normal-mapped ground, a SKINNED tube (3 joints, blended weights, unused influence slots with
+    weight 0 / joint -1 / a joint index beyond the skin) instanced twice (one instance mirrored), a MORPHED sphere (2 targets with
+    position, normal and tangent deltas) and a banner that is BOTH morphed and skinned (morph -> skin composition,
+    src/gltf_scene_animation_vk.cpp:545-556).  Returns (scene, morph_tasks, skin_tasks, pose) with pose(k) -> (morph weights per
+    morph task, joint matrices per skin task, normal matrices per skin task) for a few key poses."""
+    from .animation import MorphTask, SkinTask, joint_matrices
+    rng = np.random.default_rng(seed)
+    scn = Scene()
+    base, mr, nm = make_texture_set(tex_size, rng, (0.7, 0.72, 0.68))
+    tb, tm, tn = scn.add_texture(base, srgb=True), scn.add_texture(mr), scn.add_texture(nm)
+    textured = dict(pbrBaseColorTexture=scn.add_texture_info(tb), pbrMetallicRoughnessTexture=scn.add_texture_info(tm),
+                    normalTexture=scn.add_texture_info(tn))
+    m_floor = scn.add_material(pbrBaseColorFactor=[1, 1, 1, 1], pbrRoughnessFactor=1.0, pbrMetallicFactor=0.1, **textured)
+    m_arm = scn.add_material(pbrBaseColorFactor=[0.9, 0.55, 0.35, 1], pbrRoughnessFactor=0.6, pbrMetallicFactor=0.0, **textured)
+    m_blob = scn.add_material(pbrBaseColorFactor=[0.85, 0.85, 0.9, 1], pbrRoughnessFactor=0.3, pbrMetallicFactor=1.0, **textured)
+    m_flag = scn.add_material(pbrBaseColorFactor=[0.3, 0.5, 0.85, 1], pbrRoughnessFactor=0.7, pbrMetallicFactor=0.0, doubleSided=1, **textured)
+
+    def ground(u, v):
+        return _xyz((u * 2 - 1) * 5, np.zeros_like(u), (1 - v * 2) * 5)
+    scn.add_node(scn.add_primitive(*_split(param_surface(ground, 6, 6, (3, 3)))), m_floor)
+
+    # --- skinned tube: object space along +y, 0..2.4 ---
+    def tube(u, v):
+        a = u * 2 * math.pi
+        return _xyz(0.25 * np.cos(a), v * 2.4, -0.25 * np.sin(a))
+    tp = _split(param_surface(tube, 20, 24, (2, 4)))
+    arm = scn.add_primitive(*tp)
+    pos = tp[0]
+    y = pos[:, 1] / 2.4
+    w = np.zeros((len(pos), 4), np.float32)
+    j = np.zeros((len(pos), 4), np.int32)
+    w[:, 0] = np.clip(1.0 - y * 2.0, 0, 1)
+    w[:, 2] = np.clip(y * 2.0 - 1.0, 0, 1)
+    w[:, 1] = 1.0 - w[:, 0] - w[:, 2]
+    j[:, 0], j[:, 1], j[:, 2] = 0, 1, 2
+    j[:, 3] = np.where(np.arange(len(pos)) % 3 == 0, -1, 7)   # unused slot: weight 0 with a negative / out-of-range joint
+    w[::5, 3] = 0.25                                           # ... and a positive weight on an out-of-range joint (skipped by the shader)
+    j[::5, 3] = 7
+    arm_t = np.eye(4)
+    arm_t[:3, 3] = [-1.8, 0.0, 0.3]
+    scn.add_node(arm, m_arm, arm_t)
+    arm_m = np.diag([-1.0, 1.0, 1.0, 1.0])
+    arm_m[:3, 3] = [2.4, 0.0, -0.8]
+    scn.add_node(arm, m_arm, arm_m)
+    skin_arm = SkinTask(arm, pos.copy(), w, j, 3, base_normals=tp[2].copy(), base_tangents=tp[5].copy())
+
+    # --- morphed sphere ---
+    sp = _split(_sphere(0.0, 1.0, 0.0, 0.7, n=28))
+    blob = scn.add_primitive(*sp)
+    bp, bn, bt = sp[0], sp[2], sp[5]
+    d0 = (bn * (0.35 * np.maximum(0.0, np.sin(6.0 * bp[:, 1:2])))).astype(np.float32)              # ribs along the normal
+    d1 = np.stack([0.4 * (bp[:, 1] - 1.0) * bp[:, 2], np.zeros(len(bp)), -0.4 * (bp[:, 1] - 1.0) * bp[:, 0]], 1).astype(np.float32)  # twist
+    dn = (rng.normal(size=(2, len(bp), 3)) * 0.15).astype(np.float32)
+    dt = (rng.normal(size=(2, len(bp), 3)) * 0.10).astype(np.float32)
+    blob_t = np.eye(4)
+    blob_t[:3, 3] = [0.2, 0.0, -0.4]
+    scn.add_node(blob, m_blob, blob_t)
+    morph_blob = MorphTask(blob, bp.copy(), np.stack([d0, d1]), base_normals=bn.copy(), base_tangents=bt.copy(), normal_deltas=dn, tangent_deltas=dt)
+
+    # --- banner: morphed (wave) and then skinned (2 joints) ---
+    def banner(u, v):
+        return _xyz(u * 1.6, v * 1.0, np.zeros_like(u))
+    fp = _split(param_surface(banner, 16, 10, (2, 1)))
+    flag = scn.add_primitive(*fp)
+    fpos = fp[0]
+    wave = np.stack([np.zeros(len(fpos)), np.zeros(len(fpos)), 0.2 * np.sin(5.0 * fpos[:, 0])], 1).astype(np.float32)
+    fw = np.zeros((len(fpos), 4), np.float32)
+    fj = np.zeros((len(fpos), 4), np.int32)
+    fw[:, 1] = np.clip(fpos[:, 0] / 1.6, 0, 1)
+    fw[:, 0] = 1.0 - fw[:, 1]
+    fj[:, 1] = 1
+    flag_t = np.eye(4)
+    flag_t[:3, 3] = [0.9, 1.3, 1.0]
+    scn.add_node(flag, m_flag, flag_t)
+    morph_flag = MorphTask(flag, fpos.copy(), wave[None], base_normals=fp[2].copy(), base_tangents=fp[5].copy())
+    skin_flag = SkinTask(flag, fpos.copy(), fw, fj, 2, base_normals=fp[2].copy(), base_tangents=fp[5].copy())
+
+    scn.lights = [_light("point", position=(0.5, 3.5, 2.5), color=(1.0, 0.95, 0.9), intensity=25.0)]
+    cam = Camera()
+    cam.eye = np.array([0.4, 2.4, 5.6], np.float32)
+    cam.center = np.array([0.1, 1.0, 0.0], np.float32)
+    cam.yfov = math.radians(45.0)
+    cam.znear, cam.zfar = 0.05, 100.0
+    scn.camera = cam
+
+    def rot_z(a, pivot_y):
+        c, s_ = math.cos(a), math.sin(a)
+        r = np.array([[c, -s_, 0, 0], [s_, c, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1.0]])
+        t0, t1 = np.eye(4), np.eye(4)
+        t0[1, 3], t1[1, 3] = -pivot_y, pivot_y
+        return t1 @ r @ t0
+
+    def pose(k):
+        a = [0.0, 0.45, -0.7][k % 3]
+        # the arm's skeleton: joint nodes at y = 0 / 0.8 / 1.6 in the mesh node's frame, a chain bending about z; bind = rest pose
+        rest = [np.eye(4) for _ in range(3)]
+        for i, yy in enumerate((0.0, 0.8, 1.6)):
+            rest[i][1, 3] = yy
+        b1, b2 = rot_z(a, 0.8), rot_z(a, 0.8) @ rot_z(1.3 * a, 1.6)
+        world = [np.eye(4), rest[0], b1 @ rest[1], b2 @ rest[2]]           # node 0 = mesh node, 1..3 = joints
+        jm_arm, nm_arm = joint_matrices(world, [1, 2, 3], [np.linalg.inv(r) for r in rest], 0)
+        sc = np.diag([1.0, 1.0 + 0.3 * a, 1.0, 1.0])
+        fworld = [np.eye(4), np.eye(4), rot_z(0.8 * a, 0.5) @ sc]
+        jm_flag, nm_flag = joint_matrices(fworld, [1, 2], [np.eye(4)], 0)   # fewer inverse-bind matrices than joints: identity (:201-205)
+        mw = [np.array([[0.0, 0.0], [0.8, -0.5], [0.3, 1.0]][k % 3], np.float32), np.array([[0.0], [1.0], [-0.6]][k % 3], np.float32)]
+        return mw, [jm_arm, jm_flag], [nm_arm, nm_flag]
+    return scn, [morph_blob, morph_flag], [skin_arm, skin_flag], pose
+
+
 def triangle_soup(n, seed=1234, extent=1.0, size=0.15):
     """n random triangles in a cube: stress input for traversal parity tests."""
     rng = np.random.default_rng(seed)
