@@ -435,6 +435,35 @@ int b200pt_read_accum(b200pt_t* h, float* host_rgba32f, size_t num_floats);
 int b200pt_read_selection(b200pt_t* h, uint32_t* host_object_ids, float* host_ndc_depth, size_t num_pixels);
 int b200pt_get_selection_device(b200pt_t* h, uint32_t** dev_object_ids, float** dev_ndc_depth);
 
+/* Tone mapping + 8-bit encode of the accumulation image: what GltfRenderer::tonemap does to gBuffers[eImgRendered] before
+ * saveHeadlessOutputImage writes gBuffers[eImgTonemapped] (src/renderer.cpp:992-1054, 557-573).  The compute shader is
+ * nvshaders::Tonemapper (nvpro_core2, external to the reference tree): the struct mirrors the controls the reference's UI and
+ * Resources::tonemapperData expose, the operators are restated from their publications (csrc/tonemap.cuh) -- parity UNPINNED.
+ * method: 0 filmic (Hejl / Burgess-Dawson), 1 Uncharted 2, 2 clip (sRGB), 3 ACES (Hill fit), 4 AgX, 5 Khronos PBR neutral.
+ * isActive == 0 stores the clamped linear colour (the reference disables the tonemapper for debug / guide buffers).
+ * autoExposure != 0: exposure is multiplied by 0.18 / (log-average luminance of the image), from a 256-bin log2 histogram built
+ * on the device (the reference defaults to auto-exposure, src/resources.hpp:212).
+ *
+ * b200pt_tonemap: this handle's accumulation image (plain row tiles only; an interleaved multi-GPU tile is tonemapped after
+ * the gather with b200pt_tonemap_image) -> device RGBA8 (owned by the handle, b200pt_get_tonemapped_device) and, if
+ * host_rgba8 != NULL, copied to the host (tile_rows x width x 4 bytes).  exposure_used (may be NULL) receives the final
+ * exposure factor.  b200pt_tonemap_image: any device RGBA32F image of width x height -> a device RGBA8 image.  Synchronous. */
+typedef struct b200pt_tonemapper
+{
+  int32_t method;
+  int32_t isActive;
+  float   exposure;   /* 1 */
+  float   brightness; /* 1 */
+  float   contrast;   /* 1 */
+  float   saturation; /* 1 */
+  float   vignette;   /* 0 */
+  int32_t autoExposure;
+} b200pt_tonemapper;
+
+int b200pt_tonemap(b200pt_t* h, const b200pt_tonemapper* tm, uint8_t* host_rgba8, size_t num_bytes, float* exposure_used);
+int b200pt_tonemap_image(b200pt_t* h, const b200pt_tonemapper* tm, const float* dev_rgba32f, int width, int height, uint8_t* dev_rgba8, float* exposure_used);
+int b200pt_get_tonemapped_device(b200pt_t* h, uint8_t** dev_rgba8, size_t* num_bytes);
+
 /* Pipelined read-back: enqueue the copy of the image as of the frames submitted so far into (pinned) host memory
  * and return at once; b200pt_wait_read(slot) blocks until that copy has landed.  slot is 0..7; issuing a read on a
  * slot first waits for the slot's previous read.  With frames in flight a caller reads frame f while frame f+1

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(variant):
     L = _lib.lib(count_traversal=variant)
     for name in declared_symbols():
         assert hasattr(L, name), name
-    assert L.b200pt_abi_version() == 4
+    assert L.b200pt_abi_version() == 5
 
 
 def test_struct_layouts_match_reference_sizes():

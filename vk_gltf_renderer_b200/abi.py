@@ -126,6 +126,13 @@ class PrimitiveOmm(C.Structure):
                 ("indices", C.POINTER(C.c_int32)), ("numIndices", C.c_uint32)]
 
 
+class Tonemapper(C.Structure):
+    """b200pt_tonemapper: the controls of nvshaders::TonemapperData the reference exposes (src/resources.hpp:212, its UI);
+    method 0 filmic, 1 Uncharted 2, 2 clip, 3 ACES, 4 AgX, 5 Khronos PBR neutral"""
+    _fields_ = [("method", C.c_int32), ("isActive", C.c_int32), ("exposure", C.c_float), ("brightness", C.c_float),
+                ("contrast", C.c_float), ("saturation", C.c_float), ("vignette", C.c_float), ("autoExposure", C.c_int32)]
+
+
 class MorphTask(C.Structure):
     """b200pt_morph_task (MorphPushConstant minus the per-frame / output pointers, shaders/animation_io.h.slang:45-59)"""
     _fields_ = [("renderPrimID", C.c_uint32), ("vertexCount", C.c_uint32), ("numTargets", C.c_uint32), ("_pad", C.c_uint32),
@@ -140,7 +147,7 @@ class SkinTask(C.Structure):
                 ("weights", c_float_p), ("joints", C.POINTER(C.c_int32))]
 
 
-assert C.sizeof(MorphTask) == 64 and C.sizeof(SkinTask) == 56
+assert C.sizeof(MorphTask) == 64 and C.sizeof(SkinTask) == 56 and C.sizeof(Tonemapper) == 32
 
 OMM_FORMAT_2_STATE, OMM_FORMAT_4_STATE = 1, 2
 OMM_INDEX_FULLY_TRANSPARENT, OMM_INDEX_FULLY_OPAQUE, OMM_INDEX_FULLY_UNKNOWN_TRANSPARENT, OMM_INDEX_FULLY_UNKNOWN_OPAQUE = -1, -2, -3, -4

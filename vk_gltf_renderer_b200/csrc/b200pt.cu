@@ -29,6 +29,7 @@
 #include "animate.cuh"
 #include "lbvh.cuh"
 #include "shade.cuh"
+#include "tonemap.cuh"
 
 using namespace pt;
 
@@ -1340,6 +1341,55 @@ __global__ void __launch_bounds__(128) k_refit_level(float* nodes, const float* 
     refitNode(first + i, nodes, tris, nodeBox);
 }
 
+// ---- tone mapping + 8-bit encode (tonemap.cuh): HBM-bound, 16 B read + 4 B written per pixel (+ 16 B read for the histogram) ----
+__global__ void __launch_bounds__(256) k_tm_histogram(const float4* __restrict__ img, uint32_t n, uint32_t* __restrict__ hist)
+{
+  __shared__ uint32_t s_h[kTmBins];
+  for(int i = threadIdx.x; i < kTmBins; i += blockDim.x)
+    s_h[i] = 0u;
+  __syncthreads();
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    const float4 c = __ldg(&img[i]);
+    atomicAdd(&s_h[tmBin(0.2126f * c.x + 0.7152f * c.y + 0.0722f * c.z)], 1u);
+  }
+  __syncthreads();
+  for(int i = threadIdx.x; i < kTmBins; i += blockDim.x)
+    if(s_h[i])
+      atomicAdd(&hist[i], s_h[i]);
+}
+
+// log-average luminance over the bins above black -> exposure factor (integer counts, fixed summation order: deterministic)
+__global__ void k_tm_exposure(const uint32_t* __restrict__ hist, float baseExposure, float* __restrict__ out)
+{
+  if(blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    double sum = 0.0, cnt = 0.0;
+    for(int b = 1; b < kTmBins; b++)
+    {
+      const double centre = (double)kTmMinLog + ((double)b + 0.5) * (double)(kTmMaxLog - kTmMinLog) / (double)kTmBins;
+      sum += centre * (double)hist[b];
+      cnt += (double)hist[b];
+    }
+    *out = cnt > 0.0 ? baseExposure * (float)(0.18 / exp2(sum / cnt)) : baseExposure;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_tonemap(const float4* __restrict__ img, uchar4* __restrict__ out, int width, int rows, int y0, int fullHeight,
+                                                 const __grid_constant__ b200pt_tonemapper tm, const float* __restrict__ exposure)
+{
+  const uint32_t n = (uint32_t)width * (uint32_t)rows, stride = gridDim.x * blockDim.x;
+  const float    ex = *exposure;
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    const float4 c = __ldg(&img[i]);
+    const int    x = (int)(i % (uint32_t)width), y = y0 + (int)(i / (uint32_t)width);
+    const float3 r = tonemapPixel(tm, ex, f3(c.x, c.y, c.z), ((float)x + 0.5f) / (float)width, ((float)y + 0.5f) / (float)fullHeight);
+    out[i] = make_uchar4((unsigned char)tmUnorm8(r.x), (unsigned char)tmUnorm8(r.y), (unsigned char)tmUnorm8(r.z), (unsigned char)tmUnorm8(c.w));
+  }
+}
+
 // ---- animation feed (animate.cuh): morph.comp.slang / skinning.comp.slang, one thread per vertex like the reference's
 // ANIMATION_WORKGROUP_SIZE = 256 dispatches; HBM-bound (<= 72 B read + 40 B written per vertex, matrices stay in L1) -------------
 __global__ void __launch_bounds__(256) k_morph(MorphTaskDev T)
@@ -1594,6 +1644,8 @@ struct b200pt
   uint32_t           numPaths = 0;
   float4*            dAccumOwned = nullptr;
   float4*            dAccum = nullptr;
+  uchar4*            dTonemapped = nullptr;  // gBuffers[eImgTonemapped] of this tile (b200pt_tonemap), in poolAllocs
+  uint32_t*          dTmHist = nullptr;      // 256-bin log2-luminance histogram + the exposure factor behind it (allocated with the handle)
   uint32_t*          dSelect = nullptr;  // frame-0 outputs (gltf_pathtrace.slang:610-616): object id per pixel ...
   float*             dNdcDepth = nullptr;  // ... and NDC depth of the first hit
   // Frames in flight (like the reference app's swapchain ring): every lane owns a stream, a path pool, queues and
@@ -1894,6 +1946,7 @@ void freePool(b200pt* h)
   h->dAccum = nullptr;
   h->dSelect = nullptr;
   h->dNdcDepth = nullptr;
+  h->dTonemapped = nullptr;
   h->numPaths = 0;
   for(int l = 0; l < b200pt::kMaxLanes; l++)
   {
@@ -2144,6 +2197,7 @@ int b200pt_create(b200pt_t** out, int cuda_device)
       lutS[256 + i] = (float)i / 255.0f;
     }
     need(cudaMalloc((void**)&h->dLutSrgb, sizeof(lutS)));
+    need(cudaMalloc((void**)&h->dTmHist, (kTmBins + 1) * sizeof(uint32_t)));  // histogram + the exposure factor (a float in the last word)
     if(ok)
       need(cudaMemcpy(h->dLutSrgb, lutS, sizeof(lutS), cudaMemcpyHostToDevice));
   }
@@ -2190,6 +2244,7 @@ void b200pt_destroy(b200pt_t* h)
     cudaFree(h->dEnvAccel);
   cudaFree(h->dStats);
   cudaFree(h->dLutSrgb);
+  cudaFree(h->dTmHist);
   for(auto& e : h->evPool)
   {
     cudaEventDestroy(e.a);
@@ -3435,6 +3490,14 @@ int b200pt_resize(b200pt_t* h, int width, int height, int tile_y0, int tile_rows
     return fail(B200PT_E_NOMEM);
   }
   h->poolAllocs.push_back(h->dNdcDepth);
+  if(cudaMalloc((void**)&h->dTonemapped, n * 4) != cudaSuccess)
+  {
+    cudaGetLastError();
+    h->dTonemapped = nullptr;
+    h->err = "tonemapped image: out of device memory";
+    return fail(B200PT_E_NOMEM);
+  }
+  h->poolAllocs.push_back(h->dTonemapped);
   if(cudaMemsetAsync(h->dSelect, 0, n * 4, h->stream) != cudaSuccess || cudaMemsetAsync(h->dNdcDepth, 0, n * 4, h->stream) != cudaSuccess
      || cudaMemsetAsync(h->dAccumOwned, 0, n * 16, h->stream) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess)
   {
@@ -3516,6 +3579,79 @@ int b200pt_read_accum(b200pt_t* h, float* host, size_t num_floats)
   }
   CK(cudaMemcpyAsync(host, h->dAccum, (size_t)h->numPaths * 16, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  return B200PT_OK;
+}
+
+// histogram (when auto-exposure is on) -> exposure factor -> operator + UNORM8 store, on the handle's stream
+static int tonemapOnDevice(b200pt_t* h, const b200pt_tonemapper* tm, const float4* img, int width, int rows, int y0, int fullHeight, uchar4* out, float* exposure_used)
+{
+  if(tm->method < 0 || tm->method > 5 || !(tm->brightness > 0.0f))
+  {
+    h->err = "b200pt_tonemap: method must be 0..5 and brightness > 0";
+    return B200PT_E_INVALID;
+  }
+  cudaStream_t   st = h->stream;
+  const uint32_t n = (uint32_t)width * (uint32_t)rows;
+  float*         dExposure = reinterpret_cast<float*>(h->dTmHist + kTmBins);
+  if(tm->autoExposure && tm->isActive)
+  {
+    CK(cudaMemsetAsync(h->dTmHist, 0, kTmBins * sizeof(uint32_t), st));
+    k_tm_histogram<<<gridFor(h, 8), 256, 0, st>>>(img, n, h->dTmHist);
+    k_tm_exposure<<<1, 32, 0, st>>>(h->dTmHist, tm->exposure, dExposure);
+    h->kernelLaunches += 2;
+  }
+  else
+    CK(cudaMemcpyAsync(dExposure, &tm->exposure, sizeof(float), cudaMemcpyHostToDevice, st));
+  k_tonemap<<<gridFor(h, 8), 256, 0, st>>>(img, out, width, rows, y0, fullHeight, *tm, dExposure);
+  h->kernelLaunches++;
+  CK(cudaGetLastError());
+  if(exposure_used)
+    CK(cudaMemcpyAsync(exposure_used, dExposure, sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return B200PT_OK;
+}
+
+int b200pt_tonemap(b200pt_t* h, const b200pt_tonemapper* tm, uint8_t* host_rgba8, size_t num_bytes, float* exposure_used)
+{
+  if(!h || !tm || h->numPaths == 0 || (host_rgba8 && num_bytes < (size_t)h->numPaths * 4))
+    return B200PT_E_INVALID;
+  if(h->bandWorld > 1)
+  {
+    h->err = "b200pt_tonemap: an interleaved multi-GPU tile is tonemapped after the gather (b200pt_tonemap_image on the full image)";
+    return B200PT_E_UNSUPPORTED;
+  }
+  CK(cudaSetDevice(h->device));
+  {
+    const int frc = flushPending(h);
+    if(frc)
+      return frc;
+  }
+  const int rc = tonemapOnDevice(h, tm, h->dAccum, h->width, h->tileRows, h->tileY0, h->height, h->dTonemapped, exposure_used);
+  if(rc)
+    return rc;
+  if(host_rgba8)
+  {
+    CK(cudaMemcpyAsync(host_rgba8, h->dTonemapped, (size_t)h->numPaths * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return B200PT_OK;
+}
+
+int b200pt_tonemap_image(b200pt_t* h, const b200pt_tonemapper* tm, const float* dev_rgba32f, int width, int height, uint8_t* dev_rgba8, float* exposure_used)
+{
+  if(!h || !tm || !dev_rgba32f || !dev_rgba8 || width <= 0 || height <= 0)
+    return B200PT_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  return tonemapOnDevice(h, tm, reinterpret_cast<const float4*>(dev_rgba32f), width, height, 0, height, reinterpret_cast<uchar4*>(dev_rgba8), exposure_used);
+}
+
+int b200pt_get_tonemapped_device(b200pt_t* h, uint8_t** dev_rgba8, size_t* num_bytes)
+{
+  if(!h || h->numPaths == 0 || !dev_rgba8)
+    return B200PT_E_INVALID;
+  *dev_rgba8 = reinterpret_cast<uint8_t*>(h->dTonemapped);
+  if(num_bytes)
+    *num_bytes = (size_t)h->numPaths * 4;
   return B200PT_OK;
 }
 

@@ -252,6 +252,28 @@ class PathTracer:
         self._ck(self._L.b200pt_read_accum(self._h, out.ctypes.data_as(C.c_void_p), out.size), "b200pt_read_accum")
         return out
 
+    @staticmethod
+    def make_tonemapper(method=0, isActive=1, exposure=1.0, brightness=1.0, contrast=1.0, saturation=1.0, vignette=0.0, autoExposure=0):
+        """shaderio::TonemapperData defaults (filmic, everything neutral); the reference's Resources turns autoExposure on"""
+        return abi.Tonemapper(method, isActive, exposure, brightness, contrast, saturation, vignette, autoExposure)
+
+    def tonemap(self, tm=None):
+        """GltfRenderer::tonemap (src/renderer.cpp:992-1054): eImgRendered -> eImgTonemapped.  Returns (RGBA8 [rows, width, 4],
+        exposure factor used)."""
+        tm = tm or self.make_tonemapper()
+        w, _ = self._size
+        rows = self._tile[1]
+        out = np.empty((rows, w, 4), np.uint8)
+        ex = C.c_float()
+        self._ck(self._L.b200pt_tonemap(self._h, C.byref(tm), out.ctypes.data_as(C.c_void_p), out.size, C.byref(ex)), "b200pt_tonemap")
+        return out, ex.value
+
+    def tonemap_image(self, tm, dev_rgba32f, width, height, dev_rgba8):
+        """device RGBA32F image (e.g. the gathered multi-GPU frame) -> device RGBA8; returns the exposure factor used"""
+        ex = C.c_float()
+        self._ck(self._L.b200pt_tonemap_image(self._h, C.byref(tm), C.c_void_p(dev_rgba32f), width, height, C.c_void_p(dev_rgba8), C.byref(ex)), "b200pt_tonemap_image")
+        return ex.value
+
     def read_selection(self):
         """gBuffers[eImgSelection] (object id per pixel, render node + 1, 0 = miss) and the NDC depth image, as the first
         frame of the current accumulation wrote them (gltf_pathtrace.slang:604-616)."""
