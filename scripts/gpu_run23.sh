@@ -1,6 +1,6 @@
 # frame batch / frames in flight at the DRIVER's own invocation (--steps 20 --warmup 5), leaf cost 0.7, 7 vs 8 walk CTAs per SM
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_animation.py -q -m gpu -x 2>&1 | tail -15
+timeout 900 python -m pytest tests/test_gpu_animation.py tests/test_gpu_tonemap.py -q -m gpu 2>&1 | tail -15
 run() {
   TAG=$1; shift
   env "$@" python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-omm-pass > gpurun_out/r02y_bench_$TAG.json 2> gpurun_out/r02y_bench_$TAG.err

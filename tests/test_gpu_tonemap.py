@@ -49,3 +49,29 @@ def test_tonemap_of_a_rendered_frame_matches_the_oracle(std_env):
         pt.tonemap(pt.make_tonemapper(method=9))
     pt.onDetach(res)
     pt2.onDetach(res2)
+
+
+def test_headless_driver_writes_the_tonemapped_image(tmp_path):
+    """`--output file` of the reference application (src/renderer.cpp:171, saveHeadlessOutputImage :557-573): the C++ headless
+    driver tonemaps its accumulation image with Resources::tonemapperData's defaults (filmic, auto-exposure ON,
+    src/resources.hpp:212) through b200pt_tonemap and writes the 8-bit pixels (PPM: no jpg encoder here); they equal the
+    oracle's tonemap of the RGBA32F image the same run wrote."""
+    import os
+    import subprocess
+    from oracle import tonemap as T
+    from vk_gltf_renderer_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(os.path.dirname(_lib.LIB_PATH), "b200pt_headless")
+    raw, ppm = str(tmp_path / "box.raw"), str(tmp_path / "box.jpg")
+    cmd = [exe, "--headless", "--size", "96", "64", "--frames", "4", "--scenefile", os.path.join(root, "tests", "assets", "Box.glb"),
+           "--hdrfile", os.path.join(root, "tests", "assets", "std_env.hdr"), "--ptMaxDepth", "4", "--outRaw", raw, "--output", ppm]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert out.returncode == 0 and "HEADLESS_OUTPUT" in out.stdout, out.stdout
+    img = np.fromfile(raw, np.float32).reshape(64, 96, 4)
+    with open(ppm, "rb") as f:
+        assert f.readline() == b"P6\n" and f.readline() == b"96 64\n" and f.readline() == b"255\n"
+        got = np.frombuffer(f.read(), np.uint8).reshape(64, 96, 3)
+    ref, ex = T.tonemap(img, method=0, auto=1)
+    line = [l for l in out.stdout.splitlines() if l.startswith("HEADLESS_OUTPUT")][0]
+    assert abs(float(line.split("exposure=")[1]) / float(ex) - 1.0) < 1e-4
+    assert _close(got, ref[..., :3])

@@ -526,6 +526,23 @@ std::vector<float> PathTracer::readAccum()
   return img;
 }
 
+std::vector<uint8_t> PathTracer::tonemap(const b200pt_tonemapper& tm, float* exposureUsed)
+{
+  std::vector<uint8_t> img((size_t)m_width * (size_t)m_tileRows * 4);
+  check(b200pt_tonemap(m_h, &tm, img.data(), img.size(), exposureUsed), "b200pt_tonemap");
+  return img;
+}
+
+void PathTracer::setAnimation(const std::vector<b200pt_morph_task>& morphs, const std::vector<b200pt_skin_task>& skins)
+{
+  check(b200pt_set_animation(m_h, morphs.data(), (uint32_t)morphs.size(), skins.data(), (uint32_t)skins.size()), "b200pt_set_animation");
+}
+
+void PathTracer::animate(const std::vector<float>& morphWeights, const std::vector<float>& jointMatrices, const std::vector<float>& normalMatrices)
+{
+  check(b200pt_animate(m_h, morphWeights.data(), jointMatrices.data(), normalMatrices.data()), "b200pt_animate");
+}
+
 void PathTracer::synchronize() { check(b200pt_synchronize(m_h), "b200pt_synchronize"); }
 
 void PathTracer::setFramesInFlight(int n) { check(b200pt_set_frames_in_flight(m_h, n), "b200pt_set_frames_in_flight"); }

@@ -97,6 +97,8 @@ struct Resources
   int              hdrWidth = 0, hdrHeight = 0;
   Camera           camera;
   Settings         settings;
+  // Resources::tonemapperData (src/resources.hpp:212: the reference turns auto-exposure on): filmic, neutral controls
+  b200pt_tonemapper tonemapperData{0, 1, 1.0f, 1.0f, 1.0f, 1.0f, 0.0f, 1};
   int              width = 1920, height = 1080;
   int              frameCount = -1;  // reset to -1 and pre-incremented by the frame loop (src/renderer.cpp:1939-1977)
   int              cudaDevice = 0;
@@ -155,6 +157,11 @@ public:
 
   // gBuffers[eImgRendered] (RGBA32F running mean) of this renderer's tile
   std::vector<float> readAccum();
+  // GltfRenderer::tonemap (src/renderer.cpp:992-1054): gBuffers[eImgRendered] -> gBuffers[eImgTonemapped] (RGBA8) of this tile
+  std::vector<uint8_t> tonemap(const b200pt_tonemapper& tm, float* exposureUsed = nullptr);
+  // SceneAnimationVk::createAnimationResources / cmdUpdateAnimation analogues (b200pt_set_animation / b200pt_animate)
+  void setAnimation(const std::vector<b200pt_morph_task>& morphs, const std::vector<b200pt_skin_task>& skins);
+  void animate(const std::vector<float>& morphWeights, const std::vector<float>& jointMatrices, const std::vector<float>& normalMatrices);
   void               synchronize();
   void               setFramesInFlight(int n);
   void               setFrameBatch(int n);  // b200pt_set_frame_batch

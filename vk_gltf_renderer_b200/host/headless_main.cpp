@@ -42,6 +42,23 @@ static void writePfm(const std::string& path, const std::vector<float>& rgba, in
   std::fclose(f);
 }
 
+static void writePpm(const std::string& path, const std::vector<uint8_t>& rgba, int w, int h)
+{
+  FILE* f = std::fopen(path.c_str(), "wb");
+  if(!f)
+    throw Error("cannot write " + path);
+  std::fprintf(f, "P6\n%d %d\n255\n", w, h);
+  std::vector<uint8_t> row((size_t)w * 3);
+  for(int y = 0; y < h; y++)
+  {
+    for(int x = 0; x < w; x++)
+      for(int c = 0; c < 3; c++)
+        row[(size_t)x * 3 + c] = rgba[((size_t)y * w + x) * 4 + c];
+    std::fwrite(row.data(), 1, row.size(), f);
+  }
+  std::fclose(f);
+}
+
 static void writeRaw(const std::string& path, const std::vector<float>& rgba)
 {
   FILE* f = std::fopen(path.c_str(), "wb");
@@ -92,7 +109,7 @@ static std::string convertScene(const std::string& gltf, const std::string& hdrF
 
 int main(int argc, char** argv)
 {
-  std::string scenePath, hdrPath, outPath, rawPath, tmpBlob;
+  std::string scenePath, hdrPath, outPath, rawPath, tmpBlob, tonemappedPath;
   int         width = 1920, height = 1080, frames = 16, warmupFrames = 1, framesInFlight = 0;  // warm-up: src/benchmarking.hpp:128
   int         adaptiveSampling = 0, frameBatch = 0;
   Resources   res;
@@ -151,6 +168,14 @@ int main(int argc, char** argv)
         res.settings.useOpacityMicromap = std::stoi(next()) != 0;
       else if(a == "--out")
         outPath = next();
+      else if(a == "--output" || a == "--screenshot")
+        tonemappedPath = next();  // the reference's headless output image (src/renderer.cpp:171, 557-573; benchmarking.cpp:144-153)
+      else if(a == "--tonemapMethod")
+        res.tonemapperData.method = std::stoi(next());
+      else if(a == "--tonemapAutoExposure")
+        res.tonemapperData.autoExposure = std::stoi(next());
+      else if(a == "--tonemapExposure")
+        res.tonemapperData.exposure = std::stof(next());
       else if(a == "--outRaw")
         rawPath = next();
       else if(a.rfind("--pt", 0) == 0)
@@ -258,6 +283,16 @@ int main(int argc, char** argv)
         measuredFrames > 0 ? measuredWallMs / measuredFrames : 0.0, totalWallMs, frames > 0 ? totalWallMs / frames : 0.0, warmupFrames, measuredFrames,
         throughputMSps, sppPerSec, (unsigned long long)st.closestRays, (unsigned long long)st.shadowRays, mrays, scene.triangleCount());
 
+    if(!tonemappedPath.empty())
+    {
+      // saveHeadlessOutputImage: the tonemapped 8-bit image.  The reference encodes .jpg / .png through its image library; this
+      // driver has no encoder and writes the same pixels as a binary PPM (P6, alpha dropped), whatever the extension says.
+      float                      ex = 1.0f;
+      const std::vector<uint8_t> rgba = pt.tonemap(res.tonemapperData, &ex);
+      writePpm(tonemappedPath, rgba, width, pt.tileRows());
+      std::printf("HEADLESS_OUTPUT path=%s format=ppm tonemap_method=%d auto_exposure=%d exposure=%.6g\n", tonemappedPath.c_str(), res.tonemapperData.method,
+                  res.tonemapperData.autoExposure, ex);
+    }
     if(!outPath.empty() || !rawPath.empty())
     {
       const std::vector<float> img = pt.readAccum();
