@@ -350,6 +350,37 @@ int b200pt_bvh_build_ms(b200pt_t* h, double* ms);
  * built one.  Synchronous. */
 int b200pt_update_transforms(b200pt_t* h, const b200pt_render_node* nodes, uint32_t num_nodes);
 
+/* Animation feed, rigid part ON THE DEVICE: the node hierarchy's world matrices are propagated level by level and the render nodes
+ * (objectToWorld, worldToObject = inverse, materialID, renderPrimID) rewritten from them, then the trees are refitted -- the host
+ * uploads only the nodes' LOCAL matrices per frame.  Reference: shaders/world_matrix_propagate.comp.slang:27-42 (one dispatch per
+ * topological BFS level), shaders/update_render_instances.comp.slang:42-66, structs shaders/world_matrix_io.h.slang:29-69
+ * (PropagateWorldMatricesPushConstant, RenderNodeGpuMapping, UpdateRenderInstancesPushConstant).
+ * b200pt_set_node_hierarchy (after b200pt_set_scene; copied): parentIndices[numNodes] (-1 = root), topoNodeOrder[numNodes] in BFS
+ * order with levelOffsets[numLevels + 1] delimiting the levels, one mapping per render node of the scene (in render-node order) and
+ * optional per-render-node instance matrices (glm mat4 bytes; NULL = identity).
+ * b200pt_update_node_matrices: localMatrices[numNodes x 16] (glm mat4 bytes).  Synchronous.  Arithmetic order: csrc/animate.cuh. */
+typedef struct b200pt_render_node_mapping /* RenderNodeGpuMapping */
+{
+  int32_t nodeID;
+  int32_t pad0;
+  int32_t materialID;
+  int32_t renderPrimID;
+} b200pt_render_node_mapping;
+
+typedef struct b200pt_node_hierarchy
+{
+  uint32_t                          numNodes;
+  uint32_t                          numLevels;
+  const int32_t*                    parentIndices;
+  const int32_t*                    topoNodeOrder;
+  const uint32_t*                   levelOffsets;
+  const b200pt_render_node_mapping* mappings;          /* numRenderNodes of the current scene */
+  const float*                      instLocalMatrices; /* numRenderNodes x 16 or NULL */
+} b200pt_node_hierarchy;
+
+int b200pt_set_node_hierarchy(b200pt_t* h, const b200pt_node_hierarchy* hierarchy);
+int b200pt_update_node_matrices(b200pt_t* h, const float* local_matrices);
+
 /* Animation feed, deforming part: morph-target blending and skeletal skinning of render primitives' vertex arrays ON THE DEVICE
  * (shaders/morph.comp.slang:29-70, shaders/skinning.comp.slang:27-70, push constants shaders/animation_io.h.slang:29-59), as
  * SceneAnimationVk::createAnimationResources / cmdUpdateAnimation drive them (src/gltf_scene_animation_vk.cpp:120-260, 396-592).

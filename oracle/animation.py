@@ -109,3 +109,63 @@ def apply(scene, morph_tasks, skin_tasks, morph_weights, joint_mats, normal_mats
             prim["normals"] = nrm
         if tan is not None:
             prim["tangents"] = tan
+
+
+# ---- rigid part: shaders/world_matrix_propagate.comp.slang:27-42, shaders/update_render_instances.comp.slang:42-66 -------------
+def mat4_mul(A, B):
+    """glm product A * B on glm-ordered arrays [..., c, r]; C[c][r] = ((A[0][r] B[c][0] + A[1][r] B[c][1]) + A[2][r] B[c][2]) + A[3][r] B[c][3]"""
+    A, B = np.asarray(A, F), np.asarray(B, F)
+    C = np.empty(np.broadcast(A, B).shape, F)
+    for c in range(4):
+        for r in range(4):
+            C[..., c, r] = ((A[..., 0, r] * B[..., c, 0] + A[..., 1, r] * B[..., c, 1]) + A[..., 2, r] * B[..., c, 2]) + A[..., 3, r] * B[..., c, 3]
+    return C
+
+
+def mat4_inverse(m):
+    """glm's cofactor expansion (compute_inverse<4,4>) in fp32, same operation order as csrc/animate.cuh mat4Inverse"""
+    m = np.asarray(m, F)
+    M = lambda c, r: m[..., c, r]
+    c00 = M(2, 2) * M(3, 3) - M(3, 2) * M(2, 3); c02 = M(1, 2) * M(3, 3) - M(3, 2) * M(1, 3); c03 = M(1, 2) * M(2, 3) - M(2, 2) * M(1, 3)
+    c04 = M(2, 1) * M(3, 3) - M(3, 1) * M(2, 3); c06 = M(1, 1) * M(3, 3) - M(3, 1) * M(1, 3); c07 = M(1, 1) * M(2, 3) - M(2, 1) * M(1, 3)
+    c08 = M(2, 1) * M(3, 2) - M(3, 1) * M(2, 2); c10 = M(1, 1) * M(3, 2) - M(3, 1) * M(1, 2); c11 = M(1, 1) * M(2, 2) - M(2, 1) * M(1, 2)
+    c12 = M(2, 0) * M(3, 3) - M(3, 0) * M(2, 3); c14 = M(1, 0) * M(3, 3) - M(3, 0) * M(1, 3); c15 = M(1, 0) * M(2, 3) - M(2, 0) * M(1, 3)
+    c16 = M(2, 0) * M(3, 2) - M(3, 0) * M(2, 2); c18 = M(1, 0) * M(3, 2) - M(3, 0) * M(1, 2); c19 = M(1, 0) * M(2, 2) - M(2, 0) * M(1, 2)
+    c20 = M(2, 0) * M(3, 1) - M(3, 0) * M(2, 1); c22 = M(1, 0) * M(3, 1) - M(3, 0) * M(1, 1); c23 = M(1, 0) * M(2, 1) - M(2, 0) * M(1, 1)
+    f0, f1, f2 = (c00, c00, c02, c03), (c04, c04, c06, c07), (c08, c08, c10, c11)
+    f3, f4, f5 = (c12, c12, c14, c15), (c16, c16, c18, c19), (c20, c20, c22, c23)
+    v0 = (M(1, 0), M(0, 0), M(0, 0), M(0, 0)); v1 = (M(1, 1), M(0, 1), M(0, 1), M(0, 1))
+    v2 = (M(1, 2), M(0, 2), M(0, 2), M(0, 2)); v3 = (M(1, 3), M(0, 3), M(0, 3), M(0, 3))
+    inv = np.empty(m.shape, F)
+    for k in range(4):
+        sa = F(-1.0) if (k & 1) else F(1.0)
+        sb = -sa
+        inv[..., 0, k] = ((v1[k] * f0[k] - v2[k] * f1[k]) + v3[k] * f2[k]) * sa
+        inv[..., 1, k] = ((v0[k] * f0[k] - v2[k] * f3[k]) + v3[k] * f4[k]) * sb
+        inv[..., 2, k] = ((v0[k] * f1[k] - v1[k] * f3[k]) + v3[k] * f5[k]) * sa
+        inv[..., 3, k] = ((v0[k] * f2[k] - v1[k] * f4[k]) + v2[k] * f5[k]) * sb
+    d0, d1, d2, d3 = M(0, 0) * inv[..., 0, 0], M(0, 1) * inv[..., 1, 0], M(0, 2) * inv[..., 2, 0], M(0, 3) * inv[..., 3, 0]
+    one_over_det = F(1.0) / ((d0 + d1) + (d2 + d3))
+    return (inv * one_over_det[..., None, None]).astype(F)
+
+
+def propagate(local, parents, order, offsets):
+    """world[node] = world[parent] * local[node] level by level (identity for roots: the local matrix itself)"""
+    local = np.asarray(local, F)
+    world = np.zeros_like(local)
+    for l in range(len(offsets) - 1):
+        for n in order[offsets[l]:offsets[l + 1]]:
+            p = parents[n]
+            world[n] = local[n] if p < 0 else mat4_mul(world[p], local[n])
+    return world
+
+
+def render_nodes(world, mappings, inst_local=None):
+    """(objectToWorld [N,4,4], worldToObject [N,4,4]) per render node: instLocal * world[nodeID] (the shader's mul(world, instLocal)
+    on glm bytes), inverse by cofactors"""
+    o2w = []
+    for i, (node, _, _) in enumerate(mappings):
+        w = world[node]
+        o2w.append(w if inst_local is None else mat4_mul(np.asarray(inst_local[i], F), w))
+    o2w = np.asarray(o2w, F)
+    return o2w, mat4_inverse(o2w)

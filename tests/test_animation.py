@@ -135,3 +135,54 @@ def test_device_animation_source_matches_the_oracle(tmp_path):
             ref = A.skin(bp, bn, bt, t.weights, t.joints, m, n_)
             assert all(same(g, r) for g, r in zip(got, ref)), ("skin", k, t.render_prim)
             assert np.isfinite(ref[0]).all()
+
+
+def _glm_stack(ms):
+    return np.ascontiguousarray(np.asarray(ms, np.float64).transpose(0, 2, 1).astype(np.float32))
+
+
+def test_rigid_feed_known_answers_and_device_source(tmp_path):
+    """World-matrix propagation and render-node update (oracle/animation.py propagate / render_nodes / mat4_inverse;
+    shaders/world_matrix_propagate.comp.slang:27-42, update_render_instances.comp.slang:42-66): BFS levels put every parent before
+    its children, the propagated matrices equal the fp64 chain products, inverse * matrix = identity; and the DEVICE source
+    (csrc/animate.cuh propagateNode / updateRenderNode) compiled for the host gives the same bits."""
+    from oracle import animation as A
+    from vk_gltf_renderer_b200 import synth
+    from vk_gltf_renderer_b200.animation import topo_levels
+    scn, parents, mappings, inst, pose = synth.synth_hierarchy()
+    order, offsets = topo_levels(parents)
+    level = {int(n): l for l in range(len(offsets) - 1) for n in order[offsets[l]:offsets[l + 1]]}
+    assert sorted(order.tolist()) == list(range(len(parents))) and all(p < 0 or level[int(p)] < level[n] for n, p in enumerate(parents))
+    assert len(offsets) - 1 == 4
+    exe = None
+    if os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        exe = str(tmp_path / "host_animate_check")
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I" + CUDA_INC, "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                               os.path.join(CSRC, "tools", "host_animate_check.cpp")])
+    for k in range(3):
+        loc = pose(k)
+        world = A.propagate(_glm_stack(loc), parents, order, offsets)
+        for n in range(len(parents)):
+            m, p = loc[n], parents[n]
+            while p >= 0:
+                m, p = loc[p] @ m, parents[p]
+            assert np.allclose(world[n].T, m, atol=1e-5), n
+        o2w, w2o = A.render_nodes(world, mappings, _glm_stack(inst))
+        for i, (node, _, _) in enumerate(mappings):
+            assert np.allclose(o2w[i].T.astype(np.float64), inst[i] @ world[node].T.astype(np.float64), atol=1e-5)   # the shader's literal order
+            assert np.allclose(w2o[i].T.astype(np.float64) @ o2w[i].T.astype(np.float64), np.eye(4), atol=1e-5)
+        if exe:
+            with open(tmp_path / "task.bin", "wb") as f:
+                f.write(np.array([2, len(parents), len(mappings), len(offsets) - 1, 1, 0, 0], np.uint32).tobytes())
+                f.write(parents.astype(np.int32).tobytes() + order.astype(np.int32).tobytes() + offsets.astype(np.uint32).tobytes())
+                f.write(np.array([[n_, 0, m_, p_] for n_, m_, p_ in mappings], np.int32).tobytes())
+                f.write(_glm_stack(loc).tobytes() + _glm_stack(inst).tobytes())
+            subprocess.check_call([exe, str(tmp_path / "task.bin"), str(tmp_path / "out.bin")])
+            raw = np.fromfile(str(tmp_path / "out.bin"), np.uint8)
+            nw = len(parents) * 64
+            got_world = raw[:nw].view(np.float32).reshape(-1, 4, 4)
+            recs = raw[nw:].reshape(len(mappings), 136)
+            assert np.array_equal(got_world.view(np.uint32), world.view(np.uint32))
+            assert np.array_equal(recs[:, :64].copy().view(np.uint32).reshape(-1, 4, 4), o2w.view(np.uint32))
+            assert np.array_equal(recs[:, 64:128].copy().view(np.uint32).reshape(-1, 4, 4), w2o.view(np.uint32))
+            assert np.array_equal(recs[:, 128:].copy().view(np.int32), np.array([[m_, p_] for _, m_, p_ in mappings], np.int32))

@@ -104,3 +104,37 @@ def test_animation_argument_checks(std_env):
     with pytest.raises(B200PTError):
         pt.animate(*pose(1))
     pt.onDetach(res)
+
+
+def test_node_hierarchy_on_the_device_matches_the_oracle(std_env, oracle_mod):
+    """b200pt_set_node_hierarchy / b200pt_update_node_matrices: local matrices go up, world matrices are propagated level by level
+    on the device, the render nodes (objectToWorld, inverse, ids) rewritten and the trees refitted.  The oracle builds the scene
+    from scratch with the render nodes oracle/animation.py computes: hits bit for bit, image to 1e-3 (the inverse feeds the
+    normals).  One node chain mirrors its instance (negative determinant: the refit flips the winding)."""
+    from oracle import animation as A
+    from vk_gltf_renderer_b200 import synth
+    from vk_gltf_renderer_b200.animation import topo_levels
+    from vk_gltf_renderer_b200.renderer import B200PTError, PathTracer, Resources
+    scn, parents, mappings, inst, pose = synth.synth_hierarchy()
+    glm = lambda ms: np.ascontiguousarray(np.asarray(ms, np.float64).transpose(0, 2, 1).astype(np.float32))
+    res = Resources(scene=scn, hdr_rgb=std_env, camera=scn.camera, size=(160, 112))
+    pt = PathTracer(0)
+    pt.ptMaxDepth = 5
+    pt.onAttach(res)
+    with pytest.raises(B200PTError):
+        pt.update_node_matrices(glm(pose(0)))          # no hierarchy yet
+    pt.set_node_hierarchy(parents, mappings, glm(inst))
+    order, offsets = topo_levels(parents)
+    for k in (1, 2, 0):
+        loc = glm(pose(k))
+        pt.update_node_matrices(loc)
+        o2w, w2o = A.render_nodes(A.propagate(loc, parents, order, offsets), mappings, glm(inst))
+        ref_scn = synth.scene_from_state(copy.deepcopy(synth.scene_state(scn)))
+        for i, rn in enumerate(ref_scn.render_nodes):
+            rn["objectToWorld"], rn["worldToObject"] = o2w[i].reshape(-1).copy(), w2o[i].reshape(-1).copy()
+        _check_pose(pt, res, ref_scn, std_env, oracle_mod, "hierarchy pose %d" % k)
+    bad = parents.copy()
+    bad[1], bad[2] = 2, 1                               # a cycle: no valid level order
+    with pytest.raises(ValueError):
+        pt.set_node_hierarchy(bad, mappings)
+    pt.onDetach(res)

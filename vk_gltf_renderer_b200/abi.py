@@ -133,6 +133,16 @@ class Tonemapper(C.Structure):
                 ("contrast", C.c_float), ("saturation", C.c_float), ("vignette", C.c_float), ("autoExposure", C.c_int32)]
 
 
+class RenderNodeMapping(C.Structure):
+    """b200pt_render_node_mapping == RenderNodeGpuMapping (shaders/world_matrix_io.h.slang:41-47)"""
+    _fields_ = [("nodeID", C.c_int32), ("pad0", C.c_int32), ("materialID", C.c_int32), ("renderPrimID", C.c_int32)]
+
+
+class NodeHierarchy(C.Structure):
+    _fields_ = [("numNodes", C.c_uint32), ("numLevels", C.c_uint32), ("parentIndices", C.POINTER(C.c_int32)), ("topoNodeOrder", C.POINTER(C.c_int32)),
+                ("levelOffsets", c_u32_p), ("mappings", C.POINTER(RenderNodeMapping)), ("instLocalMatrices", c_float_p)]
+
+
 class MorphTask(C.Structure):
     """b200pt_morph_task (MorphPushConstant minus the per-frame / output pointers, shaders/animation_io.h.slang:45-59)"""
     _fields_ = [("renderPrimID", C.c_uint32), ("vertexCount", C.c_uint32), ("numTargets", C.c_uint32), ("_pad", C.c_uint32),

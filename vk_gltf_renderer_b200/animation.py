@@ -51,3 +51,28 @@ def joint_matrices(node_world, joint_nodes, inverse_bind, ref_node):
         jm.append(m.T)                               # column-major bytes
         nm.append(np.linalg.inv(m[:3, :3]))         # transpose(inverse(m3)) stored column-major: element [c, r] = inverse[c, r]
     return np.asarray(jm, np.float32), np.asarray(nm, np.float32)
+
+
+def topo_levels(parents):
+    """BFS levels of a node forest: (topoNodeOrder int32[numNodes], levelOffsets uint32[numLevels + 1]) -- what the reference
+    uploads for world_matrix_propagate.comp.slang (one dispatch per level, parents always in an earlier level)."""
+    parents = np.asarray(parents, np.int64)
+    depth = np.full(len(parents), -1, np.int64)
+    for n in range(len(parents)):
+        chain = []
+        k = n
+        while depth[k] < 0 and parents[k] >= 0:
+            chain.append(k)
+            k = parents[k]
+            if len(chain) > len(parents):
+                raise ValueError("node hierarchy has a cycle")
+        if depth[k] < 0:
+            depth[k] = 0
+        d = depth[k]
+        for c in reversed(chain):
+            d += 1
+            depth[c] = d
+    order = np.argsort(depth, kind="stable").astype(np.int32)
+    counts = np.bincount(depth, minlength=int(depth.max()) + 1)
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint32)
+    return order, offsets

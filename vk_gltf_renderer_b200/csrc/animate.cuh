@@ -119,6 +119,90 @@ PT_D void skinVertex(const SkinTaskDev& T, uint32_t v)
   }
 }
 
+// ---- rigid part on the device: world matrices down the node hierarchy, then the render nodes -------------------------------
+// shaders/world_matrix_propagate.comp.slang:27-42 (one dispatch per topological level: world[node] = world[parent] * local[node];
+// the shader's mul(local, parent) on glm bytes is the glm product parent * local) and
+// shaders/update_render_instances.comp.slang:42-66 (objectToWorld = mul(world[nodeID], instLocal[i]) -- on glm bytes that is the
+// glm product instLocal * world, followed literally although the CPU path of the reference multiplies the other way round,
+// src/gltf_scene.cpp:2419; the two agree whenever instLocal is the identity, i.e. without EXT_mesh_gpu_instancing --
+// worldToObject = inverse(objectToWorld), materialID / renderPrimID from the mapping).  Matrices are glm column-major: m[4 c + r].
+// Product: C[c][r] = ((A[0][r] B[c][0] + A[1][r] B[c][1]) + A[2][r] B[c][2]) + A[3][r] B[c][3] (glm's operator*); inverse: glm's
+// cofactor expansion (compute_inverse<4,4>), one reciprocal of the determinant times the adjugate.  The reference's shader calls the
+// GLSL.std.450 MatrixInverse, whose arithmetic is the driver's; pinned here and in oracle/animation.py alike.
+struct RenderNodeMapping  // RenderNodeGpuMapping, shaders/world_matrix_io.h.slang:41-47
+{
+  int nodeID, pad0, materialID, renderPrimID;
+};
+
+PT_HD void mat4Mul(const float* A, const float* B, float* C)  // C = A * B, may not alias
+{
+  for(int c = 0; c < 4; c++)
+    for(int r = 0; r < 4; r++)
+      C[4 * c + r] = ((A[r] * B[4 * c] + A[4 + r] * B[4 * c + 1]) + A[8 + r] * B[4 * c + 2]) + A[12 + r] * B[4 * c + 3];
+}
+
+PT_HD void mat4Inverse(const float* m, float* o)
+{
+#define M(c, r) m[4 * (c) + (r)]
+  const float c00 = M(2, 2) * M(3, 3) - M(3, 2) * M(2, 3), c02 = M(1, 2) * M(3, 3) - M(3, 2) * M(1, 3), c03 = M(1, 2) * M(2, 3) - M(2, 2) * M(1, 3);
+  const float c04 = M(2, 1) * M(3, 3) - M(3, 1) * M(2, 3), c06 = M(1, 1) * M(3, 3) - M(3, 1) * M(1, 3), c07 = M(1, 1) * M(2, 3) - M(2, 1) * M(1, 3);
+  const float c08 = M(2, 1) * M(3, 2) - M(3, 1) * M(2, 2), c10 = M(1, 1) * M(3, 2) - M(3, 1) * M(1, 2), c11 = M(1, 1) * M(2, 2) - M(2, 1) * M(1, 2);
+  const float c12 = M(2, 0) * M(3, 3) - M(3, 0) * M(2, 3), c14 = M(1, 0) * M(3, 3) - M(3, 0) * M(1, 3), c15 = M(1, 0) * M(2, 3) - M(2, 0) * M(1, 3);
+  const float c16 = M(2, 0) * M(3, 2) - M(3, 0) * M(2, 2), c18 = M(1, 0) * M(3, 2) - M(3, 0) * M(1, 2), c19 = M(1, 0) * M(2, 2) - M(2, 0) * M(1, 2);
+  const float c20 = M(2, 0) * M(3, 1) - M(3, 0) * M(2, 1), c22 = M(1, 0) * M(3, 1) - M(3, 0) * M(1, 1), c23 = M(1, 0) * M(2, 1) - M(2, 0) * M(1, 1);
+  const float f0[4] = {c00, c00, c02, c03}, f1[4] = {c04, c04, c06, c07}, f2[4] = {c08, c08, c10, c11};
+  const float f3_[4] = {c12, c12, c14, c15}, f4_[4] = {c16, c16, c18, c19}, f5[4] = {c20, c20, c22, c23};
+  const float v0[4] = {M(1, 0), M(0, 0), M(0, 0), M(0, 0)}, v1[4] = {M(1, 1), M(0, 1), M(0, 1), M(0, 1)};
+  const float v2[4] = {M(1, 2), M(0, 2), M(0, 2), M(0, 2)}, v3[4] = {M(1, 3), M(0, 3), M(0, 3), M(0, 3)};
+  float       inv[16];
+  for(int k = 0; k < 4; k++)
+  {
+    const float sa = (k & 1) ? -1.0f : 1.0f, sb = -sa;
+    inv[0 + k] = ((v1[k] * f0[k] - v2[k] * f1[k]) + v3[k] * f2[k]) * sa;
+    inv[4 + k] = ((v0[k] * f0[k] - v2[k] * f3_[k]) + v3[k] * f4_[k]) * sb;
+    inv[8 + k] = ((v0[k] * f1[k] - v1[k] * f3_[k]) + v3[k] * f5[k]) * sa;
+    inv[12 + k] = ((v0[k] * f2[k] - v1[k] * f4_[k]) + v2[k] * f5[k]) * sb;
+  }
+  const float d0 = M(0, 0) * inv[0], d1 = M(0, 1) * inv[4], d2 = M(0, 2) * inv[8], d3 = M(0, 3) * inv[12];
+  const float oneOverDet = 1.0f / ((d0 + d1) + (d2 + d3));
+  for(int k = 0; k < 16; k++)
+    o[k] = inv[k] * oneOverDet;
+#undef M
+}
+
+// one node of a level (world_matrix_propagate.comp.slang)
+PT_D void propagateNode(const float* local, float* world, const int* parents, const int* topoOrder, uint32_t levelOffset, uint32_t ti)
+{
+  const int node = topoOrder[levelOffset + ti], parent = parents[node];
+  float     out[16];
+  if(parent < 0)
+    for(int k = 0; k < 16; k++)
+      out[k] = local[(size_t)node * 16 + k];  // identity * local: exact
+  else
+    mat4Mul(world + (size_t)parent * 16, local + (size_t)node * 16, out);
+  for(int k = 0; k < 16; k++)
+    world[(size_t)node * 16 + k] = out[k];
+}
+
+// one render node (update_render_instances.comp.slang; the TlasInstance row it also writes is the refit's job here)
+PT_D void updateRenderNode(const float* world, const RenderNodeMapping* mappings, const float* instLocal, b200pt_render_node* out, uint32_t i)
+{
+  const RenderNodeMapping map = mappings[i];
+  float                   w[16];
+  if(instLocal)
+    mat4Mul(instLocal + (size_t)i * 16, world + (size_t)map.nodeID * 16, w);
+  else
+    for(int k = 0; k < 16; k++)
+      w[k] = world[(size_t)map.nodeID * 16 + k];
+  b200pt_render_node rn;
+  for(int k = 0; k < 16; k++)
+    rn.objectToWorld[k] = w[k];
+  mat4Inverse(w, rn.worldToObject);
+  rn.materialID = map.materialID;
+  rn.renderPrimID = map.renderPrimID;
+  out[i] = rn;
+}
+
 // the position / normal / tangent part of one triangle's ShadeRec from the primitive's (updated) vertex arrays; texture
 // coordinates, colours and the flags word keep what b200pt_set_scene gathered (layout: device_scene.cuh ShadeRec)
 PT_D void regatherShadeRec(ShadeRec* rec, const DevPrim& P, uint32_t tri)

@@ -193,7 +193,13 @@ __device__ __forceinline__ uint32_t fetchWork(bool need, uint32_t* workCounter, 
 // mode: TRACE_CONT = continuation round (the paths in the queue had all kCand candidates rejected by k_alpha and resume
 // behind the last one; P.hit seeds the opaque bound and is refined), TRACE_TMIN = rayO.w carries tmin (ray-level API).
 #ifndef B200PT_TRACE_MINBLOCKS
-#define B200PT_TRACE_MINBLOCKS 7  // 72 registers: 7 blocks/SM.  Measured (r02o, batched build): 6 blocks / 80 registers 944, 7 / 72 967 Mray/s (round 1: 5 -> 6 +4 %)
+#define B200PT_TRACE_MINBLOCKS 8  // 64 registers, no spills: 8 blocks/SM.  Measured: 6 blocks / 80 registers 944, 7 / 72 967 (r02o), 8 / 64 973 (r02q) and 990.8 vs 984.1 (r02x, same box, leaf cost 0.6)
+#endif
+// the production walk kernels tell step() their protocol at compile time (traverse.cuh); -DB200PT_RUNTIME_MODE keeps the runtime flags (A/B)
+#ifdef B200PT_RUNTIME_MODE
+#define B200PT_STEP_MODE(m) 0
+#else
+#define B200PT_STEP_MODE(m) (m)
 #endif
 enum : int
 {
@@ -291,7 +297,7 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_trace(PathState
       }
 #endif
       if(path >= 0 && !travDone)
-        travDone = T.step<SS, kCand, false, OMM>(stack, postponeShift, cand, cs, S.bvh.ommRef, S.bvh.ommData);
+        travDone = T.step<SS, kCand, false, OMM, B200PT_STEP_MODE(1)>(stack, postponeShift, cand, cs, S.bvh.ommRef, S.bvh.ommData);
       if(__popc(__ballot_sync(0xffffffffu, path >= 0 && !travDone)) < refillThreshold)
         break;
     }
@@ -1063,7 +1069,7 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_MINBLOCKS) k_shadow(PathStat
       }
 #endif
       if(path >= 0 && !travDone)
-        travDone = T.step<SS, kCand, false, OMM>(stack, postponeShift, cand, cs, S.bvhA.ommRef, S.bvhA.ommData);  // (only non-opaque triangles consult it: phase 1)
+        travDone = T.step<SS, kCand, false, OMM, B200PT_STEP_MODE(2)>(stack, postponeShift, cand, cs, S.bvhA.ommRef, S.bvhA.ommData);  // (only non-opaque triangles consult it: phase 1)
       if(__popc(__ballot_sync(0xffffffffu, path >= 0 && !travDone)) < refillThreshold)
         break;
     }
@@ -1406,6 +1412,22 @@ __global__ void __launch_bounds__(256) k_skin(SkinTaskDev T)
     skinVertex(T, v);
 }
 
+__global__ void __launch_bounds__(256) k_propagate_level(const float* __restrict__ local, float* world, const int* __restrict__ parents, const int* __restrict__ topo,
+                                                         uint32_t levelOffset, uint32_t levelCount)
+{
+  const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
+  if(ti < levelCount)
+    propagateNode(local, world, parents, topo, levelOffset, ti);
+}
+
+__global__ void __launch_bounds__(256) k_update_render_nodes(const float* __restrict__ world, const RenderNodeMapping* __restrict__ mappings,
+                                                             const float* __restrict__ instLocal, b200pt_render_node* out, uint32_t n)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n)
+    updateRenderNode(world, mappings, instLocal, out, i);
+}
+
 __global__ void __launch_bounds__(256) k_regather_shade(ShadeRec* recs, DevPrim P, uint32_t triCount)
 {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1632,6 +1654,13 @@ struct b200pt
   std::vector<uint32_t>     morphPrim, skinPrim;  // renderPrimID per task
   float *                   dMorphWeights = nullptr, *dJointMats = nullptr, *dNormalMats = nullptr;
   size_t                    numMorphWeights = 0, numJoints = 0;
+  // node hierarchy on the device (b200pt_set_node_hierarchy / b200pt_update_node_matrices)
+  std::vector<void*>        graphAllocs;
+  std::vector<uint32_t>     levelOffsets;
+  uint32_t                  numGraphNodes = 0;
+  int *                     dParents = nullptr, *dTopo = nullptr;
+  float *                   dLocalMats = nullptr, *dWorldMats = nullptr, *dInstLocal = nullptr;
+  RenderNodeMapping*        dMappings = nullptr;
 
   // env
   float4* dEnv = nullptr;
@@ -1915,9 +1944,22 @@ void freeAnimation(b200pt* h)
   h->numMorphWeights = h->numJoints = 0;
 }
 
+void freeHierarchy(b200pt* h)
+{
+  for(void* p : h->graphAllocs)
+    cudaFree(p);
+  h->graphAllocs.clear();
+  h->levelOffsets.clear();
+  h->numGraphNodes = 0;
+  h->dParents = h->dTopo = nullptr;
+  h->dLocalMats = h->dWorldMats = h->dInstLocal = nullptr;
+  h->dMappings = nullptr;
+}
+
 void freeScene(b200pt* h)
 {
   freeAnimation(h);
+  freeHierarchy(h);
   for(void* p : h->sceneAllocs)
     cudaFree(p);
   h->sceneAllocs.clear();
@@ -3132,6 +3174,109 @@ int b200pt_update_transforms(b200pt_t* h, const b200pt_render_node* nodes, uint3
   syncAll(h);
   cudaStream_t st = h->stream;
   CK(cudaMemcpyAsync(h->dNodesW, nodes, (size_t)num_nodes * sizeof(b200pt_render_node), cudaMemcpyHostToDevice, st));
+  return refitTrees(h);
+}
+
+int b200pt_set_node_hierarchy(b200pt_t* h, const b200pt_node_hierarchy* g)
+{
+  if(!h || !h->haveScene || !g || g->numNodes == 0 || g->numLevels == 0 || !g->parentIndices || !g->topoNodeOrder || !g->levelOffsets || !g->mappings)
+  {
+    if(h)
+      h->err = "b200pt_set_node_hierarchy: needs a scene and a complete hierarchy description";
+    return B200PT_E_INVALID;
+  }
+  CK(cudaSetDevice(h->device));
+  {
+    const int frc = flushPending(h);
+    if(frc)
+      return frc;
+  }
+  syncAll(h);
+  freeHierarchy(h);
+  auto fail = [&](const char* msg) {
+    freeHierarchy(h);
+    h->err = msg;
+    return B200PT_E_INVALID;
+  };
+  // every node exactly once, parents in earlier levels, offsets monotone and complete
+  if(g->levelOffsets[0] != 0 || g->levelOffsets[g->numLevels] != g->numNodes)
+    return fail("b200pt_set_node_hierarchy: levelOffsets must run from 0 to numNodes");
+  std::vector<int> levelOf(g->numNodes, -1);
+  for(uint32_t l = 0; l < g->numLevels; l++)
+  {
+    if(g->levelOffsets[l + 1] < g->levelOffsets[l] || g->levelOffsets[l + 1] > g->numNodes)
+      return fail("b200pt_set_node_hierarchy: levelOffsets must be monotone");
+    for(uint32_t k = g->levelOffsets[l]; k < g->levelOffsets[l + 1]; k++)
+    {
+      const int n = g->topoNodeOrder[k];
+      if(n < 0 || (uint32_t)n >= g->numNodes || levelOf[n] != -1)
+        return fail("b200pt_set_node_hierarchy: topoNodeOrder must list every node once");
+      levelOf[n] = (int)l;
+    }
+  }
+  for(uint32_t n = 0; n < g->numNodes; n++)
+  {
+    const int p = g->parentIndices[n];
+    if(p >= (int)g->numNodes || (p >= 0 && levelOf[p] >= levelOf[n]))
+      return fail("b200pt_set_node_hierarchy: a parent must sit in an earlier level than its child");
+  }
+  for(uint32_t i = 0; i < h->numSceneNodes; i++)
+  {
+    const b200pt_render_node_mapping& m = g->mappings[i];
+    if(m.nodeID < 0 || (uint32_t)m.nodeID >= g->numNodes || m.renderPrimID < 0 || (size_t)m.renderPrimID >= h->primHost.size() || m.materialID >= h->S.numMaterials)
+      return fail("b200pt_set_node_hierarchy: render-node mapping out of range");
+  }
+  int rc;
+  if((rc = upload(h, h->graphAllocs, g->parentIndices, g->numNodes, &h->dParents)))
+    return rc;
+  if((rc = upload(h, h->graphAllocs, g->topoNodeOrder, g->numNodes, &h->dTopo)))
+    return rc;
+  static_assert(sizeof(RenderNodeMapping) == sizeof(b200pt_render_node_mapping), "mapping layout");
+  if((rc = upload(h, h->graphAllocs, reinterpret_cast<const RenderNodeMapping*>(g->mappings), h->numSceneNodes, &h->dMappings)))
+    return rc;
+  if(g->instLocalMatrices && (rc = upload(h, h->graphAllocs, g->instLocalMatrices, (size_t)h->numSceneNodes * 16, &h->dInstLocal)))
+    return rc;
+  CK(cudaMalloc((void**)&h->dLocalMats, (size_t)g->numNodes * 16 * sizeof(float)));
+  h->graphAllocs.push_back(h->dLocalMats);
+  CK(cudaMalloc((void**)&h->dWorldMats, (size_t)g->numNodes * 16 * sizeof(float)));
+  h->graphAllocs.push_back(h->dWorldMats);
+  h->levelOffsets.assign(g->levelOffsets, g->levelOffsets + g->numLevels + 1);
+  h->numGraphNodes = g->numNodes;
+  CK(cudaStreamSynchronize(h->stream));
+  return B200PT_OK;
+}
+
+int b200pt_update_node_matrices(b200pt_t* h, const float* local_matrices)
+{
+  if(!h || !h->haveScene || h->numGraphNodes == 0 || !local_matrices)
+  {
+    if(h)
+      h->err = "b200pt_update_node_matrices: needs b200pt_set_node_hierarchy and the nodes' local matrices";
+    return B200PT_E_INVALID;
+  }
+  CK(cudaSetDevice(h->device));
+  {
+    const int frc = flushPending(h);
+    if(frc)
+      return frc;
+  }
+  syncAll(h);
+  cudaStream_t st = h->stream;
+  CK(cudaMemcpyAsync(h->dLocalMats, local_matrices, (size_t)h->numGraphNodes * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
+  for(size_t l = 0; l + 1 < h->levelOffsets.size(); l++)
+  {
+    const uint32_t count = h->levelOffsets[l + 1] - h->levelOffsets[l];
+    if(!count)
+      continue;
+    k_propagate_level<<<(count + 255) / 256, 256, 0, st>>>(h->dLocalMats, h->dWorldMats, h->dParents, h->dTopo, h->levelOffsets[l], count);
+    h->kernelLaunches++;
+  }
+  if(h->numSceneNodes)
+  {
+    k_update_render_nodes<<<(h->numSceneNodes + 255) / 256, 256, 0, st>>>(h->dWorldMats, h->dMappings, h->dInstLocal, h->dNodesW, h->numSceneNodes);
+    h->kernelLaunches++;
+  }
+  CK(cudaGetLastError());
   return refitTrees(h);
 }
 

@@ -245,7 +245,7 @@ void buildWideBvh(const std::vector<FlatTri>& tris, const std::vector<uint32_t>&
 
   // ---- SAH-optimal collapse: dynamic programme over the binary tree, children before parents -----------------
   // (children are always created after their parent, so a reverse sweep sees them first)
-  const float kCostNode = 1.0f, kCostPrim = getenv("BVH_CPRIM") ? (float)atof(getenv("BVH_CPRIM")) : 0.4f;  // one node step ~ 270 SASS instructions, one triangle test ~ 110
+  const float kCostNode = 1.0f, kCostPrim = getenv("BVH_CPRIM") ? (float)atof(getenv("BVH_CPRIM")) : 0.7f;  // one node step ~ 250 SASS instructions, one triangle test ~ 125, but at fewer lanes (ncu r02c): measured on the bench scene (r02x, one box) 0.4 -> 970.9 / 976.4, 0.5 -> 982.1, 0.6 -> 984.1, 0.7 -> 986.1 Mray/s (17.39 / 12.41 -> 18.03 / 11.12 nodes / triangle tests per ray)
   const float invRootArea = 1.0f / std::max(B.n2[0].box.halfArea(), 1e-30f);
   for(size_t ni = B.n2.size(); ni-- > 0;)
   {

@@ -3,7 +3,10 @@
 // written back for a bit-for-bit comparison with oracle/animation.py.
 //   host_animate_check task.bin out.bin
 // task.bin: u32 kind (0 morph, 1 skin), V, K (targets / joints), hasN, hasT, hasDN, hasDT, then the float arrays in the order of
-// MorphTaskDev / SkinTaskDev (joints as int32).
+// MorphTaskDev / SkinTaskDev (joints as int32).  kind 2 = the rigid part (propagateNode level by level, then updateRenderNode):
+// V = graph nodes, K = render nodes, hasN = levels, hasT = instance matrices present; arrays: parents i32[V], topo i32[V],
+// level offsets u32[levels + 1], mappings 4 x i32 [K], local f32[V x 16], instLocal f32[K x 16]?; out.bin: world f32[V x 16], then K
+// b200pt_render_node records.
 #include "host_shim.h"
 
 #include <cstdio>
@@ -36,6 +39,29 @@ int main(int argc, char** argv)
   const std::vector<uint32_t> hd = rd<uint32_t>(f, 7);
   const uint32_t kind = hd[0], V = hd[1], K = hd[2];
   const bool     hasN = hd[3], hasT = hd[4], hasDN = hd[5], hasDT = hd[6];
+  if(kind == 2)
+  {
+    const uint32_t              levels = hd[3];
+    const std::vector<int>      parents = rd<int>(f, V), topo = rd<int>(f, V);
+    const std::vector<uint32_t> ofs = rd<uint32_t>(f, levels + 1);
+    const std::vector<RenderNodeMapping> maps = rd<RenderNodeMapping>(f, K);
+    const std::vector<float>    local = rd<float>(f, (size_t)V * 16), inst = rd<float>(f, hd[4] ? (size_t)K * 16 : 0);
+    std::fclose(f);
+    std::vector<float>              world((size_t)V * 16, 0.f);
+    std::vector<b200pt_render_node> nodes(K);
+    for(uint32_t l = 0; l < levels; l++)
+      for(uint32_t ti = 0; ti < ofs[l + 1] - ofs[l]; ti++)
+        propagateNode(local.data(), world.data(), parents.data(), topo.data(), ofs[l], ti);
+    for(uint32_t i = 0; i < K; i++)
+      updateRenderNode(world.data(), maps.data(), hd[4] ? inst.data() : nullptr, nodes.data(), i);
+    FILE* o = std::fopen(argv[2], "wb");
+    if(!o)
+      return 2;
+    std::fwrite(world.data(), 4, world.size(), o);
+    std::fwrite(nodes.data(), sizeof(b200pt_render_node), nodes.size(), o);
+    std::fclose(o);
+    return 0;
+  }
   std::vector<float> outP((size_t)V * 3), outN((size_t)V * 3), outT((size_t)V * 4);
   const std::vector<float> bp = rd<float>(f, (size_t)V * 3), bn = rd<float>(f, hasN ? (size_t)V * 3 : 0), bt = rd<float>(f, hasT ? (size_t)V * 4 : 0);
   if(kind == 0)

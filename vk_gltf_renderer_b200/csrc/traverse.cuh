@@ -223,10 +223,16 @@ struct TravState
   // cand[i * cs]: the kernels keep it in shared memory, one column per thread).
   // FORCE_OPAQUE: every triangle counts as opaque (IRaytracer::TraceLow, RAY_FLAG_FORCE_OPAQUE: the selection ray)
   // OMM: the scene carries opacity micromaps (a separate instantiation, so that scenes without them run the walk without the lookup)
-  template <int SS = 1, int KC = kCand, bool FORCE_OPAQUE = false, bool OMM = false>
+  // MODE: the walk's protocol as a compile-time constant where the caller knows it (0 = the runtime flags of init(); 1 = closest-hit
+  // walk: not a shadow query, back faces culled, the bound shrinks; 2 = shadow walk: shadow query, no culling) -- the per-triangle
+  // flag tests and the shadow / closest branches fold away
+  template <int SS = 1, int KC = kCand, bool FORCE_OPAQUE = false, bool OMM = false, int MODE = 0>
   PT_D bool step(uint2* __restrict__ stack, int postponeShift, Cand* __restrict__ cand, int cs, const uint32_t* __restrict__ ommRef = nullptr,
                  const uint8_t* __restrict__ ommData = nullptr)
   {
+    const bool shadow = MODE == 1 ? false : (MODE == 2 ? true : this->shadow);
+    const bool cull = MODE == 1 ? true : (MODE == 2 ? false : this->cull);
+    const bool shrink = MODE == 1 ? true : this->shrink;
     // single exit: an early return inside the divergent regions would move their reconvergence point out of the
     // caller's loop and the lanes of a warp would drift apart (measured: 8 of 32 lanes active)
     bool done = false;

@@ -173,6 +173,26 @@ class PathTracer:
         w, jm, nm = cat(morph_weights, 1), cat(joint_matrices, 16), cat(normal_matrices, 9)
         self._ck(self._L.b200pt_animate(self._h, w.ctypes.data_as(C.c_void_p), jm.ctypes.data_as(C.c_void_p), nm.ctypes.data_as(C.c_void_p)), "b200pt_animate")
 
+    def set_node_hierarchy(self, parents, mappings, inst_local=None):
+        """b200pt_set_node_hierarchy: parents[numNodes] (-1 = root); the BFS levels are derived here the way the reference's
+        createGpuBuffers does for its one-dispatch-per-level propagation; mappings: (nodeID, materialID, renderPrimID) per render
+        node; inst_local: optional [numRenderNodes, 4, 4] glm-ordered instance matrices."""
+        from .animation import topo_levels
+        parents = np.ascontiguousarray(parents, np.int32)
+        order, offsets = topo_levels(parents)
+        mp = (abi.RenderNodeMapping * max(len(mappings), 1))()
+        for i, (node, mat, prim) in enumerate(mappings):
+            mp[i].nodeID, mp[i].pad0, mp[i].materialID, mp[i].renderPrimID = node, 0, mat, prim
+        il = None if inst_local is None else np.ascontiguousarray(inst_local, np.float32)
+        g = abi.NodeHierarchy(len(parents), len(offsets) - 1, parents.ctypes.data_as(C.POINTER(C.c_int32)), order.ctypes.data_as(C.POINTER(C.c_int32)),
+                              abi.u32ptr(offsets), mp, abi.fptr(il))
+        self._ck(self._L.b200pt_set_node_hierarchy(self._h, C.byref(g)), "b200pt_set_node_hierarchy")
+
+    def update_node_matrices(self, local_matrices):
+        """b200pt_update_node_matrices: [numNodes, 4, 4] glm-ordered local matrices -> world matrices, render nodes and trees on the device"""
+        lm = np.ascontiguousarray(local_matrices, np.float32)
+        self._ck(self._L.b200pt_update_node_matrices(self._h, lm.ctypes.data_as(C.c_void_p)), "b200pt_update_node_matrices")
+
     def setEnvironment(self, rgb):
         rgb = np.ascontiguousarray(rgb, np.float32)
         integral = C.c_float()

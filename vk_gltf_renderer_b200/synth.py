@@ -631,6 +631,35 @@ def synth_animated(seed=1234, tex_size=64):
     return scn, [morph_blob, morph_flag], [skin_arm, skin_flag], pose
 
 
+def synth_hierarchy(seed=1234):
+    """A scene graph for the device-side rigid feed (b200pt_set_node_hierarchy / b200pt_update_node_matrices;
+    shaders/world_matrix_propagate.comp.slang, update_render_instances.comp.slang): the lit test scene's four render nodes hang
+    in a four-level hierarchy (root -> turntable -> arm -> hand, plus a sibling chain listed child-before-parent so that the BFS
+    order is not the index order), one render node carries an instance matrix.  Returns (scene, parents, mappings, inst_local,
+    pose) with pose(k) -> local matrices [numNodes, 4, 4] (mathematical)."""
+    scn = synth_lit(seed)
+    #           0 root  1 turntable  2 arm  3 hand  4 leaf-of-5  5 under root   6 unused
+    parents = [-1, 0, 1, 2, 5, 0, -1]
+    # render nodes: ground, sphere 0, 1, 2  ->  graph nodes
+    graph_of = [0, 3, 4, 2]
+    mappings = [(graph_of[i], rn["materialID"], rn["renderPrimID"]) for i, rn in enumerate(scn.render_nodes)]
+    inst = np.stack([np.eye(4)] * len(scn.render_nodes))
+    inst[2] = np.array([[0.9, 0, 0.1, 0.2], [0, 1.1, 0, 0.1], [-0.1, 0, 0.9, -0.3], [0, 0, 0, 1.0]])
+
+    def pose(k):
+        a = [0.0, 0.6, -1.1][k % 3]
+        c, s_ = math.cos(a), math.sin(a)
+        ry = np.array([[c, 0, s_, 0], [0, 1, 0, 0], [-s_, 0, c, 0], [0, 0, 0, 1.0]])
+        def tr(x, y, z):
+            m = np.eye(4)
+            m[:3, 3] = [x, y, z]
+            return m
+        loc = [np.eye(4), ry @ tr(0.2 * k, 0, 0), tr(0.5, 0.1 * k, 0) @ np.diag([1.0, 1.0 + 0.2 * k, 1.0, 1.0]), tr(-0.3, 0.2, 0.4) @ ry,
+               np.diag([-1.0, 1.0, 1.0, 1.0]) @ tr(0.3 * k, 0, 0), tr(0, 0.15 * k, -0.5) @ ry.T, tr(9, 9, 9)]
+        return np.asarray(loc, np.float64)
+    return scn, np.asarray(parents, np.int32), mappings, inst, pose
+
+
 def triangle_soup(n, seed=1234, extent=1.0, size=0.15):
     """n random triangles in a cube: stress input for traversal parity tests."""
     rng = np.random.default_rng(seed)
