@@ -326,7 +326,8 @@ def main():
     lanes = 4
     # measured at N = 1 (r02m, frames in flight 4): batch 1 -> 821 (r02g), 4 -> 926, 6 -> 949, 8 -> 947 Mray/s.  The batch grows with N so
     # that a rank's wavefront stays as large as on one GPU, but never beyond half the timed steps (two wavefronts overlap their tails)
-    batch = max(1, min(8 * world, 64, (args.steps + 1) // 2))
+    # (r02y / r02z, --steps 20: two equal wavefronts of 10 frames 987 / 994 Mray/s against 8 + 8 + 4 at 981 / 988)
+    batch = max(1, min(8 * world if world > 1 else 16, 64, (args.steps + 1) // 2))
     if os.environ.get("B200PT_FRAMES_IN_FLIGHT"):
         lanes = int(os.environ["B200PT_FRAMES_IN_FLIGHT"])
     if os.environ.get("B200PT_FRAME_BATCH"):

@@ -466,6 +466,17 @@ int b200pt_read_accum(b200pt_t* h, float* host_rgba32f, size_t num_floats);
 int b200pt_read_selection(b200pt_t* h, uint32_t* host_object_ids, float* host_ndc_depth, size_t num_pixels);
 int b200pt_get_selection_device(b200pt_t* h, uint32_t** dev_object_ids, float** dev_ndc_depth);
 
+/* Denoiser guide image (OutputImage::eOptixAlbedoNormal, shaders/gltf_pathtrace.slang:240-263, 653-670; the buffer
+ * OptiXDenoiser::eGBufferAlbedoNormal of src/renderer_pathtracer.cpp:698): per pixel float4(guide albedo.rgb, asfloat(normal)) of
+ * the newest sample's first hit -- base colour as the reference's float16_t guide fields hold it, the shading normal taken to
+ * camera space by mul(float3x3(viewMatrix), N), normalised and compressed to 32 bits (nvshaders' compressUnitVec: octahedral,
+ * 2 x 16 bits; restated, external); (0, 0, 1) where the primary ray missed.  Written by every frame whose push constants carry
+ * B200PT_PT_USE_OPTIX_DENOISER, which requires b200pt_set_guide_outputs(h, 1) (the path pools grow by 32 bytes per slot; calling it
+ * re-allocates them like b200pt_resize).  The DLSS variant (its extra guides, frame jitter, motion vectors) is not built. */
+int b200pt_set_guide_outputs(b200pt_t* h, int enable);
+int b200pt_read_guide(b200pt_t* h, float* host_albedo_normal, size_t num_floats);
+int b200pt_get_guide_device(b200pt_t* h, float** dev_albedo_normal, size_t* num_floats);
+
 /* Tone mapping + 8-bit encode of the accumulation image: what GltfRenderer::tonemap does to gBuffers[eImgRendered] before
  * saveHeadlessOutputImage writes gBuffers[eImgTonemapped] (src/renderer.cpp:992-1054, 557-573).  The compute shader is
  * nvshaders::Tonemapper (nvpro_core2, external to the reference tree): the struct mirrors the controls the reference's UI and

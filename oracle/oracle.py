@@ -38,6 +38,7 @@ def lib():
         L.oracle_get_environment.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_render_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.oracle_render_frame_aux.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.oracle_render_frame_guide.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.oracle_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.oracle_trace_shadow.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.oracle_trace_closest_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
@@ -104,12 +105,13 @@ class Oracle:
         self.L.oracle_get_environment(self.h, _p(rgba), _p(alias), _p(q))
         return rgba, alias, q
 
-    def render_frame(self, fi, pc, accum, y0=0, rows=None, threads=None, object_id=None, ndc_depth=None):
+    def render_frame(self, fi, pc, accum, y0=0, rows=None, threads=None, object_id=None, ndc_depth=None, guide=None):
         """accum: float32 [rows, W, 4], updated in place (running mean like processPixel).  object_id (uint32 [rows, W]) /
-        ndc_depth (float32 [rows, W]), if given, receive the frame-0 outputs (selection ray id, NDC depth of the first hit)."""
+        ndc_depth (float32 [rows, W]), if given, receive the frame-0 outputs (selection ray id, NDC depth of the first hit);
+        guide (float32 [rows, W, 4]) the eOptixAlbedoNormal image of a frame whose push constants carry ePtUseOptixDenoiser."""
         rows = accum.shape[0] if rows is None else rows
         threads = threads or os.cpu_count() or 1
-        rc = self.L.oracle_render_frame_aux(self.h, C.byref(fi), C.byref(pc), _p(accum), _p(object_id), _p(ndc_depth), y0, rows, threads)
+        rc = self.L.oracle_render_frame_guide(self.h, C.byref(fi), C.byref(pc), _p(accum), _p(object_id), _p(ndc_depth), _p(guide), y0, rows, threads)
         if rc:
             raise RuntimeError(f"oracle_render_frame failed: {rc}")
 

@@ -1591,9 +1591,13 @@ static VolumeMedium makeVolumeMedium(const PbrMaterial& m)
 }
 static bool hasVolumeMedium(const VolumeMedium& v) { return maxc(v.extinction) > 0.0f || maxc(v.scatterCoefficient) > 0.0f; }
 
+// value of x after a round trip through IEEE binary16 (round to nearest even): the reference's float16_t guide fields
+static inline float half16(float x) { return (float)(_Float16)x; }
+
 struct PathTracerState
 {
   float3       radiance = f3(0.0f), throughput = f3(1.0f), firstHitPos = f3(1e34f);
+  float3       guideAlbedo = f3(0.0f), guideNormal = f3(0.0f);  // GuideScratch (pathtrace_functions.h.slang:79-88): float16_t fields, default 0
   float        lastSamplePdf = DIRAC;
   float2       maxRoughness = f2(0.0f, 0.0f);
   bool         solid = true;
@@ -1810,7 +1814,13 @@ static PathStepResult pathTraceOneBounce(const Ctx& c, Ray& ray, uint32_t& seed,
   }
 
   if(firstRay)
+  {
     pt.firstHitPos = hit.pos;
+    // USE_GUIDE_SHADER (gltf_pathtrace.slang:240-263, without the DLSS-only specular guides): base colour and shading normal of
+    // the first hit, stored as float16_t by the reference
+    pt.guideAlbedo = f3(half16(pbrMat.baseColor.x), half16(pbrMat.baseColor.y), half16(pbrMat.baseColor.z));
+    pt.guideNormal = f3(half16(pbrMat.N.x), half16(pbrMat.N.y), half16(pbrMat.N.z));
+  }
 
   pt.maxRoughness = f2(fmaxf(pbrMat.roughness.x, pt.maxRoughness.x), fmaxf(pbrMat.roughness.y, pt.maxRoughness.y));
   pbrMat.roughness = pt.maxRoughness;
@@ -1897,6 +1907,7 @@ struct SampleResult
 {
   float4 radiance;
   float3 hitPosition;
+  float3 guideAlbedo, guideNormal;  // SampleResult::guideOutput (pathtrace_functions.h.slang:94-102)
 };
 
 static SampleResult pathTrace(const Ctx& c, Ray ray, uint32_t& seed)
@@ -1937,6 +1948,8 @@ static SampleResult pathTrace(const Ctx& c, Ray ray, uint32_t& seed)
   SampleResult r;
   r.radiance = f4(pt.radiance, pt.solid ? 1.0f : 0.0f);
   r.hitPosition = pt.firstHitPos;
+  r.guideAlbedo = pt.guideAlbedo;
+  r.guideNormal = pt.guideNormal;
   return r;
 }
 
@@ -2006,7 +2019,25 @@ static int traceLowObjectId(Oracle& o, const Ray& ray)
   return (int)o.tris[h.tri].rnode + 1;
 }
 
-static void processPixel(const Ctx& c, int x, int y, float* px, uint32_t* objectId = nullptr, float* ndcDepth = nullptr)
+// nvshaders' compressUnitVec (external): octahedral 2 x 16-bit encoding (Engelhardt & Dachsbacher 2008), restated
+static uint32_t compressUnitVec(float3 nv)
+{
+  if(!(fabsf(nv.x) < 3.0e38f))
+    return ~0u;
+  const float d = 32767.0f / (fabsf(nv.x) + fabsf(nv.y) + fabsf(nv.z));
+  int         x = (int)roundf(nv.x * d), y = (int)roundf(nv.y * d);
+  if(nv.z < 0.0f)
+  {
+    const int maskx = x >> 31, masky = y >> 31;
+    const int tmp = 32767 + maskx + masky, tmpx = x;
+    x = (tmp - (y ^ masky)) ^ maskx;
+    y = (tmp - (tmpx ^ maskx)) ^ masky;
+  }
+  const uint32_t packed = ((uint32_t)(y + 32767) << 16) | (uint32_t)(x + 32767);
+  return packed == ~0u ? ~1u : packed;
+}
+
+static void processPixel(const Ctx& c, int x, int y, float* px, uint32_t* objectId = nullptr, float* ndcDepth = nullptr, float* guide = nullptr)
 {
   const float2 imageSize = f2(c.fi->imageSize[0], c.fi->imageSize[1]);
   const float2 samplePos = f2((float)x, (float)y);
@@ -2049,6 +2080,23 @@ static void processPixel(const Ctx& c, int x, int y, float* px, uint32_t* object
       const Ray  ray = getRay(samplePos, f2(0.5f, 0.5f), imageSize, *(const mat4*)c.fi->projInv, *(const mat4*)c.fi->viewInv, ortho);
       *objectId = (uint32_t)traceLowObjectId(*c.o, ray);
     }
+  }
+  if(guide && (c.pc->flags & B200PT_PT_USE_OPTIX_DENOISER))
+  {
+    // gltf_pathtrace.slang:653-670: eOptixAlbedoNormal = (guide albedo of the LAST sample, compressed camera-space normal);
+    // mul(float3x3(viewMatrix), n) on the glm bytes is M_glm^T * n (convention note)
+    float3 camN = f3(0.0f, 0.0f, 1.0f);
+    if(sr.radiance.w > 0.0f)
+    {
+      const float* m = c.fi->viewMatrix;
+      const float3 n = sr.guideNormal;
+      camN = normalize(f3((m[0] * n.x + m[1] * n.y) + m[2] * n.z, (m[4] * n.x + m[5] * n.y) + m[6] * n.z, (m[8] * n.x + m[9] * n.y) + m[10] * n.z));
+    }
+    const uint32_t packed = compressUnitVec(camN);
+    guide[0] = sr.guideAlbedo.x;
+    guide[1] = sr.guideAlbedo.y;
+    guide[2] = sr.guideAlbedo.z;
+    memcpy(&guide[3], &packed, 4);
   }
   if(firstFrame)
   {
@@ -2238,9 +2286,18 @@ int oracle_render_frame(void* h, const b200pt_frame_info* fi, const b200pt_push_
   return oracle_render_frame_aux(h, fi, pc, accum, nullptr, nullptr, y0, rows, nthreads);
 }
 
+int oracle_render_frame_guide(void* h, const b200pt_frame_info* fi, const b200pt_push_constant* pc, float* accum, uint32_t* objectId, float* ndcDepth, float* guide,
+                              int y0, int rows, int nthreads);
 // objectId / ndcDepth (rows x width, tile-local, may be null): the frame-0 outputs of processPixel
 int oracle_render_frame_aux(void* h, const b200pt_frame_info* fi, const b200pt_push_constant* pc, float* accum, uint32_t* objectId, float* ndcDepth, int y0, int rows,
                             int nthreads)
+{
+  return oracle_render_frame_guide(h, fi, pc, accum, objectId, ndcDepth, nullptr, y0, rows, nthreads);
+}
+
+// guide (rows x width x 4 floats, may be null): OutputImage::eOptixAlbedoNormal, written when pc carries B200PT_PT_USE_OPTIX_DENOISER
+int oracle_render_frame_guide(void* h, const b200pt_frame_info* fi, const b200pt_push_constant* pc, float* accum, uint32_t* objectId, float* ndcDepth, float* guide,
+                              int y0, int rows, int nthreads)
 {
   Oracle& o = *(Oracle*)h;
   if(!(fi->flags & B200PT_SCENE_USE_HDR_ENVIRONMENT) || o.envW == 0)
@@ -2259,7 +2316,8 @@ int oracle_render_frame_aux(void* h, const b200pt_frame_info* fi, const b200pt_p
       if(r >= rows)
         break;
       for(int x = 0; x < W; x++)
-        processPixel(c, x, y0 + r, accum + ((size_t)r * W + x) * 4, objectId ? objectId + (size_t)r * W + x : nullptr, ndcDepth ? ndcDepth + (size_t)r * W + x : nullptr);
+        processPixel(c, x, y0 + r, accum + ((size_t)r * W + x) * 4, objectId ? objectId + (size_t)r * W + x : nullptr, ndcDepth ? ndcDepth + (size_t)r * W + x : nullptr,
+                     guide ? guide + ((size_t)r * W + x) * 4 : nullptr);
     }
     o.stats.merge();
   };

@@ -73,5 +73,5 @@ def test_headless_driver_writes_the_tonemapped_image(tmp_path):
         got = np.frombuffer(f.read(), np.uint8).reshape(64, 96, 3)
     ref, ex = T.tonemap(img, method=0, auto=1)
     line = [l for l in out.stdout.splitlines() if l.startswith("HEADLESS_OUTPUT")][0]
-    assert abs(float(line.split("exposure=")[1]) / float(ex) - 1.0) < 1e-4
+    assert abs(float(line.split(" exposure=")[1]) / float(ex) - 1.0) < 1e-4
     assert _close(got, ref[..., :3])

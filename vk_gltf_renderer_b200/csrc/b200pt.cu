@@ -111,6 +111,11 @@ __device__ void startSample(const PathState& P, const FrameParams& F, uint32_t i
   P.medium[i] = make_uint4(0u, 0u, 0u, sampleIdx << 16);
   if(isFirstFrame(F, i))
     P.firstHit[i] = f4(1e34f, 1e34f, 1e34f, 1.0f);  // PathTracerState::firstHitPos sentinel, pt.solid = true
+  if(P.guideA)
+  {
+    P.guideA[i] = f4(0.f, 0.f, 0.f, 0.f);  // GuideScratch defaults: albedo 0, normalRoughness 0
+    P.guideN[i] = f4(0.f, 0.f, 0.f, 0.f);
+  }
 }
 
 // end of one samplePixel(): firefly clamp, add to the pixel sum, start the pixel's next sample if any
@@ -711,6 +716,15 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
     // first-hit capture for the NDC depth output of frame 0 (gltf_pathtrace.slang:228-232)
     if(depth == 0 && isFirstFrame(F, i))
       P.firstHit[i] = f4(hit.pos, 1.0f);
+    // denoiser guides of the first hit (gltf_pathtrace.slang:240-263, the USE_GUIDE_SHADER part without the DLSS-only specular guides):
+    // base colour and shading normal / roughness, stored as float16_t by the reference.  (maxRoughness is still 0 at depth 0, so the
+    // clamp above left pbrMat.roughness as evaluateMaterial returned it.)
+    if(depth == 0 && P.guideA && (F.pc.flags & B200PT_PT_USE_OPTIX_DENOISER))
+    {
+      auto h16 = [](float x) { return __half2float(__float2half_rn(x)); };
+      P.guideA[i] = f4(h16(pbrMat.baseColor.x), h16(pbrMat.baseColor.y), h16(pbrMat.baseColor.z), h16(pbrMat.roughness.x));
+      P.guideN[i] = f4(h16(pbrMat.N.x), h16(pbrMat.N.y), h16(pbrMat.N.z), 1.0f);
+    }
 
     radiance += pbrMat.emissive * throughput;
 
@@ -1254,6 +1268,44 @@ __global__ void __launch_bounds__(256) k_accumulate(PathState P, const __grid_co
   }
 }
 
+// OutputImage::eOptixAlbedoNormal (gltf_pathtrace.slang:653-670): per pixel the LAST sample's guide albedo and its shading normal in
+// camera space, compressed to 32 bits.  compressUnitVec is nvshaders code (external): restated as the octahedral 2 x 16-bit encoding it
+// implements (Engelhardt & Dachsbacher 2008): project onto |x| + |y| + |z| = 1, fold the lower hemisphere, 16 bits per axis.
+PT_HD uint32_t compressUnitVec(float3 nv)
+{
+  if(!(fabsf(nv.x) < 3.0e38f))  // NaN / infinity
+    return ~0u;
+  const float d = 32767.0f / (fabsf(nv.x) + fabsf(nv.y) + fabsf(nv.z));
+  int         x = (int)roundf(nv.x * d), y = (int)roundf(nv.y * d);
+  if(nv.z < 0.0f)
+  {
+    const int maskx = x >> 31, masky = y >> 31;
+    const int tmp = 32767 + maskx + masky, tmpx = x;
+    x = (tmp - (y ^ masky)) ^ maskx;
+    y = (tmp - (tmpx ^ maskx)) ^ masky;
+  }
+  const uint32_t packed = ((uint32_t)(y + 32767) << 16) | (uint32_t)(x + 32767);
+  return packed == ~0u ? ~1u : packed;
+}
+
+__global__ void __launch_bounds__(256) k_guide(PathState P, const __grid_constant__ FrameParams F, float4* __restrict__ guide)
+{
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < F.pixels; i += stride)
+  {
+    const uint32_t slot = i + (uint32_t)(F.batch - 1) * F.pixels;  // the newest frame of the batch
+    const float4   a = P.guideA[slot], n = P.guideN[slot];
+    float3         camN = f3(0.0f, 0.0f, 1.0f);  // primary miss: a valid forward-facing normal (:658-660)
+    if(n.w > 0.0f)
+    {
+      // mul(float3x3(viewMatrix), worldNormal) on the glm bytes (convention note): M_glm^T * n
+      const float* m = F.fi.viewMatrix;
+      camN = normalize(f3((m[0] * n.x + m[1] * n.y) + m[2] * n.z, (m[4] * n.x + m[5] * n.y) + m[6] * n.z, (m[8] * n.x + m[9] * n.y) + m[10] * n.z));
+    }
+    guide[i] = f4(a.x, a.y, a.z, __uint_as_float(compressUnitVec(camN)));
+  }
+}
+
 // traceSelectionRay (pathtrace_functions.h.slang:813-820) for every pixel of the first frame: the pixel-centre ray
 // (no jitter, no depth of field), IRaytracer::TraceLow semantics (raytracer_interface.h.slang:124-137: every triangle
 // opaque, no culling), object id = render node + 1, 0 on a miss.  One walk per thread; runs once per accumulation.
@@ -1673,6 +1725,8 @@ struct b200pt
   uint32_t           numPaths = 0;
   float4*            dAccumOwned = nullptr;
   float4*            dAccum = nullptr;
+  bool               guides = false;      // b200pt_set_guide_outputs: the path pools carry guideA / guideN, dGuide is the eOptixAlbedoNormal image
+  float4*            dGuide = nullptr;
   uchar4*            dTonemapped = nullptr;  // gBuffers[eImgTonemapped] of this tile (b200pt_tonemap), in poolAllocs
   uint32_t*          dTmHist = nullptr;      // 256-bin log2-luminance histogram + the exposure factor behind it (allocated with the handle)
   uint32_t*          dSelect = nullptr;  // frame-0 outputs (gltf_pathtrace.slang:610-616): object id per pixel ...
@@ -1803,6 +1857,19 @@ int allocPathState(b200pt* h, std::vector<void*>& owner, size_t n, PathState& P)
   }
   owner.push_back(d);
   P.candInfo = reinterpret_cast<uint2*>(d);
+  if(h->guides)
+    for(float4** a : {&P.guideA, &P.guideN})
+    {
+      void* g = nullptr;
+      if(cudaMalloc(&g, std::max<size_t>(n, 1) * 16) != cudaSuccess)
+      {
+        cudaGetLastError();
+        h->err = "path pool: out of device memory";
+        return B200PT_E_NOMEM;
+      }
+      owner.push_back(g);
+      *a = reinterpret_cast<float4*>(g);
+    }
   return B200PT_OK;
 }
 
@@ -1989,6 +2056,7 @@ void freePool(b200pt* h)
   h->dSelect = nullptr;
   h->dNdcDepth = nullptr;
   h->dTonemapped = nullptr;
+  h->dGuide = nullptr;
   h->numPaths = 0;
   for(int l = 0; l < b200pt::kMaxLanes; l++)
   {
@@ -3635,6 +3703,19 @@ int b200pt_resize(b200pt_t* h, int width, int height, int tile_y0, int tile_rows
     return fail(B200PT_E_NOMEM);
   }
   h->poolAllocs.push_back(h->dNdcDepth);
+  if(h->guides)
+  {
+    if(cudaMalloc((void**)&h->dGuide, n * 16) != cudaSuccess)
+    {
+      cudaGetLastError();
+      h->dGuide = nullptr;
+      h->err = "guide image: out of device memory";
+      return fail(B200PT_E_NOMEM);
+    }
+    h->poolAllocs.push_back(h->dGuide);
+    if(cudaMemsetAsync(h->dGuide, 0, n * 16, h->stream) != cudaSuccess)
+      return fail(B200PT_E_CUDA);
+  }
   if(cudaMalloc((void**)&h->dTonemapped, n * 4) != cudaSuccess)
   {
     cudaGetLastError();
@@ -3877,6 +3958,57 @@ int b200pt_set_frames_in_flight(b200pt_t* h, int n)
   return rc;
 }
 
+int b200pt_set_guide_outputs(b200pt_t* h, int enable)
+{
+  if(!h)
+    return B200PT_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  {
+    const int frc = flushPending(h);
+    if(frc)
+      return frc;
+  }
+  if((enable != 0) == h->guides)
+    return B200PT_OK;
+  h->guides = enable != 0;
+  if(h->numPaths == 0)
+    return B200PT_OK;
+  float4* const user = (h->dAccum != h->dAccumOwned) ? h->dAccum : nullptr;
+  int           rc;
+  if(h->bandWorld > 1)
+    rc = b200pt_resize_interleaved(h, h->width, h->height, h->bandRows, h->bandWorld, h->bandRank);
+  else
+    rc = b200pt_resize(h, h->width, h->height, h->tileY0, h->tileRows);
+  if(rc == B200PT_OK && user)
+    h->dAccum = user;
+  return rc;
+}
+
+int b200pt_read_guide(b200pt_t* h, float* host_albedo_normal, size_t num_floats)
+{
+  if(!h || h->numPaths == 0 || !h->dGuide || !host_albedo_normal || num_floats < (size_t)h->numPaths * 4)
+    return B200PT_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  {
+    const int frc = flushPending(h);
+    if(frc)
+      return frc;
+  }
+  CK(cudaMemcpyAsync(host_albedo_normal, h->dGuide, (size_t)h->numPaths * 16, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return B200PT_OK;
+}
+
+int b200pt_get_guide_device(b200pt_t* h, float** dev_albedo_normal, size_t* num_floats)
+{
+  if(!h || h->numPaths == 0 || !h->dGuide || !dev_albedo_normal)
+    return B200PT_E_INVALID;
+  *dev_albedo_normal = reinterpret_cast<float*>(h->dGuide);
+  if(num_floats)
+    *num_floats = (size_t)h->numPaths * 4;
+  return B200PT_OK;
+}
+
 int b200pt_set_frame_batch(b200pt_t* h, int n)
 {
   if(!h || n < 1 || n > 64)
@@ -3960,10 +4092,15 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
     h->err = "b200pt_render_frame: the shadow-catcher mode of the infinite plane is not built (handleShadowCatcher needs nvshaders' bsdfSampleSimple)";
     return B200PT_E_UNSUPPORTED;
   }
-  if(pc->flags & (B200PT_PT_USE_DLSS | B200PT_PT_USE_OPTIX_DENOISER))
+  if(pc->flags & B200PT_PT_USE_DLSS)
   {
-    h->err = "b200pt_render_frame: denoiser guide variants are out of scope";
+    h->err = "b200pt_render_frame: the DLSS variant (frame jitter, motion vectors, specular guides) is out of scope";
     return B200PT_E_UNSUPPORTED;
+  }
+  if((pc->flags & B200PT_PT_USE_OPTIX_DENOISER) && !h->guides)
+  {
+    h->err = "b200pt_render_frame: ePtUseOptixDenoiser needs the guide image (b200pt_set_guide_outputs(h, 1) first)";
+    return B200PT_E_INVALID;
   }
   if(pc->numSamples < 1 || pc->maxDepth < 0 || (int)fi->imageSize[0] != h->width || (int)fi->imageSize[1] != h->height)
   {
@@ -4180,6 +4317,8 @@ static int launchFrames(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
   if(pc->flags & B200PT_PT_FIRST_FRAME)
     timed(tOther, [&] { k_select<<<gridFor(h, 8), 128, 0, st>>>(h->S, F, h->dSelect, h->dStats); });
   timed(tOther, [&] { k_accumulate<<<gridWide, 256, 0, st>>>(L.P, F, h->dAccum, h->dNdcDepth); });
+  if((pc->flags & B200PT_PT_USE_OPTIX_DENOISER) && h->dGuide)
+    timed(tOther, [&] { k_guide<<<gridWide, 256, 0, st>>>(L.P, F, h->dGuide); });
   CK(cudaEventRecord(L.freed, st));
   L.busy = true;
   h->lastLane = laneIdx;

@@ -156,6 +156,10 @@ struct PathState
   // dense alpha / resolve kernels
   float4*   cand[B200PT_KCAND];
   uint2*    candInfo;  // x: count (bit 31: an opaque occluder ended the shadow query) | y: global id of the last candidate
+  // denoiser guides of the sample's first hit (GuideScratch, pathtrace_functions.h.slang:79-88; null unless b200pt_set_guide_outputs):
+  // albedo.xyz | roughness and normal.xyz | 1 (0: the primary ray missed), every value rounded through fp16 like the reference's float16_t fields
+  float4*   guideA;
+  float4*   guideN;
 };
 
 // flags word in misc.z

@@ -73,6 +73,9 @@ class PathTracer:
         # interactive use and its benchmark harness passes --ptAdaptiveSampling 0; this mirror defaults to OFF so that a
         # frame's sample count never depends on timing unless asked for.
         self.ptAdaptiveSampling = False
+        # OptiX-style guide image (albedo + camera-space normal of the first hit): set_guide_outputs(True) allocates it, every frame then
+        # carries ePtUseOptixDenoiser (reference: the flag follows the denoiser selection, src/renderer_pathtracer.cpp:1547)
+        self.ptUseOptixDenoiser = False
         self.ptPerformanceTarget = 1  # 0 interactive (60 FPS), 1 balanced (30), 2 quality (15), 3 max quality (10)
         self.last_frame_gpu_ms = None  # GPU time of the previous frame's path-trace section (the reference reads its profiler)
 
@@ -254,6 +257,8 @@ class PathTracer:
                                         max_depth=self.ptMaxDepth, firefly_clamp=self.ptFireflyClamp,
                                         tex_grad_scale=self.ptTexGradScale, aperture=self.ptAperture,
                                         focal_distance=None if self.ptAutoFocus else self.ptFocalDistance)
+        if self.ptUseOptixDenoiser:
+            pc.flags |= abi.PT_USE_OPTIX_DENOISER   # setupPushConstant :1547
         self.m_pushConst = pc
         self._ck(self._L.b200pt_render_frame(self._h, C.byref(fi), C.byref(pc)), "b200pt_render_frame")
         self.m_totalSamplesAccumulated += self.ptSamples
@@ -293,6 +298,19 @@ class PathTracer:
         ex = C.c_float()
         self._ck(self._L.b200pt_tonemap_image(self._h, C.byref(tm), C.c_void_p(dev_rgba32f), width, height, C.c_void_p(dev_rgba8), C.byref(ex)), "b200pt_tonemap_image")
         return ex.value
+
+    def set_guide_outputs(self, enable=True):
+        """b200pt_set_guide_outputs: the path pools carry the first-hit guides, frames write OutputImage::eOptixAlbedoNormal"""
+        self._ck(self._L.b200pt_set_guide_outputs(self._h, 1 if enable else 0), "b200pt_set_guide_outputs")
+        self.ptUseOptixDenoiser = bool(enable)
+
+    def read_guide(self):
+        """eOptixAlbedoNormal of the newest frame: (albedo float32 [rows, W, 3], compressed camera-space normal uint32 [rows, W])"""
+        w, _ = self._size
+        rows = self._tile[1]
+        out = np.empty((rows, w, 4), np.float32)
+        self._ck(self._L.b200pt_read_guide(self._h, out.ctypes.data_as(C.c_void_p), out.size), "b200pt_read_guide")
+        return out[..., :3].copy(), out[..., 3].copy().view(np.uint32)
 
     def read_selection(self):
         """gBuffers[eImgSelection] (object id per pixel, render node + 1, 0 = miss) and the NDC depth image, as the first
