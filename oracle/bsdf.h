@@ -485,6 +485,78 @@ static inline void iridescenceTint(const PbrMaterial& mat, int lobe, float kh, f
   }
 }
 
+// ---- bsdfEvaluateSimple / bsdfSampleSimple (nvshaders, external; call site pathtrace_functions.h.slang:537-540, the shadow catcher's
+// continuation ray): Lambert + one GGX lobe with f0 = lerp(0.04, baseColor, metallic); lobe picked by the Schlick weight at N.V, value
+// and pdf from evaluating both lobes.  Restated (parity unpinned, like the rest of this file). ----
+static inline float schlick_f0(float f0, float vdoth)
+{
+  const float m = 1.0f - vdoth, m2 = m * m;
+  return f0 + (1.0f - f0) * (m2 * m2 * m);
+}
+
+static inline void bsdfEvaluateSimple(BsdfEvaluateData& d, const PbrMaterial& mat)
+{
+  d.bsdf_diffuse = d.bsdf_glossy = f3(0.0f);
+  d.pdf = 0.0f;
+  const float3 h = normalize(d.k1 + d.k2);
+  const float  nv = clampf(dot(mat.N, d.k1), 0.0f, 1.0f), nl = clampf(dot(mat.N, d.k2), 0.0f, 1.0f);
+  const float  vh = clampf(dot(d.k1, h), 0.0f, 1.0f), nh = clampf(dot(mat.N, h), 0.0f, 1.0f);
+  if(nv == 0.0f || nl == 0.0f || vh == 0.0f || nh == 0.0f)
+    return;
+  const float  c_min_reflectance = 0.04f;
+  const float3 f0 = f3(c_min_reflectance) + (mat.baseColor - f3(c_min_reflectance)) * mat.metallic;
+  const float3 fGlossy = f3(schlick_f0(f0.x, vh), schlick_f0(f0.y, vh), schlick_f0(f0.z, vh));
+  const float  fDiffuse = (1.0f - mat.metallic) * (1.0f - schlick_f0(c_min_reflectance, vh));
+  const float3 localH = f3(dot(mat.T, h), dot(mat.B, h), nh);
+  const float  dd = hvd_ggx_eval(f2(1.0f / mat.roughness.x, 1.0f / mat.roughness.y), localH);
+  float        G1, G2;
+  ggx_smith_shadow_mask(G1, G2, f3(dot(mat.T, d.k1), dot(mat.B, d.k1), nv), f3(dot(mat.T, d.k2), dot(mat.B, d.k2), nl), mat.roughness);
+  const float diffusePdf = M_1_PI_F * nl;
+  const float specularPdf = G1 * dd * 0.25f / (nv * nh);
+  d.pdf = specularPdf + (diffusePdf - specularPdf) * fDiffuse;
+  d.bsdf_diffuse = mat.baseColor * (fDiffuse * diffusePdf);
+  d.bsdf_glossy = fGlossy * (G2 * specularPdf);
+}
+
+static inline void bsdfSampleSimple(BsdfSampleData& d, const PbrMaterial& mat)
+{
+  d.k2 = f3(0.0f);
+  d.bsdf_over_pdf = f3(0.0f);
+  d.pdf = 0.0f;
+  d.event_type = BSDF_EVENT_ABSORB;
+  const float nv = clampf(dot(mat.N, d.k1), 0.0f, 1.0f);
+  if(nv == 0.0f)
+    return;
+  const float fDiffuse = (1.0f - mat.metallic) * (1.0f - schlick_f0(0.04f, nv));
+  int         ev;
+  if(d.xi.z <= fDiffuse)
+  {
+    const float3 l = cosineSampleHemisphere(d.xi.x, d.xi.y);
+    d.k2 = mat.T * l.x + mat.B * l.y + mat.N * l.z;
+    ev = BSDF_EVENT_DIFFUSE_REFLECTION;
+  }
+  else
+  {
+    const float3 h0 = hvd_ggx_sample_vndf(f3(dot(d.k1, mat.T), dot(d.k1, mat.B), nv), mat.roughness, f2(d.xi.x, d.xi.y));
+    const float3 h = mat.T * h0.x + mat.B * h0.y + mat.N * h0.z;
+    d.k2 = h * (2.0f * dot(d.k1, h)) - d.k1;
+    ev = BSDF_EVENT_GLOSSY_REFLECTION;
+  }
+  if(dot(d.k2, mat.N) <= 0.0f)
+    return;
+  BsdfEvaluateData e;
+  e.k1 = d.k1;
+  e.k2 = d.k2;
+  e.xi = d.xi;
+  bsdfEvaluateSimple(e, mat);
+  const float3 total = e.bsdf_diffuse + e.bsdf_glossy;
+  if(!(e.pdf > 0.00001f) || total.x != total.x || total.y != total.y || total.z != total.z)
+    return;
+  d.pdf = e.pdf;
+  d.bsdf_over_pdf = total / e.pdf;
+  d.event_type = ev;
+}
+
 static inline void brdf_ggx_smith_eval(BsdfEvaluateData& d, const PbrMaterial& mat, int lobe, float3 tint)
 {
   if(dot(d.k2, mat.Ng) <= 0.0f)

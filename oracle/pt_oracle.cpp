@@ -1795,6 +1795,50 @@ static PathStepResult pathTraceOneBounce(const Ctx& c, Ray& ray, uint32_t& seed,
     pbrMat.Nc = hit.nrm;
     pbrMat.T = xyz(makeFastTangent(hit.nrm));
     pbrMat.B = cross(pbrMat.N, pbrMat.T);
+    // Shadow catcher: the plane shows only the shadows cast on it, over the environment (gltf_pathtrace.slang:175-186 +
+    // handleShadowCatcher, pathtrace_functions.h.slang:499-554, followed statement by statement)
+    if(c.fi->flags & B200PT_SCENE_INFINITE_PLANE_SHADOW_CATCHER)
+    {
+      pt.coneWidth = worldFoot;
+      DirectLight directLight;
+      sampleLights(c, hit.pos, pbrMat.N, seed, directLight, false);
+      float3 shadowFactor = f3(1.0f, 1.0f, 1.0f);
+      if(dot(directLight.direction, hit.nrm) > 0.0f && directLight.pdf != 0.0f)
+      {
+        Ray sr;
+        sr.o = hit.pos;
+        sr.d = directLight.direction;
+        sr.tmin = 0.0f;
+        sr.tmax = INFINITE_F;
+        shadowFactor = TraceShadow(*c.o, sr, seed, false);
+      }
+      float3 envColor;
+      float  envPdf;
+      sampleEnvironment(c, ray.d, envColor, envPdf);
+      if(shadowFactor.x == 1.0f && shadowFactor.y == 1.0f && shadowFactor.z == 1.0f)
+      {
+        const float misWeight = computeEnvHitMisWeight(c, pt.lastSamplePdf, envPdf);
+        pt.radiance += pt.throughput * misWeight * envColor;
+        return eBreak;
+      }
+      pt.radiance += envColor * shadowFactor;
+      pt.radiance -= envColor * (f3(1.0f) - shadowFactor) * c.fi->shadowCatcherDarkenAmount;
+      BsdfSampleData sd;
+      sd.k1 = -ray.d;
+      {
+        const float a = rnd(seed), b = rnd(seed), cc = rnd(seed);
+        sd.xi = f3(a, b, cc);
+      }
+      bsdfSampleSimple(sd, pbrMat);
+      if(sd.event_type == BSDF_EVENT_ABSORB)
+        return eBreak;
+      const float3 offsetDir = dot(sd.k2, hit.geonrm) > 0 ? hit.geonrm : -hit.geonrm;
+      ray.o = safeOffsetRay(hit.pos, offsetDir);
+      ray.d = sd.k2;
+      pt.throughput *= sd.bsdf_over_pdf;
+      pt.lastSamplePdf = sd.pdf;
+      return eEarlyContinue;
+    }
   }
   else
   {
@@ -2301,8 +2345,6 @@ int oracle_render_frame_guide(void* h, const b200pt_frame_info* fi, const b200pt
 {
   Oracle& o = *(Oracle*)h;
   if(!(fi->flags & B200PT_SCENE_USE_HDR_ENVIRONMENT) || o.envW == 0)
-    return B200PT_E_UNSUPPORTED;
-  if(fi->flags & B200PT_SCENE_INFINITE_PLANE_SHADOW_CATCHER)
     return B200PT_E_UNSUPPORTED;
   Ctx       c{&o, fi, pc};
   const int W = (int)fi->imageSize[0];

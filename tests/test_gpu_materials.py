@@ -164,8 +164,7 @@ def test_selection_ids_and_ndc_depth_of_frame_zero(std_env, oracle_mod):
 def test_render_parity_infinite_plane(std_env, oracle_mod):
     """--useInfinitePlane: the ground plane y = infinitePlaneDistance with its own base colour / metallic / roughness catches the
     rays that pass the geometry (checkInfinitePlaneIntersection, pathtrace_functions.h.slang:556-585; material swap
-    gltf_pathtrace.slang:165-173): stream-replicated parity with the oracle, the plane is visible, and the shadow-catcher mode is
-    refused instead of ignored."""
+    gltf_pathtrace.slang:165-173): stream-replicated parity with the oracle, the plane is visible."""
     from vk_gltf_renderer_b200 import synth
     from vk_gltf_renderer_b200.renderer import B200PTError, PathTracer, Resources
     scn = synth.synth_material_zoo()
@@ -174,7 +173,7 @@ def test_render_parity_infinite_plane(std_env, oracle_mod):
     o = _oracle(oracle_mod, scn, std_env)
     ref = oracle_mod.render(o, scn.camera, 192, 128, 8, max_depth=6, **kw)
     res = Resources(scene=scn, hdr_rgb=std_env, camera=scn.camera, size=(192, 128))
-    res.settings.useInfinitePlane, res.settings.infinitePlaneDistance = True, -0.02
+    res.settings.useInfinitePlane, res.settings.infinitePlaneDistance, res.settings.isShadowCatcher = True, -0.02, False
     res.settings.infinitePlaneBaseColor, res.settings.infinitePlaneMetallic, res.settings.infinitePlaneRoughness = (0.7, 0.5, 0.3), 0.1, 0.4
     from vk_gltf_renderer_b200.renderer import render_headless
     pt, img = render_headless(res, 8, ptMaxDepth=6)
@@ -187,10 +186,50 @@ def test_render_parity_infinite_plane(std_env, oracle_mod):
     res2 = Resources(scene=scn, hdr_rgb=std_env, camera=scn.camera, size=(192, 128))
     _, bare = render_headless(res2, 2, ptMaxDepth=6)
     assert (img[100:, :, 3] > 0).mean() > 0.9 and (bare[100:, :, 3] > 0).mean() < 0.6   # the lower image rows now hit the plane
-    res.settings.isShadowCatcher = True
-    res.frameCount = 0
-    with pytest.raises(B200PTError):
-        pt.onRender(None, res)
+
+
+def test_render_parity_shadow_catcher(std_env, oracle_mod):
+    """The reference's default plane mode (isShadowCatcher, src/resources.hpp:112): the plane shows the environment behind it, darkened
+    where a light sample is blocked, and shadowed hits continue with bsdfSampleSimple without consuming depth (handleShadowCatcher,
+    pathtrace_functions.h.slang:499-554; eEarlyContinue, gltf_pathtrace.slang:176-185).  Punctual lights + environment, a MASK
+    foliage scene (coloured / stochastic shadow transmission through the any-hit kernels), 2 samples per pixel, frame batching, a
+    non-zero shadowCatcherDarkness: stream-replicated parity with the oracle, identical ray budgets, and the catcher is visibly not
+    the solid plane."""
+    from vk_gltf_renderer_b200 import synth
+    from vk_gltf_renderer_b200.renderer import PathTracer, Resources, render_headless
+    lit = synth.synth_lit()
+    lit.render_nodes = lit.render_nodes[1:]          # drop the floor: the catcher plane replaces it
+    zoo = synth.synth_material_zoo()
+    zoo.render_nodes = zoo.render_nodes[:-1]
+    for name, scn, dist, dark in (("lit", lit, -0.01, 0.0), ("zoo", zoo, -0.02, 0.35)):
+        kw = dict(infinite_plane=True, plane_distance=dist, plane_color=(0.6, 0.6, 0.55), plane_metallic=0.2, plane_roughness=0.35, shadow_catcher=True,
+                  catcher_darkness=dark)
+        o = _oracle(oracle_mod, scn, std_env)
+        ref = oracle_mod.render(o, scn.camera, 192, 128, 6, max_depth=5, num_samples=2, **kw)
+        res = Resources(scene=scn, hdr_rgb=std_env, camera=scn.camera, size=(192, 128))
+        res.settings.useInfinitePlane, res.settings.infinitePlaneDistance, res.settings.shadowCatcherDarkness = True, dist, dark
+        res.settings.infinitePlaneBaseColor, res.settings.infinitePlaneMetallic, res.settings.infinitePlaneRoughness = (0.6, 0.6, 0.55), 0.2, 0.35
+        assert res.settings.isShadowCatcher                      # the reference's default
+        pt = PathTracer(0)
+        pt.ptMaxDepth, pt.ptSamples = 5, 2
+        pt.onAttach(res)
+        pt.set_frame_batch(3)
+        for f in range(6):
+            res.frameCount = f
+            pt.onRender(None, res)
+        img = pt.read_accum()
+        e = rel_rmse(img, ref)
+        print("shadow catcher", name, "rel RMSE", e)
+        assert np.isfinite(img).all() and e <= 1e-3
+        st, so = pt.stats(), o.stats()
+        assert st["closestRays"] == so["closestRays"] and st["shadowRays"] == so["shadowRays"] and st["shadedHits"] == so["shadedHits"]
+        # against the solid plane: different picture (the catcher is see-through where lit)
+        res.settings.isShadowCatcher = False
+        _, solid = render_headless(res, 2, ptMaxDepth=5)
+        ok = np.isfinite(solid).all(-1)   # (a sphere light seen from > 1 km gives the restated nvshaders light sample an infinite pdf in both
+        assert ok.mean() > 0.99          #  implementations: a handful of NaN pixels at the horizon of the SOLID plane, none with the catcher)
+        assert rel_rmse(img[ok], solid[ok]) > 0.05
+        pt.onDetach(res)
 
 
 def test_refit_after_transform_update_matches_a_fresh_build(std_env, oracle_mod):

@@ -68,7 +68,7 @@ def _glm(m):
 
 def make_frame_info(cam, width, height, *, use_hdr=True, env_rotation=0.0, env_intensity=1.0, env_blur=0.0,
                     solid_background=False, background=(0, 0, 0), infinite_plane=False, plane_distance=0.0,
-                    plane_color=(0.5, 0.5, 0.5), plane_metallic=0.0, plane_roughness=0.5, shadow_catcher=False):
+                    plane_color=(0.5, 0.5, 0.5), plane_metallic=0.0, plane_roughness=0.5, shadow_catcher=False, catcher_darkness=0.0):
     """SceneFrameInfo as filled at src/renderer.cpp:677-700 (projection uses the *window* aspect)."""
     view = look_at(cam.eye, cam.center, cam.up)
     if cam.type == "orthographic":
@@ -97,7 +97,7 @@ def make_frame_info(cam, width, height, *, use_hdr=True, env_rotation=0.0, env_i
     fi.infinitePlaneBaseColor[:] = list(plane_color)
     fi.infinitePlaneMetallic = plane_metallic
     fi.infinitePlaneRoughness = plane_roughness
-    fi.shadowCatcherDarkenAmount = 0.0
+    fi.shadowCatcherDarkenAmount = max(catcher_darkness, 0.0)   # src/renderer.cpp:700
     return fi
 
 

@@ -572,6 +572,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
   DirectLight               directLight;
   bool                      nextEventValid = false;
   bool                      onPlane = false;  // the ray met the infinite ground plane in front of the geometry
+  bool                      catcher = false;  // ... and the plane is a shadow catcher (handleShadowCatcher, pathtrace_functions.h.slang:499-554)
 #ifdef B200PT_DEBUG
   bool dbgPixel = false;
 #endif
@@ -602,6 +603,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
     // ---- infinite ground plane (checkInfinitePlaneIntersection, pathtrace_functions.h.slang:556-585): y = infinitePlaneDistance,
     //      hit from above only, when it lies in front of the geometry hit ----
     onPlane = false;
+    catcher = false;
     if(F.fi.flags & B200PT_SCENE_USE_INFINITE_PLANE)
     {
       const float3 normal = f3(0, 1, 0);
@@ -697,6 +699,13 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
       pbrMat.Nc = hit.nrm;
       pbrMat.T = xyz(makeFastTangent(hit.nrm));
       pbrMat.B = cross(pbrMat.N, pbrMat.T);
+      if(F.fi.flags & B200PT_SCENE_INFINITE_PLANE_SHADOW_CATCHER)
+      {
+        // gltf_pathtrace.slang:175-186: the catcher returns before the first-hit captures, the roughness clamp and emission; its light
+        // sample is drawn in the next section (the one sampleLights of this kernel), its second half runs after the shadow trace
+        catcher = true;
+        return true;
+      }
     }
     else
     {
@@ -742,7 +751,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
     flags &= ~(PF_POST_VOLUME | PF_SHADOW_VALID | PF_SHADOW_INSIDE);
 
     // ---- in-volume segment (pathtrace_functions.h.slang:904-939, 605-672) ----
-    if((FEAT & FEAT_VOLUME) && (flags & PF_INSIDE))
+    if((FEAT & FEAT_VOLUME) && (flags & PF_INSIDE) && !catcher)
     {
       const VolumeMedium vm = unpackMedium(med);
       if(hasVolumeMedium(vm))
@@ -809,6 +818,25 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
 
     // ---- next-event estimation: one light-or-environment sample, MIS (:316-351) ----
     directLight = sampleLights<FEAT>(S, F, hit.pos, seed);
+    if(catcher)
+    {
+      // handleShadowCatcher, first half (:511-523): the light sample and its shadow ray -- from the plane point itself, unbounded.
+      // The shadow factor comes back through the shadow / any-hit kernels in shC; finishPost continues with the second half.
+      flags |= PF_CATCHER;
+      if(dot(directLight.direction, hit.nrm) > 0.0f && directLight.pdf != 0.0f)
+      {
+        P.shO[i] = f4(hit.pos, kInfinite);
+        P.shD[i] = f4(directLight.direction, 0.0f);
+        P.shC[i] = f4(1.0f, 1.0f, 1.0f, 0.0f);
+        flags |= PF_SHADOW_VALID;
+      }
+      P.rayO[i] = f4(hit.pos, coneWidth);  // the incoming direction stays in rayD: the second half looks the environment up along it
+      P.misc[i] = f4(misc.x, misc.y, __uint_as_float(flags), __uint_as_float(seed));
+      queuePush(qPost, cntPost, i);
+      if(flags & PF_SHADOW_VALID)
+        queuePush(qShadow, cntShadow, i);
+      return false;
+    }
     nextEventValid = (dot(directLight.direction, hit.nrm) > 0.0f || pbrMat.diffuseTransmissionFactor > 0.0f) && directLight.pdf != 0.0f;
     return true;
   };
@@ -914,16 +942,67 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS * 128 / SHADE_BL
 // pathTrace() tail for every path that survived shading: delayed NEE visibility (TraceShadow), Russian
 // roulette, depth++ (gltf_pathtrace.slang:462-485).  Same persistent-warp scheme as k_trace; paths without a
 // shadow ray finish immediately and their lanes are refilled.
-__device__ void finishPost(const PathState& P, const FrameParams& F, uint32_t i, uint32_t flags, uint32_t seed, bool haveShadow, float3 Tfac,
+__device__ void finishPost(const PathState& P, const DevScene& S, const FrameParams& F, uint32_t i, uint32_t flags, uint32_t seed, bool haveShadow, float3 Tfac,
                            uint32_t* qNext, uint32_t* cntNext, DevStats* stats)
 {
   const float4 misc = P.misc[i];
   const float4 rad4 = P.rad[i];
   float3       radiance = xyz(rad4);
-  if(haveShadow)
-    radiance += xyz(P.shC[i]) * Tfac;
   const float4 thr4 = P.thr[i];
   float3       throughput = xyz(thr4);
+  if(flags & PF_CATCHER)
+  {
+    // handleShadowCatcher, second half (pathtrace_functions.h.slang:525-553): lit plane points show the environment behind them and
+    // end the path; shadowed ones show it darkened and continue with bsdfSampleSimple -- eEarlyContinue: no roulette, no depth++
+    const float3 shadowFactor = haveShadow ? xyz(P.shC[i]) * Tfac : f3(1.0f);
+    const float4 ro = P.rayO[i];
+    const float3 hitPos = xyz(ro), dir = xyz(P.rayD[i]);
+    const float4 env = sampleEnvTex(S, getSphericalUv(rotateAxis(dir, f3(0, 1, 0), -F.fi.envRotation)));
+    const float3 envColor = xyz(env) * F.fi.envIntensity;
+    flags &= ~(PF_CATCHER | PF_POST_VOLUME | PF_SHADOW_VALID | PF_SHADOW_INSIDE);
+    if(shadowFactor.x == 1.0f && shadowFactor.y == 1.0f && shadowFactor.z == 1.0f)
+    {
+      float misWeight = 1.0f;
+      if(thr4.w != kDirac)
+      {
+        float lw, ew;
+        techniqueProbabilities(S, F, lw, ew);
+        misWeight = thr4.w / (thr4.w + ew * env.w);
+      }
+      radiance += throughput * misWeight * envColor;
+      finalizeSample(P, F, i, radiance, (flags & PF_SOLID) != 0, seed, P.medium[i].w >> 16, qNext, cntNext, stats);
+      return;
+    }
+    radiance += envColor * shadowFactor;
+    radiance -= envColor * (f3(1.0f) - shadowFactor) * F.fi.shadowCatcherDarkenAmount;
+    PbrMaterial  pm = defaultPbrMaterial();  // the plane's material, as k_shade built it (gltf_pathtrace.slang:169-173)
+    const float3 n = f3(0, 1, 0);
+    pm.baseColor = f3(F.fi.infinitePlaneBaseColor[0], F.fi.infinitePlaneBaseColor[1], F.fi.infinitePlaneBaseColor[2]);
+    pm.metallic = F.fi.infinitePlaneMetallic;
+    const float r = F.fi.infinitePlaneRoughness;
+    pm.roughness = f2(r * r, r * r);
+    pm.N = pm.Ng = pm.Nc = n;
+    pm.T = xyz(makeFastTangent(n));
+    pm.B = cross(pm.N, pm.T);
+    const float      a = rnd(seed), b = rnd(seed), c = rnd(seed);
+    const BsdfSample sd = bsdfSampleSimple(pm, -dir, f3(a, b, c));
+    if(sd.event_type == BSDF_EVENT_ABSORB)
+    {
+      finalizeSample(P, F, i, radiance, (flags & PF_SOLID) != 0, seed, P.medium[i].w >> 16, qNext, cntNext, stats);
+      return;
+    }
+    const float3 offsetDir = dot(sd.k2, n) > 0 ? n : -n;
+    throughput *= sd.bsdf_over_pdf;
+    P.rayO[i] = f4(safeOffsetRay(hitPos, offsetDir), ro.w);
+    P.rayD[i] = f4(normalize(sd.k2), kInfinite);
+    P.thr[i] = f4(throughput, sd.pdf);
+    P.rad[i] = f4(radiance, rad4.w);
+    P.misc[i] = f4(misc.x, misc.y, __uint_as_float(flags), __uint_as_float(seed));
+    queuePush(qNext, cntNext, i);
+    return;
+  }
+  if(haveShadow)
+    radiance += xyz(P.shC[i]) * Tfac;
   uint32_t     depth = flags & PF_DEPTH_MASK;
   bool         alive = true, thrDirty = false;
   if(flags & PF_POST_VOLUME)
@@ -1202,7 +1281,7 @@ __global__ void __launch_bounds__(256) k_sort_scatter(PathState P, DevScene S, c
 // pathTrace() tail for every path that survived shading (gltf_pathtrace.slang:462-485), one thread per path: the
 // delayed NEE contribution (already scaled by the any-hit transmission in k_alpha<true>; an opaque occluder
 // zeroes it here), Russian roulette and depth++ in finishPost.
-__global__ void __launch_bounds__(256) k_resolve(PathState P, const __grid_constant__ FrameParams F, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn,
+__global__ void __launch_bounds__(256) k_resolve(PathState P, DevScene S, const __grid_constant__ FrameParams F, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn,
                                                  uint32_t* qNext, uint32_t* cntNext, DevStats* stats)
 {
   const uint32_t count = *cntIn;
@@ -1221,7 +1300,7 @@ __global__ void __launch_bounds__(256) k_resolve(PathState P, const __grid_const
     if(haveShadow && (float)(pixelOf(F, path) % (uint32_t)F.width) == F.pc.mouseCoord[0] && (float)pixelRow(F, pixelOf(F, path)) == F.pc.mouseCoord[1])
       printf("DBG shadow occluded=%d\n", (int)(vis.x == 0.0f));
 #endif
-    finishPost(P, F, path, flags, seed, haveShadow, vis, qNext, cntNext, stats);
+    finishPost(P, S, F, path, flags, seed, haveShadow, vis, qNext, cntNext, stats);
   }
 }
 
@@ -4087,11 +4166,6 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
     h->err = "b200pt_render_frame: only the HDR environment (--envSystem 1) is built; physical sky is out of scope";
     return B200PT_E_UNSUPPORTED;
   }
-  if(fi->flags & B200PT_SCENE_INFINITE_PLANE_SHADOW_CATCHER)
-  {
-    h->err = "b200pt_render_frame: the shadow-catcher mode of the infinite plane is not built (handleShadowCatcher needs nvshaders' bsdfSampleSimple)";
-    return B200PT_E_UNSUPPORTED;
-  }
   if(pc->flags & B200PT_PT_USE_DLSS)
   {
     h->err = "b200pt_render_frame: the DLSS variant (frame jitter, motion vectors, specular guides) is out of scope";
@@ -4230,7 +4304,9 @@ static int launchFrames(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
     int       it = 0;
     int       cur = 0;  // dQ[cur] = trace queue, dQ[2] = post queue, dQ[1-cur] = next queue
     const int firstBatch = pc->maxDepth;
-    const bool mayOverrun = h->hasVolume || pc->numSamples > 1;
+    // (a shadowed shadow-catcher hit continues without consuming depth: such a frame can need more iterations than maxDepth)
+    const bool catcherFrame = (fi->flags & B200PT_SCENE_USE_INFINITE_PLANE) && (fi->flags & B200PT_SCENE_INFINITE_PLANE_SHADOW_CATCHER);
+    const bool mayOverrun = h->hasVolume || pc->numSamples > 1 || catcherFrame;
     int        remaining = firstBatch;
     for(;;)
     {
@@ -4289,7 +4365,7 @@ static int launchFrames(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
           timed(tPost, [&] { WALK_KERNEL(k_shadow, gW, L.P, h->S, L.dQ[5], &cntContS[it], &workContS[it], L.dQ[4], &cntAlphaS1[it], h->dStats, h->refillThreshold, h->postponeShift, 1); });
           timed(tAnyHit, [&] { k_alpha<true><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS1[it], nullptr, nullptr, h->dStats, TRACE_CONT); });
         }
-        timed(tResolve, [&] { k_resolve<<<gridFor(h, 4), 256, 0, st>>>(L.P, F, L.dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats); });
+        timed(tResolve, [&] { k_resolve<<<gridFor(h, 4), 256, 0, st>>>(L.P, h->S, F, L.dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats); });
         cur = 1 - cur;
       }
       if(!mayOverrun)

@@ -706,6 +706,79 @@ __device__ __noinline__ BsdfSample bsdfSample(const PbrMaterial& mat, float3 k1,
 }
 
 // ---- small nvshaders helpers used by hit fetch / volumes / environment --------------------------
+// ---- bsdfEvaluateSimple / bsdfSampleSimple (nvshaders, external; call site: handleShadowCatcher, pathtrace_functions.h.slang:537-540) ----
+// The reference continues a shadowed shadow-catcher path with this two-lobe model: Lambert diffuse plus ONE GGX lobe whose f0 blends
+// the dielectric 0.04 and the base colour by metallic; the lobe is picked with the Schlick weight at N.V, the pair (value, pdf) then
+// comes from evaluating BOTH lobes for the sampled direction.  Restated like the rest of this file (parity unpinned).
+PT_D float schlickF0(float f0, float vdoth)
+{
+  const float m = 1.0f - vdoth, m2 = m * m;
+  return f0 + (1.0f - f0) * (m2 * m2 * m);
+}
+
+PT_D BsdfEval bsdfEvaluateSimple(const PbrMaterial& mat, float3 k1, float3 k2)
+{
+  BsdfEval d;
+  d.bsdf_diffuse = d.bsdf_glossy = f3(0.0f);
+  d.pdf = 0.0f;
+  const float3 h = normalize(k1 + k2);
+  const float  nv = clampf(dot(mat.N, k1), 0.0f, 1.0f), nl = clampf(dot(mat.N, k2), 0.0f, 1.0f);
+  const float  vh = clampf(dot(k1, h), 0.0f, 1.0f), nh = clampf(dot(mat.N, h), 0.0f, 1.0f);
+  if(nv == 0.0f || nl == 0.0f || vh == 0.0f || nh == 0.0f)
+    return d;
+  const float  cMin = 0.04f;
+  const float3 f0 = f3(cMin) + (mat.baseColor - f3(cMin)) * mat.metallic;
+  const float3 fGlossy = f3(schlickF0(f0.x, vh), schlickF0(f0.y, vh), schlickF0(f0.z, vh));
+  const float  fDiffuse = (1.0f - mat.metallic) * (1.0f - schlickF0(cMin, vh));
+  const float3 h0 = f3(dot(mat.T, h), dot(mat.B, h), nh);
+  const float  dd = ggxD(f2(1.0f / mat.roughness.x, 1.0f / mat.roughness.y), h0);
+  const float  G1 = smithG1(f3(dot(mat.T, k1), dot(mat.B, k1), nv), mat.roughness);
+  const float  G2 = smithG1(f3(dot(mat.T, k2), dot(mat.B, k2), nl), mat.roughness);
+  const float  diffusePdf = kInvPi * nl;
+  const float  specularPdf = G1 * dd * 0.25f / (nv * nh);
+  d.pdf = specularPdf + (diffusePdf - specularPdf) * fDiffuse;
+  d.bsdf_diffuse = mat.baseColor * (fDiffuse * diffusePdf);
+  d.bsdf_glossy = fGlossy * (G2 * specularPdf);
+  return d;
+}
+
+PT_D BsdfSample bsdfSampleSimple(const PbrMaterial& mat, float3 k1, float3 xi)
+{
+  BsdfSample d;
+  d.k2 = f3(0.0f);
+  d.bsdf_over_pdf = f3(0.0f);
+  d.pdf = 0.0f;
+  d.event_type = BSDF_EVENT_ABSORB;
+  const float nv = clampf(dot(mat.N, k1), 0.0f, 1.0f);
+  if(nv == 0.0f)
+    return d;
+  const float fDiffuse = (1.0f - mat.metallic) * (1.0f - schlickF0(0.04f, nv));
+  int         ev;
+  if(xi.z <= fDiffuse)
+  {
+    const float3 l = cosineSampleHemisphere(xi.x, xi.y);
+    d.k2 = mat.T * l.x + mat.B * l.y + mat.N * l.z;
+    ev = BSDF_EVENT_DIFFUSE_REFLECTION;
+  }
+  else
+  {
+    const float3 h0 = ggxSampleVndf(f3(dot(k1, mat.T), dot(k1, mat.B), nv), mat.roughness, f2(xi.x, xi.y));
+    const float3 h = mat.T * h0.x + mat.B * h0.y + mat.N * h0.z;
+    d.k2 = h * (2.0f * dot(k1, h)) - k1;
+    ev = BSDF_EVENT_GLOSSY_REFLECTION;
+  }
+  if(dot(d.k2, mat.N) <= 0.0f)
+    return d;
+  const BsdfEval e = bsdfEvaluateSimple(mat, k1, d.k2);
+  const float3   total = e.bsdf_diffuse + e.bsdf_glossy;
+  if(!(e.pdf > 0.00001f) || total.x != total.x || total.y != total.y || total.z != total.z)
+    return d;
+  d.pdf = e.pdf;
+  d.bsdf_over_pdf = total / e.pdf;
+  d.event_type = ev;
+  return d;
+}
+
 PT_D float3 pointOffset(float3 p, float3 pa, float3 pb, float3 pc, float3 na, float3 nb, float3 nc, float3 bary)
 {
   float3      tu = p - pa, tv = p - pb, tw = p - pc;

@@ -171,6 +171,7 @@ enum : uint32_t
   PF_POST_VOLUME = 1u << 18,   // post stage runs the in-volume RR rule instead of the surface one
   PF_SHADOW_VALID = 1u << 19,
   PF_SHADOW_INSIDE = 1u << 20, // TraceShadow(initialInside = true)
+  PF_CATCHER = 1u << 21,       // the path sits on the shadow-catcher plane: the post stage runs handleShadowCatcher's second half
 };
 
 struct Queues

@@ -357,6 +357,7 @@ b200pt_frame_info makeFrameInfo(const Camera& cam, int width, int height, const 
   std::memcpy(fi.infinitePlaneBaseColor, s.infinitePlaneBaseColor, 12);
   fi.infinitePlaneMetallic = s.infinitePlaneMetallic;
   fi.infinitePlaneRoughness = s.infinitePlaneRoughness;
+  fi.shadowCatcherDarkenAmount = std::max(s.shadowCatcherDarkness, 0.0f);  // src/renderer.cpp:700
   return fi;
 }
 

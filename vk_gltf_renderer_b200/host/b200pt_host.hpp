@@ -34,13 +34,14 @@ struct Settings
   bool  useSolidBackground  = false;
   float solidBackgroundColor[3] = {0.f, 0.f, 0.f};
   int   maxFrames           = 500;
-  // infinite ground plane (src/resources.hpp:111-116); the shadow-catcher mode is not built (the frame call fails)
+  // infinite ground plane (src/resources.hpp:111-117); like the reference it is a shadow catcher unless told otherwise
   bool  useInfinitePlane       = false;
-  bool  isShadowCatcher        = false;
+  bool  isShadowCatcher        = true;
   float infinitePlaneDistance  = 0.0f;
   float infinitePlaneBaseColor[3] = {0.5f, 0.5f, 0.5f};
   float infinitePlaneMetallic  = 0.0f;
   float infinitePlaneRoughness = 0.5f;
+  float shadowCatcherDarkness  = 0.0f;
   bool  useOpacityMicromap     = true;  // --useOpacityMicromap (src/main.cpp:114-115): consume EXT_mesh_opacity_micromap when the asset has it
 };
 

@@ -32,11 +32,12 @@ class Settings:
     solidBackgroundColor: tuple = (0.0, 0.0, 0.0)
     maxFrames: int = 500
     useInfinitePlane: bool = False   # src/resources.hpp:111-116
-    isShadowCatcher: bool = False    # (not built: B200PT_E_UNSUPPORTED)
+    isShadowCatcher: bool = True     # the reference's default: the plane only catches shadows (src/resources.hpp:112)
     infinitePlaneDistance: float = 0.0
     infinitePlaneBaseColor: tuple = (0.5, 0.5, 0.5)
     infinitePlaneMetallic: float = 0.0
     infinitePlaneRoughness: float = 0.5
+    shadowCatcherDarkness: float = 0.0   # non-physical shadow darkening (src/resources.hpp:117)
 
 
 @dataclass
@@ -251,7 +252,8 @@ class PathTracer:
                                      env_intensity=s.hdrEnvIntensity, env_blur=s.hdrBlur,
                                      solid_background=s.useSolidBackground, background=s.solidBackgroundColor,
                                      infinite_plane=s.useInfinitePlane, plane_distance=s.infinitePlaneDistance, plane_color=s.infinitePlaneBaseColor,
-                                     plane_metallic=s.infinitePlaneMetallic, plane_roughness=s.infinitePlaneRoughness, shadow_catcher=s.isShadowCatcher)
+                                     plane_metallic=s.infinitePlaneMetallic, plane_roughness=s.infinitePlaneRoughness, shadow_catcher=s.isShadowCatcher,
+                                     catcher_darkness=s.shadowCatcherDarkness)
         pc = cam_mod.make_push_constant(resources.camera, h, frame_count=resources.frameCount,
                                         total_samples=self.m_totalSamplesAccumulated, num_samples=self.ptSamples,
                                         max_depth=self.ptMaxDepth, firefly_clamp=self.ptFireflyClamp,
