@@ -2346,6 +2346,8 @@ int oracle_render_frame_guide(void* h, const b200pt_frame_info* fi, const b200pt
   Oracle& o = *(Oracle*)h;
   if(!(fi->flags & B200PT_SCENE_USE_HDR_ENVIRONMENT) || o.envW == 0)
     return B200PT_E_UNSUPPORTED;
+  if(fi->envBlur > 0.0f && !(fi->flags & B200PT_SCENE_USE_SOLID_BACKGROUND))
+    return B200PT_E_UNSUPPORTED;  // tryPrimaryMissBackplate's smoothHDRBlur (nvshaders, external)
   Ctx       c{&o, fi, pc};
   const int W = (int)fi->imageSize[0];
   nthreads = std::max(1, nthreads);

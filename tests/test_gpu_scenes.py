@@ -197,6 +197,11 @@ def test_unsupported_paths_fail_loudly(box_scene, std_env):
     res.frameCount = 0
     with pytest.raises(B200PTError):
         pt.onRender(None, res)
+    res.settings.envSystem, res.settings.hdrBlur = 1, 0.5   # blurred HDR backplate (smoothHDRBlur, nvshaders): not built, not ignored
+    with pytest.raises(B200PTError):
+        pt.onRender(None, res)
+    res.settings.hdrBlur = 0.0
+    pt.onRender(None, res)
 
 
 def test_frames_in_flight_and_async_readback(box_scene, std_env):

@@ -4166,6 +4166,11 @@ int b200pt_render_frame(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
     h->err = "b200pt_render_frame: only the HDR environment (--envSystem 1) is built; physical sky is out of scope";
     return B200PT_E_UNSUPPORTED;
   }
+  if((fi->flags & B200PT_SCENE_USE_HDR_ENVIRONMENT) && fi->envBlur > 0.0f && !(fi->flags & B200PT_SCENE_USE_SOLID_BACKGROUND))
+  {
+    h->err = "b200pt_render_frame: the blurred HDR backplate (envBlur > 0: nvshaders' smoothHDRBlur, external) is not built";
+    return B200PT_E_UNSUPPORTED;
+  }
   if(pc->flags & B200PT_PT_USE_DLSS)
   {
     h->err = "b200pt_render_frame: the DLSS variant (frame jitter, motion vectors, specular guides) is out of scope";
