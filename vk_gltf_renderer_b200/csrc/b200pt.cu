@@ -43,6 +43,12 @@ static_assert(sizeof(b200pt_push_constant) == 48, "PathtracePushConstant layout"
 namespace {
 
 constexpr int kMaxIters = 4096;  // per-frame iteration counter slots
+// Any-hit continuation rounds per bounce: a ray whose kCand candidates were all rejected goes through another k_trace / k_shadow round
+// that resumes behind the last one; after kContRoundsMax rounds whatever is still undecided finishes inside the last k_alpha.  Counter
+// arrays per lane: 5 (trace / post queues and cursors, shadow queue) + per ray kind (rounds + 1) any-hit counters, rounds continuation
+// counters and rounds continuation cursors.
+constexpr int kContRoundsMax = 8;
+constexpr int kCounterArrays = 5 + 2 * (3 * kContRoundsMax + 1);
 
 // -------------------------------------------------------------------------------------------------
 // queue helper: warp-aggregated append
@@ -325,7 +331,7 @@ template <bool SHADOW>
 __global__ void __launch_bounds__(128) k_alpha(PathState P, DevScene S, const uint32_t* __restrict__ q, const uint32_t* __restrict__ cntIn, uint32_t* qCont,
                                                uint32_t* cntCont, DevStats* stats, int mode)
 {
-  static_assert(kCand == 4 || kCand == 8, "kCand lanes per path");
+  static_assert(kCand == 2 || kCand == 4 || kCand == 8, "kCand lanes per path");
   // candidate slots index the triangle array of the tree that produced them: the merged tree for closest-hit rays,
   // the split opaque / non-opaque arrays for shadow rays
   const uint2* __restrict__ triMeta = SHADOW ? S.triMetaS : S.triMeta;
@@ -1748,6 +1754,11 @@ struct b200pt
   int                 refillThreshold = kRefillThresholdDefault, postponeShift = 2;  // B200PT_REFILL / B200PT_POSTPONE env overrides (tuning)
   int                 bvhBuilder = 0;  // 0: host SAH builder (bvh.cpp), 1: device LBVH (lbvh.cuh); b200pt_set_bvh_builder / B200PT_BVH_BUILDER
   double              bvhBuildMs = 0.0;  // wall time of the last scene's tree builds
+  // any-hit continuation rounds per bounce (B200PT_CONT_ROUNDS, 1..kContRoundsMax).  Measured on the bench scene (r02zg / r02zh, one box
+  // each): 4 candidates x 1 round 984 / 977 Mray/s -- the in-kernel fallback walks of the last k_alpha (2 of 32 lanes busy) were a tail
+  // on every bounce -- x 2 rounds 1019.8 / 1022.8, x 3 / 4 / 6 rounds 1011 / 1016 / 1014; 2 candidates (the bound shrinks sooner) x 2 / 3 /
+  // 4 / 5 / 6 / 8 rounds 987 / 1012 / 1024 + 1022 / 1016 / 1020 / 1014: the same plateau with more launches
+  int                 contRounds = (kCand <= 2) ? 4 : 2;
   int                 walkGridPerSM = 8, shadeGridPerSM = 2;  // CTAs per SM of the persistent walk / shade grids (B200PT_WALK_GRID, B200PT_SHADE_GRID)
   bool                sortShade = false;
   bool                sortRays = false;   // B200PT_SORT_RAYS=1 (experiment): trace queue bucketed by ray direction octant  // B200PT_SORT_SHADE=1: material-sorted shade queue (measured)
@@ -2333,6 +2344,8 @@ int b200pt_create(b200pt_t** out, int cuda_device)
     h->walkGridPerSM = std::min(std::max(atoi(e), 1), 32);
   if(const char* e = getenv("B200PT_SHADE_GRID"))
     h->shadeGridPerSM = std::min(std::max(atoi(e), 1), 8);
+  if(const char* e = getenv("B200PT_CONT_ROUNDS"))
+    h->contRounds = std::min(std::max(atoi(e), 1), kContRoundsMax);
   if(const char* e = getenv("B200PT_BVH_BUILDER"))
     h->bvhBuilder = (strcmp(e, "gpu") == 0 || strcmp(e, "1") == 0) ? 1 : 0;
   bool ok = true;
@@ -2370,7 +2383,7 @@ int b200pt_create(b200pt_t** out, int cuda_device)
     need(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
     need(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
     need(cudaEventCreateWithFlags(&L.freed, cudaEventDisableTiming));
-    need(cudaMalloc((void**)&L.dCounters, sizeof(uint32_t) * 13 * kMaxIters));
+    need(cudaMalloc((void**)&L.dCounters, sizeof(uint32_t) * kCounterArrays * kMaxIters));
     need(cudaMalloc((void**)&L.dBuckets, sizeof(uint32_t) * 2 * kSortMaxBuckets));
     if(ok)
       need(cudaMemset(L.dBuckets, 0, sizeof(uint32_t) * 2 * kSortMaxBuckets));
@@ -4263,15 +4276,12 @@ static int launchFrames(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
   uint32_t*    workTrace = L.dCounters + 2 * kMaxIters;  // dynamic-fetch cursors of the persistent kernels
   uint32_t*    workPost = L.dCounters + 3 * kMaxIters;
   uint32_t*    cntShadow = L.dCounters + 4 * kMaxIters;
-  uint32_t*    cntAlpha = L.dCounters + 5 * kMaxIters;
-  uint32_t*    cntAlphaS = L.dCounters + 6 * kMaxIters;
-  uint32_t*    cntCont = L.dCounters + 7 * kMaxIters;    // closest rays whose kCand candidates were all rejected
-  uint32_t*    cntAlpha1 = L.dCounters + 8 * kMaxIters;  // ... and their second batch of candidates
-  uint32_t*    cntContS = L.dCounters + 9 * kMaxIters;   // same for shadow rays
-  uint32_t*    cntAlphaS1 = L.dCounters + 10 * kMaxIters;
-  uint32_t*    workCont = L.dCounters + 11 * kMaxIters;
-  uint32_t*    workContS = L.dCounters + 12 * kMaxIters;
-  CK(cudaMemsetAsync(L.dCounters, 0, sizeof(uint32_t) * 13 * kMaxIters, st));
+  // any-hit counters of round r (r = 0: the main walk's candidates), continuation queue counters and cursors of round r, per ray kind
+  const int    R = h->contRounds;
+  auto cntA = [&](int shadow, int r) { return L.dCounters + (size_t)(5 + shadow * (3 * kContRoundsMax + 1) + r) * kMaxIters; };
+  auto cntC = [&](int shadow, int r) { return L.dCounters + (size_t)(5 + shadow * (3 * kContRoundsMax + 1) + (kContRoundsMax + 1) + r) * kMaxIters; };
+  auto wrkC = [&](int shadow, int r) { return L.dCounters + (size_t)(5 + shadow * (3 * kContRoundsMax + 1) + (2 * kContRoundsMax + 1) + r) * kMaxIters; };
+  CK(cudaMemsetAsync(L.dCounters, 0, sizeof(uint32_t) * kCounterArrays * kMaxIters, st));
 
   enum
   {
@@ -4338,12 +4348,15 @@ static int launchFrames(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
           timed(tOther, [&] { k_sort_scatter<1><<<gridFor(h, 4), 256, 0, st>>>(L.P, h->S, qT, &cntTrace[it], L.dBuckets + kSortMaxBuckets, L.dQ[3], 8u); });
           qWalk = L.dQ[3];
         }
-        timed(tTrace, [&] { WALK_KERNEL(k_trace, gW, L.P, h->S, qWalk, &cntTrace[it], &workTrace[it], L.dQ[4], &cntAlpha[it], h->dStats, h->refillThreshold, h->postponeShift, 0); });
+        timed(tTrace, [&] { WALK_KERNEL(k_trace, gW, L.P, h->S, qWalk, &cntTrace[it], &workTrace[it], L.dQ[4], cntA(0, 0) + it, h->dStats, h->refillThreshold, h->postponeShift, 0); });
         if(h->S.hasAlpha)
         {
-          timed(tAnyHit, [&] { k_alpha<false><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlpha[it], L.dQ[5], &cntCont[it], h->dStats, 0); });
-          timed(tTrace, [&] { WALK_KERNEL(k_trace, gW, L.P, h->S, L.dQ[5], &cntCont[it], &workCont[it], L.dQ[4], &cntAlpha1[it], h->dStats, h->refillThreshold, h->postponeShift, 1); });
-          timed(tAnyHit, [&] { k_alpha<false><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlpha1[it], nullptr, nullptr, h->dStats, TRACE_CONT); });
+          for(int r = 0; r < R; r++)
+          {
+            timed(tAnyHit, [&] { k_alpha<false><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], cntA(0, r) + it, L.dQ[5], cntC(0, r) + it, h->dStats, r ? TRACE_CONT : 0); });
+            timed(tTrace, [&] { WALK_KERNEL(k_trace, gW, L.P, h->S, L.dQ[5], cntC(0, r) + it, wrkC(0, r) + it, L.dQ[4], cntA(0, r + 1) + it, h->dStats, h->refillThreshold, h->postponeShift, 1); });
+          }
+          timed(tAnyHit, [&] { k_alpha<false><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], cntA(0, R) + it, nullptr, nullptr, h->dStats, TRACE_CONT); });
         }
         const uint32_t* qShade = qT;
         if(h->sortShade && h->S.numMaterials + 1 <= kSortMaxBuckets)
@@ -4363,12 +4376,15 @@ static int launchFrames(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
           else
             k_shade<FEAT_ALL><<<gS, SHADE_BLOCK, 2048, st>>>(L.P, h->S, F, qShade, &cntTrace[it], L.dQ[2], &cntPost[it], L.dQ[3], &cntShadow[it], qN, &cntTrace[it + 1], h->dStats);
         });
-        timed(tPost, [&] { WALK_KERNEL(k_shadow, gW, L.P, h->S, L.dQ[3], &cntShadow[it], &workPost[it], L.dQ[4], &cntAlphaS[it], h->dStats, h->refillThreshold, h->postponeShift, 0); });
+        timed(tPost, [&] { WALK_KERNEL(k_shadow, gW, L.P, h->S, L.dQ[3], &cntShadow[it], &workPost[it], L.dQ[4], cntA(1, 0) + it, h->dStats, h->refillThreshold, h->postponeShift, 0); });
         if(h->S.hasAlpha)
         {
-          timed(tAnyHit, [&] { k_alpha<true><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS[it], L.dQ[5], &cntContS[it], h->dStats, 0); });
-          timed(tPost, [&] { WALK_KERNEL(k_shadow, gW, L.P, h->S, L.dQ[5], &cntContS[it], &workContS[it], L.dQ[4], &cntAlphaS1[it], h->dStats, h->refillThreshold, h->postponeShift, 1); });
-          timed(tAnyHit, [&] { k_alpha<true><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], &cntAlphaS1[it], nullptr, nullptr, h->dStats, TRACE_CONT); });
+          for(int r = 0; r < R; r++)
+          {
+            timed(tAnyHit, [&] { k_alpha<true><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], cntA(1, r) + it, L.dQ[5], cntC(1, r) + it, h->dStats, r ? TRACE_CONT : 0); });
+            timed(tPost, [&] { WALK_KERNEL(k_shadow, gW, L.P, h->S, L.dQ[5], cntC(1, r) + it, wrkC(1, r) + it, L.dQ[4], cntA(1, r + 1) + it, h->dStats, h->refillThreshold, h->postponeShift, 1); });
+          }
+          timed(tAnyHit, [&] { k_alpha<true><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], cntA(1, R) + it, nullptr, nullptr, h->dStats, TRACE_CONT); });
         }
         timed(tResolve, [&] { k_resolve<<<gridFor(h, 4), 256, 0, st>>>(L.P, h->S, F, L.dQ[2], &cntPost[it], qN, &cntTrace[it + 1], h->dStats); });
         cur = 1 - cur;
