@@ -1759,6 +1759,11 @@ struct b200pt
   // on every bounce -- x 2 rounds 1019.8 / 1022.8, x 3 / 4 / 6 rounds 1011 / 1016 / 1014; 2 candidates (the bound shrinks sooner) x 2 / 3 /
   // 4 / 5 / 6 / 8 rounds 987 / 1012 / 1024 + 1022 / 1016 / 1020 / 1014: the same plateau with more launches
   int                 contRounds = (kCand <= 2) ? 4 : 2;
+  // grids of the continuation rounds after the first: -1 = by wavefront size (quarter-size grids below 8 M path slots), 0 = always full,
+  // 1 = always quarter-size (B200PT_CONT_SMALL_GRID).  Measured at N = 1 (20.7 M slots, r02zj, one box): full 1021.1, quarter 1009.9
+  // Mray/s.  On a 1/8 tile (2.6 M slots, r02fin2_n8 pass B) an almost empty full-size walk launch costs about as much as the round
+  // saves in k_alpha; the quarter-size rule for such tiles follows from that accounting and has NOT been measured at N > 1.
+  int                 contSmallGrid = -1;
   int                 walkGridPerSM = 8, shadeGridPerSM = 2;  // CTAs per SM of the persistent walk / shade grids (B200PT_WALK_GRID, B200PT_SHADE_GRID)
   bool                sortShade = false;
   bool                sortRays = false;   // B200PT_SORT_RAYS=1 (experiment): trace queue bucketed by ray direction octant  // B200PT_SORT_SHADE=1: material-sorted shade queue (measured)
@@ -2344,6 +2349,8 @@ int b200pt_create(b200pt_t** out, int cuda_device)
     h->walkGridPerSM = std::min(std::max(atoi(e), 1), 32);
   if(const char* e = getenv("B200PT_SHADE_GRID"))
     h->shadeGridPerSM = std::min(std::max(atoi(e), 1), 8);
+  if(const char* e = getenv("B200PT_CONT_SMALL_GRID"))
+    h->contSmallGrid = atoi(e) != 0 ? 1 : 0;
   if(const char* e = getenv("B200PT_CONT_ROUNDS"))
     h->contRounds = std::min(std::max(atoi(e), 1), kContRoundsMax);
   if(const char* e = getenv("B200PT_BVH_BUILDER"))
@@ -4333,6 +4340,8 @@ static int launchFrames(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
         // as dense one-thread-per-path kernels (k_alpha, k_resolve) sized by the device-side queue counters
         const int gP = gridFor(h, 8);
         const int  gW = gridFor(h, h->walkGridPerSM);  // persistent walk kernels
+        const bool smallRounds = h->contSmallGrid < 0 ? (F.numPaths < (8u << 20)) : (h->contSmallGrid != 0);
+        const int  gSmall = smallRounds ? gridFor(h, 2) : 0;  // any-hit continuation rounds after the first (0: full grids)
         const bool omm = h->S.bvh.ommRef != nullptr;  // scenes with opacity micromaps run the walk kernels' OMM instantiation
         const int gS = gridFor(h, h->shadeGridPerSM);  // persistent shade kernel (512-thread CTAs, one resident per SM)
         // geometry walks are persistent kernels; the texture-dependent any-hit tests and the path bookkeeping run
@@ -4353,8 +4362,11 @@ static int launchFrames(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
         {
           for(int r = 0; r < R; r++)
           {
-            timed(tAnyHit, [&] { k_alpha<false><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], cntA(0, r) + it, L.dQ[5], cntC(0, r) + it, h->dStats, r ? TRACE_CONT : 0); });
-            timed(tTrace, [&] { WALK_KERNEL(k_trace, gW, L.P, h->S, L.dQ[5], cntC(0, r) + it, wrkC(0, r) + it, L.dQ[4], cntA(0, r + 1) + it, h->dStats, h->refillThreshold, h->postponeShift, 1); });
+            // rounds after the first see the few rays whose candidates were all rejected TWICE (about 1 % of the bounce); on small
+            // wavefronts a quarter-size grid keeps the fixed cost of these extra launches down (see contSmallGrid)
+            const int gPr = (r && gSmall) ? gSmall : gP, gWr = (r && gSmall) ? gSmall : gW;
+            timed(tAnyHit, [&] { k_alpha<false><<<gPr, 128, 2048, st>>>(L.P, h->S, L.dQ[4], cntA(0, r) + it, L.dQ[5], cntC(0, r) + it, h->dStats, r ? TRACE_CONT : 0); });
+            timed(tTrace, [&] { WALK_KERNEL(k_trace, gWr, L.P, h->S, L.dQ[5], cntC(0, r) + it, wrkC(0, r) + it, L.dQ[4], cntA(0, r + 1) + it, h->dStats, h->refillThreshold, h->postponeShift, 1); });
           }
           timed(tAnyHit, [&] { k_alpha<false><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], cntA(0, R) + it, nullptr, nullptr, h->dStats, TRACE_CONT); });
         }
@@ -4381,8 +4393,9 @@ static int launchFrames(b200pt_t* h, const b200pt_frame_info* fi, const b200pt_p
         {
           for(int r = 0; r < R; r++)
           {
-            timed(tAnyHit, [&] { k_alpha<true><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], cntA(1, r) + it, L.dQ[5], cntC(1, r) + it, h->dStats, r ? TRACE_CONT : 0); });
-            timed(tPost, [&] { WALK_KERNEL(k_shadow, gW, L.P, h->S, L.dQ[5], cntC(1, r) + it, wrkC(1, r) + it, L.dQ[4], cntA(1, r + 1) + it, h->dStats, h->refillThreshold, h->postponeShift, 1); });
+            const int gPr = (r && gSmall) ? gSmall : gP, gWr = (r && gSmall) ? gSmall : gW;
+            timed(tAnyHit, [&] { k_alpha<true><<<gPr, 128, 2048, st>>>(L.P, h->S, L.dQ[4], cntA(1, r) + it, L.dQ[5], cntC(1, r) + it, h->dStats, r ? TRACE_CONT : 0); });
+            timed(tPost, [&] { WALK_KERNEL(k_shadow, gWr, L.P, h->S, L.dQ[5], cntC(1, r) + it, wrkC(1, r) + it, L.dQ[4], cntA(1, r + 1) + it, h->dStats, h->refillThreshold, h->postponeShift, 1); });
           }
           timed(tAnyHit, [&] { k_alpha<true><<<gP, 128, 2048, st>>>(L.P, h->S, L.dQ[4], cntA(1, R) + it, nullptr, nullptr, h->dStats, TRACE_CONT); });
         }
