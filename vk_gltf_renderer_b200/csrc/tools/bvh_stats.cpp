@@ -62,7 +62,7 @@ int main(int argc, char** argv)
           for(int b = 24; b < 32; b++) if(him & (1u << b)) g = fminf(g, cur.tn[b - 24]);
           dropGroup = g > best;
         }
-        else if(stale == 3 || stale == 4 || stale == 5)
+        else if(stale == 3)
           dropGroup = cur.gmin > best;
         if(dropGroup) cur.y &= 0x00ffffffu;
         if(drop) cur.y &= ~(1u << cb);
@@ -72,11 +72,10 @@ int main(int argc, char** argv)
         {
           float g = 1e38f;
           for(int b = 24; b < 32; b++) if(cur.y & (1u << b)) g = fminf(g, cur.tn[b - 24]);
-          if(stale <= 3) cur.gmin = g;
+          cur.gmin = g;
           stack[sp++] = cur;
         }
         cur.gmin = -1.f;  // the freshly opened node's own group is tested child by child
-        float gAll = 1e38f, gNode = tmin;
         uint32_t slot = (uint32_t)(cb - 24) ^ ((him >> 8) & 7u);
         uint32_t rel = __builtin_popcount(him & ~(0xffffffffu << slot));
         const float* N = &B.nodes[(size_t)(cur.x + rel) * 20];
@@ -100,11 +99,8 @@ int main(int argc, char** argv)
             float t0 = (dir[a] < 0 ? hi : lo) * ad[a] + ao[a], t1 = (dir[a] < 0 ? lo : hi) * ad[a] + ao[a];
             tn = fmaxf(tn, t0); tf = fminf(tf, t1);
           }
-          if(tn <= tf * 1.000001f) { hm |= childBits << bitIndex; if(inner) cur.tn[bitIndex - 24] = tn; gAll = fminf(gAll, tn); }
+          if(tn <= tf * 1.000001f) { hm |= childBits << bitIndex; if(inner) cur.tn[bitIndex - 24] = tn; }
         }
-        for(int a = 0; a < 3; a++) gNode = fmaxf(gNode, fminf(ao[a], ao[a] + 255.f * ad[a]));
-        if(stale == 4) cur.gmin = gAll;
-        if(stale == 5) cur.gmin = gNode;
         cur.y = (hm & 0xff000000u) | (octInv << 8) | (eim >> 24); tg.y = hm & 0x00ffffffu;
       }
       else { tg = cur; cur = G{0, 0, {0, 0, 0, 0, 0, 0, 0, 0}, 0.f}; }
