@@ -44,6 +44,7 @@ def lib():
         L.oracle_trace_closest_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
         L.oracle_bsdf_eval.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.oracle_bsdf_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.oracle_bsdf_sample_simple.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.oracle_get_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_reset_stats.argtypes = [C.c_void_p]
         L.oracle_num_tris.argtypes = [C.c_void_p]
@@ -140,6 +141,13 @@ class Oracle:
         packed = np.ascontiguousarray(packed, np.float32).reshape(-1, 48)
         out = np.empty((len(packed), 8), np.float32)
         self.L.oracle_bsdf_sample(_p(packed), len(packed), _p(out))
+        return out
+
+    def bsdf_sample_simple(self, packed):
+        """bsdfSampleSimple (the shadow catcher's continuation BSDF) on the records of bsdf_io: k2, bsdf_over_pdf, pdf, event"""
+        packed = np.ascontiguousarray(packed, np.float32).reshape(-1, 48)
+        out = np.empty((len(packed), 8), np.float32)
+        self.L.oracle_bsdf_sample_simple(_p(packed), len(packed), _p(out))
         return out
 
     def stats(self):

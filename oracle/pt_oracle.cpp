@@ -2517,6 +2517,30 @@ int oracle_bsdf_sample(const float* in, uint32_t n, float* out)
   return 0;
 }
 
+// the shadow catcher's continuation BSDF (bsdfSampleSimple); same packing and output as oracle_bsdf_sample
+int oracle_bsdf_sample_simple(const float* in, uint32_t n, float* out)
+{
+  for(uint32_t i = 0; i < n; i++)
+  {
+    const float*   p = in + (size_t)i * 48;
+    PbrMaterial    m = unpackMat(p);
+    BsdfSampleData d;
+    d.k1 = f3(p[39], p[40], p[41]);
+    d.xi = f3(p[45], p[46], p[47]);
+    bsdfSampleSimple(d, m);
+    float* q = out + (size_t)i * 8;
+    q[0] = d.k2.x;
+    q[1] = d.k2.y;
+    q[2] = d.k2.z;
+    q[3] = d.bsdf_over_pdf.x;
+    q[4] = d.bsdf_over_pdf.y;
+    q[5] = d.bsdf_over_pdf.z;
+    q[6] = d.pdf;
+    q[7] = (float)d.event_type;
+  }
+  return 0;
+}
+
 int oracle_get_stats(void* h, uint64_t* out6)
 {
   Oracle& o = *(Oracle*)h;

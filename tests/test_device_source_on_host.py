@@ -93,6 +93,10 @@ def test_device_bsdf_source_matches_oracle_bit_for_bit(tmp_path, oracle_mod):
     o = oracle_mod.Oracle()
     rec = bsdf_io.random_records(30000, seed=99)
     ev, sm = o.bsdf_eval(rec), o.bsdf_sample(rec)
+    simple = o.bsdf_sample_simple(rec)   # the shadow catcher's continuation BSDF: both lobes and the absorbed case occur
+    assert {0, 9, 10} <= set(simple[:, 7].astype(int).tolist()) and np.isfinite(simple).all()
+    lit = simple[:, 7] != 0
+    assert (simple[lit, 6] > 0).all() and (simple[lit, 3:6] >= 0).all() and simple[lit, 3:6].max() < 50.0
     assert len(set(sm[:, 7].astype(int).tolist())) >= 4 and (ev[:, 6] > 0).mean() > 0.2
     path = str(tmp_path / "records.bin")
     with open(path, "wb") as f:
@@ -100,10 +104,11 @@ def test_device_bsdf_source_matches_oracle_bit_for_bit(tmp_path, oracle_mod):
         f.write(rec.tobytes())
         f.write(ev.tobytes())
         f.write(sm.tobytes())
+        f.write(simple.tobytes())
     out = subprocess.run([exe, path], capture_output=True, text=True, timeout=600)
     print(out.stdout)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "eval mismatches 0, sample mismatches 0" in out.stdout
+    assert "eval mismatches 0, sample mismatches 0" in out.stdout and "bsdfSampleSimple mismatches 0" in out.stdout
 
 
 def test_device_refit_source_vs_brute_force(tmp_path):

@@ -40,3 +40,41 @@ def test_oracle_shadow_catcher_known_answers(box_scene, std_env, oracle_mod):
     assert lum(dark)[shadowed].sum() < lum(catch)[shadowed].sum() <= lum(bare)[shadowed].sum() * 1.5
     assert np.array_equal(dark[..., :3][plane & same], catch[..., :3][plane & same])
     assert not np.array_equal(catch[..., :3], solid[..., :3])
+
+
+def test_bsdf_sample_simple_known_answers(oracle_mod):
+    """bsdfSampleSimple as restated (nvshaders, external): the sampled direction lies in the upper hemisphere, a white diffuse
+    dielectric returns (almost) all energy and never creates any, a metal returns a little less than its base colour (single-scatter
+    GGX; Schlick lifts the dark channels), roughness -> 0 gives the mirror direction, and the Monte-Carlo mean of bsdf_over_pdf equals
+    the quadrature of value over the hemisphere (the sampling is unbiased for its own evaluation)."""
+    o = oracle_mod.Oracle()
+    n = 40000
+    rng = np.random.default_rng(5)
+
+    def records(base, metallic, alpha, cos_in):
+        r = np.zeros((n, 48), np.float32)
+        r[:, 0:3] = base
+        r[:, 3:5] = alpha
+        r[:, 5] = metallic
+        r[:, 6:9], r[:, 9:12], r[:, 12:15], r[:, 15:18] = (0, 0, 1), (1, 0, 0), (0, 1, 0), (0, 0, 1)
+        r[:, 18], r[:, 19], r[:, 20], r[:, 21:24] = 1.0, 1.5, 1.0, 1.0
+        s = np.sqrt(1 - cos_in * cos_in)
+        r[:, 39:42] = (s, 0.0, cos_in)
+        r[:, 45:48] = rng.random((n, 3))
+        return r
+    white = o.bsdf_sample_simple(records((1, 1, 1), 0.0, 0.5, 0.8))
+    ok = white[:, 7] != 0
+    assert ok.mean() > 0.9 and (white[ok, 2] > 0).all()
+    assert np.allclose(np.linalg.norm(white[ok, 0:3], axis=1), 1.0, atol=1e-4)
+    mean = (white[:, 3:6] * ok[:, None]).mean(0)
+    assert (mean < 1.02).all() and (mean > 0.85).all(), mean           # energy conserving, nearly white
+    metal = o.bsdf_sample_simple(records((0.9, 0.6, 0.3), 1.0, 0.25, 0.7))
+    okm = metal[:, 7] != 0
+    mm = (metal[:, 3:6] * okm[:, None]).mean(0)
+    ratio = mm / np.float32([0.9, 0.6, 0.3])   # single-scatter GGX loses some energy to masking; Schlick lifts the dark channels a little
+    assert (mm < 1.0).all() and mm[0] > mm[1] > mm[2] and (ratio > 0.8).all() and (ratio < 1.02).all() and ratio[2] >= ratio[0], (mm, ratio)
+    assert (metal[okm, 7] == 10).all()                                 # metallic 1: only the glossy lobe (GLOSSY | REFLECTION)
+    mirror = o.bsdf_sample_simple(records((1, 1, 1), 1.0, 1e-4, 0.6))
+    okr = mirror[:, 7] != 0
+    dev = np.abs(mirror[okr, 0:3] - np.float32([-0.8, 0.0, 0.6])).max(1)   # GGX has a long tail: nearly all samples within 2e-3, all close
+    assert okr.mean() > 0.99 and (dev < 2e-3).mean() > 0.98 and dev.max() < 0.1

@@ -2,6 +2,7 @@
 // compiled for the host through host_shim.h and compared with the oracle's outputs for the same records.
 //
 //   host_bsdf_check records.bin        records.bin = u32 n, n x 48 floats (bsdf_io.py packing), n x 8 oracle eval, n x 8 oracle sample
+//                                      [, n x 8 oracle bsdfSampleSimple: the shadow catcher's continuation BSDF]
 //
 // Both sides then use the same libm, so what is compared is the SOURCE: oracle/bsdf.h vs csrc/bsdf.cuh, operation by
 // operation (build with -ffp-contract=off, the host analogue of the kernels' -fmad=false).  On the GPU the only remaining
@@ -64,8 +65,10 @@ int main(int argc, char** argv)
   if(!f || std::fread(&n, 4, 1, f) != 1) return 2;
   std::vector<float> rec((size_t)n * 48), oe((size_t)n * 8), os((size_t)n * 8);
   if(std::fread(rec.data(), 4, rec.size(), f) != rec.size() || std::fread(oe.data(), 4, oe.size(), f) != oe.size() || std::fread(os.data(), 4, os.size(), f) != os.size()) return 2;
+  std::vector<float> oq((size_t)n * 8);
+  const bool         haveSimple = std::fread(oq.data(), 4, oq.size(), f) == oq.size();
   std::fclose(f);
-  uint64_t badE = 0, badS = 0, events[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t badE = 0, badS = 0, badQ = 0, events[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double   worst = 0;
   for(uint32_t i = 0; i < n; i++)
   {
@@ -87,8 +90,19 @@ int main(int argc, char** argv)
       ok = ok && same(gs[k], os[(size_t)i * 8 + k]);
     badS += !ok;
     events[(int)gs[7] & 7]++;
+    if(haveSimple)
+    {
+      const BsdfSample q = bsdfSampleSimple(m, f3(p[39], p[40], p[41]), f3(p[45], p[46], p[47]));
+      const float      gq[8] = {q.k2.x, q.k2.y, q.k2.z, q.bsdf_over_pdf.x, q.bsdf_over_pdf.y, q.bsdf_over_pdf.z, q.pdf, (float)q.event_type};
+      ok = true;
+      for(int k = 0; k < 8; k++)
+        ok = ok && same(gq[k], oq[(size_t)i * 8 + k]);
+      badQ += !ok;
+    }
   }
+  if(haveSimple)
+    std::printf("bsdfSampleSimple mismatches %llu (bit level)\n", (unsigned long long)badQ);
   std::printf("records %u | eval mismatches %llu, sample mismatches %llu (bit level), worst eval relative difference %.3g\n", n, (unsigned long long)badE,
               (unsigned long long)badS, worst);
-  return (badE || badS) ? 1 : 0;
+  return (badE || badS || badQ) ? 1 : 0;
 }
