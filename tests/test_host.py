@@ -157,3 +157,28 @@ def test_adaptive_sampling_controller_follows_the_reference_rules():
     pt.ptAdaptiveSampling, pt.ptSamples = False, 4
     pt.updateAdaptiveSampling(res)
     assert pt.ptSamples == 4
+
+
+def test_cpp_blob_writer_round_trip(tmp_path, box_scene, std_env):
+    """host/b2sc_writer.hpp (the scene-blob writer a maintainer drops into the reference loader: it serialises the C-ABI
+    b200pt_scene_desc): a blob written by the Python loader, loaded by the C++ SceneData and written back through
+    the header is byte-identical -- for Box.glb with its environment and for a textured scene that carries opacity micromaps, lights,
+    TEXCOORD_1, tangents and vertex colours."""
+    import os
+    import subprocess
+    from vk_gltf_renderer_b200 import _lib, omm, synth
+    exe = os.path.join(os.path.dirname(_lib.LIB_PATH), "b200pt_headless")
+    if not os.path.exists(exe):
+        pytest.skip("b200pt_headless not built")
+    zoo = synth.synth_material_zoo()
+    zoo.lights = synth.synth_lit().lights
+    atrium = synth.synth_sponza(tex_size=64, detail=0.05)
+    omm.bake_opacity_micromaps(atrium, level=3)
+    assert atrium.prim_omms
+    for name, scn, env in (("box", box_scene, std_env), ("zoo", zoo, None), ("atrium", atrium, None)):
+        a, b = str(tmp_path / (name + "_a.b2sc")), str(tmp_path / (name + "_b.b2sc"))
+        scn.save_blob(a, env)
+        out = subprocess.run([exe, "--scene", a, "--writeBlob", b], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout + out.stderr
+        ra, rb = open(a, "rb").read(), open(b, "rb").read()
+        assert len(ra) == len(rb) and ra == rb, name

@@ -22,6 +22,7 @@
 #include <unistd.h>
 
 #include "b200pt_host.hpp"
+#include "b2sc_writer.hpp"
 
 using namespace b200host;
 
@@ -109,7 +110,7 @@ static std::string convertScene(const std::string& gltf, const std::string& hdrF
 
 int main(int argc, char** argv)
 {
-  std::string scenePath, hdrPath, outPath, rawPath, tmpBlob, tonemappedPath;
+  std::string scenePath, hdrPath, outPath, rawPath, tmpBlob, tonemappedPath, writeBlobPath;
   int         width = 1920, height = 1080, frames = 16, warmupFrames = 1, framesInFlight = 0;  // warm-up: src/benchmarking.hpp:128
   int         adaptiveSampling = 0, frameBatch = 0;
   Resources   res;
@@ -168,6 +169,8 @@ int main(int argc, char** argv)
         res.settings.useOpacityMicromap = std::stoi(next()) != 0;
       else if(a == "--out")
         outPath = next();
+      else if(a == "--writeBlob")
+        writeBlobPath = next();  // re-serialise the loaded scene with host/b2sc_writer.hpp and exit (no GPU needed: round-trip check)
       else if(a == "--output" || a == "--screenshot")
         tonemappedPath = next();  // the reference's headless output image (src/renderer.cpp:171, 557-573; benchmarking.cpp:144-153)
       else if(a == "--tonemapMethod")
@@ -213,6 +216,18 @@ int main(int argc, char** argv)
     scene.load(scenePath);
     if(!tmpBlob.empty())
       unlink(tmpBlob.c_str());
+    if(!writeBlobPath.empty())
+    {
+      BlobCamera bc;
+      bc.orthographic = scene.camera.orthographic ? 1u : 0u;
+      std::memcpy(bc.eye, scene.camera.eye, 12), std::memcpy(bc.center, scene.camera.center, 12), std::memcpy(bc.up, scene.camera.up, 12);
+      bc.yfov = scene.camera.yfov, bc.znear = scene.camera.znear, bc.zfar = scene.camera.zfar, bc.xmag = scene.camera.xmag, bc.ymag = scene.camera.ymag;
+      const b200pt_scene_desc d = scene.desc();
+      writeB2sc(writeBlobPath, d, bc, scene.hdrRgb.empty() ? nullptr : scene.hdrRgb.data(), (uint32_t)scene.hdrWidth, (uint32_t)scene.hdrHeight,
+                scene.micromaps().data(), (uint32_t)scene.micromaps().size(), scene.primitiveOmms().data(), (uint32_t)scene.primitiveOmms().size());
+      std::printf("wrote %s\n", writeBlobPath.c_str());
+      return 0;
+    }
     res.scene = &scene;
     res.camera = scene.camera;
     res.width = width;
