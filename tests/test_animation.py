@@ -186,3 +186,111 @@ def test_rigid_feed_known_answers_and_device_source(tmp_path):
             assert np.array_equal(recs[:, :64].copy().view(np.uint32).reshape(-1, 4, 4), o2w.view(np.uint32))
             assert np.array_equal(recs[:, 64:128].copy().view(np.uint32).reshape(-1, 4, 4), w2o.view(np.uint32))
             assert np.array_equal(recs[:, 128:].copy().view(np.int32), np.array([[m_, p_] for _, m_, p_ in mappings], np.int32))
+
+
+def _write_skinned_gltf(path):
+    """A hand-written asset: a strip of 8 vertices along +y (0..3) skinned to a chain of two joints (joint B at y = 1.5, child of joint A),
+    one morph target (+x bulge) with mesh.weights = [0.25], NORMAL present; joints under an armature node that is translated, the mesh node
+    elsewhere (glTF ignores the skinned mesh node's own transform: inverse(meshWorld) * jointWorld * IBM)."""
+    import json
+    ys = np.repeat(np.linspace(0.0, 3.0, 4), 2)
+    pos = np.stack([np.tile([-0.2, 0.2], 4), ys, np.zeros(8)], 1).astype(np.float32)
+    nrm = np.tile(np.float32([0, 0, 1]), (8, 1))
+    idx = np.uint16([[0, 1, 3], [0, 3, 2], [2, 3, 5], [2, 5, 4], [4, 5, 7], [4, 7, 6]]).reshape(-1)
+    wB = np.clip((ys - 1.0) / 1.0, 0, 1).astype(np.float32)
+    weights = np.stack([1 - wB, wB, np.zeros(8), np.zeros(8)], 1).astype(np.float32)
+    joints = np.tile(np.uint8([0, 1, 0, 0]), (8, 1))
+    delta = np.stack([0.5 * np.sin(ys), np.zeros(8), np.zeros(8)], 1).astype(np.float32)
+    arm = np.eye(4)
+    arm[:3, 3] = [2.0, 0.5, -1.0]
+    jb = np.eye(4)
+    jb[1, 3] = 1.5
+    ibm = np.stack([np.linalg.inv(arm), np.linalg.inv(arm @ jb)]).transpose(0, 2, 1).astype(np.float32)   # glm column-major
+    chunks, views, accessors = [], [], []
+
+    def add(arr, ctype, atype, target=None, minmax=False):
+        raw = np.ascontiguousarray(arr).tobytes()
+        off = sum(len(c) for c in chunks)
+        pad = (-len(raw)) % 4
+        chunks.append(raw + b"\\0" * pad)
+        v = {"buffer": 0, "byteOffset": off, "byteLength": len(raw)}
+        if target:
+            v["target"] = target
+        views.append(v)
+        a = {"bufferView": len(views) - 1, "componentType": ctype, "count": len(arr) if atype != "SCALAR" else int(np.asarray(arr).size), "type": atype}
+        if minmax:
+            a["min"], a["max"] = np.asarray(arr).min(0).tolist(), np.asarray(arr).max(0).tolist()
+        accessors.append(a)
+        return len(accessors) - 1
+    a_pos = add(pos, 5126, "VEC3", 34962, True)
+    a_nrm = add(nrm, 5126, "VEC3", 34962)
+    a_idx = add(idx, 5123, "SCALAR", 34963)
+    a_w = add(weights, 5126, "VEC4", 34962)
+    a_j = add(joints, 5121, "VEC4", 34962)
+    a_d = add(delta, 5126, "VEC3", None, True)
+    a_ibm = add(ibm.reshape(2, 16), 5126, "MAT4")
+    blob = b"".join(chunks)
+    with open(path.replace(".gltf", ".bin"), "wb") as f:
+        f.write(blob)
+    doc = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0, 1]}],
+           "nodes": [{"name": "meshNode", "mesh": 0, "skin": 0, "translation": [7.0, 7.0, 7.0]},
+                     {"name": "armature", "translation": [2.0, 0.5, -1.0], "children": [2]},
+                     {"name": "jointA", "children": [3]},
+                     {"name": "jointB", "translation": [0.0, 1.5, 0.0]}],
+           "meshes": [{"primitives": [{"attributes": {"POSITION": a_pos, "NORMAL": a_nrm, "WEIGHTS_0": a_w, "JOINTS_0": a_j}, "indices": a_idx,
+                                       "targets": [{"POSITION": a_d}], "material": 0}], "weights": [0.25]}],
+           "skins": [{"joints": [2, 3], "inverseBindMatrices": a_ibm}],
+           "materials": [{"pbrMetallicRoughness": {"baseColorFactor": [0.8, 0.7, 0.6, 1.0]}, "doubleSided": True}],
+           "buffers": [{"uri": os.path.basename(path).replace(".gltf", ".bin"), "byteLength": len(blob)}], "bufferViews": views, "accessors": accessors}
+    with open(path, "w") as f:
+        json.dump(doc, f)
+    return pos, delta, weights, arm, jb
+
+
+def test_loader_builds_the_animation_tasks_of_a_skinned_morphed_asset(tmp_path):
+    """load_gltf gathers what AnimationSystem::parseMorphTargets / parseSkinTasks cache (src/gltf_scene_animation.cpp:150-316) and the node
+    graph; animation.tasks_from_scene / frame_inputs turn it into the C-ABI feed.  At the rest pose the joint matrices cancel the inverse
+    bind matrices (the skinned mesh node's own translation drops out) and the deformed mesh is base + 0.25 * target; bending joint B by 90
+    degrees moves the fully B-weighted vertices around B's origin."""
+    from oracle import animation as A
+    from vk_gltf_renderer_b200 import animation as anim, scene
+    path = str(tmp_path / "skinned.gltf")
+    pos, delta, weights, arm, jb = _write_skinned_gltf(path)
+    scn = scene.load_gltf(path)
+    assert len(scn.render_nodes) == 1 and scn.graph["parents"].tolist() == [-1, -1, 1, 2]
+    assert scn.graph["render_nodes"][0][:2] == (0, 0)                       # refNodeID 0, skinID 0
+    morphs, skins = anim.tasks_from_scene(scn)
+    assert len(morphs) == 1 and len(skins) == 1 and skins[0].num_joints == 2 and skins[0].ref_node == 0 and morphs[0].mesh == 0
+    assert np.array_equal(skins[0].weights, weights) and skins[0].joints.dtype == np.int32 and skins[0].joints[:, 1].tolist() == [1] * 8
+    assert morphs[0].base_normals is None                                   # no target moves the normals (:227-247)
+    parents, mappings, inst = anim.node_hierarchy(scn)
+    assert mappings == [(0, 0, 0)] and np.array_equal(inst[0], np.eye(4, dtype=np.float32))
+    order, offsets = anim.topo_levels(parents)
+    assert offsets.tolist() == [0, 2, 3, 4]
+    # rest pose
+    mw, jm, nm = anim.frame_inputs(scn, morphs, skins)
+    assert np.allclose(mw[0], [0.25]) and np.allclose(jm[0][:, :, :], np.stack([np.linalg.inv(scn.graph["locals"][0]).T] * 2), atol=1e-6)
+    ref = scene.load_gltf(path)
+    A.apply(ref, morphs, skins, mw, jm, nm)
+    mesh_inv = np.linalg.inv(scn.graph["locals"][0])
+    expect = (pos + np.float32(0.25) * delta).astype(np.float64) @ mesh_inv[:3, :3].T + mesh_inv[:3, 3]
+    assert np.allclose(ref.render_prims[0]["positions"], expect, atol=1e-5)
+    # the render node's world matrix puts it back: world position = base + 0.25 * delta, whatever the mesh node's translation is
+    o2w = np.asarray(ref.render_nodes[0]["objectToWorld"], np.float64).reshape(4, 4).T
+    world_pos = ref.render_prims[0]["positions"].astype(np.float64) @ o2w[:3, :3].T + o2w[:3, 3]
+    assert np.allclose(world_pos, pos + 0.25 * delta, atol=1e-5)
+    # bend joint B by 90 degrees about z
+    locals_ = scn.graph["locals"].copy()
+    rz = np.array([[0, -1, 0, 0], [1, 0, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1.0]])
+    locals_[3] = jb @ rz
+    mw, jm, nm = anim.frame_inputs(scn, morphs, skins, locals_, mesh_weights={0: [0.0]})
+    bent = scene.load_gltf(path)
+    A.apply(bent, morphs, skins, mw, jm, nm)
+    world_pos = bent.render_prims[0]["positions"].astype(np.float64) @ o2w[:3, :3].T + o2w[:3, 3]
+    top = weights[:, 1] == 1.0                                              # vertices fully on joint B
+    # world = jointWorld_new * IBM * p = T(a) T(b) Rz T(-b) T(-a) p: a rotation about joint B's bind-pose origin a + b
+    pivot = (arm @ jb)[:3, 3]
+    assert np.allclose(world_pos[top], pivot + (pos[top] - pivot) @ rz[:3, :3].T, atol=1e-5)
+    assert np.allclose(world_pos[weights[:, 0] == 1.0], pos[weights[:, 0] == 1.0], atol=1e-5)   # joint A's vertices stay
+    n = bent.render_prims[0]["normals"]
+    assert np.allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-6)

@@ -21,6 +21,7 @@ class MorphTask:
     base_tangents: Optional[np.ndarray] = None
     normal_deltas: Optional[np.ndarray] = None
     tangent_deltas: Optional[np.ndarray] = None
+    mesh: int = -1       # glTF mesh whose `weights` drive the targets (cmdUpdateAnimation :440-458)
 
 
 @dataclass
@@ -34,6 +35,8 @@ class SkinTask:
     num_joints: int
     base_normals: Optional[np.ndarray] = None
     base_tangents: Optional[np.ndarray] = None
+    skin: int = -1       # glTF skin index (SkinTask::skinID) and the mesh node the joints are expressed against (refNodeID)
+    ref_node: int = -1
 
 
 def joint_matrices(node_world, joint_nodes, inverse_bind, ref_node):
@@ -76,3 +79,70 @@ def topo_levels(parents):
     counts = np.bincount(depth, minlength=int(depth.max()) + 1)
     offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint32)
     return order, offsets
+
+
+# ---- what the loader's scene graph yields (vk_gltf_renderer_b200.scene.load_gltf fills Scene.graph / morph_prims / skin_prims) ----------
+def tasks_from_scene(scn):
+    """AnimationSystem::parseMorphTargets / parseSkinTasks (src/gltf_scene_animation.cpp:150-262, 270-316): one MorphTask per render
+    primitive with morph targets (base normals / tangents only when a target moves them), one SkinTask per UNIQUE skinned render
+    primitive (first render node wins), with the static base arrays taken from the primitive as loaded."""
+    morphs, skins = [], []
+    for pid, mp in sorted(scn.morph_prims.items()):
+        prim = scn.render_prims[pid]
+        morphs.append(MorphTask(pid, prim["positions"].copy(), mp["position_deltas"], mesh=mp["mesh"],
+                                base_normals=prim["normals"].copy() if (mp["normal_deltas"] is not None and prim["normals"] is not None) else None,
+                                base_tangents=prim["tangents"].copy() if (mp["tangent_deltas"] is not None and prim["tangents"] is not None) else None,
+                                normal_deltas=mp["normal_deltas"], tangent_deltas=mp["tangent_deltas"]))
+    seen = set()
+    for rn, (node_id, skin_id, _) in zip(scn.render_nodes, scn.graph["render_nodes"] if scn.graph else []):
+        pid = rn["renderPrimID"]
+        if skin_id < 0 or pid in seen or pid not in scn.skin_prims or skin_id >= len(scn.graph["skins"]):
+            continue
+        seen.add(pid)
+        prim, sp = scn.render_prims[pid], scn.skin_prims[pid]
+        skins.append(SkinTask(pid, prim["positions"].copy(), sp["weights"], sp["joints"], len(scn.graph["skins"][skin_id]["joints"]),
+                              base_normals=None if prim["normals"] is None else prim["normals"].copy(),
+                              base_tangents=None if prim["tangents"] is None else prim["tangents"].copy(), skin=skin_id, ref_node=node_id))
+    return morphs, skins
+
+
+def node_hierarchy(scn):
+    """(parents, RenderNodeGpuMapping triples, instance matrices [R,4,4] glm-ordered) for PathTracer.set_node_hierarchy"""
+    g = scn.graph
+    mappings = [(node_id, rn["materialID"], rn["renderPrimID"]) for rn, (node_id, _, _) in zip(scn.render_nodes, g["render_nodes"])]
+    inst = np.ascontiguousarray(np.asarray([lm for _, _, lm in g["render_nodes"]], np.float64).reshape(-1, 4, 4).transpose(0, 2, 1).astype(np.float32))
+    return g["parents"], mappings, inst
+
+
+def world_matrices(parents, locals_):
+    """fp64 world matrices of the node graph (the host's view; the device propagates its own in fp32)"""
+    locals_ = np.asarray(locals_, np.float64)
+    world = [None] * len(parents)
+
+    def get(n):
+        if world[n] is None:
+            world[n] = locals_[n] if parents[n] < 0 else get(int(parents[n])) @ locals_[n]
+        return world[n]
+    return np.asarray([get(n) for n in range(len(parents))])
+
+
+def frame_inputs(scn, morph_tasks, skin_tasks, locals_=None, mesh_weights=None):
+    """The per-frame data of one cmdUpdateAnimation (src/gltf_scene_animation_vk.cpp:430-494) for the given node-local matrices
+    (default: the asset's rest pose) and mesh weights (default: mesh.weights): morph weights per morph task, joint / normal matrices per
+    skin task.  (Sampling animation channels into those locals / weights is the reference's AnimationSystem and stays out of scope.)"""
+    g = scn.graph
+    world = world_matrices(g["parents"], g["locals"] if locals_ is None else locals_)
+    weights = []
+    for t in morph_tasks:
+        w = (mesh_weights or {}).get(t.mesh, g["mesh_weights"].get(t.mesh, np.zeros(0, np.float32)))
+        full = np.zeros(t.position_deltas.shape[0], np.float32)          # fewer weights than targets: the rest stay 0 (:446-452)
+        full[:min(len(w), len(full))] = np.asarray(w, np.float32)[:len(full)]
+        weights.append(full)
+    jms, nms = [], []
+    for t in skin_tasks:
+        sk = g["skins"][t.skin]
+        ibm = [] if sk["ibm"] is None else list(sk["ibm"])
+        jm, nm = joint_matrices(world, sk["joints"], ibm, t.ref_node)
+        jms.append(jm)
+        nms.append(nm)
+    return weights, jms, nms

@@ -57,6 +57,11 @@ class Scene:
         self.micromaps = []           # list of dict(data u8[N], triangles abi.MICROMAP_TRIANGLE_DTYPE[M])
         self.prim_omms = []           # list of dict(renderPrimID, micromap, baseTriangle, indices i32[T] | None)
         self.camera = None
+        # animation inputs the loader gathers like AnimationSystem::parseMorphTargets / parseSkinTasks (src/gltf_scene_animation.cpp:150-330)
+        # and the node graph the GPU transform path consumes; None for scenes built by hand
+        self.graph = None             # dict(parents i32[N], locals f64[N,4,4], render_nodes [(nodeID, skinID, instLocal f64[4,4])], skins [dict(joints, ibm)], mesh_weights {mesh: f32[T]})
+        self.morph_prims = {}         # renderPrimID -> dict(mesh, position_deltas f32[T,V,3], normal_deltas | None, tangent_deltas | None)
+        self.skin_prims = {}          # renderPrimID -> dict(joints i32[V,4], weights f32[V,4])
         self._keep = []
 
     # -- bounds (reference: Scene::getSceneBounds, gltf_scene.cpp:2303-2336, from transformed vertices)
@@ -662,9 +667,12 @@ def load_gltf(path):
     prim_map = {}
 
     def prim_key(p):
-        return " ".join(f"{k}:{v}" for k, v in sorted(p["attributes"].items())) + f" indices:{p.get('indices', -1)}"
+        key = " ".join(f"{k}:{v}" for k, v in sorted(p["attributes"].items())) + f" indices:{p.get('indices', -1)}"
+        for t in p.get("targets", []):
+            key += " target:" + ",".join(f"{k}:{v}" for k, v in sorted(t.items()))
+        return key
 
-    for mesh in j.get("meshes", []):
+    for mesh_id, mesh in enumerate(j.get("meshes", [])):
         for p in mesh["primitives"]:
             if p.get("mode", 4) != 4:
                 continue
@@ -691,6 +699,18 @@ def load_gltf(path):
                 uv1=g.accessor(at["TEXCOORD_1"]) if "TEXCOORD_1" in at else None,
                 tangents=g.accessor(at["TANGENT"]) if "TANGENT" in at else None,
                 colors=colors)
+            pid = prim_map[key]
+            # morph targets (parseMorphTargets, gltf_scene_animation.cpp:150-262) and skin attributes (parseSkinTasks, :270-316)
+            targets = p.get("targets", [])
+            if targets and all("POSITION" in t for t in targets):
+                def stack(name):
+                    if not any(name in t for t in targets):
+                        return None
+                    return np.stack([g.accessor(t[name]).astype(np.float32)[:, :3] if name in t else np.zeros((len(pos), 3), np.float32) for t in targets])
+                scn.morph_prims[pid] = dict(mesh=mesh_id, position_deltas=stack("POSITION"), normal_deltas=stack("NORMAL"), tangent_deltas=stack("TANGENT"))
+            if "JOINTS_0" in at and "WEIGHTS_0" in at:
+                scn.skin_prims[pid] = dict(joints=g.accessor(at["JOINTS_0"], normalize=False).astype(np.int32).reshape(-1, 4),
+                                           weights=g.accessor(at["WEIGHTS_0"]).astype(np.float32).reshape(-1, 4))
 
     # ---- EXT_mesh_opacity_micromap (SceneOmm::create, src/gltf_scene_omm.cpp:140-391): root micromaps[] + per-primitive linkage.
     # Malformed entries are skipped with the reference's rules (missing required field, bad bufferView, misaligned usage arrays,
@@ -744,6 +764,19 @@ def load_gltf(path):
     scene_id = j.get("scene", 0)
     cam_found = []
 
+    parents = np.full(len(nodes), -1, np.int32)
+    for nid, node in enumerate(nodes):
+        for c in node.get("children", []):
+            parents[c] = nid
+    skins = []
+    for sk in j.get("skins", []):
+        ibm = None
+        if "inverseBindMatrices" in sk:
+            ibm = g.accessor(sk["inverseBindMatrices"]).astype(np.float64).reshape(-1, 4, 4).transpose(0, 2, 1)   # glm column-major -> (row, col)
+        skins.append(dict(joints=list(sk.get("joints", [])), ibm=ibm))
+    scn.graph = dict(parents=parents, locals=np.asarray([_node_matrix(n) for n in nodes], np.float64).reshape(-1, 4, 4), render_nodes=[], skins=skins,
+                     mesh_weights={m: np.asarray(mesh.get("weights", []), np.float32) for m, mesh in enumerate(j.get("meshes", []))})
+
     def visit(nid, parent):
         node = nodes[nid]
         world = parent @ _node_matrix(node)
@@ -787,6 +820,7 @@ def load_gltf(path):
                     continue
                 for lm in locals_:
                     scn.add_node(prim_map[prim_key(p)], p.get("material", -1), world @ lm, visible)
+                    scn.graph["render_nodes"].append((nid, node.get("skin", -1), np.asarray(lm, np.float64)))   # RenderNode::refNodeID / skinID
         for c in node.get("children", []):
             visit(c, world)
 
