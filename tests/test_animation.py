@@ -229,6 +229,15 @@ def _write_skinned_gltf(path):
     a_j = add(joints, 5121, "VEC4", 34962)
     a_d = add(delta, 5126, "VEC3", None, True)
     a_ibm = add(ibm.reshape(2, 16), 5126, "MAT4")
+    # one animation: jointB rotates 0 -> 90 degrees about z (LINEAR), the mesh weights go 0.25 -> 1 (LINEAR), the armature translates
+    # along a Hermite spline (CUBICSPLINE: in-tangent, value, out-tangent per key), jointA's scale steps (STEP)
+    h = np.float32(np.sqrt(0.5))
+    a_t2 = add(np.float32([0.0, 1.0]), 5126, "SCALAR", None, True)
+    a_rot = add(np.float32([[0, 0, 0, 1], [0, 0, h, h]]), 5126, "VEC4")
+    a_wgt = add(np.float32([0.25, 1.0]), 5126, "SCALAR")
+    a_spl = add(np.float32([[0, 0, 0], [2.0, 0.5, -1.0], [1, 0, 0], [0, 2, 0], [2.0, 1.5, -1.0], [0, 0, 0]]), 5126, "VEC3")
+    a_t3 = add(np.float32([0.0, 0.5, 1.0]), 5126, "SCALAR", None, True)
+    a_scl = add(np.float32([[1, 1, 1], [1, 2, 1], [1, 3, 1]]), 5126, "VEC3")
     blob = b"".join(chunks)
     with open(path.replace(".gltf", ".bin"), "wb") as f:
         f.write(blob)
@@ -240,6 +249,12 @@ def _write_skinned_gltf(path):
            "meshes": [{"primitives": [{"attributes": {"POSITION": a_pos, "NORMAL": a_nrm, "WEIGHTS_0": a_w, "JOINTS_0": a_j}, "indices": a_idx,
                                        "targets": [{"POSITION": a_d}], "material": 0}], "weights": [0.25]}],
            "skins": [{"joints": [2, 3], "inverseBindMatrices": a_ibm}],
+           "animations": [{"name": "bend", "samplers": [{"input": a_t2, "output": a_rot, "interpolation": "LINEAR"}, {"input": a_t2, "output": a_wgt},
+                                                         {"input": a_t2, "output": a_spl, "interpolation": "CUBICSPLINE"},
+                                                         {"input": a_t3, "output": a_scl, "interpolation": "STEP"}],
+                           "channels": [{"sampler": 0, "target": {"node": 3, "path": "rotation"}}, {"sampler": 1, "target": {"node": 0, "path": "weights"}},
+                                        {"sampler": 2, "target": {"node": 1, "path": "translation"}}, {"sampler": 3, "target": {"node": 2, "path": "scale"}},
+                                        {"sampler": 0, "target": {"node": 3, "path": "pointer"}}]}],
            "materials": [{"pbrMetallicRoughness": {"baseColorFactor": [0.8, 0.7, 0.6, 1.0]}, "doubleSided": True}],
            "buffers": [{"uri": os.path.basename(path).replace(".gltf", ".bin"), "byteLength": len(blob)}], "bufferViews": views, "accessors": accessors}
     with open(path, "w") as f:
@@ -294,3 +309,40 @@ def test_loader_builds_the_animation_tasks_of_a_skinned_morphed_asset(tmp_path):
     assert np.allclose(world_pos[weights[:, 0] == 1.0], pos[weights[:, 0] == 1.0], atol=1e-5)   # joint A's vertices stay
     n = bent.render_prims[0]["normals"]
     assert np.allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-6)
+
+
+def test_animation_sampler_feeds_the_tasks(tmp_path):
+    """animation.sample_animation (AnimationSystem::updateAnimation / processAnimationChannel, src/gltf_scene_animation.cpp:352-688): LINEAR
+    slerp / lerp, STEP, CUBICSPLINE with the glTF Hermite basis, weights channels, times outside a sampler's range leave the node alone;
+    its locals and mesh weights drive frame_inputs, and the oracle's skinning then puts the fully B-weighted vertices where a 45 degree
+    bend about the moved joint puts them."""
+    from oracle import animation as A
+    from vk_gltf_renderer_b200 import animation as anim, scene
+    path = str(tmp_path / "skinned.gltf")
+    pos, delta, weights, arm, jb = _write_skinned_gltf(path)
+    scn = scene.load_gltf(path)
+    assert len(scn.graph["animations"]) == 1 and len(scn.graph["animations"][0]["channels"]) == 5
+    rest, w_rest = anim.sample_animation(scn, 0, -1.0)                     # before the first key: nothing is animated
+    assert np.array_equal(rest, scn.graph["locals"]) and np.allclose(w_rest[0], [0.25])
+    loc, w = anim.sample_animation(scn, 0, 0.5)
+    c = np.cos(np.pi / 4)
+    assert np.allclose(loc[3][:3, :3], [[c, -c, 0], [c, c, 0], [0, 0, 1]], atol=1e-6) and np.allclose(loc[3][:3, 3], [0, 1.5, 0])   # slerp half way
+    assert np.allclose(w[0], [0.625])
+    # Hermite: p(t) = (2t^3 - 3t^2 + 1) p0 + dt (t^3 - 2t^2 + t) b0 + (-2t^3 + 3t^2) p1 + dt (t^3 - t^2) a1 at t = 0.5, dt = 1
+    p0, b0, a1, p1 = np.float64([2, 0.5, -1]), np.float64([1, 0, 0]), np.float64([0, 2, 0]), np.float64([2, 1.5, -1])
+    assert np.allclose(loc[1][:3, 3], 0.5 * p0 + 0.125 * b0 + 0.5 * p1 - 0.125 * a1, atol=1e-6)
+    assert np.allclose(np.diag(loc[2])[:3], [1, 2, 1])                      # STEP: the key at 0.5 holds until 1.0
+    assert np.allclose(np.diag(anim.sample_animation(scn, 0, 0.49)[0][2])[:3], [1, 1, 1])
+    late, _ = anim.sample_animation(scn, 0, 2.0)                            # past the last key: outside every range
+    assert np.array_equal(late, scn.graph["locals"])
+    # through the feed: joint B bent by 45 degrees about its (moved, stretched) origin
+    morphs, skins = anim.tasks_from_scene(scn)
+    mw, jm, nm = anim.frame_inputs(scn, morphs, skins, loc, {0: np.zeros(1, np.float32)})
+    bent = scene.load_gltf(path)
+    A.apply(bent, morphs, skins, mw, jm, nm)
+    o2w = np.asarray(bent.render_nodes[0]["objectToWorld"], np.float64).reshape(4, 4).T
+    world_pos = bent.render_prims[0]["positions"].astype(np.float64) @ o2w[:3, :3].T + o2w[:3, 3]
+    world = anim.world_matrices(scn.graph["parents"], loc)
+    top = weights[:, 1] == 1.0
+    expect = (np.c_[pos[top], np.ones(top.sum())] @ (world[3] @ np.linalg.inv(arm @ jb)).T)[:, :3]
+    assert np.allclose(world_pos[top], expect, atol=1e-5)

@@ -146,3 +146,92 @@ def frame_inputs(scn, morph_tasks, skin_tasks, locals_=None, mesh_weights=None):
         jms.append(jm)
         nms.append(nm)
     return weights, jms, nms
+
+
+# ---- the caller of the feed: sampling an animation into node-local matrices and mesh weights ---------------------------------------
+def _slerp(q1, q2, t):
+    """glm::slerp(x, y, a) on (x, y, z, w) quaternions: shortest path, linear blend when the two are (nearly) parallel"""
+    q1, q2 = np.asarray(q1, np.float64), np.asarray(q2, np.float64)
+    c = float(np.dot(q1, q2))
+    if c < 0.0:
+        q2, c = -q2, -c
+    if c > 1.0 - 1.1920929e-07:
+        return q1 + (q2 - q1) * t
+    ang = np.arccos(c)
+    return (np.sin((1.0 - t) * ang) * q1 + np.sin(t * ang) * q2) / np.sin(ang)
+
+
+def _cubic(values, t, key_delta, index):
+    """computeCubicInterpolation (src/gltf_scene_animation.cpp:498-517): glTF Hermite spline over [in-tangent, value, out-tangent] triplets"""
+    t2, t3 = t * t, t * t * t
+    c_v1 = -2 * t3 + 3 * t2
+    c_v0 = 1 - c_v1
+    c_a = key_delta * (t3 - t2)
+    c_b = key_delta * (t3 - 2 * t2 + t)
+    prev, nxt = index * 3, (index + 1) * 3
+    return values[prev + 1] * c_v0 + values[nxt + 0] * c_a + values[prev + 2] * c_b + values[nxt + 1] * c_v1
+
+
+def sample_animation(scn, animation=0, time=0.0):
+    """AnimationSystem::updateAnimation / processAnimationChannel (src/gltf_scene_animation.cpp:352-479) evaluated from the asset's rest
+    pose: every translation / rotation / scale / weights channel whose keyframe range contains `time` overwrites its node's value --
+    LINEAR (slerp for rotations, :530-583), STEP (:598-628; weights are left alone there) and CUBICSPLINE (:640-688; rotation
+    re-normalised) -- then the node-local matrices are rebuilt (T * R * S; a node given as a matrix and not animated keeps it).
+    KHR_animation_pointer channels belong to the material / light side of the reference and are not part of this feed.
+    Returns (locals f64 [N, 4, 4], mesh_weights {mesh: f32[T]}) for frame_inputs / PathTracer.update_node_matrices."""
+    from .scene import _trs
+    g = scn.graph
+    trs = [dict(t) for t in g["trs"]]
+    weights = {m: w.copy() for m, w in g["mesh_weights"].items()}
+    animated = set()
+    if 0 <= animation < len(g["animations"]):
+        an = g["animations"][animation]
+        for ch in an["channels"]:
+            node, path = ch["node"], ch["path"]
+            if not (0 <= node < len(trs)) or path not in ("translation", "rotation", "scale", "weights"):
+                continue
+            sm = an["samplers"][ch["sampler"]]
+            inp = sm["inputs"]
+            if len(inp) < 2:
+                continue
+            k = int(np.searchsorted(inp, np.float32(time), side="right"))     # first key strictly after `time`
+            if k == 0:
+                continue
+            i = min(k - 1, len(inp) - 2)
+            t0, t1 = float(inp[i]), float(inp[i + 1])
+            if time < t0 or time > t1:
+                continue
+            dt = t1 - t0
+            f = 0.0 if abs(dt) < 1.1920929e-07 else min(max((time - t0) / dt, 0.0), 1.0)
+            out = sm["outputs"]
+            mode = sm["interpolation"]
+            if path == "weights":
+                mesh = trs[node]["mesh"]
+                if mesh < 0 or mode != "LINEAR":
+                    continue
+                nt = out.size // len(inp)
+                o = out.reshape(len(inp), nt)
+                weights[mesh] = ((1.0 - f) * o[i] + f * o[i + 1]).astype(np.float32)
+                continue
+            o = out.reshape(-1, 4 if path == "rotation" else 3).astype(np.float64)
+            if mode == "STEP":
+                v = o[i]
+            elif mode == "CUBICSPLINE":
+                if len(o) <= (i + 1) * 3 + 1:
+                    continue
+                v = _cubic(o, f, dt, i)
+                if path == "rotation":
+                    v = v / np.linalg.norm(v)
+            else:
+                if path == "rotation":
+                    v = _slerp(o[i], o[i + 1], f)
+                    v = v / np.linalg.norm(v)
+                else:
+                    v = (1.0 - f) * o[i] + f * o[i + 1]
+            trs[node][path] = v.tolist()
+            animated.add(node)
+    locals_ = g["locals"].copy()
+    for n in animated:
+        t = trs[n]
+        locals_[n] = _trs(np.asarray(t["translation"], np.float64), np.asarray(t["rotation"], np.float64), np.asarray(t["scale"], np.float64))
+    return locals_, weights

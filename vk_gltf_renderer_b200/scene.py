@@ -774,8 +774,19 @@ def load_gltf(path):
         if "inverseBindMatrices" in sk:
             ibm = g.accessor(sk["inverseBindMatrices"]).astype(np.float64).reshape(-1, 4, 4).transpose(0, 2, 1)   # glm column-major -> (row, col)
         skins.append(dict(joints=list(sk.get("joints", [])), ibm=ibm))
+    # animations as AnimationSystem::parseAnimations caches them: per sampler the key times, the decoded outputs and the interpolation
+    animations = []
+    for an in j.get("animations", []):
+        samplers = []
+        for sm in an.get("samplers", []):
+            samplers.append(dict(inputs=g.accessor(sm["input"]).astype(np.float32).reshape(-1), outputs=g.accessor(sm["output"]).astype(np.float32),
+                                 interpolation=sm.get("interpolation", "LINEAR")))
+        channels = [dict(node=ch.get("target", {}).get("node", -1), path=ch.get("target", {}).get("path", ""), sampler=ch["sampler"]) for ch in an.get("channels", [])]
+        animations.append(dict(name=an.get("name", ""), samplers=samplers, channels=channels))
     scn.graph = dict(parents=parents, locals=np.asarray([_node_matrix(n) for n in nodes], np.float64).reshape(-1, 4, 4), render_nodes=[], skins=skins,
-                     mesh_weights={m: np.asarray(mesh.get("weights", []), np.float32) for m, mesh in enumerate(j.get("meshes", []))})
+                     mesh_weights={m: np.asarray(mesh.get("weights", []), np.float32) for m, mesh in enumerate(j.get("meshes", []))},
+                     trs=[dict(matrix=n.get("matrix"), translation=n.get("translation", [0, 0, 0]), rotation=n.get("rotation", [0, 0, 0, 1]),
+                               scale=n.get("scale", [1, 1, 1]), mesh=n.get("mesh", -1)) for n in nodes], animations=animations)
 
     def visit(nid, parent):
         node = nodes[nid]
