@@ -9,6 +9,13 @@
 //                      any-hit transmission        raytracer_interface.h.slang:149-179   -> k_alpha<true> (dense)
 //   NEE add + RR + depth++ (pathTrace tail)        gltf_pathtrace.slang:462-485          -> k_resolve
 //   accumulation                                   gltf_pathtrace.slang:582-630          -> k_accumulate
+//   shadow catcher (handleShadowCatcher)           pathtrace_functions.h.slang:499-554   -> k_shade (light sample) + shadow kernels + finishPost
+//   eOptixAlbedoNormal guide image                 gltf_pathtrace.slang:240-263,653-670  -> capture in k_shade, k_guide
+// Next to the frame path (SURVEY.md section 8 f):
+//   morph.comp / skinning.comp                     shaders/*.comp.slang                  -> k_morph, k_skin, k_regather_shade (animate.cuh)
+//   world_matrix_propagate / update_render_instances                                     -> k_propagate_level, k_update_render_nodes
+//   BLAS / TLAS build and update                   src/gltf_scene_rtx.cpp:173-503        -> k_lbvh_* (lbvh.cuh), k_refit_* (refit.cuh)
+//   GltfRenderer::tonemap                          src/renderer.cpp:992-1054             -> k_tm_histogram, k_tm_exposure, k_tonemap (tonemap.cuh)
 // One path slot per pixel; samples of a pixel within a frame run back to back in the same slot
 // (path regeneration) because the reference continues ONE rng stream across a pixel's samples.
 #include <cuda_runtime.h>
